@@ -1,0 +1,418 @@
+"""Generate the golden fixtures in this directory by running the UNMODIFIED reference.
+
+Usage (authoring container only - the GPU box has no /root/reference):
+
+    python tests/golden/make_golden.py [/root/reference]
+
+For every hot-path function of SURVEY.md section 8a it instantiates the reference
+module from the reference checkout, feeds it seeded synthetic inputs on the CPU, and
+stores inputs + parameters + outputs as a small ``.npz``.  The oracle
+(``oracle/cnf_oracle.py``) and the CUDA path are both checked against these files.
+The only shim is an empty ``matplotlib`` module (absent here, imported but unused by
+``layers/flows/distributions.py:9``).
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+REF = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def _stub_matplotlib():
+    for name in ("matplotlib", "matplotlib.pyplot", "matplotlib.colors"):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules["matplotlib.colors"].hsv_to_rgb = lambda x: x
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    sys.modules["matplotlib"].colors = sys.modules["matplotlib.colors"]
+
+
+_stub_matplotlib()
+sys.path.insert(0, REF)
+
+from layers.flows.coupling_layer import CouplingLayer                                # noqa: E402
+from layers.flows.mixture_cdf_layer import MixtureCDFCoupling                        # noqa: E402
+from layers.flows.activation_normalization import ActNormFlow, ExtActNormFlow        # noqa: E402
+from layers.flows.permutation_layers import InvertibleConv                           # noqa: E402
+from layers.flows.distributions import LogisticDistribution                          # noqa: E402
+from layers.flows.autoregressive_coupling import AutoregressiveMixtureCDFCoupling    # noqa: E402
+from layers.flows.flow_model import FlowModel                                        # noqa: E402
+from layers.categorical_encoding.linear_encoding import LinearCategoricalEncoding    # noqa: E402
+from layers.networks.help_layers import SimpleLinearLayer                            # noqa: E402
+
+
+def npy(t):
+    return t.detach().cpu().numpy() if isinstance(t, torch.Tensor) else np.asarray(t)
+
+
+def save(name, **arrays):
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **{k: npy(v) for k, v in arrays.items()})
+    print("wrote %-34s %7.1f KiB" % (name + ".npz", os.path.getsize(path) / 1024))
+
+
+class _Recorder(nn.Module):
+    """Black-box coupling net that returns a preset tensor (so nn_out is an explicit input)."""
+
+    def __init__(self, out):
+        super().__init__()
+        self.out = out
+
+    def forward(self, x, **kwargs):
+        return self.out
+
+
+def lengths_to_pad(length, S):
+    return (torch.arange(S).view(1, S) < length.view(-1, 1)).float().unsqueeze(-1)
+
+
+# ---------------------------------------------------------------------------
+def gold_mixcdf(name, B, S, C, K, *, seed, nn_std=0.5, sf_std=0.0, chess=False, flip=False,
+                padded=False, reg_max=-1.0, reg_factor=1.0, training=True, ratio=0.5, z_std=1.0):
+    g = torch.Generator().manual_seed(seed)
+    z = torch.randn(B, S, C, generator=g) * z_std
+    nn_out = torch.randn(B, S, C * (2 + 3 * K), generator=g) * nn_std
+    mask = CouplingLayer.create_chess_mask() if chess else CouplingLayer.create_channel_mask(C, ratio=ratio)
+    if flip:
+        mask = 1 - mask
+    layer = MixtureCDFCoupling(c_in=C, mask=mask, model_func=lambda c_out: _Recorder(nn_out),
+                               num_mixtures=K, regularizer_max=reg_max, regularizer_factor=reg_factor)
+    layer.scaling_factor.data = torch.randn(C, generator=g) * sf_std
+    layer.mixture_scaling_factor.data = torch.randn(C, K, generator=g) * sf_std
+    layer.train(training)
+    kw = {}
+    length = torch.full((B,), S, dtype=torch.long)
+    if padded:
+        length = torch.randint(max(1, S // 3), S + 1, (B,), generator=g)
+        length[0] = S
+        kw["channel_padding_mask"] = lengths_to_pad(length, S)
+        z = z * kw["channel_padding_mask"]
+    with torch.no_grad():
+        z_fwd, ldj_fwd, det = layer(z, reverse=False, **kw)
+        z_rev, ldj_rev, _ = layer(z_fwd, reverse=True, **kw)
+        # reverse pass on an independent latent as well (sampling direction)
+        z_lat = torch.randn(B, S, C, generator=g) * 1.5
+        if padded:
+            z_lat = z_lat * kw["channel_padding_mask"]
+        z_smp, ldj_smp, _ = layer(z_lat, reverse=True, **kw)
+    save(name, z=z, nn_out=nn_out, mask=mask, K=K, sf=layer.scaling_factor.data,
+         msf=layer.mixture_scaling_factor.data, length=length, padded=int(padded),
+         reg_max=reg_max, reg_factor=reg_factor, training=int(training),
+         z_fwd=z_fwd, ldj_fwd=ldj_fwd, reg_ldj=det["regularizer_ldj"],
+         z_rev=z_rev, ldj_rev=ldj_rev, z_lat=z_lat, z_smp=z_smp, ldj_smp=ldj_smp)
+
+
+def gold_mixcdf_tails(name, seed):
+    """Extreme inputs: far tails of every component, sharp and wide components (exercises the
+    clamps at mixture_cdf_layer.py:197-198 and the float64 round-off region near CDF -> 1)."""
+    g = torch.Generator().manual_seed(seed)
+    B, S, C, K = 2, 24, 4, 4
+    z = torch.randn(B, S, C, generator=g) * 12.0
+    z[0, :6] = torch.tensor([60.0, -60.0, 35.0, -35.0])
+    z[1, :4] = torch.tensor([140.0, -140.0, 20.0, -20.0])
+    nn_out = torch.randn(B, S, C * (2 + 3 * K), generator=g) * 2.0
+    mask = CouplingLayer.create_channel_mask(C)
+    layer = MixtureCDFCoupling(c_in=C, mask=mask, model_func=lambda c_out: _Recorder(nn_out), num_mixtures=K)
+    layer.scaling_factor.data = torch.tensor([0.5, -0.5, 1.0, 0.0])
+    layer.mixture_scaling_factor.data = torch.randn(C, K, generator=g) * 0.8
+    layer.eval()
+    with torch.no_grad():
+        z_fwd, ldj_fwd, det = layer(z, reverse=False)
+    save(name, z=z, nn_out=nn_out, mask=mask, K=K, sf=layer.scaling_factor.data,
+         msf=layer.mixture_scaling_factor.data, length=torch.full((B,), S), padded=0,
+         reg_max=-1.0, reg_factor=1.0, training=0, z_fwd=z_fwd, ldj_fwd=ldj_fwd,
+         reg_ldj=det["regularizer_ldj"])
+
+
+def gold_mixcdf_selftest():
+    """The reference's own __main__ smoke block (mixture_cdf_layer.py:279-302)."""
+    torch.manual_seed(42)
+    B, S, C, K, H = 8, 16, 4, 10, 128
+    captured = {}
+
+    def model_func(c_out):
+        net = nn.Sequential(nn.Linear(C, H), nn.ReLU(), nn.Linear(H, c_out))
+        net.register_forward_hook(lambda m, i, o: captured.__setitem__("nn_out", o.detach().clone()))
+        return net
+
+    mask = CouplingLayer.create_channel_mask(C)
+    layer = MixtureCDFCoupling(c_in=C, mask=mask, model_func=model_func, block_type="Linear net", num_mixtures=K)
+    x = torch.randn(size=(B, S, C))
+    with torch.no_grad():
+        z_fwd, ldj_fwd, _ = layer(z=x, reverse=False)
+        nn_fwd = captured["nn_out"]
+        z_rev, ldj_rev, _ = layer(z=z_fwd, reverse=True)
+        nn_rev = captured["nn_out"]
+    print("   reference self-test: max reconstruction err %.3e, max ldj err %.3e"
+          % ((x - z_rev).abs().max(), (ldj_fwd + ldj_rev).abs().max()))
+    save("mixcdf_selftest", z=x, nn_out=nn_fwd, nn_out_rev=nn_rev, mask=mask, K=K,
+         sf=layer.scaling_factor.data, msf=layer.mixture_scaling_factor.data,
+         z_fwd=z_fwd, ldj_fwd=ldj_fwd, z_rev=z_rev, ldj_rev=ldj_rev)
+
+
+def gold_autoregressive(seed):
+    g = torch.Generator().manual_seed(seed)
+    B, S, C, K = 3, 20, 3, 51
+    z = torch.randn(B, S, C, generator=g)
+    nn_out = torch.randn(B, S, C * (2 + 3 * K), generator=g) * 0.7
+    layer = AutoregressiveMixtureCDFCoupling(c_in=C, model_func=lambda c_out: _Recorder(nn_out), num_mixtures=K)
+    layer.scaling_factor.data = torch.randn(C, generator=g) * 0.2
+    layer.mixture_scaling_factor.data = torch.randn(C, K, generator=g) * 0.2
+    ldj0 = torch.randn(B, generator=g)
+    length = torch.tensor([20, 13, 7])
+    pad = lengths_to_pad(length, S)
+    with torch.no_grad():
+        z_out, ldj = layer(z, ldj=ldj0.clone(), channel_padding_mask=pad)
+    save("autoregressive_mixcdf", z=z, nn_out=nn_out, K=K, sf=layer.scaling_factor.data,
+         msf=layer.mixture_scaling_factor.data, ldj_in=ldj0, pad=pad, z_out=z_out, ldj_out=ldj)
+
+
+def gold_affine(seed):
+    g = torch.Generator().manual_seed(seed)
+    B, S, C = 5, 9, 6
+    z = torch.randn(B, S, C, generator=g)
+    nn_out = torch.randn(B, S, 2 * C, generator=g)
+    mask = CouplingLayer.create_channel_mask(C)
+    layer = CouplingLayer(c_in=C, mask=mask, model_func=lambda c_out: _Recorder(nn_out))
+    layer.scaling_factor.data = torch.randn(C, generator=g) * 0.5
+    ldj0 = torch.randn(B, generator=g)
+    with torch.no_grad():
+        z_fwd, ldj_fwd = layer(z, ldj=ldj0.clone())
+        z_rev, ldj_rev = layer(z_fwd, ldj=ldj_fwd.clone(), reverse=True)
+    save("affine_coupling", z=z, nn_out=nn_out, mask=mask, sf=layer.scaling_factor.data, ldj_in=ldj0,
+         z_fwd=z_fwd, ldj_fwd=ldj_fwd, z_rev=z_rev, ldj_rev=ldj_rev)
+    # token-wise layout used inside the linear-flow encoding: [B*S, 1, D]
+    z = torch.randn(40, 1, 4, generator=g)
+    nn_out = torch.randn(40, 1, 8, generator=g)
+    mask = CouplingLayer.create_channel_mask(4)
+    layer = CouplingLayer(c_in=4, mask=mask, model_func=lambda c_out: _Recorder(nn_out))
+    with torch.no_grad():
+        z_fwd, ldj_fwd = layer(z)
+        z_rev, ldj_rev = layer(z_fwd, ldj=ldj_fwd.clone(), reverse=True)
+    save("affine_coupling_tokens", z=z, nn_out=nn_out, mask=mask, sf=layer.scaling_factor.data,
+         ldj_in=torch.zeros(40), z_fwd=z_fwd, ldj_fwd=ldj_fwd, z_rev=z_rev, ldj_rev=ldj_rev)
+
+
+def gold_actnorm(seed):
+    g = torch.Generator().manual_seed(seed)
+    B, S, C = 6, 11, 5
+    z = torch.randn(B, S, C, generator=g) * 2 + 0.7
+    length = torch.tensor([11, 3, 7, 11, 1, 9])
+    pad = lengths_to_pad(length, S)
+    layer = ActNormFlow(C)
+    layer.bias.data = torch.randn(1, 1, C, generator=g)
+    layer.scales.data = torch.randn(1, 1, C, generator=g) * 0.4
+    out = {}
+    with torch.no_grad():
+        for tag, kw in (("plain", {}), ("len", {"length": length, "channel_padding_mask": pad}),
+                        ("padonly", {"channel_padding_mask": pad})):
+            ldj0 = torch.randn(B, generator=g)
+            zf, lf = layer(z, ldj=ldj0.clone(), **kw)
+            zr, lr = layer(zf, ldj=lf.clone(), reverse=True, **kw)
+            out.update({"ldj_in_" + tag: ldj0, "z_fwd_" + tag: zf, "ldj_fwd_" + tag: lf,
+                        "z_rev_" + tag: zr, "ldj_rev_" + tag: lr})
+        init = ActNormFlow(C)
+        _quiet(init.data_init_forward, z, channel_padding_mask=pad)
+        init2 = ActNormFlow(C)
+        _quiet(init2.data_init_forward, z)
+    save("actnorm", z=z, length=length, pad=pad, bias=layer.bias.data, scales=layer.scales.data,
+         init_bias_pad=init.bias.data, init_scales_pad=init.scales.data,
+         init_bias=init2.bias.data, init_scales=init2.scales.data, **out)
+
+
+def _quiet(fn, *a, **kw):
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        return fn(*a, **kw)
+
+
+def gold_ext_actnorm(seed):
+    g = torch.Generator().manual_seed(seed)
+    N, D, E = 30, 4, 16
+    z = torch.randn(N, 1, D, generator=g)
+    ext = torch.randn(N, 1, E, generator=g)
+    net = SimpleLinearLayer(c_in=E, c_out=2 * D, data_init=True)
+    net.layer.weight.data = torch.randn(2 * D, E, generator=g) * 0.3
+    net.layer.bias.data = torch.randn(2 * D, generator=g) * 0.3
+    layer = ExtActNormFlow(c_in=D, net=net)
+    pad = (torch.rand(N, 1, 1, generator=g) > 0.3).float()
+    ldj0 = torch.randn(N, generator=g)
+    with torch.no_grad():
+        zf, lf = layer(z, ldj0.clone(), ext_input=ext, channel_padding_mask=pad)
+        zr, lr = layer(zf, lf.clone(), reverse=True, ext_input=ext, channel_padding_mask=pad)
+        zf2, lf2 = layer(z, ldj0.clone(), ext_input=ext)
+    save("ext_actnorm", z=z, ext=ext, weight=net.layer.weight.data, bias=net.layer.bias.data, pad=pad,
+         ldj_in=ldj0, z_fwd=zf, ldj_fwd=lf, z_rev=zr, ldj_rev=lr, z_fwd_nopad=zf2, ldj_fwd_nopad=lf2)
+
+
+def gold_invconv(seed):
+    out = {}
+    for C in (2, 6, 16):
+        np.random.seed(seed + C)
+        g = torch.Generator().manual_seed(seed + C)
+        layer = InvertibleConv(c_in=C)
+        # perturb away from the orthogonal init so that log_s != 0
+        layer.l.data += torch.randn(C, C, generator=g) * 0.1
+        layer.u.data += torch.randn(C, C, generator=g) * 0.1
+        layer.log_s.data += torch.randn(C, generator=g) * 0.2
+        B, S = 4, 7
+        z = torch.randn(B, S, C, generator=g)
+        length = torch.tensor([7, 2, 5, 7])
+        pad = lengths_to_pad(length, S)
+        ldj0 = torch.randn(B, generator=g)
+        layer.train()
+        with torch.no_grad():
+            w, sldj = layer._get_weight("cpu", inverse=False)
+            w_inv, _ = layer._get_weight("cpu", inverse=True)
+            zf, lf = layer(z, ldj=ldj0.clone(), length=length, channel_padding_mask=pad)
+            zr, lr = layer(zf, ldj=lf.clone(), reverse=True, length=length, channel_padding_mask=pad)
+            zf2, lf2 = layer(z, ldj=ldj0.clone())
+        t = "_c%d" % C
+        out.update({"p" + t: layer.p, "sign_s" + t: layer.sign_s, "l" + t: layer.l.data, "u" + t: layer.u.data,
+                    "log_s" + t: layer.log_s.data, "w" + t: w, "w_inv" + t: w_inv, "sldj" + t: sldj,
+                    "z" + t: z, "length" + t: length, "pad" + t: pad, "ldj_in" + t: ldj0,
+                    "z_fwd" + t: zf, "ldj_fwd" + t: lf, "z_rev" + t: zr, "ldj_rev" + t: lr,
+                    "z_fwd_plain" + t: zf2, "ldj_fwd_plain" + t: lf2})
+    save("invconv", **out)
+
+
+def gold_logistic(seed):
+    g = torch.Generator().manual_seed(seed)
+    dist = LogisticDistribution(mu=0.0, sigma=1.0)
+    u = torch.rand(64, 1, 5, generator=g)
+    u[0, 0, 0], u[1, 0, 0] = 0.0, 1.0 - 2 ** -24
+    rec = {}
+    orig = dist.distribution.sample
+    dist.distribution.sample = lambda sample_shape=torch.Size(): u
+    x = dist.sample(shape=(64, 1, 5))
+    dist.distribution.sample = orig
+    xs = torch.cat([x.flatten(), torch.tensor([0.0, 30.0, -30.0, 1e-3, 8.0])])
+    save("logistic", u=u, x=x, xs=xs, log_prob=dist.log_prob(xs), **rec)
+
+
+def gold_encoding(name, B, S, V, D, *, seed, padded=False, beta=1.0, prior_std=0.0, training=False):
+    g = torch.Generator().manual_seed(seed)
+    torch.manual_seed(seed)
+    prior = torch.randn(V, generator=g) * prior_std if prior_std > 0 else None
+    enc = LinearCategoricalEncoding(num_dimensions=D, flow_config={"num_flows": 0}, vocab_size=V,
+                                    category_prior=prior)
+    lin = enc.flow_layers[0].pred_net.layer
+    lin.weight.data = torch.randn(2 * D, 64, generator=g) * 0.25     # non-zero scale rows
+    lin.bias.data = torch.randn(2 * D, generator=g) * 0.3
+    enc.train(training)
+    x = torch.randint(0, V, (B, S), generator=g)
+    kw = {}
+    pad = torch.ones(B, S, 1)
+    if padded:
+        length = torch.randint(1, S + 1, (B,), generator=g)
+        pad = lengths_to_pad(length, S)
+        kw["channel_padding_mask"] = pad
+    noise = {}
+    orig = enc.prior_distribution.distribution.sample
+
+    def rec_sample(sample_shape=torch.Size()):
+        noise["u"] = torch.rand(sample_shape, generator=g)
+        return noise["u"]
+
+    enc.prior_distribution.distribution.sample = rec_sample
+    ldj0 = torch.randn(B, generator=g)
+    with torch.no_grad():
+        z, ldj, _ = enc(x, ldj=ldj0.clone(), beta=beta, **kw)
+        enc.prior_distribution.distribution.sample = orig
+        x_dec, _, _ = enc(z, reverse=True, **kw)
+        z_rand = torch.randn(B, S, D, generator=g)
+        x_dec_rand, _, _ = enc(z_rand, reverse=True)
+    save(name, x=x, u=noise["u"], V=V, D=D, beta=beta, pad=pad, padded=int(padded), ldj_in=ldj0,
+         embed=enc.embed_layer.weight.data, weight=lin.weight.data, bias=lin.bias.data,
+         category_prior=enc.category_prior, z=z, ldj=ldj, x_dec=x_dec, z_rand=z_rand, x_dec_rand=x_dec_rand)
+
+
+def gold_lm_flow(seed):
+    """Small version of BASELINE config 2: encode -> 3 x [ActNorm, InvConv, MixtureCDF] -> prior,
+    run through the reference's FlowModel container (flow_model.py:25-53)."""
+    g = torch.Generator().manual_seed(seed)
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+    B, S, V, D, K, NB, H = 4, 24, 51, 16, 8, 3, 32
+    enc = LinearCategoricalEncoding(num_dimensions=D, flow_config={"num_flows": 0}, vocab_size=V)
+    lin = enc.flow_layers[0].pred_net.layer
+    lin.weight.data = torch.randn(2 * D, 64, generator=g) * 0.2
+    lin.bias.data = torch.randn(2 * D, generator=g) * 0.3
+    captured = []
+
+    def model_func(c_out):
+        net = nn.Sequential(nn.Linear(D, H), nn.GELU(), nn.Linear(H, c_out))
+        net.register_forward_hook(lambda m, i, o: captured.append(o.detach().clone()))
+        return net
+
+    layers = [enc]
+    mask = CouplingLayer.create_channel_mask(D)
+    for i in range(NB):
+        an, ic = ActNormFlow(D), InvertibleConv(D)
+        an.bias.data = torch.randn(1, 1, D, generator=g) * 0.2
+        an.scales.data = torch.randn(1, 1, D, generator=g) * 0.2
+        ic.log_s.data += torch.randn(D, generator=g) * 0.1
+        cp = MixtureCDFCoupling(c_in=D, mask=mask if i % 2 == 0 else 1 - mask, model_func=model_func, num_mixtures=K)
+        cp.scaling_factor.data = torch.randn(D, generator=g) * 0.2
+        cp.mixture_scaling_factor.data = torch.randn(D, K, generator=g) * 0.2
+        layers += [an, ic, cp]
+    model = _quiet(FlowModel, layers)
+    model.eval()
+    x = torch.randint(0, V, (B, S), generator=g)
+    length = torch.tensor([24, 17, 9, 24])
+    pad = lengths_to_pad(length, S)
+    noise = {}
+
+    def rec_sample(sample_shape=torch.Size()):
+        noise["u"] = torch.rand(sample_shape, generator=g)
+        return noise["u"]
+
+    enc.prior_distribution.distribution.sample = rec_sample
+    with torch.no_grad():
+        z, ldj = model(x, reverse=False, length=length, channel_padding_mask=pad)
+        logp = (LogisticDistribution().log_prob(z) * pad).sum(dim=[1, 2])
+    arrays = dict(x=x, u=noise["u"], length=length, pad=pad, V=V, D=D, K=K, NB=NB,
+                  embed=enc.embed_layer.weight.data, enc_weight=lin.weight.data, enc_bias=lin.bias.data,
+                  category_prior=enc.category_prior, z=z, ldj=ldj, logp=logp)
+    for i in range(NB):
+        an, ic, cp = layers[1 + 3 * i: 4 + 3 * i]
+        w, sldj = ic._get_weight("cpu")
+        arrays.update({"an_bias%d" % i: an.bias.data, "an_scales%d" % i: an.scales.data,
+                       "ic_w%d" % i: w, "ic_sldj%d" % i: sldj, "mask%d" % i: cp.mask,
+                       "sf%d" % i: cp.scaling_factor.data, "msf%d" % i: cp.mixture_scaling_factor.data,
+                       "nn_out%d" % i: captured[i],
+                       "net_w0_%d" % i: cp.nn[0].weight.data, "net_b0_%d" % i: cp.nn[0].bias.data,
+                       "net_w1_%d" % i: cp.nn[2].weight.data, "net_b1_%d" % i: cp.nn[2].bias.data})
+    save("lm_flow_small", **arrays)
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(4)
+    gold_mixcdf_selftest()
+    gold_mixcdf("mixcdf_lm_small", 3, 32, 16, 8, seed=1)
+    gold_mixcdf("mixcdf_lm_padded_sf", 4, 40, 16, 8, seed=2, padded=True, sf_std=0.3)
+    gold_mixcdf("mixcdf_stress", 2, 16, 16, 8, seed=3, nn_std=2.0, z_std=2.0)
+    gold_mixcdf("mixcdf_mol_nodes", 5, 38, 6, 16, seed=4, padded=True, sf_std=0.2, reg_max=3.5, reg_factor=2.0)
+    gold_mixcdf("mixcdf_mol_edges", 3, 71, 2, 8, seed=5, padded=True, reg_max=3.5, training=False)
+    gold_mixcdf("mixcdf_chess", 4, 9, 1, 4, seed=6, chess=True, padded=True)
+    gold_mixcdf("mixcdf_chess_flip", 4, 10, 1, 4, seed=7, chess=True, flip=True)
+    gold_mixcdf("mixcdf_flip_k10", 3, 6, 4, 10, seed=8, flip=True, sf_std=0.4)
+    gold_mixcdf("mixcdf_ratio_k3", 2, 5, 5, 3, seed=9, ratio=0.3, z_std=3.0)
+    gold_mixcdf_tails("mixcdf_tails", seed=10)
+    gold_autoregressive(seed=11)
+    gold_affine(seed=12)
+    gold_actnorm(seed=13)
+    gold_ext_actnorm(seed=14)
+    gold_invconv(seed=15)
+    gold_logistic(seed=16)
+    gold_encoding("encode_lm", 3, 20, 51, 16, seed=17)
+    gold_encoding("encode_mol_nodes", 4, 38, 9, 6, seed=18, padded=True, beta=0.7, prior_std=1.0)
+    gold_encoding("encode_mol_edges", 3, 50, 3, 2, seed=19, padded=True, prior_std=0.5, training=True)
+    gold_encoding("encode_virtual", 2, 12, 1, 2, seed=20)
+    gold_lm_flow(seed=21)

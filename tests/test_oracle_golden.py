@@ -1,0 +1,168 @@
+"""Pin the oracle (oracle/cnf_oracle.py) against outputs of the unmodified reference
+(tests/golden/*.npz, produced by tests/golden/make_golden.py).  CPU only."""
+import pytest
+import torch
+
+from conftest import assert_close, load_golden
+from oracle import cnf_oracle as O
+
+MIXCDF_CASES = ["mixcdf_lm_small", "mixcdf_lm_padded_sf", "mixcdf_stress", "mixcdf_mol_nodes",
+                "mixcdf_mol_edges", "mixcdf_chess", "mixcdf_chess_flip", "mixcdf_flip_k10",
+                "mixcdf_ratio_k3"]
+TIGHT = dict(rtol=2e-6, atol=2e-6)
+
+
+def _pad(g):
+    if not g.padded:
+        return None
+    S = g.z.shape[1]
+    return (torch.arange(S).view(1, S) < g.length.view(-1, 1)).float().unsqueeze(-1)
+
+
+@pytest.mark.parametrize("name", MIXCDF_CASES)
+def test_mixcdf_forward_and_inverse(name):
+    g = load_golden(name)
+    m = O.expand_mask(g.mask, g.z)
+    kw = dict(pad=_pad(g), reg_max=g.reg_max, reg_factor=g.reg_factor, training=bool(g.training))
+    z, ldj, reg = O.mixcdf_coupling(g.z, g.nn_out, m, g.K, g.sf, g.msf, **kw)
+    assert_close(z, g.z_fwd, what="z_fwd", **TIGHT)
+    assert_close(ldj, g.ldj_fwd, what="ldj_fwd", **TIGHT)
+    assert_close(reg, g.reg_ldj, what="reg_ldj", **TIGHT)
+    zr, lr, _ = O.mixcdf_coupling(g.z_fwd, g.nn_out, m, g.K, g.sf, g.msf, reverse=True, **kw)
+    assert_close(zr, g.z_rev, what="z_rev", **TIGHT)
+    assert_close(lr, g.ldj_rev, what="ldj_rev", **TIGHT)
+    zs, ls, _ = O.mixcdf_coupling(g.z_lat, g.nn_out, m, g.K, g.sf, g.msf, reverse=True, **kw)
+    assert_close(zs, g.z_smp, what="z_smp", **TIGHT)
+    assert_close(ls, g.ldj_smp, what="ldj_smp", **TIGHT)
+
+
+def test_mixcdf_tails():
+    g = load_golden("mixcdf_tails")
+    m = O.expand_mask(g.mask, g.z)
+    z, ldj, _ = O.mixcdf_coupling(g.z, g.nn_out, m, g.K, g.sf, g.msf, training=False)
+    assert_close(z, g.z_fwd, what="z", **TIGHT)
+    assert_close(ldj, g.ldj_fwd, what="ldj", **TIGHT)
+
+
+def test_reference_selftest_case():
+    """The reference's own __main__ block: forward then reverse reconstructs to 1.2e-7."""
+    g = load_golden("mixcdf_selftest")
+    m = O.expand_mask(g.mask, g.z)
+    z, ldj, _ = O.mixcdf_coupling(g.z, g.nn_out, m, g.K, g.sf, g.msf)
+    assert_close(z, g.z_fwd, **TIGHT)
+    assert_close(ldj, g.ldj_fwd, **TIGHT)
+    zr, lr, _ = O.mixcdf_coupling(z, g.nn_out_rev, m, g.K, g.sf, g.msf, reverse=True)
+    assert_close(zr, g.z_rev, **TIGHT)
+    assert (zr - g.z).abs().max() < 5e-7
+    assert (ldj + lr).abs().max() < 1e-5
+
+
+def test_autoregressive():
+    g = load_golden("autoregressive_mixcdf")
+    z, ldj = O.autoregressive_mixcdf(g.z, g.nn_out, g.K, g.sf, g.msf, ldj=g.ldj_in, pad=g.pad)
+    assert_close(z, g.z_out, **TIGHT)
+    assert_close(ldj, g.ldj_out, **TIGHT)
+
+
+@pytest.mark.parametrize("name", ["affine_coupling", "affine_coupling_tokens"])
+def test_affine(name):
+    g = load_golden(name)
+    m = O.expand_mask(g.mask, g.z)
+    z, ldj = O.affine_coupling(g.z, g.nn_out, m, g.sf, ldj=g.ldj_in)
+    assert_close(z, g.z_fwd, **TIGHT)
+    assert_close(ldj, g.ldj_fwd, **TIGHT)
+    zr, lr = O.affine_coupling(g.z_fwd, g.nn_out, m, g.sf, ldj=g.ldj_fwd, reverse=True)
+    assert_close(zr, g.z_rev, **TIGHT)
+    assert_close(lr, g.ldj_rev, **TIGHT)
+
+
+def test_actnorm():
+    g = load_golden("actnorm")
+    for tag, kw in (("plain", {}), ("len", dict(length=g.length, pad=g.pad)), ("padonly", dict(pad=g.pad))):
+        z, ldj = O.actnorm(g.z, g.bias, g.scales, ldj=g["ldj_in_" + tag], **kw)
+        assert_close(z, g["z_fwd_" + tag], **TIGHT)
+        assert_close(ldj, g["ldj_fwd_" + tag], **TIGHT)
+        zr, lr = O.actnorm(g["z_fwd_" + tag], g.bias, g.scales, ldj=g["ldj_fwd_" + tag], reverse=True, **kw)
+        assert_close(zr, g["z_rev_" + tag], **TIGHT)
+        assert_close(lr, g["ldj_rev_" + tag], **TIGHT)
+    b, s = O.actnorm_data_init(g.z, g.pad)
+    assert_close(b, g.init_bias_pad, **TIGHT)
+    assert_close(s, g.init_scales_pad, **TIGHT)
+    b, s = O.actnorm_data_init(g.z)
+    assert_close(b, g.init_bias, **TIGHT)
+    assert_close(s, g.init_scales, **TIGHT)
+
+
+def test_ext_actnorm():
+    g = load_golden("ext_actnorm")
+    out = torch.nn.functional.linear(g.ext, g.weight, g.bias)
+    b, s = out.chunk(2, dim=2)
+    z, ldj = O.ext_actnorm(g.z, b, s, ldj=g.ldj_in, pad=g.pad)
+    assert_close(z, g.z_fwd, **TIGHT)
+    assert_close(ldj, g.ldj_fwd, **TIGHT)
+    zr, lr = O.ext_actnorm(g.z_fwd, b, s, ldj=g.ldj_fwd, reverse=True, pad=g.pad)
+    assert_close(zr, g.z_rev, **TIGHT)
+    assert_close(lr, g.ldj_rev, **TIGHT)
+    z, ldj = O.ext_actnorm(g.z, b, s, ldj=g.ldj_in)
+    assert_close(z, g.z_fwd_nopad, **TIGHT)
+    assert_close(ldj, g.ldj_fwd_nopad, **TIGHT)
+
+
+@pytest.mark.parametrize("C", [2, 6, 16])
+def test_invconv(C):
+    g = load_golden("invconv")
+    t = "_c%d" % C
+    w, sldj = O.invconv_weight(g["p" + t], g["l" + t], g["log_s" + t], g["u" + t], g["sign_s" + t])
+    assert_close(w, g["w" + t], **TIGHT)
+    assert_close(sldj, g["sldj" + t], **TIGHT)
+    w_inv = O.invconv_inverse(w)
+    assert_close(w_inv, g["w_inv" + t], **TIGHT)
+    kw = dict(length=g["length" + t], pad=g["pad" + t])
+    z, ldj = O.invconv(g["z" + t], w, sldj, ldj=g["ldj_in" + t], **kw)
+    assert_close(z, g["z_fwd" + t], **TIGHT)
+    assert_close(ldj, g["ldj_fwd" + t], **TIGHT)
+    zr, lr = O.invconv(g["z_fwd" + t], w_inv, sldj, ldj=g["ldj_fwd" + t], reverse=True, **kw)
+    assert_close(zr, g["z_rev" + t], **TIGHT)
+    assert_close(lr, g["ldj_rev" + t], **TIGHT)
+    z, ldj = O.invconv(g["z" + t], w, sldj, ldj=g["ldj_in" + t])
+    assert_close(z, g["z_fwd_plain" + t], **TIGHT)
+    assert_close(ldj, g["ldj_fwd_plain" + t], **TIGHT)
+
+
+def test_logistic():
+    g = load_golden("logistic")
+    assert_close(O.logistic_from_uniform(g.u), g.x, **TIGHT)
+    assert_close(O.logistic_log_prob(g.xs), g.log_prob, **TIGHT)
+
+
+@pytest.mark.parametrize("name", ["encode_lm", "encode_mol_nodes", "encode_mol_edges", "encode_virtual"])
+def test_categ_encode_decode(name):
+    g = load_golden(name)
+    table = O.categ_table(g.embed, g.weight, g.bias)
+    pad = g.pad if g.padded else None
+    z, ldj, _ = O.categ_encode(g.x, g.u, table, g.category_prior, beta=g.beta, pad=pad)
+    assert_close(z, g.z, **TIGHT)
+    assert_close(g.ldj_in + ldj, g.ldj, rtol=1e-5, atol=1e-4)
+    assert torch.equal(O.categ_decode(g.z, table, g.category_prior), g.x_dec)
+    assert torch.equal(O.categ_decode(g.z_rand, table, g.category_prior), g.x_dec_rand)
+
+
+def test_lm_flow_composition():
+    g = load_golden("lm_flow_small")
+    enc = dict(table=O.categ_table(g.embed, g.enc_weight, g.enc_bias), prior=g.category_prior)
+    blocks = [dict(bias=g["an_bias%d" % i], scales=g["an_scales%d" % i], weight=g["ic_w%d" % i],
+                   sldj=g["ic_sldj%d" % i], nn_out=g["nn_out%d" % i], mask=g["mask%d" % i], K=g.K,
+                   sf=g["sf%d" % i], msf=g["msf%d" % i]) for i in range(g.NB)]
+    z, ldj, logp = O.lm_flow_forward(g.x, g.u, enc, blocks, pad=g.pad, length=g.length)
+    assert_close(z, g.z, rtol=1e-5, atol=1e-5)
+    assert_close(ldj, g.ldj, rtol=1e-5, atol=1e-4)
+    assert_close(logp, g.logp, rtol=1e-5, atol=1e-4)
+    # and with the stand-in coupling nets evaluated instead of replaying nn_out
+    for i, b in enumerate(blocks):
+        w0, b0, w1, b1 = (g["net_%s_%d" % (k, i)] for k in ("w0", "b0", "w1", "b1"))
+        b.pop("nn_out")
+        b["nn_fn"] = (lambda w0, b0, w1, b1: lambda x: torch.nn.functional.linear(
+            torch.nn.functional.gelu(torch.nn.functional.linear(x, w0, b0)), w1, b1))(w0, b0, w1, b1)
+    z2, ldj2, _ = O.lm_flow_forward(g.x, g.u, enc, blocks, pad=g.pad, length=g.length)
+    assert_close(z2, g.z, rtol=1e-4, atol=1e-4)
+    assert_close(ldj2, g.ldj, rtol=1e-4, atol=1e-3)
