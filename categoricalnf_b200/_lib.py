@@ -1,0 +1,181 @@
+"""ctypes binding of the C ABI declared in ``include/cnf_b200.h``.
+
+The shared library is built in-tree by :mod:`categoricalnf_b200.build` (``libcnf_b200.so`` next to
+this file).  There is deliberately no fallback: if the library is missing or a symbol does not
+resolve, importing the compute ops raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG, "libcnf_b200.so")
+
+c_f32p = C.POINTER(C.c_float)
+c_i64p = C.POINTER(C.c_int64)
+c_u32p = C.POINTER(C.c_uint32)
+c_f64p = C.POINTER(C.c_double)
+vp = C.c_void_p
+
+
+class Mask(C.Structure):
+    _fields_ = [("cond_c_host", vp), ("cond_s_host", vp), ("s_period", C.c_int32)]
+
+
+class MixcdfArgs(C.Structure):
+    _fields_ = [
+        ("B", C.c_int64), ("S", C.c_int64), ("C", C.c_int32), ("K", C.c_int32),
+        ("z", vp), ("nn_out", vp), ("mask", Mask), ("pad", vp),
+        ("scaling_factor", vp), ("mixture_scaling_factor", vp),
+        ("reg_max", C.c_float), ("reg_factor", C.c_float), ("training", C.c_int32), ("accumulate", C.c_int32),
+        ("params_prebounded", C.c_int32),
+        ("z_out", vp), ("ldj", vp), ("reg_ldj", vp), ("status", vp),
+        ("next_actnorm_bias", vp), ("next_actnorm_scales", vp), ("next_conv_weight", vp),
+    ]
+
+
+class AffineArgs(C.Structure):
+    _fields_ = [
+        ("B", C.c_int64), ("S", C.c_int64), ("C", C.c_int32),
+        ("z", vp), ("nn_out", vp), ("mask", Mask), ("scaling_factor", vp), ("reverse", C.c_int32),
+        ("params_prebounded", C.c_int32),
+        ("z_out", vp), ("ldj", vp), ("status", vp),
+    ]
+
+
+class ActnormArgs(C.Structure):
+    _fields_ = [
+        ("B", C.c_int64), ("S", C.c_int64), ("C", C.c_int32),
+        ("z", vp), ("bias", vp), ("scales", vp), ("pad", vp), ("length", vp), ("reverse", C.c_int32),
+        ("z_out", vp), ("ldj", vp), ("status", vp),
+    ]
+
+
+class ExtActnormArgs(C.Structure):
+    _fields_ = [
+        ("B", C.c_int64), ("S", C.c_int64), ("C", C.c_int32),
+        ("z", vp), ("ext", vp), ("pad", vp), ("reverse", C.c_int32),
+        ("z_out", vp), ("ldj", vp), ("status", vp),
+    ]
+
+
+class ActnormInitArgs(C.Structure):
+    _fields_ = [
+        ("B", C.c_int64), ("S", C.c_int64), ("C", C.c_int32),
+        ("x", vp), ("pad", vp), ("workspace", vp), ("bias", vp), ("scales", vp),
+    ]
+
+
+class InvconvBuildArgs(C.Structure):
+    _fields_ = [
+        ("C", C.c_int32), ("p", vp), ("l", vp), ("u", vp), ("log_s", vp), ("sign_s", vp), ("weight", vp),
+        ("w_out", vp), ("w_inv_out", vp), ("sldj_out", vp),
+    ]
+
+
+class InvconvArgs(C.Structure):
+    _fields_ = [
+        ("B", C.c_int64), ("S", C.c_int64), ("C", C.c_int32),
+        ("z", vp), ("weight", vp), ("sldj", vp), ("pad", vp), ("length", vp), ("reverse", C.c_int32),
+        ("z_out", vp), ("ldj", vp), ("status", vp),
+    ]
+
+
+class CategEncodeArgs(C.Structure):
+    _fields_ = [
+        ("B", C.c_int64), ("S", C.c_int64), ("V", C.c_int32), ("D", C.c_int32),
+        ("tokens", vp), ("u_noise", vp), ("seed", C.c_uint64), ("offset", C.c_uint64),
+        ("table", vp), ("category_prior", vp), ("pad", vp), ("beta", C.c_float),
+        ("z_out", vp), ("ldj", vp), ("class_prob_log", vp), ("status", vp),
+    ]
+
+
+class CategDecodeArgs(C.Structure):
+    _fields_ = [
+        ("B", C.c_int64), ("S", C.c_int64), ("V", C.c_int32), ("D", C.c_int32),
+        ("z", vp), ("table", vp), ("category_prior", vp), ("tokens_out", vp),
+    ]
+
+
+class LogisticLogprobArgs(C.Structure):
+    _fields_ = [
+        ("B", C.c_int64), ("S", C.c_int64), ("C", C.c_int32),
+        ("x", vp), ("pad", vp), ("mu", C.c_float), ("sigma", C.c_float), ("accumulate", C.c_int32),
+        ("out", vp), ("elementwise", vp),
+    ]
+
+
+class LogisticSampleArgs(C.Structure):
+    _fields_ = [
+        ("n", C.c_int64), ("u_noise", vp), ("seed", C.c_uint64), ("offset", C.c_uint64),
+        ("mu", C.c_float), ("sigma", C.c_float), ("eps", C.c_float), ("x_out", vp),
+    ]
+
+
+class LdjAxpyArgs(C.Structure):
+    _fields_ = [
+        ("B", C.c_int64), ("alpha", C.c_float), ("alpha_dev", vp), ("x", vp), ("length", vp), ("y", vp),
+    ]
+
+
+# symbol -> argument struct; every entry point is `int f(const Args*, cnf_stream_t)`
+ENTRY_POINTS = {
+    "cnf_mixcdf_fwd": MixcdfArgs,
+    "cnf_mixcdf_inv": MixcdfArgs,
+    "cnf_affine_coupling": AffineArgs,
+    "cnf_actnorm": ActnormArgs,
+    "cnf_ext_actnorm": ExtActnormArgs,
+    "cnf_actnorm_data_init": ActnormInitArgs,
+    "cnf_invconv_build": InvconvBuildArgs,
+    "cnf_invconv_apply": InvconvArgs,
+    "cnf_categ_encode": CategEncodeArgs,
+    "cnf_categ_decode": CategDecodeArgs,
+    "cnf_logistic_logprob": LogisticLogprobArgs,
+    "cnf_logistic_sample": LogisticSampleArgs,
+    "cnf_ldj_axpy": LdjAxpyArgs,
+}
+PLAIN_SYMBOLS = ("cnf_last_error_string", "cnf_abi_version", "cnf_built_for_sm")
+
+ABI_VERSION = 1
+_lib = None
+
+
+class CnfError(RuntimeError):
+    """A C-ABI call returned a non-zero status."""
+
+    def __init__(self, fn, code, text):
+        super().__init__("%s failed with code %d: %s" % (fn, code, text))
+        self.fn, self.code, self.text = fn, code, text
+
+
+def load():
+    """Load ``libcnf_b200.so`` (once) and declare prototypes.  Raises if it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "categoricalnf_b200: %s is missing. Build it with `python -m categoricalnf_b200.build` "
+            "(needs nvcc); there is no CPU or PyTorch fallback for the hot path." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, struct in ENTRY_POINTS.items():
+        fn = getattr(lib, name)
+        fn.argtypes = [C.POINTER(struct), vp]
+        fn.restype = C.c_int
+    lib.cnf_last_error_string.restype = C.c_char_p
+    lib.cnf_last_error_string.argtypes = []
+    lib.cnf_abi_version.restype = C.c_int
+    lib.cnf_built_for_sm.restype = C.c_int
+    if lib.cnf_abi_version() != ABI_VERSION:
+        raise ImportError("libcnf_b200.so has ABI version %d, the Python binding expects %d - rebuild"
+                          % (lib.cnf_abi_version(), ABI_VERSION))
+    _lib = lib
+    return lib
+
+
+def call(name, args, stream):
+    lib = load()
+    rc = getattr(lib, name)(C.byref(args), vp(stream))
+    if rc != 0:
+        raise CnfError(name, rc, lib.cnf_last_error_string().decode("utf-8", "replace"))

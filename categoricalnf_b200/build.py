@@ -1,0 +1,80 @@
+"""Build the C-ABI CUDA library ``libcnf_b200.so`` in-tree for sm_100a.
+
+``python -m categoricalnf_b200.build [--force] [--verbose]``.  nvcc cross-compiles without a GPU.
+The library has no PyTorch dependency: it is plain CUDA behind ``include/cnf_b200.h``.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG)
+CSRC = os.path.join(PKG, "csrc")
+INCLUDE = os.path.join(ROOT, "include")
+OBJDIR = os.path.join(PKG, "build")
+LIB = os.path.join(PKG, "libcnf_b200.so")
+
+NVCC_FLAGS = [
+    "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",
+    "-I", INCLUDE, "-I", CSRC,
+]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found: the cnf_b200 CUDA library cannot be built")
+
+
+def sources():
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
+
+
+def _newest_header() -> float:
+    hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    hdrs += [os.path.join(INCLUDE, f) for f in os.listdir(INCLUDE)]
+    return max(os.path.getmtime(h) for h in hdrs)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    nvcc = _nvcc()
+    os.makedirs(OBJDIR, exist_ok=True)
+    hdr_time = _newest_header()
+    jobs = []
+    objs = []
+    for src in sources():
+        obj = os.path.join(OBJDIR, os.path.basename(src)[:-3] + ".o")
+        objs.append(obj)
+        stale = force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), hdr_time)
+        if stale:
+            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+            jobs.append((src, cmd))
+
+    def run(job):
+        src, cmd = job
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        return src, r
+
+    with ThreadPoolExecutor(max_workers=min(8, max(1, len(jobs)))) as ex:
+        for src, r in ex.map(run, jobs):
+            if verbose and r.stderr:
+                print(r.stderr, file=sys.stderr)
+            if r.returncode != 0:
+                raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))
+    if jobs or force or not os.path.exists(LIB):
+        cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+    return LIB
+
+
+if __name__ == "__main__":
+    path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
+    print(path)

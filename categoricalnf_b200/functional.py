@@ -1,0 +1,197 @@
+"""Autograd-aware functional layer between the drop-in modules and :mod:`categoricalnf_b200.ops`.
+
+Each function is one fused kernel launch in the forward direction.  Functions that sit on a
+training path are wrapped in ``torch.autograd.Function`` so that the reference's unchanged
+training loops (``loss.backward()``, general/train.py:148-152) differentiate through them with the
+hand-written backward kernels.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+
+
+def _needs_grad(*tensors) -> bool:
+    return torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors)
+
+
+def _no_backward(name):
+    raise NotImplementedError(
+        "categoricalnf_b200: the backward kernel of %s is not built yet; run this layer under "
+        "torch.no_grad() (evaluation / sampling) - there is deliberately no eager fallback" % name)
+
+
+# ----------------------------------------------------------------------------------------------
+# mixture-CDF coupling
+# ----------------------------------------------------------------------------------------------
+class _MixCDF(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, z, nn_out, sf, msf, pad, cfg):
+        z_out, ldj, reg = ops.mixcdf(z, nn_out, cfg["K"], mask_c=cfg["mask_c"], mask_s=cfg["mask_s"], pad=pad,
+                                     scaling_factor=sf, mixture_scaling_factor=msf, reverse=cfg["reverse"],
+                                     reg_max=cfg["reg_max"], reg_factor=cfg["reg_factor"], training=cfg["training"],
+                                     want_reg=True, prebounded=cfg.get("prebounded", False))
+        ctx.cfg = cfg
+        ctx.save_for_backward(z, nn_out, sf, msf, pad, z_out)
+        ctx.mark_non_differentiable(reg)
+        return z_out, ldj, reg
+
+    @staticmethod
+    def backward(ctx, g_z, g_ldj, g_reg):
+        from . import ops_bwd
+        z, nn_out, sf, msf, pad, z_out = ctx.saved_tensors
+        gz, gnn, gsf, gmsf = ops_bwd.mixcdf_backward(ctx.cfg, z, nn_out, sf, msf, pad, z_out, g_z, g_ldj,
+                                                     ctx.needs_input_grad)
+        return gz, gnn, gsf, gmsf, None, None
+
+
+def mixcdf(z, nn_out, num_mixtures, scaling_factor=None, mixture_scaling_factor=None, *, mask_c=None, mask_s=None,
+           pad=None, reverse=False, reg_max=-1.0, reg_factor=1.0, training=False, prebounded=False):
+    """(z_out, ldj [B], reg_ldj [B]) of the logistic-mixture coupling transform (K1 / K2)."""
+    cfg = dict(K=int(num_mixtures), mask_c=mask_c, mask_s=mask_s, reverse=bool(reverse), reg_max=float(reg_max),
+               reg_factor=float(reg_factor), training=bool(training), prebounded=bool(prebounded))
+    if _needs_grad(z, nn_out, scaling_factor, mixture_scaling_factor):
+        return _MixCDF.apply(z, nn_out, scaling_factor, mixture_scaling_factor, pad, cfg)
+    return ops.mixcdf(z, nn_out, cfg["K"], mask_c=mask_c, mask_s=mask_s, pad=pad, scaling_factor=scaling_factor,
+                      mixture_scaling_factor=mixture_scaling_factor, reverse=reverse, reg_max=reg_max,
+                      reg_factor=reg_factor, training=training, want_reg=True, prebounded=prebounded)
+
+
+# ----------------------------------------------------------------------------------------------
+# affine coupling
+# ----------------------------------------------------------------------------------------------
+class _Affine(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, z, nn_out, sf, cfg):
+        ldj = torch.zeros(z.size(0), dtype=torch.float32, device=z.device)
+        z_out, ldj = ops.affine_coupling(z, nn_out, ldj, mask_c=cfg["mask_c"], mask_s=cfg["mask_s"],
+                                         scaling_factor=sf, reverse=cfg["reverse"], prebounded=cfg["prebounded"])
+        ctx.cfg = cfg
+        ctx.save_for_backward(z, nn_out, sf, z_out)
+        return z_out, ldj
+
+    @staticmethod
+    def backward(ctx, g_z, g_ldj):
+        from . import ops_bwd
+        z, nn_out, sf, z_out = ctx.saved_tensors
+        gz, gnn, gsf = ops_bwd.affine_backward(ctx.cfg, z, nn_out, sf, z_out, g_z, g_ldj, ctx.needs_input_grad)
+        return gz, gnn, gsf, None
+
+
+def affine_coupling(z, nn_out, scaling_factor=None, *, mask_c=None, mask_s=None, reverse=False, prebounded=False):
+    """(z_out, layer_ldj [B]) of the affine coupling transform (K3)."""
+    cfg = dict(mask_c=mask_c, mask_s=mask_s, reverse=bool(reverse), prebounded=bool(prebounded))
+    if _needs_grad(z, nn_out, scaling_factor):
+        return _Affine.apply(z, nn_out, scaling_factor, cfg)
+    ldj = torch.zeros(z.size(0), dtype=torch.float32, device=z.device)
+    return ops.affine_coupling(z, nn_out, ldj, mask_c=mask_c, mask_s=mask_s, scaling_factor=scaling_factor,
+                               reverse=reverse, prebounded=prebounded)
+
+
+def affine_explicit(z, s, t, reverse=False):
+    """``CouplingLayer.run_with_params`` for explicit bounded (s, t): packs them into the [s, t]
+    record layout (pure data movement) and runs the same kernel with bounding disabled."""
+    rec = torch.stack([s.expand_as(z), t.expand_as(z)], dim=-1).reshape(z.shape[:-1] + (2 * z.shape[-1],))
+    return affine_coupling(z, rec, None, reverse=reverse, prebounded=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# activation normalisation / 1x1 convolution / prior: ldj is updated IN PLACE like upstream
+# ----------------------------------------------------------------------------------------------
+class _ActNorm(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, z, bias, scales, ldj, pad, length, reverse):
+        z_out, _ = ops.actnorm(z, bias, scales, ldj, pad=pad, length=length, reverse=reverse)
+        ctx.mark_dirty(ldj)
+        ctx.reverse = reverse
+        ctx.save_for_backward(z, bias, scales, pad, length, z_out)
+        return z_out, ldj
+
+    @staticmethod
+    def backward(ctx, g_z, g_ldj):
+        from . import ops_bwd
+        z, bias, scales, pad, length, z_out = ctx.saved_tensors
+        gz, gb, gs = ops_bwd.actnorm_backward(z, bias, scales, pad, length, z_out, g_z, g_ldj, ctx.reverse,
+                                              ctx.needs_input_grad)
+        return gz, gb, gs, g_ldj, None, None, None
+
+
+def actnorm(z, bias, scales, ldj, *, pad=None, length=None, reverse=False):
+    if _needs_grad(z, bias, scales, ldj):
+        return _ActNorm.apply(z, bias, scales, ldj, pad, length, bool(reverse))
+    return ops.actnorm(z, bias, scales, ldj, pad=pad, length=length, reverse=reverse)
+
+
+class _ExtActNorm(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, z, ext, ldj, pad, reverse):
+        z_out, _ = ops.ext_actnorm(z, ext, ldj, pad=pad, reverse=reverse)
+        ctx.mark_dirty(ldj)
+        ctx.reverse = reverse
+        ctx.save_for_backward(z, ext, pad, z_out)
+        return z_out, ldj
+
+    @staticmethod
+    def backward(ctx, g_z, g_ldj):
+        from . import ops_bwd
+        z, ext, pad, z_out = ctx.saved_tensors
+        gz, gext = ops_bwd.ext_actnorm_backward(z, ext, pad, z_out, g_z, g_ldj, ctx.reverse, ctx.needs_input_grad)
+        return gz, gext, g_ldj, None, None
+
+
+def ext_actnorm(z, ext, ldj, *, pad=None, reverse=False):
+    if _needs_grad(z, ext, ldj):
+        return _ExtActNorm.apply(z, ext, ldj, pad, bool(reverse))
+    return ops.ext_actnorm(z, ext, ldj, pad=pad, reverse=reverse)
+
+
+class _InvConv(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, z, weight, sldj, ldj, pad, length, reverse):
+        z_out, _ = ops.invconv_apply(z, weight, sldj, ldj, pad=pad, length=length, reverse=reverse)
+        ctx.mark_dirty(ldj)
+        ctx.reverse = reverse
+        ctx.save_for_backward(z, weight, pad, length)
+        return z_out, ldj
+
+    @staticmethod
+    def backward(ctx, g_z, g_ldj):
+        from . import ops_bwd
+        z, weight, pad, length = ctx.saved_tensors
+        gz, gw, gsldj = ops_bwd.invconv_backward(z, weight, pad, length, g_z, g_ldj, ctx.reverse, ctx.needs_input_grad)
+        return gz, gw, gsldj, g_ldj, None, None, None
+
+
+def invconv(z, weight, sldj, ldj, *, pad=None, length=None, reverse=False):
+    if _needs_grad(z, weight, sldj, ldj):
+        return _InvConv.apply(z, weight, sldj, ldj, pad, length, bool(reverse))
+    return ops.invconv_apply(z, weight, sldj, ldj, pad=pad, length=length, reverse=reverse)
+
+
+class _LogisticLogProb(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, x, mu, sigma):
+        _, lp = ops.logistic_logprob(x, mu=mu, sigma=sigma, reduce=False, elementwise=True)
+        ctx.mu, ctx.sigma = mu, sigma
+        ctx.save_for_backward(x)
+        return lp
+
+    @staticmethod
+    def backward(ctx, g):
+        from . import ops_bwd
+        (x,) = ctx.saved_tensors
+        return ops_bwd.logistic_logprob_backward(x, g, ctx.mu, ctx.sigma), None, None
+
+
+def logistic_logprob(x, mu=0.0, sigma=1.0 / 1.81):
+    """Element-wise log-density of Logistic(mu, sigma) (K7)."""
+    if _needs_grad(x):
+        return _LogisticLogProb.apply(x, float(mu), float(sigma))
+    return ops.logistic_logprob(x, mu=mu, sigma=sigma, reduce=False, elementwise=True)[1]

@@ -1,0 +1,12 @@
+from .flow_layer import FlowLayer
+from .flow_model import FlowModel
+from .coupling_layer import CouplingLayer
+from .mixture_cdf_layer import MixtureCDFCoupling
+from .autoregressive_coupling import AutoregressiveMixtureCDFCoupling
+from .activation_normalization import ActNormFlow, ExtActNormFlow
+from .permutation_layers import InvertibleConv
+from .distributions import LogisticDistribution, PriorDistribution, create_prior_distribution
+
+__all__ = ["FlowLayer", "FlowModel", "CouplingLayer", "MixtureCDFCoupling", "AutoregressiveMixtureCDFCoupling",
+           "ActNormFlow", "ExtActNormFlow", "InvertibleConv", "LogisticDistribution", "PriorDistribution",
+           "create_prior_distribution"]

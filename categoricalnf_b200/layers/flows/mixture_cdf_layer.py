@@ -1,0 +1,123 @@
+"""Logistic-mixture-CDF coupling (Flow++ style; reference layers/flows/mixture_cdf_layer.py).
+
+``forward`` keeps the reference's signature, parameters (``scaling_factor``,
+``mixture_scaling_factor``, ``nn.*``), its 3-tuple return and its quirk of *discarding* the
+incoming ldj (App. B #1); the parameter split + transform + ldj reduction run as one
+``cnf_mixcdf_fwd`` / ``cnf_mixcdf_inv`` launch (csrc/mixcdf.cu).
+"""
+import torch
+import torch.nn as nn
+
+from ... import functional as CF
+from ._masks import mask_lists
+from .coupling_layer import CouplingLayer
+
+
+class MixtParams:
+    """Opaque handle returned five times by :meth:`MixtureCDFCoupling.get_mixt_params`.
+
+    The reference materialises five float64 tensors here (mixture_cdf_layer.py:145-180) and hands
+    them straight to ``run_with_params`` (e.g. graph_node_edge_coupling.py:117-135,
+    autoregressive_coupling.py:32-38).  The fused kernel consumes the raw network output, so the
+    handle only records it; ``run_with_params`` recognises the handle and launches the kernel.
+    """
+
+    def __init__(self, nn_out, mask, num_mixtures, scaling_factor, mixture_scaling_factor):
+        self.nn_out, self.mask, self.num_mixtures = nn_out, mask, num_mixtures
+        self.scaling_factor, self.mixture_scaling_factor = scaling_factor, mixture_scaling_factor
+
+    def materialize(self):
+        """The five bounded, masked parameter tensors in float32 (diagnostics only)."""
+        K, pn = self.num_mixtures, 2 + 3 * self.num_mixtures
+        rec = self.nn_out.reshape(self.nn_out.shape[:-1] + (self.nn_out.shape[-1] // pn, pn))
+        t, log_s = rec[..., 0], rec[..., 1]
+        log_pi, mu, mls = rec[..., 2:2 + K], rec[..., 2 + K:2 + 2 * K], rec[..., 2 + 2 * K:]
+        if self.scaling_factor is not None:
+            b = self.scaling_factor.exp()
+            log_s = torch.tanh(log_s / b.clamp(min=1.0)) * b
+        if self.mixture_scaling_factor is not None:
+            b = self.mixture_scaling_factor.exp()
+            mls = torch.tanh(mls / b.clamp(min=1.0)) * b
+        if self.mask is not None:
+            keep = 1 - self.mask
+            t, log_s = t * keep, log_s * keep
+            log_pi, mu, mls = (v * keep.unsqueeze(-1) for v in (log_pi, mu, mls))
+        return t, log_s, log_pi, mu, mls
+
+
+def _mask_from_tensor(mask, z):
+    """Broadcastable mask tensor ([1,1,C] / [1,S,1] / [1,C]) -> (mask_c, mask_s) host lists."""
+    if mask is None:
+        return None, None
+    m = mask.detach().to("cpu", torch.float32)
+    while m.dim() > 2 and m.shape[0] == 1:
+        m = m[0]
+    if m.dim() == 1:
+        return m.tolist(), None
+    if m.shape[0] == 1:
+        return m.flatten().tolist(), None
+    if m.shape[-1] == 1:
+        return None, m.flatten().tolist()
+    raise NotImplementedError("joint position x channel mask of shape %s" % (tuple(mask.shape),))
+
+
+class MixtureCDFCoupling(CouplingLayer):
+
+    def __init__(self, c_in, mask, model_func, block_type=None, num_mixtures=10, regularizer_max=-1,
+                 regularizer_factor=1, **kwargs):
+        super().__init__(c_in=c_in, mask=mask, model_func=model_func, block_type=block_type,
+                         c_out=c_in * (2 + num_mixtures * 3), **kwargs)
+        self.num_mixtures = num_mixtures
+        self.mixture_scaling_factor = nn.Parameter(torch.zeros(self.c_in, self.num_mixtures))
+        self.regularizer_max = regularizer_max
+        self.regularizer_factor = regularizer_factor
+
+    def forward(self, z, ldj=None, reverse=False, channel_padding_mask=None, **kwargs):
+        # the incoming ldj is ignored and only this layer's ldj is returned, as upstream (:46-47,:63)
+        nn_out = self.run_network(x=z * self._prepare_mask(self.mask, z), **kwargs)
+        mask_c, mask_s = mask_lists(self, "mask", z.size(1))
+        z_out, ldj, reg = CF.mixcdf(z, nn_out, self.num_mixtures, self.scaling_factor, self.mixture_scaling_factor,
+                                    mask_c=mask_c, mask_s=mask_s, pad=channel_padding_mask, reverse=reverse,
+                                    reg_max=self.regularizer_max, reg_factor=self.regularizer_factor,
+                                    training=self.training)
+        return z_out, ldj, {"ldj": ldj, "regularizer_ldj": reg}
+
+    # -- static entry points used by other files ----------------------------------------------------
+    @staticmethod
+    def get_mixt_params(nn_out, mask, num_mixtures, scaling_factor=None, mixture_scaling_factor=None):
+        h = MixtParams(nn_out, mask, num_mixtures, scaling_factor, mixture_scaling_factor)
+        return h, h, h, h, h
+
+    @staticmethod
+    def run_with_params(orig_z, t, log_s, log_pi, mixt_t, mixt_log_s, reverse=False, reg_max=-1, reg_factor=1,
+                        mask=None, channel_padding_mask=None, is_training=True, return_reg_ldj=False):
+        """Fused transform for parameters obtained from :meth:`get_mixt_params` (handle) or given
+        as explicit tensors (packed into the record layout, bounding disabled)."""
+        z = orig_z.float()
+        if isinstance(t, MixtParams):
+            h = t
+            nn_out, K, sf, msf, pre = h.nn_out, h.num_mixtures, h.scaling_factor, h.mixture_scaling_factor, False
+            if mask is None:
+                mask = h.mask
+        else:
+            K = log_pi.shape[-1]
+            nn_out = torch.cat([t.unsqueeze(-1), log_s.unsqueeze(-1), log_pi, mixt_t, mixt_log_s], dim=-1).float()
+            nn_out = nn_out.reshape(z.shape[:-1] + (z.shape[-1] * (2 + 3 * K),))
+            sf = msf = None
+            pre = True
+        mask_c, mask_s = _mask_from_tensor(mask, z)
+        z_out, ldj, reg = CF.mixcdf(z, nn_out, K, sf, msf, mask_c=mask_c, mask_s=mask_s, pad=channel_padding_mask,
+                                    reverse=reverse, reg_max=reg_max, reg_factor=reg_factor, training=is_training,
+                                    prebounded=pre)
+        # upstream multiplies by the padding mask only in the callers (:76); the kernel has already
+        # done so, which is idempotent for 0/1 masks.
+        if return_reg_ldj:
+            return z_out, ldj, (reg if not reverse else None)
+        return z_out, ldj
+
+    def info(self):
+        kind = "channel" if self.mask.size(0) == 1 else "chess"
+        text = "Mixture CDF Coupling Layer - Input size %i" % self.c_in
+        if self.block_type is not None:
+            text += ", block type %s" % self.block_type
+        return text + ", %i mixtures, mask ratio %.2f, %s mask" % (self.num_mixtures, (1 - self.mask).mean().item(), kind)

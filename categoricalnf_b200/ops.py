@@ -1,0 +1,346 @@
+"""Tensor-level entry points: torch CUDA tensors in, C-ABI calls out.
+
+PyTorch is used here only as the owner of device memory and streams; every function launches
+hand-written sm_100a kernels from ``libcnf_b200.so`` on ``torch.cuda.current_stream()``.  CPU
+tensors are rejected - there is no fallback path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib as L
+
+STRICT = os.environ.get("CNF_B200_STRICT", "0") not in ("", "0")
+
+FLAG_NAN_Z, FLAG_NAN_LDJ, FLAG_CDF_RANGE = 1, 2, 4
+
+_status_words = {}
+_launches = 0  # number of C-ABI kernel launches issued by this process (bench.py reports it)
+
+
+def launch_count() -> int:
+    return _launches
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _f32(t: torch.Tensor, name: str, shape=None) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("%s must be a torch.Tensor" % name)
+    if not t.is_cuda:
+        raise RuntimeError("categoricalnf_b200: %s lives on %s - the hot path runs on CUDA only "
+                           "(there is no CPU fallback)" % (name, t.device))
+    if t.dtype != torch.float32:
+        t = t.float()
+    if not t.is_contiguous():
+        t = t.contiguous()
+    if shape is not None and tuple(t.shape) != tuple(shape):
+        raise ValueError("%s has shape %s, expected %s" % (name, tuple(t.shape), tuple(shape)))
+    return t
+
+
+def _opt_f32(t, name, shape=None):
+    return None if t is None else _f32(t, name, shape)
+
+
+def _pad_bs(pad, B, S, name="channel_padding_mask"):
+    """Accept [B,S], [B,S,1] (or anything with B*S elements) and return a contiguous [B,S] view."""
+    if pad is None:
+        return None
+    pad = _f32(pad, name)
+    if pad.numel() != B * S:
+        raise ValueError("%s has %d elements, expected B*S = %d" % (name, pad.numel(), B * S))
+    return pad.reshape(B, S)
+
+
+def _host_floats(vals: Optional[Sequence[float]]):
+    if vals is None:
+        return None, None
+    arr = (C.c_float * len(vals))(*[float(v) for v in vals])
+    return arr, C.cast(arr, C.c_void_p)
+
+
+def _mask_struct(mask_c, mask_s):
+    keep = []
+    m = L.Mask()
+    arr, p = _host_floats(mask_c)
+    keep.append(arr)
+    m.cond_c_host = p
+    arr, p = _host_floats(mask_s)
+    keep.append(arr)
+    m.cond_s_host = p
+    m.s_period = 0 if mask_s is None else len(mask_s)
+    return m, keep
+
+
+def status_word(device) -> torch.Tensor:
+    """Per-device uint32 word that kernels OR health flags into (cnf_b200.h: CNF_FLAG_*)."""
+    dev = torch.device(device)
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    w = _status_words.get(key)
+    if w is None:
+        w = torch.zeros(1, dtype=torch.int32, device=torch.device("cuda", key))
+        _status_words[key] = w
+    return w
+
+
+def check_status(device, where: str = "") -> None:
+    """Read and clear the status word (one host sync) and raise like the reference would:
+    AssertionError for NaNs (mixture_cdf_layer.py:82, flow_model.py:42), RuntimeError for an
+    inverse-CDF argument outside (0,1) (mixture_cdf_layer.py:238-239)."""
+    w = status_word(device)
+    bits = int(w.item())
+    if bits == 0:
+        return
+    w.zero_()
+    if bits & FLAG_CDF_RANGE:
+        raise RuntimeError("Inverse logisitic CDF got y outside (0, 1)" + (" [%s]" % where if where else ""))
+    what = []
+    if bits & FLAG_NAN_Z:
+        what.append("z")
+    if bits & FLAG_NAN_LDJ:
+        what.append("ldj")
+    raise AssertionError("[!] ERROR: Found NaN in %s%s" % (" and ".join(what), " (%s)" % where if where else ""))
+
+
+def _call(name, args, ref: torch.Tensor, keep=None):
+    global _launches
+    L.call(name, args, _stream(ref))
+    _launches += 1
+    if STRICT:
+        check_status(ref.device, name)
+
+
+# ----------------------------------------------------------------------------------------------
+def mixcdf(z, nn_out, num_mixtures, *, mask_c=None, mask_s=None, pad=None, scaling_factor=None,
+           mixture_scaling_factor=None, reverse=False, reg_max=-1.0, reg_factor=1.0, training=False,
+           ldj=None, want_reg=False, out=None, prebounded=False):
+    """K1/K2.  Returns ``(z_out, ldj[B], reg_ldj[B] | None)``.  ``ldj`` given -> accumulated into."""
+    z = _f32(z, "z")
+    if z.dim() != 3:
+        raise ValueError("z must be [B, S, C]")
+    B, S, Cc = z.shape
+    K = int(num_mixtures)
+    nn_out = _f32(nn_out, "nn_out", (B, S, Cc * (2 + 3 * K)))
+    pad = _pad_bs(pad, B, S)
+    a = L.MixcdfArgs()
+    a.B, a.S, a.C, a.K = B, S, Cc, K
+    a.mask, keep = _mask_struct(mask_c, mask_s)
+    sf = _opt_f32(scaling_factor, "scaling_factor", (Cc,))
+    msf = _opt_f32(mixture_scaling_factor, "mixture_scaling_factor", (Cc, K))
+    z_out = torch.empty_like(z) if out is None else out
+    accumulate = ldj is not None
+    ldj_t = _f32(ldj, "ldj", (B,)) if accumulate else torch.empty(B, dtype=torch.float32, device=z.device)
+    reg = torch.empty(B, dtype=torch.float32, device=z.device) if want_reg else None
+    a.z, a.nn_out, a.pad = _ptr(z), _ptr(nn_out), _ptr(pad)
+    a.scaling_factor, a.mixture_scaling_factor = _ptr(sf), _ptr(msf)
+    a.reg_max, a.reg_factor, a.training = float(reg_max), float(reg_factor), int(bool(training))
+    a.accumulate = int(accumulate)
+    a.params_prebounded = int(bool(prebounded))
+    a.z_out, a.ldj, a.reg_ldj = _ptr(z_out), _ptr(ldj_t), _ptr(reg)
+    a.status = _ptr(status_word(z.device))
+    _call("cnf_mixcdf_inv" if reverse else "cnf_mixcdf_fwd", a, z, keep)
+    return z_out, ldj_t, reg
+
+
+def affine_coupling(z, nn_out, ldj, *, mask_c=None, mask_s=None, scaling_factor=None, reverse=False,
+                    prebounded=False):
+    """K3.  ``ldj`` [B] is updated in place and returned together with z_out."""
+    z = _f32(z, "z")
+    B, S, Cc = z.shape
+    nn_out = _f32(nn_out, "nn_out", (B, S, 2 * Cc))
+    ldj = _f32(ldj, "ldj", (B,))
+    a = L.AffineArgs()
+    a.B, a.S, a.C = B, S, Cc
+    a.mask, keep = _mask_struct(mask_c, mask_s)
+    sf = _opt_f32(scaling_factor, "scaling_factor", (Cc,))
+    z_out = torch.empty_like(z)
+    a.z, a.nn_out, a.scaling_factor, a.reverse = _ptr(z), _ptr(nn_out), _ptr(sf), int(bool(reverse))
+    a.params_prebounded = int(bool(prebounded))
+    a.z_out, a.ldj, a.status = _ptr(z_out), _ptr(ldj), _ptr(status_word(z.device))
+    _call("cnf_affine_coupling", a, z, keep)
+    return z_out, ldj
+
+
+def actnorm(z, bias, scales, ldj=None, *, pad=None, length=None, reverse=False):
+    """K4.  ``ldj`` (if given) is updated IN PLACE like the reference's ``ldj +=``."""
+    z = _f32(z, "z")
+    B, S, Cc = z.shape
+    a = L.ActnormArgs()
+    a.B, a.S, a.C = B, S, Cc
+    bias = _f32(bias, "bias").reshape(-1)
+    scales = _f32(scales, "scales").reshape(-1)
+    pad = _pad_bs(pad, B, S)
+    length = _opt_f32(length, "length", (B,))
+    if ldj is not None:
+        ldj = _f32(ldj, "ldj", (B,))
+    z_out = torch.empty_like(z)
+    a.z, a.bias, a.scales, a.pad, a.length = _ptr(z), _ptr(bias), _ptr(scales), _ptr(pad), _ptr(length)
+    a.reverse, a.z_out, a.ldj, a.status = int(bool(reverse)), _ptr(z_out), _ptr(ldj), _ptr(status_word(z.device))
+    _call("cnf_actnorm", a, z)
+    return z_out, ldj
+
+
+def ext_actnorm(z, ext, ldj, *, pad=None, reverse=False):
+    """K4 (external).  ``ext`` = pred_net output ``[B,S,2C]``; ``ldj`` updated in place."""
+    z = _f32(z, "z")
+    B, S, Cc = z.shape
+    ext = _f32(ext, "ext", (B, S, 2 * Cc))
+    ldj = _f32(ldj, "ldj", (B,))
+    pad = _pad_bs(pad, B, S)
+    a = L.ExtActnormArgs()
+    a.B, a.S, a.C = B, S, Cc
+    z_out = torch.empty_like(z)
+    a.z, a.ext, a.pad, a.reverse = _ptr(z), _ptr(ext), _ptr(pad), int(bool(reverse))
+    a.z_out, a.ldj, a.status = _ptr(z_out), _ptr(ldj), _ptr(status_word(z.device))
+    _call("cnf_ext_actnorm", a, z)
+    return z_out, ldj
+
+
+def actnorm_data_init(x, pad=None):
+    """Masked per-channel statistics -> (bias [C], scales [C]) (activation_normalization.py:55-67)."""
+    x = _f32(x, "x")
+    B, S, Cc = x.shape
+    pad = _pad_bs(pad, B, S)
+    ws = torch.empty(3 * Cc, dtype=torch.float64, device=x.device)
+    bias = torch.empty(Cc, dtype=torch.float32, device=x.device)
+    scales = torch.empty(Cc, dtype=torch.float32, device=x.device)
+    a = L.ActnormInitArgs()
+    a.B, a.S, a.C = B, S, Cc
+    a.x, a.pad, a.workspace, a.bias, a.scales = _ptr(x), _ptr(pad), _ptr(ws), _ptr(bias), _ptr(scales)
+    _call("cnf_actnorm_data_init", a, x)
+    return bias, scales
+
+
+def invconv_build(p=None, l=None, u=None, log_s=None, sign_s=None, weight=None, want_inverse=True):
+    """K5 build.  Returns ``(W [C,C], W_inv [C,C] | None, sldj [1])`` as device tensors."""
+    ref = weight if weight is not None else l
+    ref = _f32(ref, "weight/l")
+    Cc = ref.shape[0]
+    a = L.InvconvBuildArgs()
+    a.C = Cc
+    ts = {k: _opt_f32(v, k) for k, v in dict(p=p, l=l, u=u, log_s=log_s, sign_s=sign_s, weight=weight).items()}
+    w = torch.empty(Cc, Cc, dtype=torch.float32, device=ref.device)
+    w_inv = torch.empty(Cc, Cc, dtype=torch.float32, device=ref.device) if want_inverse else None
+    sldj = torch.empty(1, dtype=torch.float32, device=ref.device)
+    a.p, a.l, a.u, a.log_s, a.sign_s, a.weight = (_ptr(ts[k]) for k in ("p", "l", "u", "log_s", "sign_s", "weight"))
+    a.w_out, a.w_inv_out, a.sldj_out = _ptr(w), _ptr(w_inv), _ptr(sldj)
+    _call("cnf_invconv_build", a, ref)
+    return w, w_inv, sldj
+
+
+def invconv_apply(z, weight, sldj, ldj=None, *, pad=None, length=None, reverse=False):
+    """K5 apply.  Returns ``(z_out, ldj)``; ldj (if given) is updated in place."""
+    z = _f32(z, "z")
+    B, S, Cc = z.shape
+    weight = _f32(weight, "weight", (Cc, Cc))
+    sldj = _f32(sldj, "sldj").reshape(1)
+    pad = _pad_bs(pad, B, S)
+    length = _opt_f32(length, "length", (B,))
+    if ldj is not None:
+        ldj = _f32(ldj, "ldj", (B,))
+    z_out = torch.empty_like(z)
+    a = L.InvconvArgs()
+    a.B, a.S, a.C = B, S, Cc
+    a.z, a.weight, a.sldj, a.pad, a.length = _ptr(z), _ptr(weight), _ptr(sldj), _ptr(pad), _ptr(length)
+    a.reverse, a.z_out, a.ldj, a.status = int(bool(reverse)), _ptr(z_out), _ptr(ldj), _ptr(status_word(z.device))
+    _call("cnf_invconv_apply", a, z)
+    return z_out, ldj
+
+
+def categ_encode(tokens, table, category_prior, ldj, *, noise=None, seed=0, offset=0, pad=None, beta=1.0,
+                 want_class_prob=False):
+    """K6 encode.  tokens [B,S] int64 -> (z [B,S,D], ldj (in place), class_prob_log [B,S] | None)."""
+    if not tokens.is_cuda:
+        raise RuntimeError("categoricalnf_b200: tokens live on %s - CUDA only" % tokens.device)
+    tokens = tokens.long().contiguous()
+    B, S = tokens.shape
+    table = _f32(table, "table")
+    V, D2 = table.shape
+    D = D2 // 2
+    prior = _opt_f32(category_prior, "category_prior", (V,))
+    ldj = _f32(ldj, "ldj", (B,))
+    pad = _pad_bs(pad, B, S)
+    if noise is not None:
+        noise = _f32(noise, "noise")
+        if noise.numel() != B * S * D:
+            raise ValueError("noise has %d elements, expected %d" % (noise.numel(), B * S * D))
+    z = torch.empty(B, S, D, dtype=torch.float32, device=tokens.device)
+    cpl = torch.empty(B, S, dtype=torch.float32, device=tokens.device) if want_class_prob else None
+    a = L.CategEncodeArgs()
+    a.B, a.S, a.V, a.D = B, S, V, D
+    a.tokens, a.u_noise, a.seed, a.offset = _ptr(tokens), _ptr(noise), int(seed), int(offset)
+    a.table, a.category_prior, a.pad, a.beta = _ptr(table), _ptr(prior), _ptr(pad), float(beta)
+    a.z_out, a.ldj, a.class_prob_log, a.status = _ptr(z), _ptr(ldj), _ptr(cpl), _ptr(status_word(z.device))
+    _call("cnf_categ_encode", a, z)
+    return z, ldj, cpl
+
+
+def categ_decode(z, table, category_prior):
+    """K6 decode.  z [B,S,D] -> tokens [B,S] int64 (argmax of the class-conditional density)."""
+    z = _f32(z, "z")
+    B, S, D = z.shape
+    table = _f32(table, "table")
+    V = table.shape[0]
+    if table.shape[1] != 2 * D:
+        raise ValueError("table is %s but z has D=%d" % (tuple(table.shape), D))
+    prior = _opt_f32(category_prior, "category_prior", (V,))
+    out = torch.empty(B, S, dtype=torch.int64, device=z.device)
+    a = L.CategDecodeArgs()
+    a.B, a.S, a.V, a.D = B, S, V, D
+    a.z, a.table, a.category_prior, a.tokens_out = _ptr(z), _ptr(table), _ptr(prior), _ptr(out)
+    _call("cnf_categ_decode", a, z)
+    return out
+
+
+def logistic_logprob(x, *, pad=None, mu=0.0, sigma=1.0 / 1.81, reduce=True, elementwise=False, out=None):
+    """K7.  Returns per-sample sums [B] (``reduce``) and/or the element-wise log-density."""
+    x = _f32(x, "x")
+    shape = x.shape
+    x3 = x.reshape(shape[0], -1, shape[-1]) if x.dim() >= 2 else x.reshape(1, 1, -1)
+    B, S, Cc = x3.shape
+    pad = _pad_bs(pad, B, S) if pad is not None else None
+    a = L.LogisticLogprobArgs()
+    a.B, a.S, a.C = B, S, Cc
+    acc = out is not None
+    res = _f32(out, "out", (B,)) if acc else (torch.empty(B, dtype=torch.float32, device=x.device) if reduce else None)
+    elem = torch.empty_like(x) if elementwise else None
+    a.x, a.pad, a.mu, a.sigma, a.accumulate = _ptr(x3), _ptr(pad), float(mu), float(sigma), int(acc)
+    a.out, a.elementwise = _ptr(res), _ptr(elem)
+    _call("cnf_logistic_logprob", a, x)
+    return res, elem
+
+
+def logistic_sample(shape, device, *, noise=None, seed=0, offset=0, mu=0.0, sigma=1.0 / 1.81, eps=1e-4):
+    """K7 sampler: logit of a squeezed uniform, scaled (distributions.py:139-145)."""
+    x = torch.empty(tuple(shape), dtype=torch.float32, device=device)
+    if not x.is_cuda:
+        raise RuntimeError("categoricalnf_b200: sampling runs on CUDA only")
+    if noise is not None:
+        noise = _f32(noise, "noise")
+    a = L.LogisticSampleArgs()
+    a.n, a.u_noise, a.seed, a.offset = x.numel(), _ptr(noise), int(seed), int(offset)
+    a.mu, a.sigma, a.eps, a.x_out = float(mu), float(sigma), float(eps), _ptr(x)
+    _call("cnf_logistic_sample", a, x)
+    return x
+
+
+def ldj_axpy(y, *, alpha=1.0, alpha_dev=None, x=None, length=None):
+    """y[b] += alpha * alpha_dev * x[b] * length[b] (missing factors are 1)."""
+    y = _f32(y, "y")
+    a = L.LdjAxpyArgs()
+    a.B, a.alpha = y.numel(), float(alpha)
+    a.alpha_dev, a.x, a.length, a.y = _ptr(_opt_f32(alpha_dev, "alpha_dev")), _ptr(_opt_f32(x, "x")), \
+        _ptr(_opt_f32(length, "length")), _ptr(y)
+    _call("cnf_ldj_axpy", a, y)
+    return y

@@ -1,0 +1,322 @@
+/*
+ * cnf_b200.h - C ABI of the B200-native coupling-layer hot path of CategoricalNF.
+ *
+ * The reference (phlippe/CategoricalNF) is pure Python/PyTorch and has no FFI layer; the
+ * boundary it exposes is the Python `FlowLayer` API (layers/flows/flow_layer.py:5-32).  This
+ * header is the native boundary that sits directly *under* those modules: one entry point per
+ * reference function on the path.  The Python modules in
+ * `categoricalnf_b200/layers/` bind these symbols with ctypes and keep the reference's
+ * signatures; INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every entry point is `int f(const <args>*, cnf_stream_t)`; 0 = CNF_OK, otherwise an error
+ *     code whose text is returned by cnf_last_error_string() (thread local).  No C++ exceptions
+ *     cross the boundary.
+ *   - pointers named *_host are HOST memory, read synchronously at call time; every other
+ *     pointer is DEVICE memory of the current CUDA device and is only touched on `stream`.
+ *   - the library never allocates device memory and holds no global mutable state: calls are
+ *     re-entrant and capturable in CUDA graphs.  Work is launched asynchronously.
+ *   - tensors are dense, row-major, float32 unless stated; B = samples, S = positions per
+ *     sample (sequence / nodes / node pairs), C = latent channels, K = mixture components.
+ *   - numerical health is reported through an optional device status word (`status`), OR-ed
+ *     with CNF_FLAG_* bits; the host checks it lazily instead of the reference's per-layer
+ *     `assert torch.isnan(...)` host syncs (mixture_cdf_layer.py:82, flow_model.py:42).
+ */
+#ifndef CNF_B200_H
+#define CNF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* cnf_stream_t;
+
+#if defined(__GNUC__)
+#define CNF_API __attribute__((visibility("default")))
+#else
+#define CNF_API
+#endif
+
+enum {
+    CNF_OK = 0,
+    CNF_ERR_INVALID_ARG = 1,  /* null pointer, bad size, misaligned tensor            */
+    CNF_ERR_UNSUPPORTED = 2,  /* shape outside the compiled range (C > 64, K > 256 ..) */
+    CNF_ERR_CUDA = 3          /* a CUDA runtime call failed (text has the CUDA error)  */
+};
+
+/* bits of the device status word */
+#define CNF_FLAG_NAN_Z 1u      /* NaN in an output latent (reference: AssertionError)              */
+#define CNF_FLAG_NAN_LDJ 2u    /* NaN in a log-det-Jacobian term                                    */
+#define CNF_FLAG_CDF_RANGE 4u  /* inverse CDF input outside (0,1) (reference: RuntimeError, :238)   */
+
+#define CNF_MAX_CHANNELS 64
+#define CNF_MAX_MIXTURES 256
+
+CNF_API const char* cnf_last_error_string(void);
+/* ABI version (bumped on any struct change) and the SM architecture the kernels were built for. */
+CNF_API int cnf_abi_version(void);
+CNF_API int cnf_built_for_sm(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Coupling masks.  `cond_c_host[c] != 0` marks channel c as conditioner input (mask value 1 in
+ * coupling_layer.py:101-112); NULL = no channel is a conditioner.  `cond_s_host` is the chess
+ * mask over positions (coupling_layer.py:115-121) of period `s_period` (<= 64), applied as
+ * mask[s % s_period] exactly like `_prepare_mask` tiles it (coupling_layer.py:67-74);
+ * NULL / 0 = none.  An element is transformed iff neither its channel nor its position is a
+ * conditioner; `pad` (channel_padding_mask, [B,S], 1 = real element) multiplies in as in
+ * mixture_cdf_layer.py:99-101.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    const float* cond_c_host; /* [C] or NULL */
+    const float* cond_s_host; /* [s_period] or NULL */
+    int32_t s_period;
+} cnf_mask;
+
+/* ------------------------------------------------------------------------------------------
+ * K1 / K2  logistic-mixture-CDF coupling transform
+ *   replaces MixtureCDFCoupling.get_mixt_params + run_with_params
+ *   (layers/flows/mixture_cdf_layer.py:95-142, 145-180, 197-276)
+ * nn_out record per channel: [t, log_s, log_pi x K, mu x K, log_scale x K].
+ * Forward:  F = mixture CDF(x); y = logit F; z_out = (y + t) e^{log_s};
+ *           ldj[b] (+)= sum change * (log_s - log F - log(1-F) + log f (+ reg * reg_factor)).
+ * Inverse:  y = z e^{-log_s} - t; F = clamp(sigmoid y, 1e-5, 1-1e-5); x = CDF^-1(F) by
+ *           bracketed bisection started at 0; ldj[b] (+)= -sum change * (...).
+ * Conditioner / padded elements are copied (times pad) and contribute nothing.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    int64_t B, S;
+    int32_t C, K;
+    const float* z;                      /* [B,S,C]                                   */
+    const float* nn_out;                 /* [B,S,C*(2+3K)]                            */
+    cnf_mask mask;
+    const float* pad;                    /* [B,S] or NULL                             */
+    const float* scaling_factor;         /* [C]   log of the tanh bound, or NULL      */
+    const float* mixture_scaling_factor; /* [C,K] or NULL                             */
+    float reg_max;                       /* <= 0 disables the CDF regulariser (:108)  */
+    float reg_factor;
+    int32_t training;                    /* regulariser only when training (:108)     */
+    int32_t accumulate;                  /* 0: ldj/reg_ldj overwritten, 1: added to   */
+    int32_t params_prebounded;           /* 1: log_s / log_scale entries of nn_out are
+                                            already tanh-bounded (explicit-parameter callers
+                                            of run_with_params); scaling factors ignored */
+    float* z_out;                        /* [B,S,C] (may alias z)                     */
+    float* ldj;                          /* [B]                                       */
+    float* reg_ldj;                      /* [B] or NULL (forward only)                */
+    uint32_t* status;                    /* device status word or NULL                */
+    /* optional fused epilogue (forward only): the ActNorm and 1x1 convolution of the NEXT flow
+     * block, applied to the full output row before the store (saves two passes over z).
+     * ldj terms of those layers are per-sample constants and are added by cnf_ldj_axpy. */
+    const float* next_actnorm_bias;      /* [C] or NULL                               */
+    const float* next_actnorm_scales;    /* [C] or NULL                               */
+    const float* next_conv_weight;       /* [C,C] row-major (z @ W) or NULL           */
+} cnf_mixcdf_args;
+
+CNF_API int cnf_mixcdf_fwd(const cnf_mixcdf_args* a, cnf_stream_t stream);
+CNF_API int cnf_mixcdf_inv(const cnf_mixcdf_args* a, cnf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K3  affine coupling  (layers/flows/coupling_layer.py:53-65, 76-98)
+ * nn_out record per channel: [s, t]; s = tanh(s / max(e^{sf},1)) e^{sf}.
+ * forward z_out = (z + t) e^{s}, ldj += sum s ; inverse z_out = z e^{-s} - t, ldj -= sum s.
+ * The ldj is not pad-masked (App. B #4).  `ldj` is always accumulated into.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    int64_t B, S;
+    int32_t C;
+    const float* z;              /* [B,S,C]  */
+    const float* nn_out;         /* [B,S,2C] */
+    cnf_mask mask;
+    const float* scaling_factor; /* [C] or NULL */
+    int32_t reverse;
+    int32_t params_prebounded;   /* 1: s is already tanh-bounded (explicit run_with_params) */
+    float* z_out;                /* [B,S,C] */
+    float* ldj;                  /* [B] in/out */
+    uint32_t* status;
+} cnf_affine_args;
+
+CNF_API int cnf_affine_coupling(const cnf_affine_args* a, cnf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K4  activation normalisation
+ *   ActNormFlow.forward        (layers/flows/activation_normalization.py:24-48)
+ *   ExtActNormFlow.forward     (:116-144) with the per-element (bias, raw scale) already
+ *                              produced by pred_net: `ext` is [B,S,2C] = [bias | raw scale].
+ *   data_init statistics       (:55-67)
+ * forward z_out = (z + b) e^{s} * pad ; inverse z_out = (z e^{-s} - b) * pad.
+ * ActNorm:    ldj[b] += (+/-) sum_c s_c * len_b,  len_b = length[b] | sum_s pad | S.
+ * ExtActNorm: ldj[b] += (+/-) sum_{s,c} tanh(raw)_{s,c} * pad; output is NOT pad-multiplied.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    int64_t B, S;
+    int32_t C;
+    const float* z;       /* [B,S,C] */
+    const float* bias;    /* [C] */
+    const float* scales;  /* [C] */
+    const float* pad;     /* [B,S] or NULL */
+    const float* length;  /* [B] float or NULL */
+    int32_t reverse;
+    float* z_out;         /* [B,S,C] */
+    float* ldj;           /* [B] in/out, or NULL to skip */
+    uint32_t* status;
+} cnf_actnorm_args;
+
+CNF_API int cnf_actnorm(const cnf_actnorm_args* a, cnf_stream_t stream);
+
+typedef struct {
+    int64_t B, S;
+    int32_t C;
+    const float* z;    /* [B,S,C]  */
+    const float* ext;  /* [B,S,2C] */
+    const float* pad;  /* [B,S] or NULL */
+    int32_t reverse;
+    float* z_out;
+    float* ldj;        /* [B] in/out */
+    uint32_t* status;
+} cnf_ext_actnorm_args;
+
+CNF_API int cnf_ext_actnorm(const cnf_ext_actnorm_args* a, cnf_stream_t stream);
+
+/* Masked per-channel statistics for the data-dependent init: writes bias = -mean,
+ * scales = -0.5 log(var) where var = E[(x + bias)^2] over elements with pad = 1.
+ * `workspace` needs 3*C doubles, zeroed by the call. */
+typedef struct {
+    int64_t B, S;
+    int32_t C;
+    const float* x;     /* [B,S,C] */
+    const float* pad;   /* [B,S] or NULL */
+    double* workspace;  /* [3*C] */
+    float* bias;        /* [C] out */
+    float* scales;      /* [C] out */
+} cnf_actnorm_init_args;
+
+CNF_API int cnf_actnorm_data_init(const cnf_actnorm_init_args* a, cnf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K5  invertible 1x1 convolution  (layers/flows/permutation_layers.py:61-136)
+ * build:  W = P (L o strict_lower + I)(U o strict_upper + diag(sign_s e^{log_s})),
+ *         sldj = sum log_s, W_inv = inverse(W) in float64 rounded to float32 (:77,:85).
+ *         For the non-LU parametrisation pass `weight` and sldj = log|det W| is computed by
+ *         an in-kernel LU (:64-65).
+ * apply:  z_out = (z @ W) * pad ; ldj[b] += (+/-) sldj * len_b.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t C;
+    const float* p;       /* [C,C] or NULL when `weight` given */
+    const float* l;       /* [C,C] */
+    const float* u;       /* [C,C] */
+    const float* log_s;   /* [C]   */
+    const float* sign_s;  /* [C]   */
+    const float* weight;  /* [C,C] direct parametrisation, or NULL */
+    float* w_out;         /* [C,C] */
+    float* w_inv_out;     /* [C,C] or NULL */
+    float* sldj_out;      /* [1]   */
+} cnf_invconv_build_args;
+
+CNF_API int cnf_invconv_build(const cnf_invconv_build_args* a, cnf_stream_t stream);
+
+typedef struct {
+    int64_t B, S;
+    int32_t C;
+    const float* z;       /* [B,S,C] */
+    const float* weight;  /* [C,C] (W forward, W^-1 reverse) */
+    const float* sldj;    /* [1] device scalar */
+    const float* pad;     /* [B,S] or NULL */
+    const float* length;  /* [B] float or NULL (-> S) */
+    int32_t reverse;
+    float* z_out;
+    float* ldj;           /* [B] in/out or NULL */
+    uint32_t* status;
+} cnf_invconv_args;
+
+CNF_API int cnf_invconv_apply(const cnf_invconv_args* a, cnf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K6  mixture-of-logistics categorical encoding (LinearCategoricalEncoding, num_flows = 0)
+ *   (layers/categorical_encoding/linear_encoding.py:59-196, distributions.py:117-163)
+ * table[v] = [bias_v (D) | raw scale_v (D)] = pred_net(embed(v)).
+ * encode: z0 = logit(u (1-1e-4) + 5e-5)/1.81, z = (z0 + b_x) e^{tanh s_x}; exact posterior over
+ *         the V classes; ldj[b] += sum_s pad (beta log q(x|z) - log p(z0) + sum tanh s_x).
+ *         Noise is either supplied (`u_noise`, parity mode) or drawn in-kernel from Philox4x32-10
+ *         keyed by (seed, offset) when u_noise == NULL.
+ * decode: x = argmax_v log p(z|v) + prior_v  (:184-196).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    int64_t B, S;
+    int32_t V, D;
+    const int64_t* tokens;        /* [B,S]   */
+    const float* u_noise;         /* [B,S,D] U(0,1) or NULL */
+    uint64_t seed, offset;        /* Philox key/counter when u_noise == NULL */
+    const float* table;           /* [V,2D]  */
+    const float* category_prior;  /* [V] log-softmaxed */
+    const float* pad;             /* [B,S] or NULL */
+    float beta;
+    float* z_out;                 /* [B,S,D] */
+    float* ldj;                   /* [B] in/out */
+    float* class_prob_log;        /* [B,S] or NULL */
+    uint32_t* status;
+} cnf_categ_encode_args;
+
+CNF_API int cnf_categ_encode(const cnf_categ_encode_args* a, cnf_stream_t stream);
+
+typedef struct {
+    int64_t B, S;
+    int32_t V, D;
+    const float* z;               /* [B,S,D] */
+    const float* table;           /* [V,2D]  */
+    const float* category_prior;  /* [V]     */
+    int64_t* tokens_out;          /* [B,S]   */
+} cnf_categ_decode_args;
+
+CNF_API int cnf_categ_decode(const cnf_categ_decode_args* a, cnf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K7  logistic prior  (layers/flows/distributions.py:129-163)
+ * log_prob: out[b] (+)= sum_{s,c} pad * -(softplus(v) + softplus(-v) + log sigma), v=(x-mu)/sigma
+ *           (`elementwise` != NULL additionally stores the unreduced values).
+ * sample:   x = logit(u (1-eps) + eps/2) sigma + mu, u from `u_noise` or Philox.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    int64_t B, S;
+    int32_t C;
+    const float* x;      /* [B,S,C] */
+    const float* pad;    /* [B,S] or NULL */
+    float mu, sigma;
+    int32_t accumulate;
+    float* out;          /* [B] or NULL */
+    float* elementwise;  /* [B,S,C] or NULL */
+} cnf_logistic_logprob_args;
+
+CNF_API int cnf_logistic_logprob(const cnf_logistic_logprob_args* a, cnf_stream_t stream);
+
+typedef struct {
+    int64_t n;
+    const float* u_noise; /* [n] or NULL */
+    uint64_t seed, offset;
+    float mu, sigma, eps;
+    float* x_out;         /* [n] */
+} cnf_logistic_sample_args;
+
+CNF_API int cnf_logistic_sample(const cnf_logistic_sample_args* a, cnf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Running ldj accumulator helper (layers/flows/flow_model.py:44): y[b] += alpha * x[b] * len[b]
+ * with optional device scalar `alpha_dev` (e.g. sldj); used by the fused block path for the
+ * per-sample constants of ActNorm / InvConv.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    int64_t B;
+    float alpha;
+    const float* alpha_dev; /* [1] or NULL */
+    const float* x;         /* [B] or NULL (-> 1) */
+    const float* length;    /* [B] or NULL (-> 1) */
+    float* y;               /* [B] */
+} cnf_ldj_axpy_args;
+
+CNF_API int cnf_ldj_axpy(const cnf_ldj_axpy_args* a, cnf_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CNF_B200_H */

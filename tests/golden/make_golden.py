@@ -107,14 +107,22 @@ def gold_mixcdf(name, B, S, C, K, *, seed, nn_std=0.5, sf_std=0.0, chess=False, 
          z_rev=z_rev, ldj_rev=ldj_rev, z_lat=z_lat, z_smp=z_smp, ldj_smp=ldj_smp)
 
 
-def gold_mixcdf_tails(name, seed):
+def gold_mixcdf_tails(name, seed, right_tail=False):
     """Extreme inputs: far tails of every component, sharp and wide components (exercises the
-    clamps at mixture_cdf_layer.py:197-198 and the float64 round-off region near CDF -> 1)."""
+    clamps at mixture_cdf_layer.py:197-198).
+
+    Where the CDF exceeds 1 - 1e-13 the reference's own output is round-off noise of the float64
+    `1 - exp(log_cdf)` (its log(1-F) jumps between -36.7 and the -50.66 clamp from one rounding
+    to the next), so there is nothing to pin.  The main fixture therefore moves such elements
+    left until 1 - CDF >= 1e-11; `right_tail=True` keeps them for a sanity-only test."""
+    from layers.flows.mixture_cdf_layer import mixture_log_cdf
     g = torch.Generator().manual_seed(seed)
     B, S, C, K = 2, 24, 4, 4
     z = torch.randn(B, S, C, generator=g) * 12.0
-    z[0, :6] = torch.tensor([60.0, -60.0, 35.0, -35.0])
-    z[1, :4] = torch.tensor([140.0, -140.0, 20.0, -20.0])
+    z[0, 0:6, 2] = torch.tensor([-60.0, -140.0, -300.0, -45.0, -90.0, -35.0])   # transformed channels
+    z[0, 6:12, 3] = torch.tensor([-25.0, -50.0, -75.0, -100.0, -1000.0, -20.0])
+    z[1, 0:6, 2] = torch.tensor([20.0, 35.0, 60.0, 140.0, 25.0, 30.0])
+    z[1, 6:10, 3] = torch.tensor([15.0, 45.0, 90.0, 300.0])
     nn_out = torch.randn(B, S, C * (2 + 3 * K), generator=g) * 2.0
     mask = CouplingLayer.create_channel_mask(C)
     layer = MixtureCDFCoupling(c_in=C, mask=mask, model_func=lambda c_out: _Recorder(nn_out), num_mixtures=K)
@@ -122,6 +130,14 @@ def gold_mixcdf_tails(name, seed):
     layer.mixture_scaling_factor.data = torch.randn(C, K, generator=g) * 0.8
     layer.eval()
     with torch.no_grad():
+        m3 = mask.unsqueeze(0)
+        prm = MixtureCDFCoupling.get_mixt_params(nn_out, m3, K, layer.scaling_factor, layer.mixture_scaling_factor)
+        for _ in range(200):
+            surv = 1.0 - mixture_log_cdf(z.double(), prm[2], prm[3], prm[4]).exp()
+            bad = (surv < 1e-11) & (m3 == 0)
+            if right_tail or not bad.any():
+                break
+            z = torch.where(bad, z - torch.clamp(0.1 * z.abs(), min=0.5), z)
         z_fwd, ldj_fwd, det = layer(z, reverse=False)
     save(name, z=z, nn_out=nn_out, mask=mask, K=K, sf=layer.scaling_factor.data,
          msf=layer.mixture_scaling_factor.data, length=torch.full((B,), S), padded=0,
@@ -405,6 +421,7 @@ if __name__ == "__main__":
     gold_mixcdf("mixcdf_flip_k10", 3, 6, 4, 10, seed=8, flip=True, sf_std=0.4)
     gold_mixcdf("mixcdf_ratio_k3", 2, 5, 5, 3, seed=9, ratio=0.3, z_std=3.0)
     gold_mixcdf_tails("mixcdf_tails", seed=10)
+    gold_mixcdf_tails("mixcdf_right_tail", seed=10, right_tail=True)
     gold_autoregressive(seed=11)
     gold_affine(seed=12)
     gold_actnorm(seed=13)

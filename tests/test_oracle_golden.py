@@ -36,8 +36,9 @@ def test_mixcdf_forward_and_inverse(name):
     assert_close(ls, g.ldj_smp, what="ldj_smp", **TIGHT)
 
 
-def test_mixcdf_tails():
-    g = load_golden("mixcdf_tails")
+@pytest.mark.parametrize("name", ["mixcdf_tails", "mixcdf_right_tail"])
+def test_mixcdf_tails(name):
+    g = load_golden(name)
     m = O.expand_mask(g.mask, g.z)
     z, ldj, _ = O.mixcdf_coupling(g.z, g.nn_out, m, g.K, g.sf, g.msf, training=False)
     assert_close(z, g.z_fwd, what="z", **TIGHT)
