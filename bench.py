@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""bench.py - flow forward + log-det-Jacobian throughput on BASELINE.json's LM configuration.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (configs[1]): tokens [4096, 256] over 51 classes -> mixture-of-logistics encoding (d=16)
+-> 8 x [ActNorm, 1x1 InvertibleConv, MixtureCDFCoupling K=8] -> logistic prior log-prob.  One step =
+one pass of that hot path over one batch; every rank runs its own batch of 4096 (weak scaling) and
+the ranks all-reduce (sum log-likelihood, sample count) once per step.
+
+`value`  kernel-level: coupling-network outputs given as HBM-resident inputs (8 x 1.74 GB, far
+         larger than L2), tokens resident, device-timed with CUDA events.
+`e2e`    module-level: the drop-in FlowModel (stand-in Linear coupling nets evaluated on the
+         device) driven from pinned HOST tokens, H2D copy and D2H read of the per-sample
+         log-likelihood inside the timed region.
+`roofline` the dominant kernel (mixture coupling forward): algorithmic bytes per launch / mean
+         launch duration from CUDA events recorded inside the timed region.
+`cpu_baseline` / `--impl reference`: the CPU oracle (port of the reference's eager fp64 path) on
+         the host cores, on a bounded sub-batch of the same workload.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+import workload as W  # noqa: E402
+
+METRIC = "flow fwd+ldj samples/sec"
+UNIT = "samples/s"
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.proc, self.index = None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = [s for s, p in zip(sm, pw) if p > 0.5 * max(pw)] or sm
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "power_w_max": max(pw),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU arm (oracle port of the reference's eager fp64 path)
+# --------------------------------------------------------------------------------------------------
+def cpu_step(prm, B, seed):
+    tokens, u = W.lm_tokens(B, prm.S, prm.V, seed=seed), W.lm_noise(B, prm.S, prm.D, seed=seed)
+    t0 = time.perf_counter()
+    z, ldj, logp = W.lm_oracle_forward(prm, tokens, u)
+    return time.perf_counter() - t0, W.bits_per_dim(ldj, logp, prm.S)
+
+
+def cpu_pick_batch(prm, steps, budget_s):
+    """Sub-batch so that `steps` CPU steps fit in about `budget_s` seconds (calibrated on B=8)."""
+    cpu_step(prm, 4, 99)
+    dt, _ = cpu_step(prm, 8, 98)
+    per_sample = dt / 8
+    B = 8
+    while B < 512 and 2 * B * per_sample * steps <= budget_s:
+        B *= 2
+    return B
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    torch.set_num_threads(os.cpu_count() or 1)
+    prm = W.data_init_oracle(W.lm_params(seed=0), seed=0)
+    B = cpu_pick_batch(prm, args.steps + args.warmup, budget_s=150.0)
+    for i in range(args.warmup):
+        cpu_step(prm, B, 100 + i)
+    times, bpd = [], None
+    for i in range(args.steps):
+        dt, bpd = cpu_step(prm, B, i)
+        times.append(dt)
+    total = sum(times)
+    value = B * args.steps / total
+    sample = "B=%d of the %d-sample batch per step (S=%d, d=%d, K=%d, %d blocks), eager fp64 oracle port" % (
+        B, W.LM["B"], prm.S, prm.D, prm.K, len(prm.blocks))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.gpus, extra={"cpu_sub_batch": B}),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "bits_per_dim": bpd,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_gpus, extra=None):
+    cfg = {"workload": "language_modeling: synthetic char-level tokens, seq 256, d=16, V=51, 8 x [ActNorm, InvConv1x1, "
+                       "MixtureCDFCoupling K=8], batch 4096 per GPU",
+           "batch_per_gpu": W.LM["B"], "global_batch": W.LM["B"] * n_gpus, "seq_len": W.LM["S"], "d": W.LM["D"],
+           "mixtures": W.LM["K"], "vocab": W.LM["V"], "blocks": W.LM["blocks"], "parallelism": "batch-sharded x%d" % n_gpus,
+           "l2": "inputs larger than L2 (1.74 GB of coupling parameters per layer vs 126 MB L2); no flush needed",
+           "value_leg": "coupling-net outputs given, resident in HBM", "e2e_leg": "drop-in FlowModel, stand-in Linear "
+           "coupling nets, pinned host tokens -> H2D, per-sample log-likelihood -> D2H"}
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+# --------------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------------
+def run_gpu(args, rank, local_rank, world):
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py: no CUDA device - the product path has no CPU fallback "
+                           "(use --impl reference for the CPU arm)")
+    from categoricalnf_b200 import ops
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    distributed = world > 1
+    if distributed:
+        dist.init_process_group("nccl", device_id=dev)
+
+    B, S, D, K, V = (W.LM[k] for k in ("B", "S", "D", "K", "V"))
+    prm = W.lm_params(seed=0)
+    path = W.LMDevicePath(prm, dev).data_init(seed=0)
+    tokens = W.lm_tokens(B, S, V, seed=rank).to(dev)
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    nn_outs = [torch.randn(B, S, D * (2 + 3 * K), device=dev, generator=gen) * 0.5 for _ in prm.blocks]
+    acc = torch.zeros(2, dtype=torch.float64, device=dev)
+
+    def barrier():
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(i, time_mix=False):
+        z, ldj, logp = path.forward(tokens, nn_outs=nn_outs, seed=rank, offset=i * B * S * D, time_mix=time_mix)
+        ll = ldj + logp
+        acc[0] = ll.sum(dtype=torch.float64)
+        acc[1] = float(B)
+        if distributed:
+            dist.all_reduce(acc)
+        return ldj, logp
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    launches0 = ops.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    path.mix_events = []
+    barrier()
+    ev0.record()
+    for i in range(args.steps):
+        ldj, logp = step(args.warmup + i, time_mix=True)
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    launches = ops.launch_count() - launches0
+    mix_ms = [a.elapsed_time(b) for a, b in path.mix_events]
+    bpd_gpu = W.bits_per_dim(ldj, logp, S)
+    ops.check_status(dev, "bench value leg")
+
+    # ---- e2e: module API from pinned host tokens -------------------------------------------------
+    del nn_outs
+    torch.cuda.empty_cache()
+    model, prior = W.build_lm_model(prm, dev)
+    host_tokens = [W.lm_tokens(B, S, V, seed=10 * rank + j).pin_memory() for j in range(2)]
+    host_ll = torch.empty(B, dtype=torch.float32).pin_memory()
+
+    def e2e_step(i):
+        with torch.no_grad():
+            tok = host_tokens[i % 2].to(dev, non_blocking=True)
+            z, ldj = model(tok)
+            logp, _ = ops.logistic_logprob(z)
+            ll = ldj + logp
+            if distributed:
+                acc[0] = ll.sum(dtype=torch.float64)
+                acc[1] = float(B)
+                dist.all_reduce(acc)
+            host_ll.copy_(ll, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+    for i in range(args.warmup):
+        e2e_step(i)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        e2e_step(i)
+    e1.record()
+    barrier()
+    e2e_ms_total = e0.elapsed_time(e1)
+    clk = clocks.stop() if rank == 0 else None
+
+    # ---- max over ranks ---------------------------------------------------------------------------
+    t = torch.tensor([ms_total, e2e_ms_total, sum(mix_ms) / max(1, len(mix_ms))], dtype=torch.float64, device=dev)
+    if distributed:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms_total, mix_ms_mean = (float(x) for x in t.tolist())
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        ms_step = ms_total / args.steps
+        value = B * world * args.steps / (ms_total * 1e-3)
+        e2e_value = B * world * args.steps / (e2e_ms_total * 1e-3)
+        Ct = D - D // 2
+        alg_bytes = B * S * (4 * D + 4 * D + 4 * Ct * (2 + 3 * K))     # 960 B / position
+        achieved = alg_bytes / (mix_ms_mean * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(world),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * S * 8, "d2h_bytes_per_step": B * 4,
+                    "ms_per_step": e2e_ms_total / args.steps},
+            "gpu_launches": launches,
+            "roofline": {"kernel": "mixcdf_kernel<8,false> (cnf_mixcdf_fwd)", "bound": "hbm", "achieved": achieved,
+                         "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(),
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+                         "mean_launch_ms": mix_ms_mean, "launches_timed": len(mix_ms),
+                         "share_of_step": mix_ms_mean * len(prm.blocks) / ms_step},
+            "clocks": clk, "bits_per_dim": bpd_gpu,
+        }
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline(prm)
+        print(json.dumps(line), flush=True)
+    if distributed:
+        dist.destroy_process_group()
+
+
+def ncu_traffic():
+    """dram bytes read+written per mixture-coupling launch from the committed ncu --set full capture
+    (profiles/*.json written by tools/ncu_summary.py), or None."""
+    path = os.path.join(ROOT, "profiles", "mixcdf_fwd_traffic.json")
+    if os.path.exists(path):
+        try:
+            with open(path) as f:
+                return float(json.load(f)["dram_bytes_per_launch"])
+        except (ValueError, KeyError):
+            return None
+    return None
+
+
+def cpu_baseline(prm):
+    """Oracle port on the host cores, on a bounded sub-batch (about 10-30 s of CPU work)."""
+    torch.set_num_threads(os.cpu_count() or 1)
+    B = cpu_pick_batch(prm, 1, budget_s=20.0)
+    dt, bpd = cpu_step(prm, B, 0)
+    return {"value": B / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": "one step at B=%d of the %d-sample batch (S=%d, d=%d, K=%d, %d blocks, stand-in Linear nets), "
+                      "eager fp64 oracle port, %.1f s" % (B, W.LM["B"], prm.S, prm.D, prm.K, len(prm.blocks), dt),
+            "bits_per_dim": bpd}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    rank, local_rank, world = env_int("RANK", 0), env_int("LOCAL_RANK", 0), env_int("WORLD_SIZE", 1)
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world == 1 and args.gpus > 1:
+        # plain `python bench.py --gpus N`: re-launch under torchrun, one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__),
+               "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup)]
+        sys.exit(subprocess.call(cmd))
+    run_gpu(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

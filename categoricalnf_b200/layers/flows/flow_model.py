@@ -1,0 +1,133 @@
+"""Ordered container of flow layers with the running log-det-Jacobian accumulator
+(reference layers/flows/flow_model.py:9-146).
+
+Calling convention kept from the reference: every layer is invoked as
+``layer(z, reverse=..., get_ldj_per_layer=..., **kwargs)`` *without* the running ldj (:34) and
+returns its own contribution, which is added here (:44).  The reference synchronises with the
+host once per layer for its NaN assert (:42); the kernels instead OR health bits into a device
+status word that is read once per call (``ops.check_status``), raising the same AssertionError.
+"""
+import torch
+import torch.nn as nn
+
+from ... import ops
+
+
+class FlowModel(nn.Module):
+
+    def __init__(self, layers=None, name="Flow model"):
+        super().__init__()
+        self.flow_layers = nn.ModuleList()
+        self.name = name
+        if layers is not None:
+            self.add_layers(layers)
+
+    def add_layers(self, layers):
+        for layer in layers:
+            self.flow_layers.append(layer)
+        self.print_overview()
+
+    def forward(self, z, ldj=None, reverse=False, get_ldj_per_layer=False, check_nan=True, **kwargs):
+        if ldj is None:
+            ldj = z.new_zeros(z.size(0), dtype=torch.float32)
+        order = list(enumerate(self.flow_layers))
+        if reverse:
+            order.reverse()
+        ldj_per_layer = []
+        for index, layer in order:
+            res = layer(z, reverse=reverse, get_ldj_per_layer=get_ldj_per_layer, **kwargs)
+            if len(res) == 2:
+                z, layer_ldj = res
+                detail = layer_ldj
+            elif len(res) == 3:
+                z, layer_ldj, detail = res
+            else:
+                raise ValueError("[!] ERROR: Got more return values than expected: %i (layer %i)" % (len(res), index + 1))
+            ldj = ldj + layer_ldj
+            if isinstance(detail, list):
+                ldj_per_layer += detail
+            else:
+                ldj_per_layer.append(detail)
+        if check_nan and z.is_cuda:
+            # one lazy host read for the whole stack instead of one assert per layer (:42)
+            ops.check_status(z.device, where=self.name)
+        if get_ldj_per_layer:
+            return z, ldj, ldj_per_layer
+        return z, ldj
+
+    def reverse(self, z):
+        # upstream passes the bound method as ldj here (App. B #6); the intent is plain inversion
+        return self.forward(z, reverse=True)
+
+    def test_reversibility(self, z, **kwargs):
+        """Forward then inverse of every layer; prints which layers do not reproduce their input
+        exactly (:60-78).  Returns True when all layers reproduced bit-exactly."""
+        failed = False
+        for index, layer in enumerate(self.flow_layers):
+            z_fwd, ldj_fwd = layer(z, reverse=False, **kwargs)[:2]
+            z_rec, ldj_rec = layer(z_fwd, reverse=True, **kwargs)[:2]
+            if (z_fwd - z_rec).abs().sum() != 0 or (ldj_fwd + ldj_rec).abs().sum() != 0:
+                print("-" * 100)
+                print("[!] WARNING: Reversibility check failed for layer index %i" % index)
+                print(layer.info())
+                print("-" * 100)
+                failed = True
+        print("+" * 100)
+        print("Reversibility test %s (tested %i layers)" % ("failed" if failed else "succeeded", len(self.flow_layers)))
+        print("+" * 100)
+        return not failed
+
+    def get_inner_activations(self, z, reverse=False, return_names=False, **kwargs):
+        outs, names = [z.detach()], []
+        for layer in (reversed(self.flow_layers) if reverse else self.flow_layers):
+            z = layer(z, reverse=reverse, **kwargs)[0]
+            outs.append(z.detach())
+            names.append(layer.__class__.__name__)
+        return (outs, names) if return_names else outs
+
+    # -- data-dependent initialisation (:95-135) ----------------------------------------------------
+    def initialize_data_dependent(self, batch_list):
+        """``batch_list``: list of ``(z, kwargs)`` tuples, pushed through the stack layer by layer."""
+        with torch.no_grad():
+            for index, layer in enumerate(self.flow_layers):
+                print("Processing layer %i..." % (index + 1), end="\r")
+                batch_list = FlowModel.run_data_init_layer(batch_list, layer)
+
+    @staticmethod
+    def run_data_init_layer(batch_list, layer):
+        multi_input = isinstance(batch_list[0][0], (tuple, list))
+        if layer.need_data_init():
+            merged = {}
+            for key in batch_list[0][1].keys():
+                vals = [b[1][key] for b in batch_list]
+                merged[key] = torch.cat(vals, dim=0) if isinstance(vals[0], torch.Tensor) else vals[0]
+            if not multi_input:
+                layer.data_init_forward(torch.cat([z for z, _ in batch_list], dim=0), **merged)
+            else:
+                n_in = len(batch_list[0][0])
+                layer.data_init_forward(*[torch.cat([z[i] for z, _ in batch_list], dim=0) for i in range(n_in)],
+                                        **merged)
+        outs = []
+        for z, kwargs in batch_list:
+            if isinstance(z, (tuple, list)):
+                res = layer(*z, reverse=False, **kwargs)
+                cur = [e.detach() for e in res[:-1] if isinstance(e, torch.Tensor)]
+                if len(res) == 4 and isinstance(res[-1], dict):
+                    kwargs.update(res[-1])
+                    cur = cur[:-1]
+                outs.append(cur)
+            else:
+                outs.append(layer(z, reverse=False, **kwargs)[0].detach())
+        return [(outs[i], batch_list[i][1]) for i in range(len(batch_list))]
+
+    def need_data_init(self):
+        return any(flow.need_data_init() for flow in self.flow_layers)
+
+    def print_overview(self):
+        lines = ["(%2i) %s" % (i + 1, layer.info()) for i, layer in enumerate(self.flow_layers)]
+        width = max([20] + [len(s) for s in "\n".join(lines).split("\n")])
+        print("=" * width)
+        print("%s with %i flows" % (self.name, len(self.flow_layers)))
+        print("-" * width)
+        print("\n".join(lines))
+        print("=" * width)
