@@ -1,0 +1,365 @@
+// Element-level arithmetic of the logistic-mixture-CDF coupling (shared by the generic and the
+// TMA-pipelined kernels).  Restates mixture_cdf_layer.py:95-142, 197-276 of the reference:
+// fp32 fast path with MUFU ex2/lg2/rcp, float64 restatement for the rare elements whose CDF leaves
+// the range where fp32 reproduces the reference's float64 arithmetic to 1e-4.
+#pragma once
+#include "cnf_common.cuh"
+
+namespace cnf {
+namespace mixmath {
+
+// Mixture parameters of one element, as staged in shared memory.
+struct ElemCtx {
+    const float* rec;   // [t, log_s, log_pi[K], mu[K], raw_log_scale[K]]
+    const float* mfac;  // [K] e^{msf}
+    const float* ma2;   // [K] 2 log2(e) / max(e^{msf}, 1)
+    float fac, a2;      // same for the output log-scale
+    int K;
+    bool pre;           // log-scales are already bounded: skip the tanh
+};
+
+struct MixEval {
+    float F, G, f;  // CDF, 1-CDF, PDF (fast path, linear domain)
+};
+
+// ------------------------------------------------------------------------------------------------
+// fp32 evaluation of CDF / survival / density of the mixture at x.
+// sigma_k = sigmoid(u_k) is formed from e = exp(-|u_k|), r = 1/(1+e): sigma = r or e r, so neither
+// tail cancels; weights are softmax numerators normalised once at the end.
+// ------------------------------------------------------------------------------------------------
+template <int KT>
+__device__ __forceinline__ MixEval mix_eval(float x, const ElemCtx& c, float m_l2) {
+    const int K = KT > 0 ? KT : c.K;
+    const float* lp = c.rec + 2;
+    const float* mu = lp + K;
+    const float* ms = mu + K;
+    float W = 0.f, Fs = 0.f, Gs = 0.f, fs = 0.f;
+#pragma unroll(KT > 0 ? KT : 4)
+    for (int k = 0; k < K; ++k) {
+        const float ls = c.pre ? ms[k] : tanh_from_2log2e(ms[k] * c.ma2[k]) * c.mfac[k];
+        const float einv = ex2(-ls * kLog2e);  // exp(-log_scale)
+        const float u = (x - mu[k]) * einv;
+        const float e = ex2(-fabsf(u) * kLog2e);
+        const float r = rcp(1.0f + e);
+        const float q = e * r;  // min(sigma, 1 - sigma)
+        const bool pos = u >= 0.0f;
+        const float w = ex2(fmaf(lp[k], kLog2e, -m_l2));
+        W += w;
+        Fs = fmaf(w, pos ? r : q, Fs);
+        Gs = fmaf(w, pos ? q : r, Gs);
+        fs = fmaf(w * (q * r), einv, fs);
+    }
+    const float iw = rcp(W);
+    MixEval o;
+    o.F = Fs * iw;
+    o.G = Gs * iw;
+    o.f = fs * iw;
+    return o;
+}
+
+template <int KT>
+__device__ __forceinline__ float logit_max_l2(const ElemCtx& c) {
+    const int K = KT > 0 ? KT : c.K;
+    const float* lp = c.rec + 2;
+    float m = lp[0];
+#pragma unroll(KT > 0 ? KT : 4)
+    for (int k = 1; k < K; ++k) m = fmaxf(m, lp[k]);
+    return m * kLog2e;
+}
+
+// ------------------------------------------------------------------------------------------------
+// float64 restatement of the reference formulas (mixture_cdf_layer.py:201-232, 267-276) for the
+// rare elements outside the fp32-safe range.  Parameters are bounded in fp32 first, exactly as
+// get_mixt_params does before its .double() (:157-178).
+// ------------------------------------------------------------------------------------------------
+struct SlowOut {
+    double log_cdf, log_pdf;
+};
+
+static __device__ __noinline__ SlowOut mix_eval_f64(double x, const float* rec, const float* mfac, int K) {
+    const float* lp = rec + 2;
+    const float* mu = lp + K;
+    const float* ms = mu + K;
+    float m = lp[0];
+    for (int k = 1; k < K; ++k) m = fmaxf(m, lp[k]);
+    double se = 0.0;
+    for (int k = 0; k < K; ++k) se += exp((double)lp[k] - (double)m);
+    const double lse = (double)m + log(se);
+    double amax = -INFINITY, asum = 0.0, bmax = -INFINITY, bsum = 0.0;
+    for (int k = 0; k < K; ++k) {
+        const float fk = mfac ? mfac[k] : 1.0f;
+        const double ls = mfac ? (double)(tanhf(ms[k] / fmaxf(fk, 1.0f)) * fk) : (double)ms[k];
+        const double u = (x - (double)mu[k]) * exp(-ls);
+        const double lpi = (double)lp[k] - lse;
+        const double a = lpi + (fmin(u, 0.0) - log1p(exp(-fabs(u))));   // log_pi + logsigmoid(u)
+        const double sp = u > 20.0 ? u : log1p(exp(u));                  // F.softplus, threshold 20
+        const double b = lpi + u - ls - 2.0 * sp;
+        if (a > amax) { asum = asum * exp(amax - a) + 1.0; amax = a; } else { asum += exp(a - amax); }
+        if (b > bmax) { bsum = bsum * exp(bmax - b) + 1.0; bmax = b; } else { bsum += exp(b - bmax); }
+    }
+    SlowOut o;
+    o.log_cdf = amax + log(asum);
+    o.log_pdf = bmax + log(bsum);
+    return o;
+}
+
+struct ElemResult {
+    float z;    // transformed value
+    float ldj;  // log_s + mixt_ldj + log f (+ reg * reg_factor), sign already applied for reverse
+    float reg;  // CDF regulariser term (forward, training)
+};
+
+static __device__ __noinline__ ElemResult mix_forward_f64(float x, const float* rec, const float* mfac, int K, float log_s,
+                                                   bool use_reg, float reg_max, float reg_factor) {
+    const SlowOut s = mix_eval_f64((double)x, rec, mfac, K);
+    const double F = exp(s.log_cdf);
+    const double lF = log(fmax(F, 1e-22)), lG = log(fmax(1.0 - F, 1e-22));
+    const double y = -log(fmax(1.0 / F - 1.0, 1e-22));
+    double reg = 0.0;
+    if (use_reg) {
+        const double il10 = 1.0 / log(10.0);
+        reg = (fmin(lF * il10, -(double)reg_max) + (double)reg_max) + (fmin(lG * il10, -(double)reg_max) + (double)reg_max);
+    }
+    ElemResult r;
+    r.z = (float)((y + (double)rec[0]) * exp((double)log_s));
+    r.ldj = (float)((double)log_s - lF - lG + s.log_pdf + reg * (double)reg_factor);
+    r.reg = (float)reg;
+    return r;
+}
+
+template <int KT>
+__device__ __forceinline__ ElemResult mix_forward_elem(float x, const ElemCtx& c, bool use_reg, float reg_max,
+                                                       float reg_factor) {
+    const float log_s = c.pre ? c.rec[1] : tanh_from_2log2e(c.rec[1] * c.a2) * c.fac;
+    const float m_l2 = logit_max_l2<KT>(c);
+    const MixEval e = mix_eval<KT>(x, c, m_l2);
+    // fp32 is trusted while F, 1-F and f are far from underflow and 1-F is not in the region
+    // where the reference's own float64 `1/F - 1` loses digits; NaNs fail the test as well.
+    if (!(e.F >= 1e-30f && e.G >= 1e-12f && e.f >= 1e-30f)) {
+        return mix_forward_f64(x, c.rec, c.pre ? nullptr : c.mfac, KT > 0 ? KT : c.K, log_s, use_reg, reg_max, reg_factor);
+    }
+    const float lF = fast_log(e.F), lG = fast_log(e.G);
+    const float lFc = fmaxf(lF, kLog1em22), lGc = fmaxf(lG, kLog1em22);
+    ElemResult r;
+    r.reg = 0.f;
+    if (use_reg) r.reg = (fminf(lFc * kInvLn10, -reg_max) + reg_max) + (fminf(lGc * kInvLn10, -reg_max) + reg_max);
+    r.z = (lF - lG + c.rec[0]) * fast_exp(log_s);
+    r.ldj = log_s - lFc - lGc + fast_log(e.f) + r.reg * reg_factor;
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Inverse: y -> F = clamp(sigmoid y) -> x = CDF^-1(F) by bisection (mixture_cdf_layer.py:124-136,
+// 235-264).  The reference bisects every element in float64 until the batch-wide max step is
+// <= 1e-10 (~45 halvings, one host sync each).  Here each element bisects in fp32 registers from
+// the same start (x = 0) and bracket until its bracket stops shrinking.  Where the CDF is so flat
+// that fp32 evaluation error would move the root by more than the parity tolerance
+// (min(F, 1-F) / f large), the element is finished in float64 with a bracketed Newton iteration,
+// which converges to the root the reference's float64 bisection approaches.
+// ------------------------------------------------------------------------------------------------
+static __device__ __noinline__ ElemResult mix_inverse_f64(float zin, float x0, float margin, const float* rec,
+                                                   const float* mfac, int K, float log_s, float lb0, float ub0) {
+    const double y = (double)zin * exp(-(double)log_s) - (double)rec[0];
+    double target = 1.0 / (1.0 + exp(-y));
+    target = fmin(fmax(target, 1e-5), 1.0 - 1e-5);
+    const double mixt_ldj = fabs(y) + 2.0 * log1p(exp(-fabs(y)));
+    double x = (double)x0, lo = fmax((double)lb0, x - (double)margin), hi = fmin((double)ub0, x + (double)margin);
+    SlowOut s = mix_eval_f64(x, rec, mfac, K);
+    for (int it = 0; it < 12; ++it) {
+        const double Fx = exp(s.log_cdf);
+        if (Fx > target) hi = x; else lo = x;
+        double xn = x - (Fx - target) * exp(-s.log_pdf);
+        if (!(xn > lo && xn < hi)) xn = 0.5 * (lo + hi);
+        const bool done = fabs(xn - x) <= 1e-11 * fmax(1.0, fabs(x));
+        x = xn;
+        s = mix_eval_f64(x, rec, mfac, K);
+        if (done) break;
+    }
+    ElemResult r;
+    r.z = (float)x;
+    r.ldj = (float)(-((double)log_s + mixt_ldj + s.log_pdf));
+    r.reg = 0.f;
+    return r;
+}
+
+template <int KT>
+__device__ __forceinline__ ElemResult mix_inverse_elem(float zin, const ElemCtx& c, uint32_t* status) {
+    const int K = KT > 0 ? KT : c.K;
+    const float log_s = c.pre ? c.rec[1] : tanh_from_2log2e(c.rec[1] * c.a2) * c.fac;
+    const float y = fmaf(zin, fast_exp(-log_s), -c.rec[0]);
+    const float mixt_ldj = softplus_pm(y);
+    // sigmoid in a form that keeps both tails, then the reference clamp to [1e-5, 1-1e-5] (:130)
+    const float ey = ex2(-fabsf(y) * kLog2e);
+    const float ry = rcp(1.0f + ey);
+    float Ft = y >= 0.f ? ry : ey * ry;  // target CDF
+    float Gt = y >= 0.f ? ey * ry : ry;  // 1 - target
+    if (!(Ft == Ft)) flag(status, CNF_FLAG_CDF_RANGE);
+    Ft = fminf(fmaxf(Ft, 1e-5f), 1.0f - 1e-5f);
+    Gt = fminf(fmaxf(Gt, 1e-5f), 1.0f - 1e-5f);
+    const bool upper = Ft > 0.5f;  // compare on the smaller of F and 1-F: relative accuracy in both tails
+
+    // bracket (mixture_cdf_layer.py:252-254)
+    const float* lp = c.rec + 2;
+    const float* mu = lp + K;
+    const float* ms = mu + K;
+    float span = 0.f;
+#pragma unroll(KT > 0 ? KT : 4)
+    for (int k = 0; k < K; ++k) span += fast_exp(c.pre ? ms[k] : tanh_from_2log2e(ms[k] * c.ma2[k]) * c.mfac[k]);
+    float lb = INFINITY, ub = -INFINITY;
+#pragma unroll(KT > 0 ? KT : 4)
+    for (int k = 0; k < K; ++k) {
+        lb = fminf(lb, fmaf(-20.f, span, mu[k]));
+        ub = fmaxf(ub, fmaf(20.f, span, mu[k]));
+    }
+    const float lb0 = lb, ub0 = ub;
+    const float m_l2 = logit_max_l2<KT>(c);
+    float x = 0.f;
+    MixEval e = mix_eval<KT>(x, c, m_l2);
+    for (int it = 0; it < 48; ++it) {
+        const bool gt = upper ? (e.G < Gt) : (e.F > Ft);
+        if (gt) ub = x; else lb = x;
+        const float xn = 0.5f * (lb + ub);
+        const bool done = (xn == x) || !(ub - lb > 5e-7f * fmaxf(1.0f, fabsf(xn)));
+        x = xn;
+        e = mix_eval<KT>(x, c, m_l2);
+        if (done) break;
+    }
+    // fp32 CDF values carry ~5e-7 relative error -> root error ~5e-7 min(F,G)/f
+    const float cond = fminf(e.F, e.G);
+    if (!(cond <= 8.0f * fmaxf(1.0f, fabsf(x)) * e.f) || !(e.f >= 1e-30f)) {
+        const float margin = fmaxf(4.0f * (ub - lb) + 1e-5f * fmaxf(1.0f, fabsf(x)), 1e-5f * cond / fmaxf(e.f, 1e-37f));
+        return mix_inverse_f64(zin, x, margin, c.rec, c.pre ? nullptr : c.mfac, K, log_s, lb0, ub0);
+    }
+    ElemResult r;
+    r.z = x;
+    r.ldj = -(log_s + mixt_ldj + fast_log(e.f));
+    r.reg = 0.f;
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// "Prepared" form for compile-time K: everything that depends on the parameters only (bounded
+// log-scales -> e^{-ls}, softmax numerators, their normaliser) is computed once per element and
+// held in registers; an evaluation at x then costs 2 MUFU per component (one sigmoid).  The
+// forward transform evaluates once, the inverse up to ~49 times, so this is what keeps the
+// bisection loop free of parameter work.  Same operations in the same order as mix_eval above.
+// ------------------------------------------------------------------------------------------------
+template <int KT>
+struct MixPrep {
+    float mu[KT], einv[KT], w[KT];
+    float iw, t, log_s;
+    float span;  // sum_k e^{ls_k}, inverse only (bracket of the bisection)
+};
+
+template <int KT, bool WANT_SPAN>
+__device__ __forceinline__ void mix_prepare(MixPrep<KT>& P, const float* rec, const float* mfac, const float* ma2,
+                                            float fac, float a2, bool pre) {
+    const float* lp = rec + 2;
+    const float* mu = lp + KT;
+    const float* ms = mu + KT;
+    float m = lp[0];
+#pragma unroll
+    for (int k = 1; k < KT; ++k) m = fmaxf(m, lp[k]);
+    const float m_l2 = m * kLog2e;
+    float W = 0.f, span = 0.f;
+#pragma unroll
+    for (int k = 0; k < KT; ++k) {
+        const float ls = pre ? ms[k] : tanh_from_2log2e(ms[k] * ma2[k]) * mfac[k];
+        P.einv[k] = ex2(-ls * kLog2e);
+        if (WANT_SPAN) span += fast_exp(ls);
+        P.mu[k] = mu[k];
+        P.w[k] = ex2(fmaf(lp[k], kLog2e, -m_l2));
+        W += P.w[k];
+    }
+    P.iw = rcp(W);
+    P.span = span;
+    P.t = rec[0];
+    P.log_s = pre ? rec[1] : tanh_from_2log2e(rec[1] * a2) * fac;
+}
+
+template <int KT>
+__device__ __forceinline__ MixEval mix_eval_p(float x, const MixPrep<KT>& P) {
+    float Fs = 0.f, Gs = 0.f, fs = 0.f;
+#pragma unroll
+    for (int k = 0; k < KT; ++k) {
+        const float u = (x - P.mu[k]) * P.einv[k];
+        const float e = ex2(-fabsf(u) * kLog2e);
+        const float r = rcp(1.0f + e);
+        const float q = e * r;  // min(sigma, 1 - sigma)
+        const bool pos = u >= 0.0f;
+        Fs = fmaf(P.w[k], pos ? r : q, Fs);
+        Gs = fmaf(P.w[k], pos ? q : r, Gs);
+        fs = fmaf(P.w[k] * (q * r), P.einv[k], fs);
+    }
+    MixEval o;
+    o.F = Fs * P.iw;
+    o.G = Gs * P.iw;
+    o.f = fs * P.iw;
+    return o;
+}
+
+// `rec_slow` / `mfac_slow`: where the float64 path can re-read the record and the per-channel
+// bounds (global / shared memory; only touched by the rare slow elements).
+template <int KT>
+__device__ __forceinline__ ElemResult mix_forward_p(float x, const MixPrep<KT>& P, const float* rec_slow,
+                                                    const float* mfac_slow, bool use_reg, float reg_max,
+                                                    float reg_factor) {
+    const MixEval e = mix_eval_p<KT>(x, P);
+    if (!(e.F >= 1e-30f && e.G >= 1e-12f && e.f >= 1e-30f))
+        return mix_forward_f64(x, rec_slow, mfac_slow, KT, P.log_s, use_reg, reg_max, reg_factor);
+    const float lF = fast_log(e.F), lG = fast_log(e.G);
+    const float lFc = fmaxf(lF, kLog1em22), lGc = fmaxf(lG, kLog1em22);
+    ElemResult r;
+    r.reg = 0.f;
+    if (use_reg) r.reg = (fminf(lFc * kInvLn10, -reg_max) + reg_max) + (fminf(lGc * kInvLn10, -reg_max) + reg_max);
+    r.z = (lF - lG + P.t) * fast_exp(P.log_s);
+    r.ldj = P.log_s - lFc - lGc + fast_log(e.f) + r.reg * reg_factor;
+    return r;
+}
+
+template <int KT>
+__device__ __forceinline__ ElemResult mix_inverse_p(float zin, const MixPrep<KT>& P, const float* rec_slow,
+                                                    const float* mfac_slow, uint32_t* status) {
+    const float log_s = P.log_s;
+    const float y = fmaf(zin, fast_exp(-log_s), -P.t);
+    const float mixt_ldj = softplus_pm(y);
+    const float ey = ex2(-fabsf(y) * kLog2e);
+    const float ry = rcp(1.0f + ey);
+    float Ft = y >= 0.f ? ry : ey * ry;  // target CDF
+    float Gt = y >= 0.f ? ey * ry : ry;  // 1 - target
+    if (!(Ft == Ft)) flag(status, CNF_FLAG_CDF_RANGE);
+    Ft = fminf(fmaxf(Ft, 1e-5f), 1.0f - 1e-5f);
+    Gt = fminf(fmaxf(Gt, 1e-5f), 1.0f - 1e-5f);
+    const bool upper = Ft > 0.5f;
+    float lb = INFINITY, ub = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < KT; ++k) {
+        lb = fminf(lb, fmaf(-20.f, P.span, P.mu[k]));
+        ub = fmaxf(ub, fmaf(20.f, P.span, P.mu[k]));
+    }
+    const float lb0 = lb, ub0 = ub;
+    float x = 0.f;
+    MixEval e = mix_eval_p<KT>(x, P);
+    for (int it = 0; it < 48; ++it) {
+        const bool gt = upper ? (e.G < Gt) : (e.F > Ft);
+        if (gt) ub = x; else lb = x;
+        const float xn = 0.5f * (lb + ub);
+        const bool done = (xn == x) || !(ub - lb > 5e-7f * fmaxf(1.0f, fabsf(xn)));
+        x = xn;
+        e = mix_eval_p<KT>(x, P);
+        if (done) break;
+    }
+    const float cond = fminf(e.F, e.G);
+    if (!(cond <= 8.0f * fmaxf(1.0f, fabsf(x)) * e.f) || !(e.f >= 1e-30f)) {
+        const float margin = fmaxf(4.0f * (ub - lb) + 1e-5f * fmaxf(1.0f, fabsf(x)), 1e-5f * cond / fmaxf(e.f, 1e-37f));
+        return mix_inverse_f64(zin, x, margin, rec_slow, mfac_slow, KT, log_s, lb0, ub0);
+    }
+    ElemResult r;
+    r.z = x;
+    r.ldj = -(log_s + mixt_ldj + fast_log(e.f));
+    r.reg = 0.f;
+    return r;
+}
+
+}  // namespace mixmath
+}  // namespace cnf

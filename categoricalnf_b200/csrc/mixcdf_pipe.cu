@@ -1,0 +1,337 @@
+// K1 / K2 fast path: persistent, warp-specialised, TMA-fed logistic-mixture-CDF coupling kernel.
+//
+// Same arithmetic as mixcdf.cu (mixcdf_math.cuh; reference mixture_cdf_layer.py:95-142,145-180),
+// different data movement, for the common layout where the transformed channels of a position form
+// one 16-byte aligned run of the network output (every channel mask of create_channel_mask with
+// even K, chess masks):
+//
+//   grid      2 persistent CTAs per SM, each owning a contiguous range of position tiles
+//   producer  one warp; per tile each lane issues one bulk-async copy (TMA engine,
+//             cp.async.bulk ... mbarrier::complete_tx) of a position's parameter run - only the
+//             transformed channels are ever read from HBM - plus one copy of the tile's z rows,
+//             into a ring of shared-memory stages guarded by full/empty mbarriers
+//   consumers 8 warps, one thread per (position, transformed channel): the 2+3K record is pulled
+//             from shared memory into registers with 8-byte loads (bank-conflict free for the
+//             208-float row pitch), the stage is released immediately, then the element is
+//             evaluated in fp32 (MUFU ex2/lg2/rcp) with the float64 escape for extreme tails
+//   outputs   z rows are written straight from registers as full 32-byte sectors; the ldj is
+//             reduced over a position's channels with shuffles and accumulated per warp across
+//             consecutive tiles of the same sample -> about one global atomic per (warp, sample)
+// There is no CTA-wide barrier in the steady state.
+#include "cnf_common.cuh"
+#include "mixcdf_math.cuh"
+
+namespace cnf {
+namespace {
+using namespace mixmath;
+
+constexpr int kConsumerWarps = 8;
+constexpr int kConsumers = kConsumerWarps * 32;
+constexpr int kThreadsPipe = kConsumers + 32;
+
+struct PipeParams {
+    const float* z;
+    const float* nn;
+    const float* pad;
+    const float* sf;
+    const float* msf;
+    float* z_out;
+    float* ldj;
+    float* reg_ldj;
+    uint32_t* status;
+    long long P;       // positions
+    long long ntiles;
+    int S, C, c0;      // c0: first transformed channel
+    int s_period;
+    unsigned long long cond_s;
+    float reg_max, reg_factor;
+    int use_reg, pre;
+};
+
+// ---- mbarrier / bulk-copy primitives (sm_90+; SASS: SYNCS.*, UBLKCP) ------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+template <int KT>
+constexpr int stages_for() { return KT >= 16 ? 2 : 3; }
+
+template <int KT, int CT, bool REV>
+__global__ void __launch_bounds__(kThreadsPipe, 2) mixcdf_pipe_kernel(const PipeParams p) {
+    constexpr int kStages = stages_for<KT>();
+    constexpr int PN = 2 + 3 * KT;
+    constexpr int L = CT * PN;            // parameter floats per position (transformed channels)
+    constexpr int TP = kConsumers / CT;   // positions per tile
+    constexpr int RW = 32 / CT;           // positions per warp
+    static_assert(kConsumers % CT == 0 && 32 % CT == 0, "CT must divide the warp size");
+    static_assert(PN % 2 == 0, "records are read with 8-byte loads");
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int C = p.C;
+    const int zrow = TP * C;                                      // floats of one z tile
+    float* s_par = reinterpret_cast<float*>(smem_raw);            // [kStages][TP * L]
+    float* s_z = s_par + kStages * TP * L;                        // [kStages][TP * C]
+    float* s_mfac = s_z + kStages * zrow;                         // [CT * KT]  e^{msf} (float64 escape only)
+    uint64_t* full = reinterpret_cast<uint64_t*>(s_mfac + CT * KT + ((CT * KT) & 1));
+    uint64_t* empty = full + kStages;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long t0 = (p.ntiles * (long long)blockIdx.x) / gridDim.x;
+    const long long t1 = (p.ntiles * (long long)(blockIdx.x + 1)) / gridDim.x;
+
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], kConsumerWarps);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < CT * KT; i += kThreadsPipe)
+        s_mfac[i] = p.msf ? expf(p.msf[(p.c0 + i / KT) * KT + i % KT]) : 1.0f;
+    __syncthreads();
+
+    if (warp == kConsumerWarps) {
+        // ---------------- producer warp ------------------------------------------------------------
+        int stage = 0;
+        uint32_t phase = 0;
+        for (long long t = t0; t < t1; ++t) {
+            mbar_wait(&empty[stage], phase ^ 1u);
+            const long long pos0 = t * TP;
+            const int rows = (int)min((long long)TP, p.P - pos0);
+            if (lane == 0) mbar_arrive_expect_tx(&full[stage], (uint32_t)(rows * (L + C) * 4));
+            __syncwarp();
+            float* dpar = s_par + stage * (TP * L);
+            for (int r = lane; r < rows; r += 32)
+                bulk_g2s(dpar + r * L, p.nn + ((pos0 + r) * C + p.c0) * (long long)PN, L * 4, &full[stage]);
+            if (lane == 0) bulk_g2s(s_z + stage * zrow, p.z + pos0 * C, (uint32_t)(rows * C * 4), &full[stage]);
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+        return;
+    }
+
+    // ---------------- consumer warps: thread = (position r, transformed channel j) -----------------
+    const int r = tid / CT, j = tid % CT;
+    const int ch = p.c0 + j;
+    // per-channel tanh bounds live in registers for the whole kernel (mixture_cdf_layer.py:157-162)
+    float mfac[KT], ma2[KT];
+#pragma unroll
+    for (int k = 0; k < KT; ++k) {
+        mfac[k] = s_mfac[j * KT + k];
+        ma2[k] = 2.0f * kLog2e / fmaxf(mfac[k], 1.0f);
+    }
+    const float fac = p.sf ? expf(p.sf[ch]) : 1.0f;
+    const float a2 = 2.0f * kLog2e / fmaxf(fac, 1.0f);
+    const bool pre = p.pre != 0, use_reg = p.use_reg != 0;
+
+    // running per-warp ldj accumulator over consecutive positions of one sample
+    long long cur_b = -1;
+    float acc = 0.f, acc_reg = 0.f;
+    // (sample, position-in-sample) of this warp's first position in the current tile
+    const long long wpos0 = t0 * TP + warp * RW;
+    long long wb = wpos0 / p.S;
+    int ws = (int)(wpos0 - wb * p.S);
+
+    int stage = 0;
+    uint32_t phase = 0;
+    for (long long t = t0; t < t1; ++t) {
+        const long long pos0 = t * TP;
+        const int rows = (int)min((long long)TP, p.P - pos0);
+        const long long pos = pos0 + r;
+        const bool valid = r < rows;
+        mbar_wait(&full[stage], phase);
+
+        // ---- shared memory -> registers, then hand the stage back ---------------------------------
+        float rec[PN];
+        const float2* src = reinterpret_cast<const float2*>(s_par + stage * (TP * L) + (r * CT + j) * PN);
+#pragma unroll
+        for (int i = 0; i < PN / 2; ++i) {
+            const float2 v = src[i];
+            rec[2 * i] = v.x;
+            rec[2 * i + 1] = v.y;
+        }
+        const float* zr = s_z + stage * zrow + r * C;
+        const float x = zr[ch];
+        // conditioner channels of this position are copied by the same CT threads
+        constexpr int kMaxCopy = (32 - CT + CT - 1) / CT;   // C <= 32 on this path
+        float cval[kMaxCopy > 0 ? kMaxCopy : 1];
+#pragma unroll
+        for (int n = 0; n < kMaxCopy; ++n) {
+            const int c = j + n * CT;                  // c-th conditioner channel
+            const int cc = (c < p.c0) ? c : c + CT;    // skip the transformed run
+            cval[n] = (c < C - CT) ? zr[cc] : 0.f;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[stage]);
+        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+
+        // ---- element ------------------------------------------------------------------------------
+        const int rl = r % RW;                       // position index inside the warp
+        int s_in = ws + rl;                          // position within its sample
+        long long b = wb;
+        while (s_in >= p.S) { s_in -= p.S; ++b; }
+        float padv = 1.0f;
+        if (valid && p.pad) padv = p.pad[pos];
+        bool active = valid && padv != 0.0f;
+        if (p.s_period > 0 && ((p.cond_s >> (s_in % p.s_period)) & 1ull)) active = false;  // conditioner position
+        float out = x, eldj = 0.f, ereg = 0.f;
+        if (active) {
+            MixPrep<KT> P;
+            mix_prepare<KT, REV>(P, rec, mfac, ma2, fac, a2, pre);
+            const float* rec_slow = p.nn + (pos * C + ch) * (long long)PN;
+            const float* mfac_slow = pre ? nullptr : s_mfac + j * KT;
+            ElemResult res;
+            if constexpr (!REV) res = mix_forward_p<KT>(x, P, rec_slow, mfac_slow, use_reg, p.reg_max, p.reg_factor);
+            else res = mix_inverse_p<KT>(x, P, rec_slow, mfac_slow, p.status);
+            // z_out = out * change + x * (1 - change), change = pad (mixture_cdf_layer.py:137-138)
+            out = (padv == 1.0f) ? res.z : fmaf(res.z, padv, x * (1.0f - padv));
+            eldj = res.ldj * padv;
+            ereg = res.reg * padv;
+            uint32_t bad = 0u;
+            if (res.z != res.z) bad |= CNF_FLAG_NAN_Z;
+            if (res.ldj != res.ldj) bad |= CNF_FLAG_NAN_LDJ;
+            flag(p.status, bad);
+        }
+        // ---- z row: transformed channel + conditioner copies, times pad (:76) ----------------------
+        if (valid) {
+            float* orow = p.z_out + pos * C;
+            orow[ch] = out * padv;
+#pragma unroll
+            for (int n = 0; n < kMaxCopy; ++n) {
+                const int c = j + n * CT;
+                const int cc = (c < p.c0) ? c : c + CT;
+                if (c < C - CT) orow[cc] = cval[n] * padv;
+            }
+        }
+        // ---- ldj: sum over the CT channels of a position, then per-sample accumulation -------------
+#pragma unroll
+        for (int d = 1; d < CT; d <<= 1) {
+            eldj += __shfl_xor_sync(0xffffffffu, eldj, d);
+            if (use_reg) ereg += __shfl_xor_sync(0xffffffffu, ereg, d);
+        }
+#pragma unroll
+        for (int q = 0; q < RW; ++q) {
+            const float v = __shfl_sync(0xffffffffu, eldj, q * CT);
+            const float vr = use_reg ? __shfl_sync(0xffffffffu, ereg, q * CT) : 0.f;
+            int sq = ws + q;
+            long long bq = wb;
+            while (sq >= p.S) { sq -= p.S; ++bq; }
+            if (pos0 + warp * RW + q >= p.P) break;
+            if (bq != cur_b) {
+                if (lane == 0 && cur_b >= 0) {
+                    atomicAdd(p.ldj + cur_b, acc);
+                    if (use_reg && p.reg_ldj) atomicAdd(p.reg_ldj + cur_b, acc_reg);
+                }
+                cur_b = bq; acc = 0.f; acc_reg = 0.f;
+            }
+            acc += v;
+            acc_reg += vr;
+        }
+        // advance this warp's (sample, position) by one tile
+        ws += TP;
+        while (ws >= p.S) { ws -= p.S; ++wb; }
+    }
+    if (lane == 0 && cur_b >= 0) {
+        atomicAdd(p.ldj + cur_b, acc);
+        if (use_reg && p.reg_ldj) atomicAdd(p.reg_ldj + cur_b, acc_reg);
+    }
+}
+
+template <int KT, int CT>
+size_t pipe_smem(int C) {
+    constexpr int PN = 2 + 3 * KT, L = CT * PN, TP = kConsumers / CT, kStages = stages_for<KT>();
+    size_t f = (size_t)kStages * TP * L + (size_t)kStages * TP * C + (size_t)CT * KT + ((CT * KT) & 1);
+    return f * sizeof(float) + 2 * kStages * sizeof(uint64_t);
+}
+
+template <int KT, int CT, bool REV>
+int launch_pipe(const PipeParams& p, cudaStream_t stream) {
+    const size_t smem = pipe_smem<KT, CT>(p.C);
+    constexpr int kMaxSmem = 113 * 1024;   // two CTAs per SM
+    CNF_SUPPORTED(smem <= (size_t)kMaxSmem, "pipelined mixcdf tile needs %zu bytes of shared memory", smem);
+    static thread_local int configured_dev = -1;
+    int dev = 0;
+    CNF_CUDA(cudaGetDevice(&dev));
+    if (configured_dev != dev) {
+        CNF_CUDA(cudaFuncSetAttribute(mixcdf_pipe_kernel<KT, CT, REV>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        configured_dev = dev;
+    }
+    long long grid = 2ll * sm_count();
+    if (grid > p.ntiles) grid = p.ntiles;
+    mixcdf_pipe_kernel<KT, CT, REV><<<(unsigned)grid, kThreadsPipe, smem, stream>>>(p);
+    return launch_status(REV ? "mixcdf_pipe_kernel<inv>" : "mixcdf_pipe_kernel<fwd>");
+}
+
+template <int KT, int CT>
+int launch_pipe_dir(const PipeParams& p, int reverse, cudaStream_t stream) {
+    return reverse ? launch_pipe<KT, CT, true>(p, stream) : launch_pipe<KT, CT, false>(p, stream);
+}
+
+}  // namespace
+
+// Returns CNF_OK and sets *handled = 1 when the pipelined kernel was launched; *handled = 0 when the
+// layout is not eligible and the caller must use the generic kernel.  ldj / reg_ldj have already
+// been zeroed (or are accumulated into) by the caller.
+int mixcdf_pipe_try(const cnf_mixcdf_args* a, const MaskView& mask, int reverse, cudaStream_t stream, int* handled) {
+    *handled = 0;
+    const int K = a->K, C = a->C, Ct = mask.n_t, PN = 2 + 3 * K;
+    if (!(K == 8 || K == 4 || K == 16)) return CNF_OK;
+    if (!mask.contiguous || !(Ct == 8 || Ct == 16 || Ct == 4)) return CNF_OK;
+    if (C % 4 != 0 || C > 32) return CNF_OK;
+    // bulk copies need 16-byte aligned sources and sizes
+    if ((Ct * PN) % 4 != 0 || (mask.c0 * PN) % 4 != 0 || (C * PN) % 4 != 0) return CNF_OK;
+    if ((reinterpret_cast<uintptr_t>(a->nn_out) & 15) || (reinterpret_cast<uintptr_t>(a->z) & 15)) return CNF_OK;
+    if (K == 16 && Ct == 16) return CNF_OK;   // two stages of 16 x 800 floats would not fit twice per SM
+    const long long P = a->B * a->S;
+    PipeParams p{};
+    p.z = a->z; p.nn = a->nn_out; p.pad = a->pad; p.sf = a->scaling_factor; p.msf = a->mixture_scaling_factor;
+    p.z_out = a->z_out; p.ldj = a->ldj; p.reg_ldj = a->reg_ldj; p.status = a->status;
+    p.P = P; p.S = (int)a->S; p.C = C; p.c0 = mask.c0; p.s_period = mask.s_period; p.cond_s = mask.cond_s;
+    p.reg_max = a->reg_max; p.reg_factor = a->reg_factor;
+    p.use_reg = (!reverse && a->reg_max > 0.f && a->training) ? 1 : 0;
+    p.pre = a->params_prebounded;
+    const int TP = kConsumers / Ct;
+    p.ntiles = (P + TP - 1) / TP;
+    *handled = 1;
+#define CNF_PIPE_CASE(KK, CC) \
+    if (K == KK && Ct == CC) return launch_pipe_dir<KK, CC>(p, reverse, stream);
+    CNF_PIPE_CASE(8, 8)
+    CNF_PIPE_CASE(8, 16)
+    CNF_PIPE_CASE(8, 4)
+    CNF_PIPE_CASE(4, 8)
+    CNF_PIPE_CASE(4, 16)
+    CNF_PIPE_CASE(4, 4)
+    CNF_PIPE_CASE(16, 8)
+    CNF_PIPE_CASE(16, 4)
+#undef CNF_PIPE_CASE
+    *handled = 0;
+    return CNF_OK;
+}
+
+}  // namespace cnf

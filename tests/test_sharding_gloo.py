@@ -1,0 +1,91 @@
+"""Host-side sharding logic on CPU with the gloo backend, world_size 2 (the N>1 path of bench.py):
+shards of a ragged batch reassemble to the whole, the (sum log-lik, count) all-reduce equals the
+single-process value, data-init moments agree with the oracle's global statistics, gradient
+averaging matches the mean of the per-rank gradients."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from categoricalnf_b200 import sharding as SH
+from oracle import cnf_oracle as O
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world_size, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world_size)
+    try:
+        g = torch.Generator().manual_seed(0)
+        B, S, C = 7, 5, 4      # ragged: 7 samples over 2 ranks -> 4 + 3
+        x = torch.randn(B, S, C, generator=g)
+        ll = torch.randn(B, generator=g)
+        pad = (torch.rand(B, S, 1, generator=g) > 0.3).float()
+        lo, hi = SH.shard_bounds(B, rank, world_size)
+        xs, lls, pads = SH.shard_batch((x, ll, pad))
+        assert xs.shape[0] == hi - lo and torch.equal(xs, x[lo:hi])
+        acc = SH.allreduce_loglik(lls)
+        bias, scales = SH.allreduce_moments(xs, pads)
+        lin = torch.nn.Linear(C, 3)
+        torch.manual_seed(0)
+        with torch.no_grad():
+            for p in lin.parameters():
+                p.copy_(torch.randn(p.shape, generator=torch.Generator().manual_seed(5)))
+        SH.broadcast_parameters(lin)
+        lin(xs.reshape(-1, C)).pow(2).sum().backward()
+        local_grad = lin.weight.grad.clone()
+        SH.allreduce_gradients(lin.parameters(), bucket_bytes=16)
+        out[rank] = dict(acc=acc, bias=bias, scales=scales, grad=lin.weight.grad.clone(), local_grad=local_grad,
+                         bounds=(lo, hi))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_sharding_matches_single_process():
+    world_size, port = 2, _free_port()
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_worker, args=(world_size, port, out), nprocs=world_size, join=True)
+        res = {k: v for k, v in out.items()}
+    g = torch.Generator().manual_seed(0)
+    B, S, C = 7, 5, 4
+    x = torch.randn(B, S, C, generator=g)
+    ll = torch.randn(B, generator=g)
+    pad = (torch.rand(B, S, 1, generator=g) > 0.3).float()
+    assert res[0]["bounds"] == (0, 4) and res[1]["bounds"] == (4, 7)
+    for r in range(world_size):
+        assert torch.allclose(res[r]["acc"], torch.tensor([ll.double().sum(), float(B)], dtype=torch.float64))
+    bias_ref, scales_ref = O.actnorm_data_init(x, pad)
+    for r in range(world_size):
+        assert torch.allclose(res[r]["bias"], bias_ref.flatten(), atol=1e-6)
+        assert torch.allclose(res[r]["scales"], scales_ref.flatten(), atol=1e-5)
+    mean_grad = (res[0]["local_grad"] + res[1]["local_grad"]) / 2
+    for r in range(world_size):
+        assert torch.allclose(res[r]["grad"], mean_grad, atol=1e-6)
+
+
+def test_shard_bounds_cover_and_handle_tiny_batches():
+    for n in (0, 1, 3, 8, 4097):
+        for ws in (1, 2, 4, 8):
+            spans = [SH.shard_bounds(n, r, ws) for r in range(ws)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_single_process_is_identity():
+    ll = torch.arange(6, dtype=torch.float32)
+    acc = SH.allreduce_loglik(ll)
+    assert acc.tolist() == [15.0, 6.0]
+    assert abs(SH.bits_per_dim(acc, 2.0) - (-15.0 / 12.0 * 1.4426950408889634)) < 1e-12
