@@ -171,6 +171,11 @@ size_t table_smem(int V, int D) { return sizeof(float) * (4 * (size_t)V * D + 2 
 
 using namespace cnf;
 
+namespace cnf {
+int categ_encode_tpt_try(const cnf_categ_encode_args* a, cudaStream_t stream, int* handled);
+int categ_decode_tpt_try(const cnf_categ_decode_args* a, cudaStream_t stream, int* handled);
+}
+
 static int check_dims(int V, int D, size_t* smem) {
     CNF_REQUIRE(V >= 1 && D >= 1, "V and D must be >= 1");
     CNF_SUPPORTED(D <= 32, "D=%d > 32 latent dimensions per token", D);
@@ -189,6 +194,11 @@ extern "C" int cnf_categ_encode(const cnf_categ_encode_args* a, cnf_stream_t str
     const long long T = a->B * a->S;
     if (T == 0) return CNF_OK;
     CNF_REQUIRE(a->tokens && a->table && a->z_out && a->ldj, "tokens / table / z_out / ldj is NULL");
+    {
+        int handled = 0;
+        rc = categ_encode_tpt_try(a, stream, &handled);
+        if (rc != CNF_OK || handled) return rc;
+    }
     CategParams p{};
     p.tokens = reinterpret_cast<const long long*>(a->tokens); p.u = a->u_noise; p.table = a->table;
     p.prior = a->category_prior; p.pad = a->pad; p.z_out = a->z_out; p.ldj = a->ldj; p.cpl = a->class_prob_log;
@@ -213,6 +223,11 @@ extern "C" int cnf_categ_decode(const cnf_categ_decode_args* a, cnf_stream_t str
     const long long T = a->B * a->S;
     if (T == 0) return CNF_OK;
     CNF_REQUIRE(a->z && a->table && a->tokens_out, "z / table / tokens_out is NULL");
+    {
+        int handled = 0;
+        rc = categ_decode_tpt_try(a, stream, &handled);
+        if (rc != CNF_OK || handled) return rc;
+    }
     CategParams p{};
     p.z_in = a->z; p.table = a->table; p.prior = a->category_prior;
     p.tokens_out = reinterpret_cast<long long*>(a->tokens_out); p.T = T; p.S = (int)a->S; p.V = a->V; p.D = a->D;

@@ -238,22 +238,26 @@ __device__ __forceinline__ ElemResult mix_inverse_elem(float zin, const ElemCtx&
 }
 
 // ------------------------------------------------------------------------------------------------
-// "Prepared" form for compile-time K: everything that depends on the parameters only (bounded
-// log-scales -> e^{-ls}, softmax numerators, their normaliser) is computed once per element and
-// held in registers; an evaluation at x then costs 2 MUFU per component (one sigmoid).  The
-// forward transform evaluates once, the inverse up to ~49 times, so this is what keeps the
-// bisection loop free of parameter work.  Same operations in the same order as mix_eval above.
+// "Prepared" form for compile-time K (TMA-pipelined kernels): everything that depends on the
+// parameters only (bounded log-scales -> e^{-ls}, softmax numerators, their normaliser) is computed
+// once per element and held in registers; an evaluation at x then costs 2 MUFU per component (one
+// sigmoid).  The forward transform evaluates once, the inverse up to ~49 times.  log2(e) factors
+// are folded into the per-component constants so the evaluation loop has no scaling multiplies.
 // ------------------------------------------------------------------------------------------------
 template <int KT>
 struct MixPrep {
-    float mu[KT], einv[KT], w[KT];
-    float iw, t, log_s;
-    float span;  // sum_k e^{ls_k}, inverse only (bracket of the bisection)
+    float mu[KT];
+    float einv2[KT];  // e^{-ls_k} * log2(e)
+    float w[KT];      // softmax numerators of log_pi
+    float iw;         // 1 / sum w
+    float t, log_s;
+    float span;       // sum_k e^{ls_k}, inverse only (bracket of the bisection)
 };
 
-template <int KT, bool WANT_SPAN>
-__device__ __forceinline__ void mix_prepare(MixPrep<KT>& P, const float* rec, const float* mfac, const float* ma2,
-                                            float fac, float a2, bool pre) {
+// `bnd[k * BSTRIDE]` holds, per component, (2 log2e / max(e^{msf},1), -e^{msf} log2e) - see
+// mixture_cdf_layer.py:160-162.
+template <int KT, int BSTRIDE, bool WANT_SPAN>
+__device__ __forceinline__ void mix_prepare(MixPrep<KT>& P, const float* rec, const float2* bnd, float fac, float a2) {
     const float* lp = rec + 2;
     const float* mu = lp + KT;
     const float* ms = mu + KT;
@@ -264,9 +268,10 @@ __device__ __forceinline__ void mix_prepare(MixPrep<KT>& P, const float* rec, co
     float W = 0.f, span = 0.f;
 #pragma unroll
     for (int k = 0; k < KT; ++k) {
-        const float ls = pre ? ms[k] : tanh_from_2log2e(ms[k] * ma2[k]) * mfac[k];
-        P.einv[k] = ex2(-ls * kLog2e);
-        if (WANT_SPAN) span += fast_exp(ls);
+        const float2 bk = bnd[k * BSTRIDE];
+        const float nls2 = tanh_from_2log2e(ms[k] * bk.x) * bk.y;   // -ls_k * log2(e)
+        P.einv2[k] = ex2(nls2) * kLog2e;
+        if (WANT_SPAN) span += ex2(-nls2);
         P.mu[k] = mu[k];
         P.w[k] = ex2(fmaf(lp[k], kLog2e, -m_l2));
         W += P.w[k];
@@ -274,7 +279,7 @@ __device__ __forceinline__ void mix_prepare(MixPrep<KT>& P, const float* rec, co
     P.iw = rcp(W);
     P.span = span;
     P.t = rec[0];
-    P.log_s = pre ? rec[1] : tanh_from_2log2e(rec[1] * a2) * fac;
+    P.log_s = tanh_from_2log2e(rec[1] * a2) * fac;
 }
 
 template <int KT>
@@ -282,31 +287,29 @@ __device__ __forceinline__ MixEval mix_eval_p(float x, const MixPrep<KT>& P) {
     float Fs = 0.f, Gs = 0.f, fs = 0.f;
 #pragma unroll
     for (int k = 0; k < KT; ++k) {
-        const float u = (x - P.mu[k]) * P.einv[k];
-        const float e = ex2(-fabsf(u) * kLog2e);
+        const float u2 = (x - P.mu[k]) * P.einv2[k];   // u * log2(e)
+        const float e = ex2(-fabsf(u2));
         const float r = rcp(1.0f + e);
         const float q = e * r;  // min(sigma, 1 - sigma)
-        const bool pos = u >= 0.0f;
+        const bool pos = u2 >= 0.0f;
         Fs = fmaf(P.w[k], pos ? r : q, Fs);
         Gs = fmaf(P.w[k], pos ? q : r, Gs);
-        fs = fmaf(P.w[k] * (q * r), P.einv[k], fs);
+        fs = fmaf(P.w[k] * (q * r), P.einv2[k], fs);
     }
     MixEval o;
     o.F = Fs * P.iw;
     o.G = Gs * P.iw;
-    o.f = fs * P.iw;
+    o.f = fs * (P.iw * kLn2);
     return o;
 }
 
-// `rec_slow` / `mfac_slow`: where the float64 path can re-read the record and the per-channel
-// bounds (global / shared memory; only touched by the rare slow elements).
+// fp32 is trusted while F, 1-F and f are far from underflow and 1-F is not in the region where the
+// reference's own float64 `1/F - 1` loses digits; NaNs fail the test as well.
+__device__ __forceinline__ bool mix_fast_ok(const MixEval& e) { return e.F >= 1e-30f && e.G >= 1e-12f && e.f >= 1e-30f; }
+
 template <int KT>
-__device__ __forceinline__ ElemResult mix_forward_p(float x, const MixPrep<KT>& P, const float* rec_slow,
-                                                    const float* mfac_slow, bool use_reg, float reg_max,
-                                                    float reg_factor) {
-    const MixEval e = mix_eval_p<KT>(x, P);
-    if (!(e.F >= 1e-30f && e.G >= 1e-12f && e.f >= 1e-30f))
-        return mix_forward_f64(x, rec_slow, mfac_slow, KT, P.log_s, use_reg, reg_max, reg_factor);
+__device__ __forceinline__ ElemResult mix_forward_fast(const MixEval& e, const MixPrep<KT>& P, bool use_reg,
+                                                       float reg_max, float reg_factor) {
     const float lF = fast_log(e.F), lG = fast_log(e.G);
     const float lFc = fmaxf(lF, kLog1em22), lGc = fmaxf(lG, kLog1em22);
     ElemResult r;
@@ -317,27 +320,34 @@ __device__ __forceinline__ ElemResult mix_forward_p(float x, const MixPrep<KT>& 
     return r;
 }
 
+// Inverse by bracketed bisection in fp32 registers.  Returns false when the element must be
+// finished by mix_inverse_f64 (flat CDF around the root); x / lb / ub then describe where to resume.
 template <int KT>
-__device__ __forceinline__ ElemResult mix_inverse_p(float zin, const MixPrep<KT>& P, const float* rec_slow,
-                                                    const float* mfac_slow, uint32_t* status) {
+struct InvState {
+    float x, lb, ub, lb0, ub0, cond, f, mixt_ldj;
+};
+
+template <int KT>
+__device__ __forceinline__ bool mix_inverse_fast(float zin, const MixPrep<KT>& P, uint32_t* status, InvState<KT>& st,
+                                                 ElemResult& out) {
     const float log_s = P.log_s;
     const float y = fmaf(zin, fast_exp(-log_s), -P.t);
-    const float mixt_ldj = softplus_pm(y);
+    st.mixt_ldj = softplus_pm(y);
     const float ey = ex2(-fabsf(y) * kLog2e);
     const float ry = rcp(1.0f + ey);
     float Ft = y >= 0.f ? ry : ey * ry;  // target CDF
     float Gt = y >= 0.f ? ey * ry : ry;  // 1 - target
     if (!(Ft == Ft)) flag(status, CNF_FLAG_CDF_RANGE);
-    Ft = fminf(fmaxf(Ft, 1e-5f), 1.0f - 1e-5f);
+    Ft = fminf(fmaxf(Ft, 1e-5f), 1.0f - 1e-5f);   // reference clamp (:130)
     Gt = fminf(fmaxf(Gt, 1e-5f), 1.0f - 1e-5f);
-    const bool upper = Ft > 0.5f;
+    const bool upper = Ft > 0.5f;  // compare on the smaller of F and 1-F: relative accuracy in both tails
     float lb = INFINITY, ub = -INFINITY;
 #pragma unroll
-    for (int k = 0; k < KT; ++k) {
+    for (int k = 0; k < KT; ++k) {   // bracket (:252-254)
         lb = fminf(lb, fmaf(-20.f, P.span, P.mu[k]));
         ub = fmaxf(ub, fmaf(20.f, P.span, P.mu[k]));
     }
-    const float lb0 = lb, ub0 = ub;
+    st.lb0 = lb; st.ub0 = ub;
     float x = 0.f;
     MixEval e = mix_eval_p<KT>(x, P);
     for (int it = 0; it < 48; ++it) {
@@ -349,16 +359,19 @@ __device__ __forceinline__ ElemResult mix_inverse_p(float zin, const MixPrep<KT>
         e = mix_eval_p<KT>(x, P);
         if (done) break;
     }
-    const float cond = fminf(e.F, e.G);
-    if (!(cond <= 8.0f * fmaxf(1.0f, fabsf(x)) * e.f) || !(e.f >= 1e-30f)) {
-        const float margin = fmaxf(4.0f * (ub - lb) + 1e-5f * fmaxf(1.0f, fabsf(x)), 1e-5f * cond / fmaxf(e.f, 1e-37f));
-        return mix_inverse_f64(zin, x, margin, rec_slow, mfac_slow, KT, log_s, lb0, ub0);
-    }
-    ElemResult r;
-    r.z = x;
-    r.ldj = -(log_s + mixt_ldj + fast_log(e.f));
-    r.reg = 0.f;
-    return r;
+    st.x = x; st.lb = lb; st.ub = ub; st.f = e.f;
+    // fp32 CDF values carry ~5e-7 relative error -> root error ~5e-7 min(F,G)/f
+    st.cond = fminf(e.F, e.G);
+    if (!(st.cond <= 8.0f * fmaxf(1.0f, fabsf(x)) * e.f) || !(e.f >= 1e-30f)) return false;
+    out.z = x;
+    out.ldj = -(log_s + st.mixt_ldj + fast_log(e.f));
+    out.reg = 0.f;
+    return true;
+}
+
+template <int KT>
+__device__ __forceinline__ float inv_slow_margin(const InvState<KT>& st) {
+    return fmaxf(4.0f * (st.ub - st.lb) + 1e-5f * fmaxf(1.0f, fabsf(st.x)), 1e-5f * st.cond / fmaxf(st.f, 1e-37f));
 }
 
 }  // namespace mixmath

@@ -45,7 +45,7 @@ struct PipeParams {
     int s_period;
     unsigned long long cond_s;
     float reg_max, reg_factor;
-    int use_reg, pre;
+    int use_reg;
 };
 
 // ---- mbarrier / bulk-copy primitives (sm_90+; SASS: SYNCS.*, UBLKCP) ------------------------------
@@ -98,13 +98,14 @@ __global__ void __launch_bounds__(kThreadsPipe, 2) mixcdf_pipe_kernel(const Pipe
     const int zrow = TP * C;                                      // floats of one z tile
     float* s_par = reinterpret_cast<float*>(smem_raw);            // [kStages][TP * L]
     float* s_z = s_par + kStages * TP * L;                        // [kStages][TP * C]
-    float* s_mfac = s_z + kStages * zrow;                         // [CT * KT]  e^{msf} (float64 escape only)
+    float2* s_bnd = reinterpret_cast<float2*>(s_z + kStages * zrow);  // [CT * KT] tanh bounds, see mix_prepare
+    float* s_mfac = reinterpret_cast<float*>(s_bnd + CT * KT);    // [CT * KT] e^{msf} (float64 escape only)
     uint64_t* full = reinterpret_cast<uint64_t*>(s_mfac + CT * KT + ((CT * KT) & 1));
     uint64_t* empty = full + kStages;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long t0 = (p.ntiles * (long long)blockIdx.x) / gridDim.x;
-    const long long t1 = (p.ntiles * (long long)(blockIdx.x + 1)) / gridDim.x;
+    const int tiles = (int)((p.ntiles * (long long)(blockIdx.x + 1)) / gridDim.x - t0);
 
     if (tid == 0) {
         for (int s = 0; s < kStages; ++s) {
@@ -113,17 +114,21 @@ __global__ void __launch_bounds__(kThreadsPipe, 2) mixcdf_pipe_kernel(const Pipe
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = tid; i < CT * KT; i += kThreadsPipe)
-        s_mfac[i] = p.msf ? expf(p.msf[(p.c0 + i / KT) * KT + i % KT]) : 1.0f;
+    for (int i = tid; i < CT * KT; i += kThreadsPipe) {
+        const float mf = p.msf ? expf(p.msf[(p.c0 + i / KT) * KT + i % KT]) : 1.0f;
+        s_mfac[i] = mf;
+        // [k][j] layout: the CT lanes of a position read consecutive 8-byte words (no bank conflict)
+        s_bnd[(i % KT) * CT + i / KT] = make_float2(2.0f * kLog2e / fmaxf(mf, 1.0f), -mf * kLog2e);
+    }
     __syncthreads();
 
     if (warp == kConsumerWarps) {
         // ---------------- producer warp ------------------------------------------------------------
         int stage = 0;
         uint32_t phase = 0;
-        for (long long t = t0; t < t1; ++t) {
+        long long pos0 = t0 * TP;
+        for (int it = 0; it < tiles; ++it, pos0 += TP) {
             mbar_wait(&empty[stage], phase ^ 1u);
-            const long long pos0 = t * TP;
             const int rows = (int)min((long long)TP, p.P - pos0);
             if (lane == 0) mbar_arrive_expect_tx(&full[stage], (uint32_t)(rows * (L + C) * 4));
             __syncwarp();
@@ -139,47 +144,48 @@ __global__ void __launch_bounds__(kThreadsPipe, 2) mixcdf_pipe_kernel(const Pipe
     // ---------------- consumer warps: thread = (position r, transformed channel j) -----------------
     const int r = tid / CT, j = tid % CT;
     const int ch = p.c0 + j;
-    // per-channel tanh bounds live in registers for the whole kernel (mixture_cdf_layer.py:157-162)
-    float mfac[KT], ma2[KT];
-#pragma unroll
-    for (int k = 0; k < KT; ++k) {
-        mfac[k] = s_mfac[j * KT + k];
-        ma2[k] = 2.0f * kLog2e / fmaxf(mfac[k], 1.0f);
-    }
-    const float fac = p.sf ? expf(p.sf[ch]) : 1.0f;
+    const float2* bnd = s_bnd + j;   // component k at bnd[k * CT]
+    const float fac = p.sf ? expf(p.sf[ch]) : 1.0f;   // tanh bound of log_s (mixture_cdf_layer.py:157-159)
     const float a2 = 2.0f * kLog2e / fmaxf(fac, 1.0f);
-    const bool pre = p.pre != 0, use_reg = p.use_reg != 0;
+    const bool use_reg = p.use_reg != 0;
+    const int rec_off = (r * CT + j) * PN, z_off = r * C;
+    constexpr int kMaxCopy = (32 - CT + CT - 1) / CT;   // conditioner channels copied per thread (C <= 32)
 
     // running per-warp ldj accumulator over consecutive positions of one sample
     long long cur_b = -1;
     float acc = 0.f, acc_reg = 0.f;
-    // (sample, position-in-sample) of this warp's first position in the current tile
-    const long long wpos0 = t0 * TP + warp * RW;
-    long long wb = wpos0 / p.S;
-    int ws = (int)(wpos0 - wb * p.S);
+    auto flush = [&]() {
+        if (lane == 0 && cur_b >= 0) {
+            atomicAdd(p.ldj + cur_b, acc);
+            if (use_reg && p.reg_ldj) atomicAdd(p.reg_ldj + cur_b, acc_reg);
+        }
+    };
+    // (sample, position in sample) of the current tile's first position
+    long long pos0 = t0 * TP;
+    long long tb = pos0 / p.S;
+    int ts = (int)(pos0 - tb * p.S);
+    float* orow = p.z_out + (pos0 + r) * C;
+    const float* padp = p.pad ? p.pad + pos0 + r : nullptr;
 
     int stage = 0;
     uint32_t phase = 0;
-    for (long long t = t0; t < t1; ++t) {
-        const long long pos0 = t * TP;
-        const int rows = (int)min((long long)TP, p.P - pos0);
-        const long long pos = pos0 + r;
-        const bool valid = r < rows;
+    for (int it = 0; it < tiles; ++it) {
+        const bool full_tile = pos0 + TP <= p.P;
+        const bool one_sample = full_tile && ts + TP <= p.S;   // whole tile inside one sample (CTA-uniform)
+        const bool valid = full_tile || pos0 + r < p.P;
         mbar_wait(&full[stage], phase);
 
         // ---- shared memory -> registers, then hand the stage back ---------------------------------
         float rec[PN];
-        const float2* src = reinterpret_cast<const float2*>(s_par + stage * (TP * L) + (r * CT + j) * PN);
+        const float2* src = reinterpret_cast<const float2*>(s_par + stage * (TP * L) + rec_off);
 #pragma unroll
         for (int i = 0; i < PN / 2; ++i) {
             const float2 v = src[i];
             rec[2 * i] = v.x;
             rec[2 * i + 1] = v.y;
         }
-        const float* zr = s_z + stage * zrow + r * C;
+        const float* zr = s_z + stage * zrow + z_off;
         const float x = zr[ch];
-        // conditioner channels of this position are copied by the same CT threads
-        constexpr int kMaxCopy = (32 - CT + CT - 1) / CT;   // C <= 32 on this path
         float cval[kMaxCopy > 0 ? kMaxCopy : 1];
 #pragma unroll
         for (int n = 0; n < kMaxCopy; ++n) {
@@ -192,35 +198,44 @@ __global__ void __launch_bounds__(kThreadsPipe, 2) mixcdf_pipe_kernel(const Pipe
         if (++stage == kStages) { stage = 0; phase ^= 1u; }
 
         // ---- element ------------------------------------------------------------------------------
-        const int rl = r % RW;                       // position index inside the warp
-        int s_in = ws + rl;                          // position within its sample
-        long long b = wb;
-        while (s_in >= p.S) { s_in -= p.S; ++b; }
         float padv = 1.0f;
-        if (valid && p.pad) padv = p.pad[pos];
+        if (padp != nullptr && valid) padv = *padp;
         bool active = valid && padv != 0.0f;
-        if (p.s_period > 0 && ((p.cond_s >> (s_in % p.s_period)) & 1ull)) active = false;  // conditioner position
+        if (p.s_period > 0) {   // chess mask: conditioner positions are copied through
+            int s_in = ts + r;
+            while (s_in >= p.S) s_in -= p.S;
+            if ((p.cond_s >> (s_in % p.s_period)) & 1ull) active = false;
+        }
         float out = x, eldj = 0.f, ereg = 0.f;
         if (active) {
             MixPrep<KT> P;
-            mix_prepare<KT, REV>(P, rec, mfac, ma2, fac, a2, pre);
-            const float* rec_slow = p.nn + (pos * C + ch) * (long long)PN;
-            const float* mfac_slow = pre ? nullptr : s_mfac + j * KT;
+            mix_prepare<KT, CT, REV>(P, rec, bnd, fac, a2);
             ElemResult res;
-            if constexpr (!REV) res = mix_forward_p<KT>(x, P, rec_slow, mfac_slow, use_reg, p.reg_max, p.reg_factor);
-            else res = mix_inverse_p<KT>(x, P, rec_slow, mfac_slow, p.status);
+            if constexpr (!REV) {
+                const MixEval e = mix_eval_p<KT>(x, P);
+                if (mix_fast_ok(e)) {
+                    res = mix_forward_fast<KT>(e, P, use_reg, p.reg_max, p.reg_factor);
+                } else {
+                    const float* rec_slow = p.nn + ((pos0 + r) * C + ch) * (long long)PN;
+                    res = mix_forward_f64(x, rec_slow, s_mfac + j * KT, KT, P.log_s, use_reg, p.reg_max, p.reg_factor);
+                }
+            } else {
+                InvState<KT> st;
+                if (!mix_inverse_fast<KT>(x, P, p.status, st, res)) {
+                    const float* rec_slow = p.nn + ((pos0 + r) * C + ch) * (long long)PN;
+                    res = mix_inverse_f64(x, st.x, inv_slow_margin<KT>(st), rec_slow, s_mfac + j * KT, KT, P.log_s, st.lb0,
+                                          st.ub0);
+                }
+            }
             // z_out = out * change + x * (1 - change), change = pad (mixture_cdf_layer.py:137-138)
             out = (padv == 1.0f) ? res.z : fmaf(res.z, padv, x * (1.0f - padv));
             eldj = res.ldj * padv;
             ereg = res.reg * padv;
-            uint32_t bad = 0u;
-            if (res.z != res.z) bad |= CNF_FLAG_NAN_Z;
-            if (res.ldj != res.ldj) bad |= CNF_FLAG_NAN_LDJ;
-            flag(p.status, bad);
+            if ((res.z != res.z) | (res.ldj != res.ldj))
+                flag(p.status, (res.z != res.z ? CNF_FLAG_NAN_Z : 0u) | (res.ldj != res.ldj ? CNF_FLAG_NAN_LDJ : 0u));
         }
         // ---- z row: transformed channel + conditioner copies, times pad (:76) ----------------------
         if (valid) {
-            float* orow = p.z_out + pos * C;
             orow[ch] = out * padv;
 #pragma unroll
             for (int n = 0; n < kMaxCopy; ++n) {
@@ -229,44 +244,45 @@ __global__ void __launch_bounds__(kThreadsPipe, 2) mixcdf_pipe_kernel(const Pipe
                 if (c < C - CT) orow[cc] = cval[n] * padv;
             }
         }
-        // ---- ldj: sum over the CT channels of a position, then per-sample accumulation -------------
+        // ---- ldj -----------------------------------------------------------------------------------
+        if (one_sample) {
+            eldj = warp_sum(eldj);
+            if (use_reg) ereg = warp_sum(ereg);
+            if (tb != cur_b) { flush(); cur_b = tb; acc = 0.f; acc_reg = 0.f; }
+            acc += eldj;
+            acc_reg += ereg;
+        } else {
+            // tile straddles samples or is ragged: per-position sums, then sequential per-sample accumulation
 #pragma unroll
-        for (int d = 1; d < CT; d <<= 1) {
-            eldj += __shfl_xor_sync(0xffffffffu, eldj, d);
-            if (use_reg) ereg += __shfl_xor_sync(0xffffffffu, ereg, d);
-        }
-#pragma unroll
-        for (int q = 0; q < RW; ++q) {
-            const float v = __shfl_sync(0xffffffffu, eldj, q * CT);
-            const float vr = use_reg ? __shfl_sync(0xffffffffu, ereg, q * CT) : 0.f;
-            int sq = ws + q;
-            long long bq = wb;
-            while (sq >= p.S) { sq -= p.S; ++bq; }
-            if (pos0 + warp * RW + q >= p.P) break;
-            if (bq != cur_b) {
-                if (lane == 0 && cur_b >= 0) {
-                    atomicAdd(p.ldj + cur_b, acc);
-                    if (use_reg && p.reg_ldj) atomicAdd(p.reg_ldj + cur_b, acc_reg);
-                }
-                cur_b = bq; acc = 0.f; acc_reg = 0.f;
+            for (int d = 1; d < CT; d <<= 1) {
+                eldj += __shfl_xor_sync(0xffffffffu, eldj, d);
+                ereg += __shfl_xor_sync(0xffffffffu, ereg, d);
             }
-            acc += v;
-            acc_reg += vr;
+            for (int q = 0; q < RW; ++q) {
+                const float v = __shfl_sync(0xffffffffu, eldj, q * CT);
+                const float vr = __shfl_sync(0xffffffffu, ereg, q * CT);
+                const long long pq = pos0 + warp * RW + q;
+                if (pq >= p.P) break;
+                const long long bq = pq / p.S;
+                if (bq != cur_b) { flush(); cur_b = bq; acc = 0.f; acc_reg = 0.f; }
+                acc += v;
+                acc_reg += vr;
+            }
         }
-        // advance this warp's (sample, position) by one tile
-        ws += TP;
-        while (ws >= p.S) { ws -= p.S; ++wb; }
+        // advance to the next tile
+        pos0 += TP;
+        ts += TP;
+        while (ts >= p.S) { ts -= p.S; ++tb; }
+        orow += TP * C;
+        if (padp != nullptr) padp += TP;
     }
-    if (lane == 0 && cur_b >= 0) {
-        atomicAdd(p.ldj + cur_b, acc);
-        if (use_reg && p.reg_ldj) atomicAdd(p.reg_ldj + cur_b, acc_reg);
-    }
+    flush();
 }
 
 template <int KT, int CT>
 size_t pipe_smem(int C) {
     constexpr int PN = 2 + 3 * KT, L = CT * PN, TP = kConsumers / CT, kStages = stages_for<KT>();
-    size_t f = (size_t)kStages * TP * L + (size_t)kStages * TP * C + (size_t)CT * KT + ((CT * KT) & 1);
+    size_t f = (size_t)kStages * TP * L + (size_t)kStages * TP * C + 3 * (size_t)CT * KT + ((CT * KT) & 1);
     return f * sizeof(float) + 2 * kStages * sizeof(uint64_t);
 }
 
@@ -301,6 +317,7 @@ int launch_pipe_dir(const PipeParams& p, int reverse, cudaStream_t stream) {
 int mixcdf_pipe_try(const cnf_mixcdf_args* a, const MaskView& mask, int reverse, cudaStream_t stream, int* handled) {
     *handled = 0;
     const int K = a->K, C = a->C, Ct = mask.n_t, PN = 2 + 3 * K;
+    if (a->params_prebounded) return CNF_OK;   // explicit-parameter callers: generic kernel
     if (!(K == 8 || K == 4 || K == 16)) return CNF_OK;
     if (!mask.contiguous || !(Ct == 8 || Ct == 16 || Ct == 4)) return CNF_OK;
     if (C % 4 != 0 || C > 32) return CNF_OK;
@@ -315,7 +332,6 @@ int mixcdf_pipe_try(const cnf_mixcdf_args* a, const MaskView& mask, int reverse,
     p.P = P; p.S = (int)a->S; p.C = C; p.c0 = mask.c0; p.s_period = mask.s_period; p.cond_s = mask.cond_s;
     p.reg_max = a->reg_max; p.reg_factor = a->reg_factor;
     p.use_reg = (!reverse && a->reg_max > 0.f && a->training) ? 1 : 0;
-    p.pre = a->params_prebounded;
     const int TP = kConsumers / Ct;
     p.ntiles = (P + TP - 1) / TP;
     *handled = 1;

@@ -1,0 +1,157 @@
+"""GPU parity of the fast-path kernels at sizes that select them: the TMA-pipelined mixture
+coupling (csrc/mixcdf_pipe.cu) and the thread-per-token categorical encode / decode
+(csrc/categ_tpt.cu), each against the CPU oracle on seeded inputs, plus size-independent
+properties at BASELINE's full LM size (forward -> inverse round trip, ldj antisymmetry,
+linearity of the ldj accumulator in the batch split).
+
+Tolerance: |a-b| <= 1e-4 |b| + 1e-5 on z, 1e-4 relative (+2e-4 abs) on ldj."""
+import pytest
+import torch
+
+from conftest import assert_close
+from oracle import cnf_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def dev(t):
+    return t.cuda() if isinstance(t, torch.Tensor) else t
+
+
+def _mix_inputs(B, S, C, K, seed, std=0.7):
+    g = torch.Generator().manual_seed(seed)
+    z = torch.randn(B, S, C, generator=g)
+    nn_out = torch.randn(B, S, C * (2 + 3 * K), generator=g) * std
+    sf = torch.randn(C, generator=g) * 0.3
+    msf = torch.randn(C, K, generator=g) * 0.3
+    return z, nn_out, sf, msf
+
+
+# (B, S, C, K, mask) - all eligible for the pipelined kernel: contiguous transformed run, 16-byte aligned
+PIPE_CASES = [
+    (6, 37, 16, 8, "half"),      # ragged: 222 positions, tiles straddle samples
+    (3, 256, 16, 8, "half"),     # LM layout, S multiple of the tile
+    (5, 50, 16, 8, "flip"),      # transformed channels first
+    (4, 33, 8, 8, "half"),       # Ct = 4
+    (4, 40, 16, 4, "half"),      # K = 4
+    (3, 29, 16, 16, "half"),     # K = 16 (two stages)
+    (2, 64, 16, 8, "chess"),     # position mask, all 16 channels transformed
+]
+
+
+def _mask(kind, C, S):
+    if kind == "half":
+        return O.channel_mask(C, 0.5), [1.0] * (C // 2) + [0.0] * (C - C // 2), None
+    if kind == "flip":
+        m = 1 - O.channel_mask(C, 0.5)
+        return m, m.flatten().tolist(), None
+    m = O.chess_mask(2)
+    return m, None, m.flatten().tolist()
+
+
+@pytest.mark.parametrize("B,S,C,K,kind", PIPE_CASES)
+@pytest.mark.parametrize("padded", [False, True])
+def test_mixcdf_pipe_vs_oracle(B, S, C, K, kind, padded):
+    from categoricalnf_b200 import ops
+    z, nn_out, sf, msf = _mix_inputs(B, S, C, K, seed=B * 1000 + S)
+    mask, mc, ms = _mask(kind, C, S)
+    pad = None
+    if padded:
+        length = torch.randint(S // 2, S + 1, (B,), generator=torch.Generator().manual_seed(S))
+        pad = (torch.arange(S).view(1, S) < length.view(-1, 1)).float().unsqueeze(-1)
+    m = O.expand_mask(mask, z)
+    z_ref, ldj_ref, reg_ref = O.mixcdf_coupling(z, nn_out, m, K, sf, msf, pad=pad, reg_max=2.0, reg_factor=0.5, training=True)
+    zo, ldj, reg = ops.mixcdf(dev(z), dev(nn_out), K, mask_c=mc, mask_s=ms, pad=dev(pad), scaling_factor=dev(sf),
+                              mixture_scaling_factor=dev(msf), reg_max=2.0, reg_factor=0.5, training=True, want_reg=True)
+    ops.check_status(zo.device)
+    assert_close(zo, z_ref, what="z fwd")
+    assert_close(ldj, ldj_ref, rtol=1e-4, atol=2e-4, what="ldj fwd")
+    assert_close(reg, reg_ref, rtol=1e-4, atol=2e-4, what="reg ldj")
+    # inverse of the forward output with the same parameters
+    z_inv_ref, ldj_inv_ref, _ = O.mixcdf_coupling(z_ref, nn_out, m, K, sf, msf, pad=pad, reverse=True)
+    zi, ldji, _ = ops.mixcdf(dev(z_ref), dev(nn_out), K, mask_c=mc, mask_s=ms, pad=dev(pad), scaling_factor=dev(sf),
+                             mixture_scaling_factor=dev(msf), reverse=True)
+    assert_close(zi, z_inv_ref, what="z inv")
+    assert_close(ldji, ldj_inv_ref, rtol=1e-4, atol=2e-4, what="ldj inv")
+
+
+def test_mixcdf_pipe_matches_generic_kernel(monkeypatch):
+    """Both kernels implement the same arithmetic: results agree to a few ulp on the LM layout."""
+    import subprocess, sys, os
+    code = ("import torch,sys;sys.path.insert(0,%r);from categoricalnf_b200 import ops;"
+            "g=torch.Generator().manual_seed(1);z=torch.randn(16,256,16,generator=g).cuda();"
+            "nn=(torch.randn(16,256,416,generator=g)*0.7).cuda();"
+            "o=ops.mixcdf(z,nn,8,mask_c=[1.]*8+[0.]*8);torch.save([t.cpu() for t in o[:2]],sys.argv[1])")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for env in ({}, {"CNF_B200_MIXCDF_GENERIC": "1"}):
+        path = "/tmp/cnf_pipe_vs_generic_%d.pt" % len(outs)
+        subprocess.run([sys.executable, "-c", code % root, path], check=True, env={**os.environ, **env})
+        outs.append(torch.load(path))
+    assert_close(outs[0][0], outs[1][0], rtol=2e-6, atol=2e-6, what="z pipe vs generic")
+    assert_close(outs[0][1], outs[1][1], rtol=1e-5, atol=1e-4, what="ldj pipe vs generic")
+
+
+def test_mixcdf_full_size_roundtrip_and_split_linearity():
+    """BASELINE size (B=4096, S=256, C=16, K=8): inverse(forward(z)) == z, ldj_inv == -ldj_fwd, and the
+    per-sample ldj of the full batch equals that of its two halves run separately."""
+    from categoricalnf_b200 import ops
+    B, S, C, K = 4096, 256, 16, 8
+    g = torch.Generator(device="cuda").manual_seed(0)
+    z = torch.randn(B, S, C, device="cuda", generator=g)
+    nn_out = torch.randn(B, S, C * (2 + 3 * K), device="cuda", generator=g) * 0.5
+    mc = [1.0] * 8 + [0.0] * 8
+    zf, ldj_f, _ = ops.mixcdf(z, nn_out, K, mask_c=mc)
+    zr, ldj_r, _ = ops.mixcdf(zf, nn_out, K, mask_c=mc, reverse=True)
+    ops.check_status(z.device)
+    assert torch.equal(zf[..., :8], z[..., :8])              # conditioner half untouched
+    assert_close(zr, z, rtol=1e-4, atol=2e-5, what="round trip")
+    assert_close(ldj_r, -ldj_f, rtol=1e-4, atol=1e-2, what="ldj antisymmetry")
+    h = B // 2
+    _, l0, _ = ops.mixcdf(z[:h], nn_out[:h], K, mask_c=mc)
+    _, l1, _ = ops.mixcdf(z[h:], nn_out[h:], K, mask_c=mc)
+    assert_close(torch.cat([l0, l1]), ldj_f, rtol=1e-5, atol=1e-3, what="batch split")
+
+
+@pytest.mark.parametrize("V,D,B,S", [(51, 16, 24, 100), (9, 6, 64, 38), (3, 2, 8, 300), (1, 2, 4, 20), (20, 3, 30, 70),
+                                      (51, 4, 16, 140)])
+@pytest.mark.parametrize("padded", [False, True])
+def test_categ_tpt_vs_oracle(V, D, B, S, padded):
+    from categoricalnf_b200 import ops
+    g = torch.Generator().manual_seed(V * 100 + D)
+    table = torch.cat([torch.randn(V, D, generator=g) * 1.5, torch.randn(V, D, generator=g) * 0.8], dim=1)
+    prior = torch.log_softmax(torch.randn(V, generator=g), 0)
+    x = torch.randint(0, V, (B, S), generator=g)
+    u = torch.rand(B * S, 1, D, generator=g)
+    pad = (torch.rand(B, S, 1, generator=g) > 0.2).float() if padded else None
+    z_ref, ldj_ref, cpl_ref = O.categ_encode(x, u, table, prior, beta=0.7, pad=pad)
+    ldj0 = torch.randn(B, generator=g)
+    z, ldj, cpl = ops.categ_encode(dev(x), dev(table), dev(prior), dev(ldj0.clone()), noise=dev(u), pad=dev(pad), beta=0.7,
+                                   want_class_prob=True)
+    ops.check_status(z.device)
+    assert_close(z, z_ref, what="z")
+    assert_close(ldj, ldj_ref + ldj0, rtol=1e-4, atol=2e-4, what="ldj")
+    assert_close(cpl.reshape(-1), cpl_ref, rtol=1e-4, atol=2e-5, what="class_prob_log")
+    # decode: ties aside, the argmax matches the oracle
+    dec = ops.categ_decode(dev(z_ref), dev(table), dev(prior)).cpu()
+    dec_ref = O.categ_decode(z_ref, table, prior)
+    assert (dec == dec_ref).float().mean() > 0.9999
+
+
+def test_categ_tpt_dominating_other_class():
+    """A latent that another class explains e^80 times better than its own: the reference-point
+    log-sum-exp must fall back to the exact running-max form (finite, equal to the oracle)."""
+    from categoricalnf_b200 import ops
+    V, D, B, S = 4, 4, 8, 300
+    table = torch.zeros(V, 2 * D)
+    table[0, :D] = 60.0        # class 0 sits far away from the others
+    table[:, D:] = -2.0        # narrow classes
+    prior = torch.log_softmax(torch.zeros(V), 0)
+    x = torch.zeros(B, S, dtype=torch.int64)
+    x[:, ::2] = 1
+    u = torch.rand(B * S, 1, D, generator=torch.Generator().manual_seed(0))
+    z_ref, ldj_ref, cpl_ref = O.categ_encode(x, u, table, prior)
+    z, ldj, cpl = ops.categ_encode(dev(x), dev(table), dev(prior), torch.zeros(B, device="cuda"), noise=dev(u),
+                                   want_class_prob=True)
+    assert torch.isfinite(cpl).all()
+    assert_close(ldj, ldj_ref, rtol=1e-4, atol=2e-4, what="ldj")
