@@ -225,6 +225,7 @@ def run_gpu(args, rank, local_rank, world):
     del nn_outs
     torch.cuda.empty_cache()
     model, prior = W.build_lm_model(prm, dev)
+    parity = parity_check(prm, model, dev) if rank == 0 else None
     host_tokens = [W.lm_tokens(B, S, V, seed=10 * rank + j).pin_memory() for j in range(2)]
     host_ll = torch.empty(B, dtype=torch.float32).pin_memory()
 
@@ -279,13 +280,30 @@ def run_gpu(args, rank, local_rank, world):
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                          "mean_launch_ms": mix_ms_mean, "launches_timed": len(mix_ms),
                          "share_of_step": mix_ms_mean * len(prm.blocks) / ms_step},
-            "clocks": clk, "bits_per_dim": bpd_gpu,
+            "clocks": clk, "bits_per_dim": bpd_gpu, "parity": parity,
         }
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(prm)
         print(json.dumps(line), flush=True)
     if distributed:
         dist.destroy_process_group()
+
+
+def parity_check(prm, model, dev, B=32):
+    """Same tokens and noise through the drop-in modules (GPU) and the CPU oracle: bits/dim of both and
+    the worst tolerance-normalised deviation of z and ldj (<= 1 means inside |a-b| <= 1e-4|b| + atol)."""
+    from categoricalnf_b200 import ops
+    tokens, u = W.lm_tokens(B, prm.S, prm.V, seed=77), W.lm_noise(B, prm.S, prm.D, seed=77)
+    z_ref, ldj_ref, lp_ref = W.lm_oracle_forward(prm, tokens, u)
+    with torch.no_grad():
+        z, ldj = model(tokens.to(dev), u_noise=u.to(dev))
+        lp, _ = ops.logistic_logprob(z)
+    z, ldj, lp = z.cpu().double(), ldj.cpu().double(), lp.cpu().double()
+    dev_z = ((z - z_ref).abs() / (1e-4 * z_ref.abs() + 1e-5)).max().item()
+    dev_ldj = ((ldj - ldj_ref).abs() / (1e-4 * ldj_ref.abs() + 2e-4)).max().item()
+    return {"batch": B, "bits_per_dim_gpu": W.bits_per_dim(ldj, lp, prm.S),
+            "bits_per_dim_oracle": W.bits_per_dim(ldj_ref, lp_ref, prm.S), "z_dev_over_tol": dev_z,
+            "ldj_dev_over_tol": dev_ldj}
 
 
 def ncu_traffic():

@@ -13,7 +13,7 @@ cat $out/bench.json; tail -5 $out/bench.err
 if [ "$2" != "noprof" ]; then
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu > $out/ncu_launches.log 2>&1; echo "ncu launches rc=$?"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:mixcdf_kernel -s 34 -c 2 -f -o $out/mixcdf_fwd \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:mixcdf -s 34 -c 2 -f -o $out/mixcdf_fwd \
     python bench.py --steps 2 --warmup 3 --no-cpu > $out/ncu_full.log 2>&1; echo "ncu full rc=$?"
 fi
 ls -la $out
