@@ -88,6 +88,7 @@ class CategEncodeArgs(C.Structure):
         ("tokens", vp), ("u_noise", vp), ("seed", C.c_uint64), ("offset", C.c_uint64),
         ("table", vp), ("category_prior", vp), ("pad", vp), ("beta", C.c_float),
         ("z_out", vp), ("ldj", vp), ("class_prob_log", vp), ("status", vp),
+        ("next_actnorm_bias", vp), ("next_actnorm_scales", vp), ("next_conv_weight", vp),
     ]
 
 
@@ -135,9 +136,10 @@ ENTRY_POINTS = {
     "cnf_logistic_sample": LogisticSampleArgs,
     "cnf_ldj_axpy": LdjAxpyArgs,
 }
-PLAIN_SYMBOLS = ("cnf_last_error_string", "cnf_abi_version", "cnf_built_for_sm")
+PLAIN_SYMBOLS = ("cnf_last_error_string", "cnf_abi_version", "cnf_built_for_sm", "cnf_mixcdf_fusable",
+                 "cnf_categ_encode_fusable")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 _lib = None
 
 
@@ -167,6 +169,10 @@ def load():
     lib.cnf_last_error_string.argtypes = []
     lib.cnf_abi_version.restype = C.c_int
     lib.cnf_built_for_sm.restype = C.c_int
+    lib.cnf_mixcdf_fusable.argtypes = [C.POINTER(MixcdfArgs)]
+    lib.cnf_mixcdf_fusable.restype = C.c_int
+    lib.cnf_categ_encode_fusable.argtypes = [C.POINTER(CategEncodeArgs)]
+    lib.cnf_categ_encode_fusable.restype = C.c_int
     if lib.cnf_abi_version() != ABI_VERSION:
         raise ImportError("libcnf_b200.so has ABI version %d, the Python binding expects %d - rebuild"
                           % (lib.cnf_abi_version(), ABI_VERSION))

@@ -174,6 +174,7 @@ using namespace cnf;
 namespace cnf {
 int categ_encode_tpt_try(const cnf_categ_encode_args* a, cudaStream_t stream, int* handled);
 int categ_decode_tpt_try(const cnf_categ_decode_args* a, cudaStream_t stream, int* handled);
+bool categ_encode_tpt_fusable(const cnf_categ_encode_args* a);
 }
 
 static int check_dims(int V, int D, size_t* smem) {
@@ -199,6 +200,8 @@ extern "C" int cnf_categ_encode(const cnf_categ_encode_args* a, cnf_stream_t str
         rc = categ_encode_tpt_try(a, stream, &handled);
         if (rc != CNF_OK || handled) return rc;
     }
+    CNF_SUPPORTED(a->next_actnorm_bias == nullptr && a->next_actnorm_scales == nullptr && a->next_conv_weight == nullptr,
+                  "the fused first-block epilogue needs the thread-per-token encode kernel; query cnf_categ_encode_fusable");
     CategParams p{};
     p.tokens = reinterpret_cast<const long long*>(a->tokens); p.u = a->u_noise; p.table = a->table;
     p.prior = a->category_prior; p.pad = a->pad; p.z_out = a->z_out; p.ldj = a->ldj; p.cpl = a->class_prob_log;
@@ -211,6 +214,11 @@ extern "C" int cnf_categ_encode(const cnf_categ_encode_args* a, cnf_stream_t str
     if (blocks > cap) blocks = cap;
     categ_encode_kernel<<<(unsigned)blocks, kThreads, smem, stream>>>(p);
     return launch_status("categ_encode_kernel");
+}
+
+extern "C" int cnf_categ_encode_fusable(const cnf_categ_encode_args* a) {
+    if (a == nullptr || a->V < 1 || a->D < 1) return 0;
+    return cnf::categ_encode_tpt_fusable(a) ? 1 : 0;
 }
 
 extern "C" int cnf_categ_decode(const cnf_categ_decode_args* a, cnf_stream_t stream_) {

@@ -30,6 +30,7 @@ struct TptParams {
     const long long* tokens; const float* u; const float* table; const float* prior; const float* pad;
     const float* z_in;
     float* z_out; float* ldj; float* cpl; long long* tokens_out; uint32_t* status;
+    const float* nx_bias; const float* nx_scales; const float* nx_w;   // fused first-block ActNorm + 1x1 conv
     long long T;
     int S, V;
     float beta;
@@ -44,7 +45,9 @@ template <int D>
 struct Smem {
     static constexpr int DP = (D + 1) & ~1;
     static constexpr int OWN = 2 * D + 1;
-    static size_t bytes(int V) { return sizeof(float) * ((size_t)V * DP * 2 + (size_t)V * OWN + 2 * (size_t)V + 4); }
+    static size_t bytes(int V) {
+        return sizeof(float) * ((size_t)V * DP * 2 + (size_t)V * OWN + 2 * (size_t)V + 4 + (size_t)D * D + 2 * D + 4);
+    }
 };
 
 template <int D>
@@ -104,6 +107,17 @@ __global__ void __launch_bounds__(kThreadsT) categ_encode_tpt_kernel(const TptPa
     float* own = sm + (size_t)V * DP * 2;
     float* cst = own + (size_t)V * OWN;
     float* prior = cst + V;
+    float* s_w = prior + V + (4 - ((2 * V * DP + V * OWN + 2 * V) & 3)) % 4;   // 16-byte aligned [D][D] next conv weight
+    float* s_nb = s_w + D * D;
+    float* s_ne = s_nb + D;
+    const bool fuse = p.nx_w != nullptr || p.nx_bias != nullptr || p.nx_scales != nullptr;
+    if (fuse) {
+        for (int i = threadIdx.x; i < D * D; i += kThreadsT) s_w[i] = p.nx_w ? p.nx_w[i] : (i / D == i % D ? 1.0f : 0.f);
+        for (int i = threadIdx.x; i < D; i += kThreadsT) {
+            s_nb[i] = p.nx_bias ? p.nx_bias[i] : 0.f;
+            s_ne[i] = p.nx_scales ? expf(p.nx_scales[i]) : 1.0f;
+        }
+    }
     load_tables<D>(p, eb, own, cst, prior);
 
     const long long stride = (long long)gridDim.x * kThreadsT;
@@ -176,6 +190,28 @@ __global__ void __launch_bounds__(kThreadsT) categ_encode_tpt_kernel(const TptPa
             }
             const float cpl = log_point - lse;
             ldj_tok = (p.beta * cpl - (init_log_p - ldj_fwd)) * padv;
+            if (fuse) {
+                // first block: a = (z pad + bias) e^{scales} pad ; y = (a @ W) pad  (ActNormFlow, InvertibleConv)
+                float a[D];
+#pragma unroll
+                for (int d = 0; d < D; ++d) a[d] = (z[d] * padv + s_nb[d]) * s_ne[d] * padv;
+#pragma unroll
+                for (int d = 0; d < D; ++d) z[d] = 0.f;
+#pragma unroll
+                for (int c = 0; c < D; ++c) {
+                    if constexpr ((D & 3) == 0) {
+#pragma unroll
+                        for (int o = 0; o < D; o += 4) {
+                            const float4 w = *reinterpret_cast<const float4*>(s_w + c * D + o);   // broadcast load
+                            z[o] = fmaf(a[c], w.x, z[o]); z[o + 1] = fmaf(a[c], w.y, z[o + 1]);
+                            z[o + 2] = fmaf(a[c], w.z, z[o + 2]); z[o + 3] = fmaf(a[c], w.w, z[o + 3]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int o = 0; o < D; ++o) z[o] = fmaf(a[c], s_w[c * D + o], z[o]);
+                    }
+                }
+            }
             float* zo = p.z_out + tk * D;
             if ((D & 3) == 0) {
 #pragma unroll
@@ -282,10 +318,16 @@ int categ_encode_tpt_try(const cnf_categ_encode_args* a, cudaStream_t stream, in
     p.tokens = reinterpret_cast<const long long*>(a->tokens); p.u = a->u_noise; p.table = a->table;
     p.prior = a->category_prior; p.pad = a->pad; p.z_out = a->z_out; p.ldj = a->ldj; p.cpl = a->class_prob_log;
     p.status = a->status; p.T = T; p.S = (int)a->S; p.V = a->V; p.beta = a->beta; p.seed = a->seed; p.offset = a->offset;
+    p.nx_bias = a->next_actnorm_bias; p.nx_scales = a->next_actnorm_scales; p.nx_w = a->next_conv_weight;
     *handled = 1;
     CNF_TPT_DISPATCH(launch_encode)
     *handled = 0;
     return CNF_OK;
+}
+
+bool categ_encode_tpt_fusable(const cnf_categ_encode_args* a) {
+    if (!tpt_eligible(a->V, a->D, a->B * a->S)) return false;
+    return !((a->D & 3) == 0 && (reinterpret_cast<uintptr_t>(a->z_out) & 15));
 }
 
 int categ_decode_tpt_try(const cnf_categ_decode_args* a, cudaStream_t stream, int* handled) {

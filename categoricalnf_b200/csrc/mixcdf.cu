@@ -20,6 +20,7 @@
 namespace cnf {
 
 int mixcdf_pipe_try(const cnf_mixcdf_args* a, const MaskView& mask, int reverse, cudaStream_t stream, int* handled);
+bool mixcdf_pipe_fusable(const cnf_mixcdf_args* a, const MaskView& mask, int reverse);
 
 namespace {
 using namespace mixmath;
@@ -221,8 +222,6 @@ int run(const cnf_mixcdf_args* a, cnf_stream_t stream_, int reverse) {
     CNF_SUPPORTED(a->C <= CNF_MAX_CHANNELS, "C=%d exceeds CNF_MAX_CHANNELS=%d", a->C, CNF_MAX_CHANNELS);
     CNF_SUPPORTED(a->K <= CNF_MAX_MIXTURES, "K=%d exceeds CNF_MAX_MIXTURES=%d", a->K, CNF_MAX_MIXTURES);
     CNF_SUPPORTED(a->S < (1ll << 31) && a->B * a->S < (1ll << 40), "tensor too large");
-    CNF_SUPPORTED(a->next_actnorm_bias == nullptr && a->next_actnorm_scales == nullptr && a->next_conv_weight == nullptr,
-                  "fused next-block epilogue is not available in this build");
     MixParams p{};
     int rc = build_mask(a->mask, a->C, &p.mask);
     if (rc != CNF_OK) return rc;
@@ -242,6 +241,9 @@ int run(const cnf_mixcdf_args* a, cnf_stream_t stream_, int reverse) {
         rc = mixcdf_pipe_try(a, p.mask, reverse, stream, &handled);
         if (rc != CNF_OK || handled) return rc;
     }
+    CNF_SUPPORTED(a->next_actnorm_bias == nullptr && a->next_actnorm_scales == nullptr && a->next_conv_weight == nullptr,
+                  "the fused next-block epilogue needs the pipelined layout (forward, C=16, 8 transformed channels, K=8); "
+                  "query cnf_mixcdf_fusable first");
     if (p.mask.n_t == 0) {  // nothing is transformed: copy (times pad) - degenerate but legal
         if (a->z_out != a->z) CNF_CUDA(cudaMemcpyAsync(a->z_out, a->z, nz * sizeof(float), cudaMemcpyDeviceToDevice, stream));
         CNF_SUPPORTED(a->pad == nullptr, "mask with no transformed channel together with a padding mask");
@@ -279,5 +281,12 @@ int run(const cnf_mixcdf_args* a, cnf_stream_t stream_, int reverse) {
 }  // namespace
 }  // namespace cnf
 
+extern "C" int cnf_mixcdf_fusable(const cnf_mixcdf_args* a) {
+    if (a == nullptr || a->C < 1 || a->C > CNF_MAX_CHANNELS) return 0;
+    static const bool force_generic = getenv("CNF_B200_MIXCDF_GENERIC") != nullptr;
+    cnf::MaskView mv{};
+    if (force_generic || cnf::build_mask(a->mask, a->C, &mv) != CNF_OK) return 0;
+    return cnf::mixcdf_pipe_fusable(a, mv, 0) ? 1 : 0;
+}
 extern "C" int cnf_mixcdf_fwd(const cnf_mixcdf_args* a, cnf_stream_t stream) { return cnf::run(a, stream, 0); }
 extern "C" int cnf_mixcdf_inv(const cnf_mixcdf_args* a, cnf_stream_t stream) { return cnf::run(a, stream, 1); }

@@ -39,6 +39,9 @@ struct PipeParams {
     float* ldj;
     float* reg_ldj;
     uint32_t* status;
+    const float* nx_bias;    // fused epilogue: ActNorm + 1x1 conv of the next flow block (or NULL)
+    const float* nx_scales;
+    const float* nx_w;
     long long P;       // positions
     long long ntiles;
     int S, C, c0;      // c0: first transformed channel
@@ -83,8 +86,15 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 template <int KT>
 constexpr int stages_for() { return KT >= 16 ? 2 : 3; }
 
-template <int KT, int CT, bool REV>
+// FC > 0: the next block's ActNorm and 1x1 convolution (C = FC channels) are applied to the full
+// output row before it is stored (activation_normalization.py:35-43, permutation_layers.py:111-121):
+//   a = (z + bias) e^{scales} pad ;  y = (a @ W) pad
+// saving two full read+write passes over z per flow block.  Their ldj terms are per-sample constants
+// added by the caller (cnf_ldj_axpy).
+template <int KT, int CT, bool REV, int FC>
 __global__ void __launch_bounds__(kThreadsPipe, 2) mixcdf_pipe_kernel(const PipeParams p) {
+    constexpr bool FUSE = FC > 0;
+    constexpr int NO = FUSE ? FC / CT : 1;   // output channels per lane in the fused epilogue
     constexpr int kStages = stages_for<KT>();
     constexpr int PN = 2 + 3 * KT;
     constexpr int L = CT * PN;            // parameter floats per position (transformed channels)
@@ -102,6 +112,12 @@ __global__ void __launch_bounds__(kThreadsPipe, 2) mixcdf_pipe_kernel(const Pipe
     float* s_mfac = reinterpret_cast<float*>(s_bnd + CT * KT);    // [CT * KT] e^{msf} (float64 escape only)
     uint64_t* full = reinterpret_cast<uint64_t*>(s_mfac + CT * KT + ((CT * KT) & 1));
     uint64_t* empty = full + kStages;
+    // fused epilogue tables: bias [FC], e^{scales} [FC], W regrouped so lane j finds its NO columns
+    // (j, j+CT, ..) of row c contiguously at (c*CT + j)*NO, and one scratch row block per warp
+    float* s_nb = reinterpret_cast<float*>(empty + kStages);
+    float* s_ne = s_nb + FC;
+    float* s_wt = s_ne + FC;                       // [FC * FC]
+    float* s_row = s_wt + FC * FC;                 // [kConsumerWarps][RW * FC]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long t0 = (p.ntiles * (long long)blockIdx.x) / gridDim.x;
@@ -119,6 +135,17 @@ __global__ void __launch_bounds__(kThreadsPipe, 2) mixcdf_pipe_kernel(const Pipe
         s_mfac[i] = mf;
         // [k][j] layout: the CT lanes of a position read consecutive 8-byte words (no bank conflict)
         s_bnd[(i % KT) * CT + i / KT] = make_float2(2.0f * kLog2e / fmaxf(mf, 1.0f), -mf * kLog2e);
+    }
+    if constexpr (FUSE) {
+        for (int i = tid; i < FC; i += kThreadsPipe) {
+            s_nb[i] = p.nx_bias ? p.nx_bias[i] : 0.f;
+            s_ne[i] = p.nx_scales ? expf(p.nx_scales[i]) : 1.0f;
+        }
+        for (int i = tid; i < FC * FC; i += kThreadsPipe) {
+            const int c = i / FC, o = i % FC;      // W[c][o], z @ W
+            const float w = p.nx_w ? p.nx_w[i] : (c == o ? 1.0f : 0.f);
+            s_wt[(c * CT + o % CT) * NO + o / CT] = w;
+        }
     }
     __syncthreads();
 
@@ -235,13 +262,45 @@ __global__ void __launch_bounds__(kThreadsPipe, 2) mixcdf_pipe_kernel(const Pipe
                 flag(p.status, (res.z != res.z ? CNF_FLAG_NAN_Z : 0u) | (res.ldj != res.ldj ? CNF_FLAG_NAN_LDJ : 0u));
         }
         // ---- z row: transformed channel + conditioner copies, times pad (:76) ----------------------
-        if (valid) {
-            orow[ch] = out * padv;
+        if constexpr (!FUSE) {
+            if (valid) {
+                orow[ch] = out * padv;
+#pragma unroll
+                for (int n = 0; n < kMaxCopy; ++n) {
+                    const int c = j + n * CT;
+                    const int cc = (c < p.c0) ? c : c + CT;
+                    if (c < C - CT) orow[cc] = cval[n] * padv;
+                }
+            }
+        } else {
+            // next block's ActNorm on this lane's channels -> warp scratch row -> 1x1 conv columns
+            float* srow = s_row + (warp * RW + (r % RW)) * FC;
+            srow[ch] = (out * padv + s_nb[ch]) * s_ne[ch] * padv;
 #pragma unroll
             for (int n = 0; n < kMaxCopy; ++n) {
                 const int c = j + n * CT;
                 const int cc = (c < p.c0) ? c : c + CT;
-                if (c < C - CT) orow[cc] = cval[n] * padv;
+                if (c < FC - CT) srow[cc] = (cval[n] * padv + s_nb[cc]) * s_ne[cc] * padv;
+            }
+            __syncwarp();
+            float y[NO];
+#pragma unroll
+            for (int n = 0; n < NO; ++n) y[n] = 0.f;
+#pragma unroll
+            for (int c4 = 0; c4 < FC; c4 += 4) {
+                const float4 a = *reinterpret_cast<const float4*>(srow + c4);
+                const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float* wr = s_wt + ((c4 + i) * CT + j) * NO;
+#pragma unroll
+                    for (int n = 0; n < NO; ++n) y[n] = fmaf(av[i], wr[n], y[n]);
+                }
+            }
+            __syncwarp();
+            if (valid) {
+#pragma unroll
+                for (int n = 0; n < NO; ++n) orow[j + n * CT] = y[n] * padv;
             }
         }
         // ---- ldj -----------------------------------------------------------------------------------
@@ -279,28 +338,29 @@ __global__ void __launch_bounds__(kThreadsPipe, 2) mixcdf_pipe_kernel(const Pipe
     flush();
 }
 
-template <int KT, int CT>
+template <int KT, int CT, int FC>
 size_t pipe_smem(int C) {
     constexpr int PN = 2 + 3 * KT, L = CT * PN, TP = kConsumers / CT, kStages = stages_for<KT>();
     size_t f = (size_t)kStages * TP * L + (size_t)kStages * TP * C + 3 * (size_t)CT * KT + ((CT * KT) & 1);
+    f += 2 * (size_t)FC + (size_t)FC * FC + (size_t)kConsumers / CT * FC;   // fused epilogue tables + scratch rows
     return f * sizeof(float) + 2 * kStages * sizeof(uint64_t);
 }
 
-template <int KT, int CT, bool REV>
+template <int KT, int CT, bool REV, int FC = 0>
 int launch_pipe(const PipeParams& p, cudaStream_t stream) {
-    const size_t smem = pipe_smem<KT, CT>(p.C);
+    const size_t smem = pipe_smem<KT, CT, FC>(p.C);
     constexpr int kMaxSmem = 113 * 1024;   // two CTAs per SM
     CNF_SUPPORTED(smem <= (size_t)kMaxSmem, "pipelined mixcdf tile needs %zu bytes of shared memory", smem);
     static thread_local int configured_dev = -1;
     int dev = 0;
     CNF_CUDA(cudaGetDevice(&dev));
     if (configured_dev != dev) {
-        CNF_CUDA(cudaFuncSetAttribute(mixcdf_pipe_kernel<KT, CT, REV>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        CNF_CUDA(cudaFuncSetAttribute(mixcdf_pipe_kernel<KT, CT, REV, FC>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
         configured_dev = dev;
     }
     long long grid = 2ll * sm_count();
     if (grid > p.ntiles) grid = p.ntiles;
-    mixcdf_pipe_kernel<KT, CT, REV><<<(unsigned)grid, kThreadsPipe, smem, stream>>>(p);
+    mixcdf_pipe_kernel<KT, CT, REV, FC><<<(unsigned)grid, kThreadsPipe, smem, stream>>>(p);
     return launch_status(REV ? "mixcdf_pipe_kernel<inv>" : "mixcdf_pipe_kernel<fwd>");
 }
 
@@ -311,30 +371,46 @@ int launch_pipe_dir(const PipeParams& p, int reverse, cudaStream_t stream) {
 
 }  // namespace
 
+// Layouts the pipelined kernel takes: compile-time (K, Ct) pair, one contiguous transformed run per
+// position, everything 16-byte aligned for the bulk copies.
+static bool pipe_eligible(const cnf_mixcdf_args* a, const MaskView& mask) {
+    const int K = a->K, C = a->C, Ct = mask.n_t, PN = 2 + 3 * K;
+    if (a->params_prebounded) return false;   // explicit-parameter callers: generic kernel
+    if (!(K == 8 || K == 4 || K == 16)) return false;
+    if (!mask.contiguous || !(Ct == 8 || Ct == 16 || Ct == 4)) return false;
+    if (C % 4 != 0 || C > 32) return false;
+    if ((Ct * PN) % 4 != 0 || (mask.c0 * PN) % 4 != 0 || (C * PN) % 4 != 0) return false;
+    if ((reinterpret_cast<uintptr_t>(a->nn_out) & 15) || (reinterpret_cast<uintptr_t>(a->z) & 15)) return false;
+    if (K == 16 && Ct == 16) return false;   // two stages of 16 x 800 floats would not fit twice per SM
+    return true;
+}
+
+// The fused next-block epilogue is compiled for the LM layout (C = 16, Ct = 8, K = 8), forward only.
+bool mixcdf_pipe_fusable(const cnf_mixcdf_args* a, const MaskView& mask, int reverse) {
+    return !reverse && pipe_eligible(a, mask) && a->K == 8 && mask.n_t == 8 && a->C == 16;
+}
+
 // Returns CNF_OK and sets *handled = 1 when the pipelined kernel was launched; *handled = 0 when the
 // layout is not eligible and the caller must use the generic kernel.  ldj / reg_ldj have already
 // been zeroed (or are accumulated into) by the caller.
 int mixcdf_pipe_try(const cnf_mixcdf_args* a, const MaskView& mask, int reverse, cudaStream_t stream, int* handled) {
     *handled = 0;
-    const int K = a->K, C = a->C, Ct = mask.n_t, PN = 2 + 3 * K;
-    if (a->params_prebounded) return CNF_OK;   // explicit-parameter callers: generic kernel
-    if (!(K == 8 || K == 4 || K == 16)) return CNF_OK;
-    if (!mask.contiguous || !(Ct == 8 || Ct == 16 || Ct == 4)) return CNF_OK;
-    if (C % 4 != 0 || C > 32) return CNF_OK;
-    // bulk copies need 16-byte aligned sources and sizes
-    if ((Ct * PN) % 4 != 0 || (mask.c0 * PN) % 4 != 0 || (C * PN) % 4 != 0) return CNF_OK;
-    if ((reinterpret_cast<uintptr_t>(a->nn_out) & 15) || (reinterpret_cast<uintptr_t>(a->z) & 15)) return CNF_OK;
-    if (K == 16 && Ct == 16) return CNF_OK;   // two stages of 16 x 800 floats would not fit twice per SM
+    if (!pipe_eligible(a, mask)) return CNF_OK;
+    const int K = a->K, C = a->C, Ct = mask.n_t;
+    const bool fuse = a->next_actnorm_bias || a->next_actnorm_scales || a->next_conv_weight;
+    if (fuse && !mixcdf_pipe_fusable(a, mask, reverse)) return CNF_OK;   // caller reports "unsupported"
     const long long P = a->B * a->S;
     PipeParams p{};
     p.z = a->z; p.nn = a->nn_out; p.pad = a->pad; p.sf = a->scaling_factor; p.msf = a->mixture_scaling_factor;
     p.z_out = a->z_out; p.ldj = a->ldj; p.reg_ldj = a->reg_ldj; p.status = a->status;
+    p.nx_bias = a->next_actnorm_bias; p.nx_scales = a->next_actnorm_scales; p.nx_w = a->next_conv_weight;
     p.P = P; p.S = (int)a->S; p.C = C; p.c0 = mask.c0; p.s_period = mask.s_period; p.cond_s = mask.cond_s;
     p.reg_max = a->reg_max; p.reg_factor = a->reg_factor;
     p.use_reg = (!reverse && a->reg_max > 0.f && a->training) ? 1 : 0;
     const int TP = kConsumers / Ct;
     p.ntiles = (P + TP - 1) / TP;
     *handled = 1;
+    if (fuse) return launch_pipe<8, 8, false, 16>(p, stream);
 #define CNF_PIPE_CASE(KK, CC) \
     if (K == KK && Ct == CC) return launch_pipe_dir<KK, CC>(p, reverse, stream);
     CNF_PIPE_CASE(8, 8)

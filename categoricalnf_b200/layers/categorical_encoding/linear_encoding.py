@@ -101,6 +101,27 @@ class LinearCategoricalEncoding(FlowLayer):
             return z_out, ldj, detailed_ldj
         return self._composed_forward(z, ldj, reverse, beta, channel_padding_mask, u_noise, **kwargs)
 
+    def try_forward_fused(self, z, actnorm, conv, beta=1, delta=0.0, channel_padding_mask=None, u_noise=None,
+                          length=None, **kwargs):
+        """Encode AND apply the first flow block's ``ActNormFlow`` + ``InvertibleConv`` in one kernel
+        (evaluation only); None when not available for this configuration."""
+        if self.training or not self._fused_ok(z):
+            return None
+        B, S = z.size(0), z.size(1)
+        if not ops.categ_encode_fusable(B, S, self.num_categories, self.D):
+            return None
+        from ..flows.mixture_cdf_layer import add_next_block_ldj
+        with torch.no_grad():
+            table = self.class_table()
+        weight, sldj = conv._get_weight(device_name=str(z.device), inverse=False)
+        ldj = torch.zeros(B, dtype=torch.float32, device=z.device)
+        seed, offset = (0, 0) if u_noise is not None else philox_stream(z.device, B * S * self.D)
+        z_out, ldj, _ = ops.categ_encode(z.reshape(B, S), table, self.category_prior, ldj, noise=u_noise, seed=seed,
+                                         offset=offset, pad=channel_padding_mask, beta=float(beta),
+                                         fuse_next=(actnorm.bias, actnorm.scales, weight))
+        add_next_block_ldj(ldj, actnorm, sldj, S, channel_padding_mask, length)
+        return z_out, ldj, {}
+
     # -- general path: linear flows / decoder / training (composition of the flow layers) -----------
     def _composed_forward(self, z, ldj, reverse, beta, channel_padding_mask, u_noise, **kwargs):
         batch_size, seq_length = z.size(0), z.size(1)

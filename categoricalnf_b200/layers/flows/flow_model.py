@@ -11,6 +11,8 @@ import torch
 import torch.nn as nn
 
 from ... import ops
+from .activation_normalization import ActNormFlow
+from .permutation_layers import InvertibleConv
 
 
 class FlowModel(nn.Module):
@@ -19,6 +21,7 @@ class FlowModel(nn.Module):
         super().__init__()
         self.flow_layers = nn.ModuleList()
         self.name = name
+        self.fuse_blocks = True   # evaluation-time kernel fusion across layer boundaries (results identical)
         if layers is not None:
             self.add_layers(layers)
 
@@ -34,8 +37,23 @@ class FlowModel(nn.Module):
         if reverse:
             order.reverse()
         ldj_per_layer = []
-        for index, layer in order:
-            res = layer(z, reverse=reverse, get_ldj_per_layer=get_ldj_per_layer, **kwargs)
+        skip = 0
+        can_fuse = self.fuse_blocks and not reverse and not get_ldj_per_layer and not torch.is_grad_enabled() and z.is_cuda
+        for pos, (index, layer) in enumerate(order):
+            if skip > 0:
+                skip -= 1
+                continue
+            res = None
+            if can_fuse and hasattr(layer, "try_forward_fused") and pos + 2 < len(order):
+                # [encoding | mixture coupling] followed by ActNorm + 1x1 conv: the two bandwidth-only
+                # layers run inside the producing kernel's epilogue (two passes over z saved per block)
+                an, conv = order[pos + 1][1], order[pos + 2][1]
+                if type(an) is ActNormFlow and type(conv) is InvertibleConv and not an.training and not conv.training:
+                    res = layer.try_forward_fused(z, an, conv, **kwargs)
+                    if res is not None:
+                        skip = 2
+            if res is None:
+                res = layer(z, reverse=reverse, get_ldj_per_layer=get_ldj_per_layer, **kwargs)
             if len(res) == 2:
                 z, layer_ldj = res
                 detail = layer_ldj

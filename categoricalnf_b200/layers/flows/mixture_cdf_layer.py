@@ -9,6 +9,7 @@ import torch
 import torch.nn as nn
 
 from ... import functional as CF
+from ... import ops
 from ._masks import mask_lists
 from .coupling_layer import CouplingLayer
 
@@ -61,6 +62,20 @@ def _mask_from_tensor(mask, z):
     raise NotImplementedError("joint position x channel mask of shape %s" % (tuple(mask.shape),))
 
 
+def add_next_block_ldj(ldj, actnorm, sldj, S, channel_padding_mask, length):
+    """ldj[b] += sum(scales) * len_act[b] + sldj * len_conv[b]: the per-sample-constant terms of a fused
+    ActNorm (activation_normalization.py:27-40: length, else unpadded positions, else S) and
+    InvertibleConv (permutation_layers.py:111-117: length, else S)."""
+    ssum = actnorm.scales.detach().sum().reshape(1)
+    if length is not None:
+        ops.ldj_axpy(ldj, alpha_dev=ssum + sldj.reshape(1), length=length.float())
+    elif channel_padding_mask is None:
+        ops.ldj_axpy(ldj, alpha=float(S), alpha_dev=ssum + sldj.reshape(1))
+    else:
+        ops.ldj_axpy(ldj, alpha_dev=ssum, length=channel_padding_mask.reshape(ldj.shape[0], -1).sum(dim=1))
+        ops.ldj_axpy(ldj, alpha=float(S), alpha_dev=sldj.reshape(1))
+
+
 class MixtureCDFCoupling(CouplingLayer):
 
     def __init__(self, c_in, mask, model_func, block_type=None, num_mixtures=10, regularizer_max=-1,
@@ -81,6 +96,30 @@ class MixtureCDFCoupling(CouplingLayer):
                                     reg_max=self.regularizer_max, reg_factor=self.regularizer_factor,
                                     training=self.training)
         return z_out, ldj, {"ldj": ldj, "regularizer_ldj": reg}
+
+    def try_forward_fused(self, z, actnorm, conv, channel_padding_mask=None, length=None, **kwargs):
+        """Forward of this layer AND of the following ``ActNormFlow`` + ``InvertibleConv`` in one kernel
+        (evaluation only).  Returns ``(z, ldj, detail)`` with the three layers' ldj summed, or None
+        when the kernel cannot fuse for this shape / mask (caller then runs the layers one by one)."""
+        if self.training or z.dim() != 3:
+            return None
+        mask_c, mask_s = mask_lists(self, "mask", z.size(1))
+        # cheap shape pre-check (the kernel fuses for C=16, K=8, 8 contiguous transformed channels) so the
+        # network is not run twice; the library has the final word below
+        if z.size(2) != 16 or self.num_mixtures != 8 or mask_s is not None or mask_c is None or \
+                sum(1 for m in mask_c if m == 0) != 8:
+            return None
+        nn_out = self.run_network(x=z * self._prepare_mask(self.mask, z), length=length, **kwargs)
+        if not ops.mixcdf_fusable(z, nn_out, self.num_mixtures, mask_c=mask_c, mask_s=mask_s):
+            return None   # note: the network has run; the caller's unfused call runs it again
+        weight, sldj = conv._get_weight(device_name=str(z.device), inverse=False)
+        z_out, ldj, reg = ops.mixcdf(z, nn_out, self.num_mixtures, mask_c=mask_c, mask_s=mask_s, pad=channel_padding_mask,
+                                     scaling_factor=self.scaling_factor, mixture_scaling_factor=self.mixture_scaling_factor,
+                                     reg_max=self.regularizer_max, reg_factor=self.regularizer_factor, training=False,
+                                     want_reg=True, fuse_next=(actnorm.bias, actnorm.scales, weight))
+        detail = {"ldj": ldj.clone(), "regularizer_ldj": reg}
+        add_next_block_ldj(ldj, actnorm, sldj, z.size(1), channel_padding_mask, length)
+        return z_out, ldj, detail
 
     # -- static entry points used by other files ----------------------------------------------------
     @staticmethod

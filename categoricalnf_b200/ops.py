@@ -122,10 +122,7 @@ def _call(name, args, ref: torch.Tensor, keep=None):
 
 
 # ----------------------------------------------------------------------------------------------
-def mixcdf(z, nn_out, num_mixtures, *, mask_c=None, mask_s=None, pad=None, scaling_factor=None,
-           mixture_scaling_factor=None, reverse=False, reg_max=-1.0, reg_factor=1.0, training=False,
-           ldj=None, want_reg=False, out=None, prebounded=False):
-    """K1/K2.  Returns ``(z_out, ldj[B], reg_ldj[B] | None)``.  ``ldj`` given -> accumulated into."""
+def _mixcdf_args(z, nn_out, num_mixtures, mask_c, mask_s, pad, scaling_factor, mixture_scaling_factor):
     z = _f32(z, "z")
     if z.dim() != 3:
         raise ValueError("z must be [B, S, C]")
@@ -138,17 +135,44 @@ def mixcdf(z, nn_out, num_mixtures, *, mask_c=None, mask_s=None, pad=None, scali
     a.mask, keep = _mask_struct(mask_c, mask_s)
     sf = _opt_f32(scaling_factor, "scaling_factor", (Cc,))
     msf = _opt_f32(mixture_scaling_factor, "mixture_scaling_factor", (Cc, K))
+    a.z, a.nn_out, a.pad = _ptr(z), _ptr(nn_out), _ptr(pad)
+    a.scaling_factor, a.mixture_scaling_factor = _ptr(sf), _ptr(msf)
+    return a, (keep, z, nn_out, pad, sf, msf)
+
+
+def mixcdf_fusable(z, nn_out, num_mixtures, *, mask_c=None, mask_s=None, prebounded=False):
+    """True when ``mixcdf(..., fuse_next=...)`` is available for this shape / mask / alignment."""
+    a, keep = _mixcdf_args(z, nn_out, num_mixtures, mask_c, mask_s, None, None, None)
+    a.params_prebounded = int(bool(prebounded))
+    return bool(L.load().cnf_mixcdf_fusable(C.byref(a)))
+
+
+def mixcdf(z, nn_out, num_mixtures, *, mask_c=None, mask_s=None, pad=None, scaling_factor=None,
+           mixture_scaling_factor=None, reverse=False, reg_max=-1.0, reg_factor=1.0, training=False,
+           ldj=None, want_reg=False, out=None, prebounded=False, fuse_next=None):
+    """K1/K2.  Returns ``(z_out, ldj[B], reg_ldj[B] | None)``.  ``ldj`` given -> accumulated into.
+    ``fuse_next = (bias [C], scales [C], W [C,C])`` applies the next block's ActNorm and 1x1
+    convolution to the output row inside the kernel (forward only, see ``mixcdf_fusable``); their
+    per-sample-constant ldj terms are NOT added here."""
+    a, keep = _mixcdf_args(z, nn_out, num_mixtures, mask_c, mask_s, pad, scaling_factor, mixture_scaling_factor)
+    z = keep[1]
+    B = z.shape[0]
     z_out = torch.empty_like(z) if out is None else out
     accumulate = ldj is not None
     ldj_t = _f32(ldj, "ldj", (B,)) if accumulate else torch.empty(B, dtype=torch.float32, device=z.device)
     reg = torch.empty(B, dtype=torch.float32, device=z.device) if want_reg else None
-    a.z, a.nn_out, a.pad = _ptr(z), _ptr(nn_out), _ptr(pad)
-    a.scaling_factor, a.mixture_scaling_factor = _ptr(sf), _ptr(msf)
     a.reg_max, a.reg_factor, a.training = float(reg_max), float(reg_factor), int(bool(training))
     a.accumulate = int(accumulate)
     a.params_prebounded = int(bool(prebounded))
     a.z_out, a.ldj, a.reg_ldj = _ptr(z_out), _ptr(ldj_t), _ptr(reg)
     a.status = _ptr(status_word(z.device))
+    if fuse_next is not None:
+        Cc = z.shape[2]
+        nb = _f32(fuse_next[0], "next bias").reshape(-1)
+        ns = _f32(fuse_next[1], "next scales").reshape(-1)
+        nw = _f32(fuse_next[2], "next conv weight", (Cc, Cc))
+        keep = keep + (nb, ns, nw)
+        a.next_actnorm_bias, a.next_actnorm_scales, a.next_conv_weight = _ptr(nb), _ptr(ns), _ptr(nw)
     _call("cnf_mixcdf_inv" if reverse else "cnf_mixcdf_fwd", a, z, keep)
     return z_out, ldj_t, reg
 
@@ -259,8 +283,11 @@ def invconv_apply(z, weight, sldj, ldj=None, *, pad=None, length=None, reverse=F
 
 
 def categ_encode(tokens, table, category_prior, ldj, *, noise=None, seed=0, offset=0, pad=None, beta=1.0,
-                 want_class_prob=False):
-    """K6 encode.  tokens [B,S] int64 -> (z [B,S,D], ldj (in place), class_prob_log [B,S] | None)."""
+                 want_class_prob=False, fuse_next=None):
+    """K6 encode.  tokens [B,S] int64 -> (z [B,S,D], ldj (in place), class_prob_log [B,S] | None).
+    ``fuse_next = (bias [D], scales [D], W [D,D])`` applies the first block's ActNorm + 1x1 convolution
+    inside the kernel when the shape allows it; returns None as first element otherwise is NOT done -
+    call :func:`categ_encode_fusable` first."""
     if not tokens.is_cuda:
         raise RuntimeError("categoricalnf_b200: tokens live on %s - CUDA only" % tokens.device)
     tokens = tokens.long().contiguous()
@@ -282,8 +309,22 @@ def categ_encode(tokens, table, category_prior, ldj, *, noise=None, seed=0, offs
     a.tokens, a.u_noise, a.seed, a.offset = _ptr(tokens), _ptr(noise), int(seed), int(offset)
     a.table, a.category_prior, a.pad, a.beta = _ptr(table), _ptr(prior), _ptr(pad), float(beta)
     a.z_out, a.ldj, a.class_prob_log, a.status = _ptr(z), _ptr(ldj), _ptr(cpl), _ptr(status_word(z.device))
-    _call("cnf_categ_encode", a, z)
+    keep = None
+    if fuse_next is not None:
+        nb = _f32(fuse_next[0], "next bias").reshape(-1)
+        ns = _f32(fuse_next[1], "next scales").reshape(-1)
+        nw = _f32(fuse_next[2], "next conv weight", (D, D))
+        keep = (nb, ns, nw)
+        a.next_actnorm_bias, a.next_actnorm_scales, a.next_conv_weight = _ptr(nb), _ptr(ns), _ptr(nw)
+    _call("cnf_categ_encode", a, z, keep)
     return z, ldj, cpl
+
+
+def categ_encode_fusable(B, S, V, D):
+    """True when ``categ_encode(..., fuse_next=...)`` is available for this problem size."""
+    a = L.CategEncodeArgs()
+    a.B, a.S, a.V, a.D = B, S, V, D
+    return bool(L.load().cnf_categ_encode_fusable(C.byref(a)))
 
 
 def categ_decode(z, table, category_prior):

@@ -115,6 +115,9 @@ typedef struct {
 
 CNF_API int cnf_mixcdf_fwd(const cnf_mixcdf_args* a, cnf_stream_t stream);
 CNF_API int cnf_mixcdf_inv(const cnf_mixcdf_args* a, cnf_stream_t stream);
+/* 1 when cnf_mixcdf_fwd can apply the fused next-block epilogue (next_* fields) for this shape, mask
+ * and alignment, else 0 (the caller then runs cnf_actnorm / cnf_invconv_apply as separate calls). */
+CNF_API int cnf_mixcdf_fusable(const cnf_mixcdf_args* a);
 
 /* ------------------------------------------------------------------------------------------
  * K3  affine coupling  (layers/flows/coupling_layer.py:53-65, 76-98)
@@ -256,9 +259,15 @@ typedef struct {
     float* ldj;                   /* [B] in/out */
     float* class_prob_log;        /* [B,S] or NULL */
     uint32_t* status;
+    /* optional fused epilogue: ActNorm and 1x1 convolution of the FIRST flow block applied to the
+     * encoded latent before the store (see cnf_mixcdf_args.next_*); check cnf_categ_encode_fusable. */
+    const float* next_actnorm_bias;   /* [D] or NULL */
+    const float* next_actnorm_scales; /* [D] or NULL */
+    const float* next_conv_weight;    /* [D,D] row-major (z @ W) or NULL */
 } cnf_categ_encode_args;
 
 CNF_API int cnf_categ_encode(const cnf_categ_encode_args* a, cnf_stream_t stream);
+CNF_API int cnf_categ_encode_fusable(const cnf_categ_encode_args* a);
 
 typedef struct {
     int64_t B, S;

@@ -155,3 +155,46 @@ def test_categ_tpt_dominating_other_class():
                                    want_class_prob=True)
     assert torch.isfinite(cpl).all()
     assert_close(ldj, ldj_ref, rtol=1e-4, atol=2e-4, what="ldj")
+
+
+@pytest.mark.parametrize("padded", [False, True])
+def test_block_fusion_matches_unfused_and_oracle(padded):
+    """ActNorm + 1x1 conv fused into the epilogue of the encode / mixture kernels: module level
+    (FlowModel.fuse_blocks) and kernel level (LMDevicePath.forward(fused=...)) against the unfused
+    path and the oracle composition."""
+    import workload as W
+    from categoricalnf_b200 import ops
+    B, S = 40, 64            # 2560 tokens: large enough for the fusable encode kernel
+    prm = W.data_init_oracle(W.lm_params(seed=5, S=S, blocks=3), seed=5)
+    tokens, u = W.lm_tokens(B, S, prm.V, seed=5), W.lm_noise(B, S, prm.D, seed=5)
+    dev_ = torch.device("cuda", 0)
+    path = W.LMDevicePath(prm, dev_)
+    if not padded:
+        z_ref, ldj_ref, lp_ref = W.lm_oracle_forward(prm, tokens, u)
+        z0, ldj0, lp0 = path.forward(tokens.to(dev_), u_noise=u.to(dev_), fused=False)
+        z1, ldj1, lp1 = path.forward(tokens.to(dev_), u_noise=u.to(dev_), fused=True)
+        assert ops.categ_encode_fusable(B, S, prm.V, prm.D)
+        for z, ldj, lp, what in ((z0, ldj0, lp0, "unfused"), (z1, ldj1, lp1, "fused")):
+            assert_close(z, z_ref, what="z " + what)
+            assert_close(ldj, ldj_ref, rtol=1e-4, atol=2e-4, what="ldj " + what)
+            assert_close(lp, lp_ref, rtol=1e-4, atol=2e-4, what="log prior " + what)
+    model, _ = W.build_lm_model(prm, dev_)
+    kw = {}
+    if padded:
+        length = torch.randint(S // 2, S + 1, (B,), generator=torch.Generator().manual_seed(1))
+        pad = (torch.arange(S).view(1, S) < length.view(-1, 1)).float().unsqueeze(-1)
+        kw = dict(channel_padding_mask=pad.to(dev_), length=length.to(dev_))
+    outs = []
+    launches = []
+    for fuse in (False, True):
+        model.fuse_blocks = fuse
+        n0 = ops.launch_count()
+        with torch.no_grad():
+            outs.append(model(tokens.to(dev_), u_noise=u.to(dev_), **kw))
+        launches.append(ops.launch_count() - n0)
+    assert launches[1] < launches[0], "fusion did not remove launches: %s" % (launches,)
+    assert_close(outs[1][0], outs[0][0], rtol=1e-5, atol=2e-6, what="z fused vs unfused (modules)")
+    assert_close(outs[1][1], outs[0][1], rtol=1e-5, atol=2e-4, what="ldj fused vs unfused (modules)")
+    if not padded:
+        assert_close(outs[1][0], z_ref, what="z modules")
+        assert_close(outs[1][1], ldj_ref, rtol=1e-4, atol=2e-4, what="ldj modules")

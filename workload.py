@@ -145,6 +145,7 @@ class LMDevicePath:
             self.blocks.append(dict(bias=d(b["bias"]), scales=d(b["scales"]), w=w, sldj=sldj, sf=d(b["sf"]), msf=d(b["msf"]),
                                     mask_c=b["mask"].flatten().tolist(), net_w=d(b["net_w"]), net_b=d(b["net_b"])))
         self.mix_events = []   # (start, end) CUDA events around every mixture-coupling launch when timing
+        self.ldj_const = None
 
     def data_init(self, seed=0):
         """Data-dependent ActNorm initialisation with the product's own kernels
@@ -159,6 +160,7 @@ class LMDevicePath:
         for b, pb in zip(self.blocks, prm.blocks):
             b["bias"], b["scales"] = ops.actnorm_data_init(z)
             pb["bias"], pb["scales"] = b["bias"].cpu(), b["scales"].cpu()
+            self.ldj_const = None
             z, _ = ops.actnorm(z, b["bias"], b["scales"], None)
             z, _ = ops.invconv_apply(z, b["w"], b["sldj"], None)
             zin = z * torch.tensor(b["mask_c"], device=self.dev)
@@ -167,15 +169,32 @@ class LMDevicePath:
                                  mixture_scaling_factor=b["msf"])
         return self
 
-    def forward(self, tokens, nn_outs=None, u_noise=None, seed=0, offset=0, time_mix=False):
-        """-> (z, ldj [B], log_prior [B]).  ``nn_outs`` None evaluates the stand-in net with torch."""
+    def forward(self, tokens, nn_outs=None, u_noise=None, seed=0, offset=0, time_mix=False, fused=True):
+        """-> (z, ldj [B], log_prior [B]).  ``nn_outs`` None evaluates the stand-in net with torch.
+        ``fused``: ActNorm + 1x1 conv of block i+1 run in the epilogue of the kernel producing its
+        input (encode for block 0, mixture coupling i otherwise); identical results, 2 launches and
+        two passes over z fewer per block."""
         ops, prm = self.ops, self.prm
-        B = tokens.shape[0]
+        B, S = tokens.shape
+        nb = len(self.blocks)
         ldj = torch.zeros(B, dtype=torch.float32, device=self.dev)
-        z, ldj, _ = ops.categ_encode(tokens, self.table, self.prior, ldj, noise=u_noise, seed=seed, offset=offset)
+        fused = fused and ops.categ_encode_fusable(B, S, prm.V, prm.D)
+
+        def nxt(i):
+            b = self.blocks[i]
+            return (b["bias"], b["scales"], b["w"])
+
+        if fused:
+            if self.ldj_const is None:   # sum over blocks of (sum scales + sldj): per-sample constant x S
+                self.ldj_const = torch.stack([b["scales"].sum() + b["sldj"].reshape(()) for b in self.blocks]).sum().reshape(1)
+            z, ldj, _ = ops.categ_encode(tokens, self.table, self.prior, ldj, noise=u_noise, seed=seed, offset=offset,
+                                         fuse_next=nxt(0))
+        else:
+            z, ldj, _ = ops.categ_encode(tokens, self.table, self.prior, ldj, noise=u_noise, seed=seed, offset=offset)
         for i, b in enumerate(self.blocks):
-            z, ldj = ops.actnorm(z, b["bias"], b["scales"], ldj)
-            z, ldj = ops.invconv_apply(z, b["w"], b["sldj"], ldj)
+            if not fused:
+                z, ldj = ops.actnorm(z, b["bias"], b["scales"], ldj)
+                z, ldj = ops.invconv_apply(z, b["w"], b["sldj"], ldj)
             if nn_outs is not None:
                 nn_out = nn_outs[i]
             else:
@@ -184,11 +203,16 @@ class LMDevicePath:
             if time_mix:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
+            fuse_next = nxt(i + 1) if (fused and i + 1 < nb) else None
+            if fuse_next is not None and not ops.mixcdf_fusable(z, nn_out, prm.K, mask_c=b["mask_c"]):
+                raise RuntimeError("LMDevicePath: coupling %d is not fusable although the encode was" % i)
             z, ldj, _ = ops.mixcdf(z, nn_out, prm.K, mask_c=b["mask_c"], scaling_factor=b["sf"],
-                                   mixture_scaling_factor=b["msf"], ldj=ldj)
+                                   mixture_scaling_factor=b["msf"], ldj=ldj, fuse_next=fuse_next)
             if time_mix:
                 e1.record()
                 self.mix_events.append((e0, e1))
+        if fused:
+            ops.ldj_axpy(ldj, alpha=float(S), alpha_dev=self.ldj_const)
         logp, _ = ops.logistic_logprob(z)
         return z, ldj, logp
 
