@@ -320,7 +320,7 @@ __device__ __forceinline__ ElemResult mix_forward_fast(const MixEval& e, const M
     return r;
 }
 
-// Inverse by bracketed bisection in fp32 registers.  Returns false when the element must be
+// Inverse in fp32 registers (safeguarded Newton, see below).  Returns false when the element must be
 // finished by mix_inverse_f64 (flat CDF around the root); x / lb / ub then describe where to resume.
 template <int KT>
 struct InvState {
@@ -348,14 +348,32 @@ __device__ __forceinline__ bool mix_inverse_fast(float zin, const MixPrep<KT>& P
         ub = fmaxf(ub, fmaf(20.f, P.span, P.mu[k]));
     }
     st.lb0 = lb; st.ub0 = ub;
-    float x = 0.f;
+    // Root of logit F(x) = logit(target) by Newton's method in logit space (for one logistic the
+    // function is linear there, for mixtures close to it), safeguarded by the reference's bracket
+    // ("rtsafe"): a step that leaves [lb, ub] or fails to halve the previous one is replaced by the
+    // reference's bisection step (:255-262).  The root is unique (the CDF is strictly increasing), so
+    // this lands on the point the reference's float64 bisection approaches.
+    const float yc = (lg2(Ft) - lg2(Gt)) * kLn2;   // logit of the clamped target
+    float x = 0.f, prev = INFINITY;
     MixEval e = mix_eval_p<KT>(x, P);
     for (int it = 0; it < 48; ++it) {
         const bool gt = upper ? (e.G < Gt) : (e.F > Ft);
         if (gt) ub = x; else lb = x;
-        const float xn = 0.5f * (lb + ub);
-        const bool done = (xn == x) || !(ub - lb > 5e-7f * fmaxf(1.0f, fabsf(xn)));
+        const float mid = 0.5f * (lb + ub);
+        const float sloc = e.F * e.G * rcp(e.f);                             // local logistic scale 1 / (logit F)'
+        const float step = ((lg2(e.F) - lg2(e.G)) * kLn2 - yc) * sloc;
+        const float xt = x - step;
+        // quadratic convergence: the error after a Newton step is about step^2 / sloc.  A converged
+        // step is taken even if rounding noise put it a hair outside the bracket.
+        const bool conv = step * step <= 2.5e-8f * fmaxf(1.0f, fabsf(xt)) * sloc;   // false for NaN / inf steps
+        const bool newton = conv || (xt >= lb && xt <= ub && fabsf(step) < 0.5f * prev);
+        const float xn = newton ? xt : mid;
+        prev = newton ? fabsf(step) : (ub - lb);
+        // a bisection ends like the reference's, when the bracket has collapsed
+        const bool done = conv || (!newton && !(ub - lb > 5e-7f * fmaxf(1.0f, fabsf(xn))));
+        const bool stuck = xn == x;
         x = xn;
+        if (stuck) break;
         e = mix_eval_p<KT>(x, P);
         if (done) break;
     }
