@@ -120,6 +120,13 @@ class LdjAxpyArgs(C.Structure):
     ]
 
 
+class LinearArgs(C.Structure):
+    _fields_ = [
+        ("M", C.c_int64), ("N", C.c_int32), ("K", C.c_int32),
+        ("x", vp), ("weight", vp), ("bias", vp), ("precision", C.c_int32), ("activation", C.c_int32), ("y", vp),
+    ]
+
+
 # symbol -> argument struct; every entry point is `int f(const Args*, cnf_stream_t)`
 ENTRY_POINTS = {
     "cnf_mixcdf_fwd": MixcdfArgs,
@@ -135,6 +142,7 @@ ENTRY_POINTS = {
     "cnf_logistic_logprob": LogisticLogprobArgs,
     "cnf_logistic_sample": LogisticSampleArgs,
     "cnf_ldj_axpy": LdjAxpyArgs,
+    "cnf_linear_fwd": LinearArgs,
 }
 PLAIN_SYMBOLS = ("cnf_last_error_string", "cnf_abi_version", "cnf_built_for_sm", "cnf_mixcdf_fusable",
                  "cnf_categ_encode_fusable")

@@ -385,3 +385,40 @@ def ldj_axpy(y, *, alpha=1.0, alpha_dev=None, x=None, length=None):
         _ptr(_opt_f32(length, "length")), _ptr(y)
     _call("cnf_ldj_axpy", a, y)
     return y
+
+
+# ----------------------------------------------------------------------------------------------
+# K8: dense projections of the coupling networks on tcgen05 tensor cores
+# ----------------------------------------------------------------------------------------------
+PRECISION = {"tf32": 0, "3xtf32": 1}
+ACTIVATION = {None: 0, "none": 0, "gelu": 1}
+
+
+def linear(x, weight, bias=None, *, precision="3xtf32", activation=None):
+    """y = x @ weight.T + bias (nn.Linear) on the tensor cores (``cnf_linear_fwd``).
+
+    ``x`` [..., K] fp32 CUDA, ``weight`` [N, K], ``bias`` [N] | None.  ``precision``: "tf32" (one pass)
+    or "3xtf32" (hi/lo split, fp32-level accuracy - default, keeps the 1e-4 parity of the flow).
+    K that is not a multiple of 4 is zero-padded (a copy); everything else runs in place."""
+    x = _f32(x, "x")
+    weight = _f32(weight, "weight")
+    N, K = weight.shape
+    if x.shape[-1] != K:
+        raise ValueError("x has %d input features, weight expects %d" % (x.shape[-1], K))
+    lead = x.shape[:-1]
+    x2 = x.reshape(-1, K)
+    if K % 4 != 0:
+        padk = 4 - K % 4
+        x2 = torch.nn.functional.pad(x2, (0, padk))
+        weight = torch.nn.functional.pad(weight, (0, padk))
+        K += padk
+    if x2.data_ptr() % 16 != 0:
+        x2 = x2.clone()
+    bias = _opt_f32(bias, "bias", (N,))
+    y = torch.empty(x2.shape[0], N, dtype=torch.float32, device=x.device)
+    a = L.LinearArgs()
+    a.M, a.N, a.K = x2.shape[0], N, K
+    a.x, a.weight, a.bias, a.y = _ptr(x2), _ptr(weight), _ptr(bias), _ptr(y)
+    a.precision, a.activation = PRECISION[precision], ACTIVATION[activation]
+    _call("cnf_linear_fwd", a, x2, (x2, weight, bias))
+    return y.reshape(lead + (N,))

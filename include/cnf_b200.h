@@ -325,6 +325,28 @@ typedef struct {
 
 CNF_API int cnf_ldj_axpy(const cnf_ldj_axpy_args* a, cnf_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * K8  dense projection of the coupling networks on tcgen05 tensor cores
+ *   replaces nn.Linear (y = x W^T + b) inside RGCNNet / EdgeGNN / LinearNet
+ *   (layers/networks/graph_layers.py:24-25,64-71,192-202,307-315,402-405,574-577,712-716,766-779;
+ *    layers/networks/help_layers.py:57-124), optionally followed by nn.GELU (graph_layers.py:69,176).
+ * TMA-fed, accumulators in tensor memory.  precision 0: one TF32 pass; precision 1: 3xTF32 split
+ * (hi/lo operand decomposition, fp32-level accuracy, ~1e-6 relative).
+ * Requirements: K % 4 == 0, 16-byte aligned x / weight / y (CNF_ERR_UNSUPPORTED / INVALID_ARG otherwise).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    int64_t M;            /* rows: positions / nodes / node pairs      */
+    int32_t N, K;         /* out_features, in_features                 */
+    const float* x;       /* [M,K] row-major                           */
+    const float* weight;  /* [N,K] row-major (nn.Linear.weight)        */
+    const float* bias;    /* [N] or NULL                               */
+    int32_t precision;    /* 0 = TF32, 1 = 3xTF32                      */
+    int32_t activation;   /* 0 = none, 1 = GELU (erf form, nn.GELU())  */
+    float* y;             /* [M,N]                                     */
+} cnf_linear_args;
+
+CNF_API int cnf_linear_fwd(const cnf_linear_args* a, cnf_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
