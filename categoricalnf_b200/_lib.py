@@ -127,6 +127,13 @@ class LinearArgs(C.Structure):
     ]
 
 
+class LinearMixcdfArgs(C.Structure):
+    _fields_ = [
+        ("mix", MixcdfArgs), ("H", C.c_int32), ("precision", C.c_int32),
+        ("features", vp), ("weight", vp), ("bias", vp),
+    ]
+
+
 # symbol -> argument struct; every entry point is `int f(const Args*, cnf_stream_t)`
 ENTRY_POINTS = {
     "cnf_mixcdf_fwd": MixcdfArgs,
@@ -143,9 +150,11 @@ ENTRY_POINTS = {
     "cnf_logistic_sample": LogisticSampleArgs,
     "cnf_ldj_axpy": LdjAxpyArgs,
     "cnf_linear_fwd": LinearArgs,
+    "cnf_linear_mixcdf_fwd": LinearMixcdfArgs,
+    "cnf_linear_mixcdf_inv": LinearMixcdfArgs,
 }
 PLAIN_SYMBOLS = ("cnf_last_error_string", "cnf_abi_version", "cnf_built_for_sm", "cnf_mixcdf_fusable",
-                 "cnf_categ_encode_fusable")
+                 "cnf_categ_encode_fusable", "cnf_linear_mixcdf_fusable")
 
 ABI_VERSION = 2
 _lib = None
@@ -181,6 +190,8 @@ def load():
     lib.cnf_mixcdf_fusable.restype = C.c_int
     lib.cnf_categ_encode_fusable.argtypes = [C.POINTER(CategEncodeArgs)]
     lib.cnf_categ_encode_fusable.restype = C.c_int
+    lib.cnf_linear_mixcdf_fusable.argtypes = [C.POINTER(LinearMixcdfArgs)]
+    lib.cnf_linear_mixcdf_fusable.restype = C.c_int
     if lib.cnf_abi_version() != ABI_VERSION:
         raise ImportError("libcnf_b200.so has ABI version %d, the Python binding expects %d - rebuild"
                           % (lib.cnf_abi_version(), ABI_VERSION))

@@ -296,6 +296,7 @@ extern "C" int cnf_linear_fwd(const cnf_linear_args* a, cnf_stream_t stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     CNF_REQUIRE(a != nullptr, "cnf_linear_fwd: null args");
     CNF_REQUIRE(a->M >= 0 && a->N >= 1 && a->K >= 1, "cnf_linear_fwd: bad shape M=%lld N=%d K=%d", (long long)a->M, a->N, a->K);
+    if (a->M == 0) return CNF_OK;
     CNF_REQUIRE(a->x && a->weight && a->y, "cnf_linear_fwd: null tensor");
     CNF_REQUIRE(a->precision == 0 || a->precision == 1, "cnf_linear_fwd: precision must be 0 (TF32) or 1 (3xTF32)");
     CNF_REQUIRE(a->activation == 0 || a->activation == 1, "cnf_linear_fwd: activation must be 0 (none) or 1 (GELU)");
@@ -303,7 +304,6 @@ extern "C" int cnf_linear_fwd(const cnf_linear_args* a, cnf_stream_t stream_) {
     CNF_SUPPORTED(a->M < (1ll << 31) - 256, "cnf_linear_fwd: M=%lld too large for 32-bit TMA coordinates", (long long)a->M);
     CNF_REQUIRE(((reinterpret_cast<uintptr_t>(a->x) | reinterpret_cast<uintptr_t>(a->weight) | reinterpret_cast<uintptr_t>(a->y)) & 15) == 0,
                 "cnf_linear_fwd: x, weight and y must be 16-byte aligned");
-    if (a->M == 0) return CNF_OK;
 
     LinearParams p{};
     p.bias = a->bias; p.y = a->y; p.M = a->M; p.N = a->N; p.K = a->K; p.act = a->activation;

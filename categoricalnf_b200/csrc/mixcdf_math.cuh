@@ -365,8 +365,11 @@ __device__ __forceinline__ bool mix_inverse_fast(float zin, const MixPrep<KT>& P
         const float xt = x - step;
         // quadratic convergence: the error after a Newton step is about step^2 / sloc.  A converged
         // step is taken even if rounding noise put it a hair outside the bracket.
-        const bool conv = step * step <= 2.5e-8f * fmaxf(1.0f, fabsf(xt)) * sloc;   // false for NaN / inf steps
-        const bool newton = conv || (xt >= lb && xt <= ub && fabsf(step) < 0.5f * prev);
+        // Newton needs a density that has not underflowed: with f flushed to zero and 1-F still a normal
+        // number, sloc and step are +inf and `inf <= inf` would accept x = -inf as converged.
+        const bool fin = e.f >= 1e-30f && fabsf(step) < 1e30f;
+        const bool conv = fin && step * step <= 2.5e-8f * fmaxf(1.0f, fabsf(xt)) * sloc;
+        const bool newton = conv || (fin && xt >= lb && xt <= ub && fabsf(step) < 0.5f * prev);
         const float xn = newton ? xt : mid;
         prev = newton ? fabsf(step) : (ub - lb);
         // a bisection ends like the reference's, when the bracket has collapsed

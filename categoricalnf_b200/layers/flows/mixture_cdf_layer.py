@@ -10,6 +10,7 @@ import torch.nn as nn
 
 from ... import functional as CF
 from ... import ops
+from ..networks.linear import split_final_linear
 from ._masks import mask_lists
 from .coupling_layer import CouplingLayer
 
@@ -87,10 +88,42 @@ class MixtureCDFCoupling(CouplingLayer):
         self.regularizer_max = regularizer_max
         self.regularizer_factor = regularizer_factor
 
+    # Evaluation-time fusion of the network's final projection with the transform (cnf_linear_mixcdf_*):
+    # the [B,S,C*(2+3K)] network output is then never written to memory.  Results are identical to the
+    # two-step path within the 3xTF32 projection error (~1e-6); set False to force the two-step path.
+    fuse_final_projection = True
+    projection_precision = "3xtf32"
+
+    def _projection_split(self, z):
+        """(features_fn, linear) when the final projection of ``self.nn`` can be fused for ``z``, else None."""
+        if not (self.fuse_final_projection and z.is_cuda and z.dim() == 3) or torch.is_grad_enabled():
+            return None
+        split = split_final_linear(self.nn)
+        if split is None:
+            return None
+        lin = split[1]
+        if lin.out_features != self.c_in * (2 + 3 * self.num_mixtures) or lin.in_features % 4 != 0:
+            return None
+        return split
+
     def forward(self, z, ldj=None, reverse=False, channel_padding_mask=None, **kwargs):
         # the incoming ldj is ignored and only this layer's ldj is returned, as upstream (:46-47,:63)
-        nn_out = self.run_network(x=z * self._prepare_mask(self.mask, z), **kwargs)
         mask_c, mask_s = mask_lists(self, "mask", z.size(1))
+        x_in = z * self._prepare_mask(self.mask, z)
+        split = self._projection_split(z)
+        if split is not None:
+            features_fn, lin = split
+            feats = features_fn(x_in, **kwargs)
+            if feats.dim() == 3 and ops.linear_mixcdf_fusable(z, feats, lin.weight, self.num_mixtures, mask_c=mask_c, mask_s=mask_s):
+                z_out, ldj, reg = ops.linear_mixcdf(
+                    z, feats, lin.weight, lin.bias, self.num_mixtures, mask_c=mask_c, mask_s=mask_s, pad=channel_padding_mask,
+                    scaling_factor=self.scaling_factor, mixture_scaling_factor=self.mixture_scaling_factor, reverse=reverse,
+                    reg_max=self.regularizer_max, reg_factor=self.regularizer_factor, training=self.training, want_reg=True,
+                    precision=self.projection_precision)
+                return z_out, ldj, {"ldj": ldj, "regularizer_ldj": reg}
+            nn_out = lin(feats)     # shape / alignment outside the fused kernel: finish the network as usual
+        else:
+            nn_out = self.run_network(x=x_in, **kwargs)
         z_out, ldj, reg = CF.mixcdf(z, nn_out, self.num_mixtures, self.scaling_factor, self.mixture_scaling_factor,
                                     mask_c=mask_c, mask_s=mask_s, pad=channel_padding_mask, reverse=reverse,
                                     reg_max=self.regularizer_max, reg_factor=self.regularizer_factor,
@@ -103,6 +136,8 @@ class MixtureCDFCoupling(CouplingLayer):
         when the kernel cannot fuse for this shape / mask (caller then runs the layers one by one)."""
         if self.training or z.dim() != 3:
             return None
+        if self._projection_split(z) is not None:
+            return None   # the final-projection fusion of forward() saves more traffic than this epilogue
         mask_c, mask_s = mask_lists(self, "mask", z.size(1))
         # cheap shape pre-check (the kernel fuses for C=16, K=8, 8 contiguous transformed channels) so the
         # network is not run twice; the library has the final word below

@@ -422,3 +422,57 @@ def linear(x, weight, bias=None, *, precision="3xtf32", activation=None):
     a.precision, a.activation = PRECISION[precision], ACTIVATION[activation]
     _call("cnf_linear_fwd", a, x2, (x2, weight, bias))
     return y.reshape(lead + (N,))
+
+
+def _linear_mixcdf_args(z, features, weight, bias, num_mixtures, mask_c, mask_s, pad, scaling_factor,
+                        mixture_scaling_factor, precision):
+    z = _f32(z, "z")
+    if z.dim() != 3:
+        raise ValueError("z must be [B, S, C]")
+    B, S, Cc = z.shape
+    K = int(num_mixtures)
+    features = _f32(features, "features")
+    H = features.shape[-1]
+    if features.numel() != B * S * H:
+        raise ValueError("features has shape %s, expected [%d, %d, H]" % (tuple(features.shape), B, S))
+    weight = _f32(weight, "weight", (Cc * (2 + 3 * K), H))
+    bias = _opt_f32(bias, "bias", (Cc * (2 + 3 * K),))
+    pad = _pad_bs(pad, B, S)
+    a = L.LinearMixcdfArgs()
+    a.mix.B, a.mix.S, a.mix.C, a.mix.K = B, S, Cc, K
+    a.mix.mask, keep = _mask_struct(mask_c, mask_s)
+    sf = _opt_f32(scaling_factor, "scaling_factor", (Cc,))
+    msf = _opt_f32(mixture_scaling_factor, "mixture_scaling_factor", (Cc, K))
+    a.mix.z, a.mix.pad = _ptr(z), _ptr(pad)
+    a.mix.scaling_factor, a.mix.mixture_scaling_factor = _ptr(sf), _ptr(msf)
+    a.H, a.precision = H, PRECISION[precision]
+    a.features, a.weight, a.bias = _ptr(features), _ptr(weight), _ptr(bias)
+    return a, (keep, z, features, weight, bias, pad, sf, msf)
+
+
+def linear_mixcdf_fusable(z, features, weight, num_mixtures, *, mask_c=None, mask_s=None):
+    """True when :func:`linear_mixcdf` can run this shape / mask / alignment in one kernel."""
+    a, keep = _linear_mixcdf_args(z, features, weight, None, num_mixtures, mask_c, mask_s, None, None, None, "3xtf32")
+    return bool(L.load().cnf_linear_mixcdf_fusable(C.byref(a)))
+
+
+def linear_mixcdf(z, features, weight, bias, num_mixtures, *, mask_c=None, mask_s=None, pad=None, scaling_factor=None,
+                  mixture_scaling_factor=None, reverse=False, reg_max=-1.0, reg_factor=1.0, training=False, ldj=None,
+                  want_reg=False, precision="3xtf32"):
+    """Final projection of the coupling network + mixture coupling transform in ONE kernel:
+    ``mixcdf(z, features @ weight.T + bias, ...)`` without materialising the network output
+    (``cnf_linear_mixcdf_fwd`` / ``_inv``).  Returns ``(z_out, ldj [B], reg_ldj [B] | None)``."""
+    a, keep = _linear_mixcdf_args(z, features, weight, bias, num_mixtures, mask_c, mask_s, pad, scaling_factor,
+                                  mixture_scaling_factor, precision)
+    z = keep[1]
+    B = z.shape[0]
+    z_out = torch.empty_like(z)
+    accumulate = ldj is not None
+    ldj_t = _f32(ldj, "ldj", (B,)) if accumulate else torch.empty(B, dtype=torch.float32, device=z.device)
+    reg = torch.empty(B, dtype=torch.float32, device=z.device) if want_reg else None
+    a.mix.reg_max, a.mix.reg_factor, a.mix.training = float(reg_max), float(reg_factor), int(bool(training))
+    a.mix.accumulate = int(accumulate)
+    a.mix.z_out, a.mix.ldj, a.mix.reg_ldj = _ptr(z_out), _ptr(ldj_t), _ptr(reg)
+    a.mix.status = _ptr(status_word(z.device))
+    _call("cnf_linear_mixcdf_inv" if reverse else "cnf_linear_mixcdf_fwd", a, z, keep)
+    return z_out, ldj_t, reg

@@ -347,6 +347,30 @@ typedef struct {
 
 CNF_API int cnf_linear_fwd(const cnf_linear_args* a, cnf_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * K8 + K1/K2 fused: FINAL projection of the coupling network + mixture-CDF coupling transform.
+ *   nn_out = features @ weight^T + bias   (last nn.Linear of the network, e.g.
+ *            layers/networks/graph_layers.py:198-201,775-778; help_layers.py:84-94)
+ *   followed by cnf_mixcdf_fwd / cnf_mixcdf_inv on that nn_out (mixture_cdf_layer.py:95-180),
+ *   without nn_out [B,S,C*(2+3K)] ever being written to memory: the records of the transformed
+ *   channels are produced by tcgen05.mma into tensor memory and consumed from there.
+ * `mix` is read like in cnf_mixcdf_fwd except that mix.nn_out is ignored (may be NULL) and the
+ * next_* epilogue is not available.  Shapes: see cnf_linear_mixcdf_fusable (K in {4,8,16}, 4 or 8
+ * contiguous transformed channels, C % 4 == 0, C <= 32, H % 4 == 0, 16-byte aligned tensors).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    cnf_mixcdf_args mix;
+    int32_t H;              /* in_features of the final projection           */
+    int32_t precision;      /* 0 = TF32, 1 = 3xTF32 (see cnf_linear_args)    */
+    const float* features;  /* [B,S,H] input of the final projection         */
+    const float* weight;    /* [C*(2+3K), H] nn.Linear.weight                */
+    const float* bias;      /* [C*(2+3K)] or NULL                            */
+} cnf_linear_mixcdf_args;
+
+CNF_API int cnf_linear_mixcdf_fwd(const cnf_linear_mixcdf_args* a, cnf_stream_t stream);
+CNF_API int cnf_linear_mixcdf_inv(const cnf_linear_mixcdf_args* a, cnf_stream_t stream);
+CNF_API int cnf_linear_mixcdf_fusable(const cnf_linear_mixcdf_args* a);
+
 #ifdef __cplusplus
 }
 #endif

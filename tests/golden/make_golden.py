@@ -145,6 +145,30 @@ def gold_mixcdf_tails(name, seed, right_tail=False):
          reg_ldj=det["regularizer_ldj"])
 
 
+def gold_mixcdf_inv_underflow():
+    """Inverse pass whose first bisection midpoint lands where 1-F and f underflow in float32 (found on
+    the GPU: a Newton step computed from a flushed density must not be accepted).  Parameters come from
+    a per-position Linear like tools/debug_nan.py; K = 16, C = 8."""
+    B, S, C, K, H = 3, 77, 8, 16, 64
+    g = torch.Generator().manual_seed(B * 131 + S * 7 + C + K + H)
+    PN = 2 + 3 * K
+    z_lat = torch.randn(B, S, C, generator=g) * 1.2
+    feats = torch.randn(B, S, H, generator=g)
+    w = torch.randn(C * PN, H, generator=g) * (0.5 / H ** 0.5)
+    b = torch.randn(C * PN, generator=g) * 0.1
+    sf = torch.randn(C, generator=g) * 0.3
+    msf = torch.randn(C, K, generator=g) * 0.3
+    nn_out = (feats.double() @ w.double().t() + b.double()).float()
+    mask = CouplingLayer.create_channel_mask(C)
+    layer = MixtureCDFCoupling(c_in=C, mask=mask, model_func=lambda c_out: _Recorder(nn_out), num_mixtures=K)
+    layer.scaling_factor.data = sf
+    layer.mixture_scaling_factor.data = msf
+    layer.eval()
+    with torch.no_grad():
+        z_smp, ldj_smp, _ = layer(z_lat, reverse=True)
+    save("mixcdf_inv_underflow", nn_out=nn_out, mask=mask, K=K, sf=sf, msf=msf, z_lat=z_lat, z_smp=z_smp, ldj_smp=ldj_smp)
+
+
 def gold_mixcdf_selftest():
     """The reference's own __main__ smoke block (mixture_cdf_layer.py:279-302)."""
     torch.manual_seed(42)
@@ -422,6 +446,7 @@ if __name__ == "__main__":
     gold_mixcdf("mixcdf_ratio_k3", 2, 5, 5, 3, seed=9, ratio=0.3, z_std=3.0)
     gold_mixcdf_tails("mixcdf_tails", seed=10)
     gold_mixcdf_tails("mixcdf_right_tail", seed=10, right_tail=True)
+    gold_mixcdf_inv_underflow()
     gold_autoregressive(seed=11)
     gold_affine(seed=12)
     gold_actnorm(seed=13)

@@ -48,7 +48,8 @@ def test_struct_layout_matches_c():
              "cnf_actnorm_init_args": _lib.ActnormInitArgs, "cnf_invconv_build_args": _lib.InvconvBuildArgs,
              "cnf_invconv_args": _lib.InvconvArgs, "cnf_categ_encode_args": _lib.CategEncodeArgs,
              "cnf_categ_decode_args": _lib.CategDecodeArgs, "cnf_logistic_logprob_args": _lib.LogisticLogprobArgs,
-             "cnf_logistic_sample_args": _lib.LogisticSampleArgs, "cnf_ldj_axpy_args": _lib.LdjAxpyArgs, "cnf_linear_args": _lib.LinearArgs}
+             "cnf_logistic_sample_args": _lib.LogisticSampleArgs, "cnf_ldj_axpy_args": _lib.LdjAxpyArgs, "cnf_linear_args": _lib.LinearArgs,
+             "cnf_linear_mixcdf_args": _lib.LinearMixcdfArgs}
     prog = '#include <stdio.h>\n#include "cnf_b200.h"\nint main(void){\n'
     for n in names:
         prog += '  printf("%s %%zu\\n", sizeof(%s));\n' % (n, n)

@@ -73,6 +73,24 @@ def test_mixcdf_inverse_golden(name):
         ldj_close(ldj, g.ldj_smp, "ldj_smp")
 
 
+@pytest.mark.parametrize("per_position", [False, True])
+def test_mixcdf_inverse_underflow_regression(per_position):
+    """Inverse whose bisection midpoint lands where 1-F and the density underflow in float32: a Newton
+    step formed from a flushed density must be rejected (it produced x = -inf once)."""
+    from categoricalnf_b200 import ops
+    g = load_golden("mixcdf_inv_underflow")
+    mc, _ = split_mask(g.mask)
+    z_lat, nn_out, z_ref = g.z_lat, g.nn_out, g.z_smp
+    if per_position:   # [B*S, 1, C]: generic tile shapes as well
+        z_lat, nn_out, z_ref = (t.reshape(-1, 1, t.shape[-1]) for t in (z_lat, nn_out, z_ref))
+    z, ldj, _ = ops.mixcdf(dev(z_lat), dev(nn_out), g.K, mask_c=mc, scaling_factor=dev(g.sf),
+                           mixture_scaling_factor=dev(g.msf), reverse=True)
+    ops.check_status(z.device)
+    assert_close(z, z_ref, what="z_smp")
+    if not per_position:
+        ldj_close(ldj, g.ldj_smp, "ldj_smp")
+
+
 def test_mixcdf_tails_golden():
     """Deep left tails (CDF down to exp(-850), the 1e-22 clamps) and 1-CDF down to 1e-11."""
     from categoricalnf_b200 import ops

@@ -45,6 +45,15 @@ def test_mixcdf_tails(name):
     assert_close(ldj, g.ldj_fwd, what="ldj", **TIGHT)
 
 
+def test_mixcdf_inverse_underflow_case():
+    """Sampling direction, K = 16: the fixture behind the GPU regression test of the inverse solver."""
+    g = load_golden("mixcdf_inv_underflow")
+    m = O.expand_mask(g.mask, g.z_lat)
+    zs, ls, _ = O.mixcdf_coupling(g.z_lat, g.nn_out, m, g.K, g.sf, g.msf, reverse=True, training=False)
+    assert_close(zs, g.z_smp, what="z_smp", **TIGHT)
+    assert_close(ls, g.ldj_smp, what="ldj_smp", **TIGHT)
+
+
 def test_reference_selftest_case():
     """The reference's own __main__ block: forward then reverse reconstructs to 1.2e-7."""
     g = load_golden("mixcdf_selftest")

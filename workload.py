@@ -225,11 +225,22 @@ def bits_per_dim(ldj, logp, S):
 # GPU arm, module-level: the drop-in FlowModel a user of the reference would build
 # --------------------------------------------------------------------------------------------------
 class StandInNet(torch.nn.Module):
-    """Per-position Linear coupling network with the call signature coupling_layer.py:28-35 uses."""
+    """Per-position Linear coupling network with the call signature coupling_layer.py:28-35 uses.  The
+    projection is the product's tcgen05 Linear (a16); the network also exposes the final-projection
+    protocol (categoricalnf_b200.layers.networks.split_final_linear) so that the coupling layer can fuse
+    it with the transform at evaluation time."""
 
     def __init__(self, c_in, c_out):
         super().__init__()
-        self.lin = torch.nn.Linear(c_in, c_out)
+        from categoricalnf_b200.layers.networks import TCLinear
+        self.lin = TCLinear(c_in, c_out)
+
+    @property
+    def cnf_final_linear(self):
+        return self.lin
+
+    def cnf_features(self, x, length=None, **kwargs):
+        return x
 
     def forward(self, x, length=None, **kwargs):
         return self.lin(x)
