@@ -134,6 +134,58 @@ class LinearMixcdfArgs(C.Structure):
     ]
 
 
+class MixcdfBwdArgs(C.Structure):
+    _fields_ = [
+        ("B", C.c_int64), ("S", C.c_int64), ("C", C.c_int32), ("K", C.c_int32),
+        ("z", vp), ("nn_out", vp), ("mask", Mask), ("pad", vp),
+        ("scaling_factor", vp), ("mixture_scaling_factor", vp),
+        ("reg_max", C.c_float), ("reg_factor", C.c_float), ("training", C.c_int32), ("params_prebounded", C.c_int32),
+        ("grad_z_out", vp), ("grad_ldj", vp), ("grad_z", vp), ("grad_nn_out", vp),
+        ("grad_scaling_factor", vp), ("grad_mixture_scaling_factor", vp),
+    ]
+
+
+class AffineBwdArgs(C.Structure):
+    _fields_ = [
+        ("B", C.c_int64), ("S", C.c_int64), ("C", C.c_int32),
+        ("z", vp), ("nn_out", vp), ("mask", Mask), ("scaling_factor", vp), ("reverse", C.c_int32),
+        ("params_prebounded", C.c_int32),
+        ("grad_z_out", vp), ("grad_ldj", vp), ("grad_z", vp), ("grad_nn_out", vp), ("grad_scaling_factor", vp),
+    ]
+
+
+class ActnormBwdArgs(C.Structure):
+    _fields_ = [
+        ("B", C.c_int64), ("S", C.c_int64), ("C", C.c_int32),
+        ("z", vp), ("bias", vp), ("scales", vp), ("pad", vp), ("length", vp), ("reverse", C.c_int32),
+        ("grad_z_out", vp), ("grad_ldj", vp), ("grad_z", vp), ("grad_bias", vp), ("grad_scales", vp),
+    ]
+
+
+class ExtActnormBwdArgs(C.Structure):
+    _fields_ = [
+        ("B", C.c_int64), ("S", C.c_int64), ("C", C.c_int32),
+        ("z", vp), ("ext", vp), ("pad", vp), ("reverse", C.c_int32),
+        ("grad_z_out", vp), ("grad_ldj", vp), ("grad_z", vp), ("grad_ext", vp),
+    ]
+
+
+class InvconvBwdArgs(C.Structure):
+    _fields_ = [
+        ("B", C.c_int64), ("S", C.c_int64), ("C", C.c_int32),
+        ("z", vp), ("weight", vp), ("pad", vp), ("length", vp), ("reverse", C.c_int32),
+        ("grad_z_out", vp), ("grad_ldj", vp), ("grad_z", vp), ("grad_weight", vp), ("grad_sldj", vp),
+    ]
+
+
+class LogisticLogprobBwdArgs(C.Structure):
+    _fields_ = [
+        ("B", C.c_int64), ("S", C.c_int64), ("C", C.c_int32),
+        ("x", vp), ("pad", vp), ("mu", C.c_float), ("sigma", C.c_float),
+        ("grad_out", vp), ("grad_elementwise", vp), ("grad_x", vp),
+    ]
+
+
 # symbol -> argument struct; every entry point is `int f(const Args*, cnf_stream_t)`
 ENTRY_POINTS = {
     "cnf_mixcdf_fwd": MixcdfArgs,
@@ -152,6 +204,12 @@ ENTRY_POINTS = {
     "cnf_linear_fwd": LinearArgs,
     "cnf_linear_mixcdf_fwd": LinearMixcdfArgs,
     "cnf_linear_mixcdf_inv": LinearMixcdfArgs,
+    "cnf_mixcdf_bwd": MixcdfBwdArgs,
+    "cnf_affine_coupling_bwd": AffineBwdArgs,
+    "cnf_actnorm_bwd": ActnormBwdArgs,
+    "cnf_ext_actnorm_bwd": ExtActnormBwdArgs,
+    "cnf_invconv_bwd": InvconvBwdArgs,
+    "cnf_logistic_logprob_bwd": LogisticLogprobBwdArgs,
 }
 PLAIN_SYMBOLS = ("cnf_last_error_string", "cnf_abi_version", "cnf_built_for_sm", "cnf_mixcdf_fusable",
                  "cnf_categ_encode_fusable", "cnf_linear_mixcdf_fusable")

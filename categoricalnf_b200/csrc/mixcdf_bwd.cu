@@ -1,0 +1,385 @@
+// Backward of K1 (logistic-mixture-CDF coupling, forward direction): gradients of a loss with respect to
+// z, the network output nn_out and the two scaling-factor parameters, given dL/dz_out and dL/dldj.
+//
+// The reference differentiates ~100 eager float64 ops per coupling through autograd
+// (layers/flows/mixture_cdf_layer.py:95-180 under general/train.py:148-152); here the chain rule of
+// SURVEY.md Appendix C is evaluated in one kernel:
+//   u_k = (x - mu_k) e^{-ls_k}, sigma_k = sigmoid(u_k), pi = softmax(log_pi)
+//   F = sum pi sigma, G = 1 - F = sum pi (1 - sigma), f = sum pi sigma (1 - sigma) e^{-ls}
+//   y = log F - log G, z_out = (y + t) e^{log_s}, ldj_e = log_s - log F - log G + log f (+ reg * reg_factor)
+// with log_s and ls_k tanh-bounded by the learned scaling factors (:157-162).
+//
+// One CTA per tile of TP positions, any K / C / mask: the parameter records of the transformed channels,
+// the z rows and the incoming dL/dz_out rows are staged with cp.async; one thread per (position, channel)
+// makes two passes over the K components (totals, then per-component gradients) and overwrites the record
+// IN PLACE with its gradient; the tile's full dL/dnn_out rows (zeros for conditioner channels) are then
+// written with coalesced 8-byte stores.  Scaling-factor gradients are reduced in shared memory and leave
+// with one atomic per (CTA, parameter).  Elements outside the fp32-safe range (same test as the forward
+// kernels) are differentiated in float64.
+#include "cnf_common.cuh"
+
+namespace cnf {
+namespace {
+
+constexpr int kThreads = 256;
+
+struct BwdParams {
+    const float* z;
+    const float* nn;
+    const float* pad;
+    const float* sf;
+    const float* msf;
+    const float* gz_out;
+    const float* gldj;
+    float* gz;
+    float* gnn;
+    float* gsf;
+    float* gmsf;
+    long long P;
+    int S, C, K, PN, TP;
+    MaskView mask;
+    int vec_params;
+    float reg_max, reg_factor;
+    int use_reg;
+    int pre;
+};
+
+template <typename T>
+struct Mth;
+template <>
+struct Mth<float> {
+    static __device__ __forceinline__ float ex(float v) { return __expf(v); }
+    static __device__ __forceinline__ float lg(float v) { return __logf(v); }
+    static __device__ __forceinline__ float th(float v) { return 1.0f - 2.0f / (1.0f + __expf(2.0f * v)); }
+};
+template <>
+struct Mth<double> {
+    static __device__ __forceinline__ double ex(double v) { return exp(v); }
+    static __device__ __forceinline__ double lg(double v) { return log(v); }
+    static __device__ __forceinline__ double th(double v) { return tanh(v); }
+};
+
+// Gradient of one transformed element.  `rec` (shared memory) holds [t, raw log_s, log_pi[K], mu[K],
+// raw log_scale[K]] on entry and the gradient with respect to those entries on exit.  Returns false
+// (nothing written) when T = float and the element is outside the fp32-safe range.
+template <typename T, int KT>
+__device__ __forceinline__ bool mix_backward_elem(float xf, float* rec, const float* mfac, float sfac, int Krt, bool pre,
+                                                  float g_out_f, float gl_f, bool use_reg, float reg_max, float reg_factor,
+                                                  float* gx_out, float* gsf_out, float* s_gmsf) {
+    using M = Mth<T>;
+    const int K = KT > 0 ? KT : Krt;
+    const T x = (T)xf, g_out = (T)g_out_f, gl = (T)gl_f;
+    float* lp = rec + 2;
+    float* mu = lp + K;
+    float* ms = mu + K;
+    float m = lp[0];
+#pragma unroll(KT > 0 ? KT : 4)
+    for (int k = 1; k < K; ++k) m = fmaxf(m, lp[k]);
+    T W = 0, Fs = 0, Gs = 0, fs = 0;
+#pragma unroll(KT > 0 ? KT : 4)
+    for (int k = 0; k < K; ++k) {
+        const float mf = pre ? 1.0f : mfac[k];
+        // the reference bounds the raw log-scales in float32 before its .double() (:157-178)
+        const T ls = pre ? (T)ms[k] : M::th((T)ms[k] / (T)fmaxf(mf, 1.0f)) * (T)mf;
+        const T e = M::ex(-ls);
+        const T u = (x - (T)mu[k]) * e;
+        const T ea = M::ex(-fabs(u));
+        const T r = (T)1 / ((T)1 + ea);
+        const T q = ea * r;
+        const T sg = u >= 0 ? r : q, tg = u >= 0 ? q : r;   // sigma, 1 - sigma
+        const T w = M::ex((T)lp[k] - (T)m);
+        W += w;
+        Fs += w * sg;
+        Gs += w * tg;
+        fs += w * (q * r) * e;
+    }
+    const T iw = (T)1 / W;
+    const T F = Fs * iw, G = Gs * iw, f = fs * iw;
+    if (sizeof(T) == sizeof(float)) {
+        if (!(F >= (T)1e-30 && G >= (T)1e-12 && f >= (T)1e-30)) return false;
+    }
+    const float sf_max = fmaxf(sfac, 1.0f);
+    const T ths = pre ? (T)0 : M::th((T)rec[1] / (T)sf_max);
+    const T log_s = pre ? (T)rec[1] : ths * (T)sfac;
+    const T c22 = (T)-50.65687204586900;   // log(1e-22), safe_log clamp (:197-198)
+    const T lF = M::lg(F), lG = M::lg(G);
+    const bool cF = lF >= c22, cG = lG >= c22;           // clamp of -log(max(F,1e-22)) - log(max(1-F,1e-22))
+    const bool cy = (lG - lF) >= c22;                    // clamp of y = -log(max(1/F - 1, 1e-22))
+    const T es = M::ex(log_s);
+    const T y = cy ? lF - lG : -c22;
+    const T z_out = (y + (T)rec[0]) * es;
+    const T A = cy ? g_out * es : (T)0;                  // dL/dy
+    const T g_t = g_out * es;
+    const T g_logs = g_out * z_out + gl;
+    T LlF = A - (cF ? gl : (T)0), LlG = -A - (cG ? gl : (T)0);
+    if (use_reg) {   // reg = min(log10 F, -reg_max) + reg_max + same for 1-F, added to the ldj times reg_factor (:108-123)
+        const T il10 = (T)0.43429448190325182;
+        if (cF && lF * il10 < -(T)reg_max) LlF += gl * (T)reg_factor * il10;
+        if (cG && lG * il10 < -(T)reg_max) LlG += gl * (T)reg_factor * il10;
+    }
+    const T LF = LlF / F, LG = LlG / G, Lf = gl / f;
+    const T Ssum = LF * F + LG * G + Lf * f;             // sum_j pi_j P_j
+    T gx = 0;
+#pragma unroll(KT > 0 ? KT : 4)
+    for (int k = 0; k < K; ++k) {
+        const float mf = pre ? 1.0f : mfac[k];
+        const float mf_max = fmaxf(mf, 1.0f);
+        const T raw = (T)ms[k];
+        const T thk = pre ? (T)0 : M::th(raw / (T)mf_max);
+        const T ls = pre ? raw : thk * (T)mf;
+        const T e = M::ex(-ls);
+        const T u = (x - (T)mu[k]) * e;
+        const T ea = M::ex(-fabs(u));
+        const T r = (T)1 / ((T)1 + ea);
+        const T q = ea * r;
+        const T sg = u >= 0 ? r : q, tg = u >= 0 ? q : r;
+        const T d = q * r;
+        const T pi = M::ex((T)lp[k] - (T)m) * iw;
+        const T Pk = LF * sg + LG * tg + Lf * d * e;
+        const T Lsig = pi * ((LF - LG) + Lf * (tg - sg) * e);
+        const T Lu = Lsig * d;
+        const T Lue = Lu * e;
+        gx += Lue;
+        const T Lls = -u * Lu - Lf * pi * d * e;
+        lp[k] = (float)(pi * (Pk - Ssum));
+        mu[k] = (float)(-Lue);
+        if (pre) {
+            ms[k] = (float)Lls;
+        } else {
+            const T sech2 = (T)1 - thk * thk;
+            ms[k] = (float)(Lls * sech2 * (T)mf / (T)mf_max);
+            // ls = tanh(raw / max(M,1)) M, M = e^{msf}: d ls / d msf
+            const T dmsf = (T)mf * (thk - (mf > 1.0f ? sech2 * raw / (T)mf : (T)0));
+            atomicAdd(s_gmsf + k, (float)(Lls * dmsf));
+        }
+    }
+    rec[0] = (float)g_t;
+    if (pre) {
+        rec[1] = (float)g_logs;
+    } else {
+        const T sech2 = (T)1 - ths * ths;
+        const T raw = (T)rec[1];
+        *gsf_out += (float)(g_logs * (T)sfac * (ths - (sfac > 1.0f ? sech2 * raw / (T)sfac : (T)0)));
+        rec[1] = (float)(g_logs * sech2 * (T)sfac / (T)sf_max);
+    }
+    *gx_out = (float)gx;
+    return true;
+}
+
+template <int KT>
+__global__ void __launch_bounds__(kThreads) mixcdf_bwd_kernel(const BwdParams p) {
+    extern __shared__ __align__(16) float smem[];
+    const int tid = threadIdx.x;
+    const int K = KT > 0 ? KT : p.K;
+    const int PN = 2 + 3 * K;
+    const int C = p.C, Ct = p.mask.n_t, TP = p.TP;
+    const int L = Ct * PN;
+
+    float* s_par = smem;                                   // [TP * L] parameters in, gradients out
+    float* s_z = s_par + ((TP * L + 3) & ~3);              // [TP * C] z in
+    float* s_g = s_z + ((TP * C + 3) & ~3);                // [TP * C] dL/dz_out in, dL/dz out
+    float* s_fac = s_g + ((TP * C + 3) & ~3);              // [Ct] e^{sf}
+    float* s_mfac = s_fac + Ct;                            // [Ct * K] e^{msf}
+    float* s_gsf = s_mfac + Ct * K;                        // [Ct]
+    float* s_gmsf = s_gsf + Ct;                            // [Ct * K]
+    int* s_jmap = reinterpret_cast<int*>(s_gmsf + Ct * K); // [C] channel -> transformed index or -1
+
+    const long long pos0 = (long long)blockIdx.x * TP;
+    const int rows = (int)min((long long)TP, p.P - pos0);
+
+    if (p.vec_params) {
+        const int L4 = L >> 2, total = rows * L4;
+        const float inv = 1.0f / (float)L4;
+        const float4* src = reinterpret_cast<const float4*>(p.nn);
+        const long long row4 = ((long long)C * PN) >> 2;
+        const int off4 = (p.mask.c0 * PN) >> 2;
+        float4* dst = reinterpret_cast<float4*>(s_par);
+        for (int i = tid; i < total; i += kThreads) {
+            const int r = fast_div(i, inv), q = i - r * L4;
+            cp_async16(dst + i, src + (pos0 + r) * row4 + off4 + q);
+        }
+    } else {
+        const int total = rows * L;
+        const float inv_pn = 1.0f / (float)PN, inv_ct = 1.0f / (float)Ct;
+        for (int i = tid; i < total; i += kThreads) {
+            const int e = fast_div(i, inv_pn), pp = i - e * PN;
+            const int r = fast_div(e, inv_ct), j = e - r * Ct;
+            cp_async4(s_par + i, p.nn + ((pos0 + r) * C + p.mask.tch[j]) * (long long)PN + pp);
+        }
+    }
+    {
+        const int n = rows * C;
+        for (int i = tid; i < n; i += kThreads) {
+            cp_async4(s_z + i, p.z + pos0 * C + i);
+            cp_async4(s_g + i, p.gz_out + pos0 * C + i);
+        }
+    }
+    for (int i = tid; i < Ct; i += kThreads) {
+        s_fac[i] = p.sf ? expf(p.sf[p.mask.tch[i]]) : 1.0f;
+        s_gsf[i] = 0.f;
+    }
+    for (int i = tid; i < Ct * K; i += kThreads) {
+        const int j = i / K, k = i - j * K;
+        s_mfac[i] = p.msf ? expf(p.msf[p.mask.tch[j] * K + k]) : 1.0f;
+        s_gmsf[i] = 0.f;
+    }
+    for (int i = tid; i < C; i += kThreads) s_jmap[i] = -1;
+    cp_async_wait_all();
+    __syncthreads();
+    for (int i = tid; i < Ct; i += kThreads) s_jmap[p.mask.tch[i]] = i;
+
+    // ---- one thread per (position, transformed channel) ----------------------------------------
+    const int nelem = rows * Ct;
+    const float inv_ct = 1.0f / (float)Ct;
+    for (int e = tid; e < nelem; e += kThreads) {
+        const int r = fast_div(e, inv_ct), j = e - r * Ct;
+        const long long pos = pos0 + r;
+        const int ch = p.mask.tch[j];
+        float* rec = s_par + (size_t)e * PN;
+        const float padv = p.pad ? p.pad[pos] : 1.0f;
+        bool active = padv != 0.0f;
+        if (p.mask.s_period > 0) {
+            const int s = (int)(pos % p.S);
+            if ((p.mask.cond_s >> (s % p.mask.s_period)) & 1ull) active = false;
+        }
+        const float gzo = s_g[r * C + ch];
+        if (!active) {   // copied through (times pad): no parameter gradient
+            for (int i = 0; i < PN; ++i) rec[i] = 0.f;
+            s_g[r * C + ch] = gzo * padv;
+            continue;
+        }
+        // z_final = (out * pad + x (1 - pad)) * pad, ldj_e * pad (mixture_cdf_layer.py:76,99-101,137-138)
+        const float g_out = gzo * padv * padv;
+        const float gl = (p.gldj ? p.gldj[pos / p.S] : 0.f) * padv;
+        const float x = s_z[r * C + ch];
+        float gx = 0.f, gsf = 0.f;
+        const bool ok = mix_backward_elem<float, KT>(x, rec, s_mfac + j * K, s_fac[j], K, p.pre != 0, g_out, gl, p.use_reg != 0,
+                                                      p.reg_max, p.reg_factor, &gx, &gsf, s_gmsf + j * K);
+        if (!ok)
+            mix_backward_elem<double, 0>(x, rec, s_mfac + j * K, s_fac[j], K, p.pre != 0, g_out, gl, p.use_reg != 0, p.reg_max,
+                                         p.reg_factor, &gx, &gsf, s_gmsf + j * K);
+        s_g[r * C + ch] = gx + gzo * (1.0f - padv) * padv;
+        if (gsf != 0.f) atomicAdd(s_gsf + j, gsf);
+    }
+    __syncthreads();
+    // conditioner channels: dL/dz = dL/dz_out * pad
+    if (Ct < C) {
+        const int n = rows * C;
+        const float inv_c = 1.0f / (float)C;
+        for (int i = tid; i < n; i += kThreads) {
+            const int r = fast_div(i, inv_c), c = i - r * C;
+            if (s_jmap[c] < 0 && p.pad) s_g[i] *= p.pad[pos0 + r];
+        }
+        __syncthreads();
+    }
+
+    // ---- dL/dnn_out rows: gradient records of the transformed channels, zeros elsewhere ----------
+    if ((PN & 1) == 0) {   // even K: 8-byte granules never straddle a record
+        const int PN2 = PN >> 1;
+        const int row2 = C * PN2, total = rows * row2;
+        const float inv_row = 1.0f / (float)row2, inv_pn2 = 1.0f / (float)PN2;
+        float2* dst = reinterpret_cast<float2*>(p.gnn + pos0 * (long long)C * PN);
+        for (int i = tid; i < total; i += kThreads) {
+            const int r = fast_div(i, inv_row), q = i - r * row2;
+            const int c = fast_div(q, inv_pn2), i2 = q - c * PN2;
+            const int j = s_jmap[c];
+            float2 v = make_float2(0.f, 0.f);
+            if (j >= 0) v = *reinterpret_cast<const float2*>(s_par + ((size_t)r * Ct + j) * PN + 2 * i2);
+            dst[i] = v;
+        }
+    } else {
+        const int rowlen = C * PN, total = rows * rowlen;
+        const float inv_row = 1.0f / (float)rowlen, inv_pn = 1.0f / (float)PN;
+        float* dst = p.gnn + pos0 * (long long)C * PN;
+        for (int i = tid; i < total; i += kThreads) {
+            const int r = fast_div(i, inv_row), q = i - r * rowlen;
+            const int c = fast_div(q, inv_pn), i1 = q - c * PN;
+            const int j = s_jmap[c];
+            dst[i] = j >= 0 ? s_par[((size_t)r * Ct + j) * PN + i1] : 0.f;
+        }
+    }
+    // ---- dL/dz rows ----------------------------------------------------------------------------
+    {
+        const int n = rows * C;
+        float* dst = p.gz + pos0 * C;
+        for (int i = tid; i < n; i += kThreads) dst[i] = s_g[i];
+    }
+    // ---- scaling-factor gradients: one atomic per (CTA, parameter) -----------------------------
+    if (p.gsf)
+        for (int i = tid; i < Ct; i += kThreads)
+            if (s_gsf[i] != 0.f) atomicAdd(p.gsf + p.mask.tch[i], s_gsf[i]);
+    if (p.gmsf)
+        for (int i = tid; i < Ct * K; i += kThreads)
+            if (s_gmsf[i] != 0.f) atomicAdd(p.gmsf + p.mask.tch[i / K] * K + i % K, s_gmsf[i]);
+}
+
+size_t bwd_smem(int TP, int L, int C, int Ct, int K) {
+    size_t f = ((size_t)TP * L + 3) & ~(size_t)3;
+    f += 2 * (((size_t)TP * C + 3) & ~(size_t)3);
+    f += 2 * (size_t)Ct + 2 * (size_t)Ct * K + (size_t)C;
+    return f * sizeof(float);
+}
+
+template <int KT>
+int launch_bwd(const BwdParams& p, size_t smem, cudaStream_t stream) {
+    if (smem > 48 * 1024)
+        CNF_CUDA(cudaFuncSetAttribute(mixcdf_bwd_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long grid = (p.P + p.TP - 1) / p.TP;
+    mixcdf_bwd_kernel<KT><<<(unsigned)grid, kThreads, smem, stream>>>(p);
+    return launch_status("mixcdf_bwd_kernel");
+}
+
+}  // namespace
+}  // namespace cnf
+
+extern "C" int cnf_mixcdf_bwd(const cnf_mixcdf_bwd_args* a, cnf_stream_t stream_) {
+    using namespace cnf;
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    CNF_REQUIRE(a != nullptr, "args is NULL");
+    CNF_REQUIRE(a->B >= 0 && a->S >= 0, "negative batch/sequence size");
+    CNF_REQUIRE(a->C >= 1 && a->K >= 1, "C and K must be >= 1 (got C=%d K=%d)", a->C, a->K);
+    CNF_SUPPORTED(a->C <= CNF_MAX_CHANNELS && a->K <= CNF_MAX_MIXTURES, "C=%d / K=%d outside the compiled range", a->C, a->K);
+    BwdParams p{};
+    int rc = build_mask(a->mask, a->C, &p.mask);
+    if (rc != CNF_OK) return rc;
+    const long long P = a->B * a->S;
+    if (P == 0) return CNF_OK;
+    CNF_REQUIRE(a->z && a->nn_out && a->grad_z_out && a->grad_z && a->grad_nn_out, "z / nn_out / grad_z_out / grad_z / grad_nn_out is NULL");
+    const size_t nz = (size_t)P * a->C;
+    p.PN = 2 + 3 * a->K;
+    if (p.mask.n_t == 0) {   // nothing transformed: identity (times pad), no parameter gradient
+        CNF_SUPPORTED(a->pad == nullptr, "mask with no transformed channel together with a padding mask");
+        CNF_CUDA(cudaMemcpyAsync(a->grad_z, a->grad_z_out, nz * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+        CNF_CUDA(cudaMemsetAsync(a->grad_nn_out, 0, nz * p.PN * sizeof(float), stream));
+        return CNF_OK;
+    }
+    p.z = a->z; p.nn = a->nn_out; p.pad = a->pad; p.sf = a->scaling_factor; p.msf = a->mixture_scaling_factor;
+    p.gz_out = a->grad_z_out; p.gldj = a->grad_ldj; p.gz = a->grad_z; p.gnn = a->grad_nn_out;
+    p.gsf = a->params_prebounded ? nullptr : a->grad_scaling_factor;
+    p.gmsf = a->params_prebounded ? nullptr : a->grad_mixture_scaling_factor;
+    p.P = P; p.S = (int)a->S; p.C = a->C; p.K = a->K;
+    p.reg_max = a->reg_max; p.reg_factor = a->reg_factor;
+    p.use_reg = (a->reg_max > 0.f && a->training) ? 1 : 0;
+    p.pre = a->params_prebounded;
+    const int Ct = p.mask.n_t, L = Ct * p.PN;
+    int elems = kThreads;
+    const int cap = (40 * 1024) / (4 * p.PN);
+    if (elems > cap) elems = cap;
+    int TP = elems / Ct;
+    TP &= ~3;
+    if (TP < 4) TP = 4;
+    p.TP = TP;
+    const long long rowlen = (long long)a->C * p.PN;
+    p.vec_params = p.mask.contiguous && (L % 4 == 0) && (rowlen % 4 == 0) && ((p.mask.c0 * p.PN) % 4 == 0) &&
+                   ((reinterpret_cast<uintptr_t>(a->nn_out) & 15) == 0);
+    CNF_REQUIRE((reinterpret_cast<uintptr_t>(a->grad_nn_out) & 7) == 0, "grad_nn_out must be 8-byte aligned");
+    CNF_SUPPORTED((long long)TP * a->C * p.PN < (1 << 21), "tile too large for the index arithmetic");
+    const size_t smem = bwd_smem(TP, L, a->C, Ct, a->K);
+    CNF_SUPPORTED(smem <= 200 * 1024, "C=%d K=%d needs %zu bytes of shared memory per tile", a->C, a->K, smem);
+    switch (a->K) {
+        case 4: return launch_bwd<4>(p, smem, stream);
+        case 8: return launch_bwd<8>(p, smem, stream);
+        case 16: return launch_bwd<16>(p, smem, stream);
+        default: return launch_bwd<0>(p, smem, stream);
+    }
+}

@@ -16,12 +16,6 @@ def _needs_grad(*tensors) -> bool:
     return torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors)
 
 
-def _no_backward(name):
-    raise NotImplementedError(
-        "categoricalnf_b200: the backward kernel of %s is not built yet; run this layer under "
-        "torch.no_grad() (evaluation / sampling) - there is deliberately no eager fallback" % name)
-
-
 # ----------------------------------------------------------------------------------------------
 # mixture-CDF coupling
 # ----------------------------------------------------------------------------------------------
@@ -157,6 +151,7 @@ class _InvConv(torch.autograd.Function):
         z_out, _ = ops.invconv_apply(z, weight, sldj, ldj, pad=pad, length=length, reverse=reverse)
         ctx.mark_dirty(ldj)
         ctx.reverse = reverse
+        ctx.sldj_shape = sldj.shape
         ctx.save_for_backward(z, weight, pad, length)
         return z_out, ldj
 
@@ -165,7 +160,7 @@ class _InvConv(torch.autograd.Function):
         from . import ops_bwd
         z, weight, pad, length = ctx.saved_tensors
         gz, gw, gsldj = ops_bwd.invconv_backward(z, weight, pad, length, g_z, g_ldj, ctx.reverse, ctx.needs_input_grad)
-        return gz, gw, gsldj, g_ldj, None, None, None
+        return gz, gw, gsldj.reshape(ctx.sldj_shape), g_ldj, None, None, None
 
 
 def invconv(z, weight, sldj, ldj, *, pad=None, length=None, reverse=False):

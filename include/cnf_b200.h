@@ -371,6 +371,118 @@ CNF_API int cnf_linear_mixcdf_fwd(const cnf_linear_mixcdf_args* a, cnf_stream_t 
 CNF_API int cnf_linear_mixcdf_inv(const cnf_linear_mixcdf_args* a, cnf_stream_t stream);
 CNF_API int cnf_linear_mixcdf_fusable(const cnf_linear_mixcdf_args* a);
 
+
+/* ------------------------------------------------------------------------------------------
+ * Backward passes: the reference trains by autograd through its
+ * eager float64 ops (general/train.py:148-152); these entry points evaluate the same chain rule
+ * in one kernel per layer.  `grad_z_out` = dL/d(layer output), `grad_ldj` [B] = dL/d(ldj) (NULL
+ * = 0).  Parameter gradients (`grad_scaling_factor`, `grad_bias`, ...) are ACCUMULATED into
+ * (+=): the caller zero-initialises them.  All other outputs are overwritten.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    int64_t B, S;
+    int32_t C, K;
+    const float* z;                      /* [B,S,C] forward input                     */
+    const float* nn_out;                 /* [B,S,C*(2+3K)] forward input              */
+    cnf_mask mask;
+    const float* pad;                    /* [B,S] or NULL                             */
+    const float* scaling_factor;         /* [C] or NULL                               */
+    const float* mixture_scaling_factor; /* [C,K] or NULL                             */
+    float reg_max, reg_factor;
+    int32_t training;
+    int32_t params_prebounded;
+    const float* grad_z_out;             /* [B,S,C]                                   */
+    const float* grad_ldj;               /* [B] or NULL                               */
+    float* grad_z;                       /* [B,S,C] direct path only (not through nn) */
+    float* grad_nn_out;                  /* [B,S,C*(2+3K)], zeros for conditioners    */
+    float* grad_scaling_factor;          /* [C] += or NULL                            */
+    float* grad_mixture_scaling_factor;  /* [C,K] += or NULL                          */
+} cnf_mixcdf_bwd_args;
+
+/* forward direction of cnf_mixcdf_fwd (training differentiates the density direction only) */
+CNF_API int cnf_mixcdf_bwd(const cnf_mixcdf_bwd_args* a, cnf_stream_t stream);
+
+typedef struct {
+    int64_t B, S;
+    int32_t C;
+    const float* z;              /* [B,S,C]  forward input */
+    const float* nn_out;         /* [B,S,2C] */
+    cnf_mask mask;
+    const float* scaling_factor; /* [C] or NULL */
+    int32_t reverse;
+    int32_t params_prebounded;
+    const float* grad_z_out;     /* [B,S,C] */
+    const float* grad_ldj;       /* [B] or NULL */
+    float* grad_z;               /* [B,S,C] */
+    float* grad_nn_out;          /* [B,S,2C] */
+    float* grad_scaling_factor;  /* [C] += or NULL */
+} cnf_affine_bwd_args;
+
+CNF_API int cnf_affine_coupling_bwd(const cnf_affine_bwd_args* a, cnf_stream_t stream);
+
+typedef struct {
+    int64_t B, S;
+    int32_t C;
+    const float* z;        /* [B,S,C] forward input */
+    const float* bias;     /* [C] */
+    const float* scales;   /* [C] */
+    const float* pad;      /* [B,S] or NULL */
+    const float* length;   /* [B] or NULL */
+    int32_t reverse;
+    const float* grad_z_out;
+    const float* grad_ldj; /* [B] or NULL */
+    float* grad_z;
+    float* grad_bias;      /* [C] += or NULL */
+    float* grad_scales;    /* [C] += or NULL */
+} cnf_actnorm_bwd_args;
+
+CNF_API int cnf_actnorm_bwd(const cnf_actnorm_bwd_args* a, cnf_stream_t stream);
+
+typedef struct {
+    int64_t B, S;
+    int32_t C;
+    const float* z;        /* [B,S,C]  forward input */
+    const float* ext;      /* [B,S,2C] */
+    const float* pad;      /* [B,S] or NULL */
+    int32_t reverse;
+    const float* grad_z_out;
+    const float* grad_ldj; /* [B] or NULL */
+    float* grad_z;
+    float* grad_ext;       /* [B,S,2C] */
+} cnf_ext_actnorm_bwd_args;
+
+CNF_API int cnf_ext_actnorm_bwd(const cnf_ext_actnorm_bwd_args* a, cnf_stream_t stream);
+
+typedef struct {
+    int64_t B, S;
+    int32_t C;
+    const float* z;        /* [B,S,C] forward input */
+    const float* weight;   /* [C,C] the matrix that was applied (W forward, W^-1 reverse) */
+    const float* pad;      /* [B,S] or NULL */
+    const float* length;   /* [B] or NULL (-> S) */
+    int32_t reverse;
+    const float* grad_z_out;
+    const float* grad_ldj; /* [B] or NULL */
+    float* grad_z;
+    float* grad_weight;    /* [C,C] += or NULL : gradient w.r.t. the applied matrix */
+    float* grad_sldj;      /* [1] += or NULL */
+} cnf_invconv_bwd_args;
+
+CNF_API int cnf_invconv_bwd(const cnf_invconv_bwd_args* a, cnf_stream_t stream);
+
+typedef struct {
+    int64_t B, S;
+    int32_t C;
+    const float* x;                 /* [B,S,C] */
+    const float* pad;               /* [B,S] or NULL (applies to grad_out only) */
+    float mu, sigma;
+    const float* grad_out;          /* [B] gradient of the per-sample sums, or NULL */
+    const float* grad_elementwise;  /* [B,S,C] gradient of the element-wise values, or NULL */
+    float* grad_x;                  /* [B,S,C] */
+} cnf_logistic_logprob_bwd_args;
+
+CNF_API int cnf_logistic_logprob_bwd(const cnf_logistic_logprob_bwd_args* a, cnf_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,235 @@
+"""GPU parity of the backward kernels: gradients through the fused layers against torch autograd through
+the CPU oracle (the reference trains by autograd through exactly these eager float64 ops,
+general/train.py:148-152) for a random linear functional of (z_out, ldj).
+
+Tolerance: |g - g_ref| <= 2e-4 |g_ref| + 2e-5 * max|g_ref| per tensor (fp32 kernels vs the oracle's float64
+internals), parameter gradients (long reductions) 5e-4 relative to their max."""
+import pytest
+import torch
+
+from oracle import cnf_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def grads_close(a, b, what, rtol=2e-4, atol_rel=2e-5):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    assert a.shape == b.shape, "%s: shape %s vs %s" % (what, tuple(a.shape), tuple(b.shape))
+    scale = max(b.abs().max().item(), 1e-12)
+    err = (a - b).abs()
+    tol = rtol * b.abs() + atol_rel * scale
+    bad = err > tol
+    assert not bad.any(), "%s: %d/%d out of tolerance, worst err %.3e (scale %.3e)" % (
+        what, int(bad.sum()), bad.numel(), (err - tol).max().item(), scale)
+
+
+def leaf(t, cuda=False):
+    t = t.clone().cuda() if cuda else t.clone()
+    return t.requires_grad_(True)
+
+
+def _mix_inputs(B, S, C, K, seed, padded, chess=False, flip=False, ratio=0.5, nn_std=0.7):
+    g = torch.Generator().manual_seed(seed)
+    z = torch.randn(B, S, C, generator=g) * 1.3
+    nn_out = torch.randn(B, S, C * (2 + 3 * K), generator=g) * nn_std
+    sf, msf = torch.randn(C, generator=g) * 0.4, torch.randn(C, K, generator=g) * 0.4
+    if chess:
+        mask = torch.tensor([1.0, 0.0]).view(2, 1)
+    else:
+        n_cond = int(C * ratio)
+        mask = torch.zeros(1, C)
+        mask[0, :n_cond] = 1.0
+    if flip:
+        mask = 1 - mask
+    pad = None
+    if padded:
+        lens = torch.randint(max(1, S // 2), S + 1, (B,), generator=g)
+        pad = (torch.arange(S)[None, :] < lens[:, None]).float()
+    wz, wl = torch.randn(B, S, C, generator=g), torch.randn(B, generator=g)
+    return z, nn_out, sf, msf, mask, pad, wz, wl
+
+
+@pytest.mark.parametrize("B,S,C,K,padded,chess,flip,reg", [
+    (3, 32, 16, 8, False, False, False, False), (4, 40, 16, 8, True, False, False, True), (5, 38, 6, 16, True, False, False, True),
+    (3, 71, 2, 8, True, False, False, False), (4, 9, 1, 4, True, True, False, False), (3, 6, 4, 10, False, False, True, False),
+    (2, 5, 5, 3, False, False, False, False), (64, 64, 16, 8, False, False, False, False)])
+def test_mixcdf_backward_vs_oracle_autograd(B, S, C, K, padded, chess, flip, reg):
+    from categoricalnf_b200 import functional as CF
+    z, nn_out, sf, msf, mask, pad, wz, wl = _mix_inputs(B, S, C, K, seed=B + S + C + K, padded=padded, chess=chess, flip=flip)
+    reg_max, reg_factor = (1.0, 1.5) if reg else (-1.0, 1.0)
+    # oracle + autograd (CPU)
+    zo, no, so, mo = leaf(z), leaf(nn_out), leaf(sf), leaf(msf)
+    m = O.expand_mask(mask, z)
+    out, ldj, _ = O.mixcdf_coupling(zo, no, m, K, so, mo, pad=pad.unsqueeze(-1) if pad is not None else None,
+                                    reg_max=reg_max, reg_factor=reg_factor, training=True)
+    ((out * wz).sum() + (ldj * wl).sum()).backward()
+    # kernels (GPU)
+    zg, ng, sg, mg = leaf(z, True), leaf(nn_out, True), leaf(sf, True), leaf(msf, True)
+    mc, ms = (mask.flatten().tolist(), None) if mask.shape[0] == 1 else (None, mask.flatten().tolist())
+    out_g, ldj_g, _ = CF.mixcdf(zg, ng, K, sg, mg, mask_c=mc, mask_s=ms, pad=pad.cuda() if pad is not None else None,
+                                reg_max=reg_max, reg_factor=reg_factor, training=True)
+    ((out_g * wz.cuda()).sum() + (ldj_g * wl.cuda()).sum()).backward()
+    grads_close(zg.grad, zo.grad, "dL/dz")
+    grads_close(ng.grad, no.grad, "dL/dnn_out")
+    grads_close(sg.grad, so.grad, "dL/dscaling_factor", rtol=5e-4, atol_rel=5e-4)
+    grads_close(mg.grad, mo.grad, "dL/dmixture_scaling_factor", rtol=5e-4, atol_rel=5e-4)
+
+
+@pytest.mark.parametrize("reverse", [False, True])
+def test_affine_backward(reverse):
+    from categoricalnf_b200 import functional as CF
+    g = torch.Generator().manual_seed(3)
+    B, S, C = 6, 17, 6
+    z, nn_out, sf = torch.randn(B, S, C, generator=g), torch.randn(B, S, 2 * C, generator=g) * 0.6, torch.randn(C, generator=g) * 0.4
+    wz, wl = torch.randn(B, S, C, generator=g), torch.randn(B, generator=g)
+    mask = torch.zeros(1, C)
+    mask[0, :3] = 1.0
+    zo, no, so = leaf(z), leaf(nn_out), leaf(sf)
+    out, ldj = O.affine_coupling(zo, no, mask.unsqueeze(0), so, reverse=reverse)
+    ((out * wz).sum() + (ldj * wl).sum()).backward()
+    zg, ng, sg = leaf(z, True), leaf(nn_out, True), leaf(sf, True)
+    out_g, ldj_g = CF.affine_coupling(zg, ng, sg, mask_c=mask.flatten().tolist(), reverse=reverse)
+    ((out_g * wz.cuda()).sum() + (ldj_g * wl.cuda()).sum()).backward()
+    grads_close(zg.grad, zo.grad, "dL/dz")
+    grads_close(ng.grad, no.grad, "dL/dnn_out")
+    grads_close(sg.grad, so.grad, "dL/dscaling_factor", rtol=5e-4, atol_rel=5e-4)
+
+
+@pytest.mark.parametrize("reverse,padded,with_length", [(False, False, False), (False, True, False), (True, True, True), (False, False, True)])
+def test_actnorm_backward(reverse, padded, with_length):
+    from categoricalnf_b200 import functional as CF
+    g = torch.Generator().manual_seed(5)
+    B, S, C = 7, 23, 6
+    z = torch.randn(B, S, C, generator=g)
+    bias, scales = torch.randn(1, 1, C, generator=g) * 0.3, torch.randn(1, 1, C, generator=g) * 0.3
+    wz, wl = torch.randn(B, S, C, generator=g), torch.randn(B, generator=g)
+    lens = torch.randint(S // 2, S + 1, (B,), generator=g)
+    pad = (torch.arange(S)[None, :] < lens[:, None]).float() if padded else None
+    length = lens if with_length else None
+    zo, bo, so = leaf(z), leaf(bias), leaf(scales)
+    out, ldj = O.actnorm(zo, bo, so, reverse=reverse, length=length, pad=pad.unsqueeze(-1) if padded else None)
+    ((out * wz).sum() + (ldj * wl).sum()).backward()
+    zg, bg, sg = leaf(z, True), leaf(bias, True), leaf(scales, True)
+    ldj0 = torch.zeros(B, device="cuda")
+    out_g, ldj_g = CF.actnorm(zg, bg, sg, ldj0, pad=pad.cuda() if padded else None,
+                              length=length.float().cuda() if with_length else None, reverse=reverse)
+    ((out_g * wz.cuda()).sum() + (ldj_g * wl.cuda()).sum()).backward()
+    grads_close(zg.grad, zo.grad, "dL/dz")
+    grads_close(bg.grad, bo.grad, "dL/dbias", rtol=5e-4, atol_rel=5e-4)
+    grads_close(sg.grad, so.grad, "dL/dscales", rtol=5e-4, atol_rel=5e-4)
+
+
+@pytest.mark.parametrize("reverse", [False, True])
+def test_ext_actnorm_backward(reverse):
+    from categoricalnf_b200 import functional as CF
+    g = torch.Generator().manual_seed(7)
+    B, S, C = 9, 5, 4
+    z, ext = torch.randn(B, S, C, generator=g), torch.randn(B, S, 2 * C, generator=g) * 0.7
+    wz, wl = torch.randn(B, S, C, generator=g), torch.randn(B, generator=g)
+    pad = (torch.rand(B, S, generator=g) > 0.3).float()
+    zo, eo = leaf(z), leaf(ext)
+    out, ldj = O.ext_actnorm(zo, eo[..., :C], eo[..., C:], reverse=reverse, pad=pad.unsqueeze(-1))
+    ((out * wz).sum() + (ldj * wl).sum()).backward()
+    zg, eg = leaf(z, True), leaf(ext, True)
+    out_g, ldj_g = CF.ext_actnorm(zg, eg, torch.zeros(B, device="cuda"), pad=pad.cuda(), reverse=reverse)
+    ((out_g * wz.cuda()).sum() + (ldj_g * wl.cuda()).sum()).backward()
+    grads_close(zg.grad, zo.grad, "dL/dz")
+    grads_close(eg.grad, eo.grad, "dL/dext")
+
+
+@pytest.mark.parametrize("C,reverse,padded", [(16, False, False), (6, False, True), (2, True, True), (40, False, False)])
+def test_invconv_backward(C, reverse, padded):
+    from categoricalnf_b200 import functional as CF
+    g = torch.Generator().manual_seed(11 + C)
+    B, S = 5, 29
+    z = torch.randn(B, S, C, generator=g)
+    w = torch.linalg.qr(torch.randn(C, C, generator=g))[0] + 0.05 * torch.randn(C, C, generator=g)
+    sldj = torch.randn((), generator=g)
+    wz, wl = torch.randn(B, S, C, generator=g), torch.randn(B, generator=g)
+    lens = torch.randint(S // 2, S + 1, (B,), generator=g)
+    pad = (torch.arange(S)[None, :] < lens[:, None]).float() if padded else None
+    zo, wo, so = leaf(z), leaf(w), leaf(sldj)
+    out, ldj = O.invconv(zo, wo, so, reverse=reverse, length=lens if padded else None, pad=pad.unsqueeze(-1) if padded else None)
+    ((out * wz).sum() + (ldj * wl).sum()).backward()
+    zg, wg, sg = leaf(z, True), leaf(w, True), leaf(sldj, True)
+    out_g, ldj_g = CF.invconv(zg, wg, sg, torch.zeros(B, device="cuda"), pad=pad.cuda() if padded else None,
+                              length=lens.float().cuda() if padded else None, reverse=reverse)
+    ((out_g * wz.cuda()).sum() + (ldj_g * wl.cuda()).sum()).backward()
+    grads_close(zg.grad, zo.grad, "dL/dz")
+    grads_close(wg.grad, wo.grad, "dL/dW", rtol=5e-4, atol_rel=5e-4)
+    grads_close(sg.grad, so.grad, "dL/dsldj", rtol=5e-4, atol_rel=5e-4)
+
+
+def test_logistic_logprob_backward():
+    from categoricalnf_b200 import functional as CF
+    g = torch.Generator().manual_seed(13)
+    x = torch.randn(4, 11, 6, generator=g) * 3
+    w = torch.randn(4, 11, 6, generator=g)
+    xo = leaf(x)
+    (O.logistic_log_prob(xo) * w).sum().backward()
+    xg = leaf(x, True)
+    (CF.logistic_logprob(xg) * w.cuda()).sum().backward()
+    grads_close(xg.grad, xo.grad, "dL/dx")
+
+
+def test_tclinear_backward():
+    from categoricalnf_b200.layers.networks import TCLinear
+    g = torch.Generator().manual_seed(17)
+    x = torch.randn(37, 9, 48, generator=g)
+    ref = torch.nn.Linear(48, 72)
+    mod = TCLinear(48, 72).cuda()
+    mod.load_state_dict(ref.state_dict())
+    w = torch.randn(37, 9, 72, generator=g)
+    xo, xg = leaf(x), leaf(x, True)
+    (ref(xo) * w).sum().backward()
+    (mod(xg) * w.cuda()).sum().backward()
+    grads_close(xg.grad, xo.grad, "dL/dx", rtol=1e-4, atol_rel=1e-5)
+    grads_close(mod.weight.grad, ref.weight.grad, "dL/dW", rtol=1e-4, atol_rel=1e-5)
+    grads_close(mod.bias.grad, ref.bias.grad, "dL/db", rtol=1e-4, atol_rel=1e-5)
+
+
+def test_training_step_through_the_drop_in_flow():
+    """One optimisation-style step through the module API (encoding -> [ActNorm, InvConv, MixtureCDFCoupling]
+    x 2 -> prior): loss and every parameter gradient against autograd through the oracle composition."""
+    import workload as W
+    S, B = 24, 6
+    prm = W.data_init_oracle(W.lm_params(seed=5, S=S, blocks=2), seed=5)
+    tokens, u = W.lm_tokens(B, S, prm.V, seed=5), W.lm_noise(B, S, prm.D, seed=5)
+    # ---- oracle with autograd over the raw parameters ------------------------------------------------
+    names = ["bias", "scales", "l", "u", "log_s", "net_w", "net_b", "sf", "msf"]
+    leaves = [{k: leaf(b[k]) for k in names} for b in prm.blocks]
+    embed_w, pred_w, pred_b = leaf(prm.embed_w), leaf(prm.pred_w), leaf(prm.pred_b)
+    table = torch.nn.functional.linear(embed_w, pred_w, pred_b)
+    blocks = []
+    for b, lv in zip(prm.blocks, leaves):
+        w, sldj = O.invconv_weight(b["p"], lv["l"], lv["log_s"], lv["u"], b["sign_s"])
+        blocks.append(dict(bias=lv["bias"].view(1, 1, -1), scales=lv["scales"].view(1, 1, -1), weight=w, sldj=sldj, mask=b["mask"],
+                           K=prm.K, sf=lv["sf"], msf=lv["msf"],
+                           nn_fn=(lambda zin, lv=lv: torch.nn.functional.linear(zin, lv["net_w"], lv["net_b"]))))
+    z, ldj, lp = O.lm_flow_forward(tokens, u, dict(table=table, prior=prm.prior), blocks)
+    loss_ref = ((-ldj - lp) / S).mean()
+    loss_ref.backward()
+    # ---- drop-in modules on the GPU ---------------------------------------------------------------------
+    model, _ = W.build_lm_model(prm, torch.device("cuda", 0))
+    model.train()
+    from categoricalnf_b200 import functional as CF
+    zg, ldj_g = model(tokens.cuda(), u_noise=u.cuda())
+    lp_g = CF.logistic_logprob(zg).sum(dim=[1, 2])
+    loss = ((-ldj_g - lp_g) / S).mean()
+    loss.backward()
+    assert abs(loss.item() - loss_ref.item()) <= 1e-4 * abs(loss_ref.item()) + 1e-5
+    enc = model.flow_layers[0]
+    grads_close(enc.embed_layer.weight.grad, embed_w.grad, "embed", rtol=1e-3, atol_rel=1e-3)
+    grads_close(enc.flow_layers[0].pred_net.layer.weight.grad, pred_w.grad, "pred_net.weight", rtol=1e-3, atol_rel=1e-3)
+    grads_close(enc.flow_layers[0].pred_net.layer.bias.grad, pred_b.grad, "pred_net.bias", rtol=1e-3, atol_rel=1e-3)
+    for i, lv in enumerate(leaves):
+        an, conv, mix = model.flow_layers[1 + 3 * i: 4 + 3 * i]
+        grads_close(an.bias.grad.flatten(), lv["bias"].grad, "block %d actnorm bias" % i, rtol=1e-3, atol_rel=1e-3)
+        grads_close(an.scales.grad.flatten(), lv["scales"].grad, "block %d actnorm scales" % i, rtol=1e-3, atol_rel=1e-3)
+        grads_close(conv.l.grad, lv["l"].grad, "block %d conv l" % i, rtol=1e-3, atol_rel=1e-3)
+        grads_close(conv.u.grad, lv["u"].grad, "block %d conv u" % i, rtol=1e-3, atol_rel=1e-3)
+        grads_close(conv.log_s.grad, lv["log_s"].grad, "block %d conv log_s" % i, rtol=1e-3, atol_rel=1e-3)
+        grads_close(mix.nn.lin.weight.grad, lv["net_w"].grad, "block %d net weight" % i, rtol=1e-3, atol_rel=1e-3)
+        grads_close(mix.nn.lin.bias.grad, lv["net_b"].grad, "block %d net bias" % i, rtol=1e-3, atol_rel=1e-3)
+        grads_close(mix.scaling_factor.grad, lv["sf"].grad, "block %d sf" % i, rtol=1e-3, atol_rel=1e-3)
+        grads_close(mix.mixture_scaling_factor.grad, lv["msf"].grad, "block %d msf" % i, rtol=1e-3, atol_rel=1e-3)
