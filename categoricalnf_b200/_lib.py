@@ -79,6 +79,7 @@ class InvconvArgs(C.Structure):
         ("B", C.c_int64), ("S", C.c_int64), ("C", C.c_int32),
         ("z", vp), ("weight", vp), ("sldj", vp), ("pad", vp), ("length", vp), ("reverse", C.c_int32),
         ("z_out", vp), ("ldj", vp), ("status", vp),
+        ("pre_actnorm_bias", vp), ("pre_actnorm_scales", vp), ("out_mask", vp), ("z_masked_out", vp),
     ]
 
 
@@ -130,7 +131,7 @@ class LinearArgs(C.Structure):
 class LinearMixcdfArgs(C.Structure):
     _fields_ = [
         ("mix", MixcdfArgs), ("H", C.c_int32), ("precision", C.c_int32),
-        ("features", vp), ("weight", vp), ("bias", vp),
+        ("features", vp), ("weight", vp), ("bias", vp), ("next_mask", vp), ("z_masked_out", vp),
     ]
 
 

@@ -119,6 +119,10 @@ struct ApplyParams {
     uint32_t* status;
     long long P, B;
     int S, C, reverse;
+    // optional: ActNorm of the same block applied first, a = (z + b) e^{s} pad (activation_normalization.py:35-43),
+    // and a second output y * out_mask = the masked network input of the coupling layer that follows
+    const float *pre_b, *pre_s, *omask;
+    float* z_masked;
 };
 
 __device__ __forceinline__ void ldj_term(const ApplyParams& p, long long gtid, long long stride) {
@@ -136,18 +140,30 @@ __device__ __forceinline__ void ldj_term(const ApplyParams& p, long long gtid, l
 template <int C>
 __global__ void __launch_bounds__(kThreads) invconv_rows_kernel(const ApplyParams p) {
     __shared__ __align__(16) float s_w[C * C];
+    __shared__ __align__(16) float s_pb[C], s_pe[C], s_om[C];
     for (int i = threadIdx.x; i < C * C; i += kThreads) s_w[i] = p.w[i];
+    for (int i = threadIdx.x; i < C; i += kThreads) {
+        s_pb[i] = p.pre_b ? p.pre_b[i] : 0.f;
+        s_pe[i] = p.pre_s ? expf(p.pre_s[i]) : 1.0f;
+        s_om[i] = p.omask ? p.omask[i] : 1.0f;
+    }
     __syncthreads();
+    const bool pre = p.pre_b != nullptr || p.pre_s != nullptr;
     const long long gtid = (long long)blockIdx.x * kThreads + threadIdx.x;
     const long long stride = (long long)gridDim.x * kThreads;
     ldj_term(p, gtid, stride);
     for (long long pos = gtid; pos < p.P; pos += stride) {
         float x[C], y[C];
+        const float pv = p.pad ? p.pad[pos] : 1.0f;
         const float4* src = reinterpret_cast<const float4*>(p.z + pos * C);
 #pragma unroll
         for (int j = 0; j < C / 4; ++j) {
             const float4 v = ldg_stream4(src + j);
             x[4 * j] = v.x; x[4 * j + 1] = v.y; x[4 * j + 2] = v.z; x[4 * j + 3] = v.w;
+        }
+        if (pre) {
+#pragma unroll
+            for (int c = 0; c < C; ++c) x[c] = (x[c] + s_pb[c]) * s_pe[c] * pv;
         }
 #pragma unroll
         for (int co = 0; co < C; ++co) y[co] = 0.f;
@@ -162,14 +178,16 @@ __global__ void __launch_bounds__(kThreads) invconv_rows_kernel(const ApplyParam
                 y[4 * j + 3] = fmaf(x[ci], wv.w, y[4 * j + 3]);
             }
         }
-        const float pv = p.pad ? p.pad[pos] : 1.0f;
         float4* dst = reinterpret_cast<float4*>(p.z_out + pos * C);
+        float4* dstm = p.z_masked ? reinterpret_cast<float4*>(p.z_masked + pos * C) : nullptr;
         bool bad = false;
 #pragma unroll
         for (int j = 0; j < C / 4; ++j) {
             float4 v = make_float4(y[4 * j] * pv, y[4 * j + 1] * pv, y[4 * j + 2] * pv, y[4 * j + 3] * pv);
             bad = bad || v.x != v.x || v.y != v.y || v.z != v.z || v.w != v.w;
             stg_stream4(dst + j, v);
+            if (dstm != nullptr)
+                dstm[j] = make_float4(v.x * s_om[4 * j], v.y * s_om[4 * j + 1], v.z * s_om[4 * j + 2], v.w * s_om[4 * j + 3]);
         }
         if (bad) flag(p.status, CNF_FLAG_NAN_Z);
     }
@@ -189,11 +207,20 @@ __global__ void __launch_bounds__(kThreads) invconv_generic_kernel(const ApplyPa
         const long long pos = i / C;
         const int co = (int)(i - pos * C);
         const float* row = p.z + pos * C;
+        const float pv = p.pad ? p.pad[pos] : 1.0f;
         float acc = 0.f;
-        for (int ci = 0; ci < C; ++ci) acc = fmaf(row[ci], s_w[ci * C + co], acc);
-        if (p.pad) acc *= p.pad[pos];
+        if (p.pre_b != nullptr || p.pre_s != nullptr) {
+            for (int ci = 0; ci < C; ++ci) {
+                const float a = (row[ci] + (p.pre_b ? p.pre_b[ci] : 0.f)) * (p.pre_s ? __expf(p.pre_s[ci]) : 1.0f) * pv;
+                acc = fmaf(a, s_w[ci * C + co], acc);
+            }
+        } else {
+            for (int ci = 0; ci < C; ++ci) acc = fmaf(row[ci], s_w[ci * C + co], acc);
+        }
+        acc *= pv;
         if (acc != acc) flag(p.status, CNF_FLAG_NAN_Z);
         p.z_out[i] = acc;
+        if (p.z_masked) p.z_masked[i] = acc * (p.omask ? p.omask[co] : 1.0f);
     }
 }
 
@@ -225,7 +252,10 @@ extern "C" int cnf_invconv_apply(const cnf_invconv_args* a, cnf_stream_t stream_
     if (a->B == 0) return CNF_OK;
     CNF_REQUIRE(a->weight && a->sldj, "weight / sldj is NULL");
     ApplyParams p{a->z, a->weight, a->sldj, a->pad, a->length, a->z_out, a->ldj, a->status,
-                  a->B * a->S, a->B, (int)a->S, a->C, a->reverse};
+                  a->B * a->S, a->B, (int)a->S, a->C, a->reverse,
+                  a->pre_actnorm_bias, a->pre_actnorm_scales, a->out_mask, a->z_masked_out};
+    CNF_SUPPORTED(!(a->reverse && (a->pre_actnorm_bias || a->pre_actnorm_scales)), "the fused ActNorm prologue is forward only");
+    CNF_REQUIRE(a->z_masked_out == nullptr || (reinterpret_cast<uintptr_t>(a->z_masked_out) & 15) == 0, "z_masked_out must be 16-byte aligned");
     CNF_REQUIRE(p.P == 0 || (a->z && a->z_out), "z / z_out is NULL");
     CNF_REQUIRE(a->z != a->z_out, "invconv cannot run in place");
     const bool aligned = ((reinterpret_cast<uintptr_t>(a->z) | reinterpret_cast<uintptr_t>(a->z_out)) & 15) == 0;

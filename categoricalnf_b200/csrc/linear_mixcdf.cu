@@ -59,6 +59,14 @@ struct FusedParams {
     unsigned long long cond_s;
     float reg_max, reg_factor;
     int use_reg;
+    // optional epilogue: ActNorm + 1x1 convolution of the NEXT flow block on the finished row
+    // (activation_normalization.py:35-43, permutation_layers.py:111-121), and the next coupling's masked input
+    const float* nx_bias;
+    const float* nx_scales;
+    const float* nx_w;       // [C,C] row-major, z @ W
+    const float* nx_mask;    // [C] mask of the next coupling (1 = conditioner input) or NULL
+    float* z_masked_out;     // [P,C] = z_out * nx_mask, or NULL
+    int next;                // 1: epilogue enabled
 };
 
 constexpr int padded_record(int pn) { return pn <= 16 ? 16 : (pn <= 32 ? 32 : 64); }
@@ -134,7 +142,15 @@ linear_mixcdf_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_cons
     float* s_mfac = reinterpret_cast<float*>(s_bnd + CT * KT);    // [CT * KT]
     float* s_scr = s_mfac + CT * KT;                              // [kEpiWarps][PNP] float64-escape scratch
     float2* s_fa = reinterpret_cast<float2*>(s_scr + kEpiWarps * PNP);   // [CT] (e^{sf}, 2 log2e / max(e^{sf},1))
-    uint64_t* full = reinterpret_cast<uint64_t*>(s_fa + CT);
+    // next-block epilogue: bias, e^{scales}, W^T (output-major), next mask; two output tiles (+ two masked tiles)
+    float* s_nb = reinterpret_cast<float*>(s_fa + CT);
+    float* s_ne = s_nb + (p.next ? C : 0);
+    float* s_wT = s_ne + (p.next ? C : 0);
+    float* s_nm = s_wT + (p.next ? C * C : 0);
+    float* s_out = s_nm + (p.next ? C : 0);                       // [2][128 * C]
+    float* s_msk = s_out + (p.next ? 2 * ztile : 0);              // [2][128 * C]
+    float* s_end = s_msk + ((p.next && p.z_masked_out) ? 2 * ztile : 0);
+    uint64_t* full = reinterpret_cast<uint64_t*>(s_end + ((s_end - reinterpret_cast<float*>(smem)) & 1));
     uint64_t* empty = full + p.stages;
     uint64_t* ready = empty + p.stages;
     uint64_t* tmem_full = ready + p.stages;
@@ -173,6 +189,17 @@ linear_mixcdf_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_cons
         const float mf = p.msf ? expf(p.msf[(p.c0 + i / KT) * KT + i % KT]) : 1.0f;
         s_mfac[i] = mf;
         s_bnd[(i % KT) * CT + i / KT] = make_float2(2.0f * kLog2e / fmaxf(mf, 1.0f), -mf * kLog2e);
+    }
+    if (p.next) {
+        for (int i = tid; i < C; i += kThreadsFused) {
+            s_nb[i] = p.nx_bias ? p.nx_bias[i] : 0.f;
+            s_ne[i] = p.nx_scales ? expf(p.nx_scales[i]) : 1.0f;
+            s_nm[i] = p.nx_mask ? p.nx_mask[i] : 1.0f;
+        }
+        for (int i = tid; i < C * C; i += kThreadsFused) {
+            const int c = i / C, o = i - c * C;   // W[c][o]
+            s_wT[o * C + c] = p.nx_w ? p.nx_w[i] : (c == o ? 1.0f : 0.f);
+        }
     }
     tcgen05_fence_before();
     __syncthreads();
@@ -391,13 +418,49 @@ linear_mixcdf_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_cons
             // ---- z tile out, next z tile in -------------------------------------------------------
             fence_proxy_async_smem();
             epi_barrier();
-            if (manager) {
-                const int rows = (int)min((long long)kBM, p.P - pos0);
-                bulk_store(p.z_out + pos0 * C, s_z + zb * ztile, (uint32_t)(rows * C * 4));
-                tma_store_commit();
-                if (it + 2 < tiles) {
-                    tma_store_wait_read<1>();   // the store of tile it-1 has drained buffer (it+2) % 3
-                    z_load(it + 2);
+            if (!p.next) {
+                if (manager) {
+                    const int rows = (int)min((long long)kBM, p.P - pos0);
+                    bulk_store(p.z_out + pos0 * C, s_z + zb * ztile, (uint32_t)(rows * C * 4));
+                    tma_store_commit();
+                    if (it + 2 < tiles) {
+                        tma_store_wait_read<1>();   // the store of tile it-1 has drained buffer (it+2) % 3
+                        z_load(it + 2);
+                    }
+                }
+            } else {
+                // next block on the finished row: a = (z + b) e^{s} pad ; y = (a @ W) pad.  Thread (row, g) makes
+                // the output channels o = g, g+3, ..; rows are read from the z tile and written to an output tile.
+                float* so = s_out + (it & 1) * ztile + row * C;
+                float* sk = s_msk + (it & 1) * ztile + row * C;
+                if (valid) {
+                    for (int o = g; o < C; o += kGroups) {
+                        const float* wr = s_wT + o * C;
+                        float y = 0.f;
+                        for (int c4 = 0; c4 < C; c4 += 4) {
+                            const float4 zv = *reinterpret_cast<const float4*>(zt + c4);
+                            const float4 nb = *reinterpret_cast<const float4*>(s_nb + c4);
+                            const float4 ne = *reinterpret_cast<const float4*>(s_ne + c4);
+                            const float4 wv = *reinterpret_cast<const float4*>(wr + c4);
+                            y = fmaf((zv.x + nb.x) * ne.x * padv, wv.x, y);
+                            y = fmaf((zv.y + nb.y) * ne.y * padv, wv.y, y);
+                            y = fmaf((zv.z + nb.z) * ne.z * padv, wv.z, y);
+                            y = fmaf((zv.w + nb.w) * ne.w * padv, wv.w, y);
+                        }
+                        y *= padv;
+                        so[o] = y;
+                        if (p.z_masked_out) sk[o] = y * s_nm[o];
+                    }
+                }
+                fence_proxy_async_smem();
+                epi_barrier();
+                if (manager) {
+                    const int rows = (int)min((long long)kBM, p.P - pos0);
+                    bulk_store(p.z_out + pos0 * C, s_out + (it & 1) * ztile, (uint32_t)(rows * C * 4));
+                    if (p.z_masked_out) bulk_store(p.z_masked_out + pos0 * C, s_msk + (it & 1) * ztile, (uint32_t)(rows * C * 4));
+                    tma_store_commit();
+                    tma_store_wait_read<1>();       // the stores of tile it-1 have drained the other output tile
+                    if (it + 2 < tiles) z_load(it + 2);   // buffer (it+2) % 3 was last read before this tile's barriers
                 }
             }
         }
@@ -414,24 +477,26 @@ linear_mixcdf_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_cons
 }
 
 template <int KT, int CT>
-size_t fused_smem(int C, int stages, bool strict) {
+size_t fused_smem(int C, int stages, bool strict, int next = 0, int masked = 0) {
     constexpr int PN = 2 + 3 * KT, PNP = padded_record(PN), BN = CT * PNP;
     const size_t stage = (size_t)(kABytes + BN * 128) * (strict ? 2 : 1);
     size_t f = 1024 + stages * stage + (size_t)kZStages * kBM * C * 4;
     f += ((size_t)CT * PN + 1 + 3 * (size_t)CT * KT + 1 + (size_t)kEpiWarps * PNP + 2 * CT) * 4;
     f += (3 * (size_t)stages + 4 + kZStages) * 8 + 256;
+    if (next) f += ((size_t)3 * C + (size_t)C * C + (size_t)(masked ? 4 : 2) * kBM * C) * 4;
     return f;
 }
 
 template <int KT, int CT, bool REV, bool STRICT>
 int launch_fused(const CUtensorMap& tm_h, const CUtensorMap& tm_w, FusedParams p, cudaStream_t stream) {
     constexpr size_t kMaxSmem = 232448;
+    const int msk = p.z_masked_out != nullptr;
     int stages = 4;
-    while (stages > 1 && fused_smem<KT, CT>(p.C, stages, STRICT) > kMaxSmem) --stages;
-    const size_t need = fused_smem<KT, CT>(p.C, stages, STRICT);
+    while (stages > 1 && fused_smem<KT, CT>(p.C, stages, STRICT, p.next, msk) > kMaxSmem) --stages;
+    const size_t need = fused_smem<KT, CT>(p.C, stages, STRICT, p.next, msk);
     CNF_SUPPORTED(need <= kMaxSmem, "fused projection + mixture tile does not fit shared memory");
     p.stages = stages;
-    const size_t smem = fused_smem<KT, CT>(p.C, stages, STRICT);
+    const size_t smem = need;
     CNF_CUDA(cudaFuncSetAttribute(linear_mixcdf_kernel<KT, CT, REV, STRICT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
     long long grid = sm_count();
     if (grid > p.ntiles) grid = p.ntiles;
@@ -456,7 +521,6 @@ int check_fusable(const cnf_linear_mixcdf_args* a, MaskView* mv, const char** wh
     if (m.C % 4 != 0 || m.C > 32) { *why = "C must be a multiple of 4, at most 32"; return 0; }
     if (a->H < 1 || a->H % 4 != 0) { *why = "in_features must be a multiple of 4"; return 0; }
     if (m.params_prebounded) { *why = "pre-bounded parameters"; return 0; }
-    if (m.next_actnorm_bias || m.next_actnorm_scales || m.next_conv_weight) { *why = "next-block epilogue is not available in the fused projection kernel"; return 0; }
     if ((reinterpret_cast<uintptr_t>(a->features) | reinterpret_cast<uintptr_t>(a->weight) | reinterpret_cast<uintptr_t>(m.z) |
          reinterpret_cast<uintptr_t>(m.z_out)) & 15) { *why = "features / weight / z / z_out must be 16-byte aligned"; return 0; }
     if (m.B * m.S >= (1ll << 31) - 256) { *why = "too many positions for 32-bit TMA coordinates"; return 0; }
@@ -491,6 +555,12 @@ int run_fused(const cnf_linear_mixcdf_args* a, cnf_stream_t stream_, int reverse
     p.s_period = mv.s_period; p.cond_s = mv.cond_s;
     p.reg_max = m.reg_max; p.reg_factor = m.reg_factor;
     p.use_reg = (!reverse && m.reg_max > 0.f && m.training) ? 1 : 0;
+    p.nx_bias = m.next_actnorm_bias; p.nx_scales = m.next_actnorm_scales; p.nx_w = m.next_conv_weight;
+    p.next = (p.nx_bias || p.nx_scales || p.nx_w) ? 1 : 0;
+    CNF_SUPPORTED(!(p.next && reverse), "the next-block epilogue exists for the forward direction only");
+    CNF_REQUIRE(p.next || (a->next_mask == nullptr && a->z_masked_out == nullptr), "next_mask / z_masked_out need the next-block epilogue");
+    p.nx_mask = a->next_mask; p.z_masked_out = a->z_masked_out;
+    CNF_REQUIRE(a->z_masked_out == nullptr || (reinterpret_cast<uintptr_t>(a->z_masked_out) & 15) == 0, "z_masked_out must be 16-byte aligned");
 
     CUtensorMap tm_h, tm_w;
     int rc = tc_encode_2d(&tm_h, a->features, a->H, P, kBK, kBM);

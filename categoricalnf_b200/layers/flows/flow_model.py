@@ -15,6 +15,27 @@ from .activation_normalization import ActNormFlow
 from .permutation_layers import InvertibleConv
 
 
+def _actnorm_conv_fused(z, an, conv, out_mask, channel_padding_mask=None, length=None, **kwargs):
+    """``ActNormFlow`` + ``InvertibleConv`` of one flow block in ONE pass over z (``cnf_invconv_apply`` with the
+    ActNorm prologue), optionally emitting ``z_out * out_mask`` = the masked input of the coupling that follows.
+    Returns (z_out, ldj of both layers, {}[, z_masked])."""
+    from .mixture_cdf_layer import add_next_block_ldj
+    weight, sldj = conv._get_weight(device_name=str(z.device), inverse=False)
+    out = ops.invconv_apply(z, weight, sldj, None, pad=channel_padding_mask, pre_actnorm=(an.bias, an.scales),
+                            out_mask=out_mask)
+    ldj = torch.zeros(z.size(0), dtype=torch.float32, device=z.device)
+    add_next_block_ldj(ldj, an, sldj, z.size(1), channel_padding_mask, length)
+    return (out[0], ldj, {}) + ((out[2],) if out_mask is not None else ())
+
+
+def _next_coupling_mask(order, pos):
+    """Channel mask [1, C] of the layer at ``pos`` when that layer accepts a pre-masked input, else None."""
+    nxt = order[pos][1] if pos < len(order) else None
+    if getattr(nxt, "accepts_masked_input", False) and nxt.mask.dim() == 2 and nxt.mask.size(0) == 1:
+        return nxt.mask
+    return None
+
+
 class FlowModel(nn.Module):
 
     def __init__(self, layers=None, name="Flow model"):
@@ -39,21 +60,38 @@ class FlowModel(nn.Module):
         ldj_per_layer = []
         skip = 0
         can_fuse = self.fuse_blocks and not reverse and not get_ldj_per_layer and not torch.is_grad_enabled() and z.is_cuda
+        masked = None   # z * mask of the upcoming coupling layer, when the previous kernel already produced it
         for pos, (index, layer) in enumerate(order):
             if skip > 0:
                 skip -= 1
                 continue
             res = None
+            extra = {}
+            if masked is not None and getattr(layer, "accepts_masked_input", False):
+                extra["cnf_masked_input"] = masked
+            masked = None
             if can_fuse and hasattr(layer, "try_forward_fused") and pos + 2 < len(order):
                 # [encoding | mixture coupling] followed by ActNorm + 1x1 conv: the two bandwidth-only
                 # layers run inside the producing kernel's epilogue (two passes over z saved per block)
                 an, conv = order[pos + 1][1], order[pos + 2][1]
                 if type(an) is ActNormFlow and type(conv) is InvertibleConv and not an.training and not conv.training:
-                    res = layer.try_forward_fused(z, an, conv, **kwargs)
+                    nmask = _next_coupling_mask(order, pos + 3) if getattr(layer, "accepts_masked_input", False) else None
+                    if nmask is not None:
+                        extra["cnf_next_mask"] = nmask
+                    res = layer.try_forward_fused(z, an, conv, **extra, **kwargs)
+                    extra.pop("cnf_next_mask", None)
                     if res is not None:
                         skip = 2
+            if res is None and can_fuse and type(layer) is ActNormFlow and pos + 1 < len(order) and z.dim() == 3 \
+                    and type(order[pos + 1][1]) is InvertibleConv and not layer.training and not order[pos + 1][1].training:
+                # ActNorm + 1x1 conv of a block in one pass, plus the masked input of the coupling that follows
+                res = _actnorm_conv_fused(z, layer, order[pos + 1][1], _next_coupling_mask(order, pos + 2), **kwargs)
+                skip = 1
+            if res is not None and len(res) == 4:
+                masked = res[3]
+                res = res[:3]
             if res is None:
-                res = layer(z, reverse=reverse, get_ldj_per_layer=get_ldj_per_layer, **kwargs)
+                res = layer(z, reverse=reverse, get_ldj_per_layer=get_ldj_per_layer, **extra, **kwargs)
             if len(res) == 2:
                 z, layer_ldj = res
                 detail = layer_ldj

@@ -93,6 +93,10 @@ class MixtureCDFCoupling(CouplingLayer):
     # two-step path within the 3xTF32 projection error (~1e-6); set False to force the two-step path.
     fuse_final_projection = True
     projection_precision = "3xtf32"
+    # The fused projection kernel can also run the next block's ActNorm + 1x1 conv in its epilogue, but the extra
+    # shared memory costs it a pipeline stage (measured slower than ActNorm + conv as one separate pass), so the
+    # container uses cnf_invconv_apply with the ActNorm prologue instead unless this is set.
+    fuse_next_in_projection_kernel = False
 
     def _projection_split(self, z):
         """(features_fn, linear) when the final projection of ``self.nn`` can be fused for ``z``, else None."""
@@ -106,23 +110,45 @@ class MixtureCDFCoupling(CouplingLayer):
             return None
         return split
 
-    def forward(self, z, ldj=None, reverse=False, channel_padding_mask=None, **kwargs):
+    accepts_masked_input = True   # FlowModel may hand over `cnf_masked_input` = z * mask made by the previous kernel
+
+    def forward(self, z, ldj=None, reverse=False, channel_padding_mask=None, cnf_masked_input=None, **kwargs):
         # the incoming ldj is ignored and only this layer's ldj is returned, as upstream (:46-47,:63)
+        res = self._forward_impl(z, reverse, channel_padding_mask, cnf_masked_input, None, kwargs)
+        return res[:3]
+
+    def _forward_impl(self, z, reverse, channel_padding_mask, masked_input, fuse, kwargs):
+        """``fuse`` = None or (actnorm, conv, next_mask): next-block epilogue of the fused projection kernel.
+        Returns (z_out, ldj, detail[, z_masked]) - or None when ``fuse`` was requested but is not possible."""
         mask_c, mask_s = mask_lists(self, "mask", z.size(1))
-        x_in = z * self._prepare_mask(self.mask, z)
+        x_in = masked_input if masked_input is not None else z * self._prepare_mask(self.mask, z)
         split = self._projection_split(z)
         if split is not None:
             features_fn, lin = split
             feats = features_fn(x_in, **kwargs)
             if feats.dim() == 3 and ops.linear_mixcdf_fusable(z, feats, lin.weight, self.num_mixtures, mask_c=mask_c, mask_s=mask_s):
-                z_out, ldj, reg = ops.linear_mixcdf(
+                extra = {}
+                if fuse is not None:
+                    actnorm, conv, next_mask = fuse
+                    weight, sldj = conv._get_weight(device_name=str(z.device), inverse=False)
+                    extra = dict(fuse_next=(actnorm.bias, actnorm.scales, weight), next_mask=next_mask)
+                out = ops.linear_mixcdf(
                     z, feats, lin.weight, lin.bias, self.num_mixtures, mask_c=mask_c, mask_s=mask_s, pad=channel_padding_mask,
                     scaling_factor=self.scaling_factor, mixture_scaling_factor=self.mixture_scaling_factor, reverse=reverse,
                     reg_max=self.regularizer_max, reg_factor=self.regularizer_factor, training=self.training, want_reg=True,
-                    precision=self.projection_precision)
-                return z_out, ldj, {"ldj": ldj, "regularizer_ldj": reg}
+                    precision=self.projection_precision, **extra)
+                z_out, ldj, reg = out[:3]
+                detail = {"ldj": ldj, "regularizer_ldj": reg}
+                if fuse is not None:
+                    detail = {"ldj": ldj.clone(), "regularizer_ldj": reg}
+                    add_next_block_ldj(ldj, actnorm, sldj, z.size(1), channel_padding_mask, kwargs.get("length", None))
+                return (z_out, ldj, detail) + tuple(out[3:])
+            if fuse is not None:
+                return None
             nn_out = lin(feats)     # shape / alignment outside the fused kernel: finish the network as usual
         else:
+            if fuse is not None:
+                return None
             nn_out = self.run_network(x=x_in, **kwargs)
         z_out, ldj, reg = CF.mixcdf(z, nn_out, self.num_mixtures, self.scaling_factor, self.mixture_scaling_factor,
                                     mask_c=mask_c, mask_s=mask_s, pad=channel_padding_mask, reverse=reverse,
@@ -130,21 +156,29 @@ class MixtureCDFCoupling(CouplingLayer):
                                     training=self.training)
         return z_out, ldj, {"ldj": ldj, "regularizer_ldj": reg}
 
-    def try_forward_fused(self, z, actnorm, conv, channel_padding_mask=None, length=None, **kwargs):
+    def try_forward_fused(self, z, actnorm, conv, channel_padding_mask=None, length=None, cnf_masked_input=None,
+                          cnf_next_mask=None, **kwargs):
         """Forward of this layer AND of the following ``ActNormFlow`` + ``InvertibleConv`` in one kernel
-        (evaluation only).  Returns ``(z, ldj, detail)`` with the three layers' ldj summed, or None
-        when the kernel cannot fuse for this shape / mask (caller then runs the layers one by one)."""
+        (evaluation only).  Returns ``(z, ldj, detail[, z_masked])`` with the three layers' ldj summed
+        (``z_masked`` = z * ``cnf_next_mask`` when the kernel produced it), or None when the kernel cannot fuse
+        for this shape / mask (caller then runs the layers one by one)."""
         if self.training or z.dim() != 3:
             return None
         if self._projection_split(z) is not None:
-            return None   # the final-projection fusion of forward() saves more traffic than this epilogue
+            if not self.fuse_next_in_projection_kernel:
+                return None
+            # final projection + transform + next block in the tcgen05 kernel
+            if length is not None:
+                kwargs = dict(kwargs, length=length)
+            return self._forward_impl(z, False, channel_padding_mask, cnf_masked_input, (actnorm, conv, cnf_next_mask), kwargs)
         mask_c, mask_s = mask_lists(self, "mask", z.size(1))
         # cheap shape pre-check (the kernel fuses for C=16, K=8, 8 contiguous transformed channels) so the
         # network is not run twice; the library has the final word below
         if z.size(2) != 16 or self.num_mixtures != 8 or mask_s is not None or mask_c is None or \
                 sum(1 for m in mask_c if m == 0) != 8:
             return None
-        nn_out = self.run_network(x=z * self._prepare_mask(self.mask, z), length=length, **kwargs)
+        x_in = cnf_masked_input if cnf_masked_input is not None else z * self._prepare_mask(self.mask, z)
+        nn_out = self.run_network(x=x_in, length=length, **kwargs)
         if not ops.mixcdf_fusable(z, nn_out, self.num_mixtures, mask_c=mask_c, mask_s=mask_s):
             return None   # note: the network has run; the caller's unfused call runs it again
         weight, sldj = conv._get_weight(device_name=str(z.device), inverse=False)

@@ -263,8 +263,12 @@ def invconv_build(p=None, l=None, u=None, log_s=None, sign_s=None, weight=None, 
     return w, w_inv, sldj
 
 
-def invconv_apply(z, weight, sldj, ldj=None, *, pad=None, length=None, reverse=False):
-    """K5 apply.  Returns ``(z_out, ldj)``; ldj (if given) is updated in place."""
+def invconv_apply(z, weight, sldj, ldj=None, *, pad=None, length=None, reverse=False, pre_actnorm=None, out_mask=None):
+    """K5 apply.  Returns ``(z_out, ldj)``; ldj (if given) is updated in place.
+
+    ``pre_actnorm = (bias [C], scales [C])`` applies the block's ActNorm first in the same pass (forward only;
+    its per-sample-constant ldj term is NOT added here).  With ``out_mask`` [C] a third value
+    ``z_out * out_mask`` is returned (the masked network input of the following coupling layer)."""
     z = _f32(z, "z")
     B, S, Cc = z.shape
     weight = _f32(weight, "weight", (Cc, Cc))
@@ -278,7 +282,22 @@ def invconv_apply(z, weight, sldj, ldj=None, *, pad=None, length=None, reverse=F
     a.B, a.S, a.C = B, S, Cc
     a.z, a.weight, a.sldj, a.pad, a.length = _ptr(z), _ptr(weight), _ptr(sldj), _ptr(pad), _ptr(length)
     a.reverse, a.z_out, a.ldj, a.status = int(bool(reverse)), _ptr(z_out), _ptr(ldj), _ptr(status_word(z.device))
-    _call("cnf_invconv_apply", a, z)
+    keep, z_masked = (z, weight, sldj, pad, length), None
+    if pre_actnorm is not None:
+        pb = _f32(pre_actnorm[0], "actnorm bias").reshape(-1)
+        ps = _f32(pre_actnorm[1], "actnorm scales").reshape(-1)
+        keep = keep + (pb, ps)
+        a.pre_actnorm_bias, a.pre_actnorm_scales = _ptr(pb), _ptr(ps)
+    if out_mask is not None:
+        om = _f32(out_mask, "out_mask").reshape(-1)
+        if om.numel() != Cc:
+            raise ValueError("out_mask has %d entries, expected %d" % (om.numel(), Cc))
+        z_masked = torch.empty_like(z)
+        keep = keep + (om,)
+        a.out_mask, a.z_masked_out = _ptr(om), _ptr(z_masked)
+    _call("cnf_invconv_apply", a, z, keep)
+    if z_masked is not None:
+        return z_out, ldj, z_masked
     return z_out, ldj
 
 
@@ -458,10 +477,15 @@ def linear_mixcdf_fusable(z, features, weight, num_mixtures, *, mask_c=None, mas
 
 def linear_mixcdf(z, features, weight, bias, num_mixtures, *, mask_c=None, mask_s=None, pad=None, scaling_factor=None,
                   mixture_scaling_factor=None, reverse=False, reg_max=-1.0, reg_factor=1.0, training=False, ldj=None,
-                  want_reg=False, precision="3xtf32"):
+                  want_reg=False, precision="3xtf32", fuse_next=None, next_mask=None):
     """Final projection of the coupling network + mixture coupling transform in ONE kernel:
     ``mixcdf(z, features @ weight.T + bias, ...)`` without materialising the network output
-    (``cnf_linear_mixcdf_fwd`` / ``_inv``).  Returns ``(z_out, ldj [B], reg_ldj [B] | None)``."""
+    (``cnf_linear_mixcdf_fwd`` / ``_inv``).  Returns ``(z_out, ldj [B], reg_ldj [B] | None)``.
+
+    ``fuse_next = (bias [C], scales [C], W [C,C])`` additionally applies the next block's ActNorm + 1x1
+    convolution to the finished row (forward only; their per-sample-constant ldj terms are NOT added here).
+    With ``next_mask`` ([C], the next coupling's mask) a fourth value ``z_out * next_mask`` is returned - the
+    network input of that coupling (coupling_layer.py:53) - saving its separate masking pass."""
     a, keep = _linear_mixcdf_args(z, features, weight, bias, num_mixtures, mask_c, mask_s, pad, scaling_factor,
                                   mixture_scaling_factor, precision)
     z = keep[1]
@@ -474,5 +498,24 @@ def linear_mixcdf(z, features, weight, bias, num_mixtures, *, mask_c=None, mask_
     a.mix.accumulate = int(accumulate)
     a.mix.z_out, a.mix.ldj, a.mix.reg_ldj = _ptr(z_out), _ptr(ldj_t), _ptr(reg)
     a.mix.status = _ptr(status_word(z.device))
+    z_masked = None
+    if fuse_next is not None:
+        Cc = z.shape[2]
+        nb = _f32(fuse_next[0], "next bias").reshape(-1)
+        ns = _f32(fuse_next[1], "next scales").reshape(-1)
+        nw = _f32(fuse_next[2], "next conv weight", (Cc, Cc))
+        keep = keep + (nb, ns, nw)
+        a.mix.next_actnorm_bias, a.mix.next_actnorm_scales, a.mix.next_conv_weight = _ptr(nb), _ptr(ns), _ptr(nw)
+        if next_mask is not None:
+            nm = _f32(next_mask, "next mask").reshape(-1)
+            if nm.numel() != Cc:
+                raise ValueError("next_mask has %d entries, expected %d" % (nm.numel(), Cc))
+            z_masked = torch.empty_like(z)
+            keep = keep + (nm,)
+            a.next_mask, a.z_masked_out = _ptr(nm), _ptr(z_masked)
+    elif next_mask is not None:
+        raise ValueError("next_mask needs fuse_next")
     _call("cnf_linear_mixcdf_inv" if reverse else "cnf_linear_mixcdf_fwd", a, z, keep)
+    if z_masked is not None:
+        return z_out, ldj_t, reg, z_masked
     return z_out, ldj_t, reg

@@ -231,6 +231,13 @@ typedef struct {
     float* z_out;
     float* ldj;           /* [B] in/out or NULL */
     uint32_t* status;
+    /* optional (forward only): the ActNorm of the same flow block applied first, a = (z + b) e^{s} pad
+     * (its ldj term sum(s) * len is added by the caller, cnf_ldj_axpy), and a second output
+     * z_out * out_mask = the network input of the coupling layer that follows (coupling_layer.py:53). */
+    const float* pre_actnorm_bias;    /* [C] or NULL */
+    const float* pre_actnorm_scales;  /* [C] or NULL */
+    const float* out_mask;            /* [C] or NULL */
+    float* z_masked_out;              /* [B,S,C] or NULL */
 } cnf_invconv_args;
 
 CNF_API int cnf_invconv_apply(const cnf_invconv_args* a, cnf_stream_t stream);
@@ -354,8 +361,8 @@ CNF_API int cnf_linear_fwd(const cnf_linear_args* a, cnf_stream_t stream);
  *   followed by cnf_mixcdf_fwd / cnf_mixcdf_inv on that nn_out (mixture_cdf_layer.py:95-180),
  *   without nn_out [B,S,C*(2+3K)] ever being written to memory: the records of the transformed
  *   channels are produced by tcgen05.mma into tensor memory and consumed from there.
- * `mix` is read like in cnf_mixcdf_fwd except that mix.nn_out is ignored (may be NULL) and the
- * next_* epilogue is not available.  Shapes: see cnf_linear_mixcdf_fusable (K in {4,8,16}, 4 or 8
+ * `mix` is read like in cnf_mixcdf_fwd except that mix.nn_out is ignored (may be NULL); the
+ * mix.next_* epilogue (ActNorm + 1x1 conv of the next block) is available for every fusable shape.  Shapes: see cnf_linear_mixcdf_fusable (K in {4,8,16}, 4 or 8
  * contiguous transformed channels, C % 4 == 0, C <= 32, H % 4 == 0, 16-byte aligned tensors).
  * ---------------------------------------------------------------------------------------- */
 typedef struct {
@@ -365,6 +372,10 @@ typedef struct {
     const float* features;  /* [B,S,H] input of the final projection         */
     const float* weight;    /* [C*(2+3K), H] nn.Linear.weight                */
     const float* bias;      /* [C*(2+3K)] or NULL                            */
+    /* with the mix.next_* epilogue (forward only): the NEXT coupling layer's channel mask (1 = conditioner
+     * input) and a second output z_out * next_mask = that layer's network input (coupling_layer.py:53)  */
+    const float* next_mask; /* [C] or NULL                                   */
+    float* z_masked_out;    /* [B,S,C] or NULL                               */
 } cnf_linear_mixcdf_args;
 
 CNF_API int cnf_linear_mixcdf_fwd(const cnf_linear_mixcdf_args* a, cnf_stream_t stream);

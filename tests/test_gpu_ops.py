@@ -305,3 +305,28 @@ def test_categ_encode_philox_roundtrip():
     assert (dec.cpu() == x).float().mean() > 0.999
     # oracle on the same latent: posterior of the true class, given the noise implied by z
     assert torch.isfinite(ldj).all() and (cpl <= 1e-5).all()
+
+
+@pytest.mark.parametrize("C,padded", [(16, False), (8, True), (6, True), (32, False)])
+def test_invconv_with_actnorm_prologue_and_masked_output(C, padded):
+    """cnf_invconv_apply with the ActNorm prologue (+ masked second output) equals ActNorm, 1x1 conv and the
+    mask multiply run one after the other."""
+    from categoricalnf_b200 import ops
+    g = torch.Generator().manual_seed(40 + C)
+    B, S = 5, 37
+    z = torch.randn(B, S, C, generator=g)
+    bias, scales = torch.randn(C, generator=g) * 0.3, torch.randn(C, generator=g) * 0.3
+    w = torch.linalg.qr(torch.randn(C, C, generator=g))[0].contiguous()
+    sldj = torch.randn(1, generator=g)
+    omask = (torch.rand(C, generator=g) > 0.5).float()
+    lens = torch.randint(S // 2, S + 1, (B,), generator=g)
+    pad = (torch.arange(S)[None, :] < lens[:, None]).float() if padded else None
+    z1, _ = ops.actnorm(dev(z), dev(bias), dev(scales), None, pad=dev(pad))
+    z1, _ = ops.invconv_apply(z1, dev(w), dev(sldj), None, pad=dev(pad))
+    z2, _, zm = ops.invconv_apply(dev(z), dev(w), dev(sldj), None, pad=dev(pad), pre_actnorm=(dev(bias), dev(scales)),
+                                  out_mask=dev(omask))
+    assert_close(z2, z1, rtol=1e-5, atol=2e-6, what="actnorm + conv in one pass")
+    assert torch.equal(zm, z2 * dev(omask))
+    zo, _ = O.actnorm(z, bias.view(1, 1, -1), scales.view(1, 1, -1), pad=pad.unsqueeze(-1) if padded else None)
+    zo, _ = O.invconv(zo, w, sldj, pad=pad.unsqueeze(-1) if padded else None)
+    assert_close(z2, zo, what="against the oracle")

@@ -160,3 +160,27 @@ def test_fused_full_size_properties():
     z2, l2, _ = ops.linear_mixcdf(z[100:200], feats[100:200], w, b, K, mask_c=mc)
     assert torch.equal(z2, zf[100:200])
     assert_close(l2, lf[100:200], rtol=1e-5, atol=1e-4, what="ldj of a batch slice")
+
+
+@pytest.mark.parametrize("B,S,C,K,H,padded", [(4, 64, 16, 8, 16, False), (3, 50, 8, 8, 32, True), (5, 33, 16, 4, 64, True),
+                                              (2, 300, 8, 16, 16, False)])
+def test_fused_next_block_epilogue_and_masked_output(B, S, C, K, H, padded):
+    """mix.next_* epilogue of the fused projection kernel (+ the next coupling's masked input) against the same
+    layers run one kernel at a time."""
+    from categoricalnf_b200 import ops
+    z, feats, w, b, sf, msf, mask, pad = _fused_case(B, S, C, K, H, seed=7 * B + S + C + K + H, padded=padded)
+    g = torch.Generator().manual_seed(99)
+    nb, ns = torch.randn(C, generator=g) * 0.2, torch.randn(C, generator=g) * 0.2
+    nw = torch.linalg.qr(torch.randn(C, C, generator=g))[0].contiguous()
+    nmask = torch.cat([torch.zeros(C // 2), torch.ones(C - C // 2)])
+    kw = dict(mask_c=mask.flatten().tolist(), pad=dev(pad), scaling_factor=dev(sf), mixture_scaling_factor=dev(msf))
+    z1, l1, _ = ops.linear_mixcdf(dev(z), dev(feats), dev(w), dev(b), K, **kw)
+    z1, _ = ops.actnorm(z1, dev(nb), dev(ns), None, pad=dev(pad))
+    sldj = torch.zeros(1, device="cuda")
+    z1, _ = ops.invconv_apply(z1, dev(nw), sldj, None, pad=dev(pad))
+    z2, l2, _, zm = ops.linear_mixcdf(dev(z), dev(feats), dev(w), dev(b), K, fuse_next=(dev(nb), dev(ns), dev(nw)),
+                                      next_mask=dev(nmask), **kw)
+    ops.check_status(z2.device)
+    assert_close(z2, z1, rtol=1e-5, atol=2e-6, what="z after the fused next block")
+    assert_close(l2, l1, rtol=1e-6, atol=1e-5, what="ldj")
+    assert torch.equal(zm, z2 * dev(nmask))
