@@ -157,7 +157,8 @@ def workload_config(n_gpus, extra=None):
            "mixtures": W.LM["K"], "vocab": W.LM["V"], "blocks": W.LM["blocks"], "parallelism": "batch-sharded x%d" % n_gpus,
            "l2": "inputs larger than L2 (1.74 GB of coupling parameters per layer vs 126 MB L2); no flush needed",
            "value_leg": "coupling-net outputs given, resident in HBM", "e2e_leg": "drop-in FlowModel, stand-in Linear "
-           "coupling nets, pinned host tokens -> H2D, per-sample log-likelihood -> D2H"}
+           "coupling nets (final projection fused with the mixture transform on tcgen05, 3xTF32), pinned host tokens -> H2D, "
+           "per-sample log-likelihood -> D2H"}
     if extra:
         cfg.update(extra)
     return cfg
@@ -275,7 +276,7 @@ def run_gpu(args, rank, local_rank, world):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * S * 8, "d2h_bytes_per_step": B * 4,
                     "ms_per_step": e2e_ms_total / args.steps},
             "gpu_launches": launches,
-            "roofline": {"kernel": "mixcdf_kernel<8,false> (cnf_mixcdf_fwd)", "bound": "hbm", "achieved": achieved,
+            "roofline": {"kernel": "mixcdf_pipe_kernel<8,8,fwd> (cnf_mixcdf_fwd)", "bound": "hbm", "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(),
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                          "mean_launch_ms": mix_ms_mean, "launches_timed": len(mix_ms),
