@@ -128,6 +128,14 @@ class LinearArgs(C.Structure):
     ]
 
 
+class LinearBwdArgs(C.Structure):
+    _fields_ = [
+        ("M", C.c_int64), ("N", C.c_int32), ("K", C.c_int32),
+        ("x", vp), ("weight", vp), ("grad_y", vp), ("precision", C.c_int32),
+        ("grad_x", vp), ("grad_weight", vp), ("grad_bias", vp),
+    ]
+
+
 class LinearMixcdfArgs(C.Structure):
     _fields_ = [
         ("mix", MixcdfArgs), ("H", C.c_int32), ("precision", C.c_int32),
@@ -203,6 +211,7 @@ ENTRY_POINTS = {
     "cnf_logistic_sample": LogisticSampleArgs,
     "cnf_ldj_axpy": LdjAxpyArgs,
     "cnf_linear_fwd": LinearArgs,
+    "cnf_linear_bwd": LinearBwdArgs,
     "cnf_linear_mixcdf_fwd": LinearMixcdfArgs,
     "cnf_linear_mixcdf_inv": LinearMixcdfArgs,
     "cnf_mixcdf_bwd": MixcdfBwdArgs,

@@ -27,7 +27,8 @@
 
 namespace cnf {
 
-int tc_encode_2d(CUtensorMap* map, const void* base, long long inner, long long outer, int box_inner, int box_outer);
+int tc_encode_2d(CUtensorMap* map, const void* base, long long inner, long long outer, int box_inner, int box_outer,
+                 int atom32);
 
 namespace {
 using namespace tc;
@@ -563,9 +564,9 @@ int run_fused(const cnf_linear_mixcdf_args* a, cnf_stream_t stream_, int reverse
     CNF_REQUIRE(a->z_masked_out == nullptr || (reinterpret_cast<uintptr_t>(a->z_masked_out) & 15) == 0, "z_masked_out must be 16-byte aligned");
 
     CUtensorMap tm_h, tm_w;
-    int rc = tc_encode_2d(&tm_h, a->features, a->H, P, kBK, kBM);
+    int rc = tc_encode_2d(&tm_h, a->features, a->H, P, kBK, kBM, 0);
     if (rc != CNF_OK) return rc;
-    rc = tc_encode_2d(&tm_w, a->weight, a->H, (long long)m.C * PN, kBK, PNP);
+    rc = tc_encode_2d(&tm_w, a->weight, a->H, (long long)m.C * PN, kBK, PNP, 0);
     if (rc != CNF_OK) return rc;
     const int K = m.K, Ct = mv.n_t;
 #define CNF_FUSED_CASE(KK, CC) \

@@ -38,10 +38,26 @@ struct LinearParams {
     long long M;
     int N, K;
     int block_n, n_tiles, k_blocks, stages;
-    long long tiles;
+    long long m_tiles, tiles;   // tiles = splits * m_tiles * n_tiles
+    int kb_per_split;           // split-K: tile t reduces k-blocks [split * kb_per_split, +kb_per_split) (grad_weight)
+    int a_mn, b_mn;             // operand layout in memory: 0 = reduction dim contiguous (K-major), 1 = MN-major
     int act;        // 0 none, 1 GELU (erf)
-    int store_tma;  // 1: epilogue through shared memory + TMA store; 0: guarded direct stores
+    int store;      // 0: guarded direct stores; 1: shared memory + TMA store; 2: red.global.add (split-K partial sums)
 };
+
+struct TileCoord {
+    long long m0;
+    int n0, kb0, kb1;
+};
+__device__ __forceinline__ TileCoord tile_coord(const LinearParams& p, long long t) {
+    TileCoord c;
+    c.n0 = (int)(t % p.n_tiles) * p.block_n;
+    t /= p.n_tiles;
+    c.m0 = (t % p.m_tiles) * 128;
+    c.kb0 = (int)(t / p.m_tiles) * p.kb_per_split;
+    c.kb1 = c.kb0 + p.kb_per_split < p.k_blocks ? c.kb0 + p.kb_per_split : p.k_blocks;
+    return c;
+}
 
 __device__ __forceinline__ float rna_tf32(float v) {
     uint32_t r;
@@ -99,13 +115,23 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
             int stage = 0;
             uint32_t phase = 0;
             for (long long t = blockIdx.x; t < p.tiles; t += gridDim.x) {
-                const int m0 = (int)(t / p.n_tiles) * kBM, n0 = (int)(t % p.n_tiles) * p.block_n;
-                for (int kb = 0; kb < p.k_blocks; ++kb) {
+                const TileCoord tc = tile_coord(p, t);
+                const int m0 = (int)tc.m0, n0 = tc.n0;
+                for (int kb = tc.kb0; kb < tc.kb1; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1u);
                     unsigned char* sa = smem + stage * stage_bytes;
                     mbar_arrive_expect_tx(&full[stage], (uint32_t)half_bytes);
-                    tma_load_2d(sa, &tm_x, &full[stage], kb * kBK, m0);
-                    tma_load_2d(sa + kABytes, &tm_w, &full[stage], kb * kBK, n0);
+                    if (p.a_mn) {   // [32 reduction rows x 32 MN] slabs, one per 128-byte swizzle atom along MN
+                        for (int j = 0; j < kBM / 32; ++j) tma_load_2d(sa + j * 4096, &tm_x, &full[stage], m0 + 32 * j, kb * kBK);
+                    } else {
+                        tma_load_2d(sa, &tm_x, &full[stage], kb * kBK, m0);
+                    }
+                    if (p.b_mn) {
+                        for (int j = 0; j < p.block_n / 32; ++j)
+                            tma_load_2d(sa + kABytes + j * 4096, &tm_w, &full[stage], n0 + 32 * j, kb * kBK);
+                    } else {
+                        tma_load_2d(sa + kABytes, &tm_w, &full[stage], kb * kBK, n0);
+                    }
                     if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -113,26 +139,33 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     } else if (warp == 1) {
         // ---------------- MMA issuer ----------------------------------------------------------------
         if (lane == 0) {
-            const uint32_t idesc = idesc_tf32(kBM, (uint32_t)p.block_n);
+            const uint32_t idesc = idesc_tf32(kBM, (uint32_t)p.block_n, p.a_mn != 0, p.b_mn != 0);
+            // one instruction covers 8 reduction elements: 32 bytes along a K-major row, or 8 rows (1024 bytes = two
+            // 4-row swizzle atoms) of an MN-major slab
+            const uint32_t step_a = p.a_mn ? 1024u : 32u, step_b = p.b_mn ? 1024u : 32u;
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0;
             for (long long t = blockIdx.x; t < p.tiles; t += gridDim.x) {
+                const TileCoord tc = tile_coord(p, t);
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
                 tcgen05_fence_after();
                 const uint32_t d = tmem_base + (uint32_t)(acc * kStageCols);
-                for (int kb = 0; kb < p.k_blocks; ++kb) {
+                for (int kb = tc.kb0; kb < tc.kb1; ++kb) {
                     mbar_wait(STRICT ? &ready[stage] : &full[stage], phase);
                     tcgen05_fence_after();
                     unsigned char* sa = smem + stage * stage_bytes;
-                    const uint64_t da = smem_desc_k128(sa), db = smem_desc_k128(sa + kABytes);
+                    const uint64_t da = p.a_mn ? smem_desc_mn128(sa, 4096u) : smem_desc_k128(sa);
+                    const uint64_t db = p.b_mn ? smem_desc_mn128(sa + kABytes, 4096u) : smem_desc_k128(sa + kABytes);
 #pragma unroll
                     for (int k = 0; k < kBK / 8; ++k) {
-                        const uint32_t off = (uint32_t)k * 32u;   // 8 fp32 along K inside the swizzle atom
-                        mma_tf32(d, smem_desc_advance(da, off), smem_desc_advance(db, off), idesc, kb > 0 || k > 0);
+                        const uint32_t oa = (uint32_t)k * step_a, ob = (uint32_t)k * step_b;
+                        mma_tf32(d, smem_desc_advance(da, oa), smem_desc_advance(db, ob), idesc, kb > tc.kb0 || k > 0);
                         if constexpr (STRICT) {
-                            const uint64_t dal = smem_desc_k128(sa + half_bytes), dbl = smem_desc_k128(sa + half_bytes + kABytes);
-                            mma_tf32(d, smem_desc_advance(dal, off), smem_desc_advance(db, off), idesc, true);
-                            mma_tf32(d, smem_desc_advance(da, off), smem_desc_advance(dbl, off), idesc, true);
+                            const uint64_t dal = p.a_mn ? smem_desc_mn128(sa + half_bytes, 4096u) : smem_desc_k128(sa + half_bytes);
+                            const uint64_t dbl = p.b_mn ? smem_desc_mn128(sa + half_bytes + kABytes, 4096u)
+                                                        : smem_desc_k128(sa + half_bytes + kABytes);
+                            mma_tf32(d, smem_desc_advance(dal, oa), smem_desc_advance(db, ob), idesc, true);
+                            mma_tf32(d, smem_desc_advance(da, oa), smem_desc_advance(dbl, ob), idesc, true);
                         }
                     }
                     mma_commit(&empty[stage]);     // stage reusable once these MMAs have read it
@@ -150,8 +183,9 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         uint32_t acc_phase = 0;
         unsigned chunk_no = 0;
         for (long long t = blockIdx.x; t < p.tiles; t += gridDim.x) {
-            const long long m0 = (t / p.n_tiles) * kBM;
-            const int n0 = (int)(t % p.n_tiles) * p.block_n;
+            const TileCoord tc = tile_coord(p, t);
+            const long long m0 = tc.m0;
+            const int n0 = tc.n0;
             mbar_wait(&tmem_full[acc], acc_phase);
             tcgen05_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(e * 32) << 16) + (uint32_t)(acc * kStageCols);
@@ -177,7 +211,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
                 }
-                if (p.store_tma) {
+                if (p.store == 1) {
                     unsigned char* buf = staging + (e * 2 + (int)(chunk_no & 1u)) * 4096;
                     if (lane == 0) tma_store_wait_read<1>();   // the store issued two chunks ago has read this buffer
                     __syncwarp();
@@ -193,6 +227,13 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
                         tma_store_commit();
                     }
                     ++chunk_no;
+                } else if (p.store == 2) {
+                    if (row < p.M) {
+                        float* dst = p.y + row * (long long)p.N + col0;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (col0 + i < p.N) atomicAdd(dst + i, v[i]);
+                    }
                 } else if (row < p.M) {
                     float* dst = p.y + row * (long long)p.N + col0;
                     if ((p.N & 3) == 0 && col0 + 32 <= p.N) {
@@ -212,7 +253,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1u;
         }
-        if (p.store_tma && lane == 0) tma_store_wait<0>();
+        if (p.store == 1 && lane == 0) tma_store_wait<0>();
     } else if (STRICT && warp >= 8) {
         // ---------------- 3xTF32 split: hi = tf32(x) (in place), lo = tf32(x - hi), both round-to-nearest
         // so that whatever the tensor core does with the low 13 mantissa bits, they are zero -------------
@@ -221,7 +262,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         int stage = 0;
         uint32_t phase = 0;
         for (long long t = blockIdx.x; t < p.tiles; t += gridDim.x) {
-            for (int kb = 0; kb < p.k_blocks; ++kb) {
+            const TileCoord tc = tile_coord(p, t);
+            for (int kb = tc.kb0; kb < tc.kb1; ++kb) {
                 mbar_wait(&full[stage], phase);
                 float4* hi = reinterpret_cast<float4*>(smem + stage * stage_bytes);
                 float4* lo = reinterpret_cast<float4*>(smem + stage * stage_bytes + half_bytes);
@@ -265,8 +307,10 @@ EncodeTiledFn encode_fn() {
 
 }  // namespace
 
-// fp32 row-major [outer, inner] matrix, box [box_outer, box_inner], 128-byte swizzle, zero fill out of bounds
-int tc_encode_2d(CUtensorMap* map, const void* base, long long inner, long long outer, int box_inner, int box_outer) {
+// fp32 row-major [outer, inner] matrix, box [box_outer, box_inner], 128-byte swizzle (16-byte chunks, or 32-byte
+// chunks with atom32 - the layout of MN-major fp32 tensor-core operands), zero fill out of bounds
+int tc_encode_2d(CUtensorMap* map, const void* base, long long inner, long long outer, int box_inner, int box_outer,
+                 int atom32) {
     EncodeTiledFn fn = encode_fn();
     if (fn == nullptr) return fail(CNF_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
     const cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
@@ -274,7 +318,8 @@ int tc_encode_2d(CUtensorMap* map, const void* base, long long inner, long long 
     const cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(CNF_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     return CNF_OK;
@@ -289,6 +334,101 @@ void tc_pick_block_n(int N, int* block_n, int* n_tiles) {
     *n_tiles = (N + bn - 1) / bn;
 }
 
+// ---- generic launcher: D[Mg,Ng] (+)= sum_r A(m,r) B(n,r) ------------------------------------------------------
+//   operand in memory   K-major:  [rows, R] row-major (reduction contiguous)      -> nn.Linear forward operands
+//                       MN-major: [R, rows] row-major (the M / N index contiguous) -> backward operands, no transposes
+struct GemmDesc {
+    const float* a; int a_mn;
+    const float* b; int b_mn;
+    long long Mg; int Ng; long long R;
+    const float* bias; int act; int precision;
+    float* y;
+    int split_k;      // 1: split the reduction over the grid and red.add the partial tiles into y (y pre-initialised)
+};
+
+int launch_gemm(const GemmDesc& g, const char* who, cudaStream_t stream) {
+    CNF_SUPPORTED(g.Mg < (1ll << 31) - 256 && g.R < (1ll << 31) - 256, "%s: dimension too large for 32-bit TMA coordinates", who);
+    CNF_SUPPORTED((g.a_mn ? g.Mg : g.R) % 4 == 0 && (g.b_mn ? (long long)g.Ng : g.R) % 4 == 0,
+                  "%s: operand rows must be a multiple of 4 floats (16-byte pitch for TMA)", who);
+    LinearParams p{};
+    p.bias = g.bias; p.y = g.y; p.M = g.Mg; p.N = g.Ng; p.K = (int)g.R; p.act = g.act;
+    p.a_mn = g.a_mn; p.b_mn = g.b_mn;
+    tc_pick_block_n(g.Ng, &p.block_n, &p.n_tiles);
+    p.k_blocks = (int)((g.R + kBK - 1) / kBK);
+    p.m_tiles = (g.Mg + kBM - 1) / kBM;
+    const long long base_tiles = p.m_tiles * p.n_tiles;
+    const long long sms = sm_count();
+    long long splits = 1;
+    if (g.split_k) {
+        splits = (sms + base_tiles - 1) / base_tiles;
+        if (splits > p.k_blocks) splits = p.k_blocks;
+        if (splits < 1) splits = 1;
+    }
+    p.kb_per_split = (int)((p.k_blocks + splits - 1) / splits);
+    splits = (p.k_blocks + p.kb_per_split - 1) / p.kb_per_split;
+    p.tiles = base_tiles * splits;
+    p.store = g.split_k ? 2 : ((g.Ng % 4 == 0) ? 1 : 0);
+    const bool strict = g.precision == 1;
+    const int stage_bytes = (kABytes + p.block_n * 128) * (strict ? 2 : 1);
+    const int fixed = 1024 + kStagingBytes + 512;
+    int stages = (232448 - fixed) / stage_bytes;
+    if (stages > 6) stages = 6;
+    CNF_SUPPORTED(stages >= 2, "%s: tile does not fit shared memory", who);
+    p.stages = stages;
+    const size_t smem = (size_t)fixed + (size_t)stages * stage_bytes;
+
+    CUtensorMap tm_a, tm_b, tm_y;
+    int rc = g.a_mn ? tc_encode_2d(&tm_a, g.a, g.Mg, g.R, 32, kBK, 1) : tc_encode_2d(&tm_a, g.a, g.R, g.Mg, kBK, kBM, 0);
+    if (rc != CNF_OK) return rc;
+    rc = g.b_mn ? tc_encode_2d(&tm_b, g.b, g.Ng, g.R, 32, kBK, 1) : tc_encode_2d(&tm_b, g.b, g.R, g.Ng, kBK, p.block_n, 0);
+    if (rc != CNF_OK) return rc;
+    if (p.store == 1) {
+        rc = tc_encode_2d(&tm_y, g.y, g.Ng, g.Mg, 32, 32, 0);
+        if (rc != CNF_OK) return rc;
+    } else {
+        tm_y = tm_a;
+    }
+    long long grid = sms;
+    if (grid > p.tiles) grid = p.tiles;
+    if (strict) {
+        CNF_CUDA(cudaFuncSetAttribute(linear_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+        linear_tc_kernel<true><<<(unsigned)grid, 384, smem, stream>>>(tm_a, tm_b, tm_y, p);
+    } else {
+        CNF_CUDA(cudaFuncSetAttribute(linear_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+        linear_tc_kernel<false><<<(unsigned)grid, 256, smem, stream>>>(tm_a, tm_b, tm_y, p);
+    }
+    return launch_status("linear_tc_kernel");
+}
+
+// grad_bias[n] += sum_m grad_y[m,n]: CTA = 32 columns x a slice of rows, 8 row lanes per column
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ gy, float* __restrict__ gb, long long M, int N,
+                                                     long long rows_per_cta) {
+    __shared__ float part[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int col = blockIdx.x * 32 + tx;
+    const long long r0 = (long long)blockIdx.y * rows_per_cta;
+    const long long r1 = r0 + rows_per_cta < M ? r0 + rows_per_cta : M;
+    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+    if (col < N) {
+        long long r = r0 + ty;
+        for (; r + 24 < r1; r += 32) {
+            acc0 += __ldg(gy + r * N + col);
+            acc1 += __ldg(gy + (r + 8) * N + col);
+            acc2 += __ldg(gy + (r + 16) * N + col);
+            acc3 += __ldg(gy + (r + 24) * N + col);
+        }
+        for (; r < r1; r += 8) acc0 += __ldg(gy + r * N + col);
+    }
+    part[ty][tx] = (acc0 + acc1) + (acc2 + acc3);
+    __syncthreads();
+    if (ty == 0 && col < N) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += part[i][tx];
+        atomicAdd(gb + col, s);
+    }
+}
+
 }  // namespace cnf
 
 extern "C" int cnf_linear_fwd(const cnf_linear_args* a, cnf_stream_t stream_) {
@@ -301,44 +441,62 @@ extern "C" int cnf_linear_fwd(const cnf_linear_args* a, cnf_stream_t stream_) {
     CNF_REQUIRE(a->precision == 0 || a->precision == 1, "cnf_linear_fwd: precision must be 0 (TF32) or 1 (3xTF32)");
     CNF_REQUIRE(a->activation == 0 || a->activation == 1, "cnf_linear_fwd: activation must be 0 (none) or 1 (GELU)");
     CNF_SUPPORTED(a->K % 4 == 0, "cnf_linear_fwd: in_features K=%d must be a multiple of 4 (16-byte rows for TMA)", a->K);
-    CNF_SUPPORTED(a->M < (1ll << 31) - 256, "cnf_linear_fwd: M=%lld too large for 32-bit TMA coordinates", (long long)a->M);
     CNF_REQUIRE(((reinterpret_cast<uintptr_t>(a->x) | reinterpret_cast<uintptr_t>(a->weight) | reinterpret_cast<uintptr_t>(a->y)) & 15) == 0,
                 "cnf_linear_fwd: x, weight and y must be 16-byte aligned");
+    GemmDesc g{};
+    g.a = a->x; g.a_mn = 0; g.b = a->weight; g.b_mn = 0;
+    g.Mg = a->M; g.Ng = a->N; g.R = a->K;
+    g.bias = a->bias; g.act = a->activation; g.precision = a->precision; g.y = a->y; g.split_k = 0;
+    return launch_gemm(g, "cnf_linear_fwd", stream);
+}
 
-    LinearParams p{};
-    p.bias = a->bias; p.y = a->y; p.M = a->M; p.N = a->N; p.K = a->K; p.act = a->activation;
-    tc_pick_block_n(a->N, &p.block_n, &p.n_tiles);
-    p.k_blocks = (a->K + kBK - 1) / kBK;
-    p.tiles = ((a->M + kBM - 1) / kBM) * p.n_tiles;
-    p.store_tma = (a->N % 4 == 0) ? 1 : 0;
-    const bool strict = a->precision == 1;
-    const int stage_bytes = (kABytes + p.block_n * 128) * (strict ? 2 : 1);
-    const int fixed = 1024 + kStagingBytes + 512;
-    int stages = (232448 - fixed) / stage_bytes;
-    if (stages > 6) stages = 6;
-    CNF_SUPPORTED(stages >= 2, "cnf_linear_fwd: tile does not fit shared memory");
-    p.stages = stages;
-    const size_t smem = (size_t)fixed + (size_t)stages * stage_bytes;
-
-    CUtensorMap tm_x, tm_w, tm_y;
-    int rc = tc_encode_2d(&tm_x, a->x, a->K, a->M, kBK, kBM);
-    if (rc != CNF_OK) return rc;
-    rc = tc_encode_2d(&tm_w, a->weight, a->K, a->N, kBK, p.block_n);
-    if (rc != CNF_OK) return rc;
-    if (p.store_tma) {
-        rc = tc_encode_2d(&tm_y, a->y, a->N, a->M, 32, 32);
+// Backward of y = x W^T + b.  All three products read the tensors where they lie (no transposed copies):
+//   grad_x [M,K] = grad_y [M,N] . W [N,K]        A = grad_y K-major,  B = W MN-major
+//   grad_W [N,K] += grad_y^T . x                   A = grad_y MN-major, B = x MN-major, reduction over M split across the
+//                                                  grid, partial tiles added with red.global.add.f32
+//   grad_b [N]   += column sums of grad_y
+extern "C" int cnf_linear_bwd(const cnf_linear_bwd_args* a, cnf_stream_t stream_) {
+    using namespace cnf;
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    CNF_REQUIRE(a != nullptr, "cnf_linear_bwd: null args");
+    CNF_REQUIRE(a->M >= 0 && a->N >= 1 && a->K >= 1, "cnf_linear_bwd: bad shape M=%lld N=%d K=%d", (long long)a->M, a->N, a->K);
+    if (a->M == 0) return CNF_OK;
+    CNF_REQUIRE(a->grad_y != nullptr, "cnf_linear_bwd: null grad_y");
+    CNF_REQUIRE(a->precision == 0 || a->precision == 1, "cnf_linear_bwd: precision must be 0 (TF32) or 1 (3xTF32)");
+    CNF_SUPPORTED(a->K % 4 == 0 && a->N % 4 == 0, "cnf_linear_bwd: N=%d and K=%d must be multiples of 4 (16-byte rows for TMA)",
+                  a->N, a->K);
+    uintptr_t bits = reinterpret_cast<uintptr_t>(a->grad_y);
+    if (a->grad_x) bits |= reinterpret_cast<uintptr_t>(a->grad_x) | reinterpret_cast<uintptr_t>(a->weight);
+    if (a->grad_weight) bits |= reinterpret_cast<uintptr_t>(a->grad_weight) | reinterpret_cast<uintptr_t>(a->x);
+    CNF_REQUIRE((bits & 15) == 0, "cnf_linear_bwd: tensors must be 16-byte aligned");
+    if (a->grad_x != nullptr) {
+        CNF_REQUIRE(a->weight != nullptr, "cnf_linear_bwd: grad_x needs weight");
+        GemmDesc g{};
+        g.a = a->grad_y; g.a_mn = 0; g.b = a->weight; g.b_mn = 1;
+        g.Mg = a->M; g.Ng = a->K; g.R = a->N;
+        g.precision = a->precision; g.y = a->grad_x;
+        const int rc = launch_gemm(g, "cnf_linear_bwd (grad_x)", stream);
         if (rc != CNF_OK) return rc;
-    } else {
-        tm_y = tm_x;
     }
-    long long grid = sm_count();
-    if (grid > p.tiles) grid = p.tiles;
-    if (strict) {
-        CNF_CUDA(cudaFuncSetAttribute(linear_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-        linear_tc_kernel<true><<<(unsigned)grid, 384, smem, stream>>>(tm_x, tm_w, tm_y, p);
-    } else {
-        CNF_CUDA(cudaFuncSetAttribute(linear_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-        linear_tc_kernel<false><<<(unsigned)grid, 256, smem, stream>>>(tm_x, tm_w, tm_y, p);
+    if (a->grad_weight != nullptr) {
+        CNF_REQUIRE(a->x != nullptr, "cnf_linear_bwd: grad_weight needs x");
+        GemmDesc g{};
+        g.a = a->grad_y; g.a_mn = 1; g.b = a->x; g.b_mn = 1;
+        g.Mg = a->N; g.Ng = a->K; g.R = a->M;
+        g.precision = a->precision; g.y = a->grad_weight; g.split_k = 1;
+        const int rc = launch_gemm(g, "cnf_linear_bwd (grad_weight)", stream);
+        if (rc != CNF_OK) return rc;
     }
-    return launch_status("linear_tc_kernel");
+    if (a->grad_bias != nullptr) {
+        const int col_blocks = (a->N + 31) / 32;
+        long long row_blocks = (4ll * sm_count() + col_blocks - 1) / col_blocks;
+        if (row_blocks > (a->M + 255) / 256) row_blocks = (a->M + 255) / 256;
+        if (row_blocks < 1) row_blocks = 1;
+        if (row_blocks > 65535) row_blocks = 65535;
+        const long long rows_per_cta = (a->M + row_blocks - 1) / row_blocks;
+        colsum_kernel<<<dim3((unsigned)col_blocks, (unsigned)row_blocks), 256, 0, stream>>>(a->grad_y, a->grad_bias, a->M, a->N,
+                                                                                             rows_per_cta);
+        return launch_status("colsum_kernel");
+    }
+    return CNF_OK;
 }

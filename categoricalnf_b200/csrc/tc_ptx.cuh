@@ -129,12 +129,22 @@ __device__ __forceinline__ uint64_t smem_desc_k128(const void* tile) {
     const uint64_t a = (uint64_t)((smem_addr(tile) >> 4) & 0x3FFFu);
     return a | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
+// MN-major fp32 operand (the M / N index is the contiguous one in memory).  For 32-bit elements the tensor core
+// accepts one swizzled MN-major layout only: 128-byte rows along MN with the 32-byte chunks XOR-ed by (row % 4)
+// (layout type SWIZZLE_128B_BASE32B = 1; TMA writes it with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B).  The tile is a row
+// of slabs, each [reduction rows x 128 bytes along MN] = one TMA box: leading byte offset = distance between slabs
+// (next 32 fp32 along MN), stride byte offset = 512 = next 4-row group along the reduction dimension.
+__device__ __forceinline__ uint64_t smem_desc_mn128(const void* tile, uint32_t slab_bytes) {
+    const uint64_t a = (uint64_t)((smem_addr(tile) >> 4) & 0x3FFFu);
+    return a | ((uint64_t)((slab_bytes >> 4) & 0x3FFFu) << 16) | ((uint64_t)(512u >> 4) << 32) | (1ull << 46) | (1ull << 61);
+}
 // advance along K inside the swizzle atom by `bytes` (multiple of 16)
 __device__ __forceinline__ uint64_t smem_desc_advance(uint64_t desc, uint32_t bytes) { return desc + (uint64_t)(bytes >> 4); }
 
 // Instruction descriptor, kind::tf32: fp32 accumulate, TF32 x TF32, both operands K-major, M x N tile.
-__host__ __device__ constexpr uint32_t idesc_tf32(uint32_t M, uint32_t N) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+__host__ __device__ constexpr uint32_t idesc_tf32(uint32_t M, uint32_t N, bool a_mn_major = false, bool b_mn_major = false) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) |
+           ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 // Instruction descriptor, kind::f16 with BF16 operands.
 __host__ __device__ constexpr uint32_t idesc_bf16(uint32_t M, uint32_t N) {

@@ -28,6 +28,8 @@ REPLACED = {
     "layers.categorical_encoding.linear_encoding": "categorical_encoding.linear_encoding",
     "layers.categorical_encoding.variational_encoding": "categorical_encoding.variational_encoding",
     "layers.categorical_encoding.mutils": "categorical_encoding.mutils",
+    # GraphCNF's joint node+edge coupling lives under experiments/ upstream but is hot-path row a14
+    "experiments.molecule_generation.graph_node_edge_coupling": "flows.node_edge_coupling",
 }
 
 

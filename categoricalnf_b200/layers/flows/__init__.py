@@ -5,8 +5,9 @@ from .mixture_cdf_layer import MixtureCDFCoupling
 from .autoregressive_coupling import AutoregressiveMixtureCDFCoupling
 from .activation_normalization import ActNormFlow, ExtActNormFlow
 from .permutation_layers import InvertibleConv
+from .node_edge_coupling import NodeEdgeCoupling, NodeEdgeFlowWrapper
 from .distributions import LogisticDistribution, PriorDistribution, create_prior_distribution
 
 __all__ = ["FlowLayer", "FlowModel", "CouplingLayer", "MixtureCDFCoupling", "AutoregressiveMixtureCDFCoupling",
-           "ActNormFlow", "ExtActNormFlow", "InvertibleConv", "LogisticDistribution", "PriorDistribution",
+           "ActNormFlow", "ExtActNormFlow", "InvertibleConv", "NodeEdgeCoupling", "NodeEdgeFlowWrapper", "LogisticDistribution", "PriorDistribution",
            "create_prior_distribution"]

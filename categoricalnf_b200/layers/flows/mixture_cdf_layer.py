@@ -220,7 +220,10 @@ class MixtureCDFCoupling(CouplingLayer):
         # upstream multiplies by the padding mask only in the callers (:76); the kernel has already
         # done so, which is idempotent for 0/1 masks.
         if return_reg_ldj:
-            return z_out, ldj, (reg if not reverse else None)
+            # upstream returns the regulariser per element [B,S,C] and its callers reduce over dims 1.. (e.g.
+            # graph_node_edge_coupling.py:138-139); the kernel has reduced already, so hand back [B,1,1] - the same
+            # reduction is then a no-op (a bare [B] would make `sum(dim=[])` collapse the batch as well).
+            return z_out, ldj, (reg.reshape((-1,) + (1,) * (z.dim() - 1)) if not reverse else None)
         return z_out, ldj
 
     def info(self):

@@ -21,8 +21,8 @@ from ... import ops
 
 
 class _TCLinearFn(torch.autograd.Function):
-    """y = x W^T + b with all three GEMMs (forward, grad_x, grad_W) on cnf_linear_fwd.  The two backward
-    products need transposed operands; the transposes are plain copies."""
+    """y = x W^T + b with all three GEMMs (forward, grad_x, grad_W) on the tcgen05 kernel.  The two backward
+    products read their operands in place through MN-major shared-memory descriptors (``cnf_linear_bwd``)."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, precision):
@@ -34,15 +34,8 @@ class _TCLinearFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gy):
         x, weight = ctx.saved_tensors
-        gy2 = gy.reshape(-1, gy.shape[-1]).contiguous()
-        x2 = x.reshape(-1, x.shape[-1])
-        gx = gw = gb = None
-        if ctx.needs_input_grad[0]:
-            gx = ops.linear(gy2, weight.t().contiguous(), None, precision=ctx.precision).reshape(x.shape)
-        if ctx.needs_input_grad[1]:
-            gw = ops.linear(gy2.t().contiguous(), x2.t().contiguous(), None, precision=ctx.precision)
-        if ctx.has_bias and ctx.needs_input_grad[2]:
-            gb = gy2.sum(dim=0)
+        gx, gw, gb = ops.linear_bwd(x, weight, gy, need_x=ctx.needs_input_grad[0], need_weight=ctx.needs_input_grad[1],
+                                    need_bias=ctx.has_bias and ctx.needs_input_grad[2], precision=ctx.precision)
         return gx, gw, gb, None
 
 

@@ -443,6 +443,55 @@ def linear(x, weight, bias=None, *, precision="3xtf32", activation=None):
     return y.reshape(lead + (N,))
 
 
+def linear_bwd(x, weight, grad_y, *, need_x=True, need_weight=True, need_bias=False, precision="3xtf32",
+               grad_weight=None, grad_bias=None):
+    """Backward of :func:`linear` (``cnf_linear_bwd``): ``(grad_x | None, grad_weight | None, grad_bias | None)``.
+
+    The three products read ``x`` / ``weight`` / ``grad_y`` in place (MN-major tensor-core operands, no transposed
+    copies).  ``grad_weight`` / ``grad_bias`` given -> accumulated into (gradient accumulation); otherwise fresh
+    zero-initialised tensors.  N or K not a multiple of 4 is zero-padded (copies)."""
+    x = _f32(x, "x")
+    weight = _f32(weight, "weight")
+    grad_y = _f32(grad_y, "grad_y")
+    N, K = weight.shape
+    x2 = x.reshape(-1, K)
+    gy2 = grad_y.reshape(-1, N)
+    M = x2.shape[0]
+    if gy2.shape[0] != M:
+        raise ValueError("grad_y has %d rows, x has %d" % (gy2.shape[0], M))
+    padn, padk = (-N) % 4, (-K) % 4
+    if padn or padk:       # rare (graph nets use multiples of 4): pad, run, slice
+        F = torch.nn.functional
+        gx, gw, gb = linear_bwd(F.pad(x2, (0, padk)), F.pad(weight, (0, padk, 0, padn)), F.pad(gy2, (0, padn)),
+                                need_x=need_x, need_weight=need_weight, need_bias=need_bias, precision=precision)
+        gx = gx[:, :K].reshape(x.shape) if gx is not None else None
+        gw = gw[:N, :K] if gw is not None else None
+        gb = gb[:N] if gb is not None else None
+        if gw is not None and grad_weight is not None:
+            gw = grad_weight.add_(gw)
+        if gb is not None and grad_bias is not None:
+            gb = grad_bias.add_(gb)
+        return gx, gw, gb
+    if x2.data_ptr() % 16 != 0:
+        x2 = x2.clone()
+    if gy2.data_ptr() % 16 != 0:
+        gy2 = gy2.clone()
+    gx = torch.empty(M, K, dtype=torch.float32, device=x.device) if need_x else None
+    gw = gb = None
+    if need_weight:
+        gw = _f32(grad_weight, "grad_weight", (N, K)) if grad_weight is not None else \
+            torch.zeros(N, K, dtype=torch.float32, device=x.device)
+    if need_bias:
+        gb = _f32(grad_bias, "grad_bias", (N,)) if grad_bias is not None else torch.zeros(N, dtype=torch.float32, device=x.device)
+    a = L.LinearBwdArgs()
+    a.M, a.N, a.K = M, N, K
+    a.x, a.weight, a.grad_y = _ptr(x2), _ptr(weight), _ptr(gy2)
+    a.precision = PRECISION[precision]
+    a.grad_x, a.grad_weight, a.grad_bias = _ptr(gx), _ptr(gw), _ptr(gb)
+    _call("cnf_linear_bwd", a, x2, (x2, weight, gy2, gx, gw, gb))
+    return (gx.reshape(x.shape) if gx is not None else None), gw, gb
+
+
 def _linear_mixcdf_args(z, features, weight, bias, num_mixtures, mask_c, mask_s, pad, scaling_factor,
                         mixture_scaling_factor, precision):
     z = _f32(z, "z")

@@ -354,6 +354,28 @@ typedef struct {
 
 CNF_API int cnf_linear_fwd(const cnf_linear_args* a, cnf_stream_t stream);
 
+/* Backward of the projection (what autograd derives for F.linear in the reference's training loops,
+ * general/train.py:148-152), same tcgen05 kernel with the operands read in place (MN-major shared-memory
+ * descriptors instead of transposed copies):
+ *   grad_x [M,K]  = grad_y W            (overwritten)
+ *   grad_weight [N,K] += grad_y^T x     (ACCUMULATED: the reduction over M is split across the grid and the partial
+ *                                        tiles are added with red.global.add - zero it, or keep it to accumulate)
+ *   grad_bias [N]     += column sums    (ACCUMULATED)
+ * NULL output = not computed.  Requirements: N % 4 == 0, K % 4 == 0, 16-byte aligned tensors. */
+typedef struct {
+    int64_t M;
+    int32_t N, K;
+    const float* x;        /* [M,K] (read for grad_weight)     */
+    const float* weight;   /* [N,K] (read for grad_x)          */
+    const float* grad_y;   /* [M,N]                            */
+    int32_t precision;     /* 0 = TF32, 1 = 3xTF32             */
+    float* grad_x;         /* [M,K] or NULL                    */
+    float* grad_weight;    /* [N,K] or NULL, accumulated into  */
+    float* grad_bias;      /* [N] or NULL, accumulated into    */
+} cnf_linear_bwd_args;
+
+CNF_API int cnf_linear_bwd(const cnf_linear_bwd_args* a, cnf_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * K8 + K1/K2 fused: FINAL projection of the coupling network + mixture-CDF coupling transform.
  *   nn_out = features @ weight^T + bias   (last nn.Linear of the network, e.g.

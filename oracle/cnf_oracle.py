@@ -196,6 +196,40 @@ def autoregressive_mixcdf(z, nn_out, num_mixtures, scaling_factor, mixture_scali
     return out, ldj + l.float()
 
 
+def node_edge_coupling(z_nodes, z_edges, nn_nodes, nn_edges, mask_nodes, mask_edges, k_nodes, k_edges,
+                       sf_nodes, sf_edges, msf_nodes, msf_edges, *, ldj=None, reverse=False, pad=None, mask_valid=None,
+                       reg_max=-1.0, reg_factor=1.0, training=True):
+    """a14: ``NodeEdgeCoupling.forward`` after the Edge-GNN call
+    (experiments/molecule_generation/graph_node_edge_coupling.py:63-110): network outputs and transformed latents
+    are zeroed at padded nodes / invalid pairs, both ldj are ADDED to the incoming one (:99).
+    ``pad`` is ``[B,N,1]``, ``mask_valid`` ``[B,pairs]``.  Returns (z_nodes, z_edges, ldj, reg_nodes [B], reg_edges [B])."""
+    if ldj is None:
+        ldj = z_nodes.new_zeros(z_nodes.size(0))
+    mv = mask_valid.unsqueeze(-1)
+    mn = mask_nodes[None, :min(mask_nodes.size(0), z_nodes.size(1)), :]                     # :52-53
+    me = mask_edges[None, :min(mask_edges.size(0), z_edges.size(1)), :]
+    res = []
+    for z, nn_out, m, k, sf, msf, pd in ((z_nodes, nn_nodes, mn, k_nodes, sf_nodes, msf_nodes, pad),
+                                         (z_edges, nn_edges, me, k_edges, sf_edges, msf_edges, mv)):
+        p = mixt_params(nn_out * pd, m, k, sf, msf)                                           # :64,:78,:113-118
+        out, l, reg = mixcdf_run(z, *p, reverse=reverse, mask=m, pad=pd, reg_max=reg_max, reg_factor=reg_factor,
+                                 training=training)                                           # :119-135
+        reg_b = reg.float().sum(dim=[1, 2]) if reg is not None else None                      # :138-139
+        res.append((out.float() * pd, l.float(), reg_b))                                      # :74,:88,:136-137
+    (zn, ln, rn), (ze, le, re) = res
+    return zn, ze, ldj + ln + le, rn, re
+
+
+def node_edge_wrapper(fn, z_nodes, z_edges, node_args, edge_args, *, ldj=None, reverse=False, length=None, pad=None,
+                      mask_valid=None):
+    """``NodeEdgeFlowWrapper.forward`` (graph_node_edge_coupling.py:158-165): ``fn`` = :func:`actnorm` or
+    :func:`invconv` applied to the nodes with (length, pad) and to the edges with
+    (edge_length = mask_valid.sum(1), mask_valid[..., None])."""
+    zn, ldj = fn(z_nodes, *node_args, ldj=ldj, reverse=reverse, length=length, pad=pad)
+    ze, ldj = fn(z_edges, *edge_args, ldj=ldj, reverse=reverse, length=mask_valid.sum(dim=1), pad=mask_valid.unsqueeze(-1))
+    return zn, ze, ldj
+
+
 # ---------------------------------------------------------------------------
 # a5: affine coupling   (layers/flows/coupling_layer.py:42-98)
 # ---------------------------------------------------------------------------

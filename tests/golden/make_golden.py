@@ -2,7 +2,7 @@
 
 Usage (authoring container only - the GPU box has no /root/reference):
 
-    python tests/golden/make_golden.py [/root/reference]
+    python tests/golden/make_golden.py [/root/reference] [--only=node_edge]
 
 For every hot-path function of SURVEY.md section 8a it instantiates the reference
 module from the reference checkout, feeds it seeded synthetic inputs on the CPU, and
@@ -19,7 +19,9 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-REF = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
+_ARGS = [a for a in sys.argv[1:] if not a.startswith("--only")]
+ONLY = [a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--only=")]      # --only=node_edge : just that group
+REF = _ARGS[0] if _ARGS else "/root/reference"
 OUT = os.path.dirname(os.path.abspath(__file__))
 
 
@@ -432,8 +434,74 @@ def gold_lm_flow(seed):
     save("lm_flow_small", **arrays)
 
 
+def gold_node_edge(seed):
+    """GraphCNF step-2/3 block at a small Zinc-like shape: NodeEdgeFlowWrapper(ActNorm), NodeEdgeFlowWrapper(InvConv),
+    NodeEdgeCoupling (experiments/molecule_generation/graph_node_edge_coupling.py) with a stand-in Edge-GNN that
+    returns preset outputs; forward (training mode, regulariser on) and reverse."""
+    from experiments.molecule_generation.graph_node_edge_coupling import NodeEdgeCoupling, NodeEdgeFlowWrapper
+    g = torch.Generator().manual_seed(seed)
+    np.random.seed(seed)
+    B, N, Cn, Ce, Kn, Ke = 4, 9, 6, 2, 16, 8
+    P = N * (N - 1) // 2
+    length = torch.tensor([9, 5, 7, 2])
+    pad = lengths_to_pad(length, N)                                        # [B,N,1]
+    idx = torch.tensor([(i, j) for i in range(N) for j in range(i + 1, N)])
+    mask_valid = ((idx[None, :, 0] < length[:, None]) & (idx[None, :, 1] < length[:, None])).float()   # [B,P]
+    z_nodes = torch.randn(B, N, Cn, generator=g) * pad
+    z_edges = torch.randn(B, P, Ce, generator=g) * mask_valid.unsqueeze(-1)
+    nn_nodes = torch.randn(B, N, Cn * (2 + 3 * Kn), generator=g) * 0.6
+    nn_edges = torch.randn(B, P, Ce * (2 + 3 * Ke), generator=g) * 0.6
+
+    class _Net(nn.Module):
+        def forward(self, z_nodes, z_edges, **kwargs):
+            return nn_nodes, nn_edges
+
+    cp = NodeEdgeCoupling(c_in_nodes=Cn, c_in_edges=Ce, mask_nodes=CouplingLayer.create_channel_mask(Cn),
+                          mask_edges=CouplingLayer.create_channel_mask(Ce), num_mixtures_nodes=Kn, num_mixtures_edges=Ke,
+                          model_func=lambda c_out_nodes, c_out_edges: _Net(), regularizer_max=3.5, regularizer_factor=2)
+    cp.scaling_factor_nodes.data = torch.randn(Cn, generator=g) * 0.2
+    cp.scaling_factor_edges.data = torch.randn(Ce, generator=g) * 0.2
+    cp.mixture_scaling_factor_nodes.data = torch.randn(Cn, Kn, generator=g) * 0.2
+    cp.mixture_scaling_factor_edges.data = torch.randn(Ce, Ke, generator=g) * 0.2
+    an = NodeEdgeFlowWrapper(node_flow=ActNormFlow(Cn), edge_flow=ActNormFlow(Ce))
+    ic = NodeEdgeFlowWrapper(node_flow=InvertibleConv(Cn), edge_flow=InvertibleConv(Ce))
+    for f, c in ((an.node_flow, Cn), (an.edge_flow, Ce)):
+        f.bias.data = torch.randn(1, 1, c, generator=g) * 0.2
+        f.scales.data = torch.randn(1, 1, c, generator=g) * 0.2
+    ldj0 = torch.randn(B, generator=g)
+    kw = dict(length=length, channel_padding_mask=pad, mask_valid=mask_valid)
+    out = {}
+    with torch.no_grad():
+        cp.train()
+        zn, ze, ldj, detail = cp(z_nodes, z_edges, ldj=ldj0.clone(), reverse=False, **kw)
+        out.update(cp_zn=zn, cp_ze=ze, cp_ldj=ldj, cp_reg_nodes=detail["regularizer_nodes_ldj"],
+                   cp_reg_edges=detail["regularizer_edges_ldj"])
+        cp.eval()
+        zn_e, ze_e, ldj_e, _ = cp(z_nodes, z_edges, ldj=ldj0.clone(), reverse=False, **kw)
+        zn_r, ze_r, ldj_r, _ = cp(zn_e, ze_e, ldj=ldj0.clone(), reverse=True, **kw)
+        out.update(cp_zn_eval=zn_e, cp_ze_eval=ze_e, cp_ldj_eval=ldj_e, cp_zn_rev=zn_r, cp_ze_rev=ze_r, cp_ldj_rev=ldj_r)
+        zn_a, ze_a, ldj_a = an(z_nodes, z_edges, ldj=ldj0.clone(), reverse=False, **kw)
+        zn_i, ze_i, ldj_i = ic(zn_a, ze_a, ldj=ldj_a.clone(), reverse=False, **kw)
+        zn_ir, ze_ir, ldj_ir = ic(zn_i, ze_i, ldj=ldj0.clone(), reverse=True, **kw)
+        out.update(an_zn=zn_a, an_ze=ze_a, an_ldj=ldj_a, ic_zn=zn_i, ic_ze=ze_i, ic_ldj=ldj_i,
+                   ic_zn_rev=zn_ir, ic_ze_rev=ze_ir, ic_ldj_rev=ldj_ir)
+    sd = {"ic_nodes_" + k: v for k, v in ic.node_flow.state_dict().items()}
+    sd.update({"ic_edges_" + k: v for k, v in ic.edge_flow.state_dict().items()})
+    save("node_edge_coupling", B=B, N=N, Cn=Cn, Ce=Ce, Kn=Kn, Ke=Ke, length=length, pad=pad, mask_valid=mask_valid,
+         z_nodes=z_nodes, z_edges=z_edges, nn_nodes=nn_nodes, nn_edges=nn_edges, ldj_in=ldj0,
+         mask_nodes=cp.mask_nodes, mask_edges=cp.mask_edges,
+         sf_nodes=cp.scaling_factor_nodes.data, sf_edges=cp.scaling_factor_edges.data,
+         msf_nodes=cp.mixture_scaling_factor_nodes.data, msf_edges=cp.mixture_scaling_factor_edges.data,
+         an_bias_nodes=an.node_flow.bias.data, an_scales_nodes=an.node_flow.scales.data,
+         an_bias_edges=an.edge_flow.bias.data, an_scales_edges=an.edge_flow.scales.data, **sd, **out)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(4)
+    if ONLY:
+        for _n in ONLY:
+            {"node_edge": lambda: gold_node_edge(seed=22)}[_n]()
+        sys.exit(0)
     gold_mixcdf_selftest()
     gold_mixcdf("mixcdf_lm_small", 3, 32, 16, 8, seed=1)
     gold_mixcdf("mixcdf_lm_padded_sf", 4, 40, 16, 8, seed=2, padded=True, sf_std=0.3)
@@ -458,3 +526,4 @@ if __name__ == "__main__":
     gold_encoding("encode_mol_edges", 3, 50, 3, 2, seed=19, padded=True, prior_std=0.5, training=True)
     gold_encoding("encode_virtual", 2, 12, 1, 2, seed=20)
     gold_lm_flow(seed=21)
+    gold_node_edge(seed=22)

@@ -1,4 +1,4 @@
-"""GPU parity of the tcgen05 kernels: the dense projection of the coupling networks (cnf_linear_fwd) and
+"""GPU parity of the tcgen05 kernels: the dense projection of the coupling networks (cnf_linear_fwd / _bwd) and
 the fused final projection + mixture coupling (cnf_linear_mixcdf_fwd / _inv).
 
 Tolerances: 3xTF32 projection |err| <= 3e-6 + 6e-8 K against a float64 product of O(1) outputs (the tensor
@@ -67,6 +67,63 @@ def test_tclinear_module_matches_nn_linear_state_dict():
     x = torch.randn(5, 17, 48)
     with torch.no_grad():
         assert_close(mod(x.cuda()), ref(x), rtol=1e-5, atol=5e-6, what="TCLinear")
+
+
+@pytest.mark.parametrize("M,K,N", [(128, 32, 32), (100, 32, 64), (1000, 16, 416), (4096, 384, 208), (300, 100, 52),
+                                   (777, 36, 420), (33, 1024, 1300), (1, 4, 8), (40000, 64, 512), (5000, 30, 50)])
+@pytest.mark.parametrize("precision", ["3xtf32", "tf32"])
+def test_linear_backward_vs_float64(M, K, N, precision):
+    """cnf_linear_bwd: grad_x = gy W (MN-major B), grad_W = gy^T x (both MN-major, split over M, red.add),
+    grad_b = column sums - against float64 products.  (5000, 30, 50) goes through the zero-padding wrapper."""
+    from categoricalnf_b200 import ops
+    x, w, _ = _rand_linear(M, K, N, seed=M + K + N + 1)
+    gy = torch.randn(M, N, generator=torch.Generator().manual_seed(M + 7)) / N ** 0.5
+    gx, gw, gb = ops.linear_bwd(dev(x), dev(w), dev(gy), need_bias=True, precision=precision)
+    ref_x = gy.double() @ w.double()
+    ref_w = gy.double().t() @ x.double()
+    ref_b = gy.double().sum(dim=0)
+    # error model: 3xTF32 keeps ~fp32 products, accumulation error grows with the reduction length
+    tol_x = (3e-6 + 6e-8 * N) if precision == "3xtf32" else 2e-2
+    scale_w = max(1.0, (M / N) ** 0.5)                # |grad_W| entries are O(sqrt(M/N))
+    tol_w = ((3e-6 + 6e-8 * min(M, 4096)) if precision == "3xtf32" else 2e-2) * scale_w
+    for got, ref, tol, what in ((gx, ref_x, tol_x, "grad_x"), (gw, ref_w, tol_w, "grad_weight"), (gb, ref_b, 1e-4 * scale_w, "grad_bias")):
+        assert got.shape == ref.shape, what
+        assert torch.isfinite(got).all(), what
+        err = (got.double().cpu() - ref).abs().max().item()
+        assert err <= tol, "%s: max |err| %.3e > %.3e" % (what, err, tol)
+
+
+def test_linear_backward_accumulates_and_partial_outputs():
+    from categoricalnf_b200 import ops
+    x, w, _ = _rand_linear(3000, 64, 96, seed=11)
+    gy = torch.randn(3000, 96, generator=torch.Generator().manual_seed(12)) * 0.1
+    gw0 = torch.randn(96, 64, generator=torch.Generator().manual_seed(13))
+    gb0 = torch.randn(96, generator=torch.Generator().manual_seed(14))
+    gx, gw, gb = ops.linear_bwd(dev(x), dev(w), dev(gy), need_x=False, need_bias=True, grad_weight=dev(gw0.clone()),
+                                grad_bias=dev(gb0.clone()))
+    assert gx is None
+    assert_close(gw, gw0.double() + gy.double().t() @ x.double(), rtol=1e-5, atol=2e-5, what="accumulated grad_weight")
+    assert_close(gb, gb0.double() + gy.double().sum(0), rtol=1e-5, atol=2e-5, what="accumulated grad_bias")
+    gx, gw, gb = ops.linear_bwd(dev(x), dev(w), dev(gy), need_weight=False)
+    assert gw is None and gb is None
+    assert_close(gx, gy.double() @ w.double(), rtol=1e-5, atol=5e-6, what="grad_x only")
+
+
+def test_tclinear_autograd_matches_nn_linear():
+    from categoricalnf_b200.layers.networks import TCLinear
+    torch.manual_seed(3)
+    ref = torch.nn.Linear(48, 72).double()
+    mod = TCLinear(48, 72).cuda()
+    mod.load_state_dict({k: v.float() for k, v in ref.state_dict().items()})
+    x = torch.randn(7, 33, 48)
+    xr = x.double().requires_grad_(True)
+    xg = x.cuda().requires_grad_(True)
+    wgt = torch.randn(7, 33, 72)
+    (ref(xr) * wgt.double()).sum().backward()
+    (mod(xg) * wgt.cuda()).sum().backward()
+    assert_close(xg.grad, xr.grad, rtol=1e-5, atol=5e-6, what="grad input")
+    assert_close(mod.weight.grad, ref.weight.grad, rtol=1e-5, atol=2e-5, what="grad weight")
+    assert_close(mod.bias.grad, ref.bias.grad, rtol=1e-5, atol=2e-5, what="grad bias")
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -176,3 +176,46 @@ def test_lm_flow_composition():
     z2, ldj2, _ = O.lm_flow_forward(g.x, g.u, enc, blocks, pad=g.pad, length=g.length)
     assert_close(z2, g.z, rtol=1e-4, atol=1e-4)
     assert_close(ldj2, g.ldj, rtol=1e-4, atol=1e-3)
+
+
+def _ne_weights(g, which, inverse=False):
+    w, sldj = O.invconv_weight(g["ic_%s_p" % which], g["ic_%s_l" % which], g["ic_%s_log_s" % which], g["ic_%s_u" % which],
+                               g["ic_%s_sign_s" % which])
+    return (O.invconv_inverse(w) if inverse else w), sldj
+
+
+def test_node_edge_coupling():
+    """a14: NodeEdgeCoupling forward (training, regulariser on), eval forward and reverse."""
+    g = load_golden("node_edge_coupling")
+    args = (g.z_nodes, g.z_edges, g.nn_nodes, g.nn_edges, g.mask_nodes, g.mask_edges, g.Kn, g.Ke, g.sf_nodes, g.sf_edges,
+            g.msf_nodes, g.msf_edges)
+    kw = dict(ldj=g.ldj_in, pad=g.pad, mask_valid=g.mask_valid, reg_max=3.5, reg_factor=2.0)
+    zn, ze, ldj, rn, re = O.node_edge_coupling(*args, training=True, **kw)
+    for a, b, w in ((zn, g.cp_zn, "zn"), (ze, g.cp_ze, "ze"), (ldj, g.cp_ldj, "ldj"), (rn, g.cp_reg_nodes, "reg_nodes"),
+                    (re, g.cp_reg_edges, "reg_edges")):
+        assert_close(a, b, what=w, **TIGHT)
+    zn, ze, ldj, _, _ = O.node_edge_coupling(*args, training=False, **kw)
+    assert_close(zn, g.cp_zn_eval, what="zn eval", **TIGHT)
+    assert_close(ldj, g.cp_ldj_eval, what="ldj eval", **TIGHT)
+    zr, er, lr, _, _ = O.node_edge_coupling(g.cp_zn_eval, g.cp_ze_eval, *args[2:], training=False, reverse=True, **kw)
+    assert_close(zr, g.cp_zn_rev, what="zn rev", **TIGHT)
+    assert_close(er, g.cp_ze_rev, what="ze rev", **TIGHT)
+    assert_close(lr, g.cp_ldj_rev, what="ldj rev", **TIGHT)
+
+
+def test_node_edge_wrapper():
+    """NodeEdgeFlowWrapper around ActNorm and InvertibleConv (edge length = number of valid pairs)."""
+    g = load_golden("node_edge_coupling")
+    kw = dict(length=g.length, pad=g.pad, mask_valid=g.mask_valid)
+    zn, ze, ldj = O.node_edge_wrapper(O.actnorm, g.z_nodes, g.z_edges, (g.an_bias_nodes, g.an_scales_nodes),
+                                      (g.an_bias_edges, g.an_scales_edges), ldj=g.ldj_in.clone(), **kw)
+    for a, b, w in ((zn, g.an_zn, "an zn"), (ze, g.an_ze, "an ze"), (ldj, g.an_ldj, "an ldj")):
+        assert_close(a, b, what=w, **TIGHT)
+    zi, ei, li = O.node_edge_wrapper(O.invconv, g.an_zn, g.an_ze, _ne_weights(g, "nodes"), _ne_weights(g, "edges"),
+                                     ldj=g.an_ldj.clone(), **kw)
+    for a, b, w in ((zi, g.ic_zn, "ic zn"), (ei, g.ic_ze, "ic ze"), (li, g.ic_ldj, "ic ldj")):
+        assert_close(a, b, what=w, **TIGHT)
+    zr, er, lr = O.node_edge_wrapper(O.invconv, g.ic_zn, g.ic_ze, _ne_weights(g, "nodes", True), _ne_weights(g, "edges", True),
+                                     ldj=g.ldj_in.clone(), reverse=True, **kw)
+    for a, b, w in ((zr, g.ic_zn_rev, "ic zn rev"), (er, g.ic_ze_rev, "ic ze rev"), (lr, g.ic_ldj_rev, "ic ldj rev")):
+        assert_close(a, b, what=w, **TIGHT)

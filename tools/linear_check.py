@@ -65,4 +65,19 @@ if "--time" in sys.argv:
         byts = 4.0 * (M * K + N * K + M * N)
         print("time %-7s M=%d K=%d N=%d: tcgen05 %.3f ms (%.1f TFLOP/s, %.0f GB/s) | cuBLAS fp32 %.3f ms | cuBLAS tf32 %.3f ms"
               % (prec, M, K, N, t_tc, flops / t_tc / 1e9, byts / t_tc / 1e6, t_fp32, t_tf32), flush=True)
+    if "--bwd" in sys.argv:
+        for (M, K, N) in [(4096 * 256, 64, 416), (512 * 703, 192, 384), (65536, 1024, 1024)]:
+            x = torch.randn(M, K, device=dev)
+            w = torch.randn(N, K, device=dev) / K ** 0.5
+            gy = torch.randn(M, N, device=dev)
+            gw = torch.zeros(N, K, device=dev)
+            t_dx = timeit(lambda: ops.linear_bwd(x, w, gy, need_weight=False, precision=prec))
+            t_dw = timeit(lambda: ops.linear_bwd(x, w, gy, need_x=False, precision=prec, grad_weight=gw))
+            torch.backends.cuda.matmul.allow_tf32 = True
+            c_dx = timeit(lambda: gy @ w)
+            c_dw = timeit(lambda: gy.t() @ x)
+            torch.backends.cuda.matmul.allow_tf32 = False
+            flops = 2.0 * M * N * K
+            print("time bwd %-7s M=%d K=%d N=%d: grad_x %.3f ms (%.1f TFLOP/s) cuBLAS tf32 %.3f | grad_W %.3f ms (%.1f TFLOP/s) cuBLAS tf32 %.3f"
+                  % (prec, M, K, N, t_dx, flops / t_dx / 1e9, c_dx, t_dw, flops / t_dw / 1e9, c_dw), flush=True)
 sys.exit(1 if bad else 0)
