@@ -136,6 +136,31 @@ class LinearBwdArgs(C.Structure):
     ]
 
 
+class LayernormArgs(C.Structure):
+    _fields_ = [("M", C.c_int64), ("H", C.c_int32), ("x", vp), ("gamma", vp), ("beta", vp), ("eps", C.c_float), ("y", vp)]
+
+
+class GraphAttnScoresArgs(C.Structure):
+    _fields_ = [
+        ("M", C.c_int64), ("E", C.c_int32), ("H", C.c_int32), ("Dh", C.c_int32),
+        ("hs", vp), ("hr", vp), ("ld_hs", C.c_int64), ("ld_hr", C.c_int64),
+        ("attn_weight", vp), ("score_s", vp), ("score_r", vp),
+    ]
+
+
+class GraphAggregateArgs(C.Structure):
+    _fields_ = [
+        ("B", C.c_int64), ("N", C.c_int32), ("E", C.c_int32), ("H", C.c_int32), ("Dh", C.c_int32),
+        ("adjacency", vp), ("hs", vp), ("hr", vp), ("ld_hs", C.c_int64), ("ld_hr", C.c_int64),
+        ("score_s", vp), ("score_r", vp), ("num_neighbours", vp),
+        ("mode", C.c_int32), ("leaky_slope", C.c_float), ("activation", C.c_int32), ("out", vp),
+    ]
+
+
+class SkipGateArgs(C.Structure):
+    _fields_ = [("M", C.c_int64), ("H", C.c_int32), ("config", C.c_int32), ("orig", vp), ("skip", vp), ("out", vp)]
+
+
 class LinearMixcdfArgs(C.Structure):
     _fields_ = [
         ("mix", MixcdfArgs), ("H", C.c_int32), ("precision", C.c_int32),
@@ -212,6 +237,10 @@ ENTRY_POINTS = {
     "cnf_ldj_axpy": LdjAxpyArgs,
     "cnf_linear_fwd": LinearArgs,
     "cnf_linear_bwd": LinearBwdArgs,
+    "cnf_layernorm": LayernormArgs,
+    "cnf_graph_attn_scores": GraphAttnScoresArgs,
+    "cnf_graph_aggregate": GraphAggregateArgs,
+    "cnf_skip_gate": SkipGateArgs,
     "cnf_linear_mixcdf_fwd": LinearMixcdfArgs,
     "cnf_linear_mixcdf_inv": LinearMixcdfArgs,
     "cnf_mixcdf_bwd": MixcdfBwdArgs,

@@ -568,3 +568,111 @@ def linear_mixcdf(z, features, weight, bias, num_mixtures, *, mask_c=None, mask_
     if z_masked is not None:
         return z_out, ldj_t, reg, z_masked
     return z_out, ldj_t, reg
+
+
+# ----------------------------------------------------------------------------------------------
+# glue of the graph coupling networks
+# ----------------------------------------------------------------------------------------------
+def layernorm(x, weight, bias, eps=1e-5):
+    """nn.LayerNorm over the last dimension (``cnf_layernorm``), one warp per row."""
+    x = _f32(x, "x")
+    H = x.shape[-1]
+    weight, bias = _f32(weight, "weight", (H,)), _f32(bias, "bias", (H,))
+    y = torch.empty_like(x)
+    a = L.LayernormArgs()
+    a.M, a.H = x.numel() // H, H
+    a.x, a.gamma, a.beta, a.eps, a.y = _ptr(x), _ptr(weight), _ptr(bias), float(eps), _ptr(y)
+    _call("cnf_layernorm", a, x, (x, weight, bias))
+    return y
+
+
+def _adjacency(adjacency, B, N):
+    if not adjacency.is_cuda:
+        raise RuntimeError("categoricalnf_b200: adjacency lives on %s - CUDA only" % adjacency.device)
+    if adjacency.dtype != torch.int64:
+        adjacency = adjacency.long()
+    if tuple(adjacency.shape) != (B, N, N):
+        raise ValueError("adjacency has shape %s, expected %s" % (tuple(adjacency.shape), (B, N, N)))
+    return adjacency.contiguous()
+
+
+def _rows(t, name, B, N):
+    """[B,N,F] or [B*N,F] features, possibly a column slice of a wider row-major matrix -> (tensor, row pitch in floats)."""
+    if not t.is_cuda:
+        raise RuntimeError("categoricalnf_b200: %s lives on %s - CUDA only" % (name, t.device))
+    if t.dtype != torch.float32:
+        t = t.float()
+    if t.dim() == 3:
+        if t.stride(2) == 1 and t.stride(0) == N * t.stride(1):
+            return t, t.stride(1)
+        t = t.contiguous()
+        return t, t.shape[-1]
+    if t.dim() == 2 and t.stride(1) == 1:
+        return t, t.stride(0)
+    t = t.contiguous()
+    return t, t.shape[-1]
+
+
+def graph_attention_aggregate(hs, hr, attn_weight, adjacency, num_edges, *, leaky_slope=0.2, activation=None):
+    """RelationGraphAttention core (graph_layers.py:92-151): ``hs`` [B,N,H*Dh], ``hr`` [B,N,(E+1)*H*Dh] (either may be a
+    column slice of one wider projection output), ``attn_weight`` [H,2,Dh], ``adjacency`` [B,N,N] integer edge types
+    (0 = none).  Returns the attention output [B,N,H*Dh] (GELU applied when ``activation="gelu"``)."""
+    B, N = hs.shape[0], hs.shape[1]
+    H, _, Dh = attn_weight.shape
+    E = int(num_edges)
+    aw = _f32(attn_weight, "attn_weight")
+    adjacency = _adjacency(adjacency, B, N)
+    hs_t, ld_hs = _rows(hs, "hs", B, N)
+    hr_t, ld_hr = _rows(hr, "hr", B, N)
+    if hs.shape[-1] != H * Dh or hr.shape[-1] != (E + 1) * H * Dh:
+        raise ValueError("hs / hr have %d / %d features, expected %d / %d" % (hs.shape[-1], hr.shape[-1], H * Dh, (E + 1) * H * Dh))
+    dev = hs.device
+    score_s = torch.empty(B * N, H, dtype=torch.float32, device=dev)
+    score_r = torch.empty(B * N, (E + 1) * H, dtype=torch.float32, device=dev)
+    a = L.GraphAttnScoresArgs()
+    a.M, a.E, a.H, a.Dh = B * N, E, H, Dh
+    a.hs, a.hr, a.ld_hs, a.ld_hr = _ptr(hs_t), _ptr(hr_t), ld_hs, ld_hr
+    a.attn_weight, a.score_s, a.score_r = _ptr(aw), _ptr(score_s), _ptr(score_r)
+    _call("cnf_graph_attn_scores", a, hs_t, (hs_t, hr_t, aw))
+    out = torch.empty(B, N, H * Dh, dtype=torch.float32, device=dev)
+    g = L.GraphAggregateArgs()
+    g.B, g.N, g.E, g.H, g.Dh = B, N, E, H, Dh
+    g.adjacency, g.hs, g.hr, g.ld_hs, g.ld_hr = _ptr(adjacency), None, _ptr(hr_t), ld_hs, ld_hr
+    g.score_s, g.score_r, g.num_neighbours = _ptr(score_s), _ptr(score_r), None
+    g.mode, g.leaky_slope, g.activation, g.out = 1, float(leaky_slope), ACTIVATION[activation], _ptr(out)
+    _call("cnf_graph_aggregate", g, hs_t, (adjacency, hr_t, score_s, score_r))
+    return out
+
+
+def graph_mean_aggregate(hs, hr, adjacency, num_edges, num_neighbours=None, *, activation=None):
+    """RelationGraphConv core (graph_layers.py:43-50): ``hs`` [B,N,C] + sum over neighbours j of ``hr`` [B,N,E*C] rows
+    (block of the edge type) divided by ``num_neighbours`` [B,N] (None -> the number of edges found)."""
+    B, N, Cc = hs.shape
+    E = int(num_edges)
+    adjacency = _adjacency(adjacency, B, N)
+    hs_t, ld_hs = _rows(hs, "hs", B, N)
+    hr_t, ld_hr = _rows(hr, "hr", B, N)
+    if hr.shape[-1] != E * Cc:
+        raise ValueError("hr has %d features, expected %d" % (hr.shape[-1], E * Cc))
+    nn_t = _opt_f32(num_neighbours, "num_neighbours", (B, N))
+    out = torch.empty(B, N, Cc, dtype=torch.float32, device=hs.device)
+    g = L.GraphAggregateArgs()
+    g.B, g.N, g.E, g.H, g.Dh = B, N, E, 1, Cc
+    g.adjacency, g.hs, g.hr, g.ld_hs, g.ld_hr = _ptr(adjacency), _ptr(hs_t), _ptr(hr_t), ld_hs, ld_hr
+    g.score_s, g.score_r, g.num_neighbours = None, None, _ptr(nn_t)
+    g.mode, g.leaky_slope, g.activation, g.out = 0, 0.0, ACTIVATION[activation], _ptr(out)
+    _call("cnf_graph_aggregate", g, hs_t, (adjacency, hs_t, hr_t, nn_t))
+    return out
+
+
+def skip_gate(orig, skip, config):
+    """GNNSkipConnection combination (graph_layers.py:722-733); ``skip`` = skip_layer(feat)."""
+    orig = _f32(orig, "orig")
+    H = orig.shape[-1]
+    skip = _f32(skip, "skip", orig.shape[:-1] + ((H if config == 0 else 2 * H),))
+    out = torch.empty_like(orig)
+    a = L.SkipGateArgs()
+    a.M, a.H, a.config = orig.numel() // H, H, int(config)
+    a.orig, a.skip, a.out = _ptr(orig), _ptr(skip), _ptr(out)
+    _call("cnf_skip_gate", a, orig, (orig, skip))
+    return out

@@ -377,6 +377,78 @@ typedef struct {
 CNF_API int cnf_linear_bwd(const cnf_linear_bwd_args* a, cnf_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Glue of the graph coupling networks around their projections
+ *   RGCNNet / RelationGraphConv / RelationGraphAttention / GNNSkipConnection,
+ *   layers/networks/graph_layers.py:15-154,157-235,702-733.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    int64_t M;            /* rows                                           */
+    int32_t H;            /* normalised (last) dimension                    */
+    const float* x;       /* [M,H]                                          */
+    const float* gamma;   /* [H] nn.LayerNorm.weight                        */
+    const float* beta;    /* [H] nn.LayerNorm.bias                          */
+    float eps;            /* 1e-5                                           */
+    float* y;             /* [M,H]                                          */
+} cnf_layernorm_args;
+
+CNF_API int cnf_layernorm(const cnf_layernorm_args* a, cnf_stream_t stream);
+
+/* Attention logits of RelationGraphAttention (graph_layers.py:92-96):
+ *   score_s[m,h]     = sum_d hs[m, h*Dh+d]          * attn_weight[h,0,d]
+ *   score_r[m,e,h]   = sum_d hr[m, (e*H+h)*Dh+d]    * attn_weight[h,1,d]      e in 0..E (E = self-connection) */
+typedef struct {
+    int64_t M;                /* nodes (B*N)                                  */
+    int32_t E, H, Dh;         /* edge types, heads, features per head         */
+    const float* hs;          /* [M, >= H*Dh], row pitch ld_hs                */
+    const float* hr;          /* [M, >= (E+1)*H*Dh], row pitch ld_hr          */
+    int64_t ld_hs, ld_hr;
+    const float* attn_weight; /* [H,2,Dh]                                     */
+    float* score_s;           /* [M,H]                                        */
+    float* score_r;           /* [M,(E+1)*H]                                  */
+} cnf_graph_attn_scores_args;
+
+CNF_API int cnf_graph_attn_scores(const cnf_graph_attn_scores_args* a, cnf_stream_t stream);
+
+/* Neighbour aggregation from the INTEGER adjacency (0 = no edge, 1..E = edge type; the reference one-hot
+ * encodes it first, graph_layers.py:205).
+ *   mode 0 (RelationGraphConv.forward :37-50, H = 1, Dh = c_out):
+ *       out[i] = hs[i] + sum_{j: adj[j][i] > 0} hr[j, adj[j][i]-1, :] / max(num_neighbours[i], 1e-5)
+ *   mode 1 (RelationGraphAttention.forward :98-154): neighbours j of row i plus i itself with edge slot E,
+ *       p = softmax_j leaky_relu(score_s[i,h] + score_r[j, e, h]),  out[i,h,:] = sum_j p_j hr[j, e, h, :]
+ * activation 1 applies GELU to the result (the nn.GELU opening output_projection, :68-71). */
+typedef struct {
+    int64_t B;
+    int32_t N, E, H, Dh;
+    const int64_t* adjacency;     /* [B,N,N]                                           */
+    const float* hs;              /* mode 0: [B*N, >= Dh] pitch ld_hs; mode 1: unused  */
+    const float* hr;              /* [B*N, >= (E or E+1)*H*Dh] pitch ld_hr             */
+    int64_t ld_hs, ld_hr;
+    const float* score_s;         /* mode 1: [B*N,H]                                   */
+    const float* score_r;         /* mode 1: [B*N,(E+1)*H]                             */
+    const float* num_neighbours;  /* mode 0: [B*N] or NULL (-> number of edges found)  */
+    int32_t mode;
+    float leaky_slope;            /* 0.2                                               */
+    int32_t activation;           /* 0 none, 1 GELU                                    */
+    float* out;                   /* [B*N, H*Dh]                                       */
+} cnf_graph_aggregate_args;
+
+CNF_API int cnf_graph_aggregate(const cnf_graph_aggregate_args* a, cnf_stream_t stream);
+
+/* GNNSkipConnection.forward (graph_layers.py:722-733); `skip` = skip_layer(feat):
+ *   config 0: out = orig + skip                              skip [M,H]
+ *   config 1: out = orig + val * sigmoid(gate)               skip [M,2H] = [val | gate]
+ *   config 2: out = orig * (1 - sigmoid(gate)) + val * sigmoid(gate) */
+typedef struct {
+    int64_t M;
+    int32_t H, config;
+    const float* orig;    /* [M,H]           */
+    const float* skip;    /* [M,H] or [M,2H] */
+    float* out;           /* [M,H]           */
+} cnf_skip_gate_args;
+
+CNF_API int cnf_skip_gate(const cnf_skip_gate_args* a, cnf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * K8 + K1/K2 fused: FINAL projection of the coupling network + mixture-CDF coupling transform.
  *   nn_out = features @ weight^T + bias   (last nn.Linear of the network, e.g.
  *            layers/networks/graph_layers.py:198-201,775-778; help_layers.py:84-94)

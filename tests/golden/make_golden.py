@@ -496,11 +496,105 @@ def gold_node_edge(seed):
          an_bias_edges=an.edge_flow.bias.data, an_scales_edges=an.edge_flow.scales.data, **sd, **out)
 
 
+def _rand_graphs(g, B, N, num_edge_types, p_edge=0.2, min_len=None):
+    """Random symmetric integer adjacency [B,N,N] (0 = no edge, 1..E edge type), lengths, padding zeroed."""
+    length = torch.randint(min_len or max(2, N // 2), N + 1, (B,), generator=g)
+    upper = (torch.rand(B, N, N, generator=g) < p_edge).long() * torch.randint(1, num_edge_types + 1, (B, N, N), generator=g)
+    upper = torch.triu(upper, diagonal=1)
+    adj = upper + upper.transpose(1, 2)
+    valid = (torch.arange(N)[None, :] < length[:, None])
+    adj = adj * (valid[:, :, None] & valid[:, None, :]).long()
+    return adj, length
+
+
+def _randomise(module, g, std=0.3):
+    """Give every parameter a seeded non-trivial value (fresh modules have zero biases / unit LayerNorm gains)."""
+    with torch.no_grad():
+        for name, prm in module.named_parameters():
+            if prm.dim() >= 2:
+                prm.copy_(torch.randn(prm.shape, generator=g) * (std / max(1.0, prm.shape[-1] ** 0.5) * 3.0))
+            elif "norm" in name and name.endswith("weight"):
+                prm.copy_(1.0 + torch.randn(prm.shape, generator=g) * 0.1)
+            else:
+                prm.copy_(torch.randn(prm.shape, generator=g) * 0.1)
+
+
+def gold_rgcn(name, seed, attention, num_edges, B=3, N=9, c_in=4, c_out=10, hidden=32, layers=2, skip_config=2, max_neighbours=4):
+    """RGCNNet (layers/networks/graph_layers.py:157-235) with RelationGraphAttention or RelationGraphConv layers."""
+    from layers.networks.graph_layers import RGCNNet, RelationGraphAttention, RelationGraphConv
+    g = torch.Generator().manual_seed(seed)
+    torch.manual_seed(seed)
+    net = RGCNNet(c_in=c_in, c_out=c_out, num_edges=num_edges, num_layers=layers, hidden_size=hidden, skip_config=skip_config,
+                  max_neighbours=max_neighbours, rgc_layer_fun=RelationGraphAttention if attention else RelationGraphConv)
+    _randomise(net, g)
+    net.eval()
+    adj, length = _rand_graphs(g, B, N, num_edges, p_edge=0.3)
+    x = torch.randn(B, N, c_in, generator=g)
+    pad = lengths_to_pad(length, N)
+    with torch.no_grad():
+        out = net(x, adjacency=adj)
+        out_pad = net(x, adjacency=adj, channel_padding_mask=pad)
+    sd = {"sd__" + k: v for k, v in net.state_dict().items()}
+    save(name, x=x, adjacency=adj, length=length, pad=pad, out=out, out_pad=out_pad, attention=int(attention),
+         num_edges=num_edges, c_in=c_in, c_out=c_out, hidden=hidden, layers=layers, skip_config=skip_config,
+         max_neighbours=max_neighbours, **sd)
+
+
+def gold_graph_node_flow(seed):
+    """BASELINE config 3 in small: the reference's GraphNodeFlow (experiments/graph_coloring/graph_node_flow.py) -
+    encoding (3 colours, d=2) + 2 x [ActNorm, InvConv, MixtureCDFCoupling(RGCNNet attention)] + ActNorm - forward
+    (log-likelihood direction) in eval mode and the reverse pass of the flow layers on the resulting latents."""
+    from experiments.graph_coloring.graph_node_flow import GraphNodeFlow
+    g = torch.Generator().manual_seed(seed)
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+
+    class _Dataset:
+        @staticmethod
+        def num_node_types():
+            return 3
+
+    params = {"categ_encoding": {"use_dequantization": False, "use_variational": False, "use_decoder": False,
+                                 "num_dimensions": 2, "flow_config": {"num_flows": 0, "hidden_layers": 2, "hidden_size": 128},
+                                 "decoder_config": {"num_layers": 1, "hidden_size": 64}},
+              "coupling_num_flows": 2, "coupling_hidden_size": 32, "coupling_hidden_layers": 2, "coupling_num_mixtures": 8,
+              "coupling_mask_ratio": 0.5, "coupling_dropout": 0.0}
+    model = _quiet(GraphNodeFlow, params, _Dataset)
+    _randomise(model, g)
+    model.eval()
+    B, N = 4, 8
+    adj, length = _rand_graphs(g, B, N, 1, p_edge=0.35, min_len=4)
+    x = torch.randint(0, 3, (B, N), generator=g)
+    noise = {}
+
+    def rec_sample(sample_shape=torch.Size()):
+        noise["u"] = torch.rand(sample_shape, generator=g)
+        return noise["u"]
+
+    model.node_embed_flow.prior_distribution.distribution.sample = rec_sample
+    with torch.no_grad():
+        z, ldj = model(x, adjacency=adj, length=length)
+        # reverse pass of the continuous layers only (decoding = argmax, tested separately)
+        kw = dict(adjacency=adj, length=length, channel_padding_mask=lengths_to_pad(length, N))
+        z_rev, ldj_rev = z, torch.zeros(B)
+        for layer in reversed(list(model.flow_layers)[1:]):
+            res = layer(z_rev, reverse=True, **kw)
+            z_rev, ldj_rev = res[0], ldj_rev + res[1]      # FlowModel.forward: no ldj passed, layer ldj added (:30-44)
+        x_dec = model.node_embed_flow(z_rev, reverse=True, **kw)[0]
+    sd = {"sd__" + k: v for k, v in model.state_dict().items()}
+    save("graph_node_flow", x=x, adjacency=adj, length=length, u=noise["u"], z=z, ldj=ldj, z_rev=z_rev, ldj_rev=ldj_rev,
+         x_dec=x_dec, **sd)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(4)
     if ONLY:
         for _n in ONLY:
-            {"node_edge": lambda: gold_node_edge(seed=22)}[_n]()
+            {"node_edge": lambda: gold_node_edge(seed=22),
+             "rgcn": lambda: (gold_rgcn("rgcn_attention", 23, True, 1), gold_rgcn("rgcn_attention_e3", 24, True, 3, skip_config=1),
+                              gold_rgcn("rgcn_conv", 25, False, 3, N=12), gold_rgcn("rgcn_conv_skip0", 26, False, 1, skip_config=0,
+                                                                                   max_neighbours=0)),
+             "graph_flow": lambda: gold_graph_node_flow(seed=27)}[_n]()
         sys.exit(0)
     gold_mixcdf_selftest()
     gold_mixcdf("mixcdf_lm_small", 3, 32, 16, 8, seed=1)
@@ -527,3 +621,8 @@ if __name__ == "__main__":
     gold_encoding("encode_virtual", 2, 12, 1, 2, seed=20)
     gold_lm_flow(seed=21)
     gold_node_edge(seed=22)
+    gold_rgcn("rgcn_attention", 23, True, 1)
+    gold_rgcn("rgcn_attention_e3", 24, True, 3, skip_config=1)
+    gold_rgcn("rgcn_conv", 25, False, 3, N=12)
+    gold_rgcn("rgcn_conv_skip0", 26, False, 1, skip_config=0, max_neighbours=0)
+    gold_graph_node_flow(seed=27)

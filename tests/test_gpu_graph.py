@@ -1,0 +1,220 @@
+"""GPU parity of the graph coupling networks and the graph-colouring flow (BASELINE config 3):
+glue kernels against plain formulas, ``RGCNNet`` (attention and plain relational convolution) and ``GraphNodeFlow``
+against the golden outputs of the unmodified reference (state dicts loaded by name, strict), the differentiable
+training path against the kernel path and the oracle's autograd, and size-independent properties at the
+config's full size (B 1024, N 20, hidden 384).
+
+Tolerance: networks |a-b| <= 1e-4 |b| + 2e-5 (3xTF32 projections, fp32 glue); flow outputs as everywhere:
+|a-b| <= 1e-4 |b| + 1e-5 on z, 1e-4 relative (+2e-4) on ldj."""
+import pytest
+import torch
+
+from conftest import assert_close, load_golden
+from oracle import graph_oracle as GO
+
+pytestmark = pytest.mark.gpu
+
+
+def _sd(g):
+    return {k[len("sd__"):]: v for k, v in g.items() if k.startswith("sd__")}
+
+
+def _graphs(gen, B, N, E, p=0.25):
+    length = torch.randint(max(2, N // 2), N + 1, (B,), generator=gen)
+    up = (torch.rand(B, N, N, generator=gen) < p).long() * torch.randint(1, E + 1, (B, N, N), generator=gen)
+    up = torch.triu(up, diagonal=1)
+    adj = up + up.transpose(1, 2)
+    valid = torch.arange(N)[None, :] < length[:, None]
+    return adj * (valid[:, :, None] & valid[:, None, :]).long(), length
+
+
+# ---- kernels --------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,H", [(37, 32), (1000, 384), (5, 30), (20480, 96)])
+def test_layernorm(M, H):
+    from categoricalnf_b200 import ops
+    gen = torch.Generator().manual_seed(M + H)
+    x = torch.randn(M, H, generator=gen) * 2 + 0.5
+    w, b = torch.randn(H, generator=gen), torch.randn(H, generator=gen)
+    y = ops.layernorm(x.cuda(), w.cuda(), b.cuda())
+    ref = torch.nn.functional.layer_norm(x.double(), (H,), w.double(), b.double(), 1e-5)
+    assert_close(y, ref, rtol=1e-5, atol=1e-5, what="layernorm")
+
+
+@pytest.mark.parametrize("config", [0, 1, 2])
+def test_skip_gate(config):
+    from categoricalnf_b200 import ops
+    gen = torch.Generator().manual_seed(config)
+    orig = torch.randn(6, 11, 40, generator=gen)
+    s = torch.randn(6, 11, 40 if config == 0 else 80, generator=gen)
+    out = ops.skip_gate(orig.cuda(), s.cuda(), config)
+    if config == 0:
+        ref = orig + s
+    else:
+        val, gate = s.double().chunk(2, dim=-1)
+        gate = torch.sigmoid(gate)
+        ref = orig + val * gate if config == 1 else orig * (1 - gate) + val * gate
+    assert_close(out, ref, rtol=1e-5, atol=2e-6, what="skip gate")
+
+
+@pytest.mark.parametrize("B,N,E,H,Dh", [(3, 9, 1, 4, 16), (2, 20, 3, 4, 12), (5, 38, 2, 2, 7), (4, 70, 1, 8, 8)])
+def test_attention_aggregate_vs_dense(B, N, E, H, Dh):
+    """cnf_graph_attn_scores + cnf_graph_aggregate (mode 1) against a dense masked softmax in float64."""
+    from categoricalnf_b200 import ops
+    gen = torch.Generator().manual_seed(B * N + E)
+    adj, _ = _graphs(gen, B, N, E)
+    hs = torch.randn(B, N, H * Dh, generator=gen)
+    hr = torch.randn(B, N, (E + 1) * H * Dh, generator=gen)
+    aw = torch.randn(H, 2, Dh, generator=gen) * 0.5
+    out = ops.graph_attention_aggregate(hs.cuda(), hr.cuda(), aw.cuda(), adj.cuda(), E)
+    hs4, hr5 = hs.double().view(B, N, H, Dh), hr.double().view(B, N, E + 1, H, Dh)
+    s_s = (hs4 * aw[:, 0].double()).sum(-1)
+    s_r = (hr5 * aw[:, 1].double()).sum(-1)
+    etype = torch.where(torch.eye(N, dtype=torch.bool)[None], torch.full_like(adj, E + 1), adj)
+    ref = torch.zeros(B, N, H, Dh, dtype=torch.float64)
+    for b in range(B):
+        for i in range(N):
+            js = torch.nonzero(etype[b, i] > 0).flatten()
+            es = etype[b, i, js] - 1
+            logit = torch.nn.functional.leaky_relu(s_s[b, i][None, :] + s_r[b, js, es], 0.2)       # [n,H]
+            p = torch.softmax(logit, dim=0)
+            ref[b, i] = (p[..., None] * hr5[b, js, es]).sum(0)
+    assert_close(out, ref.view(B, N, H * Dh), rtol=1e-5, atol=5e-6, what="attention aggregate")
+    # column slices of one wider matrix (the fused hs|hr projection output) and the GELU epilogue
+    wide = torch.cat([hs, hr], dim=-1).reshape(B * N, -1).cuda()
+    out2 = ops.graph_attention_aggregate(wide[:, :H * Dh].unflatten(0, (B, N)), wide[:, H * Dh:].unflatten(0, (B, N)),
+                                         aw.cuda(), adj.cuda(), E, activation="gelu")
+    assert_close(out2, torch.nn.functional.gelu(ref.view(B, N, H * Dh)), rtol=1e-5, atol=5e-6, what="sliced + gelu")
+
+
+@pytest.mark.parametrize("B,N,E,C", [(3, 12, 3, 32), (2, 38, 3, 20), (4, 9, 1, 7)])
+def test_mean_aggregate_vs_dense(B, N, E, C):
+    from categoricalnf_b200 import ops
+    gen = torch.Generator().manual_seed(B + N + E + C)
+    adj, _ = _graphs(gen, B, N, E, p=0.4)
+    hs = torch.randn(B, N, C, generator=gen)
+    hr = torch.randn(B, N, E * C, generator=gen)
+    nn_ = (adj > 0).sum(dim=1).float().clamp(max=4)
+    out = ops.graph_mean_aggregate(hs.cuda(), hr.cuda(), adj.cuda(), E, nn_.cuda())
+    onehot = torch.nn.functional.one_hot(adj, E + 1)[..., 1:].double()
+    ref = hs.double() + torch.einsum("bjie,bjec->bic", onehot, hr.double().view(B, N, E, C)) / nn_.double().unsqueeze(-1).clamp(min=1e-5)
+    assert_close(out, ref, rtol=1e-5, atol=5e-6, what="mean aggregate")
+    out = ops.graph_mean_aggregate(hs.cuda(), hr.cuda(), adj.cuda(), E, None)
+    cnt = (adj > 0).sum(dim=1).double()
+    ref = hs.double() + torch.einsum("bjie,bjec->bic", onehot, hr.double().view(B, N, E, C)) / cnt.unsqueeze(-1).clamp(min=1e-5)
+    assert_close(out, ref, rtol=1e-5, atol=5e-6, what="mean aggregate, counted neighbours")
+
+
+# ---- networks -------------------------------------------------------------------------------------------------------
+def _build_rgcn(g):
+    from categoricalnf_b200.layers.networks import RGCNNet, RelationGraphAttention, RelationGraphConv
+    net = RGCNNet(c_in=g.c_in, c_out=g.c_out, num_edges=g.num_edges, num_layers=g.layers, hidden_size=g.hidden,
+                  skip_config=g.skip_config, max_neighbours=g.max_neighbours,
+                  rgc_layer_fun=RelationGraphAttention if g.attention else RelationGraphConv)
+    net.load_state_dict(_sd(g), strict=True)          # the reference's parameter names
+    return net.cuda().eval()
+
+
+@pytest.mark.parametrize("name", ["rgcn_attention", "rgcn_attention_e3", "rgcn_conv", "rgcn_conv_skip0"])
+def test_rgcn_net_golden(name):
+    g = load_golden(name)
+    net = _build_rgcn(g)
+    with torch.no_grad():
+        out = net(g.x.cuda(), adjacency=g.adjacency.cuda())
+        out_pad = net(g.x.cuda(), adjacency=g.adjacency.cuda(), channel_padding_mask=g.pad.cuda())
+    assert_close(out, g.out, rtol=1e-4, atol=2e-5, what="RGCNNet")
+    assert_close(out_pad, g.out_pad, rtol=1e-4, atol=2e-5, what="RGCNNet padded")
+    # the reference's layers take the one-hot adjacency: same result through that form
+    layer = net.layers[0][0]
+    h = torch.randn(g.x.shape[0], g.x.shape[1], g.hidden, generator=torch.Generator().manual_seed(1)).cuda()
+    onehot = torch.nn.functional.one_hot(g.adjacency, g.num_edges + 1)[..., 1:].float().cuda()
+    with torch.no_grad():
+        assert_close(layer(h, adjacency=onehot), layer(h, adjacency=g.adjacency.cuda()), rtol=0, atol=0, what="one-hot adjacency")
+
+
+@pytest.mark.parametrize("name", ["rgcn_attention_e3", "rgcn_conv"])
+def test_rgcn_training_path_and_gradients(name):
+    """With grad enabled the glue runs as differentiable dense torch ops around the tensor-core projections: same
+    output as the kernel path, gradients equal to autograd through the CPU oracle."""
+    g = load_golden(name)
+    net = _build_rgcn(g).train()
+    sd = {k: v.clone().requires_grad_(True) for k, v in _sd(g).items()}
+    x_ref = g.x.clone().requires_grad_(True)
+    out_ref = GO.rgcn_net(sd, x_ref, g.adjacency, num_edges=g.num_edges, num_layers=g.layers, attention=bool(g.attention),
+                          skip_config=g.skip_config, max_neighbours=g.max_neighbours)
+    wgt = torch.randn(out_ref.shape, generator=torch.Generator().manual_seed(2))
+    (out_ref * wgt).sum().backward()
+    x = g.x.cuda().requires_grad_(True)
+    out = net(x, adjacency=g.adjacency.cuda())
+    assert_close(out, g.out, rtol=1e-4, atol=2e-5, what="training-path output")
+    (out * wgt.cuda()).sum().backward()
+    assert_close(x.grad, x_ref.grad, rtol=1e-3, atol=2e-5, what="grad x")
+    for k, p in net.named_parameters():
+        assert p.grad is not None, k
+        scale = float(sd[k].grad.abs().max()) + 1e-6
+        assert_close(p.grad / scale, sd[k].grad / scale, rtol=1e-3, atol=2e-4, what="grad " + k)
+
+
+def _build_flow(g, hidden=32, layers=2, flows=2, mixtures=8):
+    from categoricalnf_b200.experiments.graph_coloring import GraphNodeFlow
+
+    class _Dataset:
+        @staticmethod
+        def num_node_types():
+            return 3
+
+    params = {"categ_encoding": {"use_dequantization": False, "use_variational": False, "use_decoder": False, "num_dimensions": 2,
+                                 "flow_config": {"num_flows": 0, "hidden_layers": 2, "hidden_size": 128},
+                                 "decoder_config": {"num_layers": 1, "hidden_size": 64}},
+              "coupling_num_flows": flows, "coupling_hidden_size": hidden, "coupling_hidden_layers": layers,
+              "coupling_num_mixtures": mixtures, "coupling_mask_ratio": 0.5, "coupling_dropout": 0.0}
+    model = GraphNodeFlow(params, _Dataset)
+    if g is not None:
+        model.load_state_dict(_sd(g), strict=True)
+    return model.cuda().eval()
+
+
+def test_graph_node_flow_golden():
+    g = load_golden("graph_node_flow")
+    model = _build_flow(g)
+    with torch.no_grad():
+        z, ldj = model(g.x.cuda(), adjacency=g.adjacency.cuda(), length=g.length.cuda(), u_noise=g.u.cuda())
+        assert_close(z, g.z, what="z")
+        assert_close(ldj, g.ldj, rtol=1e-4, atol=2e-4, what="ldj")
+        # reverse pass of the continuous layers, then decoding
+        N = g.x.shape[1]
+        from categoricalnf_b200.experiments.graph_coloring.graph_node_flow import length_masks
+        kpm, cpm = length_masks(g.length.cuda(), N)
+        kw = dict(adjacency=g.adjacency.cuda(), length=g.length.cuda(), channel_padding_mask=cpm, src_key_padding_mask=kpm)
+        z_rev, ldj_rev = g.z.cuda(), torch.zeros(g.x.shape[0], device="cuda")
+        for layer in reversed(list(model.flow_layers)[1:]):
+            res = layer(z_rev, reverse=True, **kw)
+            z_rev, ldj_rev = res[0], ldj_rev + res[1]
+        assert_close(z_rev, g.z_rev, rtol=1e-4, atol=2e-5, what="z reverse")
+        assert_close(ldj_rev, g.ldj_rev, rtol=1e-4, atol=2e-4, what="ldj reverse")
+        x_dec = model.node_embed_flow(g.z_rev.cuda(), reverse=True, **kw)[0]
+        valid = cpm.squeeze(-1).bool().cpu()
+        assert torch.equal(x_dec.cpu()[valid], g.x_dec[valid])
+
+
+def test_graph_node_flow_full_size_properties():
+    """BASELINE config 3 size: B 1024, N 20, hidden 384, 4 layers, 8 flows, 8 mixtures - data-dependent init,
+    forward, batch-split consistency of the log-likelihood, forward -> reverse round trip."""
+    gen = torch.Generator().manual_seed(0)
+    torch.manual_seed(0)
+    B, N = 1024, 20
+    model = _build_flow(None, hidden=384, layers=4, flows=8, mixtures=8)
+    adj, length = _graphs(gen, B, N, 1, p=0.15)
+    x = torch.randint(0, 3, (B, N), generator=gen)
+    xc, ac, lc = x.cuda(), adj.cuda(), length.cuda()
+    with torch.no_grad():
+        model.initialize_data_dependent([(xc[:256], {"adjacency": ac[:256], "length": lc[:256]})])
+        assert model.test_reversibility(xc[:64], ac[:64], lc[:64])
+        u = torch.rand(B * N, 1, 2, generator=gen).cuda()
+        z, ldj = model(xc, adjacency=ac, length=lc, u_noise=u)
+        assert torch.isfinite(z).all() and torch.isfinite(ldj).all()
+        h = B // 2
+        z0, l0 = model(xc[:h], adjacency=ac[:h], length=lc[:h], u_noise=u[:h * N])
+        assert_close(z0, z[:h], rtol=1e-4, atol=1e-4, what="batch split z")
+        assert_close(l0, ldj[:h], rtol=1e-4, atol=1e-3, what="batch split ldj")
+        pad = (torch.arange(N)[None, :] < length[:, None]).cuda()
+        assert (z[~pad] == 0).all()

@@ -219,3 +219,34 @@ def test_node_edge_wrapper():
                                      ldj=g.ldj_in.clone(), reverse=True, **kw)
     for a, b, w in ((zr, g.ic_zn_rev, "ic zn rev"), (er, g.ic_ze_rev, "ic ze rev"), (lr, g.ic_ldj_rev, "ic ldj rev")):
         assert_close(a, b, what=w, **TIGHT)
+
+
+# ---------------------------------------------------------------------------------------------------
+# graph coupling networks and the graph-colouring flow (BASELINE config 3)
+# ---------------------------------------------------------------------------------------------------
+def _sd(g):
+    return {k[len("sd__"):]: v for k, v in g.items() if k.startswith("sd__")}
+
+
+@pytest.mark.parametrize("name", ["rgcn_attention", "rgcn_attention_e3", "rgcn_conv", "rgcn_conv_skip0"])
+def test_rgcn_net(name):
+    from oracle import graph_oracle as GO
+    g = load_golden(name)
+    kw = dict(num_edges=g.num_edges, num_layers=g.layers, attention=bool(g.attention), skip_config=g.skip_config,
+              max_neighbours=g.max_neighbours)
+    out = GO.rgcn_net(_sd(g), g.x, g.adjacency, **kw)
+    assert_close(out, g.out, rtol=1e-5, atol=2e-6, what="RGCNNet")
+    out = GO.rgcn_net(_sd(g), g.x, g.adjacency, pad=g.pad, **kw)
+    assert_close(out, g.out_pad, rtol=1e-5, atol=2e-6, what="RGCNNet padded")
+
+
+def test_graph_node_flow():
+    from oracle import graph_oracle as GO
+    g = load_golden("graph_node_flow")
+    kw = dict(num_flows=2, num_layers=2, num_mixtures=8)
+    z, ldj = GO.graph_node_flow(_sd(g), g.x, g.adjacency, g.length, g.u, **kw)
+    assert_close(z, g.z, rtol=1e-5, atol=5e-6, what="z")
+    assert_close(ldj, g.ldj, rtol=1e-5, atol=5e-5, what="ldj")
+    zr, lr = GO.graph_node_flow(_sd(g), g.x, g.adjacency, g.length, g.u, reverse_z=g.z, **kw)
+    assert_close(zr, g.z_rev, rtol=1e-4, atol=2e-5, what="z reverse")
+    assert_close(lr, g.ldj_rev, rtol=1e-4, atol=2e-4, what="ldj reverse")
