@@ -152,13 +152,30 @@ class GraphAggregateArgs(C.Structure):
     _fields_ = [
         ("B", C.c_int64), ("N", C.c_int32), ("E", C.c_int32), ("H", C.c_int32), ("Dh", C.c_int32),
         ("adjacency", vp), ("hs", vp), ("hr", vp), ("ld_hs", C.c_int64), ("ld_hr", C.c_int64),
-        ("score_s", vp), ("score_r", vp), ("num_neighbours", vp),
+        ("score_s", vp), ("score_r", vp), ("ld_score_s", C.c_int64), ("ld_score_r", C.c_int64), ("num_neighbours", vp),
         ("mode", C.c_int32), ("leaky_slope", C.c_float), ("activation", C.c_int32), ("out", vp),
     ]
 
 
 class SkipGateArgs(C.Structure):
     _fields_ = [("M", C.c_int64), ("H", C.c_int32), ("config", C.c_int32), ("orig", vp), ("skip", vp), ("out", vp)]
+
+
+class EdgeAggregateArgs(C.Structure):
+    _fields_ = [
+        ("B", C.c_int64), ("N", C.c_int32), ("H", C.c_int32), ("Dh", C.c_int32), ("R", C.c_int64),
+        ("rev", vp), ("node_val", vp), ("node_q", vp), ("node_k", vp), ("edge_val", vp), ("edge_logit", vp),
+        ("ld_node_val", C.c_int64), ("ld_node_q", C.c_int64), ("ld_node_k", C.c_int64), ("ld_edge_val", C.c_int64),
+        ("ld_edge_logit", C.c_int64), ("mode", C.c_int32), ("scale", C.c_float), ("out", vp),
+    ]
+
+
+class PairCombineArgs(C.Structure):
+    _fields_ = [
+        ("R", C.c_int64), ("N", C.c_int32), ("He", C.c_int32),
+        ("flat_indices", vp), ("x_indices1", vp), ("x_indices2", vp), ("edge_lin", vp), ("node_lin", vp),
+        ("ld_edge", C.c_int64), ("ld_node", C.c_int64), ("activation", C.c_int32), ("out", vp),
+    ]
 
 
 class LinearMixcdfArgs(C.Structure):
@@ -241,6 +258,8 @@ ENTRY_POINTS = {
     "cnf_graph_attn_scores": GraphAttnScoresArgs,
     "cnf_graph_aggregate": GraphAggregateArgs,
     "cnf_skip_gate": SkipGateArgs,
+    "cnf_edge_aggregate": EdgeAggregateArgs,
+    "cnf_pair_combine": PairCombineArgs,
     "cnf_linear_mixcdf_fwd": LinearMixcdfArgs,
     "cnf_linear_mixcdf_inv": LinearMixcdfArgs,
     "cnf_mixcdf_bwd": MixcdfBwdArgs,

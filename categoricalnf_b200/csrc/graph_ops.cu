@@ -112,7 +112,7 @@ struct AggParams {
     const long long* adj;            // [B,N,N], 0 = no edge, e in 1..E = edge type
     const float* hs; const float* hr; const float* score_s; const float* score_r; const float* num_neighbours;
     float* out;
-    long long ld_hs, ld_hr;
+    long long ld_hs, ld_hr, ld_ss, ld_sr;
     int N, E, H, Dh, mode, act, vec;
     float slope;
 };
@@ -164,12 +164,11 @@ __global__ void __launch_bounds__(kAggThreads) graph_aggregate_kernel(const AggP
 
     if (p.mode == 1) {
         // softmax over the neighbour list, one warp per head (:143-149)
-        const int EH = (p.E + 1) * p.H;
         for (int h = warp; h < p.H; h += kAggThreads / 32) {
-            const float s_self = p.score_s[node * p.H + h];
+            const float s_self = p.score_s[node * p.ld_ss + h];
             float mx = -3.0e38f;
             for (int n = lane; n < cnt; n += 32) {
-                float l = s_self + p.score_r[(b * p.N + nb_row[n]) * EH + nb_e[n] * p.H + h];
+                float l = s_self + p.score_r[(b * p.N + nb_row[n]) * p.ld_sr + nb_e[n] * p.H + h];
                 l = l > 0.f ? l : l * p.slope;
                 wgt[h * (p.N + 1) + n] = l;
                 mx = fmaxf(mx, l);
@@ -308,6 +307,8 @@ extern "C" int cnf_graph_aggregate(const cnf_graph_aggregate_args* a, cnf_stream
     p.adj = reinterpret_cast<const long long*>(a->adjacency);
     p.hs = a->hs; p.hr = a->hr; p.score_s = a->score_s; p.score_r = a->score_r; p.num_neighbours = a->num_neighbours;
     p.out = a->out; p.ld_hs = a->ld_hs; p.ld_hr = a->ld_hr;
+    p.ld_ss = a->ld_score_s > 0 ? a->ld_score_s : a->H;
+    p.ld_sr = a->ld_score_r > 0 ? a->ld_score_r : (long long)(a->E + 1) * a->H;
     p.N = a->N; p.E = a->E; p.H = a->H; p.Dh = a->Dh; p.mode = a->mode; p.act = a->activation; p.slope = a->leaky_slope;
     uintptr_t bits = reinterpret_cast<uintptr_t>(a->hr) | reinterpret_cast<uintptr_t>(a->out);
     if (a->mode == 0) bits |= reinterpret_cast<uintptr_t>(a->hs);
@@ -329,4 +330,208 @@ extern "C" int cnf_skip_gate(const cnf_skip_gate_args* a, cnf_stream_t stream_) 
     GateParams p{a->orig, a->skip, a->out, a->M, a->H, a->config};
     skip_gate_kernel<<<capped_grid((a->M * a->H + 255) / 256, 8), 256, 0, stream>>>(p);
     return launch_status("skip_gate_kernel");
+}
+
+// =====================================================================================================================
+// Edge-GNN glue (layers/networks/graph_layers.py:242-336, 388-700): node <-> node-pair message passing of GraphCNF.
+// Node pairs (a < b) are numbered node-major, p(a,b) = a (N-1) - a (a-1)/2 + (b-a-1)  (molecule_generation/mutils.py:5-10);
+// the features of the VALID pairs are stored compacted ([R, *]), `rev[b*P + p]` = 1 + row of pair p of graph b, 0 = not
+// valid (the reference's indices_reverse, graph_layers.py:349-355).
+//   cnf_edge_aggregate  Edge2NodeAttnLayer (:595-645 / 647-699)    mode 0: sigmoid weights normalised over the valid pairs
+//                       Edge2NodeQKVAttnLayer (:432-502 / 504-558) mode 1: softmax(q_i.k_j * scale + edge bias)
+//                       out[i,h,:] = sum_j w_ij (edge_val[pair(i,j),h,:] + node_val[j,h,:]);  one CTA per node walks its
+//                       N-1 pairs once.  The reference sorts / pads every pair list to [B,H,N,N-1,*] tensors (full form) or
+//                       gathers top-k neighbour lists (sparse form, one .item() sync per layer); both forms reduce to this.
+//   cnf_pair_combine    Node2EdgePlainLayer (:317-336): out[r] = GELU(edge_lin[r] + node_lin[a(r)] + node_lin[b(r)])
+// =====================================================================================================================
+namespace cnf {
+namespace {
+
+struct EdgeAggParams {
+    const long long* rev;        // [B*P]
+    const float* node_val;       // [B*N, >= H*Dh] pitch ld_nv : context features (mode 0) / values (mode 1)
+    const float* node_q;         // mode 1: queries [B*N, >= H*Dh] pitch ld_q
+    const float* node_k;         // mode 1: keys, pitch ld_k
+    const float* edge_val;       // [R, >= H*Dh] pitch ld_ev
+    const float* edge_logit;     // [R, >= H] pitch ld_el
+    float* out;                  // [B*N, H*Dh]
+    long long ld_nv, ld_q, ld_k, ld_ev, ld_el;
+    int N, P, H, Dh, mode, vec;
+    float scale;
+};
+
+__device__ __forceinline__ int pair_index(int a, int b, int N) { return a * (N - 1) - (a * (a - 1)) / 2 + (b - a - 1); }
+
+__global__ void __launch_bounds__(kAggThreads) edge_aggregate_kernel(const EdgeAggParams p) {
+    extern __shared__ unsigned char eagg_smem[];
+    int* nb_node = reinterpret_cast<int*>(eagg_smem);          // [N]
+    int* nb_row = nb_node + p.N;                                 // [N] compact edge row
+    float* wgt = reinterpret_cast<float*>(nb_row + p.N);         // [H][N]
+    __shared__ int s_cnt;
+    const long long node = blockIdx.x;
+    const long long b = node / p.N;
+    const int i = (int)(node - b * p.N);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int HD = p.H * p.Dh;
+
+    if (warp == 0) {
+        const long long* rev = p.rev + b * p.P;
+        int cnt = 0;
+        for (int j0 = 0; j0 < p.N; j0 += 32) {
+            const int j = j0 + lane;
+            long long r = 0;
+            if (j < p.N && j != i) r = rev[j < i ? pair_index(j, i, p.N) : pair_index(i, j, p.N)];
+            const bool valid = r > 0;
+            const unsigned m = __ballot_sync(0xffffffffu, valid);
+            if (valid) {
+                const int pos = cnt + __popc(m & ((1u << lane) - 1u));
+                nb_node[pos] = j;
+                nb_row[pos] = (int)(r - 1);
+            }
+            cnt += __popc(m);
+        }
+        if (lane == 0) s_cnt = cnt;
+    }
+    __syncthreads();
+    const int cnt = s_cnt;
+
+    if (p.mode == 1) {
+        // logits: warp per (neighbour, head) dot product q_i . k_j
+        for (int w = warp; w < cnt * p.H; w += kAggThreads / 32) {
+            const int n = w / p.H, h = w - n * p.H;
+            const float* q = p.node_q + node * p.ld_q + h * p.Dh;
+            const float* k = p.node_k + (b * p.N + nb_node[n]) * p.ld_k + h * p.Dh;
+            float acc = 0.f;
+            for (int d = lane; d < p.Dh; d += 32) acc = fmaf(q[d], k[d], acc);
+            acc = warp_sum(acc);
+            if (lane == 0) wgt[h * p.N + n] = fmaf(acc, p.scale, p.edge_logit[(long long)nb_row[n] * p.ld_el + h]);
+        }
+        __syncthreads();
+        for (int h = warp; h < p.H; h += kAggThreads / 32) {
+            float mx = -3.0e38f;
+            for (int n = lane; n < cnt; n += 32) mx = fmaxf(mx, wgt[h * p.N + n]);
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+            float sum = 0.f;
+            for (int n = lane; n < cnt; n += 32) {
+                const float e = __expf(wgt[h * p.N + n] - mx);
+                wgt[h * p.N + n] = e;
+                sum += e;
+            }
+            sum = warp_sum(sum);
+            const float inv = cnt > 0 ? 1.0f / sum : 0.f;
+            for (int n = lane; n < cnt; n += 32) wgt[h * p.N + n] *= inv;
+        }
+    } else {
+        for (int h = warp; h < p.H; h += kAggThreads / 32) {
+            float sum = 0.f;
+            for (int n = lane; n < cnt; n += 32) {
+                const float s = 1.0f / (1.0f + __expf(-p.edge_logit[(long long)nb_row[n] * p.ld_el + h]));
+                wgt[h * p.N + n] = s;
+                sum += s;
+            }
+            sum = warp_sum(sum);
+            const float inv = 1.0f / fmaxf(sum, 1e-5f);                                  // :629 / :688
+            for (int n = lane; n < cnt; n += 32) wgt[h * p.N + n] *= inv;
+        }
+    }
+    __syncthreads();
+
+    float* out = p.out + node * HD;
+    if (p.vec) {
+        for (int f = threadIdx.x * 4; f < HD; f += kAggThreads * 4) {
+            const int h = f / p.Dh;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int n = 0; n < cnt; ++n) {
+                const float w = wgt[h * p.N + n];
+                const float4 e = *reinterpret_cast<const float4*>(p.edge_val + (long long)nb_row[n] * p.ld_ev + f);
+                const float4 v = *reinterpret_cast<const float4*>(p.node_val + (b * p.N + nb_node[n]) * p.ld_nv + f);
+                acc.x = fmaf(w, e.x + v.x, acc.x); acc.y = fmaf(w, e.y + v.y, acc.y);
+                acc.z = fmaf(w, e.z + v.z, acc.z); acc.w = fmaf(w, e.w + v.w, acc.w);
+            }
+            *reinterpret_cast<float4*>(out + f) = acc;
+        }
+    } else {
+        for (int f = threadIdx.x; f < HD; f += kAggThreads) {
+            const int h = f / p.Dh;
+            float acc = 0.f;
+            for (int n = 0; n < cnt; ++n)
+                acc = fmaf(wgt[h * p.N + n], p.edge_val[(long long)nb_row[n] * p.ld_ev + f] + p.node_val[(b * p.N + nb_node[n]) * p.ld_nv + f], acc);
+            out[f] = acc;
+        }
+    }
+}
+
+struct PairCombineParams {
+    const long long* flat;       // [R] = b*P + p
+    const long long* idx1; const long long* idx2;   // [P] node indices of pair p
+    const float* edge_lin;       // [R, He] pitch ld_e
+    const float* node_lin;       // [B*N, He] pitch ld_n
+    float* out;                  // [R, He]
+    long long R, ld_e, ld_n;
+    int N, P, He, act;
+};
+
+__global__ void __launch_bounds__(256) pair_combine_kernel(const PairCombineParams p) {
+    const int lane = threadIdx.x & 31;
+    const long long nwarps = (long long)gridDim.x * 8;
+    for (long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); r < p.R; r += nwarps) {
+        const long long fp = p.flat[r];
+        const long long b = fp / p.P;
+        const int pr = (int)(fp - b * p.P);
+        const float* n1 = p.node_lin + (b * p.N + p.idx1[pr]) * p.ld_n;
+        const float* n2 = p.node_lin + (b * p.N + p.idx2[pr]) * p.ld_n;
+        const float* e = p.edge_lin + r * p.ld_e;
+        float* o = p.out + r * p.He;
+        for (int c = lane; c < p.He; c += 32) {
+            float v = e[c] + (n1[c] + n2[c]);
+            if (p.act == 1) v = gelu_erf(v);
+            o[c] = v;
+        }
+    }
+}
+
+}  // namespace
+}  // namespace cnf
+
+extern "C" int cnf_edge_aggregate(const cnf_edge_aggregate_args* a, cnf_stream_t stream_) {
+    using namespace cnf;
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    CNF_REQUIRE(a != nullptr, "cnf_edge_aggregate: null args");
+    CNF_REQUIRE(a->B >= 0 && a->N >= 2 && a->H >= 1 && a->Dh >= 1, "cnf_edge_aggregate: bad shape");
+    CNF_REQUIRE(a->mode == 0 || a->mode == 1, "cnf_edge_aggregate: mode must be 0 (sigmoid) or 1 (query-key softmax)");
+    if (a->B == 0) return CNF_OK;
+    CNF_REQUIRE(a->rev && a->node_val && a->out, "cnf_edge_aggregate: null tensor");
+    CNF_REQUIRE(a->R == 0 || (a->edge_val && a->edge_logit), "cnf_edge_aggregate: null edge tensor");
+    if (a->mode == 1) CNF_REQUIRE(a->node_q && a->node_k, "cnf_edge_aggregate: mode 1 needs queries and keys");
+    CNF_SUPPORTED(a->H <= kMaxHeads && a->N <= 2048, "cnf_edge_aggregate: H <= %d, N <= 2048", kMaxHeads);
+    EdgeAggParams p{};
+    p.rev = reinterpret_cast<const long long*>(a->rev);
+    p.node_val = a->node_val; p.node_q = a->node_q; p.node_k = a->node_k; p.edge_val = a->edge_val; p.edge_logit = a->edge_logit;
+    p.out = a->out;
+    p.ld_nv = a->ld_node_val; p.ld_q = a->ld_node_q; p.ld_k = a->ld_node_k; p.ld_ev = a->ld_edge_val; p.ld_el = a->ld_edge_logit;
+    p.N = a->N; p.P = a->N * (a->N - 1) / 2; p.H = a->H; p.Dh = a->Dh; p.mode = a->mode; p.scale = a->scale;
+    uintptr_t bits = reinterpret_cast<uintptr_t>(a->node_val) | reinterpret_cast<uintptr_t>(a->edge_val) | reinterpret_cast<uintptr_t>(a->out);
+    p.vec = ((a->Dh & 3) == 0 && (p.ld_nv & 3) == 0 && (p.ld_ev & 3) == 0 && (bits & 15) == 0) ? 1 : 0;
+    const size_t smem = (size_t)a->N * 8 + (size_t)a->H * a->N * 4;
+    CNF_SUPPORTED(smem <= 48 * 1024, "cnf_edge_aggregate: neighbour list does not fit shared memory");
+    edge_aggregate_kernel<<<(unsigned)(a->B * a->N), kAggThreads, smem, stream>>>(p);
+    return launch_status("edge_aggregate_kernel");
+}
+
+extern "C" int cnf_pair_combine(const cnf_pair_combine_args* a, cnf_stream_t stream_) {
+    using namespace cnf;
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    CNF_REQUIRE(a != nullptr, "cnf_pair_combine: null args");
+    CNF_REQUIRE(a->R >= 0 && a->N >= 2 && a->He >= 1, "cnf_pair_combine: bad shape");
+    if (a->R == 0) return CNF_OK;
+    CNF_REQUIRE(a->flat_indices && a->x_indices1 && a->x_indices2 && a->edge_lin && a->node_lin && a->out, "cnf_pair_combine: null tensor");
+    PairCombineParams p{};
+    p.flat = reinterpret_cast<const long long*>(a->flat_indices);
+    p.idx1 = reinterpret_cast<const long long*>(a->x_indices1);
+    p.idx2 = reinterpret_cast<const long long*>(a->x_indices2);
+    p.edge_lin = a->edge_lin; p.node_lin = a->node_lin; p.out = a->out;
+    p.R = a->R; p.ld_e = a->ld_edge; p.ld_n = a->ld_node; p.N = a->N; p.P = a->N * (a->N - 1) / 2; p.He = a->He; p.act = a->activation;
+    pair_combine_kernel<<<capped_grid((a->R + 7) / 8, 8), 256, 0, stream>>>(p);
+    return launch_status("pair_combine_kernel");
 }

@@ -11,7 +11,8 @@
 //     warp 2      tensor-memory allocation
 //     warps 4-7   epilogue: tcgen05.ld (thread = output row) -> + bias (+ GELU) -> swizzled staging tile in
 //                 shared memory -> TMA store (clips the M / N tails); or guarded direct stores
-//     warps 8-11  (3xTF32 only) split every landed stage in place into hi = tf32(x) and lo = x - hi
+//     warps 8-11  (3xTF32 only) write lo = x - trunc_tf32(x) next to every landed stage (the tensor core truncates
+//                 fp32 operands to TF32 itself, so the landed tile serves as the high part unchanged)
 //
 //   precision 0  one TF32 pass (operands rounded to 10 mantissa bits: ~5e-4 relative per product)
 //   precision 1  3xTF32: x W^T ~= hi hi + lo hi + hi lo, fp32 accumulation in tensor memory - error ~1e-6,
@@ -59,11 +60,7 @@ __device__ __forceinline__ TileCoord tile_coord(const LinearParams& p, long long
     return c;
 }
 
-__device__ __forceinline__ float rna_tf32(float v) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
-    return __uint_as_float(r);
-}
+__device__ __forceinline__ float trunc_tf32(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
 __device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f)); }
 
 template <bool STRICT>
@@ -255,8 +252,11 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         }
         if (p.store == 1 && lane == 0) tma_store_wait<0>();
     } else if (STRICT && warp >= 8) {
-        // ---------------- 3xTF32 split: hi = tf32(x) (in place), lo = tf32(x - hi), both round-to-nearest
-        // so that whatever the tensor core does with the low 13 mantissa bits, they are zero -------------
+        // ---------------- 3xTF32 split.  tcgen05 kind::tf32 TRUNCATES the 13 low mantissa bits of its fp32 operands
+        // (measured: tools/tf32_probe.py), so the landed tile already is the high part as far as the tensor core is
+        // concerned; only lo = x - trunc(x) (exact, same sign as x) has to be written.  The dropped terms (lo*lo and
+        // the truncation of lo itself) are positive multiples <= 2^-20 of each product: a ~5e-7 relative scaling of the
+        // result, not a random walk -------------------------------------------------------------------------------
         const int tt = threadIdx.x - 256;
         const int n4 = half_bytes >> 4;
         int stage = 0;
@@ -265,14 +265,12 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
             const TileCoord tc = tile_coord(p, t);
             for (int kb = tc.kb0; kb < tc.kb1; ++kb) {
                 mbar_wait(&full[stage], phase);
-                float4* hi = reinterpret_cast<float4*>(smem + stage * stage_bytes);
+                const float4* hi = reinterpret_cast<const float4*>(smem + stage * stage_bytes);
                 float4* lo = reinterpret_cast<float4*>(smem + stage * stage_bytes + half_bytes);
                 for (int i = tt; i < n4; i += 128) {
                     const float4 x = hi[i];
-                    float4 h, l;
-                    h.x = rna_tf32(x.x); h.y = rna_tf32(x.y); h.z = rna_tf32(x.z); h.w = rna_tf32(x.w);
-                    l.x = rna_tf32(x.x - h.x); l.y = rna_tf32(x.y - h.y); l.z = rna_tf32(x.z - h.z); l.w = rna_tf32(x.w - h.w);
-                    hi[i] = h;
+                    float4 l;
+                    l.x = x.x - trunc_tf32(x.x); l.y = x.y - trunc_tf32(x.y); l.z = x.z - trunc_tf32(x.z); l.w = x.w - trunc_tf32(x.w);
                     lo[i] = l;
                 }
                 fence_proxy_async_smem();

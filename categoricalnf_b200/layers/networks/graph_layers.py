@@ -58,18 +58,35 @@ def _edge_types(adjacency, num_edges):
 
 
 class _FusedPair:
-    """hs / hr projections of one layer as a single GEMM: concatenated weight and bias, rebuilt when a parameter changes."""
+    """hs / hr projections of one layer as a single GEMM: concatenated weight and bias, rebuilt when a parameter changes.
+    With ``attn_weight`` the attention logits ride along as extra output columns - they are linear in the projection
+    input: hs_i . a_0 = x_i (W_hs^T a_0) + b_hs . a_0 (graph_layers.py:93-96) - so no separate pass reads hs / hr again.
+    Column layout: [hs | hr | score_s (H) | score_r ((E+1) H) | zero padding to a multiple of 4]."""
 
     def __init__(self):
         self.key, self.weight, self.bias = None, None, None
 
-    def get(self, a, b):
+    def get(self, a, b, attn_weight=None):
         key = (a.weight.data_ptr(), a.weight._version, a.bias._version, b.weight.data_ptr(), b.weight._version,
-               b.bias._version, a.weight.device)
+               b.bias._version, a.weight.device, None if attn_weight is None else (attn_weight.data_ptr(), attn_weight._version))
         if key != self.key:
             with torch.no_grad():
-                self.weight = torch.cat([a.weight, b.weight], dim=0).contiguous()
-                self.bias = torch.cat([a.bias, b.bias], dim=0).contiguous()
+                ws, bs = [a.weight, b.weight], [a.bias, b.bias]
+                if attn_weight is not None:
+                    H, _, Dh = attn_weight.shape
+                    K = a.weight.shape[1]
+                    aw = attn_weight.double()
+                    ws.append(torch.einsum("hd,hdk->hk", aw[:, 0], a.weight.double().view(H, Dh, K)).float())
+                    bs.append((aw[:, 0] * a.bias.double().view(H, Dh)).sum(-1).float())
+                    E1 = b.weight.shape[0] // (H * Dh)
+                    ws.append(torch.einsum("hd,ehdk->ehk", aw[:, 1], b.weight.double().view(E1, H, Dh, K)).reshape(E1 * H, K).float())
+                    bs.append((aw[:, 1].unsqueeze(0) * b.bias.double().view(E1, H, Dh)).sum(-1).reshape(E1 * H).float())
+                    extra = (-(H + E1 * H)) % 4
+                    if extra:
+                        ws.append(a.weight.new_zeros(extra, K))
+                        bs.append(a.bias.new_zeros(extra))
+                self.weight = torch.cat(ws, dim=0).contiguous()
+                self.bias = torch.cat(bs, dim=0).contiguous()
             self.key = key
         return self.weight, self.bias
 
@@ -137,10 +154,12 @@ class RelationGraphAttention(nn.Module):
         B, N = x.shape[0], x.shape[1]
         width = self.c_out_per_head * self.num_heads
         xn = ops.layernorm(x, self.norm_layer.weight, self.norm_layer.bias, self.norm_layer.eps)
-        w, b = self._pair.get(self.linear_hs, self.linear_hr)
+        w, b = self._pair.get(self.linear_hs, self.linear_hr, self.attn_weight)
         y = ops.linear(xn.reshape(B * N, -1), w, b, precision=PRECISION)
-        att = ops.graph_attention_aggregate(y[:, :width].unflatten(0, (B, N)), y[:, width:].unflatten(0, (B, N)),
-                                            self.attn_weight, adj, self.num_edges,
+        H, wr = self.num_heads, width * (self.num_edges + 1)
+        scores = (y[:, width + wr:width + wr + H], y[:, width + wr + H:width + wr + H + (self.num_edges + 1) * H])
+        att = ops.graph_attention_aggregate(y[:, :width].unflatten(0, (B, N)), y[:, width:width + wr].unflatten(0, (B, N)),
+                                            self.attn_weight, adj, self.num_edges, scores=scores,
                                             leaky_slope=self.leaky_relu.negative_slope, activation="gelu")
         return ops.linear(att, self.output_projection[1].weight, self.output_projection[1].bias, precision=PRECISION,
                           activation=activation)
@@ -252,3 +271,251 @@ class RGCNNet(nn.Module):
         if channel_padding_mask is not None:
             out = out * channel_padding_mask
         return out
+
+
+# =====================================================================================================================
+# Edge-GNN (reference layers/networks/graph_layers.py:242-820): the coupling network of GraphCNF's node+edge flows
+# =====================================================================================================================
+class PairContext:
+    """Index bookkeeping of one batch of node-pair lists, built once per ``mask_valid`` tensor and shared by all layers
+    (and all couplings that receive the same tensor): ``flat_indices`` [R] = b*P + p of the valid pairs
+    (graph_layers.py:339-347), ``rev`` [B,P] = 1 + compact row or 0 (:349-355), the two node rows of every compact pair.
+    Building it costs the one host synchronisation of ``nonzero``; the reference pays one per EdgeGNN call (:802) plus one
+    per sparse layer (:508,:650)."""
+
+    def __init__(self, x_indices, mask_valid, num_nodes):
+        B, P = mask_valid.shape
+        self.B, self.P, self.N = B, P, num_nodes
+        self.x_indices = (x_indices[0].contiguous(), x_indices[1].contiguous())
+        flat_mask = (mask_valid.reshape(-1) == 1.0)
+        self.flat_indices = torch.nonzero(flat_mask).reshape(-1)
+        fm = flat_mask.long()
+        self.rev = (fm * fm.cumsum(dim=0)).reshape(B, P)
+        graph = torch.div(self.flat_indices, P, rounding_mode="floor")
+        pair = self.flat_indices - graph * P
+        self.node1 = graph * num_nodes + self.x_indices[0][pair]      # rows into [B*N, *]
+        self.node2 = graph * num_nodes + self.x_indices[1][pair]
+        self.R = int(self.flat_indices.numel())
+
+    @staticmethod
+    def of(x_indices, mask_valid, num_nodes):
+        ctx = getattr(mask_valid, "_cnf_pair_ctx", None)
+        key = (mask_valid._version, num_nodes)
+        if ctx is None or ctx[0] != key:
+            ctx = (key, PairContext(x_indices, mask_valid, num_nodes))
+            mask_valid._cnf_pair_ctx = ctx
+        return ctx[1]
+
+    def compact(self, edge_feat):
+        return edge_feat.reshape(self.B * self.P, -1).index_select(0, self.flat_indices)
+
+    def expand(self, edge_rows):
+        out = edge_rows.new_zeros(self.B * self.P, edge_rows.shape[-1])
+        return out.index_copy(0, self.flat_indices, edge_rows).reshape(self.B, self.P, -1)
+
+
+def _edge_to_node_dense(ctx, node_val, edge_val, edge_logit, H, mode, q=None, k=None, scale=1.0):
+    """Differentiable form of ``cnf_edge_aggregate``: every valid pair sends one message in each direction."""
+    BN, HD = node_val.shape
+    Dh = HD // H
+    dst = torch.cat([ctx.node1, ctx.node2])
+    src = torch.cat([ctx.node2, ctx.node1])
+    ev = torch.cat([edge_val, edge_val], dim=0)
+    lg = torch.cat([edge_logit, edge_logit], dim=0)                              # [2R,H]
+    if mode == "qkv":
+        lg = lg + (q[dst].view(-1, H, Dh) * k[src].view(-1, H, Dh)).sum(-1) * scale
+        mx = lg.new_full((BN, H), -3.0e38).scatter_reduce(0, dst.unsqueeze(-1).expand(-1, H), lg, reduce="amax")
+        w = torch.exp(lg - mx[dst])
+        denom = lg.new_zeros(BN, H).index_add(0, dst, w)
+        w = w / denom[dst]
+    else:
+        w = torch.sigmoid(lg)
+        denom = lg.new_zeros(BN, H).index_add(0, dst, w)
+        w = w / denom[dst].clamp(min=1e-5)
+    msg = (ev + node_val[src]).view(-1, H, Dh) * w.unsqueeze(-1)
+    return node_val.new_zeros(BN, H, Dh).index_add(0, dst, msg).view(BN, HD)
+
+
+class EdgeGNNLayer(nn.Module):
+    """Node update from the incident edges, then edge update from the two end nodes (graph_layers.py:242-262)."""
+
+    def __init__(self, edge2node_layer_func, node2edge_layer_func):
+        super().__init__()
+        self.node2edge_layer = node2edge_layer_func()
+        self.edge2node_layer = edge2node_layer_func()
+
+    def forward(self, node_feat, edge_feat, x_indices, mask_valid, **kwargs):
+        """Reference calling convention: ``edge_feat`` [B,P,He] over all pairs, invalid pairs come back zeroed."""
+        ctx = PairContext.of(x_indices, mask_valid, node_feat.size(1))
+        node_feat, edge_rows = self.forward_compact(node_feat, ctx.compact(edge_feat), ctx)
+        return node_feat, ctx.expand(edge_rows)
+
+    def forward_compact(self, node_feat, edge_rows, ctx):
+        node_feat = self.edge2node_layer.forward_compact(node_feat, edge_rows, ctx)
+        edge_rows = self.node2edge_layer.forward_compact(node_feat, edge_rows, ctx)
+        return node_feat, edge_rows
+
+    @staticmethod
+    def _get_sort_indices(x_indices):
+        return torch.cat([x_indices[0], x_indices[1]], dim=0).sort(0, descending=False)[1]
+
+    @staticmethod
+    def _get_node_feat_by_indices(node_feat, x_indices, dim=1):
+        return node_feat.index_select(index=x_indices[0], dim=dim), node_feat.index_select(index=x_indices[1], dim=dim)
+
+
+class _EdgeLayerBase(nn.Module):
+
+    def forward(self, node_feat, edge_feat, x_indices, mask_valid, **kwargs):
+        ctx = PairContext.of(x_indices, mask_valid, node_feat.size(1))
+        res = self.forward_compact(node_feat, ctx.compact(edge_feat), ctx)
+        return ctx.expand(res) if self._returns_edges else res
+
+
+class Node2EdgePlainLayer(_EdgeLayerBase):
+    """edge <- skip(edge, GELU(W_e LN(edge) + W_n LN(node_a) + W_n LN(node_b)))   (graph_layers.py:297-336)."""
+    _returns_edges = True
+
+    def __init__(self, hidden_size_nodes, hidden_size_edges, skip_config=0, dp_rate=0.0, act_fn=nn.GELU):
+        super().__init__()
+        self.hidden_size_nodes, self.hidden_size_edges = hidden_size_nodes, hidden_size_edges
+        self.skip_layer = GNNSkipConnection(hidden_size_edges, config=skip_config, dp_rate=dp_rate)
+        self.dropout = nn.Dropout(dp_rate)
+        self.act_fn = act_fn()
+        self.node_feat_layer = nn.Sequential(nn.LayerNorm(hidden_size_nodes), TCLinear(hidden_size_nodes, hidden_size_edges))
+        self.edge_feat_layer = nn.Sequential(nn.LayerNorm(hidden_size_edges), TCLinear(hidden_size_edges, hidden_size_edges))
+
+    def forward_compact(self, node_feat, edge_rows, ctx):
+        B, N = node_feat.shape[0], node_feat.shape[1]
+        node_lin = _linear(_layernorm(self.dropout(node_feat), self.node_feat_layer[0]), self.node_feat_layer[1]).reshape(B * N, -1)
+        edge_lin = _linear(_layernorm(self.dropout(edge_rows), self.edge_feat_layer[0]), self.edge_feat_layer[1])
+        if _grad_mode(node_lin, edge_lin) or (self.training and self.dropout.p > 0):
+            comb = self.act_fn(self.dropout(edge_lin + node_lin[ctx.node1] + node_lin[ctx.node2]))
+        else:
+            comb = ops.pair_combine(ctx.flat_indices, ctx.x_indices, edge_lin, node_lin, N, activation="gelu")
+        return self.skip_layer(orig=edge_rows, feat=comb)
+
+
+class Edge2NodeQKVAttnLayer(_EdgeLayerBase):
+    """Transformer-style node update: queries / keys / values from the nodes, value offset and logit bias from the edge
+    between them (graph_layers.py:388-558; its dense and sparse forward passes compute the same function)."""
+    _returns_edges = False
+
+    def __init__(self, hidden_size_nodes, hidden_size_edges, num_heads=4, dp_rate=0.0, act_fn=nn.GELU, skip_config=2):
+        super().__init__()
+        self.hidden_size_nodes, self.hidden_size_edges, self.num_heads = hidden_size_nodes, hidden_size_edges, num_heads
+        self.hidden_size_per_head = self.hidden_size_nodes // self.num_heads
+        self.dot_prod_scaling = float(self.hidden_size_per_head) ** -0.5
+        width = self.num_heads * self.hidden_size_per_head
+        self.node_query_key_val_layer = TCLinear(hidden_size_nodes, width * 3)
+        self.edge_val_layer = TCLinear(hidden_size_edges, width)
+        self.edge_adj_layer = TCLinear(hidden_size_edges, self.num_heads)
+        self.output_projection = TCLinear(width + self.hidden_size_nodes, self.hidden_size_nodes)
+        self.skip_layer = GNNSkipConnection(hidden_size_nodes, config=skip_config, input_size=self.hidden_size_nodes, dp_rate=dp_rate)
+        self.dropout = nn.Dropout(dp_rate)
+        self.act_fn = act_fn()
+        self.node_normalization = nn.LayerNorm(hidden_size_nodes)
+        self.edge_normalization = nn.LayerNorm(hidden_size_edges)
+
+    def forward_compact(self, node_feat, edge_rows, ctx):
+        B, N = node_feat.shape[0], node_feat.shape[1]
+        H, width = self.num_heads, self.num_heads * self.hidden_size_per_head
+        node_in = _layernorm(node_feat, self.node_normalization)
+        edge_in = _layernorm(edge_rows, self.edge_normalization)
+        qkv = _linear(self.dropout(node_in), self.node_query_key_val_layer).reshape(B * N, 3 * width)
+        q, k, v = qkv[:, :width], qkv[:, width:2 * width], qkv[:, 2 * width:]
+        edge_val = _linear(edge_in, self.edge_val_layer)
+        edge_adj = _linear(edge_in, self.edge_adj_layer)
+        if _grad_mode(qkv, edge_val, edge_adj):
+            att = _edge_to_node_dense(ctx, v, edge_val, edge_adj, H, "qkv", q, k, self.dot_prod_scaling)
+        else:
+            att = ops.edge_aggregate(ctx.rev, v, edge_val, edge_adj, H, mode="qkv", node_q=q, node_k=k, scale=self.dot_prod_scaling)
+        cat = torch.cat([node_in, att.reshape(B, N, width)], dim=-1)
+        if self.training and self.dropout.p > 0:
+            comb = self.act_fn(self.dropout(_linear(cat, self.output_projection)))
+        else:
+            comb = _linear(cat, self.output_projection, activation="gelu")
+        return self.skip_layer(orig=node_feat, feat=comb)
+
+
+class Edge2NodeAttnLayer(_EdgeLayerBase):
+    """Node update with sigmoid attention driven purely by the edges (graph_layers.py:561-699)."""
+    _returns_edges = False
+
+    def __init__(self, hidden_size_nodes, hidden_size_edges, skip_config=2, num_heads=4, dp_rate=0.0, act_fn=nn.GELU):
+        super().__init__()
+        self.hidden_size_nodes, self.hidden_size_edges, self.num_heads = hidden_size_nodes, hidden_size_edges, num_heads
+        self.hidden_size_per_head = int(self.hidden_size_nodes // self.num_heads)
+        self.hidden_size_output = self.hidden_size_per_head * self.num_heads
+        self.node_feat_layer = TCLinear(hidden_size_nodes, self.hidden_size_output * 2)
+        self.edge_feat_layer = TCLinear(hidden_size_edges, self.hidden_size_output)
+        self.edge_logits_layer = TCLinear(hidden_size_edges, self.num_heads)
+        self.skip_layer = GNNSkipConnection(hidden_size_nodes, config=skip_config, input_size=self.hidden_size_output)
+        self.dropout = nn.Dropout(dp_rate)
+        self.act_fn = act_fn()
+        self.node_normalization = nn.LayerNorm(hidden_size_nodes)
+        self.edge_normalization = nn.LayerNorm(hidden_size_edges)
+
+    def forward_compact(self, node_feat, edge_rows, ctx):
+        B, N = node_feat.shape[0], node_feat.shape[1]
+        HO = self.hidden_size_output
+        node_new = _linear(_layernorm(node_feat, self.node_normalization), self.node_feat_layer).reshape(B * N, 2 * HO)
+        node_self, node_ctx = node_new[:, :HO], node_new[:, HO:]
+        edge_in = _layernorm(edge_rows, self.edge_normalization)
+        edge_new = _linear(edge_in, self.edge_feat_layer)
+        edge_logits = _linear(edge_in, self.edge_logits_layer)
+        if _grad_mode(node_new, edge_new, edge_logits):
+            att = _edge_to_node_dense(ctx, node_ctx, edge_new, edge_logits, self.num_heads, "sigmoid")
+        else:
+            att = ops.edge_aggregate(ctx.rev, node_ctx, edge_new, edge_logits, self.num_heads, mode="sigmoid")
+        comb = self.act_fn(self.dropout(node_self + att)).reshape(B, N, HO)
+        return self.skip_layer(orig=node_feat, feat=comb)
+
+
+class EdgeGNN(nn.Module):
+    """Input MLPs, ``num_layers`` Edge-GNN layers, output MLPs for nodes and edges (graph_layers.py:737-820).  Edge features
+    live as compact rows of the valid pairs from the input MLP to the output MLP; only the final edge output is scattered
+    back to [B,P,c_out_edges] (zeros at invalid pairs, as upstream :812-813)."""
+
+    def __init__(self, c_in_nodes, c_in_edges, c_out_nodes, c_out_edges, edge_gnn_layer_func, num_layers=4, max_neighbours=-1):
+        super().__init__()
+        self.c_in_nodes, self.c_in_edges, self.c_out_nodes, self.c_out_edges = c_in_nodes, c_in_edges, c_out_nodes, c_out_edges
+        self.layers = nn.ModuleList([edge_gnn_layer_func() for _ in range(num_layers)])
+        hidden_size_edges = self.layers[0].node2edge_layer.hidden_size_edges
+        hidden_size_nodes = self.layers[0].node2edge_layer.hidden_size_nodes
+        self.input_layer_edges = self._create_input_network(c_in_edges, hidden_size_edges)
+        self.input_layer_nodes = self._create_input_network(c_in_nodes, hidden_size_nodes)
+        self.out_layer_edges = self._create_output_network(hidden_size_edges, c_out_edges)
+        self.out_layer_nodes = self._create_output_network(hidden_size_nodes, c_out_nodes)
+        if max_neighbours > 0:
+            self.max_neighbours = max_neighbours
+            self.node_neighbour_embed = TCLinear(max_neighbours + 1, hidden_size_nodes)
+
+    def _create_input_network(self, c_in, hidden_size):
+        return nn.Sequential(TCLinear(c_in, hidden_size), nn.GELU(), TCLinear(hidden_size, hidden_size))
+
+    def _create_output_network(self, hidden_size, c_out):
+        return nn.Sequential(nn.LayerNorm(hidden_size), TCLinear(hidden_size, hidden_size), nn.GELU(), TCLinear(hidden_size, c_out))
+
+    @staticmethod
+    def _mlp_in(net, x):
+        return _linear(_linear(x, net[0], activation="gelu"), net[2])
+
+    @staticmethod
+    def _mlp_out(net, x):
+        return _linear(_linear(_layernorm(x, net[0]), net[1], activation="gelu"), net[3])
+
+    def forward(self, z_nodes, z_edges, length, x_indices, mask_valid, channel_padding_mask=None, binary_adjacency=None, **kwargs):
+        ctx = PairContext.of(x_indices, mask_valid, z_nodes.size(1))
+        nodes_feat = self._mlp_in(self.input_layer_nodes, z_nodes)
+        edge_rows = self._mlp_in(self.input_layer_edges, ctx.compact(z_edges))
+        if binary_adjacency is not None and hasattr(self, "node_neighbour_embed"):
+            num_neighbours = binary_adjacency.sum(dim=-1).long().clamp(max=self.max_neighbours)
+            nodes_feat = nodes_feat + F.embedding(num_neighbours, self.node_neighbour_embed.weight.t()) + self.node_neighbour_embed.bias
+        for layer in self.layers:
+            nodes_feat, edge_rows = layer.forward_compact(nodes_feat, edge_rows, ctx)
+        nodes_out = self._mlp_out(self.out_layer_nodes, nodes_feat)
+        edges_out = ctx.expand(self._mlp_out(self.out_layer_edges, edge_rows))
+        if channel_padding_mask is not None:
+            nodes_out = nodes_out * channel_padding_mask
+        return nodes_out, edges_out

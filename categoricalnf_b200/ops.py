@@ -613,32 +613,41 @@ def _rows(t, name, B, N):
     return t, t.shape[-1]
 
 
-def graph_attention_aggregate(hs, hr, attn_weight, adjacency, num_edges, *, leaky_slope=0.2, activation=None):
+def graph_attention_aggregate(hs, hr, attn_weight, adjacency, num_edges, *, leaky_slope=0.2, activation=None, scores=None):
     """RelationGraphAttention core (graph_layers.py:92-151): ``hs`` [B,N,H*Dh], ``hr`` [B,N,(E+1)*H*Dh] (either may be a
     column slice of one wider projection output), ``attn_weight`` [H,2,Dh], ``adjacency`` [B,N,N] integer edge types
-    (0 = none).  Returns the attention output [B,N,H*Dh] (GELU applied when ``activation="gelu"``)."""
+    (0 = none).  Returns the attention output [B,N,H*Dh] (GELU applied when ``activation="gelu"``).
+    ``scores = (score_s [B*N,H], score_r [B*N,(E+1)*H])`` (column slices allowed) skips ``cnf_graph_attn_scores`` - the
+    logits are linear in the projection input, so the caller may have produced them as extra projection columns."""
     B, N = hs.shape[0], hs.shape[1]
     H, _, Dh = attn_weight.shape
     E = int(num_edges)
-    aw = _f32(attn_weight, "attn_weight")
     adjacency = _adjacency(adjacency, B, N)
     hs_t, ld_hs = _rows(hs, "hs", B, N)
     hr_t, ld_hr = _rows(hr, "hr", B, N)
     if hs.shape[-1] != H * Dh or hr.shape[-1] != (E + 1) * H * Dh:
         raise ValueError("hs / hr have %d / %d features, expected %d / %d" % (hs.shape[-1], hr.shape[-1], H * Dh, (E + 1) * H * Dh))
     dev = hs.device
-    score_s = torch.empty(B * N, H, dtype=torch.float32, device=dev)
-    score_r = torch.empty(B * N, (E + 1) * H, dtype=torch.float32, device=dev)
-    a = L.GraphAttnScoresArgs()
-    a.M, a.E, a.H, a.Dh = B * N, E, H, Dh
-    a.hs, a.hr, a.ld_hs, a.ld_hr = _ptr(hs_t), _ptr(hr_t), ld_hs, ld_hr
-    a.attn_weight, a.score_s, a.score_r = _ptr(aw), _ptr(score_s), _ptr(score_r)
-    _call("cnf_graph_attn_scores", a, hs_t, (hs_t, hr_t, aw))
+    if scores is None:
+        aw = _f32(attn_weight, "attn_weight")
+        score_s = torch.empty(B * N, H, dtype=torch.float32, device=dev)
+        score_r = torch.empty(B * N, (E + 1) * H, dtype=torch.float32, device=dev)
+        a = L.GraphAttnScoresArgs()
+        a.M, a.E, a.H, a.Dh = B * N, E, H, Dh
+        a.hs, a.hr, a.ld_hs, a.ld_hr = _ptr(hs_t), _ptr(hr_t), ld_hs, ld_hr
+        a.attn_weight, a.score_s, a.score_r = _ptr(aw), _ptr(score_s), _ptr(score_r)
+        _call("cnf_graph_attn_scores", a, hs_t, (hs_t, hr_t, aw))
+        ld_ss, ld_sr = H, (E + 1) * H
+    else:
+        score_s, ld_ss = _rows(scores[0], "score_s", B, N)
+        score_r, ld_sr = _rows(scores[1], "score_r", B, N)
+        if scores[0].shape[-1] != H or scores[1].shape[-1] != (E + 1) * H:
+            raise ValueError("scores have %d / %d columns, expected %d / %d" % (scores[0].shape[-1], scores[1].shape[-1], H, (E + 1) * H))
     out = torch.empty(B, N, H * Dh, dtype=torch.float32, device=dev)
     g = L.GraphAggregateArgs()
     g.B, g.N, g.E, g.H, g.Dh = B, N, E, H, Dh
     g.adjacency, g.hs, g.hr, g.ld_hs, g.ld_hr = _ptr(adjacency), None, _ptr(hr_t), ld_hs, ld_hr
-    g.score_s, g.score_r, g.num_neighbours = _ptr(score_s), _ptr(score_r), None
+    g.score_s, g.score_r, g.ld_score_s, g.ld_score_r, g.num_neighbours = _ptr(score_s), _ptr(score_r), ld_ss, ld_sr, None
     g.mode, g.leaky_slope, g.activation, g.out = 1, float(leaky_slope), ACTIVATION[activation], _ptr(out)
     _call("cnf_graph_aggregate", g, hs_t, (adjacency, hr_t, score_s, score_r))
     return out
@@ -659,7 +668,7 @@ def graph_mean_aggregate(hs, hr, adjacency, num_edges, num_neighbours=None, *, a
     g = L.GraphAggregateArgs()
     g.B, g.N, g.E, g.H, g.Dh = B, N, E, 1, Cc
     g.adjacency, g.hs, g.hr, g.ld_hs, g.ld_hr = _ptr(adjacency), _ptr(hs_t), _ptr(hr_t), ld_hs, ld_hr
-    g.score_s, g.score_r, g.num_neighbours = None, None, _ptr(nn_t)
+    g.score_s, g.score_r, g.ld_score_s, g.ld_score_r, g.num_neighbours = None, None, 0, 0, _ptr(nn_t)
     g.mode, g.leaky_slope, g.activation, g.out = 0, 0.0, ACTIVATION[activation], _ptr(out)
     _call("cnf_graph_aggregate", g, hs_t, (adjacency, hs_t, hr_t, nn_t))
     return out
@@ -675,4 +684,72 @@ def skip_gate(orig, skip, config):
     a.M, a.H, a.config = orig.numel() // H, H, int(config)
     a.orig, a.skip, a.out = _ptr(orig), _ptr(skip), _ptr(out)
     _call("cnf_skip_gate", a, orig, (orig, skip))
+    return out
+
+
+def _rows2(t, name):
+    """2-D feature rows, possibly a column slice of a wider row-major matrix -> (tensor, pitch)."""
+    if not t.is_cuda:
+        raise RuntimeError("categoricalnf_b200: %s lives on %s - CUDA only" % (name, t.device))
+    if t.dtype != torch.float32:
+        t = t.float()
+    if t.dim() != 2:
+        t = t.reshape(-1, t.shape[-1])
+    if t.stride(1) != 1 or (t.shape[0] > 1 and t.stride(0) < t.shape[1]):
+        t = t.contiguous()
+    return t, (t.stride(0) if t.shape[0] > 1 else t.shape[1])
+
+
+def edge_aggregate(rev, node_val, edge_val, edge_logit, num_heads, *, mode="sigmoid", node_q=None, node_k=None, scale=1.0):
+    """Edge -> node attention of the Edge-GNN (``cnf_edge_aggregate``).  ``rev`` [B,P] int64 (1 + compact row of the pair,
+    0 = invalid), ``node_val`` [B*N, H*Dh], ``edge_val`` [R, H*Dh], ``edge_logit`` [R, H] (column slices allowed);
+    ``mode="qkv"`` additionally takes ``node_q`` / ``node_k`` [B*N, H*Dh].  Returns [B*N, H*Dh]."""
+    B, P = rev.shape
+    N = int(round((1 + (1 + 8 * P) ** 0.5) / 2))
+    if N * (N - 1) // 2 != P:
+        raise ValueError("rev has %d pair columns, not N(N-1)/2" % P)
+    H = int(num_heads)
+    HD = node_val.shape[-1]
+    Dh = HD // H
+    rev = rev.contiguous()
+    nv, ld_nv = _rows2(node_val, "node_val")
+    ev, ld_ev = _rows2(edge_val, "edge_val")
+    el, ld_el = _rows2(edge_logit, "edge_logit")
+    if nv.shape[0] != B * N or ev.shape[-1] != HD or el.shape[-1] != H:
+        raise ValueError("edge_aggregate: inconsistent shapes")
+    a = L.EdgeAggregateArgs()
+    a.B, a.N, a.H, a.Dh, a.R = B, N, H, Dh, ev.shape[0]
+    keep = [rev, nv, ev, el]
+    a.rev, a.node_val, a.edge_val, a.edge_logit = _ptr(rev), _ptr(nv), _ptr(ev), _ptr(el)
+    a.ld_node_val, a.ld_edge_val, a.ld_edge_logit = ld_nv, ld_ev, ld_el
+    if mode == "qkv":
+        q, ld_q = _rows2(node_q, "node_q")
+        k, ld_k = _rows2(node_k, "node_k")
+        keep += [q, k]
+        a.node_q, a.node_k, a.ld_node_q, a.ld_node_k, a.mode = _ptr(q), _ptr(k), ld_q, ld_k, 1
+    else:
+        a.mode = 0
+    a.scale = float(scale)
+    out = torch.empty(B * N, HD, dtype=torch.float32, device=nv.device)
+    a.out = _ptr(out)
+    _call("cnf_edge_aggregate", a, nv, keep)
+    return out
+
+
+def pair_combine(flat_indices, x_indices, edge_lin, node_lin, num_nodes, *, activation="gelu"):
+    """Node -> edge message of the Edge-GNN (``cnf_pair_combine``): ``act(edge_lin[r] + node_lin[b,x1[p]] + node_lin[b,x2[p]])``
+    for every compact pair row r (``flat_indices[r] = b*P + p``)."""
+    el, ld_e = _rows2(edge_lin, "edge_lin")
+    nl, ld_n = _rows2(node_lin, "node_lin")
+    x1, x2 = x_indices[0].contiguous(), x_indices[1].contiguous()
+    flat_indices = flat_indices.contiguous()
+    He = el.shape[-1]
+    out = torch.empty(el.shape[0], He, dtype=torch.float32, device=el.device)
+    a = L.PairCombineArgs()
+    a.R, a.N, a.He = el.shape[0], int(num_nodes), He
+    a.flat_indices, a.x_indices1, a.x_indices2 = _ptr(flat_indices), _ptr(x1), _ptr(x2)
+    a.edge_lin, a.node_lin, a.ld_edge, a.ld_node = _ptr(el), _ptr(nl), ld_e, ld_n
+    a.activation, a.out = ACTIVATION[activation], _ptr(out)
+    if el.shape[0] > 0:
+        _call("cnf_pair_combine", a, nl, (flat_indices, x1, x2, el, nl))
     return out

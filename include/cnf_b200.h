@@ -423,8 +423,10 @@ typedef struct {
     const float* hs;              /* mode 0: [B*N, >= Dh] pitch ld_hs; mode 1: unused  */
     const float* hr;              /* [B*N, >= (E or E+1)*H*Dh] pitch ld_hr             */
     int64_t ld_hs, ld_hr;
-    const float* score_s;         /* mode 1: [B*N,H]                                   */
-    const float* score_r;         /* mode 1: [B*N,(E+1)*H]                             */
+    const float* score_s;         /* mode 1: [B*N,H], row pitch ld_score_s             */
+    const float* score_r;         /* mode 1: [B*N,(E+1)*H], row pitch ld_score_r       */
+    int64_t ld_score_s, ld_score_r; /* 0 = dense; the logits may be extra columns of the projection output (they are
+                                       linear in its input: hs.a_0 = x (W_hs^T a_0) + b_hs.a_0)                   */
     const float* num_neighbours;  /* mode 0: [B*N] or NULL (-> number of edges found)  */
     int32_t mode;
     float leaky_slope;            /* 0.2                                               */
@@ -447,6 +449,47 @@ typedef struct {
 } cnf_skip_gate_args;
 
 CNF_API int cnf_skip_gate(const cnf_skip_gate_args* a, cnf_stream_t stream);
+
+/* Edge-GNN message passing (layers/networks/graph_layers.py:242-336, 388-700).  Node pairs (a < b) are numbered
+ * p = a (N-1) - a (a-1)/2 + (b-a-1) (experiments/molecule_generation/mutils.py:5-10); features of the valid pairs are
+ * stored compacted [R,*]; rev[b*P + p] = 1 + compact row, 0 = pair not valid (indices_reverse, graph_layers.py:349-355).
+ *   mode 0  Edge2NodeAttnLayer (:595-645): w = sigmoid(edge_logit) / max(sum over valid pairs, 1e-5)
+ *   mode 1  Edge2NodeQKVAttnLayer (:432-502): w = softmax(scale * q_i.k_j + edge_logit) over the valid pairs
+ *   out[i,h,:] = sum_j w_ij (edge_val[pair(i,j),h,:] + node_val[j,h,:])   (0 for a node without valid pairs) */
+typedef struct {
+    int64_t B;
+    int32_t N, H, Dh;
+    int64_t R;                   /* number of compact pair rows                       */
+    const int64_t* rev;          /* [B, N(N-1)/2]                                     */
+    const float* node_val;       /* [B*N, >= H*Dh] pitch ld_node_val                  */
+    const float* node_q;         /* mode 1, pitch ld_node_q                           */
+    const float* node_k;         /* mode 1, pitch ld_node_k                           */
+    const float* edge_val;       /* [R, >= H*Dh] pitch ld_edge_val                    */
+    const float* edge_logit;     /* [R, >= H] pitch ld_edge_logit                     */
+    int64_t ld_node_val, ld_node_q, ld_node_k, ld_edge_val, ld_edge_logit;
+    int32_t mode;
+    float scale;                 /* mode 1: Dh^-0.5                                   */
+    float* out;                  /* [B*N, H*Dh]                                       */
+} cnf_edge_aggregate_args;
+
+CNF_API int cnf_edge_aggregate(const cnf_edge_aggregate_args* a, cnf_stream_t stream);
+
+/* Node2EdgePlainLayer (graph_layers.py:317-336) on the compact pair rows:
+ *   out[r,:] = act(edge_lin[r,:] + node_lin[b, x1[p],:] + node_lin[b, x2[p],:])   with flat_indices[r] = b*P + p */
+typedef struct {
+    int64_t R;
+    int32_t N, He;
+    const int64_t* flat_indices;  /* [R]                                   */
+    const int64_t* x_indices1;    /* [P] first node of pair p              */
+    const int64_t* x_indices2;    /* [P] second node of pair p             */
+    const float* edge_lin;        /* [R, >= He] pitch ld_edge              */
+    const float* node_lin;        /* [B*N, >= He] pitch ld_node            */
+    int64_t ld_edge, ld_node;
+    int32_t activation;           /* 0 none, 1 GELU                        */
+    float* out;                   /* [R, He]                               */
+} cnf_pair_combine_args;
+
+CNF_API int cnf_pair_combine(const cnf_pair_combine_args* a, cnf_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * K8 + K1/K2 fused: FINAL projection of the coupling network + mixture-CDF coupling transform.

@@ -136,3 +136,83 @@ def graph_node_flow(sd, x, adj, length, u_noise, *, num_flows, num_layers, num_m
         z, ldj = O.invconv(z, O.invconv_inverse(w), sldj, ldj, reverse=True, length=length, pad=pad)
         z, ldj = O.actnorm(z, sd["flow_layers.%d.bias" % base], sd["flow_layers.%d.scales" % base], ldj, reverse=True, length=length, pad=pad)
     return z, ldj
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Edge-GNN (layers/networks/graph_layers.py:242-820) as dense [B,N,N] algebra.  Pinned by tests/golden/edge_gnn_*.npz
+# (reference EdgeGNN, dense and sparse forward passes).
+# ---------------------------------------------------------------------------------------------------------------------
+def _to_matrix(pair_vals, x_indices, N):
+    """[B,P,*] pair list -> symmetric [B,N,N,*] (zero diagonal)."""
+    B = pair_vals.shape[0]
+    out = pair_vals.new_zeros((B, N, N) + pair_vals.shape[2:])
+    out[:, x_indices[0], x_indices[1]] = pair_vals
+    out[:, x_indices[1], x_indices[0]] = pair_vals
+    return out
+
+
+def _mlp_in(sd, pre, x):
+    return _lin(sd, pre + ".2", F.gelu(_lin(sd, pre + ".0", x)))
+
+
+def _mlp_out(sd, pre, x):
+    return _lin(sd, pre + ".3", F.gelu(_lin(sd, pre + ".1", _ln(sd, pre + ".0", x))))
+
+
+def edge2node_attn(sd, pre, node, edge, x_indices, mask_valid, H=4):
+    """Edge2NodeAttnLayer (:595-645)."""
+    B, N, _ = node.shape
+    new = _lin(sd, pre + "node_feat_layer", _ln(sd, pre + "node_normalization", node))
+    node_self, node_ctx = new.chunk(2, dim=-1)
+    edge_in = _ln(sd, pre + "edge_normalization", edge)
+    e_new = _to_matrix(_lin(sd, pre + "edge_feat_layer", edge_in), x_indices, N)          # [B,i,j,HO]
+    e_log = _to_matrix(_lin(sd, pre + "edge_logits_layer", edge_in), x_indices, N)        # [B,i,j,H]
+    m = _to_matrix(mask_valid, x_indices, N).unsqueeze(-1)
+    w = torch.sigmoid(e_log) * m
+    probs = w / w.sum(dim=2, keepdim=True).clamp(min=1e-5)                                # :628-629
+    Dh = node_ctx.shape[-1] // H
+    pair_feat = (e_new + node_ctx[:, None, :, :]).view(B, N, N, H, Dh)
+    att = (pair_feat * probs.unsqueeze(-1)).sum(dim=2).reshape(B, N, H * Dh)
+    return skip_connection(sd, pre + "skip_layer.", node, F.gelu(node_self + att), 2)
+
+
+def edge2node_qkv(sd, pre, node, edge, x_indices, mask_valid, H=4):
+    """Edge2NodeQKVAttnLayer (:432-502)."""
+    B, N, Hn = node.shape
+    Dh = Hn // H
+    node_in = _ln(sd, pre + "node_normalization", node)
+    edge_in = _ln(sd, pre + "edge_normalization", edge)
+    q, k, v = (t.view(B, N, H, Dh) for t in _lin(sd, pre + "node_query_key_val_layer", node_in).chunk(3, dim=-1))
+    e_val = _to_matrix(_lin(sd, pre + "edge_val_layer", edge_in), x_indices, N).view(B, N, N, H, Dh)
+    e_adj = _to_matrix(_lin(sd, pre + "edge_adj_layer", edge_in), x_indices, N)           # [B,i,j,H]
+    m = _to_matrix(mask_valid, x_indices, N).unsqueeze(-1)
+    logits = torch.einsum("bihd,bjhd->bijh", q, k) * float(Dh) ** -0.5 + e_adj            # :446,:476
+    logits = logits.masked_fill(m == 0, -9e15)
+    probs = torch.softmax(logits, dim=2) * (m.sum(dim=2, keepdim=True) > 0).float()       # :477-478
+    att = ((e_val + v[:, None]) * probs.unsqueeze(-1)).sum(dim=2).reshape(B, N, H * Dh)
+    comb = F.gelu(_lin(sd, pre + "output_projection", torch.cat([node_in, att], dim=-1)))
+    return skip_connection(sd, pre + "skip_layer.", node, comb, 2)
+
+
+def node2edge(sd, pre, node, edge, x_indices, mask_valid):
+    """Node2EdgePlainLayer (:317-336) + the masking of EdgeGNNLayer (:261)."""
+    nl = _lin(sd, pre + "node_feat_layer.1", _ln(sd, pre + "node_feat_layer.0", node))
+    el = _lin(sd, pre + "edge_feat_layer.1", _ln(sd, pre + "edge_feat_layer.0", edge))
+    comb = F.gelu(el + nl[:, x_indices[0]] + nl[:, x_indices[1]])
+    return skip_connection(sd, pre + "skip_layer.", edge, comb, 2) * mask_valid.unsqueeze(-1)
+
+
+def edge_gnn(sd, z_nodes, z_edges, x_indices, mask_valid, *, num_layers, qkv, pad=None, binary_adjacency=None, max_neighbours=-1, pre=""):
+    """EdgeGNN.forward (:781-820) -> (nodes_out, edges_out)."""
+    node = _mlp_in(sd, pre + "input_layer_nodes", z_nodes)
+    edge = _mlp_in(sd, pre + "input_layer_edges", z_edges)
+    if binary_adjacency is not None and max_neighbours > 0:
+        nn_ = binary_adjacency.sum(dim=-1).long().clamp(max=max_neighbours)
+        node = node + _lin(sd, pre + "node_neighbour_embed", F.one_hot(nn_, max_neighbours + 1).float())
+    for i in range(num_layers):
+        lp = "%slayers.%d." % (pre, i)
+        node = (edge2node_qkv if qkv else edge2node_attn)(sd, lp + "edge2node_layer.", node, edge, x_indices, mask_valid)
+        edge = node2edge(sd, lp + "node2edge_layer.", node, edge, x_indices, mask_valid)
+    nodes_out = _mlp_out(sd, pre + "out_layer_nodes", node)
+    edges_out = _mlp_out(sd, pre + "out_layer_edges", edge) * mask_valid.unsqueeze(-1)
+    return (nodes_out * pad if pad is not None else nodes_out), edges_out

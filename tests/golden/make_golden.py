@@ -586,6 +586,62 @@ def gold_graph_node_flow(seed):
          x_dec=x_dec, **sd)
 
 
+def _graph_layers_with_floor_division():
+    """The reference's sparse Edge-GNN path computes pair indices with `/ 2` on LongTensors (graph_layers.py:527,668), which
+    torch >= 1.6 turns into a float tensor that index_select rejects.  Load the module from its source with that one
+    operator restored to the integer division it was written for (SURVEY App. B #8); nothing else is touched."""
+    import importlib.util
+    path = os.path.join(REF, "layers", "networks", "graph_layers.py")
+    src = open(path).read()
+    assert src.count("* edge_indices[...,0]) / 2 +") == 2
+    src = src.replace("* edge_indices[...,0]) / 2 +", "* edge_indices[...,0]) // 2 +")
+    mod = types.ModuleType("graph_layers_floor_div")
+    mod.__file__ = path
+    exec(compile(src, path, "exec"), mod.__dict__)
+    return mod
+
+
+def _pairs(N, length):
+    i1 = torch.tensor([i for i in range(N) for j in range(i + 1, N)])
+    i2 = torch.tensor([j for i in range(N) for j in range(i + 1, N)])
+    mask_valid = ((i1[None, :] < length[:, None]) & (i2[None, :] < length[:, None])).float()
+    return (i1, i2), mask_valid
+
+
+def gold_edge_gnn(name, seed, qkv, sparse, B=3, N=7, c_in_nodes=6, c_in_edges=2, hn=32, he=16, layers=2, max_neighbours=4):
+    """EdgeGNN (graph_layers.py:737-820) with Edge2NodeAttnLayer (GraphCNF step 2) or Edge2NodeQKVAttnLayer (step 3) layers.
+    ``sparse``: valid pairs = bonds only and ``binary_adjacency`` given (sparse forward + neighbour-count embedding, as in
+    step 2); else valid pairs = all pairs of real nodes, dense forward (step 3)."""
+    GL = _graph_layers_with_floor_division()
+    g = torch.Generator().manual_seed(seed)
+    torch.manual_seed(seed)
+    e2n = (lambda: GL.Edge2NodeQKVAttnLayer(hidden_size_nodes=hn, hidden_size_edges=he, skip_config=2)) if qkv else \
+        (lambda: GL.Edge2NodeAttnLayer(hidden_size_nodes=hn, hidden_size_edges=he, skip_config=2))
+    n2e = lambda: GL.Node2EdgePlainLayer(hidden_size_nodes=hn, hidden_size_edges=he, skip_config=2)
+    c_out_nodes, c_out_edges = c_in_nodes * 5, c_in_edges * 8
+    net = GL.EdgeGNN(c_in_nodes=c_in_nodes, c_in_edges=c_in_edges, c_out_nodes=c_out_nodes, c_out_edges=c_out_edges,
+                     edge_gnn_layer_func=lambda: GL.EdgeGNNLayer(edge2node_layer_func=e2n, node2edge_layer_func=n2e),
+                     max_neighbours=max_neighbours, num_layers=layers)
+    _randomise(net, g)
+    net.eval()
+    adj, length = _rand_graphs(g, B, N, 3, p_edge=0.4, min_len=3)
+    x_indices, mask_all = _pairs(N, length)
+    edge_types = adj.view(B, N * N).index_select(1, x_indices[0] + x_indices[1] * N)
+    mask_valid = mask_all * (edge_types != 0).float() if sparse else mask_all
+    pad = lengths_to_pad(length, N)
+    z_nodes = torch.randn(B, N, c_in_nodes, generator=g) * pad
+    z_edges = torch.randn(B, mask_valid.shape[1], c_in_edges, generator=g) * mask_valid.unsqueeze(-1)
+    binary = (adj > 0).long() if sparse else None
+    with torch.no_grad():
+        nodes_out, edges_out = net(z_nodes, z_edges, length=length, x_indices=x_indices, mask_valid=mask_valid,
+                                   channel_padding_mask=pad, binary_adjacency=binary)
+    sd = {"sd__" + k: v for k, v in net.state_dict().items()}
+    save(name, z_nodes=z_nodes, z_edges=z_edges, adjacency=adj, length=length, pad=pad, mask_valid=mask_valid, x_indices1=x_indices[0],
+         x_indices2=x_indices[1], nodes_out=nodes_out, edges_out=edges_out, qkv=int(qkv), sparse=int(sparse), hn=hn, he=he,
+         layers=layers, max_neighbours=max_neighbours, c_in_nodes=c_in_nodes, c_in_edges=c_in_edges, c_out_nodes=c_out_nodes,
+         c_out_edges=c_out_edges, **sd)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(4)
     if ONLY:
@@ -594,7 +650,9 @@ if __name__ == "__main__":
              "rgcn": lambda: (gold_rgcn("rgcn_attention", 23, True, 1), gold_rgcn("rgcn_attention_e3", 24, True, 3, skip_config=1),
                               gold_rgcn("rgcn_conv", 25, False, 3, N=12), gold_rgcn("rgcn_conv_skip0", 26, False, 1, skip_config=0,
                                                                                    max_neighbours=0)),
-             "graph_flow": lambda: gold_graph_node_flow(seed=27)}[_n]()
+             "graph_flow": lambda: gold_graph_node_flow(seed=27),
+             "edge_gnn": lambda: (gold_edge_gnn("edge_gnn_attn_sparse", 28, False, True), gold_edge_gnn("edge_gnn_attn_dense", 29, False, False),
+                                  gold_edge_gnn("edge_gnn_qkv_dense", 30, True, False, N=9), gold_edge_gnn("edge_gnn_qkv_sparse", 31, True, True))}[_n]()
         sys.exit(0)
     gold_mixcdf_selftest()
     gold_mixcdf("mixcdf_lm_small", 3, 32, 16, 8, seed=1)
@@ -626,3 +684,7 @@ if __name__ == "__main__":
     gold_rgcn("rgcn_conv", 25, False, 3, N=12)
     gold_rgcn("rgcn_conv_skip0", 26, False, 1, skip_config=0, max_neighbours=0)
     gold_graph_node_flow(seed=27)
+    gold_edge_gnn("edge_gnn_attn_sparse", 28, False, True)
+    gold_edge_gnn("edge_gnn_attn_dense", 29, False, False)
+    gold_edge_gnn("edge_gnn_qkv_dense", 30, True, False, N=9)
+    gold_edge_gnn("edge_gnn_qkv_sparse", 31, True, True)

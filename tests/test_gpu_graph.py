@@ -218,3 +218,78 @@ def test_graph_node_flow_full_size_properties():
         assert_close(l0, ldj[:h], rtol=1e-4, atol=1e-3, what="batch split ldj")
         pad = (torch.arange(N)[None, :] < length[:, None]).cuda()
         assert (z[~pad] == 0).all()
+
+
+# ---- Edge-GNN (GraphCNF steps 2 and 3) ------------------------------------------------------------------------------
+def _build_edge_gnn(g):
+    from categoricalnf_b200.layers.networks import (Edge2NodeAttnLayer, Edge2NodeQKVAttnLayer, EdgeGNN, EdgeGNNLayer,
+                                                    Node2EdgePlainLayer)
+    e2n = (lambda: Edge2NodeQKVAttnLayer(hidden_size_nodes=g.hn, hidden_size_edges=g.he, skip_config=2)) if g.qkv else \
+        (lambda: Edge2NodeAttnLayer(hidden_size_nodes=g.hn, hidden_size_edges=g.he, skip_config=2))
+    n2e = lambda: Node2EdgePlainLayer(hidden_size_nodes=g.hn, hidden_size_edges=g.he, skip_config=2)
+    net = EdgeGNN(g.c_in_nodes, g.c_in_edges, g.c_out_nodes, g.c_out_edges, lambda: EdgeGNNLayer(e2n, n2e), num_layers=g.layers,
+                  max_neighbours=g.max_neighbours)
+    net.load_state_dict(_sd(g), strict=True)
+    return net.cuda().eval()
+
+
+EDGE_CASES = ["edge_gnn_attn_sparse", "edge_gnn_attn_dense", "edge_gnn_qkv_dense", "edge_gnn_qkv_sparse"]
+
+
+@pytest.mark.parametrize("name", EDGE_CASES)
+def test_edge_gnn_golden(name):
+    g = load_golden(name)
+    net = _build_edge_gnn(g)
+    binary = (g.adjacency > 0).long().cuda() if g.sparse else None
+    kw = dict(length=g.length.cuda(), x_indices=(g.x_indices1.cuda(), g.x_indices2.cuda()), mask_valid=g.mask_valid.cuda(),
+              channel_padding_mask=g.pad.cuda(), binary_adjacency=binary)
+    with torch.no_grad():
+        nodes, edges = net(g.z_nodes.cuda(), g.z_edges.cuda(), **kw)
+    assert_close(nodes, g.nodes_out, rtol=1e-4, atol=2e-5, what="nodes_out")
+    assert_close(edges, g.edges_out, rtol=1e-4, atol=2e-5, what="edges_out")
+    # reference calling convention of a single layer: full [B,P,He] edge tensor in and out
+    layer = net.layers[0]
+    gen = torch.Generator().manual_seed(3)
+    nf = torch.randn(g.z_nodes.shape[0], g.z_nodes.shape[1], g.hn, generator=gen).cuda()
+    ef = (torch.randn(g.z_edges.shape[0], g.z_edges.shape[1], g.he, generator=gen) * g.mask_valid.unsqueeze(-1)).cuda()
+    with torch.no_grad():
+        n1, e1 = layer(nf, ef, kw["x_indices"], kw["mask_valid"])
+    assert e1.shape == ef.shape and bool((e1[kw["mask_valid"] == 0] == 0).all())
+    # training path (dense differentiable glue) agrees with the kernels
+    with torch.enable_grad():
+        nodes_t, edges_t = net(g.z_nodes.cuda().requires_grad_(True), g.z_edges.cuda(), **kw)
+    assert_close(nodes_t, nodes, rtol=1e-4, atol=2e-5, what="training path nodes")
+    assert_close(edges_t, edges, rtol=1e-4, atol=2e-5, what="training path edges")
+
+
+@pytest.mark.parametrize("qkv", [False, True])
+def test_edge_gnn_zinc_shape_vs_oracle(qkv):
+    """GraphCNF hyper-parameters at the per-GPU molecule shape: B 64, N 38 (703 pairs), hidden 384 / 192, 4 layers."""
+    from categoricalnf_b200.layers.networks import (Edge2NodeAttnLayer, Edge2NodeQKVAttnLayer, EdgeGNN, EdgeGNNLayer,
+                                                    Node2EdgePlainLayer)
+    torch.manual_seed(int(qkv))
+    gen = torch.Generator().manual_seed(10 + int(qkv))
+    B, N, hn, he = 64, 38, 384, 192
+    e2n = (lambda: Edge2NodeQKVAttnLayer(hn, he, skip_config=2)) if qkv else (lambda: Edge2NodeAttnLayer(hn, he, skip_config=2))
+    net = EdgeGNN(6, 2, 6 * 50, 2 * 26, lambda: EdgeGNNLayer(e2n, lambda: Node2EdgePlainLayer(hn, he, skip_config=2)),
+                  num_layers=4, max_neighbours=4).eval()
+    adj, length = _graphs(gen, B, N, 3, p=0.08)
+    i1 = torch.tensor([i for i in range(N) for j in range(i + 1, N)])
+    i2 = torch.tensor([j for i in range(N) for j in range(i + 1, N)])
+    mask_all = ((i1[None, :] < length[:, None]) & (i2[None, :] < length[:, None])).float()
+    bonds = adj.view(B, N * N).index_select(1, i1 + i2 * N) != 0
+    mask_valid = mask_all if qkv else mask_all * bonds.float()
+    pad = (torch.arange(N)[None, :] < length[:, None]).float().unsqueeze(-1)
+    z_nodes = torch.randn(B, N, 6, generator=gen) * pad
+    z_edges = torch.randn(B, i1.numel(), 2, generator=gen) * mask_valid.unsqueeze(-1)
+    binary = None if qkv else (adj > 0).long()
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    ref_n, ref_e = GO.edge_gnn(sd, z_nodes, z_edges, (i1, i2), mask_valid, num_layers=4, qkv=qkv, pad=pad, binary_adjacency=binary,
+                               max_neighbours=4)
+    net = net.cuda()
+    with torch.no_grad():
+        nodes, edges = net(z_nodes.cuda(), z_edges.cuda(), length=length.cuda(), x_indices=(i1.cuda(), i2.cuda()),
+                           mask_valid=mask_valid.cuda(), channel_padding_mask=pad.cuda(),
+                           binary_adjacency=None if binary is None else binary.cuda())
+    assert_close(nodes, ref_n, rtol=1e-4, atol=2e-5, what="nodes_out")
+    assert_close(edges, ref_e, rtol=1e-4, atol=2e-5, what="edges_out")

@@ -250,3 +250,14 @@ def test_graph_node_flow():
     zr, lr = GO.graph_node_flow(_sd(g), g.x, g.adjacency, g.length, g.u, reverse_z=g.z, **kw)
     assert_close(zr, g.z_rev, rtol=1e-4, atol=2e-5, what="z reverse")
     assert_close(lr, g.ldj_rev, rtol=1e-4, atol=2e-4, what="ldj reverse")
+
+
+@pytest.mark.parametrize("name", ["edge_gnn_attn_sparse", "edge_gnn_attn_dense", "edge_gnn_qkv_dense", "edge_gnn_qkv_sparse"])
+def test_edge_gnn(name):
+    from oracle import graph_oracle as GO
+    g = load_golden(name)
+    binary = (g.adjacency > 0).long() if g.sparse else None
+    nodes, edges = GO.edge_gnn(_sd(g), g.z_nodes, g.z_edges, (g.x_indices1, g.x_indices2), g.mask_valid, num_layers=g.layers,
+                               qkv=bool(g.qkv), pad=g.pad, binary_adjacency=binary, max_neighbours=g.max_neighbours)
+    assert_close(nodes, g.nodes_out, rtol=1e-5, atol=2e-6, what="nodes_out")
+    assert_close(edges, g.edges_out, rtol=1e-5, atol=2e-6, what="edges_out")
