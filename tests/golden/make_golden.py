@@ -642,6 +642,61 @@ def gold_edge_gnn(name, seed, qkv, sparse, B=3, N=7, c_in_nodes=6, c_in_edges=2,
          c_out_edges=c_out_edges, **sd)
 
 
+def gold_graphcnf(seed):
+    """BASELINE configs 4 / 5 in small: the reference's GraphCNF (experiments/molecule_generation/graphCNF.py), forward
+    (log-likelihood) and reverse (sampling) in eval mode.  Two compatibility shims so that the 2020 code runs on this torch
+    (SURVEY App. B #8, #9), neither changes what is computed: integer division restored in the sparse Edge-GNN path, and the
+    float64 class-prior bias of the virtual-edge decoder cast to float32."""
+    sys.modules["layers.networks.graph_layers"] = _graph_layers_with_floor_division()
+    from experiments.molecule_generation.graphCNF import GraphCNF
+    g = torch.Generator().manual_seed(seed)
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+    N, V_NODES, V_EDGES = 8, 5, 3
+
+    class _Dataset:
+        max_num_nodes = staticmethod(lambda: N)
+        num_node_types = staticmethod(lambda: V_NODES)
+        num_edge_types = staticmethod(lambda: V_EDGES)
+        num_max_neighbours = staticmethod(lambda: 4)
+        get_node_prior = staticmethod(lambda data_root="data/": np.log(np.array([0.5, 0.2, 0.15, 0.1, 0.05], dtype=np.float32)))
+        get_edge_prior = staticmethod(lambda data_root="data/": np.log(np.array([0.7, 0.2, 0.1], dtype=np.float32)))
+
+    enc = lambda d: {"use_dequantization": False, "use_variational": False, "use_decoder": False, "num_dimensions": d,
+                     "flow_config": {"num_flows": 0, "hidden_layers": 2, "hidden_size": 128}, "decoder_config": {"num_layers": 1, "hidden_size": 64}}
+    params = {"categ_encoding_nodes": enc(6), "categ_encoding_edges": enc(2), "coupling_hidden_size_nodes": 32, "coupling_hidden_size_edges": 16,
+              "coupling_num_flows": "1,2,2", "coupling_hidden_layers": 2, "coupling_num_mixtures_nodes": 8, "coupling_num_mixtures_edges": 4,
+              "coupling_mask_ratio": 0.5, "coupling_dropout": 0.0, "encoding_virtual_num_flows": 0}
+    model = _quiet(GraphCNF, params, _Dataset)
+    _randomise(model, g, std=0.2)
+    bias = model.edge_virtual_decoder.layers.main_net[-1].bias
+    bias.data = bias.data.float()
+    model.eval()
+    B = 4
+    adj, length = _rand_graphs(g, B, N, V_EDGES, p_edge=0.3, min_len=4)
+    x = torch.randint(0, V_NODES, (B, N), generator=g) * (torch.arange(N)[None, :] < length[:, None]).long()
+    noise = []
+
+    def recorder(sample_shape=torch.Size()):
+        noise.append(torch.rand(sample_shape, generator=g))
+        return noise[-1]
+
+    for e in (model.node_encoding, model.edge_attr_encoding, model.edge_virtual_encoding):
+        e.prior_distribution.distribution.sample = recorder
+    with torch.no_grad():
+        z, ldj = model(x, adjacency=adj, length=length)
+    u_nodes, u_edges, u_virtual = noise
+    # reverse: sample with recorded edge latents
+    z_edges_init = torch.randn(B, N * (N - 1) // 2, 2, generator=g)
+    z_nodes_init = torch.randn(B, N, 6, generator=g) * lengths_to_pad(length, N)
+    model.prior_distribution.sample = lambda shape=None, temp=1.0, **kw: z_edges_init
+    with torch.no_grad():
+        (x_smp, adj_smp), ldj_smp = model(z_nodes_init, reverse=True, length=length)
+    sd = {"sd__" + k: v for k, v in model.state_dict().items()}
+    save("graphcnf_small", x=x, adjacency=adj, length=length, u_nodes=u_nodes, u_edges=u_edges, u_virtual=u_virtual, z=z, ldj=ldj,
+         z_edges_init=z_edges_init, z_nodes_init=z_nodes_init, x_smp=x_smp, adj_smp=adj_smp, ldj_smp=ldj_smp, N=N, **sd)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(4)
     if ONLY:
@@ -651,6 +706,7 @@ if __name__ == "__main__":
                               gold_rgcn("rgcn_conv", 25, False, 3, N=12), gold_rgcn("rgcn_conv_skip0", 26, False, 1, skip_config=0,
                                                                                    max_neighbours=0)),
              "graph_flow": lambda: gold_graph_node_flow(seed=27),
+             "graphcnf": lambda: gold_graphcnf(seed=32),
              "edge_gnn": lambda: (gold_edge_gnn("edge_gnn_attn_sparse", 28, False, True), gold_edge_gnn("edge_gnn_attn_dense", 29, False, False),
                                   gold_edge_gnn("edge_gnn_qkv_dense", 30, True, False, N=9), gold_edge_gnn("edge_gnn_qkv_sparse", 31, True, True))}[_n]()
         sys.exit(0)
@@ -688,3 +744,4 @@ if __name__ == "__main__":
     gold_edge_gnn("edge_gnn_attn_dense", 29, False, False)
     gold_edge_gnn("edge_gnn_qkv_dense", 30, True, False, N=9)
     gold_edge_gnn("edge_gnn_qkv_sparse", 31, True, True)
+    gold_graphcnf(seed=32)

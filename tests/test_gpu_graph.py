@@ -293,3 +293,79 @@ def test_edge_gnn_zinc_shape_vs_oracle(qkv):
                            binary_adjacency=None if binary is None else binary.cuda())
     assert_close(nodes, ref_n, rtol=1e-4, atol=2e-5, what="nodes_out")
     assert_close(edges, ref_e, rtol=1e-4, atol=2e-5, what="edges_out")
+
+
+# ---- GraphCNF (BASELINE configs 4 and 5) ----------------------------------------------------------------------------
+def _build_graphcnf(N, node_types=5, hidden=(32, 16), flows="1,2,2", layers=2, mixtures=(8, 4), sd=None):
+    import numpy as np
+    from categoricalnf_b200.experiments.molecule_generation import GraphCNF
+    node_prior = np.log(np.array([0.5, 0.2, 0.15, 0.1, 0.05], dtype=np.float32)) if node_types == 5 else \
+        np.zeros(node_types, dtype=np.float32)
+
+    class _Dataset:
+        max_num_nodes = staticmethod(lambda: N)
+        num_node_types = staticmethod(lambda: node_types)
+        num_edge_types = staticmethod(lambda: 3)
+        num_max_neighbours = staticmethod(lambda: 4)
+        get_node_prior = staticmethod(lambda data_root="data/": node_prior)
+        get_edge_prior = staticmethod(lambda data_root="data/": np.log(np.array([0.7, 0.2, 0.1], dtype=np.float32)))
+
+    enc = lambda d: {"use_dequantization": False, "use_variational": False, "use_decoder": False, "num_dimensions": d,
+                     "flow_config": {"num_flows": 0, "hidden_layers": 2, "hidden_size": 128},
+                     "decoder_config": {"num_layers": 1, "hidden_size": 64}}
+    params = {"categ_encoding_nodes": enc(6), "categ_encoding_edges": enc(2), "coupling_hidden_size_nodes": hidden[0],
+              "coupling_hidden_size_edges": hidden[1], "coupling_num_flows": flows, "coupling_hidden_layers": layers,
+              "coupling_num_mixtures_nodes": mixtures[0], "coupling_num_mixtures_edges": mixtures[1], "coupling_mask_ratio": 0.5,
+              "coupling_dropout": 0.0, "encoding_virtual_num_flows": 0}
+    model = GraphCNF(params, _Dataset)
+    if sd is not None:
+        model.load_state_dict(sd, strict=True)
+    return model.cuda().eval()
+
+
+def test_graphcnf_golden():
+    """Forward (log-likelihood incl. the prior of the edge latents) and reverse (sampling) of the reference's GraphCNF."""
+    g = load_golden("graphcnf_small")
+    model = _build_graphcnf(g.N, sd=_sd(g))
+    with torch.no_grad():
+        z, ldj = model(g.x.cuda(), adjacency=g.adjacency.cuda(), length=g.length.cuda(), u_noise=g.u_nodes.cuda(),
+                       u_noise_edges=g.u_edges.cuda(), u_noise_virtual=g.u_virtual.cuda())
+        assert_close(z, g.z, what="z nodes")
+        assert_close(ldj, g.ldj, rtol=1e-4, atol=5e-4, what="ldj")
+        (x_smp, adj_smp), ldj_smp = model(g.z_nodes_init.cuda(), reverse=True, length=g.length.cuda(), z_edges_init=g.z_edges_init.cuda())
+    valid = torch.arange(g.N)[None, :] < g.length[:, None]
+    assert torch.equal(adj_smp.cpu(), g.adj_smp)
+    assert torch.equal(x_smp.cpu()[valid], g.x_smp[valid])
+    assert_close(ldj_smp, g.ldj_smp, rtol=1e-4, atol=5e-4, what="ldj of the sampling pass")
+
+
+def test_graphcnf_zinc_shape_properties():
+    """BASELINE config 4 per-GPU shape (B 64, N 38, 9 node types, hidden 384 / 192, flows 4,6,6, 4 layers, K 16 / 8):
+    data-dependent init, forward, batch-split consistency, sampling produces symmetric adjacencies on valid nodes only."""
+    torch.manual_seed(0)
+    gen = torch.Generator().manual_seed(0)
+    B, N = 64, 38
+    model = _build_graphcnf(N, node_types=9, hidden=(384, 192), flows="4,6,6", layers=4, mixtures=(16, 8))
+    adj, length = _graphs(gen, B, N, 3, p=0.06)
+    x = torch.randint(0, 9, (B, N), generator=gen) * (torch.arange(N)[None, :] < length[:, None]).long()
+    xc, ac, lc = x.cuda(), adj.cuda(), length.cuda()
+    P = N * (N - 1) // 2
+    with torch.no_grad():
+        model.initialize_data_dependent([(xc[:32], {"adjacency": ac[:32], "length": lc[:32]})])
+        noise = dict(u_noise=torch.rand(B * N, 1, 6, generator=gen).cuda(), u_noise_edges=torch.rand(B * P, 1, 2, generator=gen).cuda(),
+                     u_noise_virtual=torch.rand(B * P, 1, 2, generator=gen).cuda())
+        z, ldj = model(xc, adjacency=ac, length=lc, **noise)
+        assert torch.isfinite(z).all() and torch.isfinite(ldj).all()
+        h = B // 2
+        half = dict(u_noise=noise["u_noise"][:h * N], u_noise_edges=noise["u_noise_edges"][:h * P],
+                    u_noise_virtual=noise["u_noise_virtual"][:h * P])
+        z0, l0 = model(xc[:h], adjacency=ac[:h], length=lc[:h], **half)
+        assert_close(z0, z[:h], rtol=1e-4, atol=1e-4, what="batch split z")
+        assert_close(l0, ldj[:h], rtol=1e-4, atol=5e-3, what="batch split ldj")
+        z_nodes = model.prior_distribution.sample(shape=(B, N, 6)) * (torch.arange(N, device="cuda")[None, :, None] < lc[:, None, None])
+        (x_smp, adj_smp), ldj_smp = model(z_nodes, reverse=True, length=lc)
+        assert x_smp.shape == (B, N) and adj_smp.shape == (B, N, N)
+        assert torch.equal(adj_smp, adj_smp.transpose(1, 2)) and int(adj_smp.max()) <= 3
+        valid = (torch.arange(N, device="cuda")[None, :] < lc[:, None])
+        assert bool((adj_smp * (~(valid[:, :, None] & valid[:, None, :])).long() == 0).all())
+        assert torch.isfinite(ldj_smp).all()
