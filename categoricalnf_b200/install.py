@@ -30,6 +30,15 @@ REPLACED = {
     "layers.categorical_encoding.mutils": "categorical_encoding.mutils",
     # GraphCNF's joint node+edge coupling lives under experiments/ upstream but is hot-path row a14
     "experiments.molecule_generation.graph_node_edge_coupling": "flows.node_edge_coupling",
+    # coupling networks of the graph flows: RGCNNet, RelationGraph*, GNNSkipConnection, EdgeGNN and its layers
+    "layers.networks.graph_layers": "networks.graph_layers",
+}
+
+# callers rebuilt on the drop-in layers; reference module name -> categoricalnf_b200 module
+REPLACED_CALLERS = {
+    "experiments.graph_coloring.graph_node_flow": "categoricalnf_b200.experiments.graph_coloring.graph_node_flow",
+    "experiments.molecule_generation.graphCNF": "categoricalnf_b200.experiments.molecule_generation.graphCNF",
+    "experiments.molecule_generation.mutils": "categoricalnf_b200.experiments.molecule_generation.mutils",
 }
 
 
@@ -65,8 +74,10 @@ def install(reference_root: str, stub_missing: bool = True) -> dict:
     if stub_missing:
         _stub_matplotlib()
     installed = {}
-    for ref_name, ours in REPLACED.items():
-        mod = importlib.import_module("categoricalnf_b200.layers." + ours)
+    targets = {ref_name: "categoricalnf_b200.layers." + ours for ref_name, ours in REPLACED.items()}
+    targets.update(REPLACED_CALLERS)
+    for ref_name, ours in targets.items():
+        mod = importlib.import_module(ours)
         prev = sys.modules.get(ref_name)
         if prev is not None and prev is not mod:
             raise RuntimeError("%s was imported before categoricalnf_b200.install(); call install() first" % ref_name)
@@ -76,7 +87,7 @@ def install(reference_root: str, stub_missing: bool = True) -> dict:
 
 
 def uninstall() -> None:
-    for ref_name in REPLACED:
+    for ref_name in list(REPLACED) + list(REPLACED_CALLERS):
         mod = sys.modules.get(ref_name)
         if mod is not None and mod.__name__.startswith("categoricalnf_b200."):
             del sys.modules[ref_name]

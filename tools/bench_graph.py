@@ -16,7 +16,15 @@ ap.add_argument("--nodes", type=int, default=20)
 ap.add_argument("--reps", type=int, default=10)
 ap.add_argument("--profile", action="store_true")
 ap.add_argument("--cpu", action="store_true", help="also time the CPU oracle on a 32-graph sample")
+ap.add_argument("--config", default="gc", choices=["gc", "mol"],
+                help="gc: graph colouring (config 3); mol: GraphCNF molecule generation forward (config 4, batch 64 per GPU) and "
+                     "sampling (config 5, batch 1024 per GPU)")
 args = ap.parse_args()
+if args.config == "mol":
+    import runpy
+    sys.argv = [sys.argv[0]] + (["--profile"] if args.profile else []) + ["--reps", str(args.reps)]
+    runpy.run_path(os.path.join(os.path.dirname(os.path.abspath(__file__)), "bench_graphcnf.py"), run_name="__main__")
+    sys.exit(0)
 
 from categoricalnf_b200 import ops
 from categoricalnf_b200.experiments.graph_coloring import GraphNodeFlow
