@@ -157,8 +157,8 @@ def workload_config(n_gpus, extra=None):
            "mixtures": W.LM["K"], "vocab": W.LM["V"], "blocks": W.LM["blocks"], "parallelism": "batch-sharded x%d" % n_gpus,
            "l2": "inputs larger than L2 (1.74 GB of coupling parameters per layer vs 126 MB L2); no flush needed",
            "value_leg": "coupling-net outputs given, resident in HBM", "e2e_leg": "drop-in FlowModel, stand-in Linear "
-           "coupling nets (final projection fused with the mixture transform on tcgen05, 3xTF32), pinned host tokens -> H2D, "
-           "per-sample log-likelihood -> D2H"}
+           "coupling nets (final projection fused with the mixture transform on tcgen05, 3xTF32), pinned host tokens -> H2D "
+           "(double-buffered on a copy stream), per-sample log-likelihood -> D2H (host reads step i-1 while step i runs)"}
     if extra:
         cfg.update(extra)
     return cfg
@@ -228,28 +228,57 @@ def run_gpu(args, rank, local_rank, world):
     model, prior = W.build_lm_model(prm, dev)
     parity = parity_check(prm, model, dev) if rank == 0 else None
     host_tokens = [W.lm_tokens(B, S, V, seed=10 * rank + j).pin_memory() for j in range(2)]
-    host_ll = torch.empty(B, dtype=torch.float32).pin_memory()
+    host_ll = [torch.empty(B, dtype=torch.float32).pin_memory() for _ in range(2)]
+    dev_tokens = [torch.empty(B, S, dtype=torch.int64, device=dev) for _ in range(2)]
+    copy_stream = torch.cuda.Stream(device=dev)
+    ready = [torch.cuda.Event() for _ in range(2)]      # tokens of slot j have landed
+    consumed = [torch.cuda.Event() for _ in range(2)]   # the step that read slot j has been issued and finished with it
+    result = [torch.cuda.Event() for _ in range(2)]     # log-likelihoods of slot j are in pinned host memory
 
-    def e2e_step(i):
+    # Double-buffered input pipeline: the H2D copy of step i+1 runs on a copy stream while step i computes, and the host
+    # waits for the D2H result of step i-1 while step i is in flight.  Every step's H2D and D2H happen inside the timed
+    # region (the first copy is not overlapped, the last result is awaited before the closing event).
+    def prefetch(i):
+        j = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[j])
+            dev_tokens[j].copy_(host_tokens[j], non_blocking=True)
+            ready[j].record(copy_stream)
+
+    def e2e_step(i, last):
+        j = i % 2
+        cur = torch.cuda.current_stream()
+        if not last:
+            prefetch(i + 1)
         with torch.no_grad():
-            tok = host_tokens[i % 2].to(dev, non_blocking=True)
-            z, ldj = model(tok)
+            cur.wait_event(ready[j])
+            z, ldj = model(dev_tokens[j])
+            consumed[j].record(cur)
             logp, _ = ops.logistic_logprob(z)
             ll = ldj + logp
             if distributed:
                 acc[0] = ll.sum(dtype=torch.float64)
                 acc[1] = float(B)
                 dist.all_reduce(acc)
-            host_ll.copy_(ll, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+            host_ll[j].copy_(ll, non_blocking=True)
+            result[j].record(cur)
+        if i > 0:
+            result[(i - 1) % 2].synchronize()     # the host consumes the previous step's log-likelihoods
+        if last:
+            result[j].synchronize()
 
-    for i in range(args.warmup):
-        e2e_step(i)
+    def e2e_run(n):
+        for j in range(2):
+            consumed[j].record(torch.cuda.current_stream())
+        prefetch(0)
+        for i in range(n):
+            e2e_step(i, i == n - 1)
+
+    e2e_run(args.warmup)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(args.steps):
-        e2e_step(i)
+    e2e_run(args.steps)
     e1.record()
     barrier()
     e2e_ms_total = e0.elapsed_time(e1)

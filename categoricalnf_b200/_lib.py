@@ -125,6 +125,7 @@ class LinearArgs(C.Structure):
     _fields_ = [
         ("M", C.c_int64), ("N", C.c_int32), ("K", C.c_int32),
         ("x", vp), ("weight", vp), ("bias", vp), ("precision", C.c_int32), ("activation", C.c_int32), ("y", vp),
+        ("weight_lo", vp), ("block_n", C.c_int32),
     ]
 
 

@@ -43,6 +43,7 @@ struct LinearParams {
     int kb_per_split;           // split-K: tile t reduces k-blocks [split * kb_per_split, +kb_per_split) (grad_weight)
     int a_mn, b_mn;             // operand layout in memory: 0 = reduction dim contiguous (K-major), 1 = MN-major
     int act;        // 0 none, 1 GELU (erf)
+    int w_lo;       // 3xTF32: the low part of the B operand is loaded from global memory (tm_blo) instead of being split here
     int store;      // 0: guarded direct stores; 1: shared memory + TMA store; 2: red.global.add (split-K partial sums)
 };
 
@@ -61,12 +62,19 @@ __device__ __forceinline__ TileCoord tile_coord(const LinearParams& p, long long
 }
 
 __device__ __forceinline__ float trunc_tf32(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
+// low part of an fp32 operand whose high part the tensor core forms by truncation; rounded to nearest TF32 so that the
+// hardware's own truncation of it is a no-op (a truncated low part would bias every product the same way)
+__device__ __forceinline__ float lo_tf32(float v) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v - trunc_tf32(v)));
+    return __uint_as_float(r);
+}
 __device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f)); }
 
 template <bool STRICT>
 __global__ void __launch_bounds__(STRICT ? 384 : 256, 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
-                 const __grid_constant__ CUtensorMap tm_y, const LinearParams p) {
+                 const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUtensorMap tm_blo, const LinearParams p) {
     extern __shared__ unsigned char smem_dyn[];
     // 1024-byte alignment: swizzle-128B tiles repeat every 8 rows x 128 bytes
     unsigned char* smem = smem_dyn + ((1024u - (smem_addr(smem_dyn) & 1023u)) & 1023u);
@@ -117,7 +125,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
                 for (int kb = tc.kb0; kb < tc.kb1; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1u);
                     unsigned char* sa = smem + stage * stage_bytes;
-                    mbar_arrive_expect_tx(&full[stage], (uint32_t)half_bytes);
+                    mbar_arrive_expect_tx(&full[stage], (uint32_t)(half_bytes + (STRICT && p.w_lo ? b_bytes : 0)));
+                    if (STRICT && p.w_lo) tma_load_2d(sa + half_bytes + kABytes, &tm_blo, &full[stage], kb * kBK, n0);
                     if (p.a_mn) {   // [32 reduction rows x 32 MN] slabs, one per 128-byte swizzle atom along MN
                         for (int j = 0; j < kBM / 32; ++j) tma_load_2d(sa + j * 4096, &tm_x, &full[stage], m0 + 32 * j, kb * kBK);
                     } else {
@@ -148,22 +157,36 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
                 tcgen05_fence_after();
                 const uint32_t d = tmem_base + (uint32_t)(acc * kStageCols);
                 for (int kb = tc.kb0; kb < tc.kb1; ++kb) {
-                    mbar_wait(STRICT ? &ready[stage] : &full[stage], phase);
+                    mbar_wait(&full[stage], phase);
                     tcgen05_fence_after();
                     unsigned char* sa = smem + stage * stage_bytes;
                     const uint64_t da = p.a_mn ? smem_desc_mn128(sa, 4096u) : smem_desc_k128(sa);
                     const uint64_t db = p.b_mn ? smem_desc_mn128(sa + kABytes, 4096u) : smem_desc_k128(sa + kABytes);
 #pragma unroll
-                    for (int k = 0; k < kBK / 8; ++k) {
-                        const uint32_t oa = (uint32_t)k * step_a, ob = (uint32_t)k * step_b;
-                        mma_tf32(d, smem_desc_advance(da, oa), smem_desc_advance(db, ob), idesc, kb > tc.kb0 || k > 0);
-                        if constexpr (STRICT) {
-                            const uint64_t dal = p.a_mn ? smem_desc_mn128(sa + half_bytes, 4096u) : smem_desc_k128(sa + half_bytes);
-                            const uint64_t dbl = p.b_mn ? smem_desc_mn128(sa + half_bytes + kABytes, 4096u)
-                                                        : smem_desc_k128(sa + half_bytes + kABytes);
-                            mma_tf32(d, smem_desc_advance(dal, oa), smem_desc_advance(db, ob), idesc, true);
-                            mma_tf32(d, smem_desc_advance(da, oa), smem_desc_advance(dbl, ob), idesc, true);
+                    for (int k = 0; k < kBK / 8; ++k)
+                        mma_tf32(d, smem_desc_advance(da, (uint32_t)k * step_a), smem_desc_advance(db, (uint32_t)k * step_b), idesc,
+                                 kb > tc.kb0 || k > 0);
+                    if constexpr (STRICT) {
+                        // hi*hi (above) and hi*lo_B with a pre-split B need only what TMA delivered: they are issued
+                        // before waiting for the splitter warps, whose latency they hide
+                        const uint64_t dal = p.a_mn ? smem_desc_mn128(sa + half_bytes, 4096u) : smem_desc_k128(sa + half_bytes);
+                        const uint64_t dbl = p.b_mn ? smem_desc_mn128(sa + half_bytes + kABytes, 4096u)
+                                                    : smem_desc_k128(sa + half_bytes + kABytes);
+                        if (p.w_lo) {
+#pragma unroll
+                            for (int k = 0; k < kBK / 8; ++k)
+                                mma_tf32(d, smem_desc_advance(da, (uint32_t)k * step_a), smem_desc_advance(dbl, (uint32_t)k * step_b), idesc, true);
                         }
+                        mbar_wait(&ready[stage], phase);
+                        tcgen05_fence_after();
+                        if (!p.w_lo) {
+#pragma unroll
+                            for (int k = 0; k < kBK / 8; ++k)
+                                mma_tf32(d, smem_desc_advance(da, (uint32_t)k * step_a), smem_desc_advance(dbl, (uint32_t)k * step_b), idesc, true);
+                        }
+#pragma unroll
+                        for (int k = 0; k < kBK / 8; ++k)
+                            mma_tf32(d, smem_desc_advance(dal, (uint32_t)k * step_a), smem_desc_advance(db, (uint32_t)k * step_b), idesc, true);
                     }
                     mma_commit(&empty[stage]);     // stage reusable once these MMAs have read it
                     if (++stage == p.stages) { stage = 0; phase ^= 1u; }
@@ -254,11 +277,10 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     } else if (STRICT && warp >= 8) {
         // ---------------- 3xTF32 split.  tcgen05 kind::tf32 TRUNCATES the 13 low mantissa bits of its fp32 operands
         // (measured: tools/tf32_probe.py), so the landed tile already is the high part as far as the tensor core is
-        // concerned; only lo = x - trunc(x) (exact, same sign as x) has to be written.  The dropped terms (lo*lo and
-        // the truncation of lo itself) are positive multiples <= 2^-20 of each product: a ~5e-7 relative scaling of the
-        // result, not a random walk -------------------------------------------------------------------------------
+        // concerned; only lo = rna_tf32(x - trunc(x)) has to be written.  The one dropped term, lo*lo, is <= 2^-20 of
+        // each product (and of random sign once the B operand's split is rounding based, as the pre-split weights are)
         const int tt = threadIdx.x - 256;
-        const int n4 = half_bytes >> 4;
+        const int n4 = (p.w_lo ? kABytes : half_bytes) >> 4;     // pre-split B: only the A tile is split here
         int stage = 0;
         uint32_t phase = 0;
         for (long long t = blockIdx.x; t < p.tiles; t += gridDim.x) {
@@ -270,7 +292,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
                 for (int i = tt; i < n4; i += 128) {
                     const float4 x = hi[i];
                     float4 l;
-                    l.x = x.x - trunc_tf32(x.x); l.y = x.y - trunc_tf32(x.y); l.z = x.z - trunc_tf32(x.z); l.w = x.w - trunc_tf32(x.w);
+                    l.x = lo_tf32(x.x); l.y = lo_tf32(x.y); l.z = lo_tf32(x.z); l.w = lo_tf32(x.w);
                     lo[i] = l;
                 }
                 fence_proxy_async_smem();
@@ -341,6 +363,8 @@ struct GemmDesc {
     long long Mg; int Ng; long long R;
     const float* bias; int act; int precision;
     float* y;
+    const float* b_lo;   // 3xTF32, B K-major: b - trunc_tf32(b), same layout as b, or NULL (split in the kernel)
+    int block_n;      // 0 = automatic; else the N tile (multiple of 32, <= 256) - tuning knob
     int split_k;      // 1: split the reduction over the grid and red.add the partial tiles into y (y pre-initialised)
 };
 
@@ -352,6 +376,10 @@ int launch_gemm(const GemmDesc& g, const char* who, cudaStream_t stream) {
     p.bias = g.bias; p.y = g.y; p.M = g.Mg; p.N = g.Ng; p.K = (int)g.R; p.act = g.act;
     p.a_mn = g.a_mn; p.b_mn = g.b_mn;
     tc_pick_block_n(g.Ng, &p.block_n, &p.n_tiles);
+    if (g.block_n >= 32 && g.block_n <= 256 && g.block_n % 32 == 0) {
+        p.block_n = g.block_n;
+        p.n_tiles = (g.Ng + g.block_n - 1) / g.block_n;
+    }
     p.k_blocks = (int)((g.R + kBK - 1) / kBK);
     p.m_tiles = (g.Mg + kBM - 1) / kBM;
     const long long base_tiles = p.m_tiles * p.n_tiles;
@@ -375,11 +403,18 @@ int launch_gemm(const GemmDesc& g, const char* who, cudaStream_t stream) {
     p.stages = stages;
     const size_t smem = (size_t)fixed + (size_t)stages * stage_bytes;
 
-    CUtensorMap tm_a, tm_b, tm_y;
+    CUtensorMap tm_a, tm_b, tm_y, tm_blo;
+    p.w_lo = (strict && g.b_lo != nullptr && !g.b_mn) ? 1 : 0;
     int rc = g.a_mn ? tc_encode_2d(&tm_a, g.a, g.Mg, g.R, 32, kBK, 1) : tc_encode_2d(&tm_a, g.a, g.R, g.Mg, kBK, kBM, 0);
     if (rc != CNF_OK) return rc;
     rc = g.b_mn ? tc_encode_2d(&tm_b, g.b, g.Ng, g.R, 32, kBK, 1) : tc_encode_2d(&tm_b, g.b, g.R, g.Ng, kBK, p.block_n, 0);
     if (rc != CNF_OK) return rc;
+    if (p.w_lo) {
+        rc = tc_encode_2d(&tm_blo, g.b_lo, g.R, g.Ng, kBK, p.block_n, 0);
+        if (rc != CNF_OK) return rc;
+    } else {
+        tm_blo = tm_b;
+    }
     if (p.store == 1) {
         rc = tc_encode_2d(&tm_y, g.y, g.Ng, g.Mg, 32, 32, 0);
         if (rc != CNF_OK) return rc;
@@ -390,10 +425,10 @@ int launch_gemm(const GemmDesc& g, const char* who, cudaStream_t stream) {
     if (grid > p.tiles) grid = p.tiles;
     if (strict) {
         CNF_CUDA(cudaFuncSetAttribute(linear_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-        linear_tc_kernel<true><<<(unsigned)grid, 384, smem, stream>>>(tm_a, tm_b, tm_y, p);
+        linear_tc_kernel<true><<<(unsigned)grid, 384, smem, stream>>>(tm_a, tm_b, tm_y, tm_blo, p);
     } else {
         CNF_CUDA(cudaFuncSetAttribute(linear_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-        linear_tc_kernel<false><<<(unsigned)grid, 256, smem, stream>>>(tm_a, tm_b, tm_y, p);
+        linear_tc_kernel<false><<<(unsigned)grid, 256, smem, stream>>>(tm_a, tm_b, tm_y, tm_blo, p);
     }
     return launch_status("linear_tc_kernel");
 }
@@ -445,6 +480,8 @@ extern "C" int cnf_linear_fwd(const cnf_linear_args* a, cnf_stream_t stream_) {
     g.a = a->x; g.a_mn = 0; g.b = a->weight; g.b_mn = 0;
     g.Mg = a->M; g.Ng = a->N; g.R = a->K;
     g.bias = a->bias; g.act = a->activation; g.precision = a->precision; g.y = a->y; g.split_k = 0;
+    g.b_lo = a->weight_lo;
+    g.block_n = a->block_n;
     return launch_gemm(g, "cnf_linear_fwd", stream);
 }
 

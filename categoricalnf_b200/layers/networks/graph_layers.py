@@ -86,6 +86,7 @@ class _FusedPair:
                         ws.append(a.weight.new_zeros(extra, K))
                         bs.append(a.bias.new_zeros(extra))
                 self.weight = torch.cat(ws, dim=0).contiguous()
+                self.weight._cnf_cache_lo = True       # long-lived: ops.linear may cache its TF32 low part
                 self.bias = torch.cat(bs, dim=0).contiguous()
             self.key = key
         return self.weight, self.bias

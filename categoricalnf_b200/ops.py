@@ -7,6 +7,7 @@ tensors are rejected - there is no fallback path.
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 import os
 from typing import Optional, Sequence
 
@@ -413,14 +414,46 @@ PRECISION = {"tf32": 0, "3xtf32": 1}
 ACTIVATION = {None: 0, "none": 0, "gelu": 1}
 
 
-def linear(x, weight, bias=None, *, precision="3xtf32", activation=None):
+_weight_split_cache = {}     # id(tensor) -> (weakref, key, hi, lo)
+
+
+def _rna_tf32(t):
+    """Round fp32 to the nearest TF32 value (10 mantissa bits), ties away from zero - ``cvt.rna.tf32.f32``."""
+    return ((t.contiguous().view(torch.int32) + 0x1000) & -8192).view(torch.float32)
+
+
+def weight_split(weight):
+    """(hi, lo) with hi = rna_tf32(weight), lo = rna_tf32(weight - hi): the 3xTF32 split of a weight, done once per tensor
+    object and version instead of once per tile inside the kernel.  Only long-lived weights are cached: ``nn.Parameter``s
+    and tensors marked ``_cnf_cache_lo`` (fused weight blocks); None for anything else."""
+    if not (isinstance(weight, torch.nn.Parameter) or getattr(weight, "_cnf_cache_lo", False)):
+        return None
+    key = (weight._version, weight.data_ptr(), tuple(weight.shape))
+    hit = _weight_split_cache.get(id(weight))
+    if hit is None or hit[0]() is not weight or hit[1] != key:
+        with torch.no_grad():
+            w = weight.detach()
+            hi = _rna_tf32(w)
+            lo = _rna_tf32(w - hi)
+        wid = id(weight)
+        ref = weakref.ref(weight, lambda _r, wid=wid: _weight_split_cache.pop(wid, None))
+        hit = (ref, key, hi, lo)
+        _weight_split_cache[wid] = hit
+    return hit[2], hit[3]
+
+
+def linear(x, weight, bias=None, *, precision="3xtf32", activation=None, block_n=0):
     """y = x @ weight.T + bias (nn.Linear) on the tensor cores (``cnf_linear_fwd``).
 
     ``x`` [..., K] fp32 CUDA, ``weight`` [N, K], ``bias`` [N] | None.  ``precision``: "tf32" (one pass)
     or "3xtf32" (hi/lo split, fp32-level accuracy - default, keeps the 1e-4 parity of the flow).
     K that is not a multiple of 4 is zero-padded (a copy); everything else runs in place."""
     x = _f32(x, "x")
+    split = weight_split(weight) if precision == "3xtf32" and weight.dtype == torch.float32 and weight.is_contiguous() else None
     weight = _f32(weight, "weight")
+    w_lo = None
+    if split is not None:
+        weight, w_lo = split          # B operand = exactly representable high part, low part from the cache
     N, K = weight.shape
     if x.shape[-1] != K:
         raise ValueError("x has %d input features, weight expects %d" % (x.shape[-1], K))
@@ -430,6 +463,7 @@ def linear(x, weight, bias=None, *, precision="3xtf32", activation=None):
         padk = 4 - K % 4
         x2 = torch.nn.functional.pad(x2, (0, padk))
         weight = torch.nn.functional.pad(weight, (0, padk))
+        w_lo = torch.nn.functional.pad(w_lo, (0, padk)) if w_lo is not None else None
         K += padk
     if x2.data_ptr() % 16 != 0:
         x2 = x2.clone()
@@ -439,7 +473,8 @@ def linear(x, weight, bias=None, *, precision="3xtf32", activation=None):
     a.M, a.N, a.K = x2.shape[0], N, K
     a.x, a.weight, a.bias, a.y = _ptr(x2), _ptr(weight), _ptr(bias), _ptr(y)
     a.precision, a.activation = PRECISION[precision], ACTIVATION[activation]
-    _call("cnf_linear_fwd", a, x2, (x2, weight, bias))
+    a.weight_lo, a.block_n = _ptr(w_lo), int(block_n)
+    _call("cnf_linear_fwd", a, x2, (x2, weight, bias, w_lo))
     return y.reshape(lead + (N,))
 
 

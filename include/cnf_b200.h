@@ -350,6 +350,10 @@ typedef struct {
     int32_t precision;    /* 0 = TF32, 1 = 3xTF32                      */
     int32_t activation;   /* 0 = none, 1 = GELU (erf form, nn.GELU())  */
     float* y;             /* [M,N]                                     */
+    const float* weight_lo; /* [N,K] or NULL.  precision 1 only: the low part of a weight split done once by the caller -
+                               `weight` then holds the TF32-representable high part rna_tf32(W) and weight_lo =
+                               rna_tf32(W - weight) - so that the kernel splits only the activations                      */
+    int32_t block_n;      /* 0 = automatic N tile; else a multiple of 32 <= 256 (tuning)                                 */
 } cnf_linear_args;
 
 CNF_API int cnf_linear_fwd(const cnf_linear_args* a, cnf_stream_t stream);

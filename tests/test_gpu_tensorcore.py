@@ -1,8 +1,9 @@
 """GPU parity of the tcgen05 kernels: the dense projection of the coupling networks (cnf_linear_fwd / _bwd) and
 the fused final projection + mixture coupling (cnf_linear_mixcdf_fwd / _inv).
 
-Tolerances: 3xTF32 projection |err| <= 3e-6 + 6e-8 K against a float64 product of O(1) outputs (the tensor
-core accumulates in fp32 with truncation: the error grows with K); TF32 2e-2.  The fused kernel is held to
+Tolerances: 3xTF32 projection |err| <= 6e-6 + 8e-8 K against a float64 product of O(1) outputs (the tensor core
+truncates fp32 operands to TF32 and accumulates in fp32 with truncation: the dropped lo*lo term of a split done on
+truncated high parts is a coherent ~2^-22 of sum |x w|, and the accumulation error grows with K); TF32 2e-2.  The fused kernel is held to
 the flow's parity metric |a-b| <= 1e-4 |b| + 1e-5 (z), 1e-4 relative (ldj) against the CPU oracle applied to
 a float64 projection, and against the golden fixtures of the reference (nn_out reproduced as features @ I)."""
 import pytest
@@ -34,7 +35,7 @@ def test_linear_vs_float64(M, K, N, precision):
     x, w, b = _rand_linear(M, K, N, seed=M + K + N)
     y = ops.linear(dev(x), dev(w), dev(b), precision=precision)
     ref = x.double() @ w.double().t() + b.double()
-    tol = (3e-6 + 6e-8 * K) if precision == "3xtf32" else 2e-2
+    tol = (6e-6 + 8e-8 * K) if precision == "3xtf32" else 2e-2
     err = (y.double().cpu() - ref).abs().max().item()
     assert torch.isfinite(y).all()
     assert err <= tol, "max |err| %.3e > %.3e" % (err, tol)
@@ -83,9 +84,9 @@ def test_linear_backward_vs_float64(M, K, N, precision):
     ref_w = gy.double().t() @ x.double()
     ref_b = gy.double().sum(dim=0)
     # error model: 3xTF32 keeps ~fp32 products, accumulation error grows with the reduction length
-    tol_x = (3e-6 + 6e-8 * N) if precision == "3xtf32" else 2e-2
+    tol_x = (6e-6 + 8e-8 * N) if precision == "3xtf32" else 2e-2
     scale_w = max(1.0, (M / N) ** 0.5)                # |grad_W| entries are O(sqrt(M/N))
-    tol_w = ((3e-6 + 6e-8 * min(M, 4096)) if precision == "3xtf32" else 2e-2) * scale_w
+    tol_w = ((6e-6 + 8e-8 * min(M, 4096)) if precision == "3xtf32" else 2e-2) * scale_w
     for got, ref, tol, what in ((gx, ref_x, tol_x, "grad_x"), (gw, ref_w, tol_w, "grad_weight"), (gb, ref_b, 1e-4 * scale_w, "grad_bias")):
         assert got.shape == ref.shape, what
         assert torch.isfinite(got).all(), what
@@ -241,3 +242,24 @@ def test_fused_next_block_epilogue_and_masked_output(B, S, C, K, H, padded):
     assert_close(z2, z1, rtol=1e-5, atol=2e-6, what="z after the fused next block")
     assert_close(l2, l1, rtol=1e-6, atol=1e-5, what="ldj")
     assert torch.equal(zm, z2 * dev(nmask))
+
+
+@pytest.mark.parametrize("M,K,N", [(1000, 16, 416), (4096, 384, 208), (777, 36, 418), (20480, 384, 2316)])
+def test_linear_presplit_weight(M, K, N):
+    """nn.Parameter weights take the pre-split path (high / low parts cached per parameter version, the kernel splits only
+    the activations): same result as the in-kernel split within the 3xTF32 error, and the cache follows in-place updates."""
+    from categoricalnf_b200 import ops
+    x, w, b = _rand_linear(M, K, N, seed=M + K + N + 3)
+    wp = torch.nn.Parameter(w.cuda())
+    ref = x.double() @ w.double().t() + b.double()
+    y = ops.linear(x.cuda(), wp, b.cuda())
+    tol = 4e-6 + 8e-8 * K
+    err = (y.double().cpu() - ref).abs().max().item()
+    assert err <= tol, "pre-split: max |err| %.3e > %.3e" % (err, tol)
+    assert ops.weight_split(wp) is not None and ops.weight_split(w.cuda()) is None
+    with torch.no_grad():
+        wp.mul_(1.5)                                           # version bump -> split recomputed
+    y2 = ops.linear(x.cuda(), wp, b.cuda())
+    ref2 = x.double() @ (1.5 * w.double()).t() + b.double()
+    err2 = (y2.double().cpu() - ref2).abs().max().item()
+    assert err2 <= 1.5 * tol, "after update: max |err| %.3e" % err2

@@ -56,6 +56,14 @@ if "--time" in sys.argv:
         w = torch.randn(N, K, device=dev) / K ** 0.5
         b = torch.randn(N, device=dev)
         t_tc = timeit(lambda: ops.linear(x, w, b, precision=prec))
+        if prec == "3xtf32":
+            wp = w.clone()
+            wp._cnf_cache_lo = True          # weight split precomputed and cached (what nn.Parameters get)
+            t_pre = timeit(lambda: ops.linear(x, wp, b, precision=prec))
+            t_pre128 = timeit(lambda: ops.linear(x, wp, b, precision=prec, block_n=128))
+            t_128 = timeit(lambda: ops.linear(x, w, b, precision=prec, block_n=128))
+            print("     3xtf32 variants M=%d K=%d N=%d: in-kernel split %.3f ms | BN=128 %.3f | pre-split W %.3f | pre-split W, BN=128 %.3f"
+                  % (M, K, N, t_tc, t_128, t_pre, t_pre128), flush=True)
         torch.backends.cuda.matmul.allow_tf32 = False
         t_fp32 = timeit(lambda: torch.nn.functional.linear(x, w, b))
         torch.backends.cuda.matmul.allow_tf32 = True
