@@ -439,3 +439,95 @@ def lm_flow_forward(tokens, u_noise, enc, blocks, pad=None, length=None, beta=1.
     if pad is not None:
         lp = lp * pad
     return z, ldj, lp.sum(dim=[1, 2])
+
+
+# ---------------------------------------------------------------------------
+# a12 with linear flows (BASELINE config 1: "4 affine couplings"): LinearCategoricalEncoding(num_flows > 0)
+#   flows = num_flows x [ExtActNorm, InvertibleConv, affine CouplingLayer(LinearNet)]   (linear_encoding.py:224-256)
+# Works on a state dict with the reference's parameter names.
+# ---------------------------------------------------------------------------
+def _sd_linear(sd, key, x):
+    return F.linear(x, sd[key + ".weight"], sd[key + ".bias"])
+
+
+def linear_net(sd, pre, x, ext_input=None):
+    """LinearNet.forward (layers/networks/help_layers.py:76-102): inp_layer (Linear + GELU), external input concatenated,
+    main_net = (Linear, GELU) x num_layers + Linear."""
+    h = F.gelu(_sd_linear(sd, pre + "inp_layer.0", x))
+    if ext_input is not None:
+        h = torch.cat([h, ext_input], dim=-1)
+    idx = sorted({int(k[len(pre + "main_net."):].split(".")[0]) for k in sd if k.startswith(pre + "main_net.")})
+    for n, i in enumerate(idx):
+        h = _sd_linear(sd, "%smain_net.%d" % (pre, i), h)
+        if n < len(idx) - 1:
+            h = F.gelu(h)
+    return h
+
+
+def encoding_flow_pass(sd, z, tokens, num_flows, reverse):
+    """``_flow_forward`` (linear_encoding.py:134-141) on ``z`` [M,1,D] for class ids ``tokens`` [M,1] -> (z, ldj [M])."""
+    D = z.shape[-1]
+    embed = sd["embed_layer.weight"][tokens]                                   # [M,1,E]
+    mask = expand_mask(channel_mask(D, 0.5), z)
+    ldj = z.new_zeros(z.size(0))
+    order = range(num_flows) if not reverse else reversed(range(num_flows))
+    for f in order:
+        a, c, p = 3 * f, 3 * f + 1, 3 * f + 2
+        w, sldj = invconv_weight(*(sd["flow_layers.%d.%s" % (c, k)] for k in ("p", "l", "log_s", "u", "sign_s")))
+        ext = _sd_linear(sd, "flow_layers.%d.pred_net.layer" % a, embed)
+        bias, raw = ext.chunk(2, dim=2)
+
+        def coupling(zz, ll):
+            nn_out = linear_net(sd, "flow_layers.%d.nn." % p, zz * mask, ext_input=embed)
+            out, l = affine_coupling(zz, nn_out, mask, sd["flow_layers.%d.scaling_factor" % p], reverse=reverse)
+            return out, ll + l
+
+        if not reverse:
+            z, ldj = ext_actnorm(z, bias, raw, ldj)
+            z, ldj = invconv(z, w, sldj, ldj)
+            z, ldj = coupling(z, ldj)
+        else:
+            z, ldj = coupling(z, ldj)
+            z, ldj = invconv(z, invconv_inverse(w), sldj, ldj, reverse=True)
+            z, ldj = ext_actnorm(z, bias, raw, ldj, reverse=True)
+    return z, ldj
+
+
+def categ_encode_flows(sd, x, u_noise, num_flows, beta=1.0, pad=None):
+    """LinearCategoricalEncoding.forward with linear flows (linear_encoding.py:59-132, 153-174).
+    Returns (z [B,S,D], ldj [B])."""
+    B, S = x.shape
+    V = sd["category_prior"].shape[0]
+    D = u_noise.shape[-1]
+    tok = x.reshape(B * S, 1)
+    padf = pad.reshape(B * S, 1, -1) if pad is not None else torch.ones(B * S, 1, 1)
+    z0 = logistic_from_uniform(u_noise)                                         # prior of the encoding flows (:39)
+    init_log_p = logistic_log_prob(z0).sum(dim=[1, 2])
+    z, ldj_fwd = encoding_flow_pass(sd, z0, tok, num_flows, reverse=False)
+    log_point = init_log_p - ldj_fwd + sd["category_prior"][tok.squeeze(-1)]
+    z_all = z.expand(-1, V, -1).reshape(-1, 1, D)
+    cls = torch.arange(V)[None, :].expand(B * S, -1).reshape(-1, 1)
+    z_back, ldj_back = encoding_flow_pass(sd, z_all, cls, num_flows, reverse=True)
+    back_log_p = logistic_log_prob(z_back).sum(dim=[1, 2])
+    denom = (back_log_p + ldj_back).view(B * S, V) + sd["category_prior"][None, :]
+    own = F.one_hot(tok.squeeze(-1), V).to(denom.dtype)
+    denom = denom * (1 - own) + log_point.unsqueeze(-1) * own
+    class_prob_log = log_point - torch.logsumexp(denom, dim=-1)
+    ldj_loc = (beta * class_prob_log - (init_log_p - ldj_fwd)) * padf.squeeze()
+    return (z * padf).reshape(B, S, D), ldj_loc.reshape(B, S).sum(dim=-1)
+
+
+def categ_decode_flows(sd, z, num_flows):
+    """``_posterior_sample`` (linear_encoding.py:184-196): arg-max class of the flow posterior."""
+    B, S, D = z.shape
+    V = sd["category_prior"].shape[0]
+    z_all = z.reshape(B * S, 1, D).expand(-1, V, -1).reshape(-1, 1, D)
+    cls = torch.arange(V)[None, :].expand(B * S, -1).reshape(-1, 1)
+    z_back, ldj_back = encoding_flow_pass(sd, z_all, cls, num_flows, reverse=True)
+    logp = (logistic_log_prob(z_back).sum(dim=[1, 2]) + ldj_back).view(B * S, V) + sd["category_prior"][None, :]
+    return logp.argmax(dim=-1).reshape(B, S)
+
+
+def decoder_linear(sd, z, pre=""):
+    """DecoderLinear.forward (layers/categorical_encoding/decoder.py:56-60)."""
+    return torch.log_softmax(linear_net(sd, pre + "layers.", decoder_features(z)), dim=-1)

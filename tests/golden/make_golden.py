@@ -697,6 +697,47 @@ def gold_graphcnf(seed):
          z_edges_init=z_edges_init, z_nodes_init=z_nodes_init, x_smp=x_smp, adj_smp=adj_smp, ldj_smp=ldj_smp, N=N, **sd)
 
 
+def gold_encoding_variants(seed):
+    """Encodings beyond the plain mixture model: (1) linear flows - BASELINE config 1's "4 affine couplings":
+    LinearCategoricalEncoding(num_flows=4) = 4 x [ExtActNorm, InvertibleConv, affine CouplingLayer(LinearNet)]
+    (linear_encoding.py:224-256), forward in eval mode and reverse decode; (2) DecoderLinear (decoder.py:35-63), the posterior
+    network of the decoder-based / variational encodings.  The encodings that USE the decoder cannot run upstream:
+    _decoder_forward gathers a [B*S,1,V] tensor with a [B*S,1] index (linear_encoding.py:149, variational_encoding.py:127), so
+    there is nothing to record for them beyond the decoder itself.  State dicts under the reference's parameter names."""
+    from layers.categorical_encoding.decoder import DecoderLinear
+    g = torch.Generator().manual_seed(seed)
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+    B, S, V, D = 6, 5, 4, 4
+    x = torch.randint(0, V, (B, S), generator=g)
+    length = torch.tensor([5, 3, 5, 1, 4, 2])
+    pad = lengths_to_pad(length, S)
+    out = dict(x=x, pad=pad, V=V, D=D)
+    enc = _quiet(LinearCategoricalEncoding, num_dimensions=D, flow_config={"num_flows": 4, "hidden_layers": 2, "hidden_size": 32},
+                 vocab_size=V)
+    _randomise(enc, g, std=0.3)
+    enc.eval()
+    noise = {}
+
+    def rec(sample_shape=torch.Size()):
+        noise["u"] = torch.rand(sample_shape, generator=g)
+        return noise["u"]
+
+    enc.prior_distribution.distribution.sample = rec
+    with torch.no_grad():
+        z, ldj, _ = enc(x, reverse=False, channel_padding_mask=pad, beta=0.8)
+        x_dec = enc(z, reverse=True, channel_padding_mask=pad)[0]
+    out.update(flows_u=noise["u"], flows_z=z, flows_ldj=ldj, flows_x_dec=x_dec)
+    out.update({"sd_flows__" + k: v for k, v in enc.state_dict().items()})
+    dec = DecoderLinear(num_categories=V, embed_dim=D, hidden_size=24, num_layers=2, class_prior_log=np.log(np.array([0.4, 0.3, 0.2, 0.1], dtype=np.float32)))
+    _randomise(dec, g, std=0.3)
+    z_dec = torch.randn(B * S, 1, D, generator=g)
+    with torch.no_grad():
+        out.update(dec_z=z_dec, dec_log_probs=dec(z_dec))
+    out.update({"sd_dec__" + k: v for k, v in dec.state_dict().items()})
+    save("encoding_variants", **out)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(4)
     if ONLY:
@@ -707,6 +748,7 @@ if __name__ == "__main__":
                                                                                    max_neighbours=0)),
              "graph_flow": lambda: gold_graph_node_flow(seed=27),
              "graphcnf": lambda: gold_graphcnf(seed=32),
+             "encoding_variants": lambda: gold_encoding_variants(seed=33),
              "edge_gnn": lambda: (gold_edge_gnn("edge_gnn_attn_sparse", 28, False, True), gold_edge_gnn("edge_gnn_attn_dense", 29, False, False),
                                   gold_edge_gnn("edge_gnn_qkv_dense", 30, True, False, N=9), gold_edge_gnn("edge_gnn_qkv_sparse", 31, True, True))}[_n]()
         sys.exit(0)
@@ -745,3 +787,4 @@ if __name__ == "__main__":
     gold_edge_gnn("edge_gnn_qkv_dense", 30, True, False, N=9)
     gold_edge_gnn("edge_gnn_qkv_sparse", 31, True, True)
     gold_graphcnf(seed=32)
+    gold_encoding_variants(seed=33)

@@ -261,3 +261,15 @@ def test_edge_gnn(name):
                                qkv=bool(g.qkv), pad=g.pad, binary_adjacency=binary, max_neighbours=g.max_neighbours)
     assert_close(nodes, g.nodes_out, rtol=1e-5, atol=2e-6, what="nodes_out")
     assert_close(edges, g.edges_out, rtol=1e-5, atol=2e-6, what="edges_out")
+
+
+def test_encoding_with_linear_flows_and_decoder():
+    """BASELINE config 1's encoder (4 x [ExtActNorm, InvConv, affine coupling]) and DecoderLinear."""
+    g = load_golden("encoding_variants")
+    sd = {k[len("sd_flows__"):]: v for k, v in g.items() if k.startswith("sd_flows__")}
+    z, ldj = O.categ_encode_flows(sd, g.x, g.flows_u, num_flows=4, beta=0.8, pad=g.pad)
+    assert_close(z, g.flows_z, rtol=1e-5, atol=2e-6, what="z")
+    assert_close(ldj, g.flows_ldj, rtol=1e-5, atol=2e-5, what="ldj")
+    assert torch.equal(O.categ_decode_flows(sd, g.flows_z, num_flows=4), g.flows_x_dec)
+    sdd = {k[len("sd_dec__"):]: v for k, v in g.items() if k.startswith("sd_dec__")}
+    assert_close(O.decoder_linear(sdd, g.dec_z), g.dec_log_probs, rtol=1e-5, atol=2e-6, what="decoder log-probs")
