@@ -38,7 +38,7 @@ struct BwdParams {
     long long P;
     int S, C, K, PN, TP;
     MaskView mask;
-    int vec_params;
+    int vec_params, vec_out;
     float reg_max, reg_factor;
     int use_reg;
     int pre;
@@ -48,24 +48,27 @@ template <typename T>
 struct Mth;
 template <>
 struct Mth<float> {
-    static __device__ __forceinline__ float ex(float v) { return __expf(v); }
-    static __device__ __forceinline__ float lg(float v) { return __logf(v); }
-    static __device__ __forceinline__ float th(float v) { return 1.0f - 2.0f / (1.0f + __expf(2.0f * v)); }
+    static __device__ __forceinline__ float ex(float v) { return fast_exp(v); }
+    static __device__ __forceinline__ float lg(float v) { return fast_log(v); }
+    static __device__ __forceinline__ float th(float v) { return tanh_from_2log2e(v * (2.0f * kLog2e)); }
+    static __device__ __forceinline__ float rc(float v) { return rcp(v); }     // 1 ulp: no IEEE division sequences
 };
 template <>
 struct Mth<double> {
     static __device__ __forceinline__ double ex(double v) { return exp(v); }
     static __device__ __forceinline__ double lg(double v) { return log(v); }
     static __device__ __forceinline__ double th(double v) { return tanh(v); }
+    static __device__ __forceinline__ double rc(double v) { return 1.0 / v; }
 };
 
 // Gradient of one transformed element.  `rec` (shared memory) holds [t, raw log_s, log_pi[K], mu[K],
-// raw log_scale[K]] on entry and the gradient with respect to those entries on exit.  Returns false
-// (nothing written) when T = float and the element is outside the fp32-safe range.
+// raw log_scale[K]] on entry and the gradient with respect to those entries on exit; ``gmsf_k[K]`` receives the
+// element's contribution to d/d mixture_scaling_factor (written only when the parameters are not pre-bounded).
+// Returns false (nothing written) when T = float and the element is outside the fp32-safe range.
 template <typename T, int KT>
 __device__ __forceinline__ bool mix_backward_elem(float xf, float* rec, const float* mfac, float sfac, int Krt, bool pre,
                                                   float g_out_f, float gl_f, bool use_reg, float reg_max, float reg_factor,
-                                                  float* gx_out, float* gsf_out, float* s_gmsf) {
+                                                  float* gx_out, float* gsf_out, float* gmsf_k) {
     using M = Mth<T>;
     const int K = KT > 0 ? KT : Krt;
     const T x = (T)xf, g_out = (T)g_out_f, gl = (T)gl_f;
@@ -80,11 +83,11 @@ __device__ __forceinline__ bool mix_backward_elem(float xf, float* rec, const fl
     for (int k = 0; k < K; ++k) {
         const float mf = pre ? 1.0f : mfac[k];
         // the reference bounds the raw log-scales in float32 before its .double() (:157-178)
-        const T ls = pre ? (T)ms[k] : M::th((T)ms[k] / (T)fmaxf(mf, 1.0f)) * (T)mf;
+        const T ls = pre ? (T)ms[k] : M::th((T)ms[k] * M::rc((T)fmaxf(mf, 1.0f))) * (T)mf;
         const T e = M::ex(-ls);
         const T u = (x - (T)mu[k]) * e;
         const T ea = M::ex(-fabs(u));
-        const T r = (T)1 / ((T)1 + ea);
+        const T r = M::rc((T)1 + ea);
         const T q = ea * r;
         const T sg = u >= 0 ? r : q, tg = u >= 0 ? q : r;   // sigma, 1 - sigma
         const T w = M::ex((T)lp[k] - (T)m);
@@ -93,13 +96,13 @@ __device__ __forceinline__ bool mix_backward_elem(float xf, float* rec, const fl
         Gs += w * tg;
         fs += w * (q * r) * e;
     }
-    const T iw = (T)1 / W;
+    const T iw = M::rc(W);
     const T F = Fs * iw, G = Gs * iw, f = fs * iw;
     if (sizeof(T) == sizeof(float)) {
         if (!(F >= (T)1e-30 && G >= (T)1e-12 && f >= (T)1e-30)) return false;
     }
     const float sf_max = fmaxf(sfac, 1.0f);
-    const T ths = pre ? (T)0 : M::th((T)rec[1] / (T)sf_max);
+    const T ths = pre ? (T)0 : M::th((T)rec[1] * M::rc((T)sf_max));
     const T log_s = pre ? (T)rec[1] : ths * (T)sfac;
     const T c22 = (T)-50.65687204586900;   // log(1e-22), safe_log clamp (:197-198)
     const T lF = M::lg(F), lG = M::lg(G);
@@ -117,7 +120,7 @@ __device__ __forceinline__ bool mix_backward_elem(float xf, float* rec, const fl
         if (cF && lF * il10 < -(T)reg_max) LlF += gl * (T)reg_factor * il10;
         if (cG && lG * il10 < -(T)reg_max) LlG += gl * (T)reg_factor * il10;
     }
-    const T LF = LlF / F, LG = LlG / G, Lf = gl / f;
+    const T LF = LlF * M::rc(F), LG = LlG * M::rc(G), Lf = gl * M::rc(f);
     const T Ssum = LF * F + LG * G + Lf * f;             // sum_j pi_j P_j
     T gx = 0;
 #pragma unroll(KT > 0 ? KT : 4)
@@ -125,12 +128,13 @@ __device__ __forceinline__ bool mix_backward_elem(float xf, float* rec, const fl
         const float mf = pre ? 1.0f : mfac[k];
         const float mf_max = fmaxf(mf, 1.0f);
         const T raw = (T)ms[k];
-        const T thk = pre ? (T)0 : M::th(raw / (T)mf_max);
+        const T imf_max = M::rc((T)mf_max);
+        const T thk = pre ? (T)0 : M::th(raw * imf_max);
         const T ls = pre ? raw : thk * (T)mf;
         const T e = M::ex(-ls);
         const T u = (x - (T)mu[k]) * e;
         const T ea = M::ex(-fabs(u));
-        const T r = (T)1 / ((T)1 + ea);
+        const T r = M::rc((T)1 + ea);
         const T q = ea * r;
         const T sg = u >= 0 ? r : q, tg = u >= 0 ? q : r;
         const T d = q * r;
@@ -147,10 +151,11 @@ __device__ __forceinline__ bool mix_backward_elem(float xf, float* rec, const fl
             ms[k] = (float)Lls;
         } else {
             const T sech2 = (T)1 - thk * thk;
-            ms[k] = (float)(Lls * sech2 * (T)mf / (T)mf_max);
-            // ls = tanh(raw / max(M,1)) M, M = e^{msf}: d ls / d msf
-            const T dmsf = (T)mf * (thk - (mf > 1.0f ? sech2 * raw / (T)mf : (T)0));
-            atomicAdd(s_gmsf + k, (float)(Lls * dmsf));
+            ms[k] = (float)(Lls * sech2 * (T)mf * imf_max);
+            // ls = tanh(raw / max(M,1)) M, M = e^{msf}: d ls / d msf  (for M > 1: max(M,1) = M)
+            const T dmsf = (T)mf * thk - (mf > 1.0f ? sech2 * raw : (T)0);
+            if (KT > 0) gmsf_k[k] = (float)(Lls * dmsf);            // registers, reduced across the warp by the caller
+            else atomicAdd(gmsf_k + k, (float)(Lls * dmsf));       // generic K / float64 path: shared-memory accumulator
         }
     }
     rec[0] = (float)g_t;
@@ -159,8 +164,8 @@ __device__ __forceinline__ bool mix_backward_elem(float xf, float* rec, const fl
     } else {
         const T sech2 = (T)1 - ths * ths;
         const T raw = (T)rec[1];
-        *gsf_out += (float)(g_logs * (T)sfac * (ths - (sfac > 1.0f ? sech2 * raw / (T)sfac : (T)0)));
-        rec[1] = (float)(g_logs * sech2 * (T)sfac / (T)sf_max);
+        *gsf_out += (float)(g_logs * ((T)sfac * ths - (sfac > 1.0f ? sech2 * raw : (T)0)));
+        rec[1] = (float)(g_logs * sech2 * (T)sfac * M::rc((T)sf_max));
     }
     *gx_out = (float)gx;
     return true;
@@ -231,35 +236,72 @@ __global__ void __launch_bounds__(kThreads) mixcdf_bwd_kernel(const BwdParams p)
     // ---- one thread per (position, transformed channel) ----------------------------------------
     const int nelem = rows * Ct;
     const float inv_ct = 1.0f / (float)Ct;
-    for (int e = tid; e < nelem; e += kThreads) {
-        const int r = fast_div(e, inv_ct), j = e - r * Ct;
-        const long long pos = pos0 + r;
-        const int ch = p.mask.tch[j];
-        float* rec = s_par + (size_t)e * PN;
-        const float padv = p.pad ? p.pad[pos] : 1.0f;
-        bool active = padv != 0.0f;
-        if (p.mask.s_period > 0) {
-            const int s = (int)(pos % p.S);
-            if ((p.mask.cond_s >> (s % p.mask.s_period)) & 1ull) active = false;
+    // d/d mixture_scaling_factor: per-thread registers, summed over the lanes that share a channel (lane % Ct when Ct
+    // divides 32) before touching the shared accumulator - 32/Ct times fewer shared atomics
+    const bool warp_reduce = KT > 0 && (32 % Ct) == 0 && (kThreads % Ct) == 0;
+    for (int e0 = 0; e0 < nelem; e0 += kThreads) {
+        const int e = e0 + tid;
+        float gm[KT > 0 ? KT : 1];
+#pragma unroll
+        for (int k = 0; k < (KT > 0 ? KT : 1); ++k) gm[k] = 0.f;
+        float gsf = 0.f;
+        int j = 0;
+        if (e < nelem) {
+            const int r = fast_div(e, inv_ct);
+            j = e - r * Ct;
+            const long long pos = pos0 + r;
+            const int ch = p.mask.tch[j];
+            float* rec = s_par + (size_t)e * PN;
+            const float padv = p.pad ? p.pad[pos] : 1.0f;
+            bool active = padv != 0.0f;
+            if (p.mask.s_period > 0) {
+                const int s = (int)(pos % p.S);
+                if ((p.mask.cond_s >> (s % p.mask.s_period)) & 1ull) active = false;
+            }
+            const float gzo = s_g[r * C + ch];
+            if (!active) {   // copied through (times pad): no parameter gradient
+                for (int i = 0; i < PN; ++i) rec[i] = 0.f;
+                s_g[r * C + ch] = gzo * padv;
+            } else {
+                // z_final = (out * pad + x (1 - pad)) * pad, ldj_e * pad (mixture_cdf_layer.py:76,99-101,137-138)
+                const float g_out = gzo * padv * padv;
+                const float gl = (p.gldj ? p.gldj[pos / p.S] : 0.f) * padv;
+                const float x = s_z[r * C + ch];
+                float gx = 0.f;
+                const bool ok = mix_backward_elem<float, KT>(x, rec, s_mfac + j * K, s_fac[j], K, p.pre != 0, g_out, gl, p.use_reg != 0,
+                                                              p.reg_max, p.reg_factor, &gx, &gsf, KT > 0 ? gm : s_gmsf + j * K);
+                if (!ok) {
+#pragma unroll
+                    for (int k = 0; k < (KT > 0 ? KT : 1); ++k) gm[k] = 0.f;
+                    mix_backward_elem<double, 0>(x, rec, s_mfac + j * K, s_fac[j], K, p.pre != 0, g_out, gl, p.use_reg != 0, p.reg_max,
+                                                 p.reg_factor, &gx, &gsf, s_gmsf + j * K);
+                }
+                s_g[r * C + ch] = gx + gzo * (1.0f - padv) * padv;
+            }
         }
-        const float gzo = s_g[r * C + ch];
-        if (!active) {   // copied through (times pad): no parameter gradient
-            for (int i = 0; i < PN; ++i) rec[i] = 0.f;
-            s_g[r * C + ch] = gzo * padv;
-            continue;
+        if (p.pre == 0 && (p.gsf != nullptr || p.gmsf != nullptr)) {
+            if (warp_reduce) {
+                for (int d = 16; d >= Ct; d >>= 1) {
+                    gsf += __shfl_xor_sync(0xffffffffu, gsf, d);
+#pragma unroll
+                    for (int k = 0; k < (KT > 0 ? KT : 1); ++k) gm[k] += __shfl_xor_sync(0xffffffffu, gm[k], d);
+                }
+                const int jj = (tid & 31) % Ct;      // == j for every lane that holds an element (kThreads % Ct == 0)
+                if ((tid & 31) < Ct) {
+                    if (gsf != 0.f) atomicAdd(s_gsf + jj, gsf);
+#pragma unroll
+                    for (int k = 0; k < (KT > 0 ? KT : 1); ++k)
+                        if (gm[k] != 0.f) atomicAdd(s_gmsf + jj * K + k, gm[k]);
+                }
+            } else if (e < nelem) {
+                if (gsf != 0.f) atomicAdd(s_gsf + j, gsf);
+                if (KT > 0) {
+#pragma unroll
+                    for (int k = 0; k < (KT > 0 ? KT : 1); ++k)
+                        if (gm[k] != 0.f) atomicAdd(s_gmsf + j * K + k, gm[k]);
+                }
+            }
         }
-        // z_final = (out * pad + x (1 - pad)) * pad, ldj_e * pad (mixture_cdf_layer.py:76,99-101,137-138)
-        const float g_out = gzo * padv * padv;
-        const float gl = (p.gldj ? p.gldj[pos / p.S] : 0.f) * padv;
-        const float x = s_z[r * C + ch];
-        float gx = 0.f, gsf = 0.f;
-        const bool ok = mix_backward_elem<float, KT>(x, rec, s_mfac + j * K, s_fac[j], K, p.pre != 0, g_out, gl, p.use_reg != 0,
-                                                      p.reg_max, p.reg_factor, &gx, &gsf, s_gmsf + j * K);
-        if (!ok)
-            mix_backward_elem<double, 0>(x, rec, s_mfac + j * K, s_fac[j], K, p.pre != 0, g_out, gl, p.use_reg != 0, p.reg_max,
-                                         p.reg_factor, &gx, &gsf, s_gmsf + j * K);
-        s_g[r * C + ch] = gx + gzo * (1.0f - padv) * padv;
-        if (gsf != 0.f) atomicAdd(s_gsf + j, gsf);
     }
     __syncthreads();
     // conditioner channels: dL/dz = dL/dz_out * pad
@@ -274,7 +316,27 @@ __global__ void __launch_bounds__(kThreads) mixcdf_bwd_kernel(const BwdParams p)
     }
 
     // ---- dL/dnn_out rows: gradient records of the transformed channels, zeros elsewhere ----------
-    if ((PN & 1) == 0) {   // even K: 8-byte granules never straddle a record
+    if (p.vec_params && p.vec_out) {
+        // contiguous, 16-byte aligned run of transformed records per position: copy it with 16-byte stores and zero the
+        // conditioner records before / after it the same way (no per-granule record lookup)
+        const int L4 = L >> 2, row4 = (C * PN) >> 2, off4 = (p.mask.c0 * PN) >> 2;
+        const int Z4 = row4 - L4;                               // zero float4 per position
+        const float inv_l4 = 1.0f / (float)L4;
+        float4* dst = reinterpret_cast<float4*>(p.gnn + pos0 * (long long)C * PN);
+        const float4* src = reinterpret_cast<const float4*>(s_par);
+        for (int i = tid; i < rows * L4; i += kThreads) {
+            const int r = fast_div(i, inv_l4), q = i - r * L4;
+            stg_stream4(dst + (size_t)r * row4 + off4 + q, src[i]);
+        }
+        if (Z4 > 0) {
+            const float inv_z4 = 1.0f / (float)Z4;
+            const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = tid; i < rows * Z4; i += kThreads) {
+                const int r = fast_div(i, inv_z4), q = i - r * Z4;
+                stg_stream4(dst + (size_t)r * row4 + (q < off4 ? q : q + L4), zero);
+            }
+        }
+    } else if ((PN & 1) == 0) {   // even K: 8-byte granules never straddle a record
         const int PN2 = PN >> 1;
         const int row2 = C * PN2, total = rows * row2;
         const float inv_row = 1.0f / (float)row2, inv_pn2 = 1.0f / (float)PN2;
@@ -372,6 +434,7 @@ extern "C" int cnf_mixcdf_bwd(const cnf_mixcdf_bwd_args* a, cnf_stream_t stream_
     const long long rowlen = (long long)a->C * p.PN;
     p.vec_params = p.mask.contiguous && (L % 4 == 0) && (rowlen % 4 == 0) && ((p.mask.c0 * p.PN) % 4 == 0) &&
                    ((reinterpret_cast<uintptr_t>(a->nn_out) & 15) == 0);
+    p.vec_out = (reinterpret_cast<uintptr_t>(a->grad_nn_out) & 15) == 0 ? 1 : 0;
     CNF_REQUIRE((reinterpret_cast<uintptr_t>(a->grad_nn_out) & 7) == 0, "grad_nn_out must be 8-byte aligned");
     CNF_SUPPORTED((long long)TP * a->C * p.PN < (1 << 21), "tile too large for the index arithmetic");
     const size_t smem = bwd_smem(TP, L, a->C, Ct, a->K);

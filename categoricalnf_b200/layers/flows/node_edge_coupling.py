@@ -16,18 +16,8 @@ import torch
 import torch.nn as nn
 
 from ... import functional as CF
+from ._masks import mask_lists
 from .flow_layer import FlowLayer
-
-
-def _channel_mask_list(mask, seq_len):
-    """``mask[None, :min(mask.size(0), seq_len), :]`` of the reference (:52-53) as the kernel's host mask lists."""
-    m = mask.detach().to("cpu", torch.float32)
-    m = m[:min(m.size(0), seq_len)]
-    if m.size(0) == 1:
-        return m.flatten().tolist(), None
-    if m.size(1) == 1:
-        return None, m.flatten().tolist()
-    raise NotImplementedError("joint position x channel masks %s are not supported" % (tuple(mask.shape),))
 
 
 class NodeEdgeCoupling(FlowLayer):
@@ -60,10 +50,10 @@ class NodeEdgeCoupling(FlowLayer):
         # The reference zeroes the network output at padded nodes / invalid pairs (:64,:78) and the latents after
         # the transform (:74,:88); the kernel skips those positions (no parameter read, zero ldj, z_out = 0).
         z_nodes_out, nodes_ldj, nodes_reg = self._run_mixture_layer(
-            z_nodes, nn_nodes_out, self.mask_nodes, self.num_mixtures_nodes, self.scaling_factor_nodes,
+            z_nodes, nn_nodes_out, "mask_nodes", self.num_mixtures_nodes, self.scaling_factor_nodes,
             self.mixture_scaling_factor_nodes, reverse, channel_padding_mask)
         z_edges_out, edges_ldj, edges_reg = self._run_mixture_layer(
-            z_edges, nn_edges_out, self.mask_edges, self.num_mixtures_edges, self.scaling_factor_edges,
+            z_edges, nn_edges_out, "mask_edges", self.num_mixtures_edges, self.scaling_factor_edges,
             self.mixture_scaling_factor_edges, reverse, mask_valid)
         ldj = ldj + nodes_ldj + edges_ldj
         detail_out = {"ldj": ldj}
@@ -75,7 +65,9 @@ class NodeEdgeCoupling(FlowLayer):
 
     def _run_mixture_layer(self, orig_z, nn_out, mask, num_mixtures, scaling_factor, mixture_scaling_factor, reverse,
                            channel_padding_mask, **kwargs):
-        mask_c, mask_s = _channel_mask_list(mask, orig_z.size(1))
+        # `mask` names the buffer; its host form (the kernel's mask lists, truncated like `mask[None, :min(len, S), :]` of
+        # the reference, :52-53) is cached per buffer version - no device read per call
+        mask_c, mask_s = mask_lists(self, mask, orig_z.size(1))
         z_out, ldj, reg = CF.mixcdf(orig_z, nn_out, num_mixtures, scaling_factor, mixture_scaling_factor, mask_c=mask_c,
                                     mask_s=mask_s, pad=channel_padding_mask, reverse=reverse, reg_max=self.regularizer_max,
                                     reg_factor=self.regularizer_factor, training=self.training)
