@@ -137,6 +137,14 @@ class LinearBwdArgs(C.Structure):
     ]
 
 
+class CategEncodeBwdArgs(C.Structure):
+    _fields_ = [
+        ("B", C.c_int64), ("S", C.c_int64), ("V", C.c_int32), ("D", C.c_int32),
+        ("tokens", vp), ("z", vp), ("table", vp), ("category_prior", vp), ("pad", vp), ("beta", C.c_float),
+        ("grad_z", vp), ("grad_ldj", vp), ("grad_table", vp),
+    ]
+
+
 class LayernormArgs(C.Structure):
     _fields_ = [("M", C.c_int64), ("H", C.c_int32), ("x", vp), ("gamma", vp), ("beta", vp), ("eps", C.c_float), ("y", vp)]
 
@@ -269,6 +277,7 @@ ENTRY_POINTS = {
     "cnf_ext_actnorm_bwd": ExtActnormBwdArgs,
     "cnf_invconv_bwd": InvconvBwdArgs,
     "cnf_logistic_logprob_bwd": LogisticLogprobBwdArgs,
+    "cnf_categ_encode_bwd": CategEncodeBwdArgs,
 }
 PLAIN_SYMBOLS = ("cnf_last_error_string", "cnf_abi_version", "cnf_built_for_sm", "cnf_mixcdf_fusable",
                  "cnf_categ_encode_fusable", "cnf_linear_mixcdf_fusable")

@@ -190,3 +190,37 @@ def logistic_logprob(x, mu=0.0, sigma=1.0 / 1.81):
     if _needs_grad(x):
         return _LogisticLogProb.apply(x, float(mu), float(sigma))
     return ops.logistic_logprob(x, mu=mu, sigma=sigma, reduce=False, elementwise=True)[1]
+
+
+# ----------------------------------------------------------------------------------------------
+# mixture-of-logistics categorical encoding: differentiable in the class table
+# ----------------------------------------------------------------------------------------------
+class _CategEncode(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, table, tokens, category_prior, pad, cfg):
+        ldj = torch.zeros(tokens.shape[0], dtype=torch.float32, device=tokens.device)
+        z, ldj, cpl = ops.categ_encode(tokens, table, category_prior, ldj, noise=cfg["noise"], seed=cfg["seed"], offset=cfg["offset"],
+                                       pad=pad, beta=cfg["beta"], want_class_prob=True)
+        ctx.beta = cfg["beta"]
+        ctx.save_for_backward(tokens, z, table, category_prior, pad)
+        ctx.mark_non_differentiable(cpl)
+        return z, ldj, cpl
+
+    @staticmethod
+    def backward(ctx, g_z, g_ldj, g_cpl):
+        from . import ops_bwd
+        tokens, z, table, prior, pad = ctx.saved_tensors
+        gtable = ops_bwd.categ_encode_backward(tokens, z, table, prior, pad, ctx.beta, g_z, g_ldj)
+        return gtable, None, None, None, None
+
+
+def categ_encode(tokens, table, category_prior, *, noise=None, seed=0, offset=0, pad=None, beta=1.0):
+    """(z [B,S,D], ldj [B], class_prob_log [B,S]) of the mixture-of-logistics encoding (K6); differentiable with respect to
+    ``table`` [V,2D] (the noise is a constant of the graph, as in the reference where it is a fresh sample)."""
+    cfg = dict(noise=noise, seed=int(seed), offset=int(offset), beta=float(beta))
+    if _needs_grad(table):
+        return _CategEncode.apply(table, tokens, category_prior, pad, cfg)
+    ldj = torch.zeros(tokens.shape[0], dtype=torch.float32, device=tokens.device)
+    return ops.categ_encode(tokens, table, category_prior, ldj, noise=noise, seed=seed, offset=offset, pad=pad, beta=beta,
+                            want_class_prob=True)

@@ -14,6 +14,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from ... import functional as CF
 from ... import ops
 from ..flows.activation_normalization import ExtActNormFlow
 from ..flows.coupling_layer import CouplingLayer
@@ -97,6 +98,17 @@ class LinearCategoricalEncoding(FlowLayer):
                     "[!] ERROR in categorical decoding: Input must have %i latent dimensions but got %i" % (self.D, z.shape[-1])
                 z_out = ops.categ_decode(z, table, self.category_prior)
                 ldj_loc = torch.zeros(batch_size, dtype=torch.float32, device=z.device)
+            ldj = ldj_loc if ldj is None else ldj + ldj_loc
+            return z_out, ldj, detailed_ldj
+        if self._is_mixture_model() and z.is_cuda and not reverse:
+            # training: same kernel, differentiable in the class table (cnf_categ_encode_bwd); embed / pred_net receive
+            # their gradients through table = pred_net(embed.weight), a [V,E] x [E,2D] product
+            table = self.class_table()
+            seed, offset = (0, 0) if u_noise is not None else philox_stream(z.device, batch_size * seq_length * self.D)
+            z_out, ldj_loc, cpl = CF.categ_encode(z.reshape(batch_size, seq_length), table, self.category_prior, noise=u_noise,
+                                                  seed=seed, offset=offset, pad=channel_padding_mask, beta=float(beta))
+            if self.training:
+                detailed_ldj = self._stats(z_out, cpl.reshape(-1), channel_padding_mask)
             ldj = ldj_loc if ldj is None else ldj + ldj_loc
             return z_out, ldj, detailed_ldj
         return self._composed_forward(z, ldj, reverse, beta, channel_padding_mask, u_noise, **kwargs)

@@ -133,3 +133,24 @@ def logistic_logprob_backward(x, g, mu, sigma):
     a.grad_elementwise, a.grad_x = _ptr(g), _ptr(gx)
     _call("cnf_logistic_logprob_bwd", a, x3, (x3, g))
     return gx.reshape(shape)
+
+
+def categ_encode_backward(tokens, z, table, category_prior, pad, beta, g_z, g_ldj):
+    """dL/dtable [V,2D] of ``ops.categ_encode`` (``cnf_categ_encode_bwd``); ``z`` is the forward output."""
+    tokens = tokens.long().contiguous()
+    B, S = tokens.shape
+    table = _f32(table, "table")
+    V, D2 = table.shape
+    D = D2 // 2
+    z = _f32(z, "z", (B, S, D))
+    prior = _f32(category_prior, "category_prior", (V,))
+    pad = _pad_bs(pad, B, S)
+    gz = _grad(g_z, z)
+    gl = _opt_f32(g_ldj, "grad_ldj", (B,))
+    gtable = torch.zeros_like(table)
+    a = L.CategEncodeBwdArgs()
+    a.B, a.S, a.V, a.D = B, S, V, D
+    a.tokens, a.z, a.table, a.category_prior, a.pad, a.beta = _ptr(tokens), _ptr(z), _ptr(table), _ptr(prior), _ptr(pad), float(beta)
+    a.grad_z, a.grad_ldj, a.grad_table = _ptr(gz), _ptr(gl), _ptr(gtable)
+    _call("cnf_categ_encode_bwd", a, z, (tokens, z, table, prior, pad, gz, gl))
+    return gtable

@@ -380,6 +380,26 @@ typedef struct {
 
 CNF_API int cnf_linear_bwd(const cnf_linear_bwd_args* a, cnf_stream_t stream);
 
+/* Backward of cnf_categ_encode with respect to the class table (what autograd derives through the all-class expansion of
+ * linear_encoding.py:71-92,153-174).  `z` is the forward output; the noise is a constant of the graph.
+ * grad_table [V,2D] is ACCUMULATED into (zero it first); gradients with respect to embed / pred_net follow from
+ * table = pred_net(embed.weight) by ordinary autograd on that [V,2D] product. */
+typedef struct {
+    int64_t B, S;
+    int32_t V, D;
+    const int64_t* tokens;        /* [B,S]                          */
+    const float* z;               /* [B,S,D] output of the forward  */
+    const float* table;           /* [V,2D]                         */
+    const float* category_prior;  /* [V] log-softmaxed              */
+    const float* pad;             /* [B,S] or NULL                  */
+    float beta;
+    const float* grad_z;          /* [B,S,D] dL/dz                  */
+    const float* grad_ldj;        /* [B] dL/dldj or NULL            */
+    float* grad_table;            /* [V,2D], accumulated            */
+} cnf_categ_encode_bwd_args;
+
+CNF_API int cnf_categ_encode_bwd(const cnf_categ_encode_bwd_args* a, cnf_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Glue of the graph coupling networks around their projections
  *   RGCNNet / RelationGraphConv / RelationGraphAttention / GNNSkipConnection,

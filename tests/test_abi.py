@@ -52,7 +52,7 @@ def test_struct_layout_matches_c():
              "cnf_linear_bwd_args": _lib.LinearBwdArgs, "cnf_layernorm_args": _lib.LayernormArgs,
              "cnf_graph_attn_scores_args": _lib.GraphAttnScoresArgs, "cnf_graph_aggregate_args": _lib.GraphAggregateArgs,
              "cnf_skip_gate_args": _lib.SkipGateArgs, "cnf_edge_aggregate_args": _lib.EdgeAggregateArgs,
-             "cnf_pair_combine_args": _lib.PairCombineArgs,
+             "cnf_pair_combine_args": _lib.PairCombineArgs, "cnf_categ_encode_bwd_args": _lib.CategEncodeBwdArgs,
              "cnf_linear_mixcdf_args": _lib.LinearMixcdfArgs, "cnf_mixcdf_bwd_args": _lib.MixcdfBwdArgs,
              "cnf_affine_bwd_args": _lib.AffineBwdArgs, "cnf_actnorm_bwd_args": _lib.ActnormBwdArgs,
              "cnf_ext_actnorm_bwd_args": _lib.ExtActnormBwdArgs, "cnf_invconv_bwd_args": _lib.InvconvBwdArgs,

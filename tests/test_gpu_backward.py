@@ -7,6 +7,7 @@ internals), parameter gradients (long reductions) 5e-4 relative to their max."""
 import pytest
 import torch
 
+from conftest import assert_close
 from oracle import cnf_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -233,3 +234,28 @@ def test_training_step_through_the_drop_in_flow():
         grads_close(mix.nn.lin.bias.grad, lv["net_b"].grad, "block %d net bias" % i, rtol=1e-3, atol_rel=1e-3)
         grads_close(mix.scaling_factor.grad, lv["sf"].grad, "block %d sf" % i, rtol=1e-3, atol_rel=1e-3)
         grads_close(mix.mixture_scaling_factor.grad, lv["msf"].grad, "block %d msf" % i, rtol=1e-3, atol_rel=1e-3)
+
+
+@pytest.mark.parametrize("B,S,V,D,padded,beta", [(5, 17, 51, 16, False, 1.0), (4, 38, 9, 6, True, 0.7), (3, 50, 3, 2, True, 1.0),
+                                                  (2, 12, 1, 2, False, 1.0), (6, 9, 100, 16, True, 0.5), (64, 256, 51, 16, False, 1.0)])
+def test_categ_encode_backward_vs_oracle_autograd(B, S, V, D, padded, beta):
+    """cnf_categ_encode_bwd: dL/dtable against autograd through the CPU oracle's all-class expansion
+    (linear_encoding.py:71-92,153-174), with a loss that uses both outputs (z and ldj)."""
+    from categoricalnf_b200 import functional as CF
+    g = torch.Generator().manual_seed(B * S + V + D)
+    table = torch.cat([torch.randn(V, D, generator=g) * 1.5, torch.randn(V, D, generator=g) * 0.4 - 0.5], dim=1)
+    prior = torch.log_softmax(torch.randn(V, generator=g), 0)
+    x = torch.randint(0, V, (B, S), generator=g)
+    u = torch.rand(B * S, 1, D, generator=g)
+    lens = torch.randint(1, S + 1, (B,), generator=g)
+    pad = (torch.arange(S)[None, :] < lens[:, None]).float().unsqueeze(-1) if padded else None
+    wz = torch.randn(B, S, D, generator=g)
+    wl = torch.randn(B, generator=g)
+    t_ref = table.double().requires_grad_(True)
+    z_ref, ldj_ref, _ = O.categ_encode(x, u.double(), t_ref, prior.double(), beta=beta, pad=pad.double() if padded else None)
+    ((z_ref * wz.double()).sum() + (ldj_ref * wl.double()).sum()).backward()
+    t_gpu = table.cuda().requires_grad_(True)
+    z, ldj, cpl = CF.categ_encode(x.cuda(), t_gpu, prior.cuda(), noise=u.cuda(), pad=pad.cuda() if padded else None, beta=beta)
+    ((z * wz.cuda()).sum() + (ldj * wl.cuda()).sum()).backward()
+    assert_close(z, z_ref, rtol=1e-4, atol=1e-5, what="z")
+    grads_close(t_gpu.grad, t_ref.grad.float(), "dL/dtable", rtol=2e-3, atol_rel=1e-3)
