@@ -198,10 +198,11 @@ struct ConvBwdParams {
 __global__ void __launch_bounds__(256) invconv_bwd_kernel(const ConvBwdParams p) {
     extern __shared__ float sm[];
     const int C = p.C, TP = p.TP;
-    float* s_w = sm;                 // [C*C]
-    float* s_z = s_w + C * C;        // [TP*C]
+    const int CP = C | 1;            // odd pitch: the lanes of a warp hold different rows c of W -> distinct banks
+    float* s_w = sm;                 // [C][CP]
+    float* s_z = s_w + C * CP;       // [TP*C]
     float* s_g = s_z + TP * C;       // [TP*C]  dL/dout * pad
-    for (int i = threadIdx.x; i < C * C; i += 256) s_w[i] = p.w[i];
+    for (int i = threadIdx.x; i < C * C; i += 256) s_w[(i / C) * CP + (i % C)] = p.w[i];
     // per-pair accumulators: pair index = threadIdx.x + k*256 < C*C, at most C*C/256 = 16 per thread (C <= 64)
     float acc[16];
 #pragma unroll
@@ -221,7 +222,7 @@ __global__ void __launch_bounds__(256) invconv_bwd_kernel(const ConvBwdParams p)
         for (int i = threadIdx.x; i < rows * C; i += 256) {
             const int r = i / C, c = i - r * C;
             float a = 0.f;
-            for (int o = 0; o < C; ++o) a = fmaf(s_g[r * C + o], s_w[c * C + o], a);
+            for (int o = 0; o < C; ++o) a = fmaf(s_g[r * C + o], s_w[c * CP + o], a);
             p.gz[pos0 * C + i] = a;
         }
         if (p.gw != nullptr) {
@@ -342,7 +343,7 @@ extern "C" int cnf_invconv_bwd(const cnf_invconv_bwd_args* a, cnf_stream_t strea
     p.gz = a->grad_z; p.gw = a->grad_weight; p.gsldj = a->grad_sldj;
     p.B = a->B; p.S = (int)a->S; p.C = a->C; p.reverse = a->reverse;
     p.TP = a->C <= 16 ? 256 : (a->C <= 32 ? 128 : 64);
-    const size_t smem = ((size_t)a->C * a->C + 2 * (size_t)p.TP * a->C) * sizeof(float);
+    const size_t smem = ((size_t)a->C * (a->C | 1) + 2 * (size_t)p.TP * a->C) * sizeof(float);
     long long grid = (p.P + p.TP - 1) / p.TP;
     const long long cap = (long long)sm_count() * 4;
     if (grid > cap) grid = cap;
