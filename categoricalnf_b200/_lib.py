@@ -246,6 +246,24 @@ class LogisticLogprobBwdArgs(C.Structure):
     ]
 
 
+class SigmoidFlowArgs(C.Structure):
+    _fields_ = [
+        ("B", C.c_int64), ("n_per_sample", C.c_int64), ("z", vp), ("reverse", C.c_int32), ("alpha", C.c_float),
+        ("accumulate", C.c_int32), ("add_tokens", vp), ("z_out", vp), ("ldj", vp), ("ldj_elementwise", vp), ("status", vp),
+    ]
+
+
+class SigmoidFlowBwdArgs(C.Structure):
+    _fields_ = [
+        ("B", C.c_int64), ("n_per_sample", C.c_int64), ("z", vp), ("reverse", C.c_int32), ("alpha", C.c_float),
+        ("grad_z_out", vp), ("grad_ldj", vp), ("grad_ldj_elementwise", vp), ("grad_z", vp),
+    ]
+
+
+class DequantFloorArgs(C.Structure):
+    _fields_ = [("n", C.c_int64), ("V", C.c_int32), ("z", vp), ("tokens_out", vp)]
+
+
 # symbol -> argument struct; every entry point is `int f(const Args*, cnf_stream_t)`
 ENTRY_POINTS = {
     "cnf_mixcdf_fwd": MixcdfArgs,
@@ -278,6 +296,9 @@ ENTRY_POINTS = {
     "cnf_invconv_bwd": InvconvBwdArgs,
     "cnf_logistic_logprob_bwd": LogisticLogprobBwdArgs,
     "cnf_categ_encode_bwd": CategEncodeBwdArgs,
+    "cnf_sigmoid_flow": SigmoidFlowArgs,
+    "cnf_sigmoid_flow_bwd": SigmoidFlowBwdArgs,
+    "cnf_dequant_floor": DequantFloorArgs,
 }
 PLAIN_SYMBOLS = ("cnf_last_error_string", "cnf_abi_version", "cnf_built_for_sm", "cnf_mixcdf_fusable",
                  "cnf_categ_encode_fusable", "cnf_linear_mixcdf_fusable")

@@ -193,6 +193,36 @@ def logistic_logprob(x, mu=0.0, sigma=1.0 / 1.81):
 
 
 # ----------------------------------------------------------------------------------------------
+# SigmoidFlow (sigmoid_layer.py:24-48)
+# ----------------------------------------------------------------------------------------------
+class _SigmoidFlow(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, z, ldj, reverse, alpha, sum_ldj, add_tokens):
+        z_out, l = ops.sigmoid_flow(z, None, reverse=reverse, alpha=alpha, sum_ldj=sum_ldj, add_tokens=add_tokens)
+        ctx.reverse, ctx.alpha, ctx.sum_ldj = reverse, alpha, sum_ldj
+        ctx.save_for_backward(z)
+        if sum_ldj and ldj is not None:
+            l = l + ldj
+        return z_out, l
+
+    @staticmethod
+    def backward(ctx, g_z, g_l):
+        from . import ops_bwd
+        (z,) = ctx.saved_tensors
+        gz = ops_bwd.sigmoid_flow_backward(z, g_z, g_l if ctx.sum_ldj else None, None if ctx.sum_ldj else g_l,
+                                           ctx.reverse, ctx.alpha)
+        return gz, (g_l if ctx.sum_ldj else None), None, None, None, None
+
+
+def sigmoid_flow(z, ldj=None, *, reverse=False, alpha=1e-5, sum_ldj=True, add_tokens=None):
+    """(z_out, ldj) of SigmoidFlow in its effective direction; ``ldj`` is a new tensor (``ldj + layer_ldj``, :44)."""
+    if _needs_grad(z, ldj):
+        return _SigmoidFlow.apply(z, ldj, bool(reverse), float(alpha), bool(sum_ldj), add_tokens)
+    return ops.sigmoid_flow(z, ldj, reverse=reverse, alpha=alpha, sum_ldj=sum_ldj, add_tokens=add_tokens)
+
+
+# ----------------------------------------------------------------------------------------------
 # mixture-of-logistics categorical encoding: differentiable in the class table
 # ----------------------------------------------------------------------------------------------
 class _CategEncode(torch.autograd.Function):

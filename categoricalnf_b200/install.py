@@ -4,7 +4,7 @@
 :mod:`categoricalnf_b200.layers` under the module names the reference's experiments import
 (``layers.flows.coupling_layer`` ...).  Because Python consults ``sys.modules`` first, every
 ``from layers.flows.mixture_cdf_layer import MixtureCDFCoupling`` in ``experiments/*`` and in the
-reference's un-replaced modules (sigmoid flow, graph networks, ...) then resolves to the CUDA-backed
+reference's un-replaced modules (baseline models, tasks, ...) then resolves to the CUDA-backed
 class; nothing in the checkout is edited.  Call it before importing anything from the checkout.
 """
 from __future__ import annotations
@@ -24,9 +24,11 @@ REPLACED = {
     "layers.flows.activation_normalization": "flows.activation_normalization",
     "layers.flows.permutation_layers": "flows.permutation_layers",
     "layers.flows.distributions": "flows.distributions",
+    "layers.flows.sigmoid_layer": "flows.sigmoid_layer",
     "layers.categorical_encoding.decoder": "categorical_encoding.decoder",
     "layers.categorical_encoding.linear_encoding": "categorical_encoding.linear_encoding",
     "layers.categorical_encoding.variational_encoding": "categorical_encoding.variational_encoding",
+    "layers.categorical_encoding.variational_dequantization": "categorical_encoding.variational_dequantization",
     "layers.categorical_encoding.mutils": "categorical_encoding.mutils",
     # GraphCNF's joint node+edge coupling lives under experiments/ upstream but is hot-path row a14
     "experiments.molecule_generation.graph_node_edge_coupling": "flows.node_edge_coupling",

@@ -2,7 +2,8 @@
 from .decoder import DecoderLinear, create_decoder, create_embed_layer
 from .linear_encoding import LinearCategoricalEncoding
 from .variational_encoding import VariationalCategoricalEncoding
+from .variational_dequantization import VariationalDequantization
 from .mutils import add_encoding_parameters, create_encoding, encoding_args_to_params
 
 __all__ = ["DecoderLinear", "create_decoder", "create_embed_layer", "LinearCategoricalEncoding",
-           "VariationalCategoricalEncoding", "add_encoding_parameters", "create_encoding", "encoding_args_to_params"]
+           "VariationalCategoricalEncoding", "VariationalDequantization", "add_encoding_parameters", "create_encoding", "encoding_args_to_params"]

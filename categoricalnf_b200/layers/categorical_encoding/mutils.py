@@ -1,6 +1,7 @@
 """Factory and CLI flags of the categorical encodings
 (reference layers/categorical_encoding/mutils.py:14-72)."""
 from .linear_encoding import LinearCategoricalEncoding
+from .variational_dequantization import VariationalDequantization
 from .variational_encoding import VariationalCategoricalEncoding
 
 
@@ -40,10 +41,16 @@ def create_encoding(encoding_params, dataset_class, vocab=None, vocab_size=-1, c
         "[!] ERROR: When creating the encoding, either a torchtext vocabulary or the vocabulary size needs to be passed."
     use_dequantization = encoding_params.pop("use_dequantization")
     use_variational = encoding_params.pop("use_variational")
+    if use_dequantization and "model_func" not in encoding_params["flow_config"]:
+        # as upstream (:56-59): the CLI never supplies a network for the dequantization flow
+        print("[#] WARNING: For using variational dequantization as encoding scheme, a model function needs to be specified"
+              " in the encoding parameters, key \"flow_config\" which was missing here. Will deactivate dequantization...")
+        use_dequantization = False
     if use_dequantization:
-        # the dequantization baseline is outside the hot path
-        raise NotImplementedError("categoricalnf_b200: variational dequantization is a baseline encoding outside the "
-                                  "accelerated path; use the reference implementation for it")
-    encoding_flow = VariationalCategoricalEncoding if use_variational else LinearCategoricalEncoding
+        encoding_flow = VariationalDequantization
+    elif use_variational:
+        encoding_flow = VariationalCategoricalEncoding
+    else:
+        encoding_flow = LinearCategoricalEncoding
     return encoding_flow(dataset_class=dataset_class, vocab=vocab, vocab_size=vocab_size,
                          category_prior=category_prior, **encoding_params)

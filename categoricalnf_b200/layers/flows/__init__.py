@@ -6,8 +6,9 @@ from .autoregressive_coupling import AutoregressiveMixtureCDFCoupling
 from .activation_normalization import ActNormFlow, ExtActNormFlow
 from .permutation_layers import InvertibleConv
 from .node_edge_coupling import NodeEdgeCoupling, NodeEdgeFlowWrapper
+from .sigmoid_layer import SigmoidFlow
 from .distributions import LogisticDistribution, PriorDistribution, create_prior_distribution
 
 __all__ = ["FlowLayer", "FlowModel", "CouplingLayer", "MixtureCDFCoupling", "AutoregressiveMixtureCDFCoupling",
-           "ActNormFlow", "ExtActNormFlow", "InvertibleConv", "NodeEdgeCoupling", "NodeEdgeFlowWrapper", "LogisticDistribution", "PriorDistribution",
+           "ActNormFlow", "ExtActNormFlow", "SigmoidFlow", "InvertibleConv", "NodeEdgeCoupling", "NodeEdgeFlowWrapper", "LogisticDistribution", "PriorDistribution",
            "create_prior_distribution"]

@@ -396,6 +396,43 @@ def logistic_sample(shape, device, *, noise=None, seed=0, offset=0, mu=0.0, sigm
     return x
 
 
+def sigmoid_flow(z, ldj=None, *, reverse=False, alpha=1e-5, sum_ldj=True, add_tokens=None):
+    """SigmoidFlow (sigmoid_layer.py:24-48) in its EFFECTIVE direction: ``reverse=False`` sigmoid, ``True`` logit of the
+    alpha-squeezed input.  Returns ``(z_out, ldj)``: ``ldj`` is a NEW tensor ``ldj_in + sum`` [B] (``sum_ldj``) or the
+    element-wise values.  ``add_tokens`` (int64, z's shape) is added to ``z_out`` (variational_dequantization.py:47)."""
+    z = _f32(z, "z")
+    B = z.shape[0] if z.dim() >= 1 else 1
+    per = z.numel() // max(B, 1)
+    a = L.SigmoidFlowArgs()
+    a.B, a.n_per_sample, a.z, a.reverse, a.alpha = B, per, _ptr(z), int(bool(reverse)), float(alpha)
+    out = torch.empty_like(z)
+    elem = None
+    if sum_ldj:
+        res = torch.zeros(B, dtype=torch.float32, device=z.device) if ldj is None else _f32(ldj, "ldj", (B,)).clone()
+        a.accumulate, a.ldj = 1, _ptr(res)
+    else:
+        elem = torch.empty_like(z)
+        a.accumulate, a.ldj_elementwise = 0, _ptr(elem)
+    if add_tokens is not None:
+        add_tokens = add_tokens.long().contiguous()
+        if add_tokens.numel() != z.numel() or not add_tokens.is_cuda:
+            raise ValueError("add_tokens must be a CUDA int64 tensor with as many elements as z")
+        a.add_tokens = _ptr(add_tokens)
+    a.z_out, a.status = _ptr(out), _ptr(status_word(z.device))
+    _call("cnf_sigmoid_flow", a, z, (add_tokens,))
+    return out, (res if sum_ldj else elem)
+
+
+def dequant_floor(z, vocab_size):
+    """tokens = clamp(floor(z), 0, V-1) as int64 (variational_dequantization.py:55-56); a trailing singleton dim is dropped."""
+    z = _f32(z, "z")
+    out = torch.empty(z.shape[:-1] if z.dim() > 2 and z.shape[-1] == 1 else z.shape, dtype=torch.int64, device=z.device)
+    a = L.DequantFloorArgs()
+    a.n, a.V, a.z, a.tokens_out = z.numel(), int(vocab_size), _ptr(z), _ptr(out)
+    _call("cnf_dequant_floor", a, z)
+    return out
+
+
 def ldj_axpy(y, *, alpha=1.0, alpha_dev=None, x=None, length=None):
     """y[b] += alpha * alpha_dev * x[b] * length[b] (missing factors are 1)."""
     y = _f32(y, "y")

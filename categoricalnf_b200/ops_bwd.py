@@ -135,6 +135,20 @@ def logistic_logprob_backward(x, g, mu, sigma):
     return gx.reshape(shape)
 
 
+def sigmoid_flow_backward(z, g_out, g_ldj, g_elem, reverse, alpha):
+    z = _f32(z, "z")
+    B = z.shape[0]
+    gz = torch.empty_like(z)
+    go = None if g_out is None else _f32(g_out, "grad_z_out")
+    gl = _opt_f32(g_ldj, "grad_ldj", (B,))
+    ge = None if g_elem is None else _f32(g_elem, "grad_ldj_elementwise")
+    a = L.SigmoidFlowBwdArgs()
+    a.B, a.n_per_sample, a.z, a.reverse, a.alpha = B, z.numel() // max(B, 1), _ptr(z), int(bool(reverse)), float(alpha)
+    a.grad_z_out, a.grad_ldj, a.grad_ldj_elementwise, a.grad_z = _ptr(go), _ptr(gl), _ptr(ge), _ptr(gz)
+    _call("cnf_sigmoid_flow_bwd", a, z, (z, go, gl, ge))
+    return gz
+
+
 def categ_encode_backward(tokens, z, table, category_prior, pad, beta, g_z, g_ldj):
     """dL/dtable [V,2D] of ``ops.categ_encode`` (``cnf_categ_encode_bwd``); ``z`` is the forward output."""
     tokens = tokens.long().contiguous()

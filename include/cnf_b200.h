@@ -655,6 +655,55 @@ typedef struct {
 
 CNF_API int cnf_logistic_logprob_bwd(const cnf_logistic_logprob_bwd_args* a, cnf_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * SigmoidFlow (layers/flows/sigmoid_layer.py:24-48) and the two ends of VariationalDequantization
+ * (layers/categorical_encoding/variational_dequantization.py:31-58).
+ *   reverse == 0:  z_out = sigmoid(z),                 ldj_e = -z - 2 softplus(-z)
+ *   reverse == 1:  y = z (1-alpha) + alpha/2,  z_out = log y - log(1-y),
+ *                  ldj_e = -log y - log(1-y) + log(1-alpha)          (alpha = 1e-5 upstream)
+ * `reverse` is the EFFECTIVE direction (the module resolves `reverse_layer XOR reverse`, :29).
+ * ldj[b] (+)= sum of ldj_e over the sample (`accumulate`); `ldj_elementwise` additionally stores the
+ * unreduced values (sum_ldj=False, :43-46).  `add_tokens` (int64, same element count) is added to
+ * z_out: the dequantised value `z.float() + noise` of variational_dequantization.py:47.
+ * cnf_dequant_floor: tokens_out = clamp(floor(z), 0, V-1) (:55-56).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    int64_t B, n_per_sample;
+    const float* z;              /* [B, n_per_sample] */
+    int32_t reverse;
+    float alpha;
+    int32_t accumulate;
+    const int64_t* add_tokens;   /* [B, n_per_sample] or NULL */
+    float* z_out;                /* [B, n_per_sample] */
+    float* ldj;                  /* [B] or NULL */
+    float* ldj_elementwise;      /* [B, n_per_sample] or NULL */
+    uint32_t* status;            /* CNF_FLAG_* word or NULL */
+} cnf_sigmoid_flow_args;
+
+CNF_API int cnf_sigmoid_flow(const cnf_sigmoid_flow_args* a, cnf_stream_t stream);
+
+typedef struct {
+    int64_t B, n_per_sample;
+    const float* z;                   /* [B, n_per_sample] forward INPUT */
+    int32_t reverse;
+    float alpha;
+    const float* grad_z_out;          /* [B, n_per_sample] or NULL */
+    const float* grad_ldj;            /* [B] or NULL */
+    const float* grad_ldj_elementwise;/* [B, n_per_sample] or NULL */
+    float* grad_z;                    /* [B, n_per_sample] */
+} cnf_sigmoid_flow_bwd_args;
+
+CNF_API int cnf_sigmoid_flow_bwd(const cnf_sigmoid_flow_bwd_args* a, cnf_stream_t stream);
+
+typedef struct {
+    int64_t n;
+    int32_t V;
+    const float* z;        /* [n] */
+    int64_t* tokens_out;   /* [n] */
+} cnf_dequant_floor_args;
+
+CNF_API int cnf_dequant_floor(const cnf_dequant_floor_args* a, cnf_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

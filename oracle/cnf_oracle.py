@@ -531,3 +531,56 @@ def categ_decode_flows(sd, z, num_flows):
 def decoder_linear(sd, z, pre=""):
     """DecoderLinear.forward (layers/categorical_encoding/decoder.py:56-60)."""
     return torch.log_softmax(linear_net(sd, pre + "layers.", decoder_features(z)), dim=-1)
+
+
+# ---------------------------------------------------------------------------
+# SigmoidFlow and VariationalDequantization (SURVEY 8f rank 4)
+#   layers/flows/sigmoid_layer.py:24-48; layers/categorical_encoding/variational_dequantization.py:31-98
+# ---------------------------------------------------------------------------
+SIGMOID_ALPHA = 1e-5
+
+
+def sigmoid_flow(z, ldj=None, reverse=False, reverse_layer=False, sum_ldj=True):
+    """sigmoid_layer.py:24-48 (fp32, the reference's own operation order)."""
+    if ldj is None:
+        ldj = z.new_zeros(z.size(0))
+    alpha = SIGMOID_ALPHA
+    if reverse_layer == reverse:                                                # XOR false -> sigmoid direction (:29-33)
+        layer_ldj = -z - 2 * F.softplus(-z)
+        out = torch.sigmoid(z)
+    else:
+        y = z * (1 - alpha) + alpha * 0.5
+        layer_ldj = -torch.log(y) - torch.log(1 - y) + math.log(1 - alpha)
+        out = torch.log(y) - torch.log(1 - y)
+    if sum_ldj:
+        return out, ldj + layer_ldj.view(z.size(0), -1).sum(dim=1)
+    return out, layer_ldj
+
+
+def dequant_example_net(sd, pre, x, ext_input):
+    """The coupling network of the reference's usage example (variational_dequantization.py:118-131): the user-supplied
+    black box ``model_func`` - Linear(1,h) on the noise, concatenated with the embedding, Linear-ReLU-Linear."""
+    h = torch.cat([_sd_linear(sd, pre + "inp_layer", x), ext_input], dim=-1)
+    return _sd_linear(sd, pre + "main_net.2", F.relu(_sd_linear(sd, pre + "main_net.0", h)))
+
+
+def variational_dequantization(sd, x, u_noise, num_flows, net=dequant_example_net):
+    """VariationalDequantization.forward, reverse=False (variational_dequantization.py:31-52, 61-66, 76-98).
+    ``sd``: the module's state dict; ``x`` [B,S] int64; ``u_noise`` [B,S] in [0,1).  Returns (z_out [B,S,1], ldj [B])."""
+    r = u_noise.unsqueeze(-1)                                                   # fp32 upstream; fp64 for autograd checks
+    ldj = torch.zeros(x.shape[0], dtype=r.dtype)
+    r, ldj = sigmoid_flow(r, ldj, reverse=False, reverse_layer=True)
+    embed = sd["embed_layer.weight"][x]
+    for f in range(num_flows):
+        pre_a, pre_c = "flow_layers.%d." % (2 * f), "flow_layers.%d." % (2 * f + 1)
+        r, ldj = actnorm(r, sd[pre_a + "bias"], sd[pre_a + "scales"], ldj)
+        mask = expand_mask(sd[pre_c + "mask"], r)
+        nn_out = net(sd, pre_c + "nn.", r * mask, embed)
+        r, ldj = affine_coupling(r, nn_out, mask, sd[pre_c + "scaling_factor"], ldj)
+    r, ldj = sigmoid_flow(r, ldj, reverse=True, reverse_layer=True)
+    return x.to(r.dtype).unsqueeze(-1) + r, ldj
+
+
+def dequantization_reverse(z, vocab_size):
+    """variational_dequantization.py:53-56."""
+    return torch.floor(z).clamp(min=0, max=vocab_size - 1).long().squeeze(dim=-1)

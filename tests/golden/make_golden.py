@@ -738,6 +738,57 @@ def gold_encoding_variants(seed):
     save("encoding_variants", **out)
 
 
+def gold_dequantization(seed):
+    """SigmoidFlow (sigmoid_layer.py) in both directions, with and without ldj summation, incl. inputs at
+    the ends of [0,1] and far tails; VariationalDequantization (variational_dequantization.py) with 4 flows and the network of
+    the reference's own usage example (:118-131), forward on recorded noise and reverse."""
+    from layers.flows.sigmoid_layer import SigmoidFlow
+    from layers.categorical_encoding.variational_dequantization import VariationalDequantization
+    g = torch.Generator().manual_seed(seed)
+    out = {}
+    zs = torch.randn(4, 7, 3, generator=g) * 4.0
+    zs[0, 0, 0], zs[0, 0, 1], zs[1, 2, 0] = 30.0, -30.0, 0.0
+    zu = torch.rand(4, 7, 3, generator=g)
+    zu[0, 0, 0], zu[0, 0, 1], zu[1, 1, 1], zu[2, 0, 0] = 0.0, 1.0, 0.5, 1.0 - 2.0 ** -20
+    ldj0 = torch.randn(4, generator=g)
+    with torch.no_grad():
+        s_z, s_ldj = SigmoidFlow()(zs, ldj=ldj0.clone())
+        s_z2, s_elem = SigmoidFlow(reverse=True)(zs, reverse=True, sum_ldj=False)
+        l_z, l_ldj = SigmoidFlow()(zu, ldj=ldj0.clone(), reverse=True)
+        l_z2, l_elem = SigmoidFlow(reverse=True)(zu, sum_ldj=False)
+    assert torch.equal(s_z, s_z2) and torch.equal(l_z, l_z2)
+    out.update(sig_in=zs, logit_in=zu, ldj0=ldj0, sig_z=s_z, sig_ldj=s_ldj, sig_elem=s_elem, logit_z=l_z, logit_ldj=l_ldj,
+               logit_elem=l_elem)
+
+    B, S, V, E, H, NF = 5, 7, 6, 12, 20, 4
+
+    class ExampleNetwork(nn.Module):        # as in the reference's example (variational_dequantization.py:118-131)
+        def __init__(self, c_out):
+            super().__init__()
+            self.inp_layer = nn.Linear(1, H)
+            self.main_net = nn.Sequential(nn.Linear(H + E, H), nn.ReLU(), nn.Linear(H, c_out))
+
+        def forward(self, x, ext_input, **kwargs):
+            return self.main_net(torch.cat([self.inp_layer(x), ext_input], dim=-1))
+
+    torch.manual_seed(seed)
+    deq = VariationalDequantization(flow_config={"num_flows": NF, "model_func": lambda c_out: ExampleNetwork(c_out),
+                                                 "block_type": "Linear"}, vocab_size=V, default_embed_layer_dims=E)
+    _randomise(deq, g, std=0.3)
+    deq.eval()
+    x = torch.randint(0, V, (B, S), generator=g)
+    torch.manual_seed(seed + 1)
+    u = torch.rand_like(x, dtype=torch.float32)          # the draw forward() makes first (:39)
+    torch.manual_seed(seed + 1)
+    with torch.no_grad():
+        z_cont, ldj = deq(x, reverse=False)
+        x_rec, _ = deq(z_cont, reverse=True)
+    assert torch.equal(x_rec, x)
+    out.update(x=x, u=u, z_cont=z_cont, ldj=ldj, x_rec=x_rec, V=V, num_flows=NF)
+    out.update({"sd__" + k: v for k, v in deq.state_dict().items()})
+    save("dequantization", **out)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(4)
     if ONLY:
@@ -749,6 +800,7 @@ if __name__ == "__main__":
              "graph_flow": lambda: gold_graph_node_flow(seed=27),
              "graphcnf": lambda: gold_graphcnf(seed=32),
              "encoding_variants": lambda: gold_encoding_variants(seed=33),
+             "dequantization": lambda: gold_dequantization(seed=34),
              "edge_gnn": lambda: (gold_edge_gnn("edge_gnn_attn_sparse", 28, False, True), gold_edge_gnn("edge_gnn_attn_dense", 29, False, False),
                                   gold_edge_gnn("edge_gnn_qkv_dense", 30, True, False, N=9), gold_edge_gnn("edge_gnn_qkv_sparse", 31, True, True))}[_n]()
         sys.exit(0)
@@ -788,3 +840,4 @@ if __name__ == "__main__":
     gold_edge_gnn("edge_gnn_qkv_sparse", 31, True, True)
     gold_graphcnf(seed=32)
     gold_encoding_variants(seed=33)
+    gold_dequantization(seed=34)

@@ -273,3 +273,24 @@ def test_encoding_with_linear_flows_and_decoder():
     assert torch.equal(O.categ_decode_flows(sd, g.flows_z, num_flows=4), g.flows_x_dec)
     sdd = {k[len("sd_dec__"):]: v for k, v in g.items() if k.startswith("sd_dec__")}
     assert_close(O.decoder_linear(sdd, g.dec_z), g.dec_log_probs, rtol=1e-5, atol=2e-6, what="decoder log-probs")
+
+
+def test_sigmoid_flow_and_variational_dequantization():
+    """SigmoidFlow both directions (summed and element-wise ldj) and VariationalDequantization with 4 flows."""
+    g = load_golden("dequantization")
+    z, ldj = O.sigmoid_flow(g.sig_in, g.ldj0)
+    assert_close(z, g.sig_z, rtol=1e-6, atol=1e-7, what="sigmoid z")
+    assert_close(ldj, g.sig_ldj, rtol=1e-6, atol=1e-5, what="sigmoid ldj")
+    _, elem = O.sigmoid_flow(g.sig_in, reverse=True, reverse_layer=True, sum_ldj=False)
+    assert_close(elem, g.sig_elem, rtol=1e-6, atol=1e-6, what="sigmoid element ldj")
+    z, ldj = O.sigmoid_flow(g.logit_in, g.ldj0, reverse=True)
+    assert_close(z, g.logit_z, rtol=1e-6, atol=1e-6, what="logit z")
+    assert_close(ldj, g.logit_ldj, rtol=1e-6, atol=1e-5, what="logit ldj")
+    _, elem = O.sigmoid_flow(g.logit_in, reverse_layer=True, sum_ldj=False)
+    assert_close(elem, g.logit_elem, rtol=1e-6, atol=1e-6, what="logit element ldj")
+    sd = {k[len("sd__"):]: v for k, v in g.items() if k.startswith("sd__")}
+    z_cont, ldj = O.variational_dequantization(sd, g.x, g.u, g.num_flows)
+    assert_close(z_cont, g.z_cont, rtol=1e-5, atol=2e-6, what="dequantised z")
+    assert_close(ldj, g.ldj, rtol=1e-5, atol=2e-5, what="dequantisation ldj")
+    assert torch.equal(O.dequantization_reverse(g.z_cont, g.V), g.x_rec)
+    assert ((z_cont.squeeze(-1) - g.x.float()) >= 0).all() and ((z_cont.squeeze(-1) - g.x.float()) <= 1).all()
