@@ -264,6 +264,37 @@ class DequantFloorArgs(C.Structure):
     _fields_ = [("n", C.c_int64), ("V", C.c_int32), ("z", vp), ("tokens_out", vp)]
 
 
+class GeluArgs(C.Structure):
+    _fields_ = [("n", C.c_int64), ("x", vp), ("grad_y", vp), ("y", vp)]
+
+
+class LayernormBwdArgs(C.Structure):
+    _fields_ = [("M", C.c_int64), ("H", C.c_int32), ("x", vp), ("gamma", vp), ("eps", C.c_float), ("grad_y", vp),
+                ("grad_x", vp), ("grad_gamma", vp), ("grad_beta", vp)]
+
+
+class SkipGateBwdArgs(C.Structure):
+    _fields_ = [("M", C.c_int64), ("H", C.c_int32), ("config", C.c_int32), ("orig", vp), ("skip", vp), ("grad_out", vp),
+                ("grad_orig", vp), ("grad_skip", vp)]
+
+
+class GraphAggregateBwdArgs(C.Structure):
+    _fields_ = [("fwd", GraphAggregateArgs), ("grad_out", vp), ("grad_hs", vp), ("grad_hr", vp), ("grad_score_s", vp),
+                ("grad_score_r", vp), ("ld_grad_hs", C.c_int64), ("ld_grad_hr", C.c_int64), ("ld_grad_score_s", C.c_int64),
+                ("ld_grad_score_r", C.c_int64)]
+
+
+class EdgeAggregateBwdArgs(C.Structure):
+    _fields_ = [("fwd", EdgeAggregateArgs), ("grad_out", vp), ("grad_node_val", vp), ("grad_node_q", vp), ("grad_node_k", vp),
+                ("grad_edge_val", vp), ("grad_edge_logit", vp), ("ld_grad_node_val", C.c_int64), ("ld_grad_node_q", C.c_int64),
+                ("ld_grad_node_k", C.c_int64), ("ld_grad_edge_val", C.c_int64), ("ld_grad_edge_logit", C.c_int64)]
+
+
+class PairCombineBwdArgs(C.Structure):
+    _fields_ = [("fwd", PairCombineArgs), ("grad_out", vp), ("grad_edge_lin", vp), ("grad_node_lin", vp),
+                ("ld_grad_edge", C.c_int64), ("ld_grad_node", C.c_int64)]
+
+
 # symbol -> argument struct; every entry point is `int f(const Args*, cnf_stream_t)`
 ENTRY_POINTS = {
     "cnf_mixcdf_fwd": MixcdfArgs,
@@ -299,6 +330,12 @@ ENTRY_POINTS = {
     "cnf_sigmoid_flow": SigmoidFlowArgs,
     "cnf_sigmoid_flow_bwd": SigmoidFlowBwdArgs,
     "cnf_dequant_floor": DequantFloorArgs,
+    "cnf_gelu": GeluArgs,
+    "cnf_layernorm_bwd": LayernormBwdArgs,
+    "cnf_skip_gate_bwd": SkipGateBwdArgs,
+    "cnf_graph_aggregate_bwd": GraphAggregateBwdArgs,
+    "cnf_edge_aggregate_bwd": EdgeAggregateBwdArgs,
+    "cnf_pair_combine_bwd": PairCombineBwdArgs,
 }
 PLAIN_SYMBOLS = ("cnf_last_error_string", "cnf_abi_version", "cnf_built_for_sm", "cnf_mixcdf_fusable",
                  "cnf_categ_encode_fusable", "cnf_linear_mixcdf_fusable")

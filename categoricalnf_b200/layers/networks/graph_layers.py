@@ -14,8 +14,9 @@ What runs where (evaluation / sampling, i.e. grad disabled):
     (the reference one-hot encodes it, pads every node to the batch-wide maximum degree with masked_select /
     index_select - one host sync per layer, :107 - and materialises the padded products);
   * ``GNNSkipConnection``-> ``cnf_skip_gate``.
-With grad enabled (training) the projections still run on the tensor cores (``TCLinear`` forward + ``cnf_linear_bwd``)
-and the glue is evaluated with differentiable dense torch operations of the same mathematics.
+With grad enabled (training) the same kernels run inside ``autograd.Function``s (``graph_functional.py``) whose backward
+passes are the kernels of ``csrc/graph_ops_bwd.cu`` (``cnf_layernorm_bwd``, ``cnf_graph_aggregate_bwd``, ``cnf_skip_gate_bwd``,
+``cnf_edge_aggregate_bwd``, ``cnf_pair_combine_bwd``, ``cnf_gelu``) next to ``cnf_linear_bwd`` for the projections.
 The *final* projection is exposed through ``cnf_features`` / ``cnf_final_linear`` so that ``MixtureCDFCoupling`` fuses
 it with the transform (``cnf_linear_mixcdf_fwd``).
 """
@@ -23,6 +24,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from ... import graph_functional as GF
 from ... import ops
 from .linear import TCLinear, _TCLinearFn
 
@@ -38,14 +40,13 @@ def _linear(x, lin, activation=None, precision=None):
     precision = precision or PRECISION
     if _grad_mode(x, lin.weight, lin.bias):
         y = _TCLinearFn.apply(x, lin.weight, lin.bias, precision)
-        return F.gelu(y) if activation == "gelu" else y
+        return GF.gelu(y) if activation == "gelu" else y
     return ops.linear(x, lin.weight, lin.bias, precision=precision, activation=activation)
 
 
 def _layernorm(x, ln):
-    if _grad_mode(x, ln.weight, ln.bias):
-        return F.layer_norm(x, ln.normalized_shape, ln.weight, ln.bias, ln.eps)
-    return ops.layernorm(x, ln.weight, ln.bias, ln.eps)
+    """nn.LayerNorm: ``cnf_layernorm`` forward, ``cnf_layernorm_bwd`` under autograd."""
+    return GF.layernorm(x, ln.weight, ln.bias, ln.eps)
 
 
 def _edge_types(adjacency, num_edges):
@@ -66,28 +67,32 @@ class _FusedPair:
     def __init__(self):
         self.key, self.weight, self.bias = None, None, None
 
+    @staticmethod
+    def build(a, b, attn_weight=None):
+        """(weight, bias) of the fused projection as differentiable functions of the layer's parameters."""
+        ws, bs = [a.weight, b.weight], [a.bias, b.bias]
+        if attn_weight is not None:
+            H, _, Dh = attn_weight.shape
+            K = a.weight.shape[1]
+            aw = attn_weight.double()
+            ws.append(torch.einsum("hd,hdk->hk", aw[:, 0], a.weight.double().view(H, Dh, K)).float())
+            bs.append((aw[:, 0] * a.bias.double().view(H, Dh)).sum(-1).float())
+            E1 = b.weight.shape[0] // (H * Dh)
+            ws.append(torch.einsum("hd,ehdk->ehk", aw[:, 1], b.weight.double().view(E1, H, Dh, K)).reshape(E1 * H, K).float())
+            bs.append((aw[:, 1].unsqueeze(0) * b.bias.double().view(E1, H, Dh)).sum(-1).reshape(E1 * H).float())
+            extra = (-(H + E1 * H)) % 4
+            if extra:
+                ws.append(a.weight.new_zeros(extra, K))
+                bs.append(a.bias.new_zeros(extra))
+        return torch.cat(ws, dim=0).contiguous(), torch.cat(bs, dim=0).contiguous()
+
     def get(self, a, b, attn_weight=None):
         key = (a.weight.data_ptr(), a.weight._version, a.bias._version, b.weight.data_ptr(), b.weight._version,
                b.bias._version, a.weight.device, None if attn_weight is None else (attn_weight.data_ptr(), attn_weight._version))
         if key != self.key:
             with torch.no_grad():
-                ws, bs = [a.weight, b.weight], [a.bias, b.bias]
-                if attn_weight is not None:
-                    H, _, Dh = attn_weight.shape
-                    K = a.weight.shape[1]
-                    aw = attn_weight.double()
-                    ws.append(torch.einsum("hd,hdk->hk", aw[:, 0], a.weight.double().view(H, Dh, K)).float())
-                    bs.append((aw[:, 0] * a.bias.double().view(H, Dh)).sum(-1).float())
-                    E1 = b.weight.shape[0] // (H * Dh)
-                    ws.append(torch.einsum("hd,ehdk->ehk", aw[:, 1], b.weight.double().view(E1, H, Dh, K)).reshape(E1 * H, K).float())
-                    bs.append((aw[:, 1].unsqueeze(0) * b.bias.double().view(E1, H, Dh)).sum(-1).reshape(E1 * H).float())
-                    extra = (-(H + E1 * H)) % 4
-                    if extra:
-                        ws.append(a.weight.new_zeros(extra, K))
-                        bs.append(a.bias.new_zeros(extra))
-                self.weight = torch.cat(ws, dim=0).contiguous()
+                self.weight, self.bias = self.build(a, b, attn_weight)
                 self.weight._cnf_cache_lo = True       # long-lived: ops.linear may cache its TF32 low part
-                self.bias = torch.cat(bs, dim=0).contiguous()
             self.key = key
         return self.weight, self.bias
 
@@ -107,9 +112,14 @@ class RelationGraphConv(nn.Module):
         """``adjacency``: integer edge types [B,N,N] or one-hot [B,N,N,E]; ``num_neighbours`` [B,N] (None -> counted).
         ``activation="gelu"`` applies the GELU that follows the layer inside RGCNNet in the same kernel."""
         adj = _edge_types(adjacency, self.num_edges)
-        if _grad_mode(x, self.linear_hs.weight):
-            return self._forward_dense(x, adj, num_neighbours, activation)
         B, N = x.shape[0], x.shape[1]
+        if _grad_mode(x, self.linear_hs.weight):
+            # training: same kernels, differentiable (cnf_layernorm_bwd, cnf_linear_bwd, cnf_graph_aggregate_bwd)
+            xn = _layernorm(x, self.norm_layer)
+            w, b = _FusedPair.build(self.linear_hs, self.linear_hr)
+            y = _TCLinearFn.apply(xn.reshape(B * N, -1), w, b, PRECISION)
+            cfg = dict(B=B, N=N, E=self.num_edges, H=1, Dh=self.c_out, mode=0, off_hs=0, off_hr=self.c_out, activation=activation)
+            return GF.graph_aggregate(y, adj, cfg, num_neighbours)
         xn = ops.layernorm(x, self.norm_layer.weight, self.norm_layer.bias, self.norm_layer.eps)
         w, b = self._pair.get(self.linear_hs, self.linear_hr)
         y = ops.linear(xn.reshape(B * N, -1), w, b, precision=PRECISION)
@@ -119,6 +129,8 @@ class RelationGraphConv(nn.Module):
                                         activation=activation)
 
     def _forward_dense(self, x, adj, num_neighbours, activation):
+        """The same function as dense differentiable torch algebra - kept as an independent check of the kernels' gradients
+        (tests/test_gpu_graph.py); not on any product path."""
         B, N = x.shape[0], x.shape[1]
         xn = _layernorm(x, self.norm_layer)
         hs = _linear(xn, self.linear_hs)
@@ -150,10 +162,19 @@ class RelationGraphAttention(nn.Module):
 
     def forward(self, x, adjacency, activation=None, **kwargs):
         adj = _edge_types(adjacency, self.num_edges)
-        if _grad_mode(x, self.linear_hs.weight, self.attn_weight):
-            return self._forward_dense(x, adj, activation)
         B, N = x.shape[0], x.shape[1]
         width = self.c_out_per_head * self.num_heads
+        if _grad_mode(x, self.linear_hs.weight, self.attn_weight):
+            # training: the logits stay extra columns of the fused projection (differentiable in attn_weight through the
+            # construction of the fused weight), aggregation and its backward are one kernel each
+            H, wr = self.num_heads, width * (self.num_edges + 1)
+            xn = _layernorm(x, self.norm_layer)
+            w, b = _FusedPair.build(self.linear_hs, self.linear_hr, self.attn_weight)
+            y = _TCLinearFn.apply(xn.reshape(B * N, -1), w, b, PRECISION)
+            cfg = dict(B=B, N=N, E=self.num_edges, H=H, Dh=self.c_out_per_head, mode=1, off_hr=width, off_ss=width + wr,
+                       off_sr=width + wr + H, slope=self.leaky_relu.negative_slope, activation="gelu")
+            att = GF.graph_aggregate(y, adj, cfg)
+            return _linear(att, self.output_projection[1], activation=activation)
         xn = ops.layernorm(x, self.norm_layer.weight, self.norm_layer.bias, self.norm_layer.eps)
         w, b = self._pair.get(self.linear_hs, self.linear_hr, self.attn_weight)
         y = ops.linear(xn.reshape(B * N, -1), w, b, precision=PRECISION)
@@ -166,7 +187,8 @@ class RelationGraphAttention(nn.Module):
                           activation=activation)
 
     def _forward_dense(self, x, adj, activation):
-        """Same mathematics as a dense masked softmax over all node pairs (differentiable; training path)."""
+        """Same mathematics as a dense masked softmax over all node pairs in differentiable torch algebra - an independent
+        check of the kernels' gradients (tests/test_gpu_graph.py); not on any product path."""
         B, N = x.shape[0], x.shape[1]
         H, Dh, E = self.num_heads, self.c_out_per_head, self.num_edges
         xn = _layernorm(x, self.norm_layer)
@@ -210,14 +232,7 @@ class GNNSkipConnection(nn.Module):
         return _linear(feat, self.skip_layer)
 
     def forward(self, orig, feat):
-        s = self._skip(feat)
-        if not _grad_mode(orig, s):
-            return ops.skip_gate(orig, s, self.config)
-        if self.config == 0:
-            return orig + s
-        val, gate_logits = s.chunk(2, dim=-1)
-        gate = torch.sigmoid(gate_logits)
-        return orig + val * gate if self.config == 1 else orig * (1 - gate) + val * gate
+        return GF.skip_gate(orig, self._skip(feat), self.config)
 
 
 class RGCNNet(nn.Module):
@@ -316,7 +331,8 @@ class PairContext:
 
 
 def _edge_to_node_dense(ctx, node_val, edge_val, edge_logit, H, mode, q=None, k=None, scale=1.0):
-    """Differentiable form of ``cnf_edge_aggregate``: every valid pair sends one message in each direction."""
+    """``cnf_edge_aggregate`` as differentiable torch algebra (every valid pair sends one message in each direction) - an
+    independent check of the backward kernel (tests/test_gpu_graph.py); not on any product path."""
     BN, HD = node_val.shape
     Dh = HD // H
     dst = torch.cat([ctx.node1, ctx.node2])
@@ -390,8 +406,10 @@ class Node2EdgePlainLayer(_EdgeLayerBase):
         B, N = node_feat.shape[0], node_feat.shape[1]
         node_lin = _linear(_layernorm(self.dropout(node_feat), self.node_feat_layer[0]), self.node_feat_layer[1]).reshape(B * N, -1)
         edge_lin = _linear(_layernorm(self.dropout(edge_rows), self.edge_feat_layer[0]), self.edge_feat_layer[1])
-        if _grad_mode(node_lin, edge_lin) or (self.training and self.dropout.p > 0):
-            comb = self.act_fn(self.dropout(edge_lin + node_lin[ctx.node1] + node_lin[ctx.node2]))
+        if self.training and self.dropout.p > 0:      # dropout sits between the sum and the activation (:330)
+            comb = GF.gelu(self.dropout(GF.pair_combine(edge_lin, node_lin, ctx.flat_indices, ctx.x_indices, N, activation=None)))
+        elif _grad_mode(node_lin, edge_lin):
+            comb = GF.pair_combine(edge_lin, node_lin, ctx.flat_indices, ctx.x_indices, N, activation="gelu")
         else:
             comb = ops.pair_combine(ctx.flat_indices, ctx.x_indices, edge_lin, node_lin, N, activation="gelu")
         return self.skip_layer(orig=edge_rows, feat=comb)
@@ -428,12 +446,14 @@ class Edge2NodeQKVAttnLayer(_EdgeLayerBase):
         edge_val = _linear(edge_in, self.edge_val_layer)
         edge_adj = _linear(edge_in, self.edge_adj_layer)
         if _grad_mode(qkv, edge_val, edge_adj):
-            att = _edge_to_node_dense(ctx, v, edge_val, edge_adj, H, "qkv", q, k, self.dot_prod_scaling)
+            cfg = dict(N=N, H=H, Dh=self.hidden_size_per_head, mode=1, off_q=0, off_k=width, off_val=2 * width,
+                       scale=self.dot_prod_scaling)
+            att = GF.edge_aggregate(qkv, edge_val, edge_adj, ctx.rev, cfg)
         else:
             att = ops.edge_aggregate(ctx.rev, v, edge_val, edge_adj, H, mode="qkv", node_q=q, node_k=k, scale=self.dot_prod_scaling)
         cat = torch.cat([node_in, att.reshape(B, N, width)], dim=-1)
         if self.training and self.dropout.p > 0:
-            comb = self.act_fn(self.dropout(_linear(cat, self.output_projection)))
+            comb = GF.gelu(self.dropout(_linear(cat, self.output_projection)))
         else:
             comb = _linear(cat, self.output_projection, activation="gelu")
         return self.skip_layer(orig=node_feat, feat=comb)
@@ -466,10 +486,11 @@ class Edge2NodeAttnLayer(_EdgeLayerBase):
         edge_new = _linear(edge_in, self.edge_feat_layer)
         edge_logits = _linear(edge_in, self.edge_logits_layer)
         if _grad_mode(node_new, edge_new, edge_logits):
-            att = _edge_to_node_dense(ctx, node_ctx, edge_new, edge_logits, self.num_heads, "sigmoid")
+            cfg = dict(N=N, H=self.num_heads, Dh=self.hidden_size_per_head, mode=0, off_val=HO)
+            att = GF.edge_aggregate(node_new, edge_new, edge_logits, ctx.rev, cfg)
         else:
             att = ops.edge_aggregate(ctx.rev, node_ctx, edge_new, edge_logits, self.num_heads, mode="sigmoid")
-        comb = self.act_fn(self.dropout(node_self + att)).reshape(B, N, HO)
+        comb = GF.gelu(self.dropout(node_self + att)).reshape(B, N, HO)
         return self.skip_layer(orig=node_feat, feat=comb)
 
 

@@ -704,6 +704,83 @@ typedef struct {
 
 CNF_API int cnf_dequant_floor(const cnf_dequant_floor_args* a, cnf_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Backward of the graph coupling networks' glue (csrc/graph_ops_bwd.cu): training GraphNodeFlow / GraphCNF
+ * differentiates RGCNNet / EdgeGNN (layers/networks/graph_layers.py) through these instead of autograd over dense
+ * [B,N,N,...] torch expressions.  `fwd` repeats the arguments of the forward call (its `out` is ignored); gradients
+ * marked "+=" receive scattered contributions through fp32 reductions and must be zero-initialised by the caller,
+ * the others are overwritten.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    int64_t n;
+    const float* x;        /* [n] input of the GELU                                   */
+    const float* grad_y;   /* NULL: y = gelu(x);  else: y = grad_y * gelu'(x)         */
+    float* y;              /* [n]                                                     */
+} cnf_gelu_args;
+
+CNF_API int cnf_gelu(const cnf_gelu_args* a, cnf_stream_t stream);
+
+typedef struct {
+    int64_t M;
+    int32_t H;
+    const float* x;        /* [M,H] forward input    */
+    const float* gamma;    /* [H]                    */
+    float eps;
+    const float* grad_y;   /* [M,H]                  */
+    float* grad_x;         /* [M,H]                  */
+    float* grad_gamma;     /* [H] += or NULL         */
+    float* grad_beta;      /* [H] += or NULL         */
+} cnf_layernorm_bwd_args;
+
+CNF_API int cnf_layernorm_bwd(const cnf_layernorm_bwd_args* a, cnf_stream_t stream);
+
+typedef struct {
+    int64_t M;
+    int32_t H, config;
+    const float* orig;      /* [M,H]            */
+    const float* skip;      /* [M,H] or [M,2H]  */
+    const float* grad_out;  /* [M,H]            */
+    float* grad_orig;       /* [M,H]            */
+    float* grad_skip;       /* like skip        */
+} cnf_skip_gate_bwd_args;
+
+CNF_API int cnf_skip_gate_bwd(const cnf_skip_gate_bwd_args* a, cnf_stream_t stream);
+
+typedef struct {
+    cnf_graph_aggregate_args fwd;
+    const float* grad_out;       /* [B*N, H*Dh] gradient of the (activated) output              */
+    float* grad_hs;              /* mode 0: [B*N, >= Dh] pitch ld_grad_hs (overwritten); mode 1: unused  */
+    float* grad_hr;              /* += , pitch ld_grad_hr                                        */
+    float* grad_score_s;         /* mode 1: [B*N,H] pitch ld_grad_score_s (overwritten)          */
+    float* grad_score_r;         /* mode 1: += , pitch ld_grad_score_r                           */
+    int64_t ld_grad_hs, ld_grad_hr, ld_grad_score_s, ld_grad_score_r;
+} cnf_graph_aggregate_bwd_args;
+
+CNF_API int cnf_graph_aggregate_bwd(const cnf_graph_aggregate_bwd_args* a, cnf_stream_t stream);
+
+typedef struct {
+    cnf_edge_aggregate_args fwd;
+    const float* grad_out;       /* [B*N, H*Dh]                  */
+    float* grad_node_val;        /* += , pitch ld_grad_node_val  */
+    float* grad_node_q;          /* mode 1: +=                   */
+    float* grad_node_k;          /* mode 1: +=                   */
+    float* grad_edge_val;        /* += [R, >= H*Dh]              */
+    float* grad_edge_logit;      /* += [R, >= H]                 */
+    int64_t ld_grad_node_val, ld_grad_node_q, ld_grad_node_k, ld_grad_edge_val, ld_grad_edge_logit;
+} cnf_edge_aggregate_bwd_args;
+
+CNF_API int cnf_edge_aggregate_bwd(const cnf_edge_aggregate_bwd_args* a, cnf_stream_t stream);
+
+typedef struct {
+    cnf_pair_combine_args fwd;
+    const float* grad_out;       /* [R, He]                                  */
+    float* grad_edge_lin;        /* [R, >= He] pitch ld_grad_edge (overwritten) */
+    float* grad_node_lin;        /* += [B*N, >= He] pitch ld_grad_node       */
+    int64_t ld_grad_edge, ld_grad_node;
+} cnf_pair_combine_bwd_args;
+
+CNF_API int cnf_pair_combine_bwd(const cnf_pair_combine_bwd_args* a, cnf_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
