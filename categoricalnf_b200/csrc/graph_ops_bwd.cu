@@ -23,6 +23,13 @@ __device__ __forceinline__ float gelu_grad(float v) {
     return fmaf(v * kInvSqrt2Pi, expf(-0.5f * v * v), 0.5f * (1.0f + erff(v * kInvSqrt2)));
 }
 
+// Four scalar fp32 reductions (RED.E.ADD.F32).  The 16-byte form (REDG.E.ADD.F32x4 via atomicAdd(float4*)) was measured
+// SLOWER on B200 for this scatter pattern (graph_aggregate_bwd 703 us vs 520 us at B*N = 20480, 768 features), so the
+// vector paths below only vectorise the loads.
+__device__ __forceinline__ void red_add4(float* addr, float a, float b, float c, float d) {
+    atomicAdd(addr, a); atomicAdd(addr + 1, b); atomicAdd(addr + 2, c); atomicAdd(addr + 3, d);
+}
+
 inline unsigned capped_grid(long long blocks, int per_sm) {
     const long long cap = (long long)sm_count() * per_sm;
     if (blocks > cap) blocks = cap;
@@ -127,7 +134,7 @@ struct AggBwdParams {
     const float* g_out;
     float* g_hs; float* g_hr; float* g_ss; float* g_sr;
     long long ld_hs, ld_hr, ld_ss, ld_sr, ld_ghs, ld_ghr, ld_gss, ld_gsr;
-    int N, E, H, Dh, mode, act;
+    int N, E, H, Dh, mode, act, vec;
     float slope;
 };
 
@@ -135,15 +142,15 @@ constexpr int kAggThreads = 256;
 constexpr int kMaxHeads = 16;
 
 __global__ void __launch_bounds__(kAggThreads) graph_aggregate_bwd_kernel(const AggBwdParams p) {
-    extern __shared__ unsigned char aggb_smem[];
+    extern __shared__ __align__(16) unsigned char aggb_smem[];
     const int N1 = p.N + 1;
     const int HD = p.H * p.Dh;
-    int* nb_row = reinterpret_cast<int*>(aggb_smem);            // [N+1]
+    float* gp = reinterpret_cast<float*>(aggb_smem);              // [HD] gradient at the pre-activation output (16-byte aligned)
+    int* nb_row = reinterpret_cast<int*>(gp + ((HD + 3) & ~3));   // [N+1]
     int* nb_e = nb_row + N1;                                      // [N+1]
     float* wgt = reinterpret_cast<float*>(nb_e + N1);             // [H][N+1] softmax weights (mode 1) / [0] = 1/n (mode 0)
     float* dlk = wgt + p.H * N1;                                  // [H][N+1] derivative of the leaky ReLU at the logit
-    float* gp = dlk + p.H * N1;                                   // [HD] gradient at the pre-activation output
-    float* dsum = gp + HD;                                        // [H] sum_j p_ij <g, hr_j>  = <g, out_pre>
+    float* dsum = dlk + p.H * N1;                                 // [H] sum_j p_ij <g, hr_j>  = <g, out_pre>
     float* gss = dsum + p.H;                                      // [H] gradient of score_s
     __shared__ int s_cnt;
 
@@ -228,7 +235,12 @@ __global__ void __launch_bounds__(kAggThreads) graph_aggregate_bwd_kernel(const 
         const float inv = wgt[0];
         for (int n = 0; n < cnt; ++n) {
             float* dst = p.g_hr + (b * p.N + nb_row[n]) * p.ld_ghr + (long long)nb_e[n] * HD;
-            for (int f = threadIdx.x; f < HD; f += kAggThreads) atomicAdd(dst + f, gp[f] * inv);
+            if (p.vec) {
+                for (int f = threadIdx.x * 4; f < HD; f += kAggThreads * 4)
+                    red_add4(dst + f, gp[f] * inv, gp[f + 1] * inv, gp[f + 2] * inv, gp[f + 3] * inv);
+            } else {
+                for (int f = threadIdx.x; f < HD; f += kAggThreads) atomicAdd(dst + f, gp[f] * inv);
+            }
         }
     } else {
         for (int w = warp; w < cnt * p.H; w += kAggThreads / 32) {
@@ -238,10 +250,19 @@ __global__ void __launch_bounds__(kAggThreads) graph_aggregate_bwd_kernel(const 
             float* dst = p.g_hr + row * p.ld_ghr + (long long)nb_e[n] * HD + h * p.Dh;
             const float pw = wgt[h * N1 + n];
             float dot = 0.f;
-            for (int d = lane; d < p.Dh; d += 32) {
-                const float gv = gp[h * p.Dh + d];
-                dot = fmaf(gv, src[d], dot);
-                atomicAdd(dst + d, pw * gv);
+            if (p.vec) {
+                for (int d = lane * 4; d < p.Dh; d += 128) {
+                    const float4 gv = *reinterpret_cast<const float4*>(gp + h * p.Dh + d);
+                    const float4 sv = *reinterpret_cast<const float4*>(src + d);
+                    dot = fmaf(gv.x, sv.x, fmaf(gv.y, sv.y, fmaf(gv.z, sv.z, fmaf(gv.w, sv.w, dot))));
+                    red_add4(dst + d, pw * gv.x, pw * gv.y, pw * gv.z, pw * gv.w);
+                }
+            } else {
+                for (int d = lane; d < p.Dh; d += 32) {
+                    const float gv = gp[h * p.Dh + d];
+                    dot = fmaf(gv, src[d], dot);
+                    atomicAdd(dst + d, pw * gv);
+                }
             }
             dot = warp_sum(dot);
             if (lane == 0) {
@@ -262,22 +283,22 @@ struct EdgeAggBwdParams {
     const float* g_out;
     float* g_node_val; float* g_node_q; float* g_node_k; float* g_edge_val; float* g_edge_logit;
     long long ld_nv, ld_q, ld_k, ld_ev, ld_el, ld_gnv, ld_gq, ld_gk, ld_gev, ld_gel;
-    int N, P, H, Dh, mode;
+    int N, P, H, Dh, mode, vec;
     float scale;
 };
 
 __device__ __forceinline__ int pair_index(int a, int b, int N) { return a * (N - 1) - (a * (a - 1)) / 2 + (b - a - 1); }
 
 __global__ void __launch_bounds__(kAggThreads) edge_aggregate_bwd_kernel(const EdgeAggBwdParams p) {
-    extern __shared__ unsigned char eaggb_smem[];
+    extern __shared__ __align__(16) unsigned char eaggb_smem[];
     const int HD = p.H * p.Dh;
-    int* nb_node = reinterpret_cast<int*>(eaggb_smem);          // [N]
+    float* gp = reinterpret_cast<float*>(eaggb_smem);             // [HD] gradient row of this node (16-byte aligned)
+    int* nb_node = reinterpret_cast<int*>(gp + ((HD + 3) & ~3));  // [N]
     int* nb_row = nb_node + p.N;                                  // [N]
     float* wgt = reinterpret_cast<float*>(nb_row + p.N);          // [H][N] attention weights
     float* sg = wgt + p.H * p.N;                                  // [H][N] mode 0: sigmoid(edge_logit)
     float* tn = sg + p.H * p.N;                                   // [H][N] <g, edge_val + node_val>, later d logit
-    float* gp = tn + p.H * p.N;                                   // [HD] gradient row of this node
-    float* dsum = gp + HD;                                        // [H]
+    float* dsum = tn + p.H * p.N;                                 // [H]
     float* sinv = dsum + p.H;                                     // [H] mode 0: 1 / max(sum, 1e-5)
     float* clamped = sinv + p.H;                                  // [H] mode 0: 1 when the sum was clamped
     __shared__ int s_cnt;
@@ -361,11 +382,22 @@ __global__ void __launch_bounds__(kAggThreads) edge_aggregate_bwd_kernel(const E
         float* gnv = p.g_node_val + nrow * p.ld_gnv + h * p.Dh;
         const float pw = wgt[h * p.N + n];
         float dot = 0.f;
-        for (int d = lane; d < p.Dh; d += 32) {
-            const float gv = gp[h * p.Dh + d];
-            dot = fmaf(gv, ev[d] + nv[d], dot);
-            atomicAdd(gev + d, pw * gv);
-            atomicAdd(gnv + d, pw * gv);
+        if (p.vec) {
+            for (int d = lane * 4; d < p.Dh; d += 128) {
+                const float4 gv = *reinterpret_cast<const float4*>(gp + h * p.Dh + d);
+                const float4 e4 = *reinterpret_cast<const float4*>(ev + d);
+                const float4 n4 = *reinterpret_cast<const float4*>(nv + d);
+                dot = fmaf(gv.x, e4.x + n4.x, fmaf(gv.y, e4.y + n4.y, fmaf(gv.z, e4.z + n4.z, fmaf(gv.w, e4.w + n4.w, dot))));
+                red_add4(gev + d, pw * gv.x, pw * gv.y, pw * gv.z, pw * gv.w);
+                red_add4(gnv + d, pw * gv.x, pw * gv.y, pw * gv.z, pw * gv.w);
+            }
+        } else {
+            for (int d = lane; d < p.Dh; d += 32) {
+                const float gv = gp[h * p.Dh + d];
+                dot = fmaf(gv, ev[d] + nv[d], dot);
+                atomicAdd(gev + d, pw * gv);
+                atomicAdd(gnv + d, pw * gv);
+            }
         }
         dot = warp_sum(dot);
         if (lane == 0) tn[h * p.N + n] = dot;
@@ -407,7 +439,14 @@ __global__ void __launch_bounds__(kAggThreads) edge_aggregate_bwd_kernel(const E
         const float* q = p.node_q + node * p.ld_q + h * p.Dh;
         float* gk = p.g_node_k + (b * p.N + nb_node[n]) * p.ld_gk + h * p.Dh;
         const float c = tn[h * p.N + n] * p.scale;
-        for (int d = lane; d < p.Dh; d += 32) atomicAdd(gk + d, c * q[d]);
+        if (p.vec) {
+            for (int d = lane * 4; d < p.Dh; d += 128) {
+                const float4 q4 = *reinterpret_cast<const float4*>(q + d);
+                red_add4(gk + d, c * q4.x, c * q4.y, c * q4.z, c * q4.w);
+            }
+        } else {
+            for (int d = lane; d < p.Dh; d += 32) atomicAdd(gk + d, c * q[d]);
+        }
     }
 }
 
@@ -503,7 +542,11 @@ extern "C" int cnf_graph_aggregate_bwd(const cnf_graph_aggregate_bwd_args* a, cn
     p.ld_gss = a->ld_grad_score_s > 0 ? a->ld_grad_score_s : f.H;
     p.ld_gsr = a->ld_grad_score_r > 0 ? a->ld_grad_score_r : (long long)(f.E + 1) * f.H;
     p.N = f.N; p.E = f.E; p.H = f.H; p.Dh = f.Dh; p.mode = f.mode; p.act = f.activation; p.slope = f.leaky_slope;
-    const size_t smem = (size_t)(f.N + 1) * 8 + ((size_t)2 * f.H * (f.N + 1) + (size_t)f.H * f.Dh + 2 * f.H) * 4;
+    {
+        const uintptr_t bits = reinterpret_cast<uintptr_t>(f.hr) | reinterpret_cast<uintptr_t>(a->grad_hr);
+        p.vec = ((f.Dh & 3) == 0 && (p.ld_hr & 3) == 0 && (p.ld_ghr & 3) == 0 && (bits & 15) == 0) ? 1 : 0;
+    }
+    const size_t smem = (size_t)(f.N + 1) * 8 + ((size_t)2 * f.H * (f.N + 1) + (size_t)f.H * f.Dh + 4 + 2 * f.H) * 4;
     CNF_SUPPORTED(smem <= 48 * 1024, "cnf_graph_aggregate_bwd: working set does not fit shared memory");
     graph_aggregate_bwd_kernel<<<(unsigned)(f.B * f.N), kAggThreads, smem, stream>>>(p);
     return launch_status("graph_aggregate_bwd_kernel");
@@ -530,7 +573,17 @@ extern "C" int cnf_edge_aggregate_bwd(const cnf_edge_aggregate_bwd_args* a, cnf_
     p.ld_gnv = a->ld_grad_node_val; p.ld_gq = a->ld_grad_node_q; p.ld_gk = a->ld_grad_node_k;
     p.ld_gev = a->ld_grad_edge_val; p.ld_gel = a->ld_grad_edge_logit;
     p.N = f.N; p.P = f.N * (f.N - 1) / 2; p.H = f.H; p.Dh = f.Dh; p.mode = f.mode; p.scale = f.scale;
-    const size_t smem = (size_t)f.N * 8 + ((size_t)3 * f.H * f.N + (size_t)f.H * f.Dh + 3 * f.H) * 4;
+    {
+        uintptr_t bits = reinterpret_cast<uintptr_t>(f.node_val) | reinterpret_cast<uintptr_t>(f.edge_val) |
+                         reinterpret_cast<uintptr_t>(a->grad_node_val) | reinterpret_cast<uintptr_t>(a->grad_edge_val);
+        long long lds = p.ld_nv | p.ld_ev | p.ld_gnv | p.ld_gev;
+        if (f.mode == 1) {
+            bits |= reinterpret_cast<uintptr_t>(f.node_q) | reinterpret_cast<uintptr_t>(a->grad_node_k);
+            lds |= p.ld_q | p.ld_gk;
+        }
+        p.vec = ((f.Dh & 3) == 0 && (lds & 3) == 0 && (bits & 15) == 0) ? 1 : 0;
+    }
+    const size_t smem = (size_t)f.N * 8 + ((size_t)3 * f.H * f.N + (size_t)f.H * f.Dh + 4 + 3 * f.H) * 4;
     CNF_SUPPORTED(smem <= 48 * 1024, "cnf_edge_aggregate_bwd: working set does not fit shared memory");
     edge_aggregate_bwd_kernel<<<(unsigned)(f.B * f.N), kAggThreads, smem, stream>>>(p);
     return launch_status("edge_aggregate_bwd_kernel");

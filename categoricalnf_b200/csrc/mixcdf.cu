@@ -6,10 +6,13 @@
 //
 // Work decomposition: a CTA owns a tile of TP consecutive positions.  The parameter records of
 // the *transformed* channels only (the conditioner half of nn_out is never read) and the z rows
-// are staged in shared memory with cp.async (16-byte when the layout allows), then one thread
-// evaluates one (position, channel) element: K mixture components in registers, fp32 with MUFU
-// ex2/lg2/rcp.  Elements whose CDF leaves the range where fp32 reproduces the reference's fp64
-// arithmetic to 1e-4 take a float64 path that restates the reference formulas literally.
+// are staged in shared memory with cp.async (16-byte when the layout allows), then a group of
+// G = 2^g adjacent lanes (G = 1 up to K = 8, 8 lanes at K = 64) evaluates one (position, channel)
+// element: each lane prepares its <= 8 mixture components once (bounded scales, softmax numerators)
+// and keeps them in registers, an evaluation of the mixture is 2 MUFU per component plus a
+// butterfly over the group, the inverse is the safeguarded Newton iteration of the pipelined kernel.
+// Elements whose CDF leaves the range where fp32 reproduces the reference's fp64 arithmetic to 1e-4
+// take a float64 path that restates the reference formulas literally.
 // Per-sample ldj: shared-memory per-position partials -> warp-segmented sum -> one global
 // atomicAdd per (CTA, sample).
 #include <stdlib.h>
@@ -42,6 +45,7 @@ struct MixParams {
     const float* nx_w;
     long long P;  // B * S positions
     int S, C, K, PN, TP;
+    int G;   // lanes per element (power of two, K <= NC * G)
     MaskView mask;
     int vec_params;  // parameter rows can be copied as 16-byte chunks
     float reg_max, reg_factor;
@@ -53,11 +57,11 @@ struct MixParams {
 // ------------------------------------------------------------------------------------------------
 // kernel
 // ------------------------------------------------------------------------------------------------
-template <int KT, bool REV>
+template <int NC, bool REV>
 __global__ void __launch_bounds__(kThreads) mixcdf_kernel(const MixParams p) {
     extern __shared__ __align__(16) float smem[];
     const int tid = threadIdx.x;
-    const int K = KT > 0 ? KT : p.K;
+    const int K = p.K;
     const int PN = 2 + 3 * K;
     const int C = p.C, Ct = p.mask.n_t, TP = p.TP;
     const int L = Ct * PN;  // parameter floats per position (transformed channels only)
@@ -122,10 +126,15 @@ __global__ void __launch_bounds__(kThreads) mixcdf_kernel(const MixParams p) {
     cp_async_wait_all();
     __syncthreads();
 
-    // ---- one thread per (position, transformed channel) ----------------------------------------
+    // ---- one lane group per (position, transformed channel) -------------------------------------
     const int nelem = rows * Ct;
     const float inv_ct = 1.0f / (float)Ct;
-    for (int e = tid; e < nelem; e += kThreads) {
+    LaneGroup g;
+    g.G = p.G;
+    g.sub = tid & (p.G - 1);
+    g.mask = p.G == 32 ? 0xffffffffu : (((1u << p.G) - 1u) << ((tid & 31) & ~(p.G - 1)));
+    const int gshift = 31 - __clz(p.G);
+    for (int e = tid >> gshift; e < nelem; e += kThreads >> gshift) {
         const int r = fast_div(e, inv_ct), j = e - r * Ct;
         const long long pos = pos0 + r;
         if (p.mask.s_period > 0) {
@@ -144,9 +153,19 @@ __global__ void __launch_bounds__(kThreads) mixcdf_kernel(const MixParams p) {
         c.K = K;
         c.pre = p.pre != 0;
         const float x = s_z[r * C + ch];
+        MixPrep<NC> P;
+        mix_prepare_g<NC>(P, c, g);
         ElemResult res;
-        if constexpr (!REV) res = mix_forward_elem<KT>(x, c, p.use_reg != 0, p.reg_max, p.reg_factor);
-        else res = mix_inverse_elem<KT>(x, c, p.status);
+        if constexpr (!REV) {
+            const MixEval ev = mix_eval_g<NC>(x, P, g);
+            if (mix_fast_ok(ev)) res = mix_forward_fast<NC>(ev, P, p.use_reg != 0, p.reg_max, p.reg_factor);
+            else res = mix_forward_f64(x, c.rec, c.pre ? nullptr : c.mfac, K, P.log_s, p.use_reg != 0, p.reg_max, p.reg_factor);
+        } else {
+            InvState<NC> st;
+            if (!mix_inverse_g<NC>(x, P, g, g.sub == 0 ? p.status : nullptr, st, res))
+                res = mix_inverse_f64(x, st.x, inv_slow_margin<NC>(st), c.rec, c.pre ? nullptr : c.mfac, K, P.log_s, st.lb0, st.ub0);
+        }
+        if (g.sub != 0) continue;   // every lane of the group holds the same result; lane 0 publishes it
         // z_out = out * change + x * (1 - change) with change = pad (mixture_cdf_layer.py:137-138)
         s_z[r * C + ch] = (padv == 1.0f) ? res.z : fmaf(res.z, padv, x * (1.0f - padv));
         atomicAdd(&s_ldj[r], res.ldj * padv);
@@ -200,18 +219,18 @@ size_t smem_bytes(int TP, int L, int C, int Ct, int K) {
     return f * sizeof(float);
 }
 
-template <int KT, bool REV>
+template <int NC, bool REV>
 int launch2(const MixParams& p, size_t smem, cudaStream_t stream) {
     if (smem > 48 * 1024)
-        CNF_CUDA(cudaFuncSetAttribute(mixcdf_kernel<KT, REV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CNF_CUDA(cudaFuncSetAttribute(mixcdf_kernel<NC, REV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long grid = (p.P + p.TP - 1) / p.TP;
-    mixcdf_kernel<KT, REV><<<(unsigned)grid, kThreads, smem, stream>>>(p);
+    mixcdf_kernel<NC, REV><<<(unsigned)grid, kThreads, smem, stream>>>(p);
     return launch_status(REV ? "mixcdf_inv_kernel" : "mixcdf_fwd_kernel");
 }
 
-template <int KT>
+template <int NC>
 int launch(const MixParams& p, size_t smem, cudaStream_t stream) {
-    return p.reverse ? launch2<KT, true>(p, smem, stream) : launch2<KT, false>(p, smem, stream);
+    return p.reverse ? launch2<NC, true>(p, smem, stream) : launch2<NC, false>(p, smem, stream);
 }
 
 int run(const cnf_mixcdf_args* a, cnf_stream_t stream_, int reverse) {
@@ -257,9 +276,16 @@ int run(const cnf_mixcdf_args* a, cnf_stream_t stream_, int reverse) {
     p.reverse = reverse;
     p.pre = a->params_prebounded;
     const int Ct = p.mask.n_t, L = Ct * p.PN;
-    // tile: about one element per thread, bounded by ~44 KB of parameter staging
-    int elems = kThreads;
-    const int cap = (44 * 1024) / (4 * p.PN);
+    // lanes per element: up to 8 components per lane (4 when K <= 4)
+    const int NC = a->K <= 4 ? 4 : 8;
+    int G = 1;
+    while (NC * G < a->K) G <<= 1;
+    CNF_SUPPORTED(G <= 32, "K=%d exceeds %d mixture components", a->K, NC * 32);
+    p.G = G;
+    // tile: about one element per lane group (two passes when groups are wide), bounded by the parameter staging
+    // (~44 KB, 64 KB for wide groups where a record alone is several hundred bytes)
+    int elems = G == 1 ? kThreads : 2 * kThreads / G;
+    const int cap = ((G == 1 ? 44 : 64) * 1024) / (4 * p.PN);
     if (elems > cap) elems = cap;
     int TP = elems / Ct;
     TP &= ~3;
@@ -270,12 +296,7 @@ int run(const cnf_mixcdf_args* a, cnf_stream_t stream_, int reverse) {
                    ((reinterpret_cast<uintptr_t>(a->nn_out) & 15) == 0);
     const size_t smem = smem_bytes(TP, L, a->C, Ct, a->K);
     CNF_SUPPORTED(smem <= 200 * 1024, "C=%d K=%d needs %zu bytes of shared memory per tile", a->C, a->K, smem);
-    switch (a->K) {
-        case 4: return launch<4>(p, smem, stream);
-        case 8: return launch<8>(p, smem, stream);
-        case 16: return launch<16>(p, smem, stream);
-        default: return launch<0>(p, smem, stream);
-    }
+    return NC == 4 ? launch<4>(p, smem, stream) : launch<8>(p, smem, stream);
 }
 
 }  // namespace

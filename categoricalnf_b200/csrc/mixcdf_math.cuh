@@ -395,5 +395,128 @@ __device__ __forceinline__ float inv_slow_margin(const InvState<KT>& st) {
     return fmaxf(4.0f * (st.ub - st.lb) + 1e-5f * fmaxf(1.0f, fabsf(st.x)), 1e-5f * st.cond / fmaxf(st.f, 1e-37f));
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Group-cooperative prepared form for a RUN-TIME number of components (generic kernel): G = 2^g
+// adjacent lanes share one element, lane `sub` owns the components sub, sub + G, ... (at most NC of
+// them, held in registers as a MixPrep<NC>); partial sums meet in xor-butterflies over the group's
+// lanes, which leave bit-identical values in every lane, so the Newton iteration below stays
+// uniform inside a group.  G = 1 degenerates to one thread per element.  Same arithmetic as the
+// compile-time form above (mix_prepare / mix_eval_p / mix_inverse_fast).
+// ------------------------------------------------------------------------------------------------
+struct LaneGroup {
+    unsigned mask;   // lanes of this group
+    int G, sub;
+    __device__ __forceinline__ float sum(float v) const {
+        for (int d = G >> 1; d > 0; d >>= 1) v += __shfl_xor_sync(mask, v, d);
+        return v;
+    }
+    __device__ __forceinline__ float max(float v) const {
+        for (int d = G >> 1; d > 0; d >>= 1) v = fmaxf(v, __shfl_xor_sync(mask, v, d));
+        return v;
+    }
+    __device__ __forceinline__ float min(float v) const {
+        for (int d = G >> 1; d > 0; d >>= 1) v = fminf(v, __shfl_xor_sync(mask, v, d));
+        return v;
+    }
+};
+
+template <int NC>
+__device__ __forceinline__ void mix_prepare_g(MixPrep<NC>& P, const ElemCtx& c, const LaneGroup& g) {
+    const int K = c.K;
+    const float* lp = c.rec + 2;
+    const float* mu = lp + K;
+    const float* ms = mu + K;
+    float m = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+        const int k = g.sub + i * g.G;
+        if (k < K) m = fmaxf(m, lp[k]);
+    }
+    const float m_l2 = g.max(m) * kLog2e;
+    float W = 0.f, span = 0.f;
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+        const int k = g.sub + i * g.G;
+        const bool v = k < K;
+        const int kk = v ? k : g.sub;   // G <= K: component `sub` always exists; padding slots copy it with weight 0
+        const float nls2 = c.pre ? -ms[kk] * kLog2e : tanh_from_2log2e(ms[kk] * c.ma2[kk]) * (-c.mfac[kk] * kLog2e);
+        P.einv2[i] = ex2(nls2) * kLog2e;
+        P.mu[i] = mu[kk];
+        const float w = v ? ex2(fmaf(lp[kk], kLog2e, -m_l2)) : 0.f;
+        P.w[i] = w;
+        W += w;
+        if (v) span += ex2(-nls2);
+    }
+    P.iw = rcp(g.sum(W));
+    P.span = g.sum(span);
+    P.t = c.rec[0];
+    P.log_s = c.pre ? c.rec[1] : tanh_from_2log2e(c.rec[1] * c.a2) * c.fac;
+}
+
+template <int NC>
+__device__ __forceinline__ MixEval mix_eval_g(float x, const MixPrep<NC>& P, const LaneGroup& g) {
+    MixEval e = mix_eval_p<NC>(x, P);
+    e.F = g.sum(e.F);
+    e.G = g.sum(e.G);
+    e.f = g.sum(e.f);
+    return e;
+}
+
+// mix_inverse_fast for a lane group (see there for the method).
+template <int NC>
+__device__ __forceinline__ bool mix_inverse_g(float zin, const MixPrep<NC>& P, const LaneGroup& g, uint32_t* status,
+                                              InvState<NC>& st, ElemResult& out) {
+    const float log_s = P.log_s;
+    const float y = fmaf(zin, fast_exp(-log_s), -P.t);
+    st.mixt_ldj = softplus_pm(y);
+    const float ey = ex2(-fabsf(y) * kLog2e);
+    const float ry = rcp(1.0f + ey);
+    float Ft = y >= 0.f ? ry : ey * ry;
+    float Gt = y >= 0.f ? ey * ry : ry;
+    if (!(Ft == Ft)) flag(status, CNF_FLAG_CDF_RANGE);
+    Ft = fminf(fmaxf(Ft, 1e-5f), 1.0f - 1e-5f);   // reference clamp (mixture_cdf_layer.py:130)
+    Gt = fminf(fmaxf(Gt, 1e-5f), 1.0f - 1e-5f);
+    const bool upper = Ft > 0.5f;
+    float lb = INFINITY, ub = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {   // bracket (:252-254)
+        lb = fminf(lb, fmaf(-20.f, P.span, P.mu[k]));
+        ub = fmaxf(ub, fmaf(20.f, P.span, P.mu[k]));
+    }
+    lb = g.min(lb);
+    ub = g.max(ub);
+    st.lb0 = lb; st.ub0 = ub;
+    const float yc = (lg2(Ft) - lg2(Gt)) * kLn2;
+    float x = 0.f, prev = INFINITY;
+    MixEval e = mix_eval_g<NC>(x, P, g);
+    for (int it = 0; it < 48; ++it) {
+        const bool gt = upper ? (e.G < Gt) : (e.F > Ft);
+        if (gt) ub = x; else lb = x;
+        const float mid = 0.5f * (lb + ub);
+        const float sloc = e.F * e.G * rcp(e.f);
+        const float step = ((lg2(e.F) - lg2(e.G)) * kLn2 - yc) * sloc;
+        const float xt = x - step;
+        const bool fin = e.f >= 1e-30f && fabsf(step) < 1e30f;
+        const bool conv = fin && step * step <= 2.5e-8f * fmaxf(1.0f, fabsf(xt)) * sloc;
+        const bool newton = conv || (fin && xt >= lb && xt <= ub && fabsf(step) < 0.5f * prev);
+        const float xn = newton ? xt : mid;
+        prev = newton ? fabsf(step) : (ub - lb);
+        const bool done = conv || (!newton && !(ub - lb > 5e-7f * fmaxf(1.0f, fabsf(xn))));
+        const bool stuck = xn == x;
+        x = xn;
+        if (stuck) break;
+        e = mix_eval_g<NC>(x, P, g);
+        if (done) break;
+    }
+    st.x = x; st.lb = lb; st.ub = ub; st.f = e.f;
+    st.cond = fminf(e.F, e.G);
+    if (!(st.cond <= 8.0f * fmaxf(1.0f, fabsf(x)) * e.f) || !(e.f >= 1e-30f)) return false;
+    out.z = x;
+    out.ldj = -(log_s + st.mixt_ldj + fast_log(e.f));
+    out.reg = 0.f;
+    return true;
+}
+
 }  // namespace mixmath
 }  // namespace cnf

@@ -17,7 +17,14 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
+import os
+
 from ... import ops
+
+# Precision of the two backward GEMMs (grad_x, grad_W).  None = the forward's precision (3xTF32 by default: gradients
+# at fp32 level, like the reference, which trains in plain fp32).  "tf32" (or CNF_B200_BWD_PRECISION=tf32) runs them as
+# one-pass TF32 - a third of the tensor-core work, ~1e-3 relative gradient error.
+BACKWARD_PRECISION = os.environ.get("CNF_B200_BWD_PRECISION") or None
 
 
 class _TCLinearFn(torch.autograd.Function):
@@ -35,7 +42,8 @@ class _TCLinearFn(torch.autograd.Function):
     def backward(ctx, gy):
         x, weight = ctx.saved_tensors
         gx, gw, gb = ops.linear_bwd(x, weight, gy, need_x=ctx.needs_input_grad[0], need_weight=ctx.needs_input_grad[1],
-                                    need_bias=ctx.has_bias and ctx.needs_input_grad[2], precision=ctx.precision)
+                                    need_bias=ctx.has_bias and ctx.needs_input_grad[2],
+                                    precision=BACKWARD_PRECISION or ctx.precision)
         return gx, gw, gb, None
 
 

@@ -16,6 +16,7 @@ ap.add_argument("--nodes", type=int, default=20)
 ap.add_argument("--reps", type=int, default=10)
 ap.add_argument("--profile", action="store_true")
 ap.add_argument("--cpu", action="store_true", help="also time the CPU oracle on a 32-graph sample")
+ap.add_argument("--train", action="store_true", help="also time a training step (forward in training mode + backward)")
 ap.add_argument("--config", default="gc", choices=["gc", "mol"],
                 help="gc: graph colouring (config 3); mol: GraphCNF molecule generation forward (config 4, batch 64 per GPU) and "
                      "sampling (config 5, batch 1024 per GPU)")
@@ -97,6 +98,21 @@ with torch.no_grad():
 out = {"config": "graph_coloring B=%d N=%d (8 flows, hidden 384, 4 attention layers, K=8, d=2)" % (B, N), "fwd_ms": fwd_ms,
        "fwd_graphs_per_s": B / fwd_ms * 1e3, "reverse_ms": rev_ms, "reverse_graphs_per_s": B / rev_ms * 1e3,
        "cnf_launches_per_forward": launches}
+if args.train:
+    model.train()
+    params_ = [p_ for p_ in model.parameters() if p_.requires_grad]
+
+    def step():
+        for p_ in params_:
+            p_.grad = None
+        zt, lt = model(xc, adjacency=ac, length=lc)
+        (-(lt.sum()) + 0.5 * (zt ** 2).sum()).backward()
+    n0 = ops.launch_count()
+    step()
+    out["cnf_launches_per_train_step"] = ops.launch_count() - n0
+    out["train_step_ms"] = timed(step, max(3, args.reps // 2))
+    out["train_graphs_per_s"] = B / out["train_step_ms"] * 1e3
+    model.eval()
 if args.cpu:
     from oracle import graph_oracle as GO
     sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
@@ -109,7 +125,15 @@ if args.cpu:
     out["cpu_oracle_graphs_per_s"] = nb / dt
     out["cpu_cores"] = os.cpu_count()
 print(json.dumps(out))
-if args.profile:
+if args.profile and args.train:
+    from torch.profiler import profile, ProfilerActivity
+    model.train()
+    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+        for _ in range(2):
+            step()
+        torch.cuda.synchronize()
+    print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=30, max_name_column_width=70))
+elif args.profile:
     from torch.profiler import profile, ProfilerActivity
     with torch.no_grad(), profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
         for _ in range(3):
