@@ -228,6 +228,32 @@ __global__ void __launch_bounds__(kThreads) logistic_logprob_kernel(const LogPro
     }
 }
 
+// Per-sample sums only, S*C a multiple of 1024: a warp owns 1024 consecutive elements of ONE sample per step (eight
+// 16-byte loads per lane in flight), so the reduction is one warp sum and one atomic per 4 KB of input - the kernel runs at
+// HBM speed instead of at the issue rate of a segmented scan per element.
+__global__ void __launch_bounds__(kThreads) logistic_logprob_rows_kernel(const LogProbParams p) {
+    const int lane = threadIdx.x & 31;
+    const long long nchunks = p.n >> 10;
+    const long long nwarps = (long long)gridDim.x * (kThreads / 32);
+    const int c4 = p.C >> 2;   // p.C % 4 == 0 on this path: a 16-byte load never straddles two positions
+    for (long long w = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); w < nchunks; w += nwarps) {
+        const long long base = w << 10;
+        float4 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = __ldcs(reinterpret_cast<const float4*>(p.x + base) + j * 32 + lane);
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float s = softplus_pm((v[j].x - p.mu) * p.inv_sigma) + softplus_pm((v[j].y - p.mu) * p.inv_sigma) +
+                      softplus_pm((v[j].z - p.mu) * p.inv_sigma) + softplus_pm((v[j].w - p.mu) * p.inv_sigma) + 4.0f * p.log_sigma;
+            if (p.pad) s *= p.pad[((base >> 2) + j * 32 + lane) / c4];
+            acc -= s;
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) atomicAdd(p.out + base / p.SC, acc);
+    }
+}
+
 struct SampleParams {
     const float* u; float* x; long long n;
     unsigned long long seed, offset;
@@ -344,6 +370,11 @@ extern "C" int cnf_logistic_logprob(const cnf_logistic_logprob_args* a, cnf_stre
     CNF_REQUIRE(a->x && (a->out || a->elementwise), "x is NULL or no output requested");
     p.x = a->x; p.pad = a->pad; p.out = a->out; p.elem = a->elementwise;
     p.SC = a->S * a->C; p.C = a->C; p.mu = a->mu; p.inv_sigma = 1.0f / a->sigma; p.log_sigma = logf(a->sigma);
+    if (p.out != nullptr && p.elem == nullptr && (p.SC & 1023) == 0 && (p.C & 3) == 0 &&
+        (reinterpret_cast<uintptr_t>(p.x) & 15) == 0) {
+        logistic_logprob_rows_kernel<<<grid_for((p.n >> 10) * 32, 8), kThreads, 0, stream>>>(p);
+        return launch_status("logistic_logprob_rows_kernel");
+    }
     logistic_logprob_kernel<<<grid_for(p.n), kThreads, 0, stream>>>(p);
     return launch_status("logistic_logprob_kernel");
 }

@@ -198,3 +198,25 @@ def test_block_fusion_matches_unfused_and_oracle(padded):
     if not padded:
         assert_close(outs[1][0], z_ref, what="z modules")
         assert_close(outs[1][1], ldj_ref, rtol=1e-4, atol=2e-4, what="ldj modules")
+
+
+@pytest.mark.parametrize("B,S,C,padded,accumulate", [(5, 64, 16, False, False), (3, 256, 16, True, True), (7, 512, 4, True, False),
+                                                     (2, 63, 16, True, False)])
+def test_logistic_logprob_row_kernel(B, S, C, padded, accumulate):
+    """Per-sample prior log-likelihood (distributions.py:129-137): the warp-per-1024-elements kernel (S*C % 1024 == 0) and,
+    last case, the general kernel on the same checks."""
+    from categoricalnf_b200 import ops
+    g = torch.Generator().manual_seed(B * S)
+    x = torch.randn(B, S, C, generator=g) * 3
+    x[0, 0, 0], x[0, 0, 1] = 60.0, -60.0
+    pad = None
+    if padded:
+        length = torch.randint(1, S + 1, (B,), generator=g)
+        pad = (torch.arange(S)[None, :] < length[:, None]).float()
+    ref = O.logistic_log_prob(x.double())
+    ref = (ref * pad.unsqueeze(-1).double()).sum(dim=[1, 2]) if padded else ref.sum(dim=[1, 2])
+    base = torch.randn(B, generator=g)
+    out = base.clone().cuda() if accumulate else None
+    res, _ = ops.logistic_logprob(x.cuda(), pad=None if pad is None else pad.cuda(), out=out)
+    want = ref + base.double() if accumulate else ref
+    assert_close(res, want, rtol=1e-5, atol=1e-3, what="per-sample log-prob")
