@@ -53,7 +53,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         objs.append(obj)
         stale = force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), hdr_time)
         if stale:
-            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+            extra = os.environ.get("CNF_B200_NVCC_FLAGS", "").split()      # e.g. -DCNF_NO_F32X2 for A/B builds
+            cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
             jobs.append((src, cmd))
 
     def run(job):

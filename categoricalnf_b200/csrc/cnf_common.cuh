@@ -78,6 +78,34 @@ __device__ __forceinline__ float rcp(float x) {
 __device__ __forceinline__ float fast_exp(float x) { return ex2(x * kLog2e); }
 __device__ __forceinline__ float fast_log(float x) { return lg2(x) * kLn2; }
 
+// Packed fp32 pairs (sm_100: FADD2 / FMUL2 / FFMA2 issue two IEEE fp32 operations per instruction - same rounding as the
+// scalar forms, half the issue slots).  A pair lives in one 64-bit register pair.
+struct f2 {
+    unsigned long long v;
+};
+__device__ __forceinline__ f2 f2_make(float lo, float hi) {
+    f2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ f2 f2_splat(float x) { return f2_make(x, x); }
+__device__ __forceinline__ void f2_get(f2 a, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v)); }
+__device__ __forceinline__ f2 f2_add(f2 a, f2 b) {
+    f2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+__device__ __forceinline__ f2 f2_mul(f2 a, f2 b) {
+    f2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+__device__ __forceinline__ f2 f2_fma(f2 a, f2 b, f2 c) {
+    f2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+    return r;
+}
+
 // tanh(v) with v already multiplied by 2*log2(e): 1 - 2/(1 + 2^{v2}).  Absolute error ~1.2e-7.
 __device__ __forceinline__ float tanh_from_2log2e(float v2) { return fmaf(-2.0f, rcp(1.0f + ex2(v2)), 1.0f); }
 

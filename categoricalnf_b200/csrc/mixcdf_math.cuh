@@ -244,6 +244,13 @@ __device__ __forceinline__ ElemResult mix_inverse_elem(float zin, const ElemCtx&
 // sigmoid).  The forward transform evaluates once, the inverse up to ~49 times.  log2(e) factors
 // are folded into the per-component constants so the evaluation loop has no scaling multiplies.
 // ------------------------------------------------------------------------------------------------
+// Packed fp32 pairs in the per-component loops (cnf_common.cuh: f2_*); -DCNF_NO_F32X2 builds the scalar form for A/B runs.
+#ifdef CNF_NO_F32X2
+constexpr bool kPackedPairs = false;
+#else
+constexpr bool kPackedPairs = true;
+#endif
+
 template <int KT>
 struct MixPrep {
     float mu[KT];
@@ -266,15 +273,45 @@ __device__ __forceinline__ void mix_prepare(MixPrep<KT>& P, const float* rec, co
     for (int k = 1; k < KT; ++k) m = fmaxf(m, lp[k]);
     const float m_l2 = m * kLog2e;
     float W = 0.f, span = 0.f;
+    if constexpr (kPackedPairs && KT % 2 == 0) {
+        // two components per instruction (FMUL2 / FADD2 / FFMA2); the MUFU calls stay scalar
+        const f2 one = f2_splat(1.0f), mtwo = f2_splat(-2.0f), l2e = f2_splat(kLog2e), nm = f2_splat(-m_l2);
+        f2 W2 = f2_splat(0.f);
 #pragma unroll
-    for (int k = 0; k < KT; ++k) {
-        const float2 bk = bnd[k * BSTRIDE];
-        const float nls2 = tanh_from_2log2e(ms[k] * bk.x) * bk.y;   // -ls_k * log2(e)
-        P.einv2[k] = ex2(nls2) * kLog2e;
-        if (WANT_SPAN) span += ex2(-nls2);
-        P.mu[k] = mu[k];
-        P.w[k] = ex2(fmaf(lp[k], kLog2e, -m_l2));
-        W += P.w[k];
+        for (int k = 0; k < KT; k += 2) {
+            const float2 b0 = bnd[k * BSTRIDE], b1 = bnd[(k + 1) * BSTRIDE];
+            float t0, t1;
+            f2_get(f2_mul(f2_make(ms[k], ms[k + 1]), f2_make(b0.x, b1.x)), t0, t1);
+            const f2 r = f2_make(rcp(1.0f + ex2(t0)), rcp(1.0f + ex2(t1)));          // tanh = 1 - 2 / (1 + 2^v)
+            float n0, n1;
+            f2_get(f2_mul(f2_fma(mtwo, r, one), f2_make(b0.y, b1.y)), n0, n1);        // -ls_k * log2(e)
+            float e0, e1;
+            f2_get(f2_mul(f2_make(ex2(n0), ex2(n1)), l2e), e0, e1);
+            P.einv2[k] = e0;
+            P.einv2[k + 1] = e1;
+            if (WANT_SPAN) span += ex2(-n0) + ex2(-n1);
+            P.mu[k] = mu[k];
+            P.mu[k + 1] = mu[k + 1];
+            float a0, a1;
+            f2_get(f2_fma(f2_make(lp[k], lp[k + 1]), l2e, nm), a0, a1);
+            P.w[k] = ex2(a0);
+            P.w[k + 1] = ex2(a1);
+            W2 = f2_add(W2, f2_make(P.w[k], P.w[k + 1]));
+        }
+        float w0, w1;
+        f2_get(W2, w0, w1);
+        W = w0 + w1;
+    } else {
+#pragma unroll
+        for (int k = 0; k < KT; ++k) {
+            const float2 bk = bnd[k * BSTRIDE];
+            const float nls2 = tanh_from_2log2e(ms[k] * bk.x) * bk.y;   // -ls_k * log2(e)
+            P.einv2[k] = ex2(nls2) * kLog2e;
+            if (WANT_SPAN) span += ex2(-nls2);
+            P.mu[k] = mu[k];
+            P.w[k] = ex2(fmaf(lp[k], kLog2e, -m_l2));
+            W += P.w[k];
+        }
     }
     P.iw = rcp(W);
     P.span = span;
@@ -285,16 +322,45 @@ __device__ __forceinline__ void mix_prepare(MixPrep<KT>& P, const float* rec, co
 template <int KT>
 __device__ __forceinline__ MixEval mix_eval_p(float x, const MixPrep<KT>& P) {
     float Fs = 0.f, Gs = 0.f, fs = 0.f;
+    if constexpr (kPackedPairs && KT % 2 == 0) {
+        const f2 xx = f2_splat(x), one = f2_splat(1.0f), mone = f2_splat(-1.0f);
+        f2 F2 = f2_splat(0.f), G2 = f2_splat(0.f), d2 = f2_splat(0.f);
 #pragma unroll
-    for (int k = 0; k < KT; ++k) {
-        const float u2 = (x - P.mu[k]) * P.einv2[k];   // u * log2(e)
-        const float e = ex2(-fabsf(u2));
-        const float r = rcp(1.0f + e);
-        const float q = e * r;  // min(sigma, 1 - sigma)
-        const bool pos = u2 >= 0.0f;
-        Fs = fmaf(P.w[k], pos ? r : q, Fs);
-        Gs = fmaf(P.w[k], pos ? q : r, Gs);
-        fs = fmaf(P.w[k] * (q * r), P.einv2[k], fs);
+        for (int k = 0; k < KT; k += 2) {
+            const f2 ei = f2_make(P.einv2[k], P.einv2[k + 1]);
+            const f2 w = f2_make(P.w[k], P.w[k + 1]);
+            float u0, u1;
+            f2_get(f2_mul(f2_fma(f2_make(P.mu[k], P.mu[k + 1]), mone, xx), ei), u0, u1);   // u * log2(e)
+            const float e0 = ex2(-fabsf(u0)), e1 = ex2(-fabsf(u1));
+            const f2 e = f2_make(e0, e1);
+            float s0, s1;
+            f2_get(f2_add(e, one), s0, s1);
+            const float r0 = rcp(s0), r1 = rcp(s1);
+            const f2 r = f2_make(r0, r1);
+            const f2 q = f2_mul(e, r);                                                    // min(sigma, 1 - sigma)
+            float q0, q1;
+            f2_get(q, q0, q1);
+            const bool p0 = u0 >= 0.0f, p1 = u1 >= 0.0f;
+            F2 = f2_fma(w, f2_make(p0 ? r0 : q0, p1 ? r1 : q1), F2);
+            G2 = f2_fma(w, f2_make(p0 ? q0 : r0, p1 ? q1 : r1), G2);
+            d2 = f2_fma(f2_mul(w, f2_mul(q, r)), ei, d2);
+        }
+        float a, b;
+        f2_get(F2, a, b); Fs = a + b;
+        f2_get(G2, a, b); Gs = a + b;
+        f2_get(d2, a, b); fs = a + b;
+    } else {
+#pragma unroll
+        for (int k = 0; k < KT; ++k) {
+            const float u2 = (x - P.mu[k]) * P.einv2[k];   // u * log2(e)
+            const float e = ex2(-fabsf(u2));
+            const float r = rcp(1.0f + e);
+            const float q = e * r;  // min(sigma, 1 - sigma)
+            const bool pos = u2 >= 0.0f;
+            Fs = fmaf(P.w[k], pos ? r : q, Fs);
+            Gs = fmaf(P.w[k], pos ? q : r, Gs);
+            fs = fmaf(P.w[k] * (q * r), P.einv2[k], fs);
+        }
     }
     MixEval o;
     o.F = Fs * P.iw;
