@@ -14,8 +14,12 @@
 //     warp 1        tcgen05.mma kind::tf32, M=128, N=CT*PNP; accumulator = the records, in tensor memory,
 //                   two accumulator stages: the mixture math of tile i overlaps the GEMM of tile i+1
 //     warps 2-3     3xTF32 operand split (precision 1) ; warp 2 owns the tensor-memory allocation
-//     warps 4-15    12 epilogue warps: TMEM lane = position; warp (q, g) handles lane quadrant q and the
-//                   channels j = g, g+3, ... (128 registers per thread: the element math does not spill).  tcgen05.ld pulls the record of one (position, channel) into registers, bias is
+//     warps 4-19    16 epilogue warps: TMEM lane = position; warp (q, g) handles lane quadrant q and the
+//                   channels j = g, g+4, ... (2 per thread at 8 transformed channels).  The CTA starts with 96
+//                   registers per thread; the service warpgroup (warps 0-3) releases down to 32 and the four
+//                   epilogue warpgroups grow to 112 (setmaxnreg - the pool is per CTA, so the two sides must
+//                   balance), which keeps the element math free of spills.  12 warps at 128 registers: 0.272 ms,
+//                   16 at 112: 0.250 ms.  tcgen05.ld pulls the record of one (position, channel) into registers, bias is
 //                   added, and the element is transformed exactly like mixcdf_pipe.cu (same mixmath code).
 //                   The z tile sits in shared memory (bulk-async load), is updated in place and leaves with
 //                   one bulk-async store; ldj through warp sums and ~1 atomic per (warp, sample).
@@ -38,7 +42,18 @@ constexpr int kBM = 128;
 constexpr int kBK = 32;
 constexpr int kABytes = kBM * 128;
 constexpr int kStageCols = 256;
-constexpr int kEpiWarps = 12;   // 3 channel groups x 4 lane quadrants: 512 threads per CTA -> 128 registers each
+#ifndef CNF_FUSED_EPI_WARPS
+#define CNF_FUSED_EPI_WARPS 16
+#endif
+// 4 channel groups x 4 lane quadrants.  640 threads start with 96 registers each; the four service warps (one warpgroup)
+// then release theirs down to kAuxRegs and the four epilogue warpgroups grow to kEpiRegs (setmaxnreg), so the element
+// math keeps the ~110 registers it needs without spilling while 16 instead of 12 warps hide its MUFU latency, and the
+// 8 transformed channels split evenly (2 per thread instead of 3/3/2).
+constexpr int kEpiWarps = CNF_FUSED_EPI_WARPS;
+constexpr int kAuxRegs = 32, kEpiRegs = 112;
+// setmaxnreg.inc draws from the CTA's own pool only: what the service warpgroup releases must cover what the epilogue
+// warpgroups claim
+static_assert(128 * (96 - kAuxRegs) >= 32 * kEpiWarps * (kEpiRegs - 96), "register hand-over does not balance");
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kThreadsFused = 128 + kEpiThreads;
 constexpr int kZStages = 3;
@@ -206,7 +221,9 @@ linear_mixcdf_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_cons
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-
+    if (warp < 4) {
+    // register hand-over between warpgroups: 128 * (96 - 32) = 512 * (112 - 96)
+    if constexpr (kEpiWarps == 16) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kAuxRegs));
     if (warp == 0) {
         // ---------------- TMA producer --------------------------------------------------------------
         if (lane == 0) {
@@ -259,7 +276,7 @@ linear_mixcdf_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_cons
                 if (acc == 0) acc_phase ^= 1u;
             }
         }
-    } else if (warp < 4) {
+    } else {
         // ---------------- 3xTF32 split (see linear_tc.cu) ------------------------------------------
         if constexpr (STRICT) {
             const int tt = tid - 64;
@@ -284,8 +301,10 @@ linear_mixcdf_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_cons
                 }
             }
         }
+    }
     } else {
         // ---------------- epilogue: thread = (position row, channel group g) ------------------------
+        if constexpr (kEpiWarps == 16) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kEpiRegs));
         const int ew = warp - 4;
         const int q = ew & 3, g = ew >> 2;
         const int row = q * 32 + lane;
