@@ -31,7 +31,14 @@ def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream(t: torch.Tensor) -> int:
+    """cudaStream_t of torch's current stream on ``t``'s device (the raw-handle query is ~10x cheaper than building a
+    ``torch.cuda.Stream`` object per launch, which matters for the launch-bound graph flows)."""
+    if _raw_stream is not None:
+        return _raw_stream(t.device.index)
     return torch.cuda.current_stream(t.device).cuda_stream
 
 

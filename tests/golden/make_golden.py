@@ -695,6 +695,18 @@ def gold_graphcnf(seed):
     sd = {"sd__" + k: v for k, v in model.state_dict().items()}
     save("graphcnf_small", x=x, adjacency=adj, length=length, u_nodes=u_nodes, u_edges=u_edges, u_virtual=u_virtual, z=z, ldj=ldj,
          z_edges_init=z_edges_init, z_nodes_init=z_nodes_init, x_smp=x_smp, adj_smp=adj_smp, ldj_smp=ldj_smp, N=N, **sd)
+    # training step of the reference (general/train.py:148-152 calls loss.backward() on the negative log-likelihood): the same
+    # forward on the recorded noise with autograd enabled, gradients of every parameter -> graphcnf_small_grads.npz
+    replay = iter([u_nodes, u_edges, u_virtual])
+    for e in (model.node_encoding, model.edge_attr_encoding, model.edge_virtual_encoding):
+        e.prior_distribution.distribution.sample = lambda sample_shape=torch.Size(): next(replay)
+    model.zero_grad()
+    z2, ldj2 = model(x, adjacency=adj, length=length)
+    assert torch.allclose(z2, z, atol=1e-6) and torch.allclose(ldj2, ldj, atol=1e-5)
+    wz = torch.randn(z2.shape, generator=torch.Generator().manual_seed(seed + 100))
+    (-(ldj2.sum()) + (z2 * wz).sum()).backward()
+    grads = {"grad__" + k: p_.grad for k, p_ in model.named_parameters() if p_.grad is not None}
+    save("graphcnf_small_grads", wz=wz, **grads)
 
 
 def gold_encoding_variants(seed):

@@ -221,3 +221,33 @@ def test_edge_gnn_training_gradients_vs_oracle(name):
         scale = max(float(sd[k].grad.abs().max()), floor)
         assert p.grad is not None, k
         assert_close(p.grad / scale, sd[k].grad / scale, rtol=1e-3, atol=3e-4, what="grad " + k)
+
+
+def test_graphcnf_training_step_gradients_vs_reference():
+    """One training step of GraphCNF (BASELINE config 4 in small): the forward of the golden run with autograd enabled, the
+    loss the golden script used, and the gradient of EVERY parameter against the gradients the unmodified reference produced
+    for it (tests/golden/graphcnf_small_grads.npz) - encodings, node / edge-attribute / virtual-edge flows, RGCN and Edge-GNN
+    coupling networks all differentiate through the backward kernels."""
+    from test_gpu_graph import _build_graphcnf, _sd
+    from categoricalnf_b200 import ops
+    g, gg = load_golden("graphcnf_small"), load_golden("graphcnf_small_grads")
+    model = _build_graphcnf(g.N, sd=_sd(g))          # eval mode, like the golden run; autograd on
+    before = ops.launch_count()
+    z, ldj = model(g.x.cuda(), adjacency=g.adjacency.cuda(), length=g.length.cuda(), u_noise=g.u_nodes.cuda(),
+                   u_noise_edges=g.u_edges.cuda(), u_noise_virtual=g.u_virtual.cuda())
+    assert_close(z, g.z, what="z nodes")
+    assert_close(ldj, g.ldj, rtol=1e-4, atol=5e-4, what="ldj")
+    (-(ldj.sum()) + (z * gg.wz.cuda()).sum()).backward()
+    assert ops.launch_count() - before > 300, "forward + backward must run on the C-ABI kernels"
+    ref = {k[len("grad__"):]: v for k, v in gg.items() if k.startswith("grad__")}
+    floor = 1e-3 * max(float(v.abs().max()) for v in ref.values())
+    checked = 0
+    for name, p in model.named_parameters():
+        if name not in ref:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, "unexpected gradient for " + name
+            continue
+        assert p.grad is not None, "no gradient for " + name
+        scale = max(float(ref[name].abs().max()), floor)
+        assert_close(p.grad / scale, ref[name] / scale, rtol=2e-3, atol=5e-4, what="grad " + name)
+        checked += 1
+    assert checked == len(ref)

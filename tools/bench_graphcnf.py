@@ -15,6 +15,7 @@ import torch
 ap = argparse.ArgumentParser()
 ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--profile", action="store_true")
+ap.add_argument("--cprofile", action="store_true", help="host-side cProfile of the forward pass (where the launch-bound time goes)")
 ap.add_argument("--fwd-batch", type=int, default=64)
 ap.add_argument("--inv-batch", type=int, default=1024)
 args = ap.parse_args()
@@ -104,6 +105,19 @@ with torch.no_grad():
 print(json.dumps({"config": "GraphCNF Zinc250k shape (N=38, flows 4/6/6, hidden 384/192, 4 layers)", "fwd_batch": Bf, "fwd_ms": fwd_ms,
                   "fwd_graphs_per_s": Bf / fwd_ms * 1e3, "cnf_launches_per_forward": launches, "sampling_batch": Bi, "sampling_ms": inv_ms,
                   "sampling_graphs_per_s": Bi / inv_ms * 1e3}))
+if args.cprofile:
+    import cProfile
+    import pstats
+    pr = cProfile.Profile()
+    with torch.no_grad():
+        pr.enable()
+        for _ in range(3):
+            fwd()
+        torch.cuda.synchronize()
+        pr.disable()
+    st = pstats.Stats(pr)
+    st.sort_stats("tottime").print_stats(28)
+    st.sort_stats("cumulative").print_stats(35)
 if args.profile:
     from torch.profiler import profile, ProfilerActivity
     for tag, fn in (("forward B=%d" % Bf, fwd), ("sampling B=%d" % Bi, inv)):
