@@ -231,12 +231,12 @@ def test_graphcnf_training_step_gradients_vs_reference():
     from test_gpu_graph import _build_graphcnf, _sd
     from categoricalnf_b200 import ops
     g, gg = load_golden("graphcnf_small"), load_golden("graphcnf_small_grads")
-    model = _build_graphcnf(g.N, sd=_sd(g))          # eval mode, like the golden run; autograd on
+    model = _build_graphcnf(g.N, sd=_sd(g)).train()
     before = ops.launch_count()
     z, ldj = model(g.x.cuda(), adjacency=g.adjacency.cuda(), length=g.length.cuda(), u_noise=g.u_nodes.cuda(),
                    u_noise_edges=g.u_edges.cuda(), u_noise_virtual=g.u_virtual.cuda())
-    assert_close(z, g.z, what="z nodes")
-    assert_close(ldj, g.ldj, rtol=1e-4, atol=5e-4, what="ldj")
+    assert_close(z, gg.z_train, what="z nodes")
+    assert_close(ldj, gg.ldj_train, rtol=1e-4, atol=5e-4, what="ldj")
     (-(ldj.sum()) + (z * gg.wz.cuda()).sum()).backward()
     assert ops.launch_count() - before > 300, "forward + backward must run on the C-ABI kernels"
     ref = {k[len("grad__"):]: v for k, v in gg.items() if k.startswith("grad__")}

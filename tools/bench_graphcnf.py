@@ -15,6 +15,7 @@ import torch
 ap = argparse.ArgumentParser()
 ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--profile", action="store_true")
+ap.add_argument("--train", action="store_true", help="also time a training step (forward in training mode + backward) at --fwd-batch")
 ap.add_argument("--cprofile", action="store_true", help="host-side cProfile of the forward pass (where the launch-bound time goes)")
 ap.add_argument("--fwd-batch", type=int, default=64)
 ap.add_argument("--inv-batch", type=int, default=1024)
@@ -102,9 +103,26 @@ with torch.no_grad():
     z_nodes = model.prior_distribution.sample(shape=(Bi, N, 6)) * (torch.arange(N, device="cuda")[None, :, None] < len_i[:, None, None])
     inv = lambda: model(z_nodes, reverse=True, length=len_i)
     inv_ms = timed(inv, max(2, args.reps // 2))
-print(json.dumps({"config": "GraphCNF Zinc250k shape (N=38, flows 4/6/6, hidden 384/192, 4 layers)", "fwd_batch": Bf, "fwd_ms": fwd_ms,
-                  "fwd_graphs_per_s": Bf / fwd_ms * 1e3, "cnf_launches_per_forward": launches, "sampling_batch": Bi, "sampling_ms": inv_ms,
-                  "sampling_graphs_per_s": Bi / inv_ms * 1e3}))
+out = {"config": "GraphCNF Zinc250k shape (N=38, flows 4/6/6, hidden 384/192, 4 layers)", "fwd_batch": Bf, "fwd_ms": fwd_ms,
+       "fwd_graphs_per_s": Bf / fwd_ms * 1e3, "cnf_launches_per_forward": launches, "sampling_batch": Bi, "sampling_ms": inv_ms,
+       "sampling_graphs_per_s": Bi / inv_ms * 1e3}
+if args.train:
+    model.train()
+    params_ = [p_ for p_ in model.parameters() if p_.requires_grad]
+
+    def step():
+        for p_ in params_:
+            p_.grad = None
+        zt, lt = model(xc[:Bf], adjacency=ac[:Bf], length=lc[:Bf])
+        (-(lt.mean())).backward()
+    step()
+    n0 = ops.launch_count()
+    step()
+    out["cnf_launches_per_train_step"] = ops.launch_count() - n0
+    out["train_step_ms"] = timed(step, max(2, args.reps // 2))
+    out["train_graphs_per_s"] = Bf / out["train_step_ms"] * 1e3
+    model.eval()
+print(json.dumps(out))
 if args.cprofile:
     import cProfile
     import pstats
