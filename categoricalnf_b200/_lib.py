@@ -383,8 +383,13 @@ def load():
     return lib
 
 
+_entry = {}      # symbol -> bound foreign function (one dict lookup per launch instead of a CDLL attribute walk)
+
+
 def call(name, args, stream):
-    lib = load()
-    rc = getattr(lib, name)(C.byref(args), vp(stream))
+    fn = _entry.get(name)
+    if fn is None:
+        fn = _entry[name] = getattr(load(), name)
+    rc = fn(C.byref(args), stream)
     if rc != 0:
-        raise CnfError(name, rc, lib.cnf_last_error_string().decode("utf-8", "replace"))
+        raise CnfError(name, rc, load().cnf_last_error_string().decode("utf-8", "replace"))

@@ -430,6 +430,7 @@ class Edge2NodeQKVAttnLayer(_EdgeLayerBase):
         self.edge_val_layer = TCLinear(hidden_size_edges, width)
         self.edge_adj_layer = TCLinear(hidden_size_edges, self.num_heads)
         self.output_projection = TCLinear(width + self.hidden_size_nodes, self.hidden_size_nodes)
+        self.__dict__["_pair"] = _FusedPair()
         self.skip_layer = GNNSkipConnection(hidden_size_nodes, config=skip_config, input_size=self.hidden_size_nodes, dp_rate=dp_rate)
         self.dropout = nn.Dropout(dp_rate)
         self.act_fn = act_fn()
@@ -443,8 +444,13 @@ class Edge2NodeQKVAttnLayer(_EdgeLayerBase):
         edge_in = _layernorm(edge_rows, self.edge_normalization)
         qkv = _linear(self.dropout(node_in), self.node_query_key_val_layer).reshape(B * N, 3 * width)
         q, k, v = qkv[:, :width], qkv[:, width:2 * width], qkv[:, 2 * width:]
-        edge_val = _linear(edge_in, self.edge_val_layer)
-        edge_adj = _linear(edge_in, self.edge_adj_layer)
+        if _grad_mode(edge_in, self.edge_val_layer.weight, self.edge_adj_layer.weight):
+            edge_val = _linear(edge_in, self.edge_val_layer)
+            edge_adj = _linear(edge_in, self.edge_adj_layer)
+        else:   # both edge projections read the same rows: one GEMM over the stacked weights, consumers take column slices
+            w, b = self._pair.get(self.edge_val_layer, self.edge_adj_layer)
+            ev = ops.linear(edge_in, w, b, precision=PRECISION)
+            edge_val, edge_adj = ev[:, :width], ev[:, width:width + H]
         if _grad_mode(qkv, edge_val, edge_adj):
             cfg = dict(N=N, H=H, Dh=self.hidden_size_per_head, mode=1, off_q=0, off_k=width, off_val=2 * width,
                        scale=self.dot_prod_scaling)
@@ -471,6 +477,7 @@ class Edge2NodeAttnLayer(_EdgeLayerBase):
         self.node_feat_layer = TCLinear(hidden_size_nodes, self.hidden_size_output * 2)
         self.edge_feat_layer = TCLinear(hidden_size_edges, self.hidden_size_output)
         self.edge_logits_layer = TCLinear(hidden_size_edges, self.num_heads)
+        self.__dict__["_pair"] = _FusedPair()
         self.skip_layer = GNNSkipConnection(hidden_size_nodes, config=skip_config, input_size=self.hidden_size_output)
         self.dropout = nn.Dropout(dp_rate)
         self.act_fn = act_fn()
@@ -483,8 +490,13 @@ class Edge2NodeAttnLayer(_EdgeLayerBase):
         node_new = _linear(_layernorm(node_feat, self.node_normalization), self.node_feat_layer).reshape(B * N, 2 * HO)
         node_self, node_ctx = node_new[:, :HO], node_new[:, HO:]
         edge_in = _layernorm(edge_rows, self.edge_normalization)
-        edge_new = _linear(edge_in, self.edge_feat_layer)
-        edge_logits = _linear(edge_in, self.edge_logits_layer)
+        if _grad_mode(edge_in, self.edge_feat_layer.weight, self.edge_logits_layer.weight):
+            edge_new = _linear(edge_in, self.edge_feat_layer)
+            edge_logits = _linear(edge_in, self.edge_logits_layer)
+        else:   # one GEMM over the stacked weights of the two edge projections
+            w, b = self._pair.get(self.edge_feat_layer, self.edge_logits_layer)
+            ev = ops.linear(edge_in, w, b, precision=PRECISION)
+            edge_new, edge_logits = ev[:, :HO], ev[:, HO:HO + self.num_heads]
         if _grad_mode(node_new, edge_new, edge_logits):
             cfg = dict(N=N, H=self.num_heads, Dh=self.hidden_size_per_head, mode=0, off_val=HO)
             att = GF.edge_aggregate(node_new, edge_new, edge_logits, ctx.rev, cfg)
