@@ -158,7 +158,7 @@ def workload_config(n_gpus, extra=None):
            "l2": "inputs larger than L2 (1.74 GB of coupling parameters per layer vs 126 MB L2); no flush needed",
            "value_leg": "coupling-net outputs given, resident in HBM", "e2e_leg": "drop-in FlowModel, stand-in Linear "
            "coupling nets (final projection fused with the mixture transform on tcgen05, 3xTF32), pinned host tokens -> H2D "
-           "(double-buffered on a copy stream), per-sample log-likelihood -> D2H (host reads step i-1 while step i runs)"}
+           "(double-buffered on a copy stream), per-sample log-likelihood + kernel status word -> D2H (host reads step i-1 while step i runs)"}
     if extra:
         cfg.update(extra)
     return cfg
@@ -245,6 +245,14 @@ def run_gpu(args, rank, local_rank, world):
             dev_tokens[j].copy_(host_tokens[j], non_blocking=True)
             ready[j].record(copy_stream)
 
+    status_dev = ops.status_word(dev)
+    host_status = [torch.zeros(1, dtype=torch.int32).pin_memory() for _ in range(2)]
+
+    def consume(j):
+        result[j].synchronize()
+        if int(host_status[j][0]) != 0:
+            ops.check_status(dev, "bench e2e leg")      # raises like the reference's per-layer asserts would have
+
     def e2e_step(i, last):
         j = i % 2
         cur = torch.cuda.current_stream()
@@ -252,7 +260,9 @@ def run_gpu(args, rank, local_rank, world):
             prefetch(i + 1)
         with torch.no_grad():
             cur.wait_event(ready[j])
-            z, ldj = model(dev_tokens[j])
+            # numerical-health word of the kernels (NaN / CDF-range flags): instead of one blocking read per forward
+            # (check_nan=True) it travels to the host with the step's result and is examined when that result is consumed
+            z, ldj = model(dev_tokens[j], check_nan=False)
             consumed[j].record(cur)
             logp, _ = ops.logistic_logprob(z)
             ll = ldj + logp
@@ -261,11 +271,12 @@ def run_gpu(args, rank, local_rank, world):
                 acc[1] = float(B)
                 dist.all_reduce(acc)
             host_ll[j].copy_(ll, non_blocking=True)
+            host_status[j].copy_(status_dev, non_blocking=True)
             result[j].record(cur)
         if i > 0:
-            result[(i - 1) % 2].synchronize()     # the host consumes the previous step's log-likelihoods
+            consume((i - 1) % 2)                  # the host consumes the previous step's log-likelihoods
         if last:
-            result[j].synchronize()
+            consume(j)
 
     def e2e_run(n):
         for j in range(2):
@@ -282,6 +293,7 @@ def run_gpu(args, rank, local_rank, world):
     e1.record()
     barrier()
     e2e_ms_total = e0.elapsed_time(e1)
+    ops.check_status(dev, "bench e2e leg")
     clk = clocks.stop() if rank == 0 else None
 
     # ---- max over ranks ---------------------------------------------------------------------------
@@ -302,7 +314,7 @@ def run_gpu(args, rank, local_rank, world):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": workload_config(world),
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * S * 8, "d2h_bytes_per_step": B * 4,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * S * 8, "d2h_bytes_per_step": B * 4 + 4,
                     "ms_per_step": e2e_ms_total / args.steps},
             "gpu_launches": launches,
             "roofline": {"kernel": "mixcdf_pipe_kernel<8,8,fwd> (cnf_mixcdf_fwd)", "bound": "hbm", "achieved": achieved,
