@@ -5,6 +5,8 @@
 incoming ldj (App. B #1); the parameter split + transform + ldj reduction run as one
 ``cnf_mixcdf_fwd`` / ``cnf_mixcdf_inv`` launch (csrc/mixcdf.cu).
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -96,7 +98,7 @@ class MixtureCDFCoupling(CouplingLayer):
     # The fused projection kernel can also run the next block's ActNorm + 1x1 conv in its epilogue, but the extra
     # shared memory costs it a pipeline stage (measured slower than ActNorm + conv as one separate pass), so the
     # container uses cnf_invconv_apply with the ActNorm prologue instead unless this is set.
-    fuse_next_in_projection_kernel = False
+    fuse_next_in_projection_kernel = os.environ.get("CNF_B200_FUSE_NEXT_IN_PROJECTION", "0") not in ("", "0")
 
     def _projection_split(self, z):
         """(features_fn, linear) when the final projection of ``self.nn`` can be fused for ``z``, else None."""
