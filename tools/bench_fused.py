@@ -15,10 +15,11 @@ B, S, C, K = 4096, 256, 16, 8
 PN = 2 + 3 * K
 z = torch.randn(B, S, C, device=dev)
 feats = torch.randn(B, S, a.H, device=dev)
-w = torch.randn(C * PN, a.H, device=dev) * (0.5 / a.H ** 0.5)
-b = torch.randn(C * PN, device=dev) * 0.1
+w = torch.nn.Parameter(torch.randn(C * PN, a.H, device=dev) * (0.5 / a.H ** 0.5))      # parameters: folded-bias path
+b = torch.nn.Parameter(torch.randn(C * PN, device=dev) * 0.1)
 mask_c = [1.0] * 8 + [0.0] * 8
 fn = lambda: ops.linear_mixcdf(z, feats, w, b, K, mask_c=mask_c, precision=a.prec, reverse=a.inv)
+torch.set_grad_enabled(False)
 for _ in range(3):
     fn()
 torch.cuda.synchronize()
