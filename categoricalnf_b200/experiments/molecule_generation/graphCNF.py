@@ -154,8 +154,13 @@ class GraphCNF(FlowModel):
         ldj_per_layer = []
         if not reverse:
             z_nodes, ldj = self._step1_forward(z_nodes, adjacency, ldj, False, ldj_per_layer, **kwargs)
-            z_edges_disc, x_indices, mask_valid = adjacency2pairs(adjacency=adjacency, length=length)
-            kwargs["mask_valid"] = mask_valid * (z_edges_disc != 0).to(mask_valid.dtype)
+            pre = kwargs.pop("cnf_edge_masks", None)     # precomputed by graphed.GraphedLogLikelihood (static buffers)
+            if pre is None:
+                z_edges_disc, x_indices, mask_valid = adjacency2pairs(adjacency=adjacency, length=length)
+                mask_bond = mask_valid * (z_edges_disc != 0).to(mask_valid.dtype)
+            else:
+                z_edges_disc, x_indices, mask_valid, mask_bond = pre
+            kwargs["mask_valid"] = mask_bond
             kwargs["x_indices"] = x_indices
             binary_adjacency = (adjacency > 0).long()
             z_nodes, z_edges, ldj = self._step2_forward(z_nodes, z_edges_disc, ldj, False, ldj_per_layer,

@@ -330,6 +330,47 @@ class PairContext:
         return out.index_copy(0, self.flat_indices, edge_rows).reshape(self.B, self.P, -1)
 
 
+class StaticPairContext(PairContext):
+    """A PairContext over preallocated buffers with a FIXED number of compact rows, for CUDA-graph replay: ``load`` refills the
+    buffers for a new ``mask_valid`` (the one host synchronisation, outside the graph); rows beyond the real count repeat
+    the first valid pair - they compute the same values as that pair's real row, ``expand`` writes them to the same place
+    and the edge -> node aggregation never sees them (it walks ``rev``)."""
+
+    def __init__(self, x_indices, batch_size, num_nodes, rows, device):
+        P = x_indices[0].numel()
+        self.B, self.P, self.N, self.R = batch_size, P, num_nodes, int(rows)
+        self.x_indices = (x_indices[0].contiguous(), x_indices[1].contiguous())
+        self.flat_indices = torch.zeros(self.R, dtype=torch.int64, device=device)
+        self.rev = torch.zeros(batch_size, P, dtype=torch.int64, device=device)
+        self.node1 = torch.zeros(self.R, dtype=torch.int64, device=device)
+        self.node2 = torch.zeros(self.R, dtype=torch.int64, device=device)
+
+    @staticmethod
+    def count(mask_valid):
+        return int((mask_valid == 1.0).sum().item())
+
+    def load(self, mask_valid):
+        flat_mask = (mask_valid.reshape(-1) == 1.0)
+        idx = torch.nonzero(flat_mask).reshape(-1)
+        r = int(idx.numel())
+        if r == 0 or r > self.R:
+            return False
+        self.flat_indices[:r] = idx
+        if r < self.R:
+            self.flat_indices[r:] = idx[0]
+        fm = flat_mask.long()
+        self.rev.copy_((fm * fm.cumsum(dim=0)).reshape(self.B, self.P))
+        graph = torch.div(self.flat_indices, self.P, rounding_mode="floor")
+        pair = self.flat_indices - graph * self.P
+        self.node1.copy_(graph * self.N + self.x_indices[0][pair])
+        self.node2.copy_(graph * self.N + self.x_indices[1][pair])
+        return True
+
+    def attach(self, mask_valid):
+        """Make ``PairContext.of(x_indices, mask_valid, N)`` return this context for the tensor's current version."""
+        mask_valid._cnf_pair_ctx = ((mask_valid._version, self.N), self)
+
+
 def _edge_to_node_dense(ctx, node_val, edge_val, edge_logit, H, mode, q=None, k=None, scale=1.0):
     """``cnf_edge_aggregate`` as differentiable torch algebra (every valid pair sends one message in each direction) - an
     independent check of the backward kernel (tests/test_gpu_graph.py); not on any product path."""

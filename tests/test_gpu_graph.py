@@ -369,3 +369,33 @@ def test_graphcnf_zinc_shape_properties():
         valid = (torch.arange(N, device="cuda")[None, :] < lc[:, None])
         assert bool((adj_smp * (~(valid[:, :, None] & valid[:, None, :])).long() == 0).all())
         assert torch.isfinite(ldj_smp).all()
+
+
+def test_graphcnf_cuda_graph_replay_matches_eager():
+    """GraphedLogLikelihood: the forward pass captured once per (batch shape, padded pair-row counts) and replayed - same
+    z and log-likelihood as the eager pass on the same noise, for the batch it was captured on, for other batches of the
+    same bucket (replay only) and for a batch that needs a new capture; golden parity through the replay as well."""
+    from categoricalnf_b200.experiments.molecule_generation import GraphedLogLikelihood
+    g = load_golden("graphcnf_small")
+    model = _build_graphcnf(g.N, sd=_sd(g))
+    graphed = GraphedLogLikelihood(model, bucket=16)
+    x, adj, length = g.x.cuda(), g.adjacency.cuda(), g.length.cuda()
+    noise = dict(u_noise=g.u_nodes.cuda(), u_noise_edges=g.u_edges.cuda(), u_noise_virtual=g.u_virtual.cuda())
+    with torch.no_grad():
+        z, ldj = graphed(x, adj, length, **noise)
+        assert_close(z, g.z, what="z nodes (graph replay vs reference golden)")
+        assert_close(ldj, g.ldj, rtol=1e-4, atol=5e-4, what="ldj (graph replay vs reference golden)")
+        gen = torch.Generator().manual_seed(5)
+        for trial in range(4):
+            adj2, len2 = _graphs(gen, x.shape[0], g.N, 3, p=0.25 + 0.1 * (trial % 2))
+            x2 = torch.randint(0, 5, x.shape, generator=gen) * (torch.arange(g.N)[None, :] < len2[:, None]).long()
+            P = g.N * (g.N - 1) // 2
+            nz = dict(u_noise=torch.rand(x.shape[0], g.N, 6, generator=gen).cuda(), u_noise_edges=torch.rand(x.shape[0], P, 2, generator=gen).cuda(),
+                      u_noise_virtual=torch.rand(x.shape[0], P, 2, generator=gen).cuda())
+            z_e, ldj_e = model(x2.cuda(), adjacency=adj2.cuda(), length=len2.cuda(), **nz)
+            z_g, ldj_g = graphed(x2.cuda(), adj2.cuda(), len2.cuda(), **nz)
+            assert_close(z_g, z_e, rtol=1e-5, atol=1e-6, what="z (trial %d)" % trial)
+            assert_close(ldj_g, ldj_e, rtol=1e-5, atol=1e-4, what="ldj (trial %d)" % trial)
+        z_r, ldj_r = graphed(x, adj, length)          # internal noise: finite, different draw
+        assert torch.isfinite(ldj_r).all() and not torch.equal(ldj_r, ldj)
+    assert 1 <= graphed.captures <= 5

@@ -106,6 +106,15 @@ with torch.no_grad():
 out = {"config": "GraphCNF Zinc250k shape (N=38, flows 4/6/6, hidden 384/192, 4 layers)", "fwd_batch": Bf, "fwd_ms": fwd_ms,
        "fwd_graphs_per_s": Bf / fwd_ms * 1e3, "cnf_launches_per_forward": launches, "sampling_batch": Bi, "sampling_ms": inv_ms,
        "sampling_graphs_per_s": Bi / inv_ms * 1e3}
+if True:
+    from categoricalnf_b200.experiments.molecule_generation import GraphedLogLikelihood
+    graphed = GraphedLogLikelihood(model)
+    gfwd = lambda: graphed(xc[:Bf], ac[:Bf], lc[:Bf])
+    with torch.no_grad():
+        gfwd()
+        out["graphed_fwd_ms"] = timed(gfwd, args.reps * 2)
+    out["graphed_fwd_graphs_per_s"] = Bf / out["graphed_fwd_ms"] * 1e3
+    out["graph_captures"] = graphed.captures
 if args.train:
     model.train()
     params_ = [p_ for p_ in model.parameters() if p_.requires_grad]
