@@ -11,7 +11,12 @@ the host cannot issue them as fast as the GPU retires them.  ``GraphedLogLikelih
 * the noise is drawn by torch's generator outside the graph and handed to the encodings through their ``u_noise`` hooks, so
   replays do not reuse the Philox offsets that a capture would have frozen.
 
-Results are those of ``model(x, adjacency=..., length=..., u_noise=...)`` on the same noise (padding rows only duplicate work).
+Results are those of ``model(x, adjacency=..., length=..., u_noise=...)`` on the same noise (padding rows carry zeros, land in a
+spare slot and receive zero gradients).
+
+``GraphedTrainingStep`` does the same for one training step - forward in training mode, loss, ``loss.backward()`` through the
+backward kernels - and leaves the gradients in ``p.grad`` (static tensors that every replay rewrites), ready for the
+optimiser of the caller's training loop (general/train.py:148-160 of the reference).
 """
 import torch
 
@@ -59,11 +64,9 @@ class GraphedLogLikelihood:
                           u_noise_edges=self.u_edges, u_noise_virtual=self.u_virtual,
                           cnf_edge_masks=(self.z_edges_disc, x_indices, self.mask_all, self.mask_bond))
 
-    @torch.no_grad()
-    def __call__(self, x, adjacency, length, u_noise=None, u_noise_edges=None, u_noise_virtual=None):
-        """-> (z_nodes [B,N,D], ldj [B]) like ``model(x, adjacency=adjacency, length=length)`` in eval mode."""
-        if self.model.training:
-            raise RuntimeError("GraphedLogLikelihood replays the evaluation pass: call model.eval() first")
+    def _load(self, x, adjacency, length, u_noise, u_noise_edges, u_noise_virtual):
+        """Inputs -> static buffers, pair contexts for this batch.  Returns (x_indices, key) with key = None when a mask has
+        no valid pair (nothing to pad with: the caller runs the plain pass)."""
         if self.shape != (x.shape[0], x.shape[1], x.device):
             self._setup(x, adjacency, length)
         self.x.copy_(x)
@@ -79,8 +82,8 @@ class GraphedLogLikelihood:
             else:
                 buf.copy_(given.reshape(buf.shape))
         r_bond, r_all = StaticPairContext.count(self.mask_bond), StaticPairContext.count(self.mask_all)
-        if r_bond == 0 or r_all == 0:      # nothing to pad with: plain pass
-            return self._run(x_indices)
+        if r_bond == 0 or r_all == 0:
+            return x_indices, None
         up = lambda r: -(-r // self.bucket) * self.bucket
         key = (up(r_bond), up(r_all))
         c_bond, c_all = self._context("bond", key[0], x_indices), self._context("all", key[1], x_indices)
@@ -88,6 +91,16 @@ class GraphedLogLikelihood:
         c_all.load(self.mask_all)
         c_bond.attach(self.mask_bond)
         c_all.attach(self.mask_all)
+        return x_indices, key
+
+    @torch.no_grad()
+    def __call__(self, x, adjacency, length, u_noise=None, u_noise_edges=None, u_noise_virtual=None):
+        """-> (z_nodes [B,N,D], ldj [B]) like ``model(x, adjacency=adjacency, length=length)`` in eval mode."""
+        if self.model.training:
+            raise RuntimeError("GraphedLogLikelihood replays the evaluation pass: call model.eval() first")
+        x_indices, key = self._load(x, adjacency, length, u_noise, u_noise_edges, u_noise_virtual)
+        if key is None:      # nothing to pad with: plain pass
+            return self._run(x_indices)
         hit = self.graphs.get(key)
         if hit is None:
             # warm-up on a side stream (fills every host-side cache and cudaFuncSetAttribute outside the capture), then capture
@@ -105,3 +118,57 @@ class GraphedLogLikelihood:
         g, z, ldj = hit
         g.replay()
         return z.clone(), ldj.clone()
+
+
+class GraphedTrainingStep(GraphedLogLikelihood):
+    """One training step of GraphCNF replayed from a CUDA graph: ``loss = loss_fn(z, ldj, length)`` (default: the mean
+    negative log-likelihood per node, the reference's objective up to its bits-per-dimension scale) and ``loss.backward()``.
+    Calling it returns the loss (a 0-d tensor) and leaves the gradient of every parameter in ``p.grad``; the caller then runs
+    its optimiser.  Dropout must be 0 (the flows' default) and the data-dependent initialisation done.  No autograd graph
+    of an eager pass over the same parameters may be alive at the first call (its gradient accumulators are bound to the
+    stream it ran on, and the capture may not touch another stream)."""
+
+    def __init__(self, model, loss_fn=None, bucket=2048):
+        super().__init__(model, bucket)
+        self.loss_fn = loss_fn or (lambda z, ldj, length: -(ldj / length.to(ldj.dtype)).mean())
+        self.params = [p for p in model.parameters() if p.requires_grad]
+
+    def _step(self, x_indices):
+        z, ldj = self._run(x_indices)
+        loss = self.loss_fn(z, ldj, self.length)
+        loss.backward()
+        return loss
+
+    def __call__(self, x, adjacency, length, u_noise=None, u_noise_edges=None, u_noise_virtual=None):
+        if not self.model.training:
+            raise RuntimeError("GraphedTrainingStep replays the training pass: call model.train() first")
+        with torch.no_grad():
+            x_indices, key = self._load(x, adjacency, length, u_noise, u_noise_edges, u_noise_virtual)
+        if key is None:
+            for p in self.params:
+                p.grad = None
+            return self._step(x_indices).detach()
+        hit = self.graphs.get(key)
+        if hit is None:
+            side = torch.cuda.Stream(device=x.device)
+            side.wait_stream(torch.cuda.current_stream(x.device))
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    for p in self.params:
+                        p.grad = None
+                    self._step(x_indices)
+            torch.cuda.current_stream(x.device).wait_stream(side)
+            torch.cuda.synchronize(x.device)
+            for p in self.params:
+                p.grad = None
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                loss = self._step(x_indices)
+            grads = [p.grad for p in self.params]      # allocated in the graph's pool: every replay rewrites them
+            hit = self.graphs[key] = (g, loss, grads)
+            self.captures += 1
+        g, loss, grads = hit
+        g.replay()
+        for p, gr in zip(self.params, grads):
+            p.grad = gr
+        return loss.detach().clone()

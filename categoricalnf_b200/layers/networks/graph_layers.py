@@ -332,15 +332,18 @@ class PairContext:
 
 class StaticPairContext(PairContext):
     """A PairContext over preallocated buffers with a FIXED number of compact rows, for CUDA-graph replay: ``load`` refills the
-    buffers for a new ``mask_valid`` (the one host synchronisation, outside the graph); rows beyond the real count repeat
-    the first valid pair - they compute the same values as that pair's real row, ``expand`` writes them to the same place
-    and the edge -> node aggregation never sees them (it walks ``rev``)."""
+    buffers for a new ``mask_valid`` (the one host synchronisation, outside the graph).  Rows beyond the real count are
+    padding: they are gathered from / scattered to an extra all-zero slot behind the last pair (``scatter_indices``), so they
+    carry zeros in, their results go nowhere and they receive zero gradients; for the kernels that look a pair's nodes up
+    (``flat_indices``, ``node1/2``) they alias the first valid pair, and the edge -> node aggregation never sees them (it
+    walks ``rev``)."""
 
     def __init__(self, x_indices, batch_size, num_nodes, rows, device):
         P = x_indices[0].numel()
         self.B, self.P, self.N, self.R = batch_size, P, num_nodes, int(rows)
         self.x_indices = (x_indices[0].contiguous(), x_indices[1].contiguous())
         self.flat_indices = torch.zeros(self.R, dtype=torch.int64, device=device)
+        self.scatter_indices = torch.zeros(self.R, dtype=torch.int64, device=device)
         self.rev = torch.zeros(batch_size, P, dtype=torch.int64, device=device)
         self.node1 = torch.zeros(self.R, dtype=torch.int64, device=device)
         self.node2 = torch.zeros(self.R, dtype=torch.int64, device=device)
@@ -356,8 +359,10 @@ class StaticPairContext(PairContext):
         if r == 0 or r > self.R:
             return False
         self.flat_indices[:r] = idx
+        self.scatter_indices[:r] = idx
         if r < self.R:
             self.flat_indices[r:] = idx[0]
+            self.scatter_indices[r:] = self.B * self.P
         fm = flat_mask.long()
         self.rev.copy_((fm * fm.cumsum(dim=0)).reshape(self.B, self.P))
         graph = torch.div(self.flat_indices, self.P, rounding_mode="floor")
@@ -369,6 +374,14 @@ class StaticPairContext(PairContext):
     def attach(self, mask_valid):
         """Make ``PairContext.of(x_indices, mask_valid, N)`` return this context for the tensor's current version."""
         mask_valid._cnf_pair_ctx = ((mask_valid._version, self.N), self)
+
+    def compact(self, edge_feat):
+        flat = edge_feat.reshape(self.B * self.P, -1)
+        return F.pad(flat, (0, 0, 0, 1)).index_select(0, self.scatter_indices)
+
+    def expand(self, edge_rows):
+        out = edge_rows.new_zeros(self.B * self.P + 1, edge_rows.shape[-1])
+        return out.index_copy(0, self.scatter_indices, edge_rows)[:self.B * self.P].reshape(self.B, self.P, -1)
 
 
 def _edge_to_node_dense(ctx, node_val, edge_val, edge_logit, H, mode, q=None, k=None, scale=1.0):

@@ -251,3 +251,43 @@ def test_graphcnf_training_step_gradients_vs_reference():
         assert_close(p.grad / scale, ref[name] / scale, rtol=2e-3, atol=5e-4, what="grad " + name)
         checked += 1
     assert checked == len(ref)
+
+
+def test_graphcnf_training_step_cuda_graph_replay():
+    """GraphedTrainingStep: forward + backward replayed from a CUDA graph leave the same loss and parameter gradients as the
+    eager training step on the same noise - on the capture batch and on later batches that only replay."""
+    from test_gpu_graph import _build_graphcnf, _graphs, _sd
+    from categoricalnf_b200.experiments.molecule_generation import GraphedTrainingStep
+    g = load_golden("graphcnf_small")
+    model = _build_graphcnf(g.N, sd=_sd(g)).train()
+    loss_fn = lambda z, ldj, length: -(ldj / length.to(ldj.dtype)).mean() + 0.01 * (z ** 2).mean()
+    step = GraphedTrainingStep(model, loss_fn=loss_fn, bucket=16)
+    gen = torch.Generator().manual_seed(9)
+    B, N = g.x.shape
+    P = N * (N - 1) // 2
+    params = [p for p in model.parameters() if p.requires_grad]
+    for trial in range(3):
+        adj, length = _graphs(gen, B, N, 3, p=0.3)
+        x = torch.randint(0, 5, (B, N), generator=gen) * (torch.arange(N)[None, :] < length[:, None]).long()
+        nz = dict(u_noise=torch.rand(B, N, 6, generator=gen).cuda(), u_noise_edges=torch.rand(B, P, 2, generator=gen).cuda(),
+                  u_noise_virtual=torch.rand(B, P, 2, generator=gen).cuda())
+        for p in params:
+            p.grad = None
+        z, ldj = model(x.cuda(), adjacency=adj.cuda(), length=length.cuda(), **nz)
+        loss_e = loss_fn(z, ldj, length.cuda())
+        loss_e.backward()
+        ref = [None if p.grad is None else p.grad.clone() for p in params]
+        loss_ref = loss_e.detach().clone()
+        # autograd graphs of the eager pass keep the parameters' gradient accumulators bound to the stream they were made on
+        # (the default stream); none of them may be alive when the step is captured on the capture stream
+        del z, ldj, loss_e
+        loss_g = step(x.cuda(), adj.cuda(), length.cuda(), **nz)
+        assert_close(loss_g, loss_ref, rtol=1e-5, atol=1e-5, what="loss (trial %d)" % trial)
+        scale = max(float(r.abs().max()) for r in ref if r is not None)
+        for p, r in zip(params, ref):
+            if r is None:
+                assert p.grad is None or float(p.grad.abs().max()) == 0.0
+                continue
+            # the scatter reductions of the backward kernels sum in a different order from run to run
+            assert_close(p.grad / scale, r / scale, rtol=1e-3, atol=1e-5, what="grad (trial %d)" % trial)
+    assert 1 <= step.captures <= 3

@@ -130,6 +130,12 @@ if args.train:
     out["cnf_launches_per_train_step"] = ops.launch_count() - n0
     out["train_step_ms"] = timed(step, max(2, args.reps // 2))
     out["train_graphs_per_s"] = Bf / out["train_step_ms"] * 1e3
+    from categoricalnf_b200.experiments.molecule_generation import GraphedTrainingStep
+    gstep_ = GraphedTrainingStep(model)
+    gstep = lambda: gstep_(xc[:Bf], ac[:Bf], lc[:Bf])
+    gstep()
+    out["graphed_train_step_ms"] = timed(gstep, max(3, args.reps))
+    out["graphed_train_graphs_per_s"] = Bf / out["graphed_train_step_ms"] * 1e3
     model.eval()
 print(json.dumps(out))
 if args.cprofile:
