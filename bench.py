@@ -156,7 +156,7 @@ def workload_config(n_gpus, extra=None):
            "batch_per_gpu": W.LM["B"], "global_batch": W.LM["B"] * n_gpus, "seq_len": W.LM["S"], "d": W.LM["D"],
            "mixtures": W.LM["K"], "vocab": W.LM["V"], "blocks": W.LM["blocks"], "parallelism": "batch-sharded x%d" % n_gpus,
            "l2": "inputs larger than L2 (1.74 GB of coupling parameters per layer vs 126 MB L2); no flush needed",
-           "value_leg": "coupling-net outputs given, resident in HBM", "e2e_leg": "drop-in FlowModel, stand-in Linear "
+           "value_leg": "coupling-net outputs given, resident in HBM", "e2e_leg": "drop-in FlowModel replayed from a CUDA graph (GraphedFlowForward), stand-in Linear "
            "coupling nets (final projection fused with the mixture transform on tcgen05, 3xTF32), pinned host tokens -> H2D "
            "(double-buffered on a copy stream), per-sample log-likelihood + kernel status word -> D2H (host reads step i-1 while step i runs)"}
     if extra:
@@ -245,6 +245,10 @@ def run_gpu(args, rank, local_rank, world):
             dev_tokens[j].copy_(host_tokens[j], non_blocking=True)
             ready[j].record(copy_stream)
 
+    graphed = None
+    if not args.eager_e2e:
+        from categoricalnf_b200.layers.flows import GraphedFlowForward
+        graphed = GraphedFlowForward(model, log_prior=lambda z, pad: ops.logistic_logprob(z, pad=pad)[0])
     status_dev = ops.status_word(dev)
     host_status = [torch.zeros(1, dtype=torch.int32).pin_memory() for _ in range(2)]
 
@@ -262,10 +266,15 @@ def run_gpu(args, rank, local_rank, world):
             cur.wait_event(ready[j])
             # numerical-health word of the kernels (NaN / CDF-range flags): instead of one blocking read per forward
             # (check_nan=True) it travels to the host with the step's result and is examined when that result is consumed
-            z, ldj = model(dev_tokens[j], check_nan=False)
-            consumed[j].record(cur)
-            logp, _ = ops.logistic_logprob(z)
-            ll = ldj + logp
+            if graphed is not None:
+                # whole forward + prior log-likelihood replayed from one CUDA graph (tokens copied into its static buffer)
+                z, ldj, ll = graphed(dev_tokens[j])
+                consumed[j].record(cur)
+            else:
+                z, ldj = model(dev_tokens[j], check_nan=False)
+                consumed[j].record(cur)
+                logp, _ = ops.logistic_logprob(z)
+                ll = ldj + logp
             if distributed:
                 acc[0] = ll.sum(dtype=torch.float64)
                 acc[1] = float(B)
@@ -385,6 +394,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--eager-e2e", action="store_true", help="e2e leg launches kernel by kernel instead of replaying a CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank, local_rank, world = env_int("RANK", 0), env_int("LOCAL_RANK", 0), env_int("WORLD_SIZE", 1)

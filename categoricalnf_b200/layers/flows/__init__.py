@@ -1,5 +1,6 @@
 from .flow_layer import FlowLayer
 from .flow_model import FlowModel
+from .graphed import GraphedFlowForward
 from .coupling_layer import CouplingLayer
 from .mixture_cdf_layer import MixtureCDFCoupling
 from .autoregressive_coupling import AutoregressiveMixtureCDFCoupling
@@ -9,6 +10,6 @@ from .node_edge_coupling import NodeEdgeCoupling, NodeEdgeFlowWrapper
 from .sigmoid_layer import SigmoidFlow
 from .distributions import LogisticDistribution, PriorDistribution, create_prior_distribution
 
-__all__ = ["FlowLayer", "FlowModel", "CouplingLayer", "MixtureCDFCoupling", "AutoregressiveMixtureCDFCoupling",
+__all__ = ["FlowLayer", "FlowModel", "GraphedFlowForward", "CouplingLayer", "MixtureCDFCoupling", "AutoregressiveMixtureCDFCoupling",
            "ActNormFlow", "ExtActNormFlow", "SigmoidFlow", "InvertibleConv", "NodeEdgeCoupling", "NodeEdgeFlowWrapper", "LogisticDistribution", "PriorDistribution",
            "create_prior_distribution"]
