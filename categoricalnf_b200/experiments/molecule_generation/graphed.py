@@ -111,7 +111,7 @@ class GraphedLogLikelihood:
             torch.cuda.current_stream(x.device).wait_stream(side)
             torch.cuda.synchronize(x.device)
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):   # other threads (NCCL watchdog) may touch CUDA meanwhile
                 z, ldj = self._run(x_indices)
             hit = self.graphs[key] = (g, z, ldj)
             self.captures += 1
@@ -162,7 +162,7 @@ class GraphedTrainingStep(GraphedLogLikelihood):
             for p in self.params:
                 p.grad = None
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):   # other threads (NCCL watchdog) may touch CUDA meanwhile
                 loss = self._step(x_indices)
             grads = [p.grad for p in self.params]      # allocated in the graph's pool: every replay rewrites them
             hit = self.graphs[key] = (g, loss, grads)

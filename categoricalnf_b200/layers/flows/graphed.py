@@ -64,7 +64,7 @@ class GraphedFlowForward:
             torch.cuda.current_stream(dev).wait_stream(side)
             torch.cuda.synchronize(dev)
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):   # other threads (NCCL watchdog) may touch CUDA meanwhile
                 st["out"] = self._run(st)
             st["graph"] = g
             self.graphs[key] = st
