@@ -54,3 +54,38 @@ def test_pair_helpers_match_definition():
     assert torch.equal(M.pairs2adjacency(N, pairs, length, (x1, x2)), adj)
     mv, idx = M.get_adjacency_indices(N, length)
     assert torch.equal(mv, mask_valid) and torch.equal(idx[0], x1)
+
+
+def test_static_pair_context_padding_semantics():
+    """Host logic of the CUDA-graph wrappers (CPU tensors): a StaticPairContext with more rows than valid pairs compacts /
+    expands like the exact PairContext on its real rows, its padding rows read zeros, write nowhere and carry no gradient."""
+    import torch
+    from categoricalnf_b200.layers.networks.graph_layers import PairContext, StaticPairContext
+    from categoricalnf_b200.experiments.molecule_generation.mutils import pair_indices
+    gen = torch.Generator().manual_seed(0)
+    B, N, F = 3, 6, 4
+    x_indices = pair_indices(N, "cpu")
+    P = N * (N - 1) // 2
+    mask = (torch.rand(B, P, generator=gen) < 0.5).float()
+    mask[1] = 0
+    exact = PairContext(x_indices, mask, N)
+    padded = StaticPairContext(x_indices, B, N, exact.R + 5, "cpu")
+    assert StaticPairContext.count(mask) == exact.R and padded.load(mask)
+    assert not StaticPairContext(x_indices, B, N, exact.R - 1, "cpu").load(mask), "too few rows must be refused"
+    assert not padded.load(torch.zeros(B, P)), "no valid pair: nothing to pad with"
+    assert padded.load(mask)
+    feat = torch.randn(B, P, F, generator=gen, requires_grad=True)
+    rows = padded.compact(feat)
+    assert rows.shape == (exact.R + 5, F)
+    assert torch.equal(rows[:exact.R], exact.compact(feat)) and bool((rows[exact.R:] == 0).all())
+    assert torch.equal(padded.rev, exact.rev)
+    assert torch.equal(padded.node1[:exact.R], exact.node1) and torch.equal(padded.node2[:exact.R], exact.node2)
+    assert bool((padded.flat_indices[exact.R:] == exact.flat_indices[0]).all())       # kernels see a valid pair there
+    vals = torch.randn(exact.R + 5, F, generator=gen, requires_grad=True)
+    out = padded.expand(vals)
+    assert torch.equal(out, exact.expand(vals[:exact.R]))
+    (out.sum() + rows.sum()).backward()
+    assert bool((vals.grad[exact.R:] == 0).all()) and bool((vals.grad[:exact.R] == 1).all())
+    assert torch.equal(feat.grad, mask.unsqueeze(-1).expand(B, P, F))
+    padded.attach(mask)
+    assert PairContext.of(x_indices, mask, N) is padded
