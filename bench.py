@@ -156,7 +156,7 @@ def workload_config(n_gpus, extra=None):
            "batch_per_gpu": W.LM["B"], "global_batch": W.LM["B"] * n_gpus, "seq_len": W.LM["S"], "d": W.LM["D"],
            "mixtures": W.LM["K"], "vocab": W.LM["V"], "blocks": W.LM["blocks"], "parallelism": "batch-sharded x%d" % n_gpus,
            "l2": "inputs larger than L2 (1.74 GB of coupling parameters per layer vs 126 MB L2); no flush needed",
-           "value_leg": "coupling-net outputs given, resident in HBM", "e2e_leg": "drop-in FlowModel replayed from a CUDA graph (GraphedFlowForward), stand-in Linear "
+           "value_leg": "coupling-net outputs given, resident in HBM", "e2e_leg": "drop-in FlowModel (see e2e_mode), stand-in Linear "
            "coupling nets (final projection fused with the mixture transform on tcgen05, 3xTF32), pinned host tokens -> H2D "
            "(double-buffered on a copy stream), per-sample log-likelihood + kernel status word -> D2H (host reads step i-1 while step i runs)"}
     if extra:
@@ -249,6 +249,16 @@ def run_gpu(args, rank, local_rank, world):
     if not args.eager_e2e:
         from categoricalnf_b200.layers.flows import GraphedFlowForward
         graphed = GraphedFlowForward(model, log_prior=lambda z, pad: ops.logistic_logprob(z, pad=pad)[0])
+    if graphed is not None:
+        try:      # capture now; a box where the capture fails still gets an e2e number (launch by launch)
+            dev_tokens[0].copy_(host_tokens[0])
+            graphed(dev_tokens[0])
+            torch.cuda.synchronize()
+        except Exception as exc:      # noqa: BLE001
+            print("bench: CUDA-graph replay unavailable (%s: %s) - the e2e leg launches kernel by kernel" % (type(exc).__name__, exc),
+                  file=sys.stderr)
+            graphed = None
+    e2e_mode = "replayed from a CUDA graph (GraphedFlowForward)" if graphed is not None else "launched kernel by kernel"
     status_dev = ops.status_word(dev)
     host_status = [torch.zeros(1, dtype=torch.int32).pin_memory() for _ in range(2)]
 
@@ -322,7 +332,7 @@ def run_gpu(args, rank, local_rank, world):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": workload_config(world),
+            "data": "synthetic", "config": workload_config(world, extra={"e2e_mode": e2e_mode}),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * S * 8, "d2h_bytes_per_step": B * 4 + 4,
                     "ms_per_step": e2e_ms_total / args.steps},
             "gpu_launches": launches,
