@@ -20,6 +20,7 @@ optimiser of the caller's training loop (general/train.py:148-160 of the referen
 """
 import torch
 
+from ... import ops
 from ...layers.networks.graph_layers import StaticPairContext
 from .mutils import adjacency2pairs
 
@@ -32,6 +33,16 @@ class GraphedLogLikelihood:
         self.ctx = {}           # ("bond" | "all", rows) -> StaticPairContext
         self.shape = None
         self.captures = 0
+        self._tensors = list(model.parameters()) + list(model.buffers())
+        self._fingerprint = None
+
+    def _check_parameters(self):
+        """Evaluation graphs hold pointers to tensors derived from the parameters (built 1x1-conv matrices, fused / split
+        projection weights): drop them when the parameters changed (``ops.param_fingerprint``)."""
+        fp = ops.param_fingerprint(self._tensors)
+        if fp != self._fingerprint:
+            self.graphs.clear()
+            self._fingerprint = fp
 
     def _setup(self, x, adjacency, length):
         dev = x.device
@@ -98,6 +109,7 @@ class GraphedLogLikelihood:
         """-> (z_nodes [B,N,D], ldj [B]) like ``model(x, adjacency=adjacency, length=length)`` in eval mode."""
         if self.model.training:
             raise RuntimeError("GraphedLogLikelihood replays the evaluation pass: call model.eval() first")
+        self._check_parameters()
         x_indices, key = self._load(x, adjacency, length, u_noise, u_noise_edges, u_noise_virtual)
         if key is None:      # nothing to pad with: plain pass
             return self._run(x_indices)

@@ -78,12 +78,14 @@ class CouplingLayer(FlowLayer):
 
     @staticmethod
     def create_chess_mask(seq_len=2):
-        """[seq_len, 1]: ceil(seq_len/2) conditioning positions followed by transformed ones."""
+        """[seq_len, 1].  Upstream concatenates a ones and a zeros COLUMN and flattens the [n, 2] result row by row
+        (coupling_layer.py:115-120), which alternates conditioning / transformed positions: [1,0] for 2, [1,0,1,0] for 4.
+        Odd lengths fail upstream (the two columns differ in height) and fail here."""
         assert seq_len > 1
-        n_t = seq_len // 2
-        mask = torch.zeros(seq_len, 1)
-        mask[: seq_len - n_t] = 1.0
-        return mask
+        if seq_len % 2 != 0:
+            raise RuntimeError("create_chess_mask: odd seq_len %d (the reference's torch.cat of a [%d,1] and a [%d,1] "
+                               "column along dim 1 fails as well)" % (seq_len, seq_len - seq_len // 2, seq_len // 2))
+        return torch.stack([torch.ones(seq_len // 2), torch.zeros(seq_len // 2)], dim=1).view(-1, 1)
 
     def info(self):
         kind = "channel" if self.mask.size(0) == 1 else "chess"

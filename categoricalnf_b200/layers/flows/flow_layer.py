@@ -7,8 +7,17 @@ one-line description used by ``FlowModel.print_overview``.
 """
 import torch.nn as nn
 
+from ... import ops
+
 
 class FlowLayer(nn.Module):
+
+    def train(self, mode=True):
+        # caches derived from parameters (built 1x1-conv matrices, fused / split projection weights, captured CUDA
+        # graphs) are keyed on ops.param_epoch(): a train <-> eval switch starts a new generation
+        if bool(mode) != self.training:
+            ops.invalidate_caches()
+        return super().train(mode)
 
     def forward(self, z, ldj=None, reverse=False, **kwargs):
         raise NotImplementedError

@@ -4,10 +4,15 @@ A forward pass of the LM flow is ~25 kernel launches; replaying them from one CU
 lets the host run ahead of the device.  ``GraphedFlowForward`` keeps the inputs in static buffers (tokens, optional tensor
 keyword arguments such as ``length`` / ``channel_padding_mask``, the uniform noise of the categorical encoding, drawn outside
 the graph so that replays do not reuse frozen Philox offsets) and captures ``model(...)`` - plus the prior log-likelihood when
-``log_prior`` is given - once per input signature.  The numerical-health word of the kernels is not read inside the graph
+``log_prior`` is given - once per input signature.  A captured graph holds pointers to tensors DERIVED from the parameters
+(built 1x1-convolution matrices, fused / split projection weights), so all graphs are dropped and re-captured when the
+parameters change: ``ops.param_fingerprint`` (version counters, storage addresses and the generation counter that every
+optimiser step, ``train()`` / ``eval()`` switch and ``ops.invalidate_caches()`` advance).  The numerical-health word of the kernels is not read inside the graph
 (``check_nan=False``): read it with ``ops.check_status`` when the results are consumed.
 """
 import torch
+
+from ... import ops
 
 
 class GraphedFlowForward:
@@ -18,6 +23,8 @@ class GraphedFlowForward:
         self.model, self.log_prior = model, log_prior
         self.graphs = {}
         self.captures = 0
+        self._tensors = list(model.parameters()) + list(model.buffers())
+        self._fingerprint = None
 
     def _signature(self, x, kwargs):
         sig = [tuple(x.shape), x.dtype, x.device]
@@ -38,6 +45,10 @@ class GraphedFlowForward:
         """-> (z, ldj, log_likelihood | None): static output tensors, overwritten by the next call with the same signature."""
         if self.model.training:
             raise RuntimeError("GraphedFlowForward replays the evaluation pass: call model.eval() first")
+        fp = ops.param_fingerprint(self._tensors)
+        if fp != self._fingerprint:          # parameters changed since the captures: their derived tensors are stale
+            self.graphs.clear()
+            self._fingerprint = fp
         key = self._signature(x, kwargs)
         st = self.graphs.get(key)
         if st is None:

@@ -4,7 +4,8 @@ Same parameters / buffers as upstream (``p``, ``sign_s``, ``l``, ``log_s``, ``u`
 ``eye`` or ``weight``).  W, its float64 inverse and log|det| are produced by one single-CTA kernel
 (``cnf_invconv_build``); the per-position product by ``cnf_invconv_apply`` (csrc/invconv.cu).
 In eval mode the built matrices are cached in ``eval_dict`` like upstream, but keyed on the
-parameter version counters so a ``load_state_dict`` invalidates them (fixes App. B #12).
+parameter version counters and ``ops.param_epoch()`` so a ``load_state_dict`` or an optimiser step
+(also one that writes through ``p.data``) invalidates them (fixes App. B #12).
 """
 from collections import defaultdict
 
@@ -55,7 +56,7 @@ class InvertibleConv(FlowLayer):
 
     def _param_version(self):
         ps = [self.weight] if not self.LU_decomposed else [self.p, self.sign_s, self.l, self.log_s, self.u]
-        return tuple((t.data_ptr(), t._version) for t in ps)
+        return (ops.param_epoch(),) + tuple((t.data_ptr(), t._version) for t in ps)
 
     def _build(self, differentiable):
         if differentiable:

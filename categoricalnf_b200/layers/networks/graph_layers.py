@@ -88,7 +88,8 @@ class _FusedPair:
 
     def get(self, a, b, attn_weight=None):
         key = (a.weight.data_ptr(), a.weight._version, a.bias._version, b.weight.data_ptr(), b.weight._version,
-               b.bias._version, a.weight.device, None if attn_weight is None else (attn_weight.data_ptr(), attn_weight._version))
+               b.bias._version, a.weight.device, None if attn_weight is None else (attn_weight.data_ptr(), attn_weight._version),
+               ops.param_epoch())
         if key != self.key:
             with torch.no_grad():
                 self.weight, self.bias = self.build(a, b, attn_weight)

@@ -36,7 +36,8 @@ class _TCLinearFn(torch.autograd.Function):
         ctx.precision = precision
         ctx.save_for_backward(x, weight)
         ctx.has_bias = bias is not None
-        return ops.linear(x, weight, bias, precision=precision)
+        # grad mode is off inside Function.forward, so say explicitly that this is a training step: no cached split
+        return ops.linear(x, weight, bias, precision=precision, cache_weight=False)
 
     @staticmethod
     def backward(ctx, gy):
@@ -60,6 +61,11 @@ class TCLinear(nn.Linear):
         if torch.is_grad_enabled() and (x.requires_grad or self.weight.requires_grad):
             return _TCLinearFn.apply(x, self.weight, self.bias, self.precision)
         return ops.linear(x, self.weight, self.bias, precision=self.precision)
+
+    def train(self, mode=True):
+        if bool(mode) != self.training:      # train <-> eval switch: parameters may have moved through p.data
+            ops.invalidate_caches()
+        return super().train(mode)
 
     def extra_repr(self):
         return super().extra_repr() + ", tcgen05 %s" % self.precision

@@ -61,6 +61,17 @@ def _opt_f32(t, name, shape=None):
     return None if t is None else _f32(t, name, shape)
 
 
+def _ldj(t: torch.Tensor, B: int) -> torch.Tensor:
+    """A per-sample ldj that a kernel updates IN PLACE: it must already be a contiguous fp32 CUDA tensor of shape [B] -
+    a silent ``.float()`` / ``.contiguous()`` copy would break the in-place contract (the caller's tensor would not change)."""
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError("categoricalnf_b200: ldj must be a CUDA tensor (there is no CPU fallback)")
+    if t.dtype != torch.float32 or not t.is_contiguous() or tuple(t.shape) != (B,):
+        raise ValueError("ldj is updated in place and must be a contiguous float32 tensor of shape [%d]; got %s %s%s"
+                         % (B, t.dtype, tuple(t.shape), "" if t.is_contiguous() else " (non-contiguous)"))
+    return t
+
+
 def _pad_bs(pad, B, S, name="channel_padding_mask"):
     """Accept [B,S], [B,S,1] (or anything with B*S elements) and return a contiguous [B,S] view."""
     if pad is None:
@@ -121,12 +132,40 @@ def check_status(device, where: str = "") -> None:
     raise AssertionError("[!] ERROR: Found NaN in %s%s" % (" and ".join(what), " (%s)" % where if where else ""))
 
 
+_cur_device = getattr(torch._C, "_cuda_getDevice", None) or torch.cuda.current_device
+_set_device = getattr(torch._C, "_cuda_setDevice", None) or torch.cuda.set_device
+
+
 def _call(name, args, ref: torch.Tensor, keep=None):
+    """Launch ``name`` on torch's current stream of ``ref``'s device.  The C side launches on the calling thread's current
+    device, so that device is switched to ``ref``'s for the duration of the call when it differs (model on cuda:1 while
+    cuda:0 is current); every tensor in ``keep`` must live on the same device."""
     global _launches
-    L.call(name, args, _stream(ref))
+    dev = ref.device.index
+    if keep is not None:
+        _same_device(dev, keep, name)
+    cur = _cur_device()
+    if cur != dev:
+        _set_device(dev)
+        try:
+            L.call(name, args, _stream(ref))
+        finally:
+            _set_device(cur)
+    else:
+        L.call(name, args, _stream(ref))
     _launches += 1
     if STRICT:
         check_status(ref.device, name)
+
+
+def _same_device(dev, items, name):
+    for t in items:
+        if isinstance(t, torch.Tensor):
+            if t.is_cuda and t.device.index != dev:
+                raise RuntimeError("categoricalnf_b200: %s got tensors on cuda:%d and cuda:%d - all arguments of one call "
+                                   "must live on one device" % (name, dev, t.device.index))
+        elif isinstance(t, (tuple, list)):
+            _same_device(dev, t, name)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -167,7 +206,7 @@ def mixcdf(z, nn_out, num_mixtures, *, mask_c=None, mask_s=None, pad=None, scali
     B = z.shape[0]
     z_out = torch.empty_like(z) if out is None else out
     accumulate = ldj is not None
-    ldj_t = _f32(ldj, "ldj", (B,)) if accumulate else torch.empty(B, dtype=torch.float32, device=z.device)
+    ldj_t = _ldj(ldj, B) if accumulate else torch.empty(B, dtype=torch.float32, device=z.device)
     reg = torch.empty(B, dtype=torch.float32, device=z.device) if want_reg else None
     a.reg_max, a.reg_factor, a.training = float(reg_max), float(reg_factor), int(bool(training))
     a.accumulate = int(accumulate)
@@ -191,7 +230,7 @@ def affine_coupling(z, nn_out, ldj, *, mask_c=None, mask_s=None, scaling_factor=
     z = _f32(z, "z")
     B, S, Cc = z.shape
     nn_out = _f32(nn_out, "nn_out", (B, S, 2 * Cc))
-    ldj = _f32(ldj, "ldj", (B,))
+    ldj = _ldj(ldj, B)
     a = L.AffineArgs()
     a.B, a.S, a.C = B, S, Cc
     a.mask, keep = _mask_struct(mask_c, mask_s)
@@ -215,7 +254,7 @@ def actnorm(z, bias, scales, ldj=None, *, pad=None, length=None, reverse=False):
     pad = _pad_bs(pad, B, S)
     length = _opt_f32(length, "length", (B,))
     if ldj is not None:
-        ldj = _f32(ldj, "ldj", (B,))
+        ldj = _ldj(ldj, B)
     z_out = torch.empty_like(z)
     a.z, a.bias, a.scales, a.pad, a.length = _ptr(z), _ptr(bias), _ptr(scales), _ptr(pad), _ptr(length)
     a.reverse, a.z_out, a.ldj, a.status = int(bool(reverse)), _ptr(z_out), _ptr(ldj), _ptr(status_word(z.device))
@@ -228,7 +267,7 @@ def ext_actnorm(z, ext, ldj, *, pad=None, reverse=False):
     z = _f32(z, "z")
     B, S, Cc = z.shape
     ext = _f32(ext, "ext", (B, S, 2 * Cc))
-    ldj = _f32(ldj, "ldj", (B,))
+    ldj = _ldj(ldj, B)
     pad = _pad_bs(pad, B, S)
     a = L.ExtActnormArgs()
     a.B, a.S, a.C = B, S, Cc
@@ -284,7 +323,7 @@ def invconv_apply(z, weight, sldj, ldj=None, *, pad=None, length=None, reverse=F
     pad = _pad_bs(pad, B, S)
     length = _opt_f32(length, "length", (B,))
     if ldj is not None:
-        ldj = _f32(ldj, "ldj", (B,))
+        ldj = _ldj(ldj, B)
     z_out = torch.empty_like(z)
     a = L.InvconvArgs()
     a.B, a.S, a.C = B, S, Cc
@@ -323,7 +362,7 @@ def categ_encode(tokens, table, category_prior, ldj, *, noise=None, seed=0, offs
     V, D2 = table.shape
     D = D2 // 2
     prior = _opt_f32(category_prior, "category_prior", (V,))
-    ldj = _f32(ldj, "ldj", (B,))
+    ldj = _ldj(ldj, B)
     pad = _pad_bs(pad, B, S)
     if noise is not None:
         noise = _f32(noise, "noise")
@@ -459,6 +498,41 @@ ACTIVATION = {None: 0, "none": 0, "gelu": 1}
 
 
 _weight_split_cache = {}     # id(tensor) -> (weakref, key, hi, lo)
+_param_epoch = 0             # bumped whenever parameters may have changed without their ``_version`` moving
+
+
+def param_epoch() -> int:
+    """Generation counter of everything DERIVED from parameters (3xTF32 weight splits, fused projection weights, built 1x1
+    convolution matrices, captured CUDA graphs).  ``tensor._version`` alone cannot key those caches: in-place writes through
+    ``p.data`` - which is how the reference's default optimiser updates weights (general/radam.py:82,147) - leave it
+    unchanged.  The counter moves on every optimiser step (a global ``register_optimizer_step_post_hook``), on every
+    ``train()`` / ``eval()`` switch of a drop-in module and on :func:`invalidate_caches`; and caches are bypassed
+    altogether while gradients are being recorded."""
+    return _param_epoch
+
+
+def invalidate_caches(*_args, **_kwargs) -> None:
+    """Call after changing parameters in a way autograd's version counters cannot see (``p.data`` writes outside an
+    ``torch.optim.Optimizer.step``, e.g. swapping in EMA weights)."""
+    global _param_epoch
+    _param_epoch += 1
+
+
+def param_fingerprint(tensors) -> tuple:
+    """Cheap identity of a set of parameters / buffers for caches that hold DERIVED device tensors (captured CUDA graphs):
+    the cache generation, the version counters and the storage addresses."""
+    v = a = 0
+    for t in tensors:
+        v += t._version
+        a ^= t.data_ptr()
+    return (_param_epoch, v, a)
+
+
+try:        # every torch.optim.Optimizer subclass - the reference's RAdam / Adam included - runs this after step()
+    from torch.optim.optimizer import register_optimizer_step_post_hook as _reg_post_step
+    _reg_post_step(invalidate_caches)
+except ImportError:      # pragma: no cover - torch < 2.0
+    pass
 
 
 def _rna_tf32(t):
@@ -466,13 +540,21 @@ def _rna_tf32(t):
     return ((t.contiguous().view(torch.int32) + 0x1000) & -8192).view(torch.float32)
 
 
-def weight_split(weight):
-    """(hi, lo) with hi = rna_tf32(weight), lo = rna_tf32(weight - hi): the 3xTF32 split of a weight, done once per tensor
-    object and version instead of once per tile inside the kernel.  Only long-lived weights are cached: ``nn.Parameter``s
-    and tensors marked ``_cnf_cache_lo`` (fused weight blocks); None for anything else."""
+def weight_split(weight, use_cache=True):
+    """(hi, lo) with hi = rna_tf32(weight), lo = rna_tf32(weight - hi): the 3xTF32 split of a weight, done on the host
+    side of the ABI instead of once per tile inside the kernel.  Only long-lived weights are split here: ``nn.Parameter``s
+    and tensors marked ``_cnf_cache_lo`` (fused weight blocks); None for anything else.  ``use_cache=False`` (training:
+    the weight changes every step) splits afresh and stores nothing; otherwise the split is cached per tensor object,
+    version and :func:`param_epoch`."""
     if not (isinstance(weight, torch.nn.Parameter) or getattr(weight, "_cnf_cache_lo", False)):
         return None
-    key = (weight._version, weight.data_ptr(), tuple(weight.shape))
+    if not use_cache or (torch.is_grad_enabled() and weight.requires_grad):
+        _weight_split_cache.pop(id(weight), None)
+        with torch.no_grad():
+            w = weight.detach()
+            hi = _rna_tf32(w)
+            return hi, _rna_tf32(w - hi)
+    key = (weight._version, weight.data_ptr(), tuple(weight.shape), _param_epoch)
     hit = _weight_split_cache.get(id(weight))
     if hit is None or hit[0]() is not weight or hit[1] != key:
         with torch.no_grad():
@@ -486,14 +568,15 @@ def weight_split(weight):
     return hit[2], hit[3]
 
 
-def linear(x, weight, bias=None, *, precision="3xtf32", activation=None, block_n=0):
+def linear(x, weight, bias=None, *, precision="3xtf32", activation=None, block_n=0, cache_weight=True):
     """y = x @ weight.T + bias (nn.Linear) on the tensor cores (``cnf_linear_fwd``).
 
     ``x`` [..., K] fp32 CUDA, ``weight`` [N, K], ``bias`` [N] | None.  ``precision``: "tf32" (one pass)
     or "3xtf32" (hi/lo split, fp32-level accuracy - default, keeps the 1e-4 parity of the flow).
-    K that is not a multiple of 4 is zero-padded (a copy); everything else runs in place."""
+    K that is not a multiple of 4 is zero-padded (a copy); everything else runs in place.  ``cache_weight=False``: the
+    3xTF32 split of the weight is recomputed for this call (training step: the weight is about to change)."""
     x = _f32(x, "x")
-    split = weight_split(weight) if precision == "3xtf32" and weight.dtype == torch.float32 and weight.is_contiguous() else None
+    split = weight_split(weight, cache_weight) if precision == "3xtf32" and weight.dtype == torch.float32 and weight.is_contiguous() else None
     weight = _f32(weight, "weight")
     w_lo = None
     if split is not None:
@@ -620,7 +703,7 @@ def linear_mixcdf(z, features, weight, bias, num_mixtures, *, mask_c=None, mask_
     B = z.shape[0]
     z_out = torch.empty_like(z)
     accumulate = ldj is not None
-    ldj_t = _f32(ldj, "ldj", (B,)) if accumulate else torch.empty(B, dtype=torch.float32, device=z.device)
+    ldj_t = _ldj(ldj, B) if accumulate else torch.empty(B, dtype=torch.float32, device=z.device)
     reg = torch.empty(B, dtype=torch.float32, device=z.device) if want_reg else None
     a.mix.reg_max, a.mix.reg_factor, a.mix.training = float(reg_max), float(reg_factor), int(bool(training))
     a.mix.accumulate = int(accumulate)

@@ -127,5 +127,8 @@ def broadcast_parameters(module: torch.nn.Module, src: int = 0, group=None) -> N
     data-dependent initialisation)."""
     if world(group)[1] == 1:
         return
-    for t in list(module.parameters()) + list(module.buffers()):
-        dist.broadcast(t.data, src=src, group=group)
+    from . import ops
+    with torch.no_grad():      # broadcast into the tensor itself (not ``.data``) so its version counter moves
+        for t in list(module.parameters()) + list(module.buffers()):
+            dist.broadcast(t, src=src, group=group)
+    ops.invalidate_caches()
