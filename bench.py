@@ -16,8 +16,9 @@ the ranks all-reduce (sum log-likelihood, sample count) once per step.
          log-likelihood inside the timed region.
 `roofline` the dominant kernel (mixture coupling forward): algorithmic bytes per launch / mean
          launch duration from CUDA events recorded inside the timed region.
-`cpu_baseline` / `--impl reference`: the CPU oracle (port of the reference's eager fp64 path) on
-         the host cores, on a bounded sub-batch of the same workload.
+`cpu_baseline` / `--impl reference`: the UNMODIFIED reference modules (baseline/_ref, vendored by
+         tools/vendor_reference.sh) on the host cores, on a bounded sub-batch of the same workload;
+         the oracle port only when baseline/_ref did not travel with the repo.
 Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
@@ -102,24 +103,51 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------------
-# CPU arm (oracle port of the reference's eager fp64 path)
+# CPU arm: the UNMODIFIED reference modules from baseline/_ref (tools/vendor_reference.sh) when they travelled with the
+# repo (kind "reference"), else the oracle port of the reference's eager fp64 path (kind "port")
 # --------------------------------------------------------------------------------------------------
-def cpu_step(prm, B, seed):
-    tokens, u = W.lm_tokens(B, prm.S, prm.V, seed=seed), W.lm_noise(B, prm.S, prm.D, seed=seed)
-    t0 = time.perf_counter()
-    z, ldj, logp = W.lm_oracle_forward(prm, tokens, u)
-    return time.perf_counter() - t0, W.bits_per_dim(ldj, logp, prm.S)
+class CpuArm:
+    def __init__(self, prm):
+        self.prm = prm
+        self.kind = "reference" if W.reference_available() else "port"
+        if self.kind == "reference":
+            self.model, self.prior = W.build_lm_reference_model(prm)
+        self.what = ("unmodified reference modules (baseline/_ref: layers/flows, layers/categorical_encoding; eager fp32/fp64)"
+                     if self.kind == "reference" else "eager fp64 oracle port (baseline/_ref absent)")
 
+    def step(self, B, seed):
+        prm = self.prm
+        tokens = W.lm_tokens(B, prm.S, prm.V, seed=seed)
+        if self.kind == "reference":
+            torch.manual_seed(seed)
+            t0 = time.perf_counter()
+            with torch.no_grad():
+                z, ldj = self.model(tokens, reverse=False)
+                logp = self.prior.log_prob(z).sum(dim=[1, 2])
+        else:
+            u = W.lm_noise(B, prm.S, prm.D, seed=seed)
+            t0 = time.perf_counter()
+            z, ldj, logp = W.lm_oracle_forward(prm, tokens, u)
+        return time.perf_counter() - t0, W.bits_per_dim(ldj, logp, prm.S)
 
-def cpu_pick_batch(prm, steps, budget_s):
-    """Sub-batch so that `steps` CPU steps fit in about `budget_s` seconds (calibrated on B=8)."""
-    cpu_step(prm, 4, 99)
-    dt, _ = cpu_step(prm, 8, 98)
-    per_sample = dt / 8
-    B = 8
-    while B < 512 and 2 * B * per_sample * steps <= budget_s:
-        B *= 2
-    return B
+    def pick_batch(self, steps, budget_s):
+        """Sub-batch so that `steps` CPU steps fit in about `budget_s` seconds (calibrated on B=8)."""
+        self.step(4, 99)
+        dt, _ = self.step(8, 98)
+        per_sample = dt / 8
+        B = 8
+        while B < 512 and 2 * B * per_sample * steps <= budget_s:
+            B *= 2
+        return B
+
+    def cross_check(self, B=4):
+        """reference arm only: the oracle port on the noise the reference drew - how far the test oracle is from the real thing."""
+        if self.kind != "reference":
+            return None
+        tokens = W.lm_tokens(B, self.prm.S, self.prm.V, seed=55)
+        z, ldj, lp, u = W.lm_reference_forward(self.model, self.prior, tokens, 55)
+        z2, ldj2, lp2 = W.lm_oracle_forward(self.prm, tokens, u)
+        return {"batch": B, "max_abs_z": float((z - z2).abs().max()), "max_rel_ldj": float(((ldj - ldj2).abs() / ldj2.abs()).max())}
 
 
 def run_reference(args, rank):
@@ -127,25 +155,26 @@ def run_reference(args, rank):
         return
     torch.set_num_threads(os.cpu_count() or 1)
     prm = W.data_init_oracle(W.lm_params(seed=0), seed=0)
-    B = cpu_pick_batch(prm, args.steps + args.warmup, budget_s=150.0)
+    arm = CpuArm(prm)
+    B = arm.pick_batch(args.steps + args.warmup, budget_s=150.0)
     for i in range(args.warmup):
-        cpu_step(prm, B, 100 + i)
+        arm.step(B, 100 + i)
     times, bpd = [], None
     for i in range(args.steps):
-        dt, bpd = cpu_step(prm, B, i)
+        dt, bpd = arm.step(B, i)
         times.append(dt)
     total = sum(times)
     value = B * args.steps / total
-    sample = "B=%d of the %d-sample batch per step (S=%d, d=%d, K=%d, %d blocks), eager fp64 oracle port" % (
-        B, W.LM["B"], prm.S, prm.D, prm.K, len(prm.blocks))
+    sample = "B=%d of the %d-sample batch per step (S=%d, d=%d, K=%d, %d blocks), %s" % (
+        B, W.LM["B"], prm.S, prm.D, prm.K, len(prm.blocks), arm.what)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args.gpus, extra={"cpu_sub_batch": B}),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": arm.kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0, "bits_per_dim": bpd,
+        "gpu_launches": 0, "bits_per_dim": bpd, "oracle_vs_reference": arm.cross_check(),
     }
     print(json.dumps(line), flush=True)
 
@@ -381,19 +410,21 @@ def ncu_traffic():
 
 
 def cpu_baseline(prm):
-    """Oracle port on the host cores, on a bounded sub-batch (about 10-30 s of CPU work)."""
+    """The reference (baseline/_ref) - or, when it did not travel, the oracle port - on the host cores, on a bounded
+    sub-batch (about 10-30 s of CPU work)."""
     torch.set_num_threads(os.cpu_count() or 1)
-    B = cpu_pick_batch(prm, 1, budget_s=20.0)
-    cpu_step(prm, B, 1)                      # warm-up at the measured size (allocator, thread pool)
+    arm = CpuArm(prm)
+    B = arm.pick_batch(1, budget_s=20.0)
+    arm.step(B, 1)                           # warm-up at the measured size (allocator, thread pool)
     times, bpd, t_start = [], None, time.perf_counter()
     while len(times) < 3 or (time.perf_counter() - t_start < 12.0 and len(times) < 8):
-        dt, bpd = cpu_step(prm, B, len(times))
+        dt, bpd = arm.step(B, len(times))
         times.append(dt)
     total = sum(times)
-    return {"value": B * len(times) / total, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+    return {"value": B * len(times) / total, "unit": UNIT, "cores": torch.get_num_threads(), "kind": arm.kind,
             "sample": "%d steps at B=%d of the %d-sample batch (S=%d, d=%d, K=%d, %d blocks, stand-in Linear nets), "
-                      "eager fp64 oracle port, %.1f s of CPU work, best step %.0f samples/s"
-                      % (len(times), B, W.LM["B"], prm.S, prm.D, prm.K, len(prm.blocks), total, B / min(times)),
+                      "%s, %.1f s of CPU work, best step %.0f samples/s"
+                      % (len(times), B, W.LM["B"], prm.S, prm.D, prm.K, len(prm.blocks), arm.what, total, B / min(times)),
             "bits_per_dim": bpd}
 
 

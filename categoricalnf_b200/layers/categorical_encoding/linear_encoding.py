@@ -10,6 +10,8 @@ tensors through ~60 launches.  Linear flows (``num_flows>0``) and the decoder va
 the drop-in flow layers exactly as upstream does.
 """
 import numpy as np
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -23,6 +25,14 @@ from ..flows.flow_layer import FlowLayer
 from ..flows.permutation_layers import InvertibleConv
 from ..networks.help_layers import LinearNet, SimpleLinearLayer
 from .decoder import _param, create_decoder, create_embed_layer
+
+
+def _host_noise() -> bool:
+    """``CNF_B200_HOST_NOISE=1``: draw the encoding's uniform noise from torch's CPU generator with the reference's own call
+    (``Uniform(0,1).sample((B*S, 1, D))`` on the host, then ``.to(device)`` - linear_encoding.py:78, distributions.py:139)
+    instead of Philox inside the kernel.  Slower (one H2D copy per forward) but bit-identical noise to a reference run with
+    the same seed - what ``tools/run_set_modeling.py`` uses to compare training runs step by step."""
+    return os.environ.get("CNF_B200_HOST_NOISE", "0") not in ("", "0")
 
 
 def philox_stream(device, n):
@@ -81,6 +91,8 @@ class LinearCategoricalEncoding(FlowLayer):
         internal random draw - the hook parity tests use to replay the reference's noise."""
         batch_size, seq_length = z.size(0), z.size(1)
         detailed_ldj = {}
+        if u_noise is None and not reverse and _host_noise():
+            u_noise = torch.rand(batch_size * seq_length, 1, self.D).to(z.device)
         if self._fused_ok(z):
             with torch.no_grad():
                 table = self.class_table()

@@ -246,33 +246,123 @@ class StandInNet(torch.nn.Module):
         return self.lin(x)
 
 
-def build_lm_model(prm: LMParams, device):
-    """(encoding + blocks as a drop-in FlowModel, prior) with ``prm`` loaded, in eval mode on ``device``."""
+def _lm_model_from(prm: LMParams, C, net_factory):
+    """The LM flow built from the classes in namespace ``C`` (the drop-in modules or the reference's own - they share
+    constructor signatures and parameter names) with ``prm`` loaded.  -> (FlowModel, prior)."""
     import contextlib
     import io
-    from categoricalnf_b200.layers.categorical_encoding import LinearCategoricalEncoding
-    from categoricalnf_b200.layers.flows import (ActNormFlow, FlowModel, InvertibleConv, LogisticDistribution,
-                                                 MixtureCDFCoupling)
     D, K = prm.D, prm.K
-    enc = LinearCategoricalEncoding(num_dimensions=D, flow_config={"num_flows": 0}, vocab_size=prm.V,
-                                    default_embed_layer_dims=prm.embed_w.shape[1], category_prior=prm.prior.clone())
+    with contextlib.redirect_stdout(io.StringIO()):
+        enc = C.LinearCategoricalEncoding(num_dimensions=D, flow_config={"num_flows": 0, "hidden_layers": 2, "hidden_size": 64},
+                                          vocab_size=prm.V, default_embed_layer_dims=prm.embed_w.shape[1],
+                                          category_prior=prm.prior.clone())
     layers = [enc]
     with torch.no_grad():
         enc.embed_layer.weight.copy_(prm.embed_w)
         enc.flow_layers[0].pred_net.layer.weight.copy_(prm.pred_w)
         enc.flow_layers[0].pred_net.layer.bias.copy_(prm.pred_b)
         for b in prm.blocks:
-            an = ActNormFlow(c_in=D, data_init=False)
+            an = C.ActNormFlow(c_in=D, data_init=False)
             an.bias.copy_(b["bias"].view(1, 1, -1))
             an.scales.copy_(b["scales"].view(1, 1, -1))
-            conv = InvertibleConv(c_in=D)
+            conv = C.InvertibleConv(c_in=D)
             conv.p.copy_(b["p"]); conv.l.copy_(b["l"]); conv.u.copy_(b["u"])
             conv.log_s.copy_(b["log_s"]); conv.sign_s.copy_(b["sign_s"])
-            mix = MixtureCDFCoupling(c_in=D, mask=b["mask"].clone(), model_func=lambda c_out: StandInNet(D, c_out),
-                                     num_mixtures=K)
+            mix = C.MixtureCDFCoupling(c_in=D, mask=b["mask"].clone(), model_func=lambda c_out: net_factory(D, c_out),
+                                       num_mixtures=K)
             mix.scaling_factor.copy_(b["sf"]); mix.mixture_scaling_factor.copy_(b["msf"])
             mix.nn.lin.weight.copy_(b["net_w"]); mix.nn.lin.bias.copy_(b["net_b"])
             layers += [an, conv, mix]
     with contextlib.redirect_stdout(io.StringIO()):
-        model = FlowModel(layers, name="LM flow (synthetic)")
-    return model.to(device).eval(), LogisticDistribution(mu=0.0, sigma=1.0).to(device)
+        model = C.FlowModel(layers, name="LM flow (synthetic)")
+    return model, C.LogisticDistribution(mu=0.0, sigma=1.0)
+
+
+def build_lm_model(prm: LMParams, device):
+    """(encoding + blocks as a drop-in FlowModel, prior) with ``prm`` loaded, in eval mode on ``device``."""
+    from types import SimpleNamespace
+    from categoricalnf_b200.layers.categorical_encoding import LinearCategoricalEncoding
+    from categoricalnf_b200.layers.flows import (ActNormFlow, FlowModel, InvertibleConv, LogisticDistribution,
+                                                 MixtureCDFCoupling)
+    C = SimpleNamespace(LinearCategoricalEncoding=LinearCategoricalEncoding, ActNormFlow=ActNormFlow, FlowModel=FlowModel,
+                        InvertibleConv=InvertibleConv, LogisticDistribution=LogisticDistribution,
+                        MixtureCDFCoupling=MixtureCDFCoupling)
+    model, prior = _lm_model_from(prm, C, StandInNet)
+    return model.to(device).eval(), prior.to(device)
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU reference arm proper: the UNMODIFIED reference modules from baseline/_ref (tools/vendor_reference.sh)
+# --------------------------------------------------------------------------------------------------
+import os as _os
+
+REF_ROOT = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "baseline", "_ref")
+
+
+def reference_available() -> bool:
+    return _os.path.isdir(_os.path.join(REF_ROOT, "layers", "flows"))
+
+
+def import_reference():
+    """Namespace of the reference's own flow classes, imported from baseline/_ref.  Must not be mixed with
+    ``categoricalnf_b200.install`` in one process (both claim the top-level ``layers`` package)."""
+    import sys
+    from types import SimpleNamespace
+    if "categoricalnf_b200.install" in sys.modules and any(
+            getattr(sys.modules.get(n), "__name__", "").startswith("categoricalnf_b200.") for n in ("layers.flows.flow_model",)):
+        raise RuntimeError("import_reference: the drop-in modules are installed under the reference's names in this process")
+    if not reference_available():
+        raise FileNotFoundError("baseline/_ref is missing: run tools/vendor_reference.sh where /root/reference exists")
+    if REF_ROOT not in sys.path:
+        sys.path.insert(0, REF_ROOT)
+    try:
+        import matplotlib  # noqa: F401
+    except ImportError:      # general/task.py:8 and layers/flows/flow_model.py import it without using it here
+        import types
+        mpl = types.ModuleType("matplotlib")
+        mpl.use = lambda *a, **k: None
+        mpl.pyplot, mpl.colors = types.ModuleType("matplotlib.pyplot"), types.ModuleType("matplotlib.colors")
+        sys.modules.update({"matplotlib": mpl, "matplotlib.pyplot": mpl.pyplot, "matplotlib.colors": mpl.colors})
+    from layers.categorical_encoding.linear_encoding import LinearCategoricalEncoding
+    from layers.flows.activation_normalization import ActNormFlow
+    from layers.flows.distributions import LogisticDistribution
+    from layers.flows.flow_model import FlowModel
+    from layers.flows.mixture_cdf_layer import MixtureCDFCoupling
+    from layers.flows.permutation_layers import InvertibleConv
+    assert FlowModel.__module__ == "layers.flows.flow_model" and REF_ROOT in _os.path.abspath(sys.modules[FlowModel.__module__].__file__)
+    return SimpleNamespace(LinearCategoricalEncoding=LinearCategoricalEncoding, ActNormFlow=ActNormFlow, FlowModel=FlowModel,
+                           InvertibleConv=InvertibleConv, LogisticDistribution=LogisticDistribution,
+                           MixtureCDFCoupling=MixtureCDFCoupling)
+
+
+class _RefStandInNet(torch.nn.Module):
+    """The stand-in per-position Linear coupling network for the reference arm: plain ``nn.Linear`` (the reference's
+    networks are plain torch modules), same call signature (coupling_layer.py:28-35)."""
+
+    def __init__(self, c_in, c_out):
+        super().__init__()
+        self.lin = torch.nn.Linear(c_in, c_out)
+
+    def forward(self, x, length=None, **kwargs):
+        return self.lin(x)
+
+
+def build_lm_reference_model(prm: LMParams):
+    """The same LM flow from the reference's own classes on the CPU, eval mode.  -> (FlowModel, prior)."""
+    model, prior = _lm_model_from(prm, import_reference(), _RefStandInNet)
+    return model.eval(), prior
+
+
+def lm_reference_forward(model, prior, tokens, seed):
+    """(z, ldj [B], log_prior [B], u_noise) through the unmodified reference on the CPU.  The encoding draws its noise
+    from torch's global CPU generator (linear_encoding.py:78): seeding it makes the draw reproducible, and the same draw
+    is returned so the oracle port / the GPU path can be run on identical noise."""
+    B, S = tokens.shape
+    D = model.flow_layers[0].D
+    torch.manual_seed(seed)
+    u = torch.rand(B * S, 1, D)                # what Uniform(0,1).sample((B*S,1,D)) will draw next
+    torch.manual_seed(seed)
+    with torch.no_grad():
+        z, ldj = model(tokens, reverse=False)
+        logp = prior.log_prob(z).sum(dim=[1, 2])
+    return z, ldj, logp, u
