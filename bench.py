@@ -171,8 +171,9 @@ def run_reference(args, rank):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args.gpus, extra={"cpu_sub_batch": B}),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": arm.kind, "sample": sample},
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": arm.kind, "sample": sample,
+                         "sub_batch": B},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "bits_per_dim": bpd, "oracle_vs_reference": arm.cross_check(),
     }
@@ -185,7 +186,7 @@ def workload_config(n_gpus, extra=None):
            "batch_per_gpu": W.LM["B"], "global_batch": W.LM["B"] * n_gpus, "seq_len": W.LM["S"], "d": W.LM["D"],
            "mixtures": W.LM["K"], "vocab": W.LM["V"], "blocks": W.LM["blocks"], "parallelism": "batch-sharded x%d" % n_gpus,
            "l2": "inputs larger than L2 (1.74 GB of coupling parameters per layer vs 126 MB L2); no flush needed",
-           "value_leg": "coupling-net outputs given, resident in HBM", "e2e_leg": "drop-in FlowModel (see e2e_mode), stand-in Linear "
+           "value_leg": "coupling-net outputs given, resident in HBM", "e2e_leg": "drop-in FlowModel (see e2e.mode), stand-in Linear "
            "coupling nets (final projection fused with the mixture transform on tcgen05, 3xTF32), pinned host tokens -> H2D "
            "(double-buffered on a copy stream), per-sample log-likelihood + kernel status word -> D2H (host reads step i-1 while step i runs)"}
     if extra:
@@ -350,6 +351,14 @@ def run_gpu(args, rank, local_rank, world):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total, e2e_ms_total, mix_ms_mean = (float(x) for x in t.tolist())
 
+    # ---- BASELINE configs 3, 4, 5 (graph colouring, GraphCNF log-likelihood, GraphCNF sampling) ---------------------------
+    graph_records = None
+    if not args.no_graphs:
+        del model, prior, graphed
+        torch.cuda.empty_cache()
+        import bench_graphs
+        graph_records = bench_graphs.run_all(args, rank, world, dev, dist, ClockSampler(local_rank) if rank == 0 else None)
+
     if rank == 0:
         peak, peak_src = measured_peaks()
         ms_step = ms_total / args.steps
@@ -361,9 +370,9 @@ def run_gpu(args, rank, local_rank, world):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": workload_config(world, extra={"e2e_mode": e2e_mode}),
+            "data": "synthetic", "config": workload_config(world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * S * 8, "d2h_bytes_per_step": B * 4 + 4,
-                    "ms_per_step": e2e_ms_total / args.steps},
+                    "ms_per_step": e2e_ms_total / args.steps, "mode": e2e_mode},
             "gpu_launches": launches,
             "roofline": {"kernel": "mixcdf_pipe_kernel<8,8,fwd> (cnf_mixcdf_fwd)", "bound": "hbm", "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(),
@@ -374,6 +383,8 @@ def run_gpu(args, rank, local_rank, world):
         }
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(prm)
+        if graph_records is not None:
+            line["configs"] = graph_records
         print(json.dumps(line), flush=True)
     if distributed:
         dist.destroy_process_group()
@@ -434,7 +445,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / reference-parity legs")
+    ap.add_argument("--no-graphs", action="store_true", help="skip the records of BASELINE configs 3, 4, 5 (key `configs`)")
+    ap.add_argument("--graph-steps", type=int, default=5, help="timed steps per graph config (capped by --steps)")
     ap.add_argument("--eager-e2e", action="store_true", help="e2e leg launches kernel by kernel instead of replaying a CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

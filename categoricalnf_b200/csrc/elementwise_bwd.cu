@@ -91,7 +91,7 @@ __global__ void affine_bwd_kernel(const AffineBwdParams p) {
         } else {
             const float sech2 = 1.0f - th * th;
             p.gnn[i] = make_float2(gs * sech2 * fac / fmax_, gt);
-            gsf += gs * fac * (th - (fac > 1.0f ? sech2 * st.x / fac : 0.f));
+            gsf += gs * fac * (th - (fac >= 1.0f ? sech2 * st.x / fac : 0.f));   // torch.clamp passes the gradient AT the bound (fac == 1: every freshly built layer, scaling_factor = 0)
         }
     }
     block_channel_add(s_acc, p.gsf, gsf, c, p.C);

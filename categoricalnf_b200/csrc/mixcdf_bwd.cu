@@ -153,7 +153,7 @@ __device__ __forceinline__ bool mix_backward_elem(float xf, float* rec, const fl
             const T sech2 = (T)1 - thk * thk;
             ms[k] = (float)(Lls * sech2 * (T)mf * imf_max);
             // ls = tanh(raw / max(M,1)) M, M = e^{msf}: d ls / d msf  (for M > 1: max(M,1) = M)
-            const T dmsf = (T)mf * thk - (mf > 1.0f ? sech2 * raw : (T)0);
+            const T dmsf = (T)mf * thk - (mf >= 1.0f ? sech2 * raw : (T)0);
             if (KT > 0) gmsf_k[k] = (float)(Lls * dmsf);            // registers, reduced across the warp by the caller
             else atomicAdd(gmsf_k + k, (float)(Lls * dmsf));       // generic K / float64 path: shared-memory accumulator
         }
@@ -164,7 +164,7 @@ __device__ __forceinline__ bool mix_backward_elem(float xf, float* rec, const fl
     } else {
         const T sech2 = (T)1 - ths * ths;
         const T raw = (T)rec[1];
-        *gsf_out += (float)(g_logs * ((T)sfac * ths - (sfac > 1.0f ? sech2 * raw : (T)0)));
+        *gsf_out += (float)(g_logs * ((T)sfac * ths - (sfac >= 1.0f ? sech2 * raw : (T)0)));
         rec[1] = (float)(g_logs * sech2 * (T)sfac * M::rc((T)sf_max));
     }
     *gx_out = (float)gx;

@@ -497,6 +497,7 @@ PRECISION = {"tf32": 0, "3xtf32": 1}
 ACTIVATION = {None: 0, "none": 0, "gelu": 1}
 
 
+linear_profile = None        # set to a list: every cnf_linear_fwd launch appends (M, N, K, precision, start event, end event)
 _weight_split_cache = {}     # id(tensor) -> (weakref, key, hi, lo)
 _param_epoch = 0             # bumped whenever parameters may have changed without their ``_version`` moving
 
@@ -601,7 +602,14 @@ def linear(x, weight, bias=None, *, precision="3xtf32", activation=None, block_n
     a.x, a.weight, a.bias, a.y = _ptr(x2), _ptr(weight), _ptr(bias), _ptr(y)
     a.precision, a.activation = PRECISION[precision], ACTIVATION[activation]
     a.weight_lo, a.block_n = _ptr(w_lo), int(block_n)
-    _call("cnf_linear_fwd", a, x2, (x2, weight, bias, w_lo))
+    if linear_profile is None:
+        _call("cnf_linear_fwd", a, x2, (x2, weight, bias, w_lo))
+    else:       # bench.py's tensor-pipe roofline: CUDA events around every projection launch on the launching stream
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _call("cnf_linear_fwd", a, x2, (x2, weight, bias, w_lo))
+        e1.record()
+        linear_profile.append((a.M, N, K, precision, e0, e1))
     return y.reshape(lead + (N,))
 
 

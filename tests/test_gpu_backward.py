@@ -76,12 +76,36 @@ def test_mixcdf_backward_vs_oracle_autograd(B, S, C, K, padded, chess, flip, reg
     grads_close(mg.grad, mo.grad, "dL/dmixture_scaling_factor", rtol=5e-4, atol_rel=5e-4)
 
 
+def test_mixcdf_backward_at_zero_scaling_factors():
+    """Freshly built layers have scaling_factor = mixture_scaling_factor = 0, i.e. exp(.) sits exactly ON the bound of
+    ``scaling_fac.clamp(min=1.0)`` (mixture_cdf_layer.py:158-162), where torch passes the gradient through the clamp.
+    Found by tests/test_gpu_reference_training.py: the first optimiser step of every training run starts here."""
+    from categoricalnf_b200 import functional as CF
+    B, S, C, K = 4, 12, 6, 8
+    z, nn_out, sf, msf, mask, pad, wz, wl = _mix_inputs(B, S, C, K, seed=91, padded=False)
+    sf, msf = torch.zeros_like(sf), torch.zeros_like(msf)
+    msf[0, :3] = torch.tensor([0.3, -0.3, 0.0])          # both sides of the bound next to it
+    zo, no, so, mo = leaf(z), leaf(nn_out), leaf(sf), leaf(msf)
+    out, ldj, _ = O.mixcdf_coupling(zo, no, O.expand_mask(mask, z), K, so, mo, training=True)
+    ((out * wz).sum() + (ldj * wl).sum()).backward()
+    zg, ng, sg, mg = leaf(z, True), leaf(nn_out, True), leaf(sf, True), leaf(msf, True)
+    out_g, ldj_g, _ = CF.mixcdf(zg, ng, K, sg, mg, mask_c=mask.flatten().tolist(), training=True)
+    ((out_g * wz.cuda()).sum() + (ldj_g * wl.cuda()).sum()).backward()
+    assert so.grad.abs().max() > 1e-3 and mo.grad.abs().max() > 1e-3
+    grads_close(ng.grad, no.grad, "dL/dnn_out")
+    grads_close(sg.grad, so.grad, "dL/dscaling_factor at 0", rtol=5e-4, atol_rel=5e-4)
+    grads_close(mg.grad, mo.grad, "dL/dmixture_scaling_factor at 0", rtol=5e-4, atol_rel=5e-4)
+
+
 @pytest.mark.parametrize("reverse", [False, True])
-def test_affine_backward(reverse):
+@pytest.mark.parametrize("zero_sf", [False, True])
+def test_affine_backward(reverse, zero_sf):
     from categoricalnf_b200 import functional as CF
     g = torch.Generator().manual_seed(3)
     B, S, C = 6, 17, 6
     z, nn_out, sf = torch.randn(B, S, C, generator=g), torch.randn(B, S, 2 * C, generator=g) * 0.6, torch.randn(C, generator=g) * 0.4
+    if zero_sf:          # exp(0) = 1 is exactly the clamp bound (coupling_layer.py:82): torch passes the gradient there
+        sf = torch.zeros_like(sf)
     wz, wl = torch.randn(B, S, C, generator=g), torch.randn(B, generator=g)
     mask = torch.zeros(1, C)
     mask[0, :3] = 1.0

@@ -45,8 +45,9 @@ def run(impl, tmp, extra):
 def test_set_modeling_training_matches_cpu_reference(tmp_path):
     tmp = str(tmp_path)
     init = os.path.join(tmp, "init.pt")
-    ref = run("reference", tmp, ["--state-out", init])
-    gpu = run("b200", tmp, ["--state-in", init])
+    f_ref, f_gpu = os.path.join(tmp, "final_ref.pt"), os.path.join(tmp, "final_gpu.pt")
+    ref = run("reference", tmp, ["--state-out", init, "--final-state-out", f_ref])
+    gpu = run("b200", tmp, ["--state-in", init, "--final-state-out", f_gpu])
 
     assert ref["device"] == "cpu" and gpu["device"].startswith("cuda")
     # the reference run used only reference modules; the patched run got the drop-in layers under the same names
@@ -68,7 +69,33 @@ def test_set_modeling_training_matches_cpu_reference(tmp_path):
     for a, b in zip(ref["eval"], gpu["eval"]):
         assert abs(a["bpd"] - b["bpd"]) <= 1e-3, (a, b)
 
-    # trained parameters: per-tensor |.|-sums within 1e-3 relative (20 RAdam steps from identical starting points)
-    for name, want in ref["final_param_abs_sum"].items():
-        got = gpu["final_param_abs_sum"][name]
-        assert abs(got - want) <= 1e-3 * abs(want) + 1e-5, "%s: %r vs %r" % (name, got, want)
+    # trained parameters: what 20 RAdam steps changed, tensor by tensor.  delta = final - initial; the GPU run's delta must
+    # match the CPU reference's in relative L2 norm: 5e-2 over all parameters together, 0.25 for every single tensor (an
+    # Adam-type update lr * m / sqrt(v) amplifies rounding noise where the true gradient is ~0, so this is not a 1e-4 check;
+    # a wrong gradient of one tensor - e.g. the clamp-boundary derivative of scaling_factor this test found - shows as ~1).
+    import torch
+    s0, sr, sg = torch.load(init), torch.load(f_ref), torch.load(f_gpu)
+    assert set(sr) == set(sg)
+    num = den = 0.0
+    worst = []
+    for name in sr:
+        if not sr[name].dtype.is_floating_point:
+            continue
+        dr, dg = (sr[name].double() - s0[name].double()), (sg[name].double() - s0[name].double())
+        n, d = float((dg - dr).norm()) ** 2, float(dr.norm()) ** 2
+        num, den = num + n, den + d
+        if d > 1e-16:
+            worst.append(((n / d) ** 0.5, name))
+        else:
+            assert n <= 1e-12, "%s moved on the GPU (%.3e) but not in the reference" % (name, n ** 0.5)
+    worst.sort(reverse=True)
+    report = "\n".join("%.3e  %s" % w for w in worst[:8])
+    assert (num / den) ** 0.5 <= 5e-2, "parameter updates differ: global relative L2 %.3e\n%s" % ((num / den) ** 0.5, report)
+    # The (mixture_)scaling_factor tensors (4 and 32 numbers per layer) get a looser bound: with a freshly initialised
+    # network raw = nn_out is ~1e-3 and d/dsf [tanh(raw / max(e^sf, 1)) e^sf] = tanh(raw) - raw sech^2(raw) = O(raw^3) is the
+    # difference of two nearly equal fp32 numbers - in the reference's autograd (two separately accumulated sums) as much
+    # as in the kernel - so their first updates are rounding noise through lr * m / sqrt(v) in BOTH runs (measured 0.1-0.4).
+    for err, name in worst:
+        bound = 0.6 if name.endswith("scaling_factor") else 0.25
+        assert err <= bound, "parameter update of %s differs (%.3e > %.2f):\n%s" % (name, err, bound, report)
+    print("parameter-update agreement: global rel L2 %.3e; worst tensors:\n%s" % ((num / den) ** 0.5, report))
