@@ -215,21 +215,22 @@ def run_gpu(args, rank, local_rank, world):
     tokens = W.lm_tokens(B, S, V, seed=rank).to(dev)
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     nn_outs = [torch.randn(B, S, D * (2 + 3 * K), device=dev, generator=gen) * 0.5 for _ in prm.blocks]
-    acc = torch.zeros(2, dtype=torch.float64, device=dev)
+    from categoricalnf_b200.sharding import LogLikAllReducer
+    # (sum log-likelihood, count) of every step: produced by the epilogue of the step's last kernel (the prior log-prob, which
+    # also adds ldj), all-reduced over the ranks on a communication stream - nothing is queued on the compute stream for it
+    reducer = LogLikAllReducer(dev, slots=4)
 
     def barrier():
+        reducer.finish()
         if distributed:
             dist.barrier()
         torch.cuda.synchronize()
 
     def step(i, time_mix=False):
-        z, ldj, logp = path.forward(tokens, nn_outs=nn_outs, seed=rank, offset=i * B * S * D, time_mix=time_mix)
-        ll = ldj + logp
-        acc[0] = ll.sum(dtype=torch.float64)
-        acc[1] = float(B)
-        if distributed:
-            dist.all_reduce(acc)
-        return ldj, logp
+        z, ldj, ll = path.forward(tokens, nn_outs=nn_outs, seed=rank, offset=i * B * S * D, time_mix=time_mix,
+                                  total=reducer.slot())
+        reducer.reduce()
+        return ldj, ll
 
     for i in range(args.warmup):
         step(i)
@@ -243,13 +244,16 @@ def run_gpu(args, rank, local_rank, world):
     barrier()
     ev0.record()
     for i in range(args.steps):
-        ldj, logp = step(args.warmup + i, time_mix=True)
+        ldj, ll = step(args.warmup + i, time_mix=True)
+    reducer.finish()          # the timed region ends when the last step's all-reduce has landed
     ev1.record()
     barrier()
     ms_total = ev0.elapsed_time(ev1)
     launches = ops.launch_count() - launches0
     mix_ms = [a.elapsed_time(b) for a, b in path.mix_events]
-    bpd_gpu = W.bits_per_dim(ldj, logp, S)
+    bpd_gpu = W.bits_per_dim(ll, torch.zeros_like(ll), S)
+    pair = reducer.result(reducer.step - 1)          # global (sum log-likelihood, count) of the last step
+    bpd_global = float(-pair[0] / (pair[1] * S) * 1.4426950408889634)
     ops.check_status(dev, "bench value leg")
 
     # ---- e2e: module API from pinned host tokens -------------------------------------------------
@@ -278,7 +282,9 @@ def run_gpu(args, rank, local_rank, world):
     graphed = None
     if not args.eager_e2e:
         from categoricalnf_b200.layers.flows import GraphedFlowForward
-        graphed = GraphedFlowForward(model, log_prior=lambda z, pad: ops.logistic_logprob(z, pad=pad)[0])
+        pair_static = torch.zeros(2, dtype=torch.float64, device=dev)      # written by the graph's last kernel every replay
+        graphed = GraphedFlowForward(model, log_likelihood=lambda z, ldj, pad: ops.logistic_logprob(z, pad=pad, add=ldj,
+                                                                                                     total=pair_static)[0])
     if graphed is not None:
         try:      # capture now; a box where the capture fails still gets an e2e number (launch by launch)
             dev_tokens[0].copy_(host_tokens[0])
@@ -308,17 +314,16 @@ def run_gpu(args, rank, local_rank, world):
             # (check_nan=True) it travels to the host with the step's result and is examined when that result is consumed
             if graphed is not None:
                 # whole forward + prior log-likelihood replayed from one CUDA graph (tokens copied into its static buffer)
+                slot = reducer.slot()
                 z, ldj, ll = graphed(dev_tokens[j])
                 consumed[j].record(cur)
+                if distributed:
+                    slot.copy_(pair_static, non_blocking=True)
             else:
                 z, ldj = model(dev_tokens[j], check_nan=False)
                 consumed[j].record(cur)
-                logp, _ = ops.logistic_logprob(z)
-                ll = ldj + logp
-            if distributed:
-                acc[0] = ll.sum(dtype=torch.float64)
-                acc[1] = float(B)
-                dist.all_reduce(acc)
+                ll, _ = ops.logistic_logprob(z, add=ldj, total=reducer.slot())
+            reducer.reduce()                      # 16-byte all-reduce on the communication stream (no-op at N = 1)
             host_ll[j].copy_(ll, non_blocking=True)
             host_status[j].copy_(status_dev, non_blocking=True)
             result[j].record(cur)
@@ -339,6 +344,7 @@ def run_gpu(args, rank, local_rank, world):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     e2e_run(args.steps)
+    reducer.finish()
     e1.record()
     barrier()
     e2e_ms_total = e0.elapsed_time(e1)
@@ -379,7 +385,9 @@ def run_gpu(args, rank, local_rank, world):
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                          "mean_launch_ms": mix_ms_mean, "launches_timed": len(mix_ms),
                          "share_of_step": mix_ms_mean * len(prm.blocks) / ms_step},
-            "clocks": clk, "bits_per_dim": bpd_gpu, "parity": parity,
+            "clocks": clk, "bits_per_dim": bpd_gpu, "bits_per_dim_all_ranks": bpd_global, "parity": parity,
+            "collective": "one all-reduce of (sum log-likelihood, count) = 16 bytes per step; the pair comes from the epilogue of "
+                          "the step's last kernel (cnf_logistic_logprob add/total) and is reduced on a communication stream",
         }
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(prm)
@@ -447,6 +455,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / reference-parity legs")
     ap.add_argument("--no-graphs", action="store_true", help="skip the records of BASELINE configs 3, 4, 5 (key `configs`)")
+    ap.add_argument("--no-train", action="store_true", help="skip the GraphCNF training-step record")
     ap.add_argument("--graph-steps", type=int, default=5, help="timed steps per graph config (capped by --steps)")
     ap.add_argument("--eager-e2e", action="store_true", help="e2e leg launches kernel by kernel instead of replaying a CUDA graph")
     args = ap.parse_args()

@@ -46,18 +46,21 @@ class Ctx:
         self.distributed = world > 1
         self.steps = max(2, min(args.steps, args.graph_steps))
         self.warmup = 3
-        self.acc = torch.zeros(2, dtype=torch.float64, device=dev)
+        from categoricalnf_b200.sharding import LogLikAllReducer
+        self.reducer = LogLikAllReducer(dev, slots=4)
 
     def barrier(self):
+        self.reducer.finish()
         if self.distributed:
             self.dist.barrier()
         torch.cuda.synchronize()
 
-    def allreduce_ll(self, ll):
-        self.acc[0] = ll.sum(dtype=torch.float64)
-        self.acc[1] = float(ll.numel())
-        if self.distributed:
-            self.dist.all_reduce(self.acc)
+    def loglik(self, ops, z, ldj, pad):
+        """Per-graph log-likelihood ldj + log p(z) and the step's (sum, count) pair from ONE kernel (cnf_logistic_logprob
+        add / total); the pair is all-reduced over the ranks on the communication stream."""
+        ll, _ = ops.logistic_logprob(z, pad=pad, add=ldj, total=self.reducer.slot())
+        self.reducer.reduce()
+        return ll
 
     def timed(self, fn, steps=None):
         """ms per step of ``fn`` (max over ranks)."""
@@ -69,6 +72,7 @@ class Ctx:
         e0.record()
         for _ in range(steps):
             fn()
+        self.reducer.finish()
         e1.record()
         self.barrier()
         t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=self.dev)
@@ -145,9 +149,7 @@ def run_graph_coloring(c: Ctx):
     def step(xi=xc, ai=ac, li=lc):
         with torch.no_grad():
             z, ldj = model(xi, adjacency=ai, length=li)
-            logp, _ = ops.logistic_logprob(z, pad=pad)
-            ll = ldj + logp
-            c.allreduce_ll(ll)
+            ll = c.loglik(ops, z, ldj, pad)
         return ll
 
     step()
@@ -244,9 +246,7 @@ def run_molecules(c: Ctx):
             else:
                 z, ldj = model(xi, adjacency=ai, length=li)
             pad = (torch.arange(N, device=dev)[None, :] < li[:, None]).float()
-            logp, _ = ops.logistic_logprob(z, pad=pad)
-            ll = ldj + logp
-            c.allreduce_ll(ll)
+            ll = c.loglik(ops, z, ldj, pad)
         return ll
 
     def fwd_eager():
@@ -346,7 +346,70 @@ def run_molecules(c: Ctx):
         legs4, legs5 = _mol_reference_legs(c, model)
         rec.update(legs4)
         rec5.update(legs5)
+    if not c.args.no_train:
+        records.append(run_molecule_training(c, model, ops))
     return records
+
+
+def run_molecule_training(c: Ctx, model, ops):
+    """Training step of config 4 (general/train.py:148-160 on experiments/molecule_generation/task.py's loss): GLOBAL batch
+    512 sharded over the ranks; forward in training mode, loss = mean over the shard of -(ldj + log p(z)) / length, backward
+    through the backward kernels, gradients all-reduced over NCCL in flat buckets WHILE backward runs
+    (sharding.GradientReducer: per-parameter post-accumulate hooks, communication stream), fused Adam step."""
+    from categoricalnf_b200.sharding import GradientReducer
+    dev, N = c.dev, G.MOL["N"]
+    Bg = G.MOL["B_fwd"]
+    lo, hi = _shard(Bg, c.rank, c.world)
+    B = hi - lo
+    x, adj, length = G.molecules(torch.Generator().manual_seed(200), Bg)
+    xc, ac, lc = x[lo:hi].contiguous().to(dev), adj[lo:hi].contiguous().to(dev), length[lo:hi].contiguous().to(dev)
+    pad3 = (torch.arange(N, device=dev)[None, :] < lc[:, None]).float().unsqueeze(-1)
+    model.train()
+    params = [p for p in model.parameters() if p.requires_grad]
+    n_params = sum(p.numel() for p in params)
+    red = GradientReducer(params, bucket_bytes=32 << 20, profile=True)
+    opt = torch.optim.Adam(params, lr=1e-5, fused=True)
+    state = {}
+
+    def train_step():
+        red.zero_grad()
+        z, ldj = model(xc, adjacency=ac, length=lc)
+        logp = (model.prior_distribution.log_prob(z) * pad3).sum(dim=[1, 2])
+        loss = (-(ldj + logp) / lc.to(ldj.dtype)).mean()
+        loss.backward()
+        red.finish()
+        opt.step()
+        state["loss"] = loss.detach()
+
+    steps = max(2, min(c.steps, 3))
+    try:
+        train_step()
+        n0 = ops.launch_count()
+        train_step()
+        launches = ops.launch_count() - n0
+        torch.cuda.synchronize()
+        red.comm_stats()
+        ms = c.timed(train_step, steps)
+        nbytes, comm_ms, bus = red.comm_stats()
+        nsteps = steps + c.warmup
+        ops.check_status(dev, "bench molecule_generation training")
+        rec = {"name": "molecule_generation_train", "baseline_config": "configs[3], training step", "unit": "graphs/s",
+               "metric": "GraphCNF training step (fwd + bwd + gradient all-reduce + Adam) graphs/sec",
+               "value": Bg / (ms * 1e-3), "ms_per_step": ms, "steps": steps, "warmup": c.warmup, "scaling": "strong",
+               "global_batch": Bg, "batch_per_gpu": B, "parameters": n_params, "gpu_launches_per_step": launches,
+               "mode": "eager; gradients reduced bucket by bucket on a communication stream while backward runs "
+                       "(%d flat buckets of <= 32 MiB, p.grad = views), fused Adam" % len(red.buckets),
+               "loss": float(state["loss"]), "dtype": "f32 (projections 3xTF32)",
+               "collective": {"kind": "NCCL all-reduce (sum) of the flat gradient buckets, overlapped with backward",
+                              "bytes_per_step": nbytes / nsteps if c.world > 1 else 0,
+                              "comm_stream_ms_per_step": comm_ms / nsteps if c.world > 1 else 0.0,
+                              "bus_GBps": bus, "bus_formula": "2 (N-1) / N x bytes / time on the communication stream"}}
+    finally:
+        red.close()
+        model.eval()
+        for p in params:
+            p.grad = None
+    return rec
 
 
 def _shard(n, rank, world):
@@ -426,6 +489,8 @@ def _mol_reference_legs(c, model):
 
 
 def run_all(args, rank, world, dev, dist, clock_sampler=None):
+    if not hasattr(args, "no_train"):
+        args.no_train = False
     c = Ctx(args, rank, world, dev, dist)
     records = []
     for fn in (run_graph_coloring, run_molecules):

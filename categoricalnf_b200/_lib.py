@@ -104,7 +104,7 @@ class LogisticLogprobArgs(C.Structure):
     _fields_ = [
         ("B", C.c_int64), ("S", C.c_int64), ("C", C.c_int32),
         ("x", vp), ("pad", vp), ("mu", C.c_float), ("sigma", C.c_float), ("accumulate", C.c_int32),
-        ("out", vp), ("elementwise", vp),
+        ("out", vp), ("elementwise", vp), ("add", vp), ("total", vp),
     ]
 
 
@@ -340,7 +340,7 @@ ENTRY_POINTS = {
 PLAIN_SYMBOLS = ("cnf_last_error_string", "cnf_abi_version", "cnf_built_for_sm", "cnf_mixcdf_fusable",
                  "cnf_categ_encode_fusable", "cnf_linear_mixcdf_fusable")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 _lib = None
 
 

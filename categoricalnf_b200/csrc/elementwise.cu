@@ -207,13 +207,33 @@ __global__ void actnorm_finalize_kernel(const InitParams p) {
 // --------------------------------------------------------------------------------------------
 struct LogProbParams {
     const float* x; const float* pad; float* out; float* elem;
-    long long n, SC; int C;
+    const float* add; double* total;
+    long long n, SC, B; int C;
     float mu, inv_sigma, log_sigma;
 };
+
+// Block-level tail shared by both log-prob kernels: the block's partial of sum_b out[b] goes to total[0] with ONE double
+// atomic per block (total[1] = number of samples, written once).  This is the (sum log-likelihood, count) pair the ranks
+// all-reduce once per step - produced by the kernel that finishes the log-likelihood instead of by a separate reduction.
+__device__ __forceinline__ void block_total_add(const LogProbParams& p, float part) {
+    if (p.total == nullptr) return;
+    __shared__ float s_part[kThreads / 32];
+    part = warp_sum(part);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < kThreads / 32; ++w) t += (double)s_part[w];
+        if (t != 0.0) atomicAdd(p.total, t);
+        if (blockIdx.x == 0) p.total[1] = (double)p.B;
+    }
+}
 
 __global__ void __launch_bounds__(kThreads) logistic_logprob_kernel(const LogProbParams p) {
     const long long stride = (long long)gridDim.x * kThreads;
     const long long n_round = (p.n + 31) & ~31ll;
+    float part = 0.f;
     for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n_round; i += stride) {
         const bool in = i < p.n;
         float lp = 0.f;
@@ -223,9 +243,12 @@ __global__ void __launch_bounds__(kThreads) logistic_logprob_kernel(const LogPro
             lp = -(softplus_pm((p.x[i] - p.mu) * p.inv_sigma) + p.log_sigma);
             if (p.elem) p.elem[i] = lp;
             if (p.pad) lp *= p.pad[i / p.C];
+            if (p.add && i == b * p.SC) lp += p.add[b];      // first element of the sample carries add[b] into out[b]
         }
+        part += lp;
         if (p.out) warp_segmented_atomic_add(p.out, b, lp, in);
     }
+    block_total_add(p, part);
 }
 
 // Per-sample sums only, S*C a multiple of 1024: a warp owns 1024 consecutive elements of ONE sample per step (eight
@@ -236,6 +259,7 @@ __global__ void __launch_bounds__(kThreads) logistic_logprob_rows_kernel(const L
     const long long nchunks = p.n >> 10;
     const long long nwarps = (long long)gridDim.x * (kThreads / 32);
     const int c4 = p.C >> 2;   // p.C % 4 == 0 on this path: a 16-byte load never straddles two positions
+    float part = 0.f;          // lane 0: this warp's share of sum_b out[b]
     for (long long w = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); w < nchunks; w += nwarps) {
         const long long base = w << 10;
         float4 v[8];
@@ -250,8 +274,14 @@ __global__ void __launch_bounds__(kThreads) logistic_logprob_rows_kernel(const L
             acc -= s;
         }
         acc = warp_sum(acc);
-        if (lane == 0) atomicAdd(p.out + base / p.SC, acc);
+        if (lane == 0) {
+            const long long b = base / p.SC;
+            if (p.add && base == b * p.SC) acc += p.add[b];      // the sample's first chunk carries add[b] into out[b]
+            atomicAdd(p.out + b, acc);
+            part += acc;
+        }
     }
+    if (p.total != nullptr) block_total_add(p, (lane == 0) ? part : 0.f);
 }
 
 struct SampleParams {
@@ -364,11 +394,14 @@ extern "C" int cnf_logistic_logprob(const cnf_logistic_logprob_args* a, cnf_stre
     CNF_REQUIRE(a != nullptr, "args is NULL");
     CNF_REQUIRE(a->B >= 0 && a->S >= 0 && a->C >= 1 && a->sigma > 0.f, "bad sizes / sigma");
     if (a->out && !a->accumulate) CNF_CUDA(cudaMemsetAsync(a->out, 0, sizeof(float) * (size_t)a->B, stream));
+    if (a->total) CNF_CUDA(cudaMemsetAsync(a->total, 0, 2 * sizeof(double), stream));
+    CNF_REQUIRE(!(a->add || a->total) || (a->out && !a->accumulate), "add / total need `out` with accumulate = 0");
+    CNF_REQUIRE(!a->add || a->add != a->out, "add must not alias out");
     LogProbParams p{};
     p.n = a->B * a->S * a->C;
     if (p.n == 0) return CNF_OK;
     CNF_REQUIRE(a->x && (a->out || a->elementwise), "x is NULL or no output requested");
-    p.x = a->x; p.pad = a->pad; p.out = a->out; p.elem = a->elementwise;
+    p.x = a->x; p.pad = a->pad; p.out = a->out; p.elem = a->elementwise; p.add = a->add; p.total = a->total; p.B = a->B;
     p.SC = a->S * a->C; p.C = a->C; p.mu = a->mu; p.inv_sigma = 1.0f / a->sigma; p.log_sigma = logf(a->sigma);
     if (p.out != nullptr && p.elem == nullptr && (p.SC & 1023) == 0 && (p.C & 3) == 0 &&
         (reinterpret_cast<uintptr_t>(p.x) & 15) == 0) {

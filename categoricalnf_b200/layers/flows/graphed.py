@@ -17,10 +17,13 @@ from ... import ops
 
 class GraphedFlowForward:
 
-    def __init__(self, model, log_prior=None):
+    def __init__(self, model, log_prior=None, log_likelihood=None):
         """``log_prior(z, channel_padding_mask | None) -> [B]`` per-sample prior log-likelihood, e.g.
-        ``lambda z, pad: ops.logistic_logprob(z, pad=pad)[0]``; None: the third return value is None."""
-        self.model, self.log_prior = model, log_prior
+        ``lambda z, pad: ops.logistic_logprob(z, pad=pad)[0]``; None: the third return value is None.
+        ``log_likelihood(z, ldj, channel_padding_mask | None) -> [B]`` instead finishes the log-likelihood itself, e.g.
+        ``lambda z, ldj, pad: ops.logistic_logprob(z, pad=pad, add=ldj, total=pair)[0]`` (one kernel, which also leaves the
+        (sum, count) pair of the step's all-reduce in the static tensor ``pair``)."""
+        self.model, self.log_prior, self.log_likelihood = model, log_prior, log_likelihood
         self.graphs = {}
         self.captures = 0
         self._tensors = list(model.parameters()) + list(model.buffers())
@@ -36,6 +39,8 @@ class GraphedFlowForward:
     def _run(self, st):
         extra = {} if st["noise"] is None else {"u_noise": st["noise"]}
         z, ldj = self.model(st["x"], check_nan=False, **extra, **st["kwargs"])[:2]
+        if self.log_likelihood is not None:
+            return z, ldj, self.log_likelihood(z, ldj, st["kwargs"].get("channel_padding_mask"))
         if self.log_prior is None:
             return z, ldj, None
         return z, ldj, ldj + self.log_prior(z, st["kwargs"].get("channel_padding_mask"))

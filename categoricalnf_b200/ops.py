@@ -410,8 +410,12 @@ def categ_decode(z, table, category_prior):
     return out
 
 
-def logistic_logprob(x, *, pad=None, mu=0.0, sigma=1.0 / 1.81, reduce=True, elementwise=False, out=None):
-    """K7.  Returns per-sample sums [B] (``reduce``) and/or the element-wise log-density."""
+def logistic_logprob(x, *, pad=None, mu=0.0, sigma=1.0 / 1.81, reduce=True, elementwise=False, out=None, add=None, total=None):
+    """K7.  Returns per-sample sums [B] (``reduce``) and/or the element-wise log-density.
+
+    ``add`` [B] (e.g. the flow's ldj): the returned per-sample values are ``add + log_prob`` - the per-sample
+    log-likelihood - written by the same kernel.  ``total`` (float64 [2], CUDA): receives ``(sum_b result[b], B)``, the pair
+    the ranks all-reduce once per step (``sharding.LogLikAllReducer``), from the kernel's epilogue - no separate reduction."""
     x = _f32(x, "x")
     shape = x.shape
     x3 = x.reshape(shape[0], -1, shape[-1]) if x.dim() >= 2 else x.reshape(1, 1, -1)
@@ -420,11 +424,16 @@ def logistic_logprob(x, *, pad=None, mu=0.0, sigma=1.0 / 1.81, reduce=True, elem
     a = L.LogisticLogprobArgs()
     a.B, a.S, a.C = B, S, Cc
     acc = out is not None
-    res = _f32(out, "out", (B,)) if acc else (torch.empty(B, dtype=torch.float32, device=x.device) if reduce else None)
+    if (add is not None or total is not None) and (acc or not reduce):
+        raise ValueError("add / total need reduce=True and no `out` to accumulate into")
+    res = _ldj(out, B) if acc else (torch.empty(B, dtype=torch.float32, device=x.device) if reduce else None)
     elem = torch.empty_like(x) if elementwise else None
+    add = _opt_f32(add, "add", (B,))
+    if total is not None and (not total.is_cuda or total.dtype != torch.float64 or total.numel() != 2 or not total.is_contiguous()):
+        raise ValueError("total must be a contiguous CUDA float64 tensor with 2 elements")
     a.x, a.pad, a.mu, a.sigma, a.accumulate = _ptr(x3), _ptr(pad), float(mu), float(sigma), int(acc)
-    a.out, a.elementwise = _ptr(res), _ptr(elem)
-    _call("cnf_logistic_logprob", a, x)
+    a.out, a.elementwise, a.add, a.total = _ptr(res), _ptr(elem), _ptr(add), _ptr(total)
+    _call("cnf_logistic_logprob", a, x, (x3, pad, add, total))
     return res, elem
 
 

@@ -291,6 +291,11 @@ CNF_API int cnf_categ_decode(const cnf_categ_decode_args* a, cnf_stream_t stream
  * K7  logistic prior  (layers/flows/distributions.py:129-163)
  * log_prob: out[b] (+)= sum_{s,c} pad * -(softplus(v) + softplus(-v) + log sigma), v=(x-mu)/sigma
  *           (`elementwise` != NULL additionally stores the unreduced values).
+ *           `add` != NULL (accumulate = 0): out[b] = add[b] + log_prob[b] - the per-sample log-likelihood ldj + log p(z)
+ *           (general/task.py / experiments/.../task.py `_calc_loss`) finished by this kernel.
+ *           `total` != NULL: total[0] = sum_b out[b] in float64, total[1] = B - the (sum log-likelihood, count) pair the
+ *           ranks all-reduce once per step (replaces nn.DataParallel's gather, general/mutils.py:243-249), folded into
+ *           the epilogue of the kernel that finishes the log-likelihood.
  * sample:   x = logit(u (1-eps) + eps/2) sigma + mu, u from `u_noise` or Philox.
  * ---------------------------------------------------------------------------------------- */
 typedef struct {
@@ -302,6 +307,8 @@ typedef struct {
     int32_t accumulate;
     float* out;          /* [B] or NULL */
     float* elementwise;  /* [B,S,C] or NULL */
+    const float* add;    /* [B] or NULL; needs out, accumulate = 0, must not alias out (ABI v3) */
+    double* total;       /* [2] or NULL; needs out, accumulate = 0 (ABI v3) */
 } cnf_logistic_logprob_args;
 
 CNF_API int cnf_logistic_logprob(const cnf_logistic_logprob_args* a, cnf_stream_t stream);

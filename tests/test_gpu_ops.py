@@ -273,6 +273,31 @@ def test_logistic_golden():
     assert abs(a.mean().item()) < 5e-3 and abs(a.std().item() - 1.0021) < 1e-2
 
 
+@pytest.mark.parametrize("B,S,C,padded", [(64, 256, 16, False), (33, 64, 16, True), (7, 20, 2, True), (5, 38, 6, False), (1, 1, 1, False)])
+def test_logistic_logprob_loglik_and_total(B, S, C, padded):
+    """``add`` / ``total`` of cnf_logistic_logprob (ABI v3): out = add + log_prob per sample and (sum_b out, B) as a float64
+    pair from the same kernel - both the 1024-element row kernel (first two shapes) and the general one - against the oracle."""
+    from categoricalnf_b200 import ops
+    g = torch.Generator().manual_seed(B + S + C)
+    x = torch.randn(B, S, C, generator=g) * 1.5
+    ldj = torch.randn(B, generator=g) * 100
+    pad = (torch.rand(B, S, generator=g) > 0.3).float() if padded else None
+    want = O.logistic_log_prob(x).double()
+    if padded:
+        want = want * pad.unsqueeze(-1)
+    want = want.sum(dim=[1, 2]) + ldj.double()
+    total = torch.full((2,), 7.0, dtype=torch.float64, device="cuda")          # stale contents must not survive
+    ll, _ = ops.logistic_logprob(dev(x), pad=dev(pad) if padded else None, add=dev(ldj), total=total)
+    assert_close(ll, want, rtol=1e-5, atol=2e-4, what="ldj + log_prob")
+    assert total[1].item() == float(B)
+    assert abs(total[0].item() - want.sum().item()) <= 1e-6 * want.abs().sum().item() + 1e-3
+    assert abs(total[0].item() - ll.double().sum().item()) <= 1e-6 * want.abs().sum().item() + 1e-3
+    ll2, _ = ops.logistic_logprob(dev(x), pad=dev(pad) if padded else None)     # plain call unchanged
+    assert_close(ll2, want - ldj.double(), rtol=1e-5, atol=2e-4, what="log_prob")
+    with pytest.raises(ValueError):
+        ops.logistic_logprob(dev(x), add=dev(ldj), out=torch.zeros(B, device="cuda"))
+
+
 @pytest.mark.parametrize("name", ["encode_lm", "encode_mol_nodes", "encode_mol_edges", "encode_virtual"])
 def test_categ_encode_decode_golden(name):
     from categoricalnf_b200 import ops

@@ -89,3 +89,82 @@ def test_single_process_is_identity():
     acc = SH.allreduce_loglik(ll)
     assert acc.tolist() == [15.0, 6.0]
     assert abs(SH.bits_per_dim(acc, 2.0) - (-15.0 / 12.0 * 1.4426950408889634)) < 1e-12
+
+
+# ---- overlapped gradient reducer / weighted averaging / log-likelihood reducer (world size 2, gloo) --------------------------
+def _model():
+    torch.manual_seed(3)
+    return torch.nn.Sequential(torch.nn.Linear(4, 8), torch.nn.Tanh(), torch.nn.Linear(8, 8), torch.nn.Tanh(), torch.nn.Linear(8, 1))
+
+
+def _reducer_worker(rank, world_size, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world_size)
+    try:
+        g = torch.Generator().manual_seed(1)
+        B = 7                                              # ragged: 4 + 3
+        x, y = torch.randn(B, 4, generator=g), torch.randn(B, 1, generator=g)
+        lo, hi = SH.shard_bounds(B, rank, world_size)
+        model = _model()
+        red = SH.GradientReducer(model.parameters(), bucket_bytes=64)       # several buckets
+        assert len(red.buckets) >= 3
+        res = {}
+        for step in range(2):                              # second step: views survive zero_grad()
+            red.zero_grad()
+            loss = ((model(x[lo:hi]) - y[lo:hi]) ** 2).mean()
+            red.weight_loss(loss, hi - lo).backward()
+            assert all(b["issued"] for b in red.buckets)   # every bucket went out from the hooks, during backward
+            red.finish(hi - lo)
+            res["grads%d" % step] = [p.grad.clone() for p in model.parameters()]
+            assert all(p.grad.data_ptr() == red._owner[id(p)][1].data_ptr() for p in model.parameters())
+        # a loop that drops the views (optimizer.zero_grad(set_to_none=True)) still reduces correctly
+        for p in model.parameters():
+            p.grad = None
+        for b in red.buckets:
+            b["flat"].zero_()
+            b["pending"], b["issued"] = len(b["params"]), False
+        loss = ((model(x[lo:hi]) - y[lo:hi]) ** 2).mean()
+        red.weight_loss(loss, hi - lo).backward()
+        red.finish(hi - lo)
+        res["grads_dropped"] = [p.grad.clone() for p in model.parameters()]
+        red.close()
+        # simple post-backward form with weights; an EMPTY shard on rank 1
+        model2 = _model()
+        n_local = B if rank == 0 else 0
+        model2.zero_grad()
+        if n_local:
+            ((model2(x) - y) ** 2).mean().backward()
+        SH.allreduce_gradients(model2.parameters(), bucket_bytes=64, local_count=n_local)
+        res["grads_empty"] = [p.grad.clone() for p in model2.parameters()]
+        # log-likelihood pair: rotating slots, reduce, result
+        ll = torch.arange(B, dtype=torch.float64)[lo:hi]
+        llr = SH.LogLikAllReducer("cpu", slots=2)
+        steps = []
+        for k in range(3):
+            slot = llr.slot()
+            slot[0], slot[1] = float(ll.sum()) + k, float(hi - lo)
+            steps.append(llr.reduce())
+            res["ll%d" % k] = llr.result(steps[-1]).clone()
+        out[rank] = res
+    finally:
+        dist.destroy_process_group()
+
+
+def test_overlapped_gradient_reducer_and_weighted_average():
+    world_size, port = 2, _free_port()
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_reducer_worker, args=(world_size, port, out), nprocs=world_size, join=True)
+        res = {k: v for k, v in out.items()}
+    g = torch.Generator().manual_seed(1)
+    B = 7
+    x, y = torch.randn(B, 4, generator=g), torch.randn(B, 1, generator=g)
+    model = _model()
+    ((model(x) - y) ** 2).mean().backward()                # single-process gradient of the GLOBAL mean
+    want = [p.grad for p in model.parameters()]
+    for r in range(world_size):
+        for key in ("grads0", "grads1", "grads_dropped", "grads_empty"):
+            for got, w in zip(res[r][key], want):
+                assert torch.allclose(got, w, atol=1e-6), key
+        for k in range(3):
+            assert res[r]["ll%d" % k].tolist() == [float(sum(range(B))) + 2 * k, float(B)]

@@ -169,8 +169,10 @@ class LMDevicePath:
                                  mixture_scaling_factor=b["msf"])
         return self
 
-    def forward(self, tokens, nn_outs=None, u_noise=None, seed=0, offset=0, time_mix=False, fused=True):
+    def forward(self, tokens, nn_outs=None, u_noise=None, seed=0, offset=0, time_mix=False, fused=True, total=None):
         """-> (z, ldj [B], log_prior [B]).  ``nn_outs`` None evaluates the stand-in net with torch.
+        ``total`` (float64 [2] on the device): the last kernel - the prior log-prob - also adds ldj, so the third return
+        value is the per-sample LOG-LIKELIHOOD ldj + log_prior, and leaves (sum log-likelihood, B) in ``total``.
         ``fused``: ActNorm + 1x1 conv of block i+1 run in the epilogue of the kernel producing its
         input (encode for block 0, mixture coupling i otherwise); identical results, 2 launches and
         two passes over z fewer per block."""
@@ -213,6 +215,9 @@ class LMDevicePath:
                 self.mix_events.append((e0, e1))
         if fused:
             ops.ldj_axpy(ldj, alpha=float(S), alpha_dev=self.ldj_const)
+        if total is not None:
+            ll, _ = ops.logistic_logprob(z, add=ldj, total=total)
+            return z, ldj, ll
         logp, _ = ops.logistic_logprob(z)
         return z, ldj, logp
 
