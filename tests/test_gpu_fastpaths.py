@@ -255,3 +255,105 @@ def test_flow_forward_cuda_graph_replay_matches_eager():
         b = graphed(tokens)[1].clone()
         assert torch.isfinite(a).all() and not torch.equal(a, b), "internal noise must differ between replays"
     ops.check_status(dev_, "graphed flow")
+
+
+# ---- full BASELINE size against the ORACLE on a random subset of samples ---------------------------------------------------
+# Samples are independent on the whole path, so the oracle can be run on just the spot-checked samples while the kernel runs
+# the full problem (>= 296 CTAs of work for the persistent schedulers, tiles straddling samples, the full grid-stride loops).
+def _spot(B, n, seed):
+    return torch.randperm(B, generator=torch.Generator().manual_seed(seed))[:n].sort().values
+
+
+def test_mixcdf_full_size_spot_check_vs_oracle():
+    """cnf_mixcdf_fwd / _inv at B 4096 x S 256 x C 16, K 8 (mixcdf_pipe_kernel): 16 random samples vs the oracle,
+    forward (z, ldj, regulariser) and inverse; pure-relative ldj deviation asserted next to the usual tolerance."""
+    from categoricalnf_b200 import ops
+    B, S, C, K = 4096, 256, 16, 8
+    g = torch.Generator(device="cuda").manual_seed(11)
+    z = torch.randn(B, S, C, device="cuda", generator=g)
+    nn_out = torch.randn(B, S, C * (2 + 3 * K), device="cuda", generator=g) * 0.6
+    sf = (torch.randn(C, generator=torch.Generator().manual_seed(1)) * 0.3)
+    msf = (torch.randn(C, K, generator=torch.Generator().manual_seed(2)) * 0.3)
+    mc = [1.0] * 8 + [0.0] * 8
+    zf, ldj, reg = ops.mixcdf(z, nn_out, K, mask_c=mc, scaling_factor=dev(sf), mixture_scaling_factor=dev(msf), reg_max=2.0,
+                              reg_factor=0.5, training=True, want_reg=True)
+    zi, ldji, _ = ops.mixcdf(zf, nn_out, K, mask_c=mc, scaling_factor=dev(sf), mixture_scaling_factor=dev(msf), reverse=True)
+    ops.check_status(z.device)
+    idx = _spot(B, 16, 3)
+    zs, ns = z[idx.cuda()].cpu(), nn_out[idx.cuda()].cpu()
+    m = O.expand_mask(O.channel_mask(C, 0.5), zs)
+    z_ref, ldj_ref, reg_ref = O.mixcdf_coupling(zs, ns, m, K, sf, msf, reg_max=2.0, reg_factor=0.5, training=True)
+    assert_close(zf[idx.cuda()], z_ref, what="z fwd (full size, 16 samples)")
+    assert_close(ldj[idx.cuda()], ldj_ref, rtol=1e-4, atol=2e-4, what="ldj fwd")
+    assert_close(reg[idx.cuda()], reg_ref, rtol=1e-4, atol=2e-4, what="reg ldj")
+    rel = ((ldj[idx.cuda()].cpu().double() - ldj_ref.double()).abs() / ldj_ref.double().abs()).max().item()
+    assert rel <= 1e-4, "pure relative ldj deviation %.3e" % rel
+    z_inv_ref, ldj_inv_ref, _ = O.mixcdf_coupling(zf[idx.cuda()].cpu(), ns, m, K, sf, msf, reverse=True)
+    assert_close(zi[idx.cuda()], z_inv_ref, what="z inv (full size, 16 samples)")
+    assert_close(ldji[idx.cuda()], ldj_inv_ref, rtol=1e-4, atol=2e-4, what="ldj inv")
+
+
+def test_linear_mixcdf_full_size_spot_check_vs_oracle():
+    """cnf_linear_mixcdf_fwd (projection + transform in one tcgen05 kernel) at B 4096 x S 256 x C 16, K 8, H 16."""
+    from categoricalnf_b200 import ops
+    B, S, C, K, H = 4096, 256, 16, 8, 16
+    g = torch.Generator(device="cuda").manual_seed(12)
+    z = torch.randn(B, S, C, device="cuda", generator=g)
+    feat = z * torch.tensor([1.0] * 8 + [0.0] * 8, device="cuda")
+    gw = torch.Generator().manual_seed(4)
+    w = torch.randn(C * (2 + 3 * K), H, generator=gw) * (0.5 / (H / 2) ** 0.5)
+    b = torch.randn(C * (2 + 3 * K), generator=gw) * 0.1
+    sf, msf = torch.randn(C, generator=gw) * 0.3, torch.randn(C, K, generator=gw) * 0.3
+    mc = [1.0] * 8 + [0.0] * 8
+    if not ops.linear_mixcdf_fusable(z, feat, dev(w), K, mask_c=mc):
+        pytest.skip("shape not fusable")
+    zf, ldj, _ = ops.linear_mixcdf(z, feat, dev(w), dev(b), K, mask_c=mc, scaling_factor=dev(sf), mixture_scaling_factor=dev(msf))
+    ops.check_status(z.device)
+    idx = _spot(B, 16, 5)
+    zs = z[idx.cuda()].cpu()
+    m = O.expand_mask(O.channel_mask(C, 0.5), zs)
+    nn_out = torch.nn.functional.linear((zs * m).double(), w.double(), b.double()).float()
+    z_ref, ldj_ref, _ = O.mixcdf_coupling(zs, nn_out, m, K, sf, msf)
+    assert_close(zf[idx.cuda()], z_ref, what="z (full size, 16 samples)")
+    assert_close(ldj[idx.cuda()], ldj_ref, rtol=1e-4, atol=2e-4, what="ldj")
+    rel = ((ldj[idx.cuda()].cpu().double() - ldj_ref.double()).abs() / ldj_ref.double().abs()).max().item()
+    assert rel <= 1e-4, "pure relative ldj deviation %.3e" % rel
+
+
+def test_categ_encode_full_size_spot_check_vs_oracle():
+    """cnf_categ_encode at tokens [4096, 256], V 51, d 16 (categ_encode_tpt_kernel<16>) on explicit noise."""
+    from categoricalnf_b200 import ops
+    import workload as W
+    B, S, V, D = 4096, 256, 51, 16
+    prm = W.lm_params(seed=0)
+    tokens = W.lm_tokens(B, S, V, seed=3)
+    u = torch.rand(B * S, 1, D, generator=torch.Generator().manual_seed(9))
+    ldj0 = torch.zeros(B, device="cuda")
+    z, ldj, _ = ops.categ_encode(dev(tokens), dev(prm.table()), dev(prm.prior), ldj0, noise=dev(u))
+    ops.check_status(z.device)
+    idx = _spot(B, 16, 7)
+    u_s = u.view(B, S, 1, D)[idx].reshape(-1, 1, D)
+    z_ref, ldj_ref, _ = O.categ_encode(tokens[idx], u_s, prm.table(), prm.prior)
+    assert_close(z[idx.cuda()], z_ref, what="z (full size, 16 samples)")
+    assert_close(ldj[idx.cuda()], ldj_ref, rtol=1e-4, atol=2e-4, what="ldj")
+
+
+def test_lm_flow_full_size_spot_check_vs_oracle():
+    """The whole LM path of bench.py at its full size (tokens [4096,256] -> encode -> 8 x [ActNorm, 1x1 conv, mixture coupling]
+    -> prior) through the kernel-level path with fused blocks: 8 random samples against the oracle's composition, incl.
+    bits/dim within 1e-3."""
+    import workload as W
+    B = 4096
+    prm = W.data_init_oracle(W.lm_params(seed=0), seed=0)
+    path = W.LMDevicePath(prm, torch.device("cuda", 0))
+    tokens = W.lm_tokens(B, prm.S, prm.V, seed=21)
+    u = torch.rand(B * prm.S, 1, prm.D, generator=torch.Generator().manual_seed(22))
+    z, ldj, lp = path.forward(tokens.cuda(), u_noise=u.cuda())
+    idx = _spot(B, 8, 23)
+    u_s = u.view(B, prm.S, 1, prm.D)[idx].reshape(-1, 1, prm.D)
+    z_ref, ldj_ref, lp_ref = W.lm_oracle_forward(prm, tokens[idx], u_s)
+    assert_close(z[idx.cuda()], z_ref, what="z (full size, 8 samples)")
+    assert_close(ldj[idx.cuda()], ldj_ref, rtol=1e-4, atol=2e-4, what="ldj")
+    assert_close(lp[idx.cuda()], lp_ref, rtol=1e-4, atol=2e-4, what="log prior")
+    bpd, bpd_ref = W.bits_per_dim(ldj[idx.cuda()].cpu(), lp[idx.cuda()].cpu(), prm.S), W.bits_per_dim(ldj_ref, lp_ref, prm.S)
+    assert abs(bpd - bpd_ref) <= 1e-3

@@ -399,3 +399,58 @@ def test_graphcnf_cuda_graph_replay_matches_eager():
         z_r, ldj_r = graphed(x, adj, length)          # internal noise: finite, different draw
         assert torch.isfinite(ldj_r).all() and not torch.equal(ldj_r, ldj)
     assert 1 <= graphed.captures <= 5
+
+
+# ---- BASELINE configs 3 / 4 at FULL size: random samples against the oracle / the unmodified reference ---------------------
+def test_graph_node_flow_full_size_spot_check_vs_oracle():
+    """Config 3 (B 1024, N 20, 8 flows, hidden 384, 4 layers, K 8): the model runs the whole batch, 8 random graphs are
+    recomputed by the oracle on the same noise (graphs are independent samples)."""
+    import graph_workloads as G
+    dev_ = torch.device("cuda", 0)
+    model = G.build_gc_model(dev_, seed=0)
+    x, adj, length = G.gc_graphs(torch.Generator().manual_seed(5), G.GC["B"])
+    x0, a0, l0 = G.gc_graphs(torch.Generator().manual_seed(7), G.GC["init_batch"])
+    G.data_init(model, x0.cuda(), a0.cuda(), l0.cuda())
+    B, N = x.shape
+    u = torch.rand(B * N, 1, 2, generator=torch.Generator().manual_seed(6))
+    with torch.no_grad():
+        z, ldj = model(x.cuda(), adjacency=adj.cuda(), length=length.cuda(), u_noise=u.cuda())
+    idx = torch.randperm(B, generator=torch.Generator().manual_seed(8))[:8].sort().values
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    u_s = u.view(B, N, 1, 2)[idx].reshape(-1, 1, 2)
+    z_ref, ldj_ref = GO.graph_node_flow(sd, x[idx], adj[idx], length[idx], u_s, num_flows=G.GC["flows"], num_layers=G.GC["layers"],
+                                        num_mixtures=G.GC["K"])
+    assert_close(z[idx.cuda()], z_ref, rtol=1e-4, atol=2e-5, what="z (full size, 8 graphs)")
+    assert_close(ldj[idx.cuda()], ldj_ref, rtol=1e-4, atol=2e-4, what="ldj")
+
+
+@pytest.mark.skipif(not __import__("workload").reference_available(), reason="baseline/_ref absent (tools/vendor_reference.sh)")
+def test_graphcnf_full_size_spot_check_vs_reference():
+    """Config 4 (GraphCNF at the Zinc shape, batch 512 on one GPU): 4 random molecules recomputed by the UNMODIFIED reference
+    model (baseline/_ref, state dict loaded by name) on the same noise; and config 5's reverse pass on 2 sets of latents."""
+    import graph_workloads as G
+    dev_ = torch.device("cuda", 0)
+    N = G.MOL["N"]
+    P = N * (N - 1) // 2
+    model = G.build_mol_model(dev_, seed=0)
+    x0, a0, l0 = G.molecules(torch.Generator().manual_seed(7), G.MOL["init_batch"])
+    G.data_init(model, x0.cuda(), a0.cuda(), l0.cuda())
+    B = 512
+    x, adj, length = G.molecules(torch.Generator().manual_seed(11), B)
+    gen = torch.Generator().manual_seed(12)
+    un, ue, uv = torch.rand(B * N, 1, 6, generator=gen), torch.rand(B * P, 1, 2, generator=gen), torch.rand(B * P, 1, 2, generator=gen)
+    with torch.no_grad():
+        z, ldj = model(x.cuda(), adjacency=adj.cuda(), length=length.cuda(), u_noise=un.cuda(), u_noise_edges=ue.cuda(),
+                       u_noise_virtual=uv.cuda())
+    idx = torch.randperm(B, generator=torch.Generator().manual_seed(13))[:4].sort().values
+    ref = G.build_reference_like(model, "mol")
+    draws = iter([un.view(B, N, 1, 6)[idx].reshape(-1, 1, 6), ue.view(B, P, 1, 2)[idx].reshape(-1, 1, 2),
+                  uv.view(B, P, 1, 2)[idx].reshape(-1, 1, 2)])
+    for e in G.reference_encodings(ref, "mol"):
+        e.prior_distribution.distribution.sample = lambda sample_shape=torch.Size(): next(draws)
+    with torch.no_grad():
+        z_ref, ldj_ref = ref(x[idx], adjacency=adj[idx], length=length[idx])
+    assert_close(z[idx.cuda()], z_ref, rtol=1e-4, atol=4e-5, what="z nodes (full size, 4 molecules)")
+    assert_close(ldj[idx.cuda()], ldj_ref, rtol=1e-4, atol=5e-4, what="ldj")
+    rel = ((ldj[idx.cuda()].cpu().double() - ldj_ref.double()).abs() / ldj_ref.double().abs()).max().item()
+    assert rel <= 1e-4, "pure relative ldj deviation %.3e" % rel
