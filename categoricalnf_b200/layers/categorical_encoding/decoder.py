@@ -1,6 +1,7 @@
 """Embedding factory and the linear decoder of the categorical encodings
-(reference layers/categorical_encoding/decoder.py:11-63).  Dense ``nn.Linear`` stacks - library
-GEMMs - with the reference's parameter names (``layers.inp_layer.0.*``, ``layers.main_net.<i>.*``).
+(reference layers/categorical_encoding/decoder.py:11-63).  The decoder MLP is a ``LinearNet`` of ``TCLinear`` layers (the
+tcgen05 projection kernel, GELU in its epilogue) with the reference's parameter names (``layers.inp_layer.0.*``,
+``layers.main_net.<i>.*``).
 """
 import numpy as np
 import torch

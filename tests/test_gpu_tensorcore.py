@@ -263,3 +263,15 @@ def test_linear_presplit_weight(M, K, N):
     ref2 = x.double() @ (1.5 * w.double()).t() + b.double()
     err2 = (y2.double().cpu() - ref2).abs().max().item()
     assert err2 <= 1.5 * tol, "after update: max |err| %.3e" % err2
+    # the reference's RAdam writes weights through p.data (general/radam.py:82): no version bump - the optimiser post-step
+    # hook (ops.param_epoch) is what invalidates the cached split on the evaluation path
+    with torch.no_grad():
+        ops.linear(x.cuda(), wp, b.cuda())                     # cached split of the current weight
+        version = wp._version
+        wp.data.mul_(2.0)
+        assert wp._version == version
+        torch.optim.SGD([wp], lr=0.0).step()
+        y3 = ops.linear(x.cuda(), wp, b.cuda())
+    ref3 = x.double() @ (3.0 * w.double()).t() + b.double()
+    err3 = (y3.double().cpu() - ref3).abs().max().item()
+    assert err3 <= 3.0 * tol, "after a p.data update + optimizer step: max |err| %.3e (stale cached split?)" % err3
