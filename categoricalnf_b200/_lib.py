@@ -337,7 +337,7 @@ ENTRY_POINTS = {
     "cnf_edge_aggregate_bwd": EdgeAggregateBwdArgs,
     "cnf_pair_combine_bwd": PairCombineBwdArgs,
 }
-PLAIN_SYMBOLS = ("cnf_last_error_string", "cnf_abi_version", "cnf_built_for_sm", "cnf_mixcdf_fusable",
+PLAIN_SYMBOLS = ("cnf_last_error_string", "cnf_abi_version", "cnf_built_for_sm", "cnf_mixcdf_fusable", "cnf_mixcdf_path",
                  "cnf_categ_encode_fusable", "cnf_linear_mixcdf_fusable")
 
 ABI_VERSION = 3
@@ -372,6 +372,8 @@ def load():
     lib.cnf_built_for_sm.restype = C.c_int
     lib.cnf_mixcdf_fusable.argtypes = [C.POINTER(MixcdfArgs)]
     lib.cnf_mixcdf_fusable.restype = C.c_int
+    lib.cnf_mixcdf_path.argtypes = [C.POINTER(MixcdfArgs)]
+    lib.cnf_mixcdf_path.restype = C.c_int
     lib.cnf_categ_encode_fusable.argtypes = [C.POINTER(CategEncodeArgs)]
     lib.cnf_categ_encode_fusable.restype = C.c_int
     lib.cnf_linear_mixcdf_fusable.argtypes = [C.POINTER(LinearMixcdfArgs)]

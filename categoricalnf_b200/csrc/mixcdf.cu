@@ -23,7 +23,10 @@
 namespace cnf {
 
 int mixcdf_pipe_try(const cnf_mixcdf_args* a, const MaskView& mask, int reverse, cudaStream_t stream, int* handled);
+int mixcdf_gpipe_try(const cnf_mixcdf_args* a, const MaskView& mask, int reverse, cudaStream_t stream, int* handled);
 bool mixcdf_pipe_fusable(const cnf_mixcdf_args* a, const MaskView& mask, int reverse);
+bool mixcdf_pipe_eligible(const cnf_mixcdf_args* a, const MaskView& mask);
+bool mixcdf_gpipe_eligible(const cnf_mixcdf_args* a, const MaskView& mask);
 
 namespace {
 using namespace mixmath;
@@ -257,7 +260,9 @@ int run(const cnf_mixcdf_args* a, cnf_stream_t stream_, int reverse) {
     static const bool force_generic = getenv("CNF_B200_MIXCDF_GENERIC") != nullptr;   // A/B switch for profiling
     if (p.mask.n_t > 0 && !force_generic) {
         int handled = 0;
-        rc = mixcdf_pipe_try(a, p.mask, reverse, stream, &handled);
+        rc = mixcdf_pipe_try(a, p.mask, reverse, stream, &handled);              // compile-time (K, Ct), thread per element
+        if (rc != CNF_OK || handled) return rc;
+        rc = mixcdf_gpipe_try(a, p.mask, reverse, stream, &handled);             // any K: lane groups on the same pipeline
         if (rc != CNF_OK || handled) return rc;
     }
     CNF_SUPPORTED(a->next_actnorm_bias == nullptr && a->next_actnorm_scales == nullptr && a->next_conv_weight == nullptr,
@@ -308,6 +313,16 @@ extern "C" int cnf_mixcdf_fusable(const cnf_mixcdf_args* a) {
     cnf::MaskView mv{};
     if (force_generic || cnf::build_mask(a->mask, a->C, &mv) != CNF_OK) return 0;
     return cnf::mixcdf_pipe_fusable(a, mv, 0) ? 1 : 0;
+}
+extern "C" int cnf_mixcdf_path(const cnf_mixcdf_args* a) {
+    if (a == nullptr || a->C < 1 || a->C > CNF_MAX_CHANNELS || a->K < 1 || a->K > CNF_MAX_MIXTURES) return -1;
+    static const bool force_generic = getenv("CNF_B200_MIXCDF_GENERIC") != nullptr;
+    cnf::MaskView mv{};
+    if (cnf::build_mask(a->mask, a->C, &mv) != CNF_OK) return -1;
+    if (force_generic || mv.n_t == 0) return 0;
+    if (cnf::mixcdf_pipe_eligible(a, mv)) return 1;
+    if (cnf::mixcdf_gpipe_eligible(a, mv)) return 2;
+    return 0;
 }
 extern "C" int cnf_mixcdf_fwd(const cnf_mixcdf_args* a, cnf_stream_t stream) { return cnf::run(a, stream, 0); }
 extern "C" int cnf_mixcdf_inv(const cnf_mixcdf_args* a, cnf_stream_t stream) { return cnf::run(a, stream, 1); }

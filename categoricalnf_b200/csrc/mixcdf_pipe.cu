@@ -385,6 +385,11 @@ static bool pipe_eligible(const cnf_mixcdf_args* a, const MaskView& mask) {
     return true;
 }
 
+bool mixcdf_pipe_eligible(const cnf_mixcdf_args* a, const MaskView& mask) {
+    const bool fuse = a->next_actnorm_bias || a->next_actnorm_scales || a->next_conv_weight;
+    return pipe_eligible(a, mask) && !(fuse && !(a->K == 8 && mask.n_t == 8 && a->C == 16));
+}
+
 // The fused next-block epilogue is compiled for the LM layout (C = 16, Ct = 8, K = 8), forward only.
 bool mixcdf_pipe_fusable(const cnf_mixcdf_args* a, const MaskView& mask, int reverse) {
     return !reverse && pipe_eligible(a, mask) && a->K == 8 && mask.n_t == 8 && a->C == 16;

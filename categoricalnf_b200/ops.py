@@ -194,6 +194,17 @@ def mixcdf_fusable(z, nn_out, num_mixtures, *, mask_c=None, mask_s=None, preboun
     return bool(L.load().cnf_mixcdf_fusable(C.byref(a)))
 
 
+MIXCDF_PATHS = {0: "generic", 1: "pipe", 2: "gpipe"}
+
+
+def mixcdf_path(z, nn_out, num_mixtures, *, mask_c=None, mask_s=None, prebounded=False):
+    """Which kernel :func:`mixcdf` launches for this shape / mask / alignment: "generic" (staged), "pipe" (TMA pipeline,
+    compile-time K and Ct, thread per element) or "gpipe" (TMA pipeline, lane groups, any K)."""
+    a, keep = _mixcdf_args(z, nn_out, num_mixtures, mask_c, mask_s, None, None, None)
+    a.params_prebounded = int(bool(prebounded))
+    return MIXCDF_PATHS[int(L.load().cnf_mixcdf_path(C.byref(a)))]
+
+
 def mixcdf(z, nn_out, num_mixtures, *, mask_c=None, mask_s=None, pad=None, scaling_factor=None,
            mixture_scaling_factor=None, reverse=False, reg_max=-1.0, reg_factor=1.0, training=False,
            ldj=None, want_reg=False, out=None, prebounded=False, fuse_next=None):

@@ -118,6 +118,10 @@ CNF_API int cnf_mixcdf_inv(const cnf_mixcdf_args* a, cnf_stream_t stream);
 /* 1 when cnf_mixcdf_fwd can apply the fused next-block epilogue (next_* fields) for this shape, mask
  * and alignment, else 0 (the caller then runs cnf_actnorm / cnf_invconv_apply as separate calls). */
 CNF_API int cnf_mixcdf_fusable(const cnf_mixcdf_args* a);
+/* Which kernel cnf_mixcdf_fwd / _inv would launch for these arguments (pointers are only checked for alignment):
+ * 0 staged generic kernel (mixcdf_kernel), 1 TMA pipeline with compile-time (K, Ct) and one thread per element
+ * (mixcdf_pipe_kernel), 2 TMA pipeline with lane groups for any K (mixcdf_gpipe_kernel); -1 invalid arguments. */
+CNF_API int cnf_mixcdf_path(const cnf_mixcdf_args* a);
 
 /* ------------------------------------------------------------------------------------------
  * K3  affine coupling  (layers/flows/coupling_layer.py:53-65, 76-98)

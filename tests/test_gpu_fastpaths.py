@@ -357,3 +357,99 @@ def test_lm_flow_full_size_spot_check_vs_oracle():
     assert_close(lp[idx.cuda()], lp_ref, rtol=1e-4, atol=2e-4, what="log prior")
     bpd, bpd_ref = W.bits_per_dim(ldj[idx.cuda()].cpu(), lp[idx.cuda()].cpu(), prm.S), W.bits_per_dim(ldj_ref, lp_ref, prm.S)
     assert abs(bpd - bpd_ref) <= 1e-3
+
+
+# ---- lane-group TMA pipeline (csrc/mixcdf_gpipe.cu): any K, unaligned transformed runs -----------------------------------
+# (B, S, C, K, mask): K = 64 is the reference's LM default; C = 6 / K = 16 and C = 2 / K = 8 are GraphCNF's node and edge
+# flows (runs of 600 and 104 bytes at offsets that are not multiples of 16); odd B * S leaves a ragged last tile whose z rows
+# are not a multiple of 16 bytes.
+GPIPE_CASES = [
+    (3, 50, 16, 64, "half"),
+    (2, 40, 16, 32, "half"),
+    (5, 38, 6, 16, "half"),
+    (3, 33, 6, 16, "flip"),
+    (7, 21, 2, 8, "half"),
+    (4, 20, 2, 8, "chess"),
+    (3, 19, 4, 10, "half"),
+    (2, 300, 6, 16, "half"),
+    (3, 17, 8, 3, "half"),
+]
+
+
+def _mask_any(kind, C):
+    if kind == "chess":
+        m = O.chess_mask(2)
+        return m, None, m.flatten().tolist()
+    m = O.channel_mask(C, 0.5)
+    if kind == "flip":
+        m = 1 - m
+    return m, m.flatten().tolist(), None
+
+
+@pytest.mark.parametrize("B,S,C,K,kind", GPIPE_CASES)
+@pytest.mark.parametrize("padded", [False, True])
+def test_mixcdf_gpipe_vs_oracle(B, S, C, K, kind, padded):
+    from categoricalnf_b200 import ops
+    z, nn_out, sf, msf = _mix_inputs(B, S, C, K, seed=B * 977 + S + K)
+    mask, mc, ms = _mask_any(kind, C)
+    assert ops.mixcdf_path(dev(z), dev(nn_out), K, mask_c=mc, mask_s=ms) == "gpipe"
+    pad = None
+    if padded:
+        length = torch.randint(S // 2, S + 1, (B,), generator=torch.Generator().manual_seed(S))
+        pad = (torch.arange(S).view(1, S) < length.view(-1, 1)).float().unsqueeze(-1)
+    m = O.expand_mask(mask, z)
+    z_ref, ldj_ref, reg_ref = O.mixcdf_coupling(z, nn_out, m, K, sf, msf, pad=pad, reg_max=2.0, reg_factor=0.5, training=True)
+    zo, ldj, reg = ops.mixcdf(dev(z), dev(nn_out), K, mask_c=mc, mask_s=ms, pad=dev(pad), scaling_factor=dev(sf),
+                              mixture_scaling_factor=dev(msf), reg_max=2.0, reg_factor=0.5, training=True, want_reg=True)
+    ops.check_status(zo.device)
+    assert_close(zo, z_ref, what="z fwd")
+    assert_close(ldj, ldj_ref, rtol=1e-4, atol=2e-4, what="ldj fwd")
+    assert_close(reg, reg_ref, rtol=1e-4, atol=2e-4, what="reg ldj")
+    z_inv_ref, ldj_inv_ref, _ = O.mixcdf_coupling(z_ref, nn_out, m, K, sf, msf, pad=pad, reverse=True)
+    ldj0 = torch.randn(B, generator=torch.Generator().manual_seed(1))
+    zi, ldji, _ = ops.mixcdf(dev(z_ref), dev(nn_out), K, mask_c=mc, mask_s=ms, pad=dev(pad), scaling_factor=dev(sf),
+                             mixture_scaling_factor=dev(msf), reverse=True, ldj=dev(ldj0.clone()))      # accumulate mode
+    assert_close(zi, z_inv_ref, what="z inv")
+    assert_close(ldji, ldj_inv_ref + ldj0, rtol=1e-4, atol=2e-4, what="ldj inv (accumulated)")
+
+
+def test_mixcdf_paths():
+    """Dispatch: compile-time pipeline for the LM layout, lane-group pipeline for other K / unaligned runs, staged generic kernel
+    for non-contiguous masks and rows that are not a multiple of 16 bytes."""
+    from categoricalnf_b200 import ops
+    def path(C, K, mc=None, ms=None, B=2, S=8):
+        z = torch.zeros(B, S, C, device="cuda")
+        return ops.mixcdf_path(z, torch.zeros(B, S, C * (2 + 3 * K), device="cuda"), K, mask_c=mc, mask_s=ms)
+    half = lambda C: [1.0] * (C // 2) + [0.0] * (C - C // 2)
+    assert path(16, 8, half(16)) == "pipe"
+    assert path(16, 64, half(16)) == "gpipe"
+    assert path(6, 16, half(6)) == "gpipe" and path(2, 8, half(2)) == "gpipe"
+    assert path(4, 8, [1.0, 0.0, 1.0, 0.0]) == "generic"          # transformed channels not contiguous
+    assert path(3, 3, [1.0, 0.0, 0.0]) == "generic"               # row of 33 floats: not a multiple of 16 bytes
+
+
+def test_mixcdf_gpipe_k64_large_batch_split_and_roundtrip():
+    """K = 64 at B 256 x S 256 x C 16 (>= 2 CTAs of tiles per SM on the persistent grid): round trip, ldj antisymmetry, batch
+    split, and 8 random samples against the oracle."""
+    from categoricalnf_b200 import ops
+    B, S, C, K = 256, 256, 16, 64
+    g = torch.Generator(device="cuda").manual_seed(3)
+    z = torch.randn(B, S, C, device="cuda", generator=g)
+    nn_out = torch.randn(B, S, C * (2 + 3 * K), device="cuda", generator=g) * 0.6
+    mc = [1.0] * 8 + [0.0] * 8
+    assert ops.mixcdf_path(z, nn_out, K, mask_c=mc) == "gpipe"
+    zf, ldj, _ = ops.mixcdf(z, nn_out, K, mask_c=mc)
+    zr, ldjr, _ = ops.mixcdf(zf, nn_out, K, mask_c=mc, reverse=True)
+    ops.check_status(z.device)
+    assert torch.equal(zf[..., :8], z[..., :8])
+    assert_close(zr, z, rtol=1e-4, atol=2e-5, what="round trip")
+    assert_close(ldjr, -ldj, rtol=1e-4, atol=1e-2, what="ldj antisymmetry")
+    h = B // 2
+    _, l0, _ = ops.mixcdf(z[:h], nn_out[:h], K, mask_c=mc)
+    assert_close(l0, ldj[:h], rtol=1e-5, atol=1e-3, what="batch split")
+    idx = _spot(B, 8, 4)
+    zs, ns = z[idx.cuda()].cpu(), nn_out[idx.cuda()].cpu()
+    m = O.expand_mask(O.channel_mask(C, 0.5), zs)
+    z_ref, ldj_ref, _ = O.mixcdf_coupling(zs, ns, m, K, None, None)
+    assert_close(zf[idx.cuda()], z_ref, what="z fwd (8 samples)")
+    assert_close(ldj[idx.cuda()], ldj_ref, rtol=1e-4, atol=2e-4, what="ldj fwd")
