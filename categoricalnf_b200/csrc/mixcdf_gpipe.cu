@@ -61,8 +61,81 @@ struct GPipeParams {
 
 __device__ __forceinline__ void cons_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kCons) : "memory"); }
 
-template <int NC, bool REV>
-__global__ void __launch_bounds__(kThreadsG) mixcdf_gpipe_kernel(const GPipeParams p) {
+// ---- compile-time lane groups: K = 8 * GT, lane `sub` of a group owns components 8 sub .. 8 sub + 7 ------------------------
+// All 32 lanes of a warp run the element loop in lock step (ragged tails are clamped, padded elements computed and
+// dropped), so the butterflies use the full-warp mask: xor distances below GT never leave the aligned group.
+template <int GT>
+struct FullWarpGroup {
+    int sub;
+    __device__ __forceinline__ float sum(float v) const {
+#pragma unroll
+        for (int d = GT >> 1; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+        return v;
+    }
+    __device__ __forceinline__ float max(float v) const {
+#pragma unroll
+        for (int d = GT >> 1; d > 0; d >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, d));
+        return v;
+    }
+};
+
+// MixPrep of this lane's 8 components.  `rec` = the element's record in shared memory (8-byte aligned), `bnd` = the channel's
+// (2 log2e / max(e^{msf},1), -e^{msf} log2e) table [K].  Same arithmetic as mix_prepare (mixcdf_math.cuh), with the softmax
+// reference point and the normalisation taken over the whole group.
+template <int GT, bool WANT_SPAN>
+__device__ __forceinline__ void mix_prepare_lane(MixPrep<8>& P, const float* rec, const float2* bnd, float fac, float a2,
+                                                 const FullWarpGroup<GT>& g) {
+    constexpr int K = 8 * GT;
+    const float2* lp2 = reinterpret_cast<const float2*>(rec + 2 + 8 * g.sub);
+    const float2* mu2 = lp2 + K / 2;
+    const float2* ms2 = mu2 + K / 2;
+    const float2* bn = bnd + 8 * g.sub;
+    float lp[8], ms[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 a = lp2[i], b = mu2[i], c = ms2[i];
+        lp[2 * i] = a.x; lp[2 * i + 1] = a.y;
+        P.mu[2 * i] = b.x; P.mu[2 * i + 1] = b.y;
+        ms[2 * i] = c.x; ms[2 * i + 1] = c.y;
+    }
+    float m = lp[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) m = fmaxf(m, lp[i]);
+    const float m_l2 = g.max(m) * kLog2e;
+    const f2 one = f2_splat(1.0f), mtwo = f2_splat(-2.0f), l2e = f2_splat(kLog2e), nm = f2_splat(-m_l2);
+    f2 W2 = f2_splat(0.f);
+    float span = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; k += 2) {
+        const float2 b0 = bn[k], b1 = bn[k + 1];
+        float t0, t1;
+        f2_get(f2_mul(f2_make(ms[k], ms[k + 1]), f2_make(b0.x, b1.x)), t0, t1);
+        const f2 r = f2_make(rcp(1.0f + ex2(t0)), rcp(1.0f + ex2(t1)));          // tanh = 1 - 2 / (1 + 2^v)
+        float n0, n1;
+        f2_get(f2_mul(f2_fma(mtwo, r, one), f2_make(b0.y, b1.y)), n0, n1);        // -ls_k * log2(e)
+        float e0, e1;
+        f2_get(f2_mul(f2_make(ex2(n0), ex2(n1)), l2e), e0, e1);
+        P.einv2[k] = e0;
+        P.einv2[k + 1] = e1;
+        if (WANT_SPAN) span += ex2(-n0) + ex2(-n1);
+        float a0, a1;
+        f2_get(f2_fma(f2_make(lp[k], lp[k + 1]), l2e, nm), a0, a1);
+        P.w[k] = ex2(a0);
+        P.w[k + 1] = ex2(a1);
+        W2 = f2_add(W2, f2_make(P.w[k], P.w[k + 1]));
+    }
+    float w0, w1;
+    f2_get(W2, w0, w1);
+    P.iw = rcp(g.sum(w0 + w1));
+    P.span = WANT_SPAN ? g.sum(span) : 0.f;
+    P.t = rec[0];
+    P.log_s = tanh_from_2log2e(rec[1] * a2) * fac;
+}
+
+// GT > 0: K = 8 GT at compile time, full-warp butterflies (forward) - the lean path; GT = 0: run-time K through the
+// LaneGroup helpers of the generic kernel.  NC = components per lane (8, or 4 for K <= 4 at GT = 0).
+template <int NC, bool REV, int GT>
+__global__ void __launch_bounds__(kThreadsG, (GT > 0 ? 3 : 1)) mixcdf_gpipe_kernel(const GPipeParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int C = p.C, K = p.K, PN = p.PN, Ct = p.Ct, TP = p.TP;
     const int par_stage = TP * p.hull;                   // floats
@@ -73,9 +146,11 @@ __global__ void __launch_bounds__(kThreadsG) mixcdf_gpipe_kernel(const GPipePara
     float* s_a2 = s_fac + Ct;                            // [Ct]
     float* s_mfac = s_a2 + Ct;                           // [Ct * K]
     float* s_ma2 = s_mfac + Ct * K;                      // [Ct * K]
-    float* s_ldj = s_ma2 + Ct * K;                       // [2][TP]  (alternating per tile)
+    float2* s_bnd = reinterpret_cast<float2*>(s_ma2 + Ct * K);   // [Ct * K] (2 log2e / max(e^{msf},1), -e^{msf} log2e); 8-byte
+                                                         // aligned: every block before it has an even number of floats
+    float* s_ldj = reinterpret_cast<float*>(s_bnd + Ct * K);   // [2][TP]  (alternating per tile)
     float* s_reg = s_ldj + 2 * TP;                       // [2][TP]
-    uint64_t* full = reinterpret_cast<uint64_t*>(s_reg + 2 * TP + ((2 * Ct + 2 * Ct * K + 4 * TP) & 1));
+    uint64_t* full = reinterpret_cast<uint64_t*>(s_reg + 2 * TP);
     uint64_t* empty = full + p.stages;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -99,6 +174,7 @@ __global__ void __launch_bounds__(kThreadsG) mixcdf_gpipe_kernel(const GPipePara
         const float fac = (p.msf && !p.pre) ? expf(p.msf[(p.c0 + j) * K + k]) : 1.0f;
         s_mfac[i] = fac;
         s_ma2[i] = 2.0f * kLog2e / fmaxf(fac, 1.0f);
+        s_bnd[i] = make_float2(2.0f * kLog2e / fmaxf(fac, 1.0f), -fac * kLog2e);
     }
     for (int i = tid; i < 2 * TP; i += kThreadsG) { s_ldj[i] = 0.f; s_reg[i] = 0.f; }
     __syncthreads();
@@ -131,14 +207,17 @@ __global__ void __launch_bounds__(kThreadsG) mixcdf_gpipe_kernel(const GPipePara
     }
 
     // ---------------- consumer warps: one lane group per (position, transformed channel) -------------
-    LaneGroup g;
-    g.G = p.G;
-    g.sub = tid & (p.G - 1);
-    g.mask = p.G == 32 ? 0xffffffffu : (((1u << p.G) - 1u) << (lane & ~(p.G - 1)));
-    const int gshift = 31 - __clz(p.G);
+    constexpr int kG = GT > 0 ? GT : 1;
+    LaneGroup g;                                 // run-time groups (GT = 0, and the inverse's Newton loop at any GT)
+    g.G = GT > 0 ? GT : p.G;
+    g.sub = tid & (g.G - 1);
+    g.mask = g.G == 32 ? 0xffffffffu : (((1u << g.G) - 1u) << (lane & ~(g.G - 1)));
+    const int gshift = 31 - __clz(g.G);
     const int ngroups = kCons >> gshift;
     const float inv_ct = 1.0f / (float)Ct;
     const bool use_reg = p.use_reg != 0;
+    FullWarpGroup<kG> fg;
+    fg.sub = g.sub;
 
     int stage = 0;
     uint32_t phase = 0;
@@ -152,6 +231,41 @@ __global__ void __launch_bounds__(kThreadsG) mixcdf_gpipe_kernel(const GPipePara
         float* l_reg = s_reg + (it & 1) * TP;
         mbar_wait(&full[stage], phase);
 
+        if constexpr (GT > 0 && !REV) {
+            // ---- forward, K = 8 GT: every lane of the warp takes part in every iteration ----------------------------
+            for (int base = 0; base < nelem; base += ngroups) {
+                const int e_raw = base + (tid >> gshift);
+                const bool in = e_raw < nelem;
+                const int e = in ? e_raw : nelem - 1;
+                const int r = fast_div(e, inv_ct), j = e - r * Ct;
+                const long long pos = pos0 + r;
+                bool active = in;
+                if (p.s_period > 0) {
+                    const int sp = (int)(pos % p.S);
+                    if ((p.cond_s >> (sp % p.s_period)) & 1ull) active = false;      // conditioner position
+                }
+                const float padv = p.pad ? p.pad[pos] : 1.0f;
+                if (padv == 0.0f) active = false;                                  // padded: copied through (times 0) below
+                const int ch = p.c0 + j;
+                const float* rec = par + (size_t)r * p.hull + j * PN;
+                const float x = zt[r * C + ch];
+                MixPrep<8> P;
+                mix_prepare_lane<kG, false>(P, rec, s_bnd + j * K, s_fac[j], s_a2[j], fg);
+                MixEval ev = mix_eval_p<8>(x, P);
+                ev.F = fg.sum(ev.F);
+                ev.G = fg.sum(ev.G);
+                ev.f = fg.sum(ev.f);
+                if (!active || g.sub != 0) continue;      // no shuffle below this line
+                ElemResult res;
+                if (mix_fast_ok(ev)) res = mix_forward_fast<8>(ev, P, use_reg, p.reg_max, p.reg_factor);
+                else res = mix_forward_f64(x, rec, s_mfac + j * K, K, P.log_s, use_reg, p.reg_max, p.reg_factor);
+                zt[r * C + ch] = (padv == 1.0f) ? res.z : fmaf(res.z, padv, x * (1.0f - padv));
+                atomicAdd(&l_ldj[r], res.ldj * padv);
+                if (use_reg) atomicAdd(&l_reg[r], res.reg * padv);
+                if ((res.z != res.z) | (res.ldj != res.ldj))
+                    flag(p.status, (res.z != res.z ? CNF_FLAG_NAN_Z : 0u) | (res.ldj != res.ldj ? CNF_FLAG_NAN_LDJ : 0u));
+            }
+        } else {
         for (int e = tid >> gshift; e < nelem; e += ngroups) {
             const int r = fast_div(e, inv_ct), j = e - r * Ct;
             const long long pos = pos0 + r;
@@ -190,6 +304,7 @@ __global__ void __launch_bounds__(kThreadsG) mixcdf_gpipe_kernel(const GPipePara
             if (use_reg) atomicAdd(&l_reg[r], res.reg * padv);
             if ((res.z != res.z) | (res.ldj != res.ldj))
                 flag(p.status, (res.z != res.z ? CNF_FLAG_NAN_Z : 0u) | (res.ldj != res.ldj ? CNF_FLAG_NAN_LDJ : 0u));
+        }
         }
         cons_barrier();      // every result of the tile is in shared memory
 
@@ -235,22 +350,22 @@ __global__ void __launch_bounds__(kThreadsG) mixcdf_gpipe_kernel(const GPipePara
 
 size_t gpipe_smem(const GPipeParams& p) {
     size_t f = (size_t)p.stages * p.TP * p.hull + (size_t)p.stages * ((p.TP * p.C + 3) & ~3);
-    f += 2 * (size_t)p.Ct + 2 * (size_t)p.Ct * p.K + 4 * (size_t)p.TP + 2;
+    f += 2 * (size_t)p.Ct + 4 * (size_t)p.Ct * p.K + 4 * (size_t)p.TP + 2;
     return f * sizeof(float) + 2 * (size_t)p.stages * sizeof(uint64_t) + 16;
 }
 
-template <int NC, bool REV>
+template <int NC, bool REV, int GT>
 int launch_gpipe(const GPipeParams& p, cudaStream_t stream) {
     const size_t smem = gpipe_smem(p);
-    CNF_CUDA(cudaFuncSetAttribute(mixcdf_gpipe_kernel<NC, REV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CNF_CUDA(cudaFuncSetAttribute(mixcdf_gpipe_kernel<NC, REV, GT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // persistent grid = exactly the CTAs that are resident at once (registers and shared memory both count)
     int per_sm = 0;
-    CNF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mixcdf_gpipe_kernel<NC, REV>, kThreadsG, smem));
+    CNF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mixcdf_gpipe_kernel<NC, REV, GT>, kThreadsG, smem));
     if (per_sm > 4) per_sm = 4;
     CNF_SUPPORTED(per_sm >= 1, "lane-group pipeline: a CTA with %zu bytes of shared memory does not fit an SM", smem);
     long long grid = (long long)per_sm * sm_count();
     if (grid > p.ntiles) grid = p.ntiles;
-    mixcdf_gpipe_kernel<NC, REV><<<(unsigned)grid, kThreadsG, smem, stream>>>(p);
+    mixcdf_gpipe_kernel<NC, REV, GT><<<(unsigned)grid, kThreadsG, smem, stream>>>(p);
     return launch_status(REV ? "mixcdf_gpipe_kernel<inv>" : "mixcdf_gpipe_kernel<fwd>");
 }
 
@@ -286,8 +401,9 @@ static bool gpipe_plan(const cnf_mixcdf_args* a, const MaskView& mask, GPipePara
     if (TP < 4) TP = 4;
     if ((TP * C) % 4 != 0) return false;
     p.TP = TP;
+    // three CTAs per SM (24 consumer warps) matter more than a third stage: the ring of a CTA stays under ~72 KB
     p.stages = 3;
-    if (gpipe_smem(p) > 100 * 1024) p.stages = 2;
+    if (gpipe_smem(p) > 72 * 1024) p.stages = 2;
     if (gpipe_smem(p) > 200 * 1024) return false;
     *out = p;
     return true;
@@ -312,8 +428,18 @@ int mixcdf_gpipe_try(const cnf_mixcdf_args* a, const MaskView& mask, int reverse
     p.pre = a->params_prebounded;
     p.ntiles = (P + p.TP - 1) / p.TP;
     *handled = 1;
-    if (p.K <= 4) return reverse ? launch_gpipe<4, true>(p, stream) : launch_gpipe<4, false>(p, stream);
-    return reverse ? launch_gpipe<8, true>(p, stream) : launch_gpipe<8, false>(p, stream);
+    // forward with K = 8 G and bounded (not pre-bounded) parameters: compile-time lane groups, full-warp butterflies
+    if (!reverse && !p.pre && p.K == 8 * p.G) {
+        switch (p.G) {
+            case 1: return launch_gpipe<8, false, 1>(p, stream);
+            case 2: return launch_gpipe<8, false, 2>(p, stream);
+            case 4: return launch_gpipe<8, false, 4>(p, stream);
+            case 8: return launch_gpipe<8, false, 8>(p, stream);
+            default: break;
+        }
+    }
+    if (p.K <= 4) return reverse ? launch_gpipe<4, true, 0>(p, stream) : launch_gpipe<4, false, 0>(p, stream);
+    return reverse ? launch_gpipe<8, true, 0>(p, stream) : launch_gpipe<8, false, 0>(p, stream);
 }
 
 }  // namespace cnf

@@ -209,6 +209,9 @@ def mixcdf(z, nn_out, num_mixtures, *, mask_c=None, mask_s=None, pad=None, scali
            mixture_scaling_factor=None, reverse=False, reg_max=-1.0, reg_factor=1.0, training=False,
            ldj=None, want_reg=False, out=None, prebounded=False, fuse_next=None):
     """K1/K2.  Returns ``(z_out, ldj[B], reg_ldj[B] | None)``.  ``ldj`` given -> accumulated into.
+    ``scaling_factor`` / ``mixture_scaling_factor`` None = zeros, i.e. tanh bounds e^0 = 1 like a freshly built layer (the
+    module always passes its parameters; the reference's static helper treats None as "no bounding", which is
+    ``prebounded=True`` here).
     ``fuse_next = (bias [C], scales [C], W [C,C])`` applies the next block's ActNorm and 1x1
     convolution to the output row inside the kernel (forward only, see ``mixcdf_fusable``); their
     per-sample-constant ldj terms are NOT added here."""

@@ -450,6 +450,7 @@ def test_mixcdf_gpipe_k64_large_batch_split_and_roundtrip():
     idx = _spot(B, 8, 4)
     zs, ns = z[idx.cuda()].cpu(), nn_out[idx.cuda()].cpu()
     m = O.expand_mask(O.channel_mask(C, 0.5), zs)
-    z_ref, ldj_ref, _ = O.mixcdf_coupling(zs, ns, m, K, None, None)
+    zero = torch.zeros(C), torch.zeros(C, K)       # scaling factors omitted = 0, i.e. bounds e^0 = 1 (a freshly built layer)
+    z_ref, ldj_ref, _ = O.mixcdf_coupling(zs, ns, m, K, zero[0], zero[1])
     assert_close(zf[idx.cuda()], z_ref, what="z fwd (8 samples)")
     assert_close(ldj[idx.cuda()], ldj_ref, rtol=1e-4, atol=2e-4, what="ldj fwd")
