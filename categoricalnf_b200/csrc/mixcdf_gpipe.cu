@@ -51,6 +51,7 @@ struct GPipeParams {
     int TP;        // positions per tile
     int G;         // lanes per element
     int stages;
+    int whole_rows;  // 1: a tile's parameter rows arrive as ONE bulk copy of whole rows (short transformed runs)
     int mis;       // floats between the 16-byte-aligned hull start and the first transformed record
     int hull;      // floats copied per position (multiple of 4)
     int s_period;
@@ -198,8 +199,17 @@ __global__ void __launch_bounds__(kThreadsG, (GT > 0 ? 3 : 1)) mixcdf_gpipe_kern
             if (lane == 0) mbar_arrive_expect_tx(&full[stage], (uint32_t)((rows * p.hull + zbulk) * 4));
             __syncwarp();
             float* dpar = s_par + stage * par_stage;
+            if (p.whole_rows) {
+                // hull = row: the tile's rows are contiguous in memory; chunks of <= 16 KB, one per lane
+                const long long total = (long long)rows * p.hull;
+                for (long long c = (long long)lane * 4096; c < total; c += 32 * 4096) {
+                    const int n = (int)min((long long)4096, total - c);
+                    bulk_load(dpar + c, p.nn + pos0 * row + c, (uint32_t)(n * 4), &full[stage]);
+                }
+            } else {
             for (int r = lane; r < rows; r += 32)
                 bulk_load(dpar + r * p.hull, p.nn + (pos0 + r) * row + off, (uint32_t)(p.hull * 4), &full[stage]);
+            }
             if (lane == 0 && zbulk > 0) bulk_load(dz, p.z + pos0 * C, (uint32_t)(zbulk * 4), &full[stage]);
             if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
@@ -385,22 +395,39 @@ static bool gpipe_plan(const cnf_mixcdf_args* a, const MaskView& mask, GPipePara
     GPipeParams p{};
     p.C = C; p.K = K; p.PN = PN; p.Ct = Ct; p.c0 = mask.c0;
     const int L = Ct * PN;
-    p.mis = (mask.c0 * PN) & 3;
-    p.hull = (p.mis + L + 3) & ~3;
     const int NC = K <= 4 ? 4 : 8;
     int G = 1;
     while (NC * G < K) G <<= 1;
     if (G > 32) return false;
     p.G = G;
-    // tile: about two elements per lane group, at most ~24 KB of parameters per stage, z tile a multiple of 16 bytes
-    int elems = 2 * (kCons / G);
-    const int cap = (24 * 1024) / (4 * PN);
-    if (elems > cap) elems = cap;
-    int TP = elems / Ct;
-    TP &= ~3;
-    if (TP < 4) TP = 4;
-    if ((TP * C) % 4 != 0) return false;
-    p.TP = TP;
+    // What one bulk copy brings in per position: the aligned hull of the transformed run - or, when that run is short
+    // (< 512 bytes: C = 2 / K = 8 edge flows, 104 of 208 bytes), the WHOLE row, so that a tile is ONE contiguous copy
+    // instead of hundreds of tiny ones (the TMA engine is request-bound there; the extra sectors were mostly being
+    // fetched anyway, a 104-byte run touches 4-5 of the row's 6.5 sectors).
+    p.whole_rows = (L * 4 < 512) ? 1 : 0;
+    if (p.whole_rows) {
+        p.mis = mask.c0 * PN;
+        p.hull = C * PN;
+    } else {
+        p.mis = (mask.c0 * PN) & 3;
+        p.hull = (p.mis + L + 3) & ~3;
+    }
+    // tile: a whole number of elements per lane group (1 or 2 rounds), <= ~32 KB of parameters per stage, z tile a
+    // multiple of 16 bytes
+    const int ngroups = kCons / G;
+    const size_t cap = (p.whole_rows ? 48 : 32) * 1024;
+    int best = 0;
+    float best_eff = 0.f;
+    for (int tp = 4; tp <= 1024; tp += 4) {
+        if ((size_t)tp * p.hull * 4 > cap && best) break;
+        if ((tp * C) % 4 != 0) continue;
+        const int elems = tp * Ct, rounds = (elems + ngroups - 1) / ngroups;
+        if (rounds > 2 && best) break;
+        const float eff = (float)elems / (float)(rounds * ngroups);      // busy lane groups in the tile's last round
+        if (eff >= best_eff - 0.02f) { best = tp; best_eff = eff > best_eff ? eff : best_eff; }
+    }
+    if (!best) return false;
+    p.TP = best;
     // three CTAs per SM (24 consumer warps) matter more than a third stage: the ring of a CTA stays under ~72 KB
     p.stages = 3;
     if (gpipe_smem(p) > 72 * 1024) p.stages = 2;
