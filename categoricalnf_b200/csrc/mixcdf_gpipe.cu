@@ -87,17 +87,24 @@ template <int GT, bool WANT_SPAN>
 __device__ __forceinline__ void mix_prepare_lane(MixPrep<8>& P, const float* rec, const float2* bnd, float fac, float a2,
                                                  const FullWarpGroup<GT>& g) {
     constexpr int K = 8 * GT;
-    const float2* lp2 = reinterpret_cast<const float2*>(rec + 2 + 8 * g.sub);
+    // lane `sub` owns the component PAIRS sub, sub + GT, sub + 2 GT, sub + 3 GT (components 2p, 2p + 1): for a fixed i the
+    // lanes of a group read consecutive 8-byte words - no bank conflict inside the group (a lane-contiguous split, 32 bytes
+    // apart, cost 4.6 extra wavefronts per load: r02b ncu)
+    const float2* lp2 = reinterpret_cast<const float2*>(rec + 2) + g.sub;
     const float2* mu2 = lp2 + K / 2;
     const float2* ms2 = mu2 + K / 2;
-    const float2* bn = bnd + 8 * g.sub;
+    const float4* bn4 = reinterpret_cast<const float4*>(bnd) + g.sub;      // two (a2, -mf log2e) entries per pair
     float lp[8], ms[8];
+    float2 bn[8];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const float2 a = lp2[i], b = mu2[i], c = ms2[i];
+        const float2 a = lp2[i * GT], b = mu2[i * GT], c = ms2[i * GT];
+        const float4 d = bn4[i * GT];
         lp[2 * i] = a.x; lp[2 * i + 1] = a.y;
         P.mu[2 * i] = b.x; P.mu[2 * i + 1] = b.y;
         ms[2 * i] = c.x; ms[2 * i + 1] = c.y;
+        bn[2 * i] = make_float2(d.x, d.y);
+        bn[2 * i + 1] = make_float2(d.z, d.w);
     }
     float m = lp[0];
 #pragma unroll
@@ -143,13 +150,14 @@ __global__ void __launch_bounds__(kThreadsG, (GT > 0 ? 3 : 1)) mixcdf_gpipe_kern
     const int z_stage = (TP * C + 3) & ~3;
     float* s_par = reinterpret_cast<float*>(smem_raw);   // [stages][TP * hull]
     float* s_z = s_par + p.stages * par_stage;           // [stages][TP * C]
-    float* s_fac = s_z + p.stages * z_stage;             // [Ct] e^{sf}
+    float2* s_bnd = reinterpret_cast<float2*>(s_z + p.stages * z_stage);   // [Ct * K] (2 log2e / max(e^{msf},1), -e^{msf} log2e);
+                                                         // 16-byte aligned (read as float4 pairs): the blocks before it are
+                                                         // multiples of 4 floats
+    float* s_fac = reinterpret_cast<float*>(s_bnd + Ct * K);   // [Ct] e^{sf}
     float* s_a2 = s_fac + Ct;                            // [Ct]
     float* s_mfac = s_a2 + Ct;                           // [Ct * K]
     float* s_ma2 = s_mfac + Ct * K;                      // [Ct * K]
-    float2* s_bnd = reinterpret_cast<float2*>(s_ma2 + Ct * K);   // [Ct * K] (2 log2e / max(e^{msf},1), -e^{msf} log2e); 8-byte
-                                                         // aligned: every block before it has an even number of floats
-    float* s_ldj = reinterpret_cast<float*>(s_bnd + Ct * K);   // [2][TP]  (alternating per tile)
+    float* s_ldj = s_ma2 + Ct * K;                       // [2][TP]  (alternating per tile)
     float* s_reg = s_ldj + 2 * TP;                       // [2][TP]
     uint64_t* full = reinterpret_cast<uint64_t*>(s_reg + 2 * TP);
     uint64_t* empty = full + p.stages;
