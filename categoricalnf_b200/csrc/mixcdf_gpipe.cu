@@ -142,8 +142,8 @@ __device__ __forceinline__ void mix_prepare_lane(MixPrep<8>& P, const float* rec
 
 // GT > 0: K = 8 GT at compile time, full-warp butterflies (forward) - the lean path; GT = 0: run-time K through the
 // LaneGroup helpers of the generic kernel.  NC = components per lane (8, or 4 for K <= 4 at GT = 0).
-template <int NC, bool REV, int GT>
-__global__ void __launch_bounds__(kThreadsG, (GT > 0 ? 3 : 1)) mixcdf_gpipe_kernel(const GPipeParams p) {
+template <int NC, bool REV, int GT, int MINB>
+__global__ void __launch_bounds__(kThreadsG, MINB) mixcdf_gpipe_kernel(const GPipeParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int C = p.C, K = p.K, PN = p.PN, Ct = p.Ct, TP = p.TP;
     const int par_stage = TP * p.hull;                   // floats
@@ -251,11 +251,18 @@ __global__ void __launch_bounds__(kThreadsG, (GT > 0 ? 3 : 1)) mixcdf_gpipe_kern
 
         if constexpr (GT > 0 && !REV) {
             // ---- forward, K = 8 GT: every lane of the warp takes part in every iteration ----------------------------
-            for (int base = 0; base < nelem; base += ngroups) {
+            // element e -> (position 2a + b, channel j) with e = ((a Ct + j) << 1) | b: ADJACENT lane groups work on the same
+            // channel of two consecutive positions, whose records lie `hull` floats apart (= 16 mod 32 banks at K = 64,
+            // Ct = 8) instead of PN apart (= 2 mod 32: overlapping bank ranges)
+            const int nloop = ((rows + 1) & ~1) * Ct;
+            for (int base = 0; base < nloop; base += ngroups) {
                 const int e_raw = base + (tid >> gshift);
-                const bool in = e_raw < nelem;
-                const int e = in ? e_raw : nelem - 1;
-                const int r = fast_div(e, inv_ct), j = e - r * Ct;
+                const int e = e_raw < nloop ? e_raw : nloop - 1;
+                const int aj = e >> 1;
+                const int a = fast_div(aj, inv_ct), j = aj - a * Ct;
+                const int r_raw = 2 * a + (e & 1);
+                const bool in = e_raw < nloop && r_raw < rows;
+                const int r = r_raw < rows ? r_raw : rows - 1;
                 const long long pos = pos0 + r;
                 bool active = in;
                 if (p.s_period > 0) {
@@ -372,18 +379,18 @@ size_t gpipe_smem(const GPipeParams& p) {
     return f * sizeof(float) + 2 * (size_t)p.stages * sizeof(uint64_t) + 16;
 }
 
-template <int NC, bool REV, int GT>
+template <int NC, bool REV, int GT, int MINB = 1>
 int launch_gpipe(const GPipeParams& p, cudaStream_t stream) {
     const size_t smem = gpipe_smem(p);
-    CNF_CUDA(cudaFuncSetAttribute(mixcdf_gpipe_kernel<NC, REV, GT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CNF_CUDA(cudaFuncSetAttribute(mixcdf_gpipe_kernel<NC, REV, GT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // persistent grid = exactly the CTAs that are resident at once (registers and shared memory both count)
     int per_sm = 0;
-    CNF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mixcdf_gpipe_kernel<NC, REV, GT>, kThreadsG, smem));
+    CNF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mixcdf_gpipe_kernel<NC, REV, GT, MINB>, kThreadsG, smem));
     if (per_sm > 4) per_sm = 4;
     CNF_SUPPORTED(per_sm >= 1, "lane-group pipeline: a CTA with %zu bytes of shared memory does not fit an SM", smem);
     long long grid = (long long)per_sm * sm_count();
     if (grid > p.ntiles) grid = p.ntiles;
-    mixcdf_gpipe_kernel<NC, REV, GT><<<(unsigned)grid, kThreadsG, smem, stream>>>(p);
+    mixcdf_gpipe_kernel<NC, REV, GT, MINB><<<(unsigned)grid, kThreadsG, smem, stream>>>(p);
     return launch_status(REV ? "mixcdf_gpipe_kernel<inv>" : "mixcdf_gpipe_kernel<fwd>");
 }
 
@@ -423,7 +430,10 @@ static bool gpipe_plan(const cnf_mixcdf_args* a, const MaskView& mask, GPipePara
     // tile: a whole number of elements per lane group (1 or 2 rounds), <= ~32 KB of parameters per stage, z tile a
     // multiple of 16 bytes
     const int ngroups = kCons / G;
-    const size_t cap = (p.whole_rows ? 48 : 32) * 1024;
+    // K = 64 (G = 8): two rounds of elements per tile halve the per-tile barrier / ring hand-shake per element and two CTAs
+    // with ~96 registers beat three with 72 (measured, r02: 0.461 -> 0.429 ms at B 1024 x S 256); K = 32 and below are
+    // fastest with one round and three CTAs
+    const size_t cap = (p.whole_rows ? 48 : (G >= 8 ? 52 : 32)) * 1024;
     int best = 0;
     float best_eff = 0.f;
     for (int tp = 4; tp <= 1024; tp += 4) {
@@ -436,9 +446,17 @@ static bool gpipe_plan(const cnf_mixcdf_args* a, const MaskView& mask, GPipePara
     }
     if (!best) return false;
     p.TP = best;
+    if (const char* e = getenv("CNF_GPIPE_TP")) {      // experiment knob
+        const int tp = atoi(e);
+        if (tp >= 4 && tp % 4 == 0 && (tp * C) % 4 == 0) p.TP = tp;
+    }
     // three CTAs per SM (24 consumer warps) matter more than a third stage: the ring of a CTA stays under ~72 KB
     p.stages = 3;
     if (gpipe_smem(p) > 72 * 1024) p.stages = 2;
+    if (const char* e = getenv("CNF_GPIPE_STAGES")) {  // experiment knob
+        const int st = atoi(e);
+        if (st >= 2 && st <= 4) p.stages = st;
+    }
     if (gpipe_smem(p) > 200 * 1024) return false;
     *out = p;
     return true;
@@ -466,10 +484,10 @@ int mixcdf_gpipe_try(const cnf_mixcdf_args* a, const MaskView& mask, int reverse
     // forward with K = 8 G and bounded (not pre-bounded) parameters: compile-time lane groups, full-warp butterflies
     if (!reverse && !p.pre && p.K == 8 * p.G) {
         switch (p.G) {
-            case 1: return launch_gpipe<8, false, 1>(p, stream);
-            case 2: return launch_gpipe<8, false, 2>(p, stream);
-            case 4: return launch_gpipe<8, false, 4>(p, stream);
-            case 8: return launch_gpipe<8, false, 8>(p, stream);
+            case 1: return launch_gpipe<8, false, 1, 3>(p, stream);
+            case 2: return launch_gpipe<8, false, 2, 3>(p, stream);
+            case 4: return launch_gpipe<8, false, 4, 3>(p, stream);
+            case 8: return launch_gpipe<8, false, 8, 2>(p, stream);
             default: break;
         }
     }
