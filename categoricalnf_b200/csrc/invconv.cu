@@ -7,6 +7,9 @@
 #include "cnf_common.cuh"
 
 namespace cnf {
+
+int invconv_tile_try(const cnf_invconv_args* a, cudaStream_t stream, int* handled);      // invconv_tile.cu (C = 16, TMA tiles)
+
 namespace {
 
 constexpr int kThreads = 256;
@@ -259,6 +262,11 @@ extern "C" int cnf_invconv_apply(const cnf_invconv_args* a, cnf_stream_t stream_
     CNF_REQUIRE(p.P == 0 || (a->z && a->z_out), "z / z_out is NULL");
     CNF_REQUIRE(a->z != a->z_out, "invconv cannot run in place");
     const bool aligned = ((reinterpret_cast<uintptr_t>(a->z) | reinterpret_cast<uintptr_t>(a->z_out)) & 15) == 0;
+    if (aligned && p.P > 0) {
+        int handled = 0;
+        const int rc = invconv_tile_try(a, stream, &handled);
+        if (rc != CNF_OK || handled) return rc;
+    }
     const int sms = sm_count();
     auto grid = [&](long long items) {
         long long blocks = (items + kThreads - 1) / kThreads;

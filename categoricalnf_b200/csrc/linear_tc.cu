@@ -345,6 +345,22 @@ int tc_encode_2d(CUtensorMap* map, const void* base, long long inner, long long 
     return CNF_OK;
 }
 
+// fp32 row-major [outer, inner] matrix whose rows are exactly 64 bytes (inner = 16): box [box_outer, 16], 64-byte swizzle
+// (16-byte chunk index ^= (row >> 1) & 3 - a thread per row then reads / writes its row without bank conflicts)
+int tc_encode_2d_rows64(CUtensorMap* map, const void* base, long long outer, int box_outer) {
+    EncodeTiledFn fn = encode_fn();
+    if (fn == nullptr) return fail(CNF_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t dims[2] = {16, (cuuint64_t)outer};
+    const cuuint64_t strides[1] = {64};
+    const cuuint32_t box[2] = {16, (cuuint32_t)box_outer};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(CNF_ERR_CUDA, "cuTensorMapEncodeTiled (64-byte rows) failed with CUresult %d", (int)r);
+    return CNF_OK;
+}
+
 // N split into equal tiles of a multiple of 32 columns, at most 256 each
 void tc_pick_block_n(int N, int* block_n, int* n_tiles) {
     const int nt = (N + 255) / 256;
