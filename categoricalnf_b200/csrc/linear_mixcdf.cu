@@ -24,6 +24,7 @@
 //                   The z tile sits in shared memory (bulk-async load), is updated in place and leaves with
 //                   one bulk-async store; ldj through warp sums and ~1 atomic per (warp, sample).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "cnf_common.cuh"
 #include "mixcdf_math.cuh"
@@ -136,7 +137,11 @@ __device__ __forceinline__ void load_record(uint32_t taddr, float (&rec)[PN]) {
     }
 }
 
-template <int KT, int CT, bool REV, bool STRICT>
+// RESW ("resident weights", in_features <= 32 = one k-block): the weight rows of the transformed channels' records are
+// loaded - and for 3xTF32 split into high / low parts - ONCE per CTA and stay in shared memory; the stage ring then carries
+// only the 16 KB feature tile (+ its low part).  Per tile that removes 32 KB of TMA traffic and two thirds of the operand
+// split work, which the two split warps otherwise do while competing with the epilogue warps for the same issue ports.
+template <int KT, int CT, bool REV, bool STRICT, bool RESW>
 __global__ void __launch_bounds__(kThreadsFused, 1)
 linear_mixcdf_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ CUtensorMap tm_w, const FusedParams p) {
     constexpr int PN = 2 + 3 * KT;
@@ -144,12 +149,14 @@ linear_mixcdf_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_cons
     constexpr int BN = CT * PNP;               // UMMA N: one padded record per transformed channel
     constexpr int kGroups = kEpiWarps / 4;     // channel j of a position is handled by group j % kGroups
     constexpr int kBBytes = BN * 128;
-    constexpr int kHalf = kABytes + kBBytes;
+    constexpr int kHalf = RESW ? kABytes : kABytes + kBBytes;      // bytes one TMA fill of a stage brings in
     constexpr int kStageBytes = STRICT ? 2 * kHalf : kHalf;
+    constexpr int kWBytes = RESW ? (STRICT ? 2 * kBBytes : kBBytes) : 0;   // resident weight block in front of the ring
     static_assert(BN <= 256 && BN % 16 == 0 && CT % 4 == 0, "tile shape");
 
     extern __shared__ unsigned char smem_dyn[];
-    unsigned char* smem = smem_dyn + ((1024u - (smem_addr(smem_dyn) & 1023u)) & 1023u);
+    unsigned char* smem_w = smem_dyn + ((1024u - (smem_addr(smem_dyn) & 1023u)) & 1023u);    // [W hi | W lo] (RESW)
+    unsigned char* smem = smem_w + kWBytes;                                                   // stage ring
     const int C = p.C;
     const int ztile = kBM * C;                                    // floats per z tile
     float* s_z = reinterpret_cast<float*>(smem + p.stages * kStageBytes);   // [kZStages][128 * C]
@@ -172,7 +179,9 @@ linear_mixcdf_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_cons
     uint64_t* tmem_full = ready + p.stages;
     uint64_t* tmem_empty = tmem_full + 2;
     uint64_t* zfull = tmem_empty + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(zfull + kZStages);
+    uint64_t* wfull = zfull + kZStages;        // RESW: the weight block has landed / has been split
+    uint64_t* wready = wfull + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wready + 1);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long t0 = (p.ntiles * (long long)blockIdx.x) / gridDim.x;
@@ -193,6 +202,8 @@ linear_mixcdf_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_cons
             mbar_init(&tmem_empty[s], kEpiWarps);
         }
         for (int s = 0; s < kZStages; ++s) mbar_init(&zfull[s], 1);
+        mbar_init(wfull, 1);
+        mbar_init(wready, 64);
         mbar_fence_init();
     }
     if (warp == 2) tmem_alloc(tmem_slot, 512);
@@ -229,6 +240,11 @@ linear_mixcdf_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_cons
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
+            if constexpr (RESW) {      // the whole weight block, once
+                mbar_arrive_expect_tx(wfull, (uint32_t)kBBytes);
+#pragma unroll
+                for (int j = 0; j < CT; ++j) tma_load_2d(smem_w + j * (PNP * 128), &tm_w, wfull, 0, (p.c0 + j) * PN);
+            }
             for (int it = 0; it < tiles; ++it) {
                 const int m0 = (int)((t0 + it) * kBM);
                 for (int kb = 0; kb < p.k_blocks; ++kb) {
@@ -236,9 +252,11 @@ linear_mixcdf_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_cons
                     unsigned char* sa = smem + stage * kStageBytes;
                     mbar_arrive_expect_tx(&full[stage], (uint32_t)kHalf);
                     tma_load_2d(sa, &tm_h, &full[stage], kb * kBK, m0);
+                    if constexpr (!RESW) {
 #pragma unroll
-                    for (int j = 0; j < CT; ++j)   // weight rows of channel c0+j's record (+ padding rows, ignored)
-                        tma_load_2d(sa + kABytes + j * (PNP * 128), &tm_w, &full[stage], kb * kBK, (p.c0 + j) * PN);
+                        for (int j = 0; j < CT; ++j)   // weight rows of channel c0+j's record (+ padding rows, ignored)
+                            tma_load_2d(sa + kABytes + j * (PNP * 128), &tm_w, &full[stage], kb * kBK, (p.c0 + j) * PN);
+                    }
                     if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -249,6 +267,7 @@ linear_mixcdf_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_cons
             constexpr uint32_t idesc = idesc_tf32(kBM, BN);
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0;
+            if constexpr (RESW) mbar_wait(STRICT ? wready : wfull, 0u);
             for (int it = 0; it < tiles; ++it) {
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
                 tcgen05_fence_after();
@@ -257,13 +276,15 @@ linear_mixcdf_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_cons
                     mbar_wait(STRICT ? &ready[stage] : &full[stage], phase);
                     tcgen05_fence_after();
                     unsigned char* sa = smem + stage * kStageBytes;
-                    const uint64_t da = smem_desc_k128(sa), db = smem_desc_k128(sa + kABytes);
+                    const unsigned char* sb = RESW ? smem_w : sa + kABytes;
+                    const unsigned char* sbl = RESW ? smem_w + kBBytes : sa + kHalf + kABytes;
+                    const uint64_t da = smem_desc_k128(sa), db = smem_desc_k128(sb);
 #pragma unroll
                     for (int k = 0; k < kBK / 8; ++k) {
                         const uint32_t off = (uint32_t)k * 32u;
                         mma_tf32(d, smem_desc_advance(da, off), smem_desc_advance(db, off), idesc, kb > 0 || k > 0);
                         if constexpr (STRICT) {
-                            const uint64_t dal = smem_desc_k128(sa + kHalf), dbl = smem_desc_k128(sa + kHalf + kABytes);
+                            const uint64_t dal = smem_desc_k128(sa + kHalf), dbl = smem_desc_k128(sbl);
                             mma_tf32(d, smem_desc_advance(dal, off), smem_desc_advance(db, off), idesc, true);
                             mma_tf32(d, smem_desc_advance(da, off), smem_desc_advance(dbl, off), idesc, true);
                         }
@@ -282,6 +303,21 @@ linear_mixcdf_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_cons
             const int tt = tid - 64;
             int stage = 0;
             uint32_t phase = 0;
+            if constexpr (RESW) {      // split the resident weight block once
+                mbar_wait(wfull, 0u);
+                float4* hi = reinterpret_cast<float4*>(smem_w);
+                float4* lo = reinterpret_cast<float4*>(smem_w + kBBytes);
+                for (int i = tt; i < (kBBytes >> 4); i += 64) {
+                    const float4 x = hi[i];
+                    float4 h, l;
+                    h.x = rna_tf32(x.x); h.y = rna_tf32(x.y); h.z = rna_tf32(x.z); h.w = rna_tf32(x.w);
+                    l.x = rna_tf32(x.x - h.x); l.y = rna_tf32(x.y - h.y); l.z = rna_tf32(x.z - h.z); l.w = rna_tf32(x.w - h.w);
+                    hi[i] = h;
+                    lo[i] = l;
+                }
+                fence_proxy_async_smem();
+                mbar_arrive(wready);
+            }
             for (int it = 0; it < tiles; ++it) {
                 for (int kb = 0; kb < p.k_blocks; ++kb) {
                     mbar_wait(&full[stage], phase);
@@ -497,37 +533,47 @@ linear_mixcdf_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_cons
 }
 
 template <int KT, int CT>
-size_t fused_smem(int C, int stages, bool strict, int next = 0, int masked = 0) {
+size_t fused_smem(int C, int stages, bool strict, bool resw, int next = 0, int masked = 0) {
     constexpr int PN = 2 + 3 * KT, PNP = padded_record(PN), BN = CT * PNP;
-    const size_t stage = (size_t)(kABytes + BN * 128) * (strict ? 2 : 1);
+    const size_t stage = (size_t)(kABytes + (resw ? 0 : BN * 128)) * (strict ? 2 : 1);
     size_t f = 1024 + stages * stage + (size_t)kZStages * kBM * C * 4;
+    if (resw) f += (size_t)BN * 128 * (strict ? 2 : 1);      // resident weight block (high + low part)
     f += ((size_t)CT * PN + 1 + 3 * (size_t)CT * KT + 1 + (size_t)kEpiWarps * PNP + 2 * CT) * 4;
-    f += (3 * (size_t)stages + 4 + kZStages) * 8 + 256;
+    f += (3 * (size_t)stages + 6 + kZStages) * 8 + 256;
     if (next) f += ((size_t)3 * C + (size_t)C * C + (size_t)(masked ? 4 : 2) * kBM * C) * 4;
     return f;
 }
 
-template <int KT, int CT, bool REV, bool STRICT>
+template <int KT, int CT, bool REV, bool STRICT, bool RESW>
 int launch_fused(const CUtensorMap& tm_h, const CUtensorMap& tm_w, FusedParams p, cudaStream_t stream) {
     constexpr size_t kMaxSmem = 232448;
     const int msk = p.z_masked_out != nullptr;
     int stages = 4;
-    while (stages > 1 && fused_smem<KT, CT>(p.C, stages, STRICT, p.next, msk) > kMaxSmem) --stages;
-    const size_t need = fused_smem<KT, CT>(p.C, stages, STRICT, p.next, msk);
+    while (stages > 1 && fused_smem<KT, CT>(p.C, stages, STRICT, RESW, p.next, msk) > kMaxSmem) --stages;
+    const size_t need = fused_smem<KT, CT>(p.C, stages, STRICT, RESW, p.next, msk);
     CNF_SUPPORTED(need <= kMaxSmem, "fused projection + mixture tile does not fit shared memory");
     p.stages = stages;
     const size_t smem = need;
-    CNF_CUDA(cudaFuncSetAttribute(linear_mixcdf_kernel<KT, CT, REV, STRICT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+    CNF_CUDA(cudaFuncSetAttribute(linear_mixcdf_kernel<KT, CT, REV, STRICT, RESW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)kMaxSmem));
     long long grid = sm_count();
     if (grid > p.ntiles) grid = p.ntiles;
-    linear_mixcdf_kernel<KT, CT, REV, STRICT><<<(unsigned)grid, kThreadsFused, smem, stream>>>(tm_h, tm_w, p);
+    linear_mixcdf_kernel<KT, CT, REV, STRICT, RESW><<<(unsigned)grid, kThreadsFused, smem, stream>>>(tm_h, tm_w, p);
     return launch_status("linear_mixcdf_kernel");
+}
+
+template <int KT, int CT, bool RESW>
+int launch_fused_rs(const CUtensorMap& tm_h, const CUtensorMap& tm_w, const FusedParams& p, int reverse, int strict, cudaStream_t stream) {
+    if (reverse) return strict ? launch_fused<KT, CT, true, true, RESW>(tm_h, tm_w, p, stream) : launch_fused<KT, CT, true, false, RESW>(tm_h, tm_w, p, stream);
+    return strict ? launch_fused<KT, CT, false, true, RESW>(tm_h, tm_w, p, stream) : launch_fused<KT, CT, false, false, RESW>(tm_h, tm_w, p, stream);
 }
 
 template <int KT, int CT>
 int launch_fused_kc(const CUtensorMap& tm_h, const CUtensorMap& tm_w, const FusedParams& p, int reverse, int strict, cudaStream_t stream) {
-    if (reverse) return strict ? launch_fused<KT, CT, true, true>(tm_h, tm_w, p, stream) : launch_fused<KT, CT, true, false>(tm_h, tm_w, p, stream);
-    return strict ? launch_fused<KT, CT, false, true>(tm_h, tm_w, p, stream) : launch_fused<KT, CT, false, false>(tm_h, tm_w, p, stream);
+    // one k-block (in_features <= 32) without the next-block epilogue: the weights stay resident in shared memory
+    static const bool no_resw = getenv("CNF_B200_FUSED_NORESW") != nullptr;      // A/B switch for profiling
+    if (p.k_blocks == 1 && !p.next && !no_resw) return launch_fused_rs<KT, CT, true>(tm_h, tm_w, p, reverse, strict, stream);
+    return launch_fused_rs<KT, CT, false>(tm_h, tm_w, p, reverse, strict, stream);
 }
 
 bool fused_shape_ok(int K, int Ct) { return (K == 8 && (Ct == 8 || Ct == 4)) || (K == 16 && Ct == 4) || (K == 4 && (Ct == 8 || Ct == 4)); }
