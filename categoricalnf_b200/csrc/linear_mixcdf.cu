@@ -43,6 +43,9 @@ constexpr int kBM = 128;
 constexpr int kBK = 32;
 constexpr int kABytes = kBM * 128;
 constexpr int kStageCols = 256;
+#ifndef CNF_FUSED_UNROLL
+#define CNF_FUSED_UNROLL 1      // elements of one thread evaluated one after the other (2: interleaved - A/B build knob)
+#endif
 #ifndef CNF_FUSED_EPI_WARPS
 #define CNF_FUSED_EPI_WARPS 16
 #endif
@@ -84,6 +87,7 @@ struct FusedParams {
     const float* nx_mask;    // [C] mask of the next coupling (1 = conditioner input) or NULL
     float* z_masked_out;     // [P,C] = z_out * nx_mask, or NULL
     int next;                // 1: epilogue enabled
+    uint32_t sleep_ns;       // back-off of the service warps' barrier polls (0: spin)
 };
 
 constexpr int padded_record(int pn) { return pn <= 16 ? 16 : (pn <= 32 ? 32 : 64); }
@@ -96,6 +100,26 @@ __device__ __forceinline__ float rna_tf32(float v) {
 __device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_addr(ssrc)), "r"(bytes)
                  : "memory");
+}
+// mbarrier wait for the SERVICE warps (TMA producer, MMA issuer, operand split): between failed polls the warp sleeps, so
+// that its SYNCS / BRA pairs stop competing with the epilogue warps for the issue port and the MIO queue (with the plain
+// spin the four service warps issued ~4400 polls per tile: 36 % of all warp instructions, mio_throttle the top stall)
+__device__ __forceinline__ void mbar_wait_svc(uint64_t* bar, uint32_t parity, uint32_t sleep_ns) {
+    if (sleep_ns == 0) { mbar_wait(bar, parity); return; }
+    for (;;) {
+        uint32_t ok;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(smem_addr(bar)), "r"(parity)
+            : "memory");
+        if (ok) return;
+        __nanosleep(sleep_ns);
+    }
 }
 __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
 
@@ -248,7 +272,7 @@ linear_mixcdf_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_cons
             for (int it = 0; it < tiles; ++it) {
                 const int m0 = (int)((t0 + it) * kBM);
                 for (int kb = 0; kb < p.k_blocks; ++kb) {
-                    mbar_wait(&empty[stage], phase ^ 1u);
+                    mbar_wait_svc(&empty[stage], phase ^ 1u, p.sleep_ns);
                     unsigned char* sa = smem + stage * kStageBytes;
                     mbar_arrive_expect_tx(&full[stage], (uint32_t)kHalf);
                     tma_load_2d(sa, &tm_h, &full[stage], kb * kBK, m0);
@@ -269,11 +293,11 @@ linear_mixcdf_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_cons
             uint32_t phase = 0, acc_phase = 0;
             if constexpr (RESW) mbar_wait(STRICT ? wready : wfull, 0u);
             for (int it = 0; it < tiles; ++it) {
-                mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
+                mbar_wait_svc(&tmem_empty[acc], acc_phase ^ 1u, p.sleep_ns);
                 tcgen05_fence_after();
                 const uint32_t d = tmem_base + (uint32_t)(acc * kStageCols);
                 for (int kb = 0; kb < p.k_blocks; ++kb) {
-                    mbar_wait(STRICT ? &ready[stage] : &full[stage], phase);
+                    mbar_wait_svc(STRICT ? &ready[stage] : &full[stage], phase, p.sleep_ns);
                     tcgen05_fence_after();
                     unsigned char* sa = smem + stage * kStageBytes;
                     const unsigned char* sb = RESW ? smem_w : sa + kABytes;
@@ -320,7 +344,7 @@ linear_mixcdf_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_cons
             }
             for (int it = 0; it < tiles; ++it) {
                 for (int kb = 0; kb < p.k_blocks; ++kb) {
-                    mbar_wait(&full[stage], phase);
+                    mbar_wait_svc(&full[stage], phase, p.sleep_ns);
                     float4* hi = reinterpret_cast<float4*>(smem + stage * kStageBytes);
                     float4* lo = reinterpret_cast<float4*>(smem + stage * kStageBytes + kHalf);
                     for (int i = tt; i < (kHalf >> 4); i += 64) {
@@ -391,7 +415,7 @@ linear_mixcdf_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_cons
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kStageCols);
 
             float eldj = 0.f, ereg = 0.f;
-#pragma unroll 1
+#pragma unroll CNF_FUSED_UNROLL
             for (int j = g; j < CT; j += kGroups) {
                 const int ch = p.c0 + j;
                 float rec[PN];
@@ -626,6 +650,8 @@ int run_fused(const cnf_linear_mixcdf_args* a, cnf_stream_t stream_, int reverse
     CNF_SUPPORTED(!(p.next && reverse), "the next-block epilogue exists for the forward direction only");
     CNF_REQUIRE(p.next || (a->next_mask == nullptr && a->z_masked_out == nullptr), "next_mask / z_masked_out need the next-block epilogue");
     p.nx_mask = a->next_mask; p.z_masked_out = a->z_masked_out;
+    static const int sleep_ns = getenv("CNF_B200_FUSED_SLEEP_NS") ? atoi(getenv("CNF_B200_FUSED_SLEEP_NS")) : 0;
+    p.sleep_ns = (uint32_t)(sleep_ns > 0 ? sleep_ns : 0);
     CNF_REQUIRE(a->z_masked_out == nullptr || (reinterpret_cast<uintptr_t>(a->z_masked_out) & 15) == 0, "z_masked_out must be 16-byte aligned");
 
     CUtensorMap tm_h, tm_w;
