@@ -121,7 +121,11 @@ __device__ __forceinline__ void mbar_wait_svc(uint64_t* bar, uint32_t parity, ui
         __nanosleep(sleep_ns);
     }
 }
+#ifdef CNF_EXP_NOBARRIER     // timing experiment only (races on the z tile)
+__device__ __forceinline__ void epi_barrier() {}
+#else
 __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
+#endif
 
 // record of one (position, channel): PN consecutive tensor-memory columns of this thread's lane
 template <int PN>
@@ -415,22 +419,30 @@ linear_mixcdf_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_cons
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kStageCols);
 
             float eldj = 0.f, ereg = 0.f;
-#pragma unroll CNF_FUSED_UNROLL
+            constexpr int kUnrollJ = CNF_FUSED_UNROLL;
+#pragma unroll kUnrollJ
             for (int j = g; j < CT; j += kGroups) {
                 const int ch = p.c0 + j;
                 float rec[PN];
                 __syncwarp();
+#ifdef CNF_EXP_NOTMEMLD      // timing experiment only: what do the tensor-memory loads cost?
+#pragma unroll
+                for (int i = 0; i < PN; ++i) rec[i] = zt[(ch + i) & 15] * 0.37f;
+#else
                 load_record<PN>(taddr + (uint32_t)(j * PNP), rec);   // warp-collective: outside the divergent part
+#endif
                 const float x = zt[ch];
                 float out = x;
                 if (active) {
                     const float2* bj = reinterpret_cast<const float2*>(s_bias + j * PN);   // PN is even
+#ifndef CNF_EXP_NOBIAS       // timing experiment only
 #pragma unroll
                     for (int i = 0; i < PN / 2; ++i) {
                         const float2 bv = bj[i];
                         rec[2 * i] += bv.x;
                         rec[2 * i + 1] += bv.y;
                     }
+#endif
                     const float2 fa = s_fa[j];
                     MixPrep<KT> P;
                     mix_prepare<KT, CT, REV>(P, rec, s_bnd + j, fa.x, fa.y);
