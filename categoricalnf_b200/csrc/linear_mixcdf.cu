@@ -209,12 +209,17 @@ linear_mixcdf_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_cons
     uint64_t* zfull = tmem_empty + 2;
     uint64_t* wfull = zfull + 4 * kZStages;    // RESW: the weight block has landed / has been split
     uint64_t* wready = wfull + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wready + 1);
+    uint64_t* zempty = wready + 1;             // direct mode: every epilogue warp has read its values of z stage b
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(zempty + kZStages);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long t0 = (p.ntiles * (long long)blockIdx.x) / gridDim.x;
     const int tiles = (int)((p.ntiles * (long long)(blockIdx.x + 1)) / gridDim.x - t0);
 
+    // Without the next-block epilogue no thread needs another thread's results, so the z tile is read-only shared memory
+    // (loaded by the TMA producer, released through zempty as soon as every warp holds its values in registers) and the
+    // outputs go from registers straight to global memory: no barrier of any kind between the epilogue warps.
+    const bool direct = !p.next;
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tm_h);
         tma_prefetch_desc(&tm_w);
@@ -232,6 +237,7 @@ linear_mixcdf_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_cons
         for (int s = 0; s < 4 * kZStages; ++s) mbar_init(&zfull[s], 1);      // [stage][quadrant]
         mbar_init(wfull, 1);
         mbar_init(wready, 64);
+        for (int s = 0; s < kZStages; ++s) mbar_init(&zempty[s], kEpiWarps);
         mbar_fence_init();
     }
     if (warp == 2) tmem_alloc(tmem_slot, 512);
@@ -286,6 +292,14 @@ linear_mixcdf_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_cons
                             tma_load_2d(sa + kABytes + j * (PNP * 128), &tm_w, &full[stage], kb * kBK, (p.c0 + j) * PN);
                     }
                     if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                }
+                if (direct) {      // the tile's z rows, three tiles deep
+                    const int b = it % kZStages;
+                    mbar_wait_svc(&zempty[b], (uint32_t)(((it / kZStages) & 1) ^ 1), p.sleep_ns);
+                    const long long pos0 = (t0 + it) * kBM;
+                    const int rows = (int)min((long long)kBM, p.P - pos0);
+                    mbar_arrive_expect_tx(&zfull[b * 4], (uint32_t)(rows * C * 4));
+                    bulk_load(s_z + b * ztile, p.z + pos0 * C, (uint32_t)(rows * C * 4), &zfull[b * 4]);
                 }
             }
         }
@@ -390,10 +404,12 @@ linear_mixcdf_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_cons
             mbar_arrive_expect_tx(&zfull[b * 4 + q], (uint32_t)(rows * C * 4));
             bulk_load(s_z + b * ztile + qoff, p.z + posq * C, (uint32_t)(rows * C * 4), &zfull[b * 4 + q]);
         };
-        if (manager) {
+        if (manager && !direct) {
             if (tiles > 0) z_load(0);
             if (tiles > 1) z_load(1);
         }
+        constexpr int kNX = (CT + kGroups - 1) / kGroups;      // transformed channels per thread
+        constexpr int kNC = 8;                                 // conditioner channels copied per thread (C <= 32, CT >= 4)
 
         long long cur_b = -1;
         float acc_ldj = 0.f, acc_reg = 0.f;
@@ -421,7 +437,24 @@ linear_mixcdf_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_cons
                 if ((p.cond_s >> (s_in % p.s_period)) & 1ull) active = false;
             }
             const int qrows = quad_rows(it);
-            if (qrows > 0) mbar_wait(&zfull[zb * 4 + q], (uint32_t)((it / kZStages) & 1));
+            float xs[kNX];
+            if (direct) {
+                mbar_wait(&zfull[zb * 4], (uint32_t)((it / kZStages) & 1));
+#pragma unroll
+                for (int n = 0; n < kNX; ++n) xs[n] = (g + n * kGroups < CT) ? zt[p.c0 + g + n * kGroups] : 0.f;
+                // conditioner channels pass through, times pad (mixture_cdf_layer.py:76,137-138): written right away, so
+                // that nothing but the xs stays in registers across the element math
+#pragma unroll
+                for (int n = 0; n < kNC; ++n) {
+                    const int c = g + n * kGroups;                    // c-th conditioner channel
+                    const int cc = (c < p.c0) ? c : c + CT;           // skip the transformed run
+                    if (c < C - CT && valid) p.z_out[pos * C + cc] = zt[cc] * padv;
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&zempty[zb]);              // the producer may refill this z stage
+            } else if (qrows > 0) {
+                mbar_wait(&zfull[zb * 4 + q], (uint32_t)((it / kZStages) & 1));
+            }
             mbar_wait(&tmem_full[acc], acc_phase);
             tcgen05_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kStageCols);
@@ -439,7 +472,15 @@ linear_mixcdf_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_cons
 #else
                 load_record<PN>(taddr + (uint32_t)(j * PNP), rec);   // warp-collective: outside the divergent part
 #endif
-                const float x = zt[ch];
+                float x;
+                if (direct) {
+                    x = xs[0];
+#pragma unroll
+                    for (int n = 1; n < kNX; ++n)
+                        if (j == g + n * kGroups) x = xs[n];      // static register indices
+                } else {
+                    x = zt[ch];
+                }
                 float out = x;
                 if (active) {
                     const float2* bj = reinterpret_cast<const float2*>(s_bias + j * PN);   // PN is even
@@ -486,10 +527,13 @@ linear_mixcdf_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_cons
                     if ((res.z != res.z) | (res.ldj != res.ldj))
                         flag(p.status, (res.z != res.z ? CNF_FLAG_NAN_Z : 0u) | (res.ldj != res.ldj ? CNF_FLAG_NAN_LDJ : 0u));
                 }
-                if (valid) zt[ch] = out * padv;
+                if (valid) {
+                    if (direct) p.z_out[pos * C + ch] = out * padv;      // registers -> global, 4 bytes per lane at a 4 C stride:
+                    else zt[ch] = out * padv;                            // the row's 4 warps complete its sectors in L2
+                }
             }
             // conditioner channels pass through, times pad (mixture_cdf_layer.py:76,137-138)
-            if (p.pad != nullptr && valid && padv != 1.0f) {
+            if (!direct && p.pad != nullptr && valid && padv != 1.0f) {
                 for (int c = g; c < C - CT; c += kGroups) {
                     const int cc = (c < p.c0) ? c : c + CT;
                     zt[cc] *= padv;
@@ -515,7 +559,8 @@ linear_mixcdf_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_cons
                 if (use_reg && p.reg_ldj) warp_segmented_atomic_add(p.reg_ldj, b_idx, ereg, valid);
             }
 
-            // ---- z tile out, next z tile in -------------------------------------------------------
+            // ---- z tile out, next z tile in (shared mode only) ----------------------------------------
+            if (direct) continue;
             fence_proxy_async_smem();
             quad_barrier(q);
             const long long posq = pos0 + q * 32;
@@ -567,7 +612,7 @@ linear_mixcdf_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_cons
             }
         }
         flush();
-        if (manager) tma_store_wait<0>();
+        if (manager && !direct) tma_store_wait<0>();
     }
 
     tcgen05_fence_before();
@@ -585,7 +630,7 @@ size_t fused_smem(int C, int stages, bool strict, bool resw, int next = 0, int m
     size_t f = 1024 + stages * stage + (size_t)kZStages * kBM * C * 4;
     if (resw) f += (size_t)BN * 128 * (strict ? 2 : 1);      // resident weight block (high + low part)
     f += ((size_t)CT * PN + 1 + 3 * (size_t)CT * KT + 1 + (size_t)kEpiWarps * PNP + 2 * CT) * 4;
-    f += (3 * (size_t)stages + 6 + 4 * kZStages) * 8 + 256;
+    f += (3 * (size_t)stages + 6 + 5 * kZStages) * 8 + 256;
     if (next) f += ((size_t)3 * C + (size_t)C * C + (size_t)(masked ? 4 : 2) * kBM * C) * 4;
     return f;
 }
