@@ -265,6 +265,8 @@ int run(const cnf_mixcdf_args* a, cnf_stream_t stream_, int reverse) {
         rc = mixcdf_gpipe_try(a, p.mask, reverse, stream, &handled);             // any K: lane groups on the same pipeline
         if (rc != CNF_OK || handled) return rc;
     }
+    CNF_SUPPORTED(!a->nn_compact, "the compact network-output layout needs one of the TMA pipelines (contiguous transformed "
+                                   "channels, 16-byte aligned rows): query cnf_mixcdf_path with nn_compact set");
     CNF_SUPPORTED(a->next_actnorm_bias == nullptr && a->next_actnorm_scales == nullptr && a->next_conv_weight == nullptr,
                   "the fused next-block epilogue needs the pipelined layout (forward, C=16, 8 transformed channels, K=8); "
                   "query cnf_mixcdf_fusable first");

@@ -39,6 +39,7 @@ struct BwdParams {
     int S, C, K, PN, TP;
     MaskView mask;
     int vec_params, vec_out;
+    int compact;      // nn / gnn hold the transformed channels' records only: [P, Ct * PN] (needs vec_params && vec_out)
     float reg_max, reg_factor;
     int use_reg;
     int pre;
@@ -196,8 +197,8 @@ __global__ void __launch_bounds__(kThreads) mixcdf_bwd_kernel(const BwdParams p)
         const int L4 = L >> 2, total = rows * L4;
         const float inv = 1.0f / (float)L4;
         const float4* src = reinterpret_cast<const float4*>(p.nn);
-        const long long row4 = ((long long)C * PN) >> 2;
-        const int off4 = (p.mask.c0 * PN) >> 2;
+        const long long row4 = p.compact ? (long long)L4 : ((long long)C * PN) >> 2;
+        const int off4 = p.compact ? 0 : (p.mask.c0 * PN) >> 2;
         float4* dst = reinterpret_cast<float4*>(s_par);
         for (int i = tid; i < total; i += kThreads) {
             const int r = fast_div(i, inv), q = i - r * L4;
@@ -319,10 +320,10 @@ __global__ void __launch_bounds__(kThreads) mixcdf_bwd_kernel(const BwdParams p)
     if (p.vec_params && p.vec_out) {
         // contiguous, 16-byte aligned run of transformed records per position: copy it with 16-byte stores and zero the
         // conditioner records before / after it the same way (no per-granule record lookup)
-        const int L4 = L >> 2, row4 = (C * PN) >> 2, off4 = (p.mask.c0 * PN) >> 2;
-        const int Z4 = row4 - L4;                               // zero float4 per position
+        const int L4 = L >> 2, row4 = p.compact ? L4 : (C * PN) >> 2, off4 = p.compact ? 0 : (p.mask.c0 * PN) >> 2;
+        const int Z4 = row4 - L4;                               // zero float4 per position (none in the compact layout)
         const float inv_l4 = 1.0f / (float)L4;
-        float4* dst = reinterpret_cast<float4*>(p.gnn + pos0 * (long long)C * PN);
+        float4* dst = reinterpret_cast<float4*>(p.gnn) + pos0 * (long long)row4;
         const float4* src = reinterpret_cast<const float4*>(s_par);
         for (int i = tid; i < rows * L4; i += kThreads) {
             const int r = fast_div(i, inv_l4), q = i - r * L4;
@@ -412,7 +413,7 @@ extern "C" int cnf_mixcdf_bwd(const cnf_mixcdf_bwd_args* a, cnf_stream_t stream_
     if (p.mask.n_t == 0) {   // nothing transformed: identity (times pad), no parameter gradient
         CNF_SUPPORTED(a->pad == nullptr, "mask with no transformed channel together with a padding mask");
         CNF_CUDA(cudaMemcpyAsync(a->grad_z, a->grad_z_out, nz * sizeof(float), cudaMemcpyDeviceToDevice, stream));
-        CNF_CUDA(cudaMemsetAsync(a->grad_nn_out, 0, nz * p.PN * sizeof(float), stream));
+        if (!a->nn_compact) CNF_CUDA(cudaMemsetAsync(a->grad_nn_out, 0, nz * p.PN * sizeof(float), stream));
         return CNF_OK;
     }
     p.z = a->z; p.nn = a->nn_out; p.pad = a->pad; p.sf = a->scaling_factor; p.msf = a->mixture_scaling_factor;
@@ -435,6 +436,12 @@ extern "C" int cnf_mixcdf_bwd(const cnf_mixcdf_bwd_args* a, cnf_stream_t stream_
     p.vec_params = p.mask.contiguous && (L % 4 == 0) && (rowlen % 4 == 0) && ((p.mask.c0 * p.PN) % 4 == 0) &&
                    ((reinterpret_cast<uintptr_t>(a->nn_out) & 15) == 0);
     p.vec_out = (reinterpret_cast<uintptr_t>(a->grad_nn_out) & 15) == 0 ? 1 : 0;
+    p.compact = a->nn_compact ? 1 : 0;
+    if (p.compact) {
+        p.vec_params = p.mask.contiguous && (L % 4 == 0) && ((reinterpret_cast<uintptr_t>(a->nn_out) & 15) == 0);
+        CNF_SUPPORTED(p.vec_params && p.vec_out, "the compact gradient layout needs a contiguous run of transformed channels with "
+                                                   "Ct * (2 + 3K) a multiple of 4 and 16-byte aligned nn_out / grad_nn_out");
+    }
     CNF_REQUIRE((reinterpret_cast<uintptr_t>(a->grad_nn_out) & 7) == 0, "grad_nn_out must be 8-byte aligned");
     CNF_SUPPORTED((long long)TP * a->C * p.PN < (1 << 21), "tile too large for the index arithmetic");
     const size_t smem = bwd_smem(TP, L, a->C, Ct, a->K);

@@ -51,6 +51,7 @@ struct GPipeParams {
     int TP;        // positions per tile
     int G;         // lanes per element
     int stages;
+    int compact;     // nn_out holds the transformed channels' records only ([P, Ct * PN])
     int whole_rows;  // 1: a tile's parameter rows arrive as ONE bulk copy of whole rows (short transformed runs)
     int mis;       // floats between the 16-byte-aligned hull start and the first transformed record
     int hull;      // floats copied per position (multiple of 4)
@@ -193,8 +194,8 @@ __global__ void __launch_bounds__(kThreadsG, MINB) mixcdf_gpipe_kernel(const GPi
         int stage = 0;
         uint32_t phase = 0;
         long long pos0 = t0 * TP;
-        const long long row = (long long)C * PN;
-        const long long off = (long long)p.c0 * PN - p.mis;     // hull start inside a position's row (multiple of 4 floats)
+        const long long row = p.compact ? (long long)Ct * PN : (long long)C * PN;
+        const long long off = p.compact ? 0 : (long long)p.c0 * PN - p.mis;   // hull start inside a position's row (multiple of 4)
         for (int it = 0; it < tiles; ++it, pos0 += TP) {
             mbar_wait(&empty[stage], phase ^ 1u);
             const int rows = (int)min((long long)TP, p.P - pos0);
@@ -405,10 +406,11 @@ static bool gpipe_plan(const cnf_mixcdf_args* a, const MaskView& mask, GPipePara
     const int K = a->K, C = a->C, Ct = mask.n_t, PN = 2 + 3 * K;
     if (!mask.contiguous || Ct < 1) return false;
     if (a->next_actnorm_bias || a->next_actnorm_scales || a->next_conv_weight) return false;
-    if (((long long)C * PN) % 4 != 0) return false;
+    if (((long long)(a->nn_compact ? Ct : C) * PN) % 4 != 0) return false;
     if ((reinterpret_cast<uintptr_t>(a->nn_out) & 15) || (reinterpret_cast<uintptr_t>(a->z) & 15)) return false;
     GPipeParams p{};
     p.C = C; p.K = K; p.PN = PN; p.Ct = Ct; p.c0 = mask.c0;
+    p.compact = a->nn_compact ? 1 : 0;
     const int L = Ct * PN;
     const int NC = K <= 4 ? 4 : 8;
     int G = 1;
@@ -419,8 +421,11 @@ static bool gpipe_plan(const cnf_mixcdf_args* a, const MaskView& mask, GPipePara
     // (< 512 bytes: C = 2 / K = 8 edge flows, 104 of 208 bytes), the WHOLE row, so that a tile is ONE contiguous copy
     // instead of hundreds of tiny ones (the TMA engine is request-bound there; the extra sectors were mostly being
     // fetched anyway, a 104-byte run touches 4-5 of the row's 6.5 sectors).
-    p.whole_rows = (L * 4 < 512) ? 1 : 0;
-    if (p.whole_rows) {
+    p.whole_rows = (L * 4 < 512 || p.compact) ? 1 : 0;      // compact: the row IS the run - one copy per tile
+    if (p.compact) {
+        p.mis = 0;
+        p.hull = L;
+    } else if (p.whole_rows) {
         p.mis = mask.c0 * PN;
         p.hull = C * PN;
     } else {
@@ -433,7 +438,7 @@ static bool gpipe_plan(const cnf_mixcdf_args* a, const MaskView& mask, GPipePara
     // K = 64 (G = 8): two rounds of elements per tile halve the per-tile barrier / ring hand-shake per element and two CTAs
     // with ~96 registers beat three with 72 (measured, r02: 0.461 -> 0.429 ms at B 1024 x S 256); K = 32 and below are
     // fastest with one round and three CTAs
-    const size_t cap = (p.whole_rows ? 48 : (G >= 8 ? 52 : 32)) * 1024;
+    const size_t cap = (G >= 8 ? 52 : (p.whole_rows ? 48 : 32)) * 1024;
     int best = 0;
     float best_eff = 0.f;
     for (int tp = 4; tp <= 1024; tp += 4) {

@@ -45,6 +45,8 @@ struct PipeParams {
     long long P;       // positions
     long long ntiles;
     int S, C, c0;      // c0: first transformed channel
+    long long nn_row;  // floats per position of nn_out (C * PN, or Ct * PN for the compact layout)
+    long long nn_off;  // floats from the start of a position's row to its first transformed record
     int s_period;
     unsigned long long cond_s;
     float reg_max, reg_factor;
@@ -161,7 +163,7 @@ __global__ void __launch_bounds__(kThreadsPipe, 2) mixcdf_pipe_kernel(const Pipe
             __syncwarp();
             float* dpar = s_par + stage * (TP * L);
             for (int r = lane; r < rows; r += 32)
-                bulk_g2s(dpar + r * L, p.nn + ((pos0 + r) * C + p.c0) * (long long)PN, L * 4, &full[stage]);
+                bulk_g2s(dpar + r * L, p.nn + (pos0 + r) * p.nn_row + p.nn_off, L * 4, &full[stage]);
             if (lane == 0) bulk_g2s(s_z + stage * zrow, p.z + pos0 * C, (uint32_t)(rows * C * 4), &full[stage]);
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
@@ -243,13 +245,13 @@ __global__ void __launch_bounds__(kThreadsPipe, 2) mixcdf_pipe_kernel(const Pipe
                 if (mix_fast_ok(e)) {
                     res = mix_forward_fast<KT>(e, P, use_reg, p.reg_max, p.reg_factor);
                 } else {
-                    const float* rec_slow = p.nn + ((pos0 + r) * C + ch) * (long long)PN;
+                    const float* rec_slow = p.nn + (pos0 + r) * p.nn_row + p.nn_off + (long long)j * PN;
                     res = mix_forward_f64(x, rec_slow, s_mfac + j * KT, KT, P.log_s, use_reg, p.reg_max, p.reg_factor);
                 }
             } else {
                 InvState<KT> st;
                 if (!mix_inverse_fast<KT>(x, P, p.status, st, res)) {
-                    const float* rec_slow = p.nn + ((pos0 + r) * C + ch) * (long long)PN;
+                    const float* rec_slow = p.nn + (pos0 + r) * p.nn_row + p.nn_off + (long long)j * PN;
                     res = mix_inverse_f64(x, st.x, inv_slow_margin<KT>(st), rec_slow, s_mfac + j * KT, KT, P.log_s, st.lb0,
                                           st.ub0);
                 }
@@ -379,7 +381,8 @@ static bool pipe_eligible(const cnf_mixcdf_args* a, const MaskView& mask) {
     if (!(K == 8 || K == 4 || K == 16)) return false;
     if (!mask.contiguous || !(Ct == 8 || Ct == 16 || Ct == 4)) return false;
     if (C % 4 != 0 || C > 32) return false;
-    if ((Ct * PN) % 4 != 0 || (mask.c0 * PN) % 4 != 0 || (C * PN) % 4 != 0) return false;
+    if ((Ct * PN) % 4 != 0) return false;
+    if (!a->nn_compact && ((mask.c0 * PN) % 4 != 0 || (C * PN) % 4 != 0)) return false;
     if ((reinterpret_cast<uintptr_t>(a->nn_out) & 15) || (reinterpret_cast<uintptr_t>(a->z) & 15)) return false;
     if (K == 16 && Ct == 16) return false;   // two stages of 16 x 800 floats would not fit twice per SM
     return true;
@@ -410,6 +413,8 @@ int mixcdf_pipe_try(const cnf_mixcdf_args* a, const MaskView& mask, int reverse,
     p.z_out = a->z_out; p.ldj = a->ldj; p.reg_ldj = a->reg_ldj; p.status = a->status;
     p.nx_bias = a->next_actnorm_bias; p.nx_scales = a->next_actnorm_scales; p.nx_w = a->next_conv_weight;
     p.P = P; p.S = (int)a->S; p.C = C; p.c0 = mask.c0; p.s_period = mask.s_period; p.cond_s = mask.cond_s;
+    p.nn_row = a->nn_compact ? (long long)Ct * (2 + 3 * K) : (long long)C * (2 + 3 * K);
+    p.nn_off = a->nn_compact ? 0 : (long long)mask.c0 * (2 + 3 * K);
     p.reg_max = a->reg_max; p.reg_factor = a->reg_factor;
     p.use_reg = (!reverse && a->reg_max > 0.f && a->training) ? 1 : 0;
     const int TP = kConsumers / Ct;

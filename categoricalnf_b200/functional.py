@@ -26,7 +26,7 @@ class _MixCDF(torch.autograd.Function):
         z_out, ldj, reg = ops.mixcdf(z, nn_out, cfg["K"], mask_c=cfg["mask_c"], mask_s=cfg["mask_s"], pad=pad,
                                      scaling_factor=sf, mixture_scaling_factor=msf, reverse=cfg["reverse"],
                                      reg_max=cfg["reg_max"], reg_factor=cfg["reg_factor"], training=cfg["training"],
-                                     want_reg=True, prebounded=cfg.get("prebounded", False))
+                                     want_reg=True, prebounded=cfg.get("prebounded", False), compact=cfg.get("compact", False))
         ctx.cfg = cfg
         ctx.save_for_backward(z, nn_out, sf, msf, pad, z_out)
         ctx.mark_non_differentiable(reg)
@@ -42,15 +42,16 @@ class _MixCDF(torch.autograd.Function):
 
 
 def mixcdf(z, nn_out, num_mixtures, scaling_factor=None, mixture_scaling_factor=None, *, mask_c=None, mask_s=None,
-           pad=None, reverse=False, reg_max=-1.0, reg_factor=1.0, training=False, prebounded=False):
-    """(z_out, ldj [B], reg_ldj [B]) of the logistic-mixture coupling transform (K1 / K2)."""
+           pad=None, reverse=False, reg_max=-1.0, reg_factor=1.0, training=False, prebounded=False, compact=False):
+    """(z_out, ldj [B], reg_ldj [B]) of the logistic-mixture coupling transform (K1 / K2).  ``compact``: ``nn_out`` (and
+    its gradient) hold the transformed channels' records only, [B,S,Ct*(2+3K)]."""
     cfg = dict(K=int(num_mixtures), mask_c=mask_c, mask_s=mask_s, reverse=bool(reverse), reg_max=float(reg_max),
-               reg_factor=float(reg_factor), training=bool(training), prebounded=bool(prebounded))
+               reg_factor=float(reg_factor), training=bool(training), prebounded=bool(prebounded), compact=bool(compact))
     if _needs_grad(z, nn_out, scaling_factor, mixture_scaling_factor):
         return _MixCDF.apply(z, nn_out, scaling_factor, mixture_scaling_factor, pad, cfg)
     return ops.mixcdf(z, nn_out, cfg["K"], mask_c=mask_c, mask_s=mask_s, pad=pad, scaling_factor=scaling_factor,
                       mixture_scaling_factor=mixture_scaling_factor, reverse=reverse, reg_max=reg_max,
-                      reg_factor=reg_factor, training=training, want_reg=True, prebounded=prebounded)
+                      reg_factor=reg_factor, training=training, want_reg=True, prebounded=prebounded, compact=compact)
 
 
 # ----------------------------------------------------------------------------------------------

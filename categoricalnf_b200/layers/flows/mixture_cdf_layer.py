@@ -151,12 +151,57 @@ class MixtureCDFCoupling(CouplingLayer):
         else:
             if fuse is not None:
                 return None
+            compact = self._compact_projection(z, x_in, mask_c, mask_s, channel_padding_mask, kwargs)
+            if compact is not None:
+                z_out, ldj, reg = CF.mixcdf(z, compact, self.num_mixtures, self.scaling_factor, self.mixture_scaling_factor,
+                                            mask_c=mask_c, mask_s=mask_s, pad=channel_padding_mask, reverse=reverse,
+                                            reg_max=self.regularizer_max, reg_factor=self.regularizer_factor,
+                                            training=self.training, compact=True)
+                return z_out, ldj, {"ldj": ldj, "regularizer_ldj": reg}
             nn_out = self.run_network(x=x_in, **kwargs)
         z_out, ldj, reg = CF.mixcdf(z, nn_out, self.num_mixtures, self.scaling_factor, self.mixture_scaling_factor,
                                     mask_c=mask_c, mask_s=mask_s, pad=channel_padding_mask, reverse=reverse,
                                     reg_max=self.regularizer_max, reg_factor=self.regularizer_factor,
                                     training=self.training)
         return z_out, ldj, {"ldj": ldj, "regularizer_ldj": reg}
+
+    # Training-time counterpart of the fused projection: when the network ends in a Linear, only the weight rows of the
+    # TRANSFORMED channels' records are multiplied - the transform never reads the conditioner half of the network output
+    # (mixture_cdf_layer.py:166-173 zeroes it) - and the transform / its backward kernel take that compact
+    # [B,S,Ct*(2+3K)] layout: half the projection GEMMs (forward, grad_x, grad_W) and no zeros written for conditioner
+    # channels in dL/dnn_out.  Gradients of the skipped weight rows are exactly zero in the reference too.
+    compact_projection_in_training = True
+
+    def _compact_projection(self, z, x_in, mask_c, mask_s, channel_padding_mask, kwargs):
+        """Compact network output [B,S,Ct*(2+3K)] (differentiable), or None when this configuration does not allow it."""
+        if not (self.compact_projection_in_training and torch.is_grad_enabled() and z.is_cuda and z.dim() == 3):
+            return None
+        if mask_c is None or mask_s is not None:
+            return None
+        split = split_final_linear(self.nn)
+        if split is None:
+            return None
+        features_fn, lin = split
+        pn = 2 + 3 * self.num_mixtures
+        if lin.out_features != self.c_in * pn or lin.in_features % 4 != 0:
+            return None
+        tch = [c for c, m in enumerate(mask_c) if float(m) == 0.0]
+        if not tch or tch != list(range(tch[0], tch[0] + len(tch))) or len(tch) == self.c_in:
+            return None                                   # needs a contiguous run, and a conditioner half worth skipping
+        r0, r1 = tch[0] * pn, (tch[-1] + 1) * pn
+        if (r0 * lin.in_features) % 4 != 0 or ((r1 - r0) % 4) != 0:
+            return None                                   # 16-byte aligned weight block / output rows
+        probe = z.new_empty(z.shape[0], z.shape[1], r1 - r0)
+        if ops.mixcdf_path(z, probe, self.num_mixtures, mask_c=mask_c, compact=True) == "generic":
+            return None
+        feats = features_fn(x_in, **kwargs)
+        if feats.dim() != 3:
+            return None
+        from ..networks.linear import _TCLinearFn
+        bias = None if lin.bias is None else lin.bias[r0:r1]
+        out = _TCLinearFn.apply(feats.reshape(-1, feats.shape[-1]), lin.weight[r0:r1], bias, self.projection_precision)
+        # (no pad multiply here: channel_padding_mask is bound by forward() and never reaches run_network, App. B #3)
+        return out.view(z.shape[0], z.shape[1], r1 - r0)
 
     def try_forward_fused(self, z, actnorm, conv, channel_padding_mask=None, length=None, cnf_masked_input=None,
                           cnf_next_mask=None, **kwargs):

@@ -169,13 +169,17 @@ def _same_device(dev, items, name):
 
 
 # ----------------------------------------------------------------------------------------------
-def _mixcdf_args(z, nn_out, num_mixtures, mask_c, mask_s, pad, scaling_factor, mixture_scaling_factor):
+def _n_transformed(mask_c, Cc):
+    return Cc if mask_c is None else sum(1 for m in mask_c if float(m) == 0.0)
+
+
+def _mixcdf_args(z, nn_out, num_mixtures, mask_c, mask_s, pad, scaling_factor, mixture_scaling_factor, compact=False):
     z = _f32(z, "z")
     if z.dim() != 3:
         raise ValueError("z must be [B, S, C]")
     B, S, Cc = z.shape
     K = int(num_mixtures)
-    nn_out = _f32(nn_out, "nn_out", (B, S, Cc * (2 + 3 * K)))
+    nn_out = _f32(nn_out, "nn_out", (B, S, (_n_transformed(mask_c, Cc) if compact else Cc) * (2 + 3 * K)))
     pad = _pad_bs(pad, B, S)
     a = L.MixcdfArgs()
     a.B, a.S, a.C, a.K = B, S, Cc, K
@@ -184,6 +188,7 @@ def _mixcdf_args(z, nn_out, num_mixtures, mask_c, mask_s, pad, scaling_factor, m
     msf = _opt_f32(mixture_scaling_factor, "mixture_scaling_factor", (Cc, K))
     a.z, a.nn_out, a.pad = _ptr(z), _ptr(nn_out), _ptr(pad)
     a.scaling_factor, a.mixture_scaling_factor = _ptr(sf), _ptr(msf)
+    a.nn_compact = int(bool(compact))
     return a, (keep, z, nn_out, pad, sf, msf)
 
 
@@ -197,25 +202,28 @@ def mixcdf_fusable(z, nn_out, num_mixtures, *, mask_c=None, mask_s=None, preboun
 MIXCDF_PATHS = {0: "generic", 1: "pipe", 2: "gpipe"}
 
 
-def mixcdf_path(z, nn_out, num_mixtures, *, mask_c=None, mask_s=None, prebounded=False):
+def mixcdf_path(z, nn_out, num_mixtures, *, mask_c=None, mask_s=None, prebounded=False, compact=False):
     """Which kernel :func:`mixcdf` launches for this shape / mask / alignment: "generic" (staged), "pipe" (TMA pipeline,
-    compile-time K and Ct, thread per element) or "gpipe" (TMA pipeline, lane groups, any K)."""
-    a, keep = _mixcdf_args(z, nn_out, num_mixtures, mask_c, mask_s, None, None, None)
+    compile-time K and Ct, thread per element) or "gpipe" (TMA pipeline, lane groups, any K).  ``compact``: ``nn_out`` holds
+    only the transformed channels' records ([B,S,Ct*(2+3K)]) - taken by the two pipelines only."""
+    a, keep = _mixcdf_args(z, nn_out, num_mixtures, mask_c, mask_s, None, None, None, compact)
     a.params_prebounded = int(bool(prebounded))
     return MIXCDF_PATHS[int(L.load().cnf_mixcdf_path(C.byref(a)))]
 
 
 def mixcdf(z, nn_out, num_mixtures, *, mask_c=None, mask_s=None, pad=None, scaling_factor=None,
            mixture_scaling_factor=None, reverse=False, reg_max=-1.0, reg_factor=1.0, training=False,
-           ldj=None, want_reg=False, out=None, prebounded=False, fuse_next=None):
+           ldj=None, want_reg=False, out=None, prebounded=False, fuse_next=None, compact=False):
     """K1/K2.  Returns ``(z_out, ldj[B], reg_ldj[B] | None)``.  ``ldj`` given -> accumulated into.
+    ``compact``: ``nn_out`` is [B,S,Ct*(2+3K)] - the records of the transformed channels only (one contiguous run); the
+    conditioner half of the network output is never read, so its producer need not compute it (see ``mixcdf_path``).
     ``scaling_factor`` / ``mixture_scaling_factor`` None = zeros, i.e. tanh bounds e^0 = 1 like a freshly built layer (the
     module always passes its parameters; the reference's static helper treats None as "no bounding", which is
     ``prebounded=True`` here).
     ``fuse_next = (bias [C], scales [C], W [C,C])`` applies the next block's ActNorm and 1x1
     convolution to the output row inside the kernel (forward only, see ``mixcdf_fusable``); their
     per-sample-constant ldj terms are NOT added here."""
-    a, keep = _mixcdf_args(z, nn_out, num_mixtures, mask_c, mask_s, pad, scaling_factor, mixture_scaling_factor)
+    a, keep = _mixcdf_args(z, nn_out, num_mixtures, mask_c, mask_s, pad, scaling_factor, mixture_scaling_factor, compact)
     z = keep[1]
     B = z.shape[0]
     z_out = torch.empty_like(z) if out is None else out

@@ -25,7 +25,8 @@ def mixcdf_backward(cfg, z, nn_out, sf, msf, pad, z_out, g_z, g_ldj, needs):
     z = _f32(z, "z")
     B, S, Cc = z.shape
     K = cfg["K"]
-    nn_out = _f32(nn_out, "nn_out", (B, S, Cc * (2 + 3 * K)))
+    compact = bool(cfg.get("compact", False))
+    nn_out = _f32(nn_out, "nn_out", (B, S, (ops._n_transformed(cfg["mask_c"], Cc) if compact else Cc) * (2 + 3 * K)))
     a = L.MixcdfBwdArgs()
     a.B, a.S, a.C, a.K = B, S, Cc, K
     a.mask, keep = _mask_struct(cfg["mask_c"], cfg["mask_s"])
@@ -42,6 +43,7 @@ def mixcdf_backward(cfg, z, nn_out, sf, msf, pad, z_out, g_z, g_ldj, needs):
     a.z, a.nn_out, a.pad, a.scaling_factor, a.mixture_scaling_factor = _ptr(z), _ptr(nn_out), _ptr(pad), _ptr(sf), _ptr(msf)
     a.reg_max, a.reg_factor, a.training = float(cfg["reg_max"]), float(cfg["reg_factor"]), int(bool(cfg["training"]))
     a.params_prebounded = int(pre)
+    a.nn_compact = int(compact)
     a.grad_z_out, a.grad_ldj, a.grad_z, a.grad_nn_out = _ptr(gz_out), _ptr(gl), _ptr(gz), _ptr(gnn)
     a.grad_scaling_factor, a.grad_mixture_scaling_factor = _ptr(gsf), _ptr(gmsf)
     _call("cnf_mixcdf_bwd", a, z, (keep, z, nn_out, pad, sf, msf, gz_out, gl))

@@ -111,6 +111,12 @@ typedef struct {
     const float* next_actnorm_bias;      /* [C] or NULL                               */
     const float* next_actnorm_scales;    /* [C] or NULL                               */
     const float* next_conv_weight;       /* [C,C] row-major (z @ W) or NULL           */
+    /* ABI v4: 1 = `nn_out` is COMPACT, [B,S,Ct*(2+3K)] with only the records of the Ct transformed channels (in
+     * channel order; they must form one contiguous run c0..c0+Ct-1).  The conditioner half of the network output is
+     * never read, so a caller that owns the final projection need not produce it (training: half the GEMM, half the
+     * gradient traffic).  Supported by the TMA pipelines (cnf_mixcdf_path 1 and 2) - query cnf_mixcdf_path with this
+     * flag set; the staged generic kernel rejects it. */
+    int32_t nn_compact;
 } cnf_mixcdf_args;
 
 CNF_API int cnf_mixcdf_fwd(const cnf_mixcdf_args* a, cnf_stream_t stream);
@@ -580,6 +586,9 @@ typedef struct {
     float* grad_nn_out;                  /* [B,S,C*(2+3K)], zeros for conditioners    */
     float* grad_scaling_factor;          /* [C] += or NULL                            */
     float* grad_mixture_scaling_factor;  /* [C,K] += or NULL                          */
+    /* ABI v4: 1 = nn_out AND grad_nn_out are compact, [B,S,Ct*(2+3K)] (see cnf_mixcdf_args.nn_compact): no zeros are
+     * written for conditioner channels.  Needs a contiguous run of transformed channels and 16-byte aligned rows. */
+    int32_t nn_compact;
 } cnf_mixcdf_bwd_args;
 
 /* forward direction of cnf_mixcdf_fwd (training differentiates the density direction only) */

@@ -283,3 +283,73 @@ def test_categ_encode_backward_vs_oracle_autograd(B, S, V, D, padded, beta):
     ((z * wz.cuda()).sum() + (ldj * wl.cuda()).sum()).backward()
     assert_close(z, z_ref, rtol=1e-4, atol=1e-5, what="z")
     grads_close(t_gpu.grad, t_ref.grad.float(), "dL/dtable", rtol=2e-3, atol_rel=1e-3)
+
+
+@pytest.mark.parametrize("B,S,C,K,flip", [(5, 41, 16, 8, False), (4, 33, 16, 8, True), (3, 20, 16, 64, False), (2, 50, 16, 32, False),
+                                          (3, 37, 8, 8, False), (600, 64, 16, 8, False)])
+def test_mixcdf_compact_layout_matches_full(B, S, C, K, flip):
+    """ABI v4 ``nn_compact``: the network output holds the transformed channels' records only.  Forward, inverse and
+    backward on the compact tensor equal the full-layout calls (bit for bit forward, to rounding in the gradients), and
+    dL/dnn_out comes back compact - nothing is written for conditioner channels."""
+    from categoricalnf_b200 import functional as CF
+    from categoricalnf_b200 import ops
+    z, nn_out, sf, msf, mask, pad, wz, wl = _mix_inputs(B, S, C, K, seed=B + S + C + K, padded=True, flip=flip)
+    mc = mask.flatten().tolist()
+    PN = 2 + 3 * K
+    tch = [c for c, m in enumerate(mc) if m == 0.0]
+    r0, r1 = tch[0] * PN, (tch[-1] + 1) * PN
+    nn_c = nn_out[..., r0:r1].contiguous()
+    assert ops.mixcdf_path(z.cuda(), nn_c.cuda(), K, mask_c=mc, compact=True) in ("pipe", "gpipe")
+    kw = dict(mask_c=mc, pad=pad.cuda(), scaling_factor=sf.cuda(), mixture_scaling_factor=msf.cuda())
+    zf, lf, _ = ops.mixcdf(z.cuda(), nn_out.cuda(), K, **kw)
+    zc, lc, _ = ops.mixcdf(z.cuda(), nn_c.cuda(), K, compact=True, **kw)
+    assert torch.equal(zf, zc) and torch.equal(lf, lc)
+    zi, li, _ = ops.mixcdf(zf, nn_out.cuda(), K, reverse=True, **kw)
+    zic, lic, _ = ops.mixcdf(zf, nn_c.cuda(), K, reverse=True, compact=True, **kw)
+    assert torch.equal(zi, zic) and torch.equal(li, lic)
+    # backward: full vs compact
+    res = {}
+    for compact in (False, True):
+        zg, sg, mg = leaf(z, True), leaf(sf, True), leaf(msf, True)
+        ng = leaf(nn_c if compact else nn_out, True)
+        out_g, ldj_g, _ = CF.mixcdf(zg, ng, K, sg, mg, mask_c=mc, pad=pad.cuda(), reg_max=1.0, reg_factor=1.5, training=True,
+                                    compact=compact)
+        ((out_g * wz.cuda()).sum() + (ldj_g * wl.cuda()).sum()).backward()
+        res[compact] = (zg.grad, ng.grad, sg.grad, mg.grad)
+    assert res[True][1].shape == nn_c.shape
+    grads_close(res[True][0], res[False][0], "dL/dz", rtol=1e-6, atol_rel=1e-7)
+    grads_close(res[True][1], res[False][1][..., r0:r1], "dL/dnn_out (compact)", rtol=1e-6, atol_rel=1e-7)
+    assert float(res[False][1][..., :r0].abs().sum() + res[False][1][..., r1:].abs().sum()) == 0.0
+    grads_close(res[True][2], res[False][2], "dL/dsf", rtol=1e-4, atol_rel=1e-5)
+    grads_close(res[True][3], res[False][3], "dL/dmsf", rtol=1e-4, atol_rel=1e-5)
+
+
+def test_compact_projection_in_training_matches_two_step_path():
+    """MixtureCDFCoupling in training mode with a network that ends in a Linear: the compact path (only the transformed
+    channels' weight rows are multiplied) gives the same outputs and the same gradients - incl. exact zeros for the skipped
+    weight rows - as the full network output through the two-step path."""
+    import workload as W
+    from categoricalnf_b200.layers.flows import MixtureCDFCoupling
+    torch.manual_seed(0)
+    D, K, B, S = 16, 8, 7, 50
+    mask = torch.cat([torch.ones(D // 2), torch.zeros(D - D // 2)]).view(1, D)
+    layer = MixtureCDFCoupling(c_in=D, mask=mask, model_func=lambda c_out: W.StandInNet(D, c_out), num_mixtures=K).cuda().train()
+    with torch.no_grad():
+        layer.scaling_factor.normal_(0, 0.3)
+        layer.mixture_scaling_factor.normal_(0, 0.3)
+    z = torch.randn(B, S, D, device="cuda")
+    wz, wl = torch.randn(B, S, D, device="cuda"), torch.randn(B, device="cuda")
+    out = {}
+    for compact in (True, False):
+        layer.compact_projection_in_training = compact
+        layer.zero_grad()
+        zin = z.clone().requires_grad_(True)
+        zo, ldj, _ = layer(zin)
+        ((zo * wz).sum() + (ldj * wl).sum()).backward()
+        out[compact] = (zo.detach(), ldj.detach(), zin.grad, layer.nn.lin.weight.grad.clone(), layer.nn.lin.bias.grad.clone(),
+                        layer.scaling_factor.grad.clone(), layer.mixture_scaling_factor.grad.clone())
+    names = ["z", "ldj", "dL/dz", "dL/dW", "dL/db", "dL/dsf", "dL/dmsf"]
+    for a, b, n in zip(out[True], out[False], names):
+        grads_close(a, b, n, rtol=2e-5, atol_rel=2e-6)
+    pn = 2 + 3 * K
+    assert float(out[True][3][: (D // 2) * pn].abs().sum()) == 0.0        # conditioner records: no gradient, as in the reference
