@@ -164,7 +164,7 @@ class LMDevicePath:
             z, _ = ops.actnorm(z, b["bias"], b["scales"], None)
             z, _ = ops.invconv_apply(z, b["w"], b["sldj"], None)
             zin = z * torch.tensor(b["mask_c"], device=self.dev)
-            nn_out = torch.nn.functional.linear(zin, b["net_w"], b["net_b"])
+            nn_out = ops.linear(zin, b["net_w"], b["net_b"])      # the product's tcgen05 projection (3xTF32), not cuBLAS
             z, _, _ = ops.mixcdf(z, nn_out, prm.K, mask_c=b["mask_c"], scaling_factor=b["sf"],
                                  mixture_scaling_factor=b["msf"])
         return self
@@ -201,7 +201,7 @@ class LMDevicePath:
                 nn_out = nn_outs[i]
             else:
                 zin = z * torch.tensor(b["mask_c"], device=self.dev)
-                nn_out = torch.nn.functional.linear(zin, b["net_w"], b["net_b"])
+                nn_out = ops.linear(zin, b["net_w"], b["net_b"])      # the product's tcgen05 projection (3xTF32), not cuBLAS
             if time_mix:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
