@@ -10,8 +10,6 @@
 //                          one CTA per node walks its adjacency row once and reads only the rows of real neighbours.
 //   cnf_skip_gate          GNNSkipConnection (:722-733): residual / gated / highway combination
 // All HBM / L2 bound, no host synchronisation (the reference's max_neighbours.item() at :107 is one per layer).
-#include <stdlib.h>
-
 #include "cnf_common.cuh"
 
 namespace cnf {
@@ -464,155 +462,6 @@ __global__ void __launch_bounds__(kAggThreads) edge_aggregate_kernel(const EdgeA
     }
 }
 
-
-// ---------------------------------------------------------------------------------------------------------------------
-// cnf_edge_aggregate, second form (r02): ONE CTA PER (GRAPH, 128-FEATURE SLICE) instead of one CTA per node.
-// The node-per-CTA kernel above reads every pair row twice (once from each endpoint) and every node row N-1 times: at
-// the GraphCNF shapes it moves ~4.3 MB per graph through L2 for 1.1 MB of distinct pair rows and was 22 % of the
-// log-likelihood / sampling passes (r02 profile).  Here a CTA
-//   A. turns rev[b, :] into the graph's pair-row table and builds ALL attention weights W[h][i][j] in shared memory
-//      (mode 0: sigmoid(edge_logit) normalised per node; mode 1: per head Q_h K_h^T from shared-memory tiles + edge bias,
-//      row softmax),
-//   B. walks the valid pairs once: a warp per pair loads the pair row's slice ONCE (16 bytes per lane) and adds
-//      W[h][i][j] (e + v_j) to node i and W[h][j][i] (e + v_i) to node j - accumulators and the node rows' slice live in
-//      shared memory (red.shared adds),
-//   C. writes the N output row slices.
-// Needs H * Dh a multiple of 128, Dh a multiple of 4, N <= 64, 16-byte aligned rows; anything else takes the node kernel.
-// ---------------------------------------------------------------------------------------------------------------------
-constexpr int kEgThreads = 256;
-constexpr int kEgSlice = 128;
-
-__global__ void __launch_bounds__(kEgThreads) edge_aggregate_graph_kernel(const EdgeAggParams p) {
-    extern __shared__ __align__(16) unsigned char eg_smem[];
-    const int N = p.N, P = p.P, H = p.H, Dh = p.Dh;
-    const int HD = H * Dh;
-    float* W = reinterpret_cast<float*>(eg_smem);                 // [H][N][N]  weights (logits while being built)
-    float* accum = W + H * N * N;                                  // [N][128]
-    float* nval = accum + N * kEgSlice;                            // [N][128]   node_val slice
-    int* rows = reinterpret_cast<int*>(nval + N * kEgSlice);       // [P]        compact row of the pair, -1 = not valid
-    float* qk = accum;                                             // mode 1, phase A: [2][N][Dh] (Q_h | K_h) aliases accum + nval
-
-    const int nslices = HD / kEgSlice;
-    const long long b = blockIdx.x / nslices;
-    const int f0 = (int)(blockIdx.x - b * nslices) * kEgSlice;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-
-    for (int q = tid; q < P; q += kEgThreads) rows[q] = (int)(p.rev[b * P + q]) - 1;
-    for (int i = tid; i < H * N * N; i += kEgThreads) W[i] = (p.mode == 1) ? -3.0e38f : 0.f;
-    __syncthreads();
-
-    // ---- A. weights ---------------------------------------------------------------------------------------------
-    if (p.mode == 0) {
-        // s_p = sigmoid(logit_p) for both directions; node sums through shared-memory adds into the diagonal W[h][i][i]
-        for (int e = tid; e < P * H; e += kEgThreads) {
-            const int q = e / H, h = e - q * H;
-            const int r = rows[q];
-            if (r < 0) continue;
-            // pair q = (i, j), i < j: invert the node-major numbering
-            int i = 0, base = 0;
-            while (base + (N - 1 - i) <= q) { base += N - 1 - i; ++i; }
-            const int j = i + 1 + (q - base);
-            const float sg = 1.0f / (1.0f + __expf(-p.edge_logit[(long long)r * p.ld_el + h]));
-            W[(h * N + i) * N + j] = sg;
-            W[(h * N + j) * N + i] = sg;
-            atomicAdd(&W[(h * N + i) * N + i], sg);
-            atomicAdd(&W[(h * N + j) * N + j], sg);
-        }
-        __syncthreads();
-        for (int e = tid; e < H * N * N; e += kEgThreads) {
-            const int hi = e / N, j = e - hi * N, i = hi % N;
-            if (i == j) continue;
-            const float sum = W[hi * N + i];
-            W[e] *= 1.0f / fmaxf(sum, 1e-5f);                                             // :629 / :688
-        }
-    } else {
-        for (int h = 0; h < H; ++h) {
-            __syncthreads();
-            for (int e = tid; e < N * Dh; e += kEgThreads) {
-                const int n = e / Dh, d = e - n * Dh;
-                qk[e] = p.node_q[(b * N + n) * p.ld_q + h * Dh + d];
-                qk[N * Dh + e] = p.node_k[(b * N + n) * p.ld_k + h * Dh + d];
-            }
-            __syncthreads();
-            for (int e = tid; e < N * N; e += kEgThreads) {
-                const int i = e / N, j = e - i * N;
-                if (i == j) continue;
-                const int q = i < j ? pair_index(i, j, N) : pair_index(j, i, N);
-                const int r = rows[q];
-                if (r < 0) continue;
-                const float* qi = qk + i * Dh;
-                const float* kj = qk + N * Dh + j * Dh;
-                float acc = 0.f;
-                int dd = lane % Dh;                                     // skewed start: rows are Dh floats apart (same bank)
-                for (int d = 0; d < Dh; ++d) {
-                    acc = fmaf(qi[dd], kj[dd], acc);
-                    if (++dd == Dh) dd = 0;
-                }
-                W[(h * N + i) * N + j] = fmaf(acc, p.scale, p.edge_logit[(long long)r * p.ld_el + h]);
-            }
-        }
-        __syncthreads();
-        for (int hi = warp; hi < H * N; hi += kEgThreads / 32) {       // softmax over j of row (h, i)
-            float* row = W + hi * N;
-            float mx = -3.0e38f;
-            for (int j = lane; j < N; j += 32) mx = fmaxf(mx, row[j]);
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, d));
-            float sum = 0.f;
-            for (int j = lane; j < N; j += 32) {
-                const float e = row[j] > -1.0e38f ? __expf(row[j] - mx) : 0.f;
-                row[j] = e;
-                sum += e;
-            }
-            sum = warp_sum(sum);
-            const float inv = sum > 0.f ? 1.0f / sum : 0.f;
-            for (int j = lane; j < N; j += 32) row[j] *= inv;
-        }
-    }
-    __syncthreads();
-
-    // ---- B. one pass over the valid pairs ---------------------------------------------------------------------------
-    for (int e = tid; e < N * (kEgSlice / 4); e += kEgThreads) {
-        const int n = e / (kEgSlice / 4), c = e - n * (kEgSlice / 4);
-        reinterpret_cast<float4*>(nval)[e] = *reinterpret_cast<const float4*>(p.node_val + (b * N + n) * p.ld_nv + f0 + 4 * c);
-        reinterpret_cast<float4*>(accum)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    __syncthreads();
-    {
-        const int f = f0 + 4 * lane;          // this lane's 4 features
-        const int h = f / Dh;
-        int i = 0, base = 0;                  // pair q = (i, j), advanced incrementally
-        for (int q = warp; q < P; q += kEgThreads / 32) {
-            while (base + (N - 1 - i) <= q) { base += N - 1 - i; ++i; }
-            const int j = i + 1 + (q - base);
-            const int r = rows[q];
-            if (r < 0) continue;
-            const float4 ev = *reinterpret_cast<const float4*>(p.edge_val + (long long)r * p.ld_ev + f);
-            const float4 vi = reinterpret_cast<const float4*>(nval)[i * (kEgSlice / 4) + lane];
-            const float4 vj = reinterpret_cast<const float4*>(nval)[j * (kEgSlice / 4) + lane];
-            const float wij = W[(h * N + i) * N + j], wji = W[(h * N + j) * N + i];
-            float* ai = accum + i * kEgSlice + 4 * lane;
-            float* aj = accum + j * kEgSlice + 4 * lane;
-            atomicAdd(ai + 0, wij * (ev.x + vj.x)); atomicAdd(ai + 1, wij * (ev.y + vj.y));
-            atomicAdd(ai + 2, wij * (ev.z + vj.z)); atomicAdd(ai + 3, wij * (ev.w + vj.w));
-            atomicAdd(aj + 0, wji * (ev.x + vi.x)); atomicAdd(aj + 1, wji * (ev.y + vi.y));
-            atomicAdd(aj + 2, wji * (ev.z + vi.z)); atomicAdd(aj + 3, wji * (ev.w + vi.w));
-        }
-    }
-    __syncthreads();
-    // ---- C. output row slices -----------------------------------------------------------------------------------------
-    for (int e = tid; e < N * (kEgSlice / 4); e += kEgThreads) {
-        const int n = e / (kEgSlice / 4), c = e - n * (kEgSlice / 4);
-        *reinterpret_cast<float4*>(p.out + (b * N + n) * HD + f0 + 4 * c) = reinterpret_cast<const float4*>(accum)[e];
-    }
-}
-
-static size_t edge_graph_smem(int N, int H, int Dh) {
-    const size_t tiles = (size_t)2 * N * kEgSlice;                       // accum + nval
-    const size_t qk = (size_t)2 * N * Dh;                                // mode 1 phase A (aliases the tiles)
-    return ((size_t)H * N * N + (tiles > qk ? tiles : qk)) * 4 + (size_t)(N * (N - 1) / 2) * 4 + 16;
-}
-
 struct PairCombineParams {
     const long long* flat;       // [R] = b*P + p
     const long long* idx1; const long long* idx2;   // [P] node indices of pair p
@@ -664,18 +513,6 @@ extern "C" int cnf_edge_aggregate(const cnf_edge_aggregate_args* a, cnf_stream_t
     p.N = a->N; p.P = a->N * (a->N - 1) / 2; p.H = a->H; p.Dh = a->Dh; p.mode = a->mode; p.scale = a->scale;
     uintptr_t bits = reinterpret_cast<uintptr_t>(a->node_val) | reinterpret_cast<uintptr_t>(a->edge_val) | reinterpret_cast<uintptr_t>(a->out);
     p.vec = ((a->Dh & 3) == 0 && (p.ld_nv & 3) == 0 && (p.ld_ev & 3) == 0 && (bits & 15) == 0) ? 1 : 0;
-    // per-graph form: every pair row is read once (see edge_aggregate_graph_kernel)
-    static const bool node_form = getenv("CNF_B200_EDGE_AGG_NODES") != nullptr;      // A/B switch for profiling
-    const int HD = a->H * a->Dh;
-    const bool q_ok = a->mode == 0 || ((p.ld_q & 3) == 0 && (p.ld_k & 3) == 0);
-    if (!node_form && p.vec && q_ok && HD % kEgSlice == 0 && a->N <= 64 && a->R > 0 &&
-        (reinterpret_cast<uintptr_t>(a->out) & 15) == 0 && edge_graph_smem(a->N, a->H, a->Dh) <= 100 * 1024) {
-        const size_t gsmem = edge_graph_smem(a->N, a->H, a->Dh);
-        if (gsmem > 48 * 1024)
-            CNF_CUDA(cudaFuncSetAttribute(edge_aggregate_graph_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
-        edge_aggregate_graph_kernel<<<(unsigned)(a->B * (HD / kEgSlice)), kEgThreads, gsmem, stream>>>(p);
-        return launch_status("edge_aggregate_graph_kernel");
-    }
     const size_t smem = (size_t)a->N * 8 + (size_t)a->H * a->N * 4;
     CNF_SUPPORTED(smem <= 48 * 1024, "cnf_edge_aggregate: neighbour list does not fit shared memory");
     edge_aggregate_kernel<<<(unsigned)(a->B * a->N), kAggThreads, smem, stream>>>(p);
