@@ -15,16 +15,28 @@ from .activation_normalization import ActNormFlow
 from .permutation_layers import InvertibleConv
 
 
-def _actnorm_conv_fused(z, an, conv, out_mask, channel_padding_mask=None, length=None, **kwargs):
+def _actnorm_conv_fused(z, an, conv, out_mask, channel_padding_mask=None, length=None, ldj_acc=None, **kwargs):
     """``ActNormFlow`` + ``InvertibleConv`` of one flow block in ONE pass over z (``cnf_invconv_apply`` with the
     ActNorm prologue), optionally emitting ``z_out * out_mask`` = the masked input of the coupling that follows.
-    Returns (z_out, ldj of both layers, {}[, z_masked])."""
+    Returns (z_out, ldj of both layers, {}[, z_masked]).  ``ldj_acc`` given: the two layers' ldj - a per-sample constant
+    times the sample's length - is added into that running accumulator by one ``cnf_ldj_axpy`` (with the constant cached
+    per parameter version when there is no padding) and None is returned in its place."""
     from .mixture_cdf_layer import add_next_block_ldj
     weight, sldj = conv._get_weight(device_name=str(z.device), inverse=False)
     out = ops.invconv_apply(z, weight, sldj, None, pad=channel_padding_mask, pre_actnorm=(an.bias, an.scales),
                             out_mask=out_mask)
-    ldj = torch.zeros(z.size(0), dtype=torch.float32, device=z.device)
-    add_next_block_ldj(ldj, an, sldj, z.size(1), channel_padding_mask, length)
+    if ldj_acc is not None and length is None and channel_padding_mask is None:
+        key = (ops.param_epoch(), an.scales._version, an.scales.data_ptr(), sldj.data_ptr(), sldj._version)
+        hit = an.__dict__.get("_cnf_block_const")
+        if hit is None or hit[0] != key:
+            hit = (key, (an.scales.detach().sum() + sldj.reshape(())).reshape(1))
+            an.__dict__["_cnf_block_const"] = hit
+        ops.ldj_axpy(ldj_acc, alpha=float(z.size(1)), alpha_dev=hit[1])
+        ldj = None
+    else:
+        ldj = torch.zeros(z.size(0), dtype=torch.float32, device=z.device) if ldj_acc is None else ldj_acc
+        add_next_block_ldj(ldj, an, sldj, z.size(1), channel_padding_mask, length)
+        ldj = None if ldj_acc is not None else ldj
     return (out[0], ldj, {}) + ((out[2],) if out_mask is not None else ())
 
 
@@ -32,6 +44,9 @@ def _next_coupling_mask(order, pos):
     """Channel mask [1, C] of the layer at ``pos`` when that layer accepts a pre-masked input, else None."""
     nxt = order[pos][1] if pos < len(order) else None
     if getattr(nxt, "accepts_masked_input", False) and nxt.mask.dim() == 2 and nxt.mask.size(0) == 1:
+        needs = getattr(nxt, "needs_masked_input", None)
+        if needs is not None and not needs():
+            return None           # the layer folds its mask into its projection weight: no masked copy of z is needed
         return nxt.mask
     return None
 
@@ -52,6 +67,7 @@ class FlowModel(nn.Module):
         self.print_overview()
 
     def forward(self, z, ldj=None, reverse=False, get_ldj_per_layer=False, check_nan=True, **kwargs):
+        own_ldj = ldj is None
         if ldj is None:
             ldj = z.new_zeros(z.size(0), dtype=torch.float32)
         order = list(enumerate(self.flow_layers))
@@ -60,6 +76,11 @@ class FlowModel(nn.Module):
         ldj_per_layer = []
         skip = 0
         can_fuse = self.fuse_blocks and not reverse and not get_ldj_per_layer and not torch.is_grad_enabled() and z.is_cuda
+        # evaluation-time fusion also lets kernels add their ldj straight into the running accumulator (never into a
+        # caller-provided tensor: that one is copied once)
+        acc_mode = can_fuse
+        if acc_mode and not own_ldj:
+            ldj = ldj.float().clone()
         masked = None   # z * mask of the upcoming coupling layer, when the previous kernel already produced it
         for pos, (index, layer) in enumerate(order):
             if skip > 0:
@@ -85,11 +106,18 @@ class FlowModel(nn.Module):
             if res is None and can_fuse and type(layer) is ActNormFlow and pos + 1 < len(order) and z.dim() == 3 \
                     and type(order[pos + 1][1]) is InvertibleConv and not layer.training and not order[pos + 1][1].training:
                 # ActNorm + 1x1 conv of a block in one pass, plus the masked input of the coupling that follows
-                res = _actnorm_conv_fused(z, layer, order[pos + 1][1], _next_coupling_mask(order, pos + 2), **kwargs)
+                res = _actnorm_conv_fused(z, layer, order[pos + 1][1], _next_coupling_mask(order, pos + 2),
+                                          ldj_acc=ldj if acc_mode else None, **kwargs)
                 skip = 1
             if res is not None and len(res) == 4:
                 masked = res[3]
                 res = res[:3]
+            if res is None and acc_mode and hasattr(layer, "forward_accumulate") and not layer.training:
+                z_acc = layer.forward_accumulate(z, ldj, **extra, **kwargs)      # ldj added in the kernel
+                if z_acc is not None:
+                    z = z_acc
+                    ldj_per_layer.append({})
+                    continue
             if res is None:
                 res = layer(z, reverse=reverse, get_ldj_per_layer=get_ldj_per_layer, **extra, **kwargs)
             if len(res) == 2:
@@ -99,7 +127,8 @@ class FlowModel(nn.Module):
                 z, layer_ldj, detail = res
             else:
                 raise ValueError("[!] ERROR: Got more return values than expected: %i (layer %i)" % (len(res), index + 1))
-            ldj = ldj + layer_ldj
+            if layer_ldj is not None:       # None: the kernel(s) accumulated into `ldj` already
+                ldj = ldj + layer_ldj
             if isinstance(detail, list):
                 ldj_per_layer += detail
             else:

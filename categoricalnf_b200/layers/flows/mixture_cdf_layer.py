@@ -114,42 +114,78 @@ class MixtureCDFCoupling(CouplingLayer):
 
     accepts_masked_input = True   # FlowModel may hand over `cnf_masked_input` = z * mask made by the previous kernel
 
+    def needs_masked_input(self):
+        """False when the network IS its final Linear applied to the masked input (``nn.cnf_features_are_input``, e.g. a
+        per-position linear conditioner): ``(z * mask) @ W^T == z @ (W * mask)^T`` exactly, so at evaluation time the mask
+        is folded into the weight columns once per parameter version and no masked copy of z is ever made."""
+        return not (getattr(self.nn, "cnf_features_are_input", False) and self.mask.dim() == 2 and self.mask.size(0) == 1
+                    and not torch.is_grad_enabled() and self.fuse_final_projection)
+
+    def _mask_folded_weight(self, lin):
+        key = (ops.param_epoch(), lin.weight._version, lin.weight.data_ptr(), self.mask._version, self.mask.data_ptr())
+        hit = self.__dict__.get("_cnf_folded")
+        if hit is None or hit[0] != key:
+            with torch.no_grad():
+                w = (lin.weight * self.mask.reshape(1, -1).to(lin.weight.dtype)).contiguous()
+            hit = (key, w)
+            self.__dict__["_cnf_folded"] = hit
+        return hit[1]
+
     def forward(self, z, ldj=None, reverse=False, channel_padding_mask=None, cnf_masked_input=None, **kwargs):
         # the incoming ldj is ignored and only this layer's ldj is returned, as upstream (:46-47,:63)
         res = self._forward_impl(z, reverse, channel_padding_mask, cnf_masked_input, None, kwargs)
         return res[:3]
 
-    def _forward_impl(self, z, reverse, channel_padding_mask, masked_input, fuse, kwargs):
+    def forward_accumulate(self, z, ldj_acc, channel_padding_mask=None, cnf_masked_input=None, **kwargs):
+        """Evaluation-time variant for ``FlowModel``: this layer's ldj is ADDED into ``ldj_acc`` [B] by the kernel itself
+        (no per-layer ldj tensor, no separate add).  -> z_out, or None when the fused projection path is not available
+        (the caller then uses :meth:`forward`)."""
+        res = self._forward_impl(z, False, channel_padding_mask, cnf_masked_input, None, kwargs, ldj_acc=ldj_acc)
+        return None if res is None else res[0]
+
+    def _forward_impl(self, z, reverse, channel_padding_mask, masked_input, fuse, kwargs, ldj_acc=None):
         """``fuse`` = None or (actnorm, conv, next_mask): next-block epilogue of the fused projection kernel.
-        Returns (z_out, ldj, detail[, z_masked]) - or None when ``fuse`` was requested but is not possible."""
+        ``ldj_acc``: accumulate the layer's ldj into this tensor (fused projection path only, else None is returned).
+        Returns (z_out, ldj, detail[, z_masked]) - or None when ``fuse`` / ``ldj_acc`` was requested but is not possible."""
         mask_c, mask_s = mask_lists(self, "mask", z.size(1))
-        x_in = masked_input if masked_input is not None else z * self._prepare_mask(self.mask, z)
         split = self._projection_split(z)
+        if split is None and (fuse is not None or ldj_acc is not None):
+            return None
+        folded = split is not None and not self.needs_masked_input()
+        if folded:
+            x_in = z                      # mask folded into the weight columns below
+        else:
+            x_in = masked_input if masked_input is not None else z * self._prepare_mask(self.mask, z)
         if split is not None:
             features_fn, lin = split
             feats = features_fn(x_in, **kwargs)
-            if feats.dim() == 3 and ops.linear_mixcdf_fusable(z, feats, lin.weight, self.num_mixtures, mask_c=mask_c, mask_s=mask_s):
+            weight = self._mask_folded_weight(lin) if folded else lin.weight
+            if feats.dim() == 3 and ops.linear_mixcdf_fusable(z, feats, weight, self.num_mixtures, mask_c=mask_c, mask_s=mask_s):
                 extra = {}
                 if fuse is not None:
                     actnorm, conv, next_mask = fuse
-                    weight, sldj = conv._get_weight(device_name=str(z.device), inverse=False)
-                    extra = dict(fuse_next=(actnorm.bias, actnorm.scales, weight), next_mask=next_mask)
+                    weight_c, sldj = conv._get_weight(device_name=str(z.device), inverse=False)
+                    extra = dict(fuse_next=(actnorm.bias, actnorm.scales, weight_c), next_mask=next_mask)
                 out = ops.linear_mixcdf(
-                    z, feats, lin.weight, lin.bias, self.num_mixtures, mask_c=mask_c, mask_s=mask_s, pad=channel_padding_mask,
+                    z, feats, weight, lin.bias, self.num_mixtures, mask_c=mask_c, mask_s=mask_s, pad=channel_padding_mask,
                     scaling_factor=self.scaling_factor, mixture_scaling_factor=self.mixture_scaling_factor, reverse=reverse,
-                    reg_max=self.regularizer_max, reg_factor=self.regularizer_factor, training=self.training, want_reg=True,
-                    precision=self.projection_precision, **extra)
+                    reg_max=self.regularizer_max, reg_factor=self.regularizer_factor, training=self.training,
+                    want_reg=ldj_acc is None, precision=self.projection_precision, ldj=ldj_acc, **extra)
                 z_out, ldj, reg = out[:3]
+                if ldj_acc is not None:
+                    return (z_out, None, {})
                 detail = {"ldj": ldj, "regularizer_ldj": reg}
                 if fuse is not None:
                     detail = {"ldj": ldj.clone(), "regularizer_ldj": reg}
                     add_next_block_ldj(ldj, actnorm, sldj, z.size(1), channel_padding_mask, kwargs.get("length", None))
                 return (z_out, ldj, detail) + tuple(out[3:])
-            if fuse is not None:
+            if fuse is not None or ldj_acc is not None:
                 return None
+            if folded:
+                feats = features_fn(z * self._prepare_mask(self.mask, z), **kwargs)
             nn_out = lin(feats)     # shape / alignment outside the fused kernel: finish the network as usual
         else:
-            if fuse is not None:
+            if fuse is not None or ldj_acc is not None:
                 return None
             compact = self._compact_projection(z, x_in, mask_c, mask_s, channel_padding_mask, kwargs)
             if compact is not None:

@@ -240,6 +240,8 @@ class StandInNet(torch.nn.Module):
         from categoricalnf_b200.layers.networks import TCLinear
         self.lin = TCLinear(c_in, c_out)
 
+    cnf_features_are_input = True      # the network IS its final Linear: the coupling may fold its mask into the weight
+
     @property
     def cnf_final_linear(self):
         return self.lin
