@@ -121,6 +121,15 @@ class MixtureCDFCoupling(CouplingLayer):
         return not (getattr(self.nn, "cnf_features_are_input", False) and self.mask.dim() == 2 and self.mask.size(0) == 1
                     and not torch.is_grad_enabled() and self.fuse_final_projection)
 
+    def _fused_shape_possible(self, z, lin, mask_c):
+        """Static part of ``cnf_linear_mixcdf_fusable`` (csrc/linear_mixcdf.cu ``fused_shape_ok`` / ``check_fusable``):
+        lets callers that cannot fall back cheaply decide before the network body has been evaluated."""
+        C, K = z.size(2), self.num_mixtures
+        tch = list(range(C)) if mask_c is None else [c for c, m in enumerate(mask_c) if float(m) == 0.0]
+        if not tch or tch != list(range(tch[0], tch[0] + len(tch))):
+            return False
+        return (K, len(tch)) in ((8, 8), (8, 4), (16, 4), (4, 8), (4, 4)) and C % 4 == 0 and C <= 32 and lin.in_features % 4 == 0
+
     def _mask_folded_weight(self, lin):
         key = (ops.param_epoch(), lin.weight._version, lin.weight.data_ptr(), self.mask._version, self.mask.data_ptr())
         hit = self.__dict__.get("_cnf_folded")
@@ -149,8 +158,8 @@ class MixtureCDFCoupling(CouplingLayer):
         Returns (z_out, ldj, detail[, z_masked]) - or None when ``fuse`` / ``ldj_acc`` was requested but is not possible."""
         mask_c, mask_s = mask_lists(self, "mask", z.size(1))
         split = self._projection_split(z)
-        if split is None and (fuse is not None or ldj_acc is not None):
-            return None
+        if (fuse is not None or ldj_acc is not None) and (split is None or not self._fused_shape_possible(z, split[1], mask_c)):
+            return None           # decided BEFORE the network body runs: the caller falls back to forward()
         folded = split is not None and not self.needs_masked_input()
         if folded:
             x_in = z                      # mask folded into the weight columns below
