@@ -454,3 +454,29 @@ def test_graphcnf_full_size_spot_check_vs_reference():
     assert_close(ldj[idx.cuda()], ldj_ref, rtol=1e-4, atol=5e-4, what="ldj")
     rel = ((ldj[idx.cuda()].cpu().double() - ldj_ref.double()).abs() / ldj_ref.double().abs()).max().item()
     assert rel <= 1e-4, "pure relative ldj deviation %.3e" % rel
+
+
+def test_coupling_networks_run_once_per_forward():
+    """The evaluation-time fast paths of FlowModel (accumulate / next-block forms) must decide BEFORE a coupling network
+    has been evaluated whether they apply: a fallback after the fact would run the RGCN twice (caught by the N = 2 bench
+    run of round 2: graph colouring 18 -> 36 ms).  ``RGCNNet.cnf_features`` is the body of the network on every path
+    (``forward`` calls it as well), so it must run exactly once per coupling layer and pass."""
+    from categoricalnf_b200.layers.networks import graph_layers as GL
+    g = load_golden("graph_node_flow")
+    model = _build_flow(g)
+    orig = GL.RGCNNet.cnf_features
+    calls = {"n": 0}
+
+    def counted(self, *a, **k):
+        calls["n"] += 1
+        return orig(self, *a, **k)
+
+    GL.RGCNNet.cnf_features = counted
+    try:
+        with torch.no_grad():
+            z, ldj = model(g.x.cuda(), adjacency=g.adjacency.cuda(), length=g.length.cuda(), u_noise=g.u.cuda())
+    finally:
+        GL.RGCNNet.cnf_features = orig
+    n_couplings = sum(1 for layer in model.flow_layers if isinstance(getattr(layer, "nn", None), GL.RGCNNet))
+    assert n_couplings >= 2 and calls["n"] == n_couplings, "RGCN bodies evaluated %d times for %d couplings" % (calls["n"], n_couplings)
+    assert_close(ldj, g.ldj, rtol=1e-4, atol=2e-4, what="ldj")
