@@ -367,7 +367,8 @@ def run_molecule_training(c: Ctx, model, ops):
     model.train()
     params = [p for p in model.parameters() if p.requires_grad]
     n_params = sum(p.numel() for p in params)
-    red = GradientReducer(params, bucket_bytes=32 << 20, profile=True)
+    use_graph = B <= 128
+    red = GradientReducer(params, bucket_bytes=32 << 20, profile=True, hooks=not use_graph)
     opt = torch.optim.Adam(params, lr=1e-5, fused=True)
     state = {}
 
@@ -381,6 +382,25 @@ def run_molecule_training(c: Ctx, model, ops):
         opt.step()
         state["loss"] = loss.detach()
 
+    # small shards (N = 8: 64 molecules per GPU) are launch-bound (~2300 launches per step): replay forward + backward from
+    # a CUDA graph (GraphedTrainingStep) and reduce the gradients right after the replay
+    graphed = None
+    if use_graph:
+        from categoricalnf_b200.experiments.molecule_generation import GraphedTrainingStep
+        ar = torch.arange(N, device=dev)
+
+        def loss_fn(z, ldj, length):
+            pad = (ar[None, :] < length[:, None]).to(z.dtype).unsqueeze(-1)
+            logp = (model.prior_distribution.log_prob(z) * pad).sum(dim=[1, 2])
+            return (-(ldj + logp) / length.to(ldj.dtype)).mean()
+        graphed = GraphedTrainingStep(model, loss_fn=loss_fn)
+
+        def train_step():      # noqa: F811
+            state["loss"] = graphed(xc, ac, lc)
+            red.reduce_now()
+            red.finish()
+            opt.step()
+
     steps = max(2, min(c.steps, 3))
     try:
         train_step()
@@ -393,14 +413,17 @@ def run_molecule_training(c: Ctx, model, ops):
         nbytes, comm_ms, bus = red.comm_stats()
         nsteps = steps + c.warmup
         ops.check_status(dev, "bench molecule_generation training")
+        mode = ("forward + backward replayed from a CUDA graph (GraphedTrainingStep), gradients copied into %d flat buckets and "
+                "all-reduced on a communication stream right after the replay, fused Adam" % len(red.buckets)) if graphed is not None \
+            else ("eager; gradients reduced bucket by bucket on a communication stream while backward runs "
+                  "(%d flat buckets of <= 32 MiB, p.grad = views), fused Adam" % len(red.buckets))
         rec = {"name": "molecule_generation_train", "baseline_config": "configs[3], training step", "unit": "graphs/s",
                "metric": "GraphCNF training step (fwd + bwd + gradient all-reduce + Adam) graphs/sec",
                "value": Bg / (ms * 1e-3), "ms_per_step": ms, "steps": steps, "warmup": c.warmup, "scaling": "strong",
                "global_batch": Bg, "batch_per_gpu": B, "parameters": n_params, "gpu_launches_per_step": launches,
-               "mode": "eager; gradients reduced bucket by bucket on a communication stream while backward runs "
-                       "(%d flat buckets of <= 32 MiB, p.grad = views), fused Adam" % len(red.buckets),
-               "loss": float(state["loss"]), "dtype": "f32 (projections 3xTF32)",
-               "collective": {"kind": "NCCL all-reduce (sum) of the flat gradient buckets, overlapped with backward",
+               "mode": mode, "loss": float(state["loss"]), "dtype": "f32 (projections 3xTF32)",
+               "collective": {"kind": "NCCL all-reduce (sum) of the flat gradient buckets" +
+                                      (", overlapped with backward" if graphed is None else ", after the graph replay"),
                               "bytes_per_step": nbytes / nsteps if c.world > 1 else 0,
                               "comm_stream_ms_per_step": comm_ms / nsteps if c.world > 1 else 0.0,
                               "bus_GBps": bus, "bus_formula": "2 (N-1) / N x bytes / time on the communication stream"}}

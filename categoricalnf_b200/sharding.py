@@ -165,7 +165,10 @@ class GradientReducer:
       them; if a training loop does that anyway the hook copies the fresh gradient into its slot - still correct,
       one small copy per parameter slower)."""
 
-    def __init__(self, params: Iterable[torch.nn.Parameter], bucket_bytes: int = 32 << 20, group=None, profile=False):
+    def __init__(self, params: Iterable[torch.nn.Parameter], bucket_bytes: int = 32 << 20, group=None, profile=False,
+                 hooks: bool = True):
+        """``hooks=False``: no autograd hooks are registered - for gradients produced outside autograd's view (CUDA-graph
+        replay of a whole training step); use :meth:`reduce_now` + :meth:`finish` after each step."""
         self.group = group
         self.profile = profile     # record CUDA events around every bucket's all-reduce on the communication stream
         self.comm_events = []
@@ -187,8 +190,9 @@ class GradientReducer:
         self.stream = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
         self.count = torch.zeros(1, dtype=torch.float64, device=dev)
         self.bytes_reduced = 0
-        self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params]
-        self.zero_grad()
+        self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params] if hooks else []
+        if hooks:
+            self.zero_grad()
 
     def _make_bucket(self, ps):
         n = sum(p.numel() for p in ps)
@@ -240,6 +244,26 @@ class GradientReducer:
             b["done"].record(self.stream)
             if self.profile:
                 self.comm_events.append((b["flat"].numel() * 4, e0, b["done"]))
+
+    def reduce_now(self):
+        """For gradients that did NOT come through the hooks - e.g. left in ``p.grad`` by a CUDA-graph replay of the whole
+        training step (``GraphedTrainingStep``: no autograd runs at replay time) - copy them into the flat buckets (one
+        multi-tensor copy per bucket), point ``p.grad`` at the views and issue every bucket's all-reduce on the
+        communication stream.  Follow with :meth:`finish`."""
+        for b in self.buckets:
+            src, dst = [], []
+            for p, v in zip(b["params"], b["views"]):
+                if p.grad is None:
+                    v.zero_()
+                elif p.grad is not v and p.grad.data_ptr() != v.data_ptr():
+                    src.append(p.grad)
+                    dst.append(v)
+            if src:
+                torch._foreach_copy_(dst, src)
+            for p, v in zip(b["params"], b["views"]):
+                p.grad = v
+            b["pending"], b["issued"] = 0, False
+            self._issue(b)
 
     def comm_stats(self):
         """(bytes reduced, ms on the communication stream, bus GB/s = 2 (N-1) / N x bytes / time) of the recorded buckets

@@ -168,3 +168,19 @@ def test_overlapped_gradient_reducer_and_weighted_average():
                 assert torch.allclose(got, w, atol=1e-6), key
         for k in range(3):
             assert res[r]["ll%d" % k].tolist() == [float(sum(range(B))) + 2 * k, float(B)]
+
+
+def test_reduce_now_without_hooks_single_process():
+    """``GradientReducer(hooks=False)`` + ``reduce_now()``: gradients produced outside autograd's view (a CUDA-graph replay
+    leaves them in ``p.grad``) are copied into the flat buckets, ``p.grad`` becomes the bucket view, values unchanged."""
+    model = _model()
+    red = SH.GradientReducer(model.parameters(), bucket_bytes=64, hooks=False)
+    x = torch.randn(5, 4)
+    model(x).sum().backward()
+    want = [p.grad.clone() for p in model.parameters()]
+    red.reduce_now()
+    red.finish()
+    for p, w in zip(model.parameters(), want):
+        assert torch.equal(p.grad, w)
+        assert p.grad.data_ptr() == red._owner[id(p)][1].data_ptr()
+    red.close()
