@@ -18,6 +18,7 @@
 //   precision 1  3xTF32: x W^T ~= hi hi + lo hi + hi lo, fp32 accumulation in tensor memory - error ~1e-6,
 //                inside the 1e-4 parity budget of the flow transforms fed by this projection
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "cnf_common.cuh"
 #include "tc_ptx.cuh"
@@ -384,6 +385,11 @@ struct GemmDesc {
     int split_k;      // 1: split the reduction over the grid and red.add the partial tiles into y (y pre-initialised)
 };
 
+static bool auto_block_n_off() {
+    static const bool off = getenv("CNF_B200_LINEAR_WIDE_TILES") != nullptr;      // A/B switch: always the widest N tile
+    return off;
+}
+
 int launch_gemm(const GemmDesc& g, const char* who, cudaStream_t stream) {
     CNF_SUPPORTED(g.Mg < (1ll << 31) - 256 && g.R < (1ll << 31) - 256, "%s: dimension too large for 32-bit TMA coordinates", who);
     CNF_SUPPORTED((g.a_mn ? g.Mg : g.R) % 4 == 0 && (g.b_mn ? (long long)g.Ng : g.R) % 4 == 0,
@@ -392,12 +398,33 @@ int launch_gemm(const GemmDesc& g, const char* who, cudaStream_t stream) {
     p.bias = g.bias; p.y = g.y; p.M = g.Mg; p.N = g.Ng; p.K = (int)g.R; p.act = g.act;
     p.a_mn = g.a_mn; p.b_mn = g.b_mn;
     tc_pick_block_n(g.Ng, &p.block_n, &p.n_tiles);
+    p.k_blocks = (int)((g.R + kBK - 1) / kBK);
+    p.m_tiles = (g.Mg + kBM - 1) / kBM;
     if (g.block_n >= 32 && g.block_n <= 256 && g.block_n % 32 == 0) {
         p.block_n = g.block_n;
         p.n_tiles = (g.Ng + g.block_n - 1) / g.block_n;
+    } else if (!g.split_k && !auto_block_n_off() && p.m_tiles * p.n_tiles <= 2 * sm_count()) {
+        // Few tiles - less than two waves of the widest N tile; larger problems keep it (measured 0.91 of the TF32 peak
+        // there) - e.g. the projections of a 64-molecule shard, M = 2432 is 19 row tiles: the widest N tile leaves most SMs
+        // idle and - at 96 KB per 3xTF32 stage - runs on a 2-deep ring.  Choose the N tile that minimises
+        // waves x time per tile, time per tile ~ k_blocks x (a + b block_n) + c (a: the A tile and per-k-block latencies,
+        // b: B tile traffic + MMA time per column, c: prologue + epilogue; measured on B200: one 256-wide 3xTF32 k-block
+        // ~1.5 us).  Narrower tiles also buy ring depth: 64 KB per stage at 128 columns (3 stages), 48 KB at 64 (4).
+        const long long sms_ = sm_count();
+        double best = 1e30;
+        int best_bn = p.block_n;
+        for (int bn = 256; bn >= 32; bn -= 32) {
+            const int nt = (g.Ng + bn - 1) / bn;
+            if (bn != 256 && (nt - 1) * bn >= g.Ng) continue;
+            if (bn > 32 && (g.Ng + nt - 1) / nt + 31 < bn) continue;      // same tile count fits a narrower tile: that one is listed too
+            const long long tiles = p.m_tiles * nt;
+            const double waves = (double)((tiles + sms_ - 1) / sms_);
+            const double t = waves * (p.k_blocks * (0.25 + 1.25 * bn / 256.0) + 3.0);
+            if (t < best - 1e-9) { best = t; best_bn = bn; }
+        }
+        p.block_n = best_bn;
+        p.n_tiles = (g.Ng + best_bn - 1) / best_bn;
     }
-    p.k_blocks = (int)((g.R + kBK - 1) / kBK);
-    p.m_tiles = (g.Mg + kBM - 1) / kBM;
     const long long base_tiles = p.m_tiles * p.n_tiles;
     const long long sms = sm_count();
     long long splits = 1;

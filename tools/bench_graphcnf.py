@@ -19,6 +19,7 @@ ap.add_argument("--train", action="store_true", help="also time a training step 
 ap.add_argument("--cprofile", action="store_true", help="host-side cProfile of the forward pass (where the launch-bound time goes)")
 ap.add_argument("--fwd-batch", type=int, default=64)
 ap.add_argument("--inv-batch", type=int, default=1024)
+ap.add_argument("--gemm-shapes", action="store_true", help="per-shape table of the projection launches of one forward pass (ops.linear_profile)")
 args = ap.parse_args()
 
 from categoricalnf_b200 import ops
@@ -115,6 +116,22 @@ if True:
         out["graphed_fwd_ms"] = timed(gfwd, args.reps * 2)
     out["graphed_fwd_graphs_per_s"] = Bf / out["graphed_fwd_ms"] * 1e3
     out["graph_captures"] = graphed.captures
+if args.gemm_shapes:
+    ops.linear_profile = []
+    with torch.no_grad():
+        fwd()
+    torch.cuda.synchronize()
+    prof, ops.linear_profile = ops.linear_profile, None
+    tab = {}
+    for (M, Nn, K, prec, e0, e1) in prof:
+        t = tab.setdefault((M, Nn, K, prec), [0, 0.0])
+        t[0] += 1
+        t[1] += e0.elapsed_time(e1)
+    rows = sorted(tab.items(), key=lambda kv: -kv[1][1])
+    out["gemm_shapes"] = [{"M": k[0], "N": k[1], "K": k[2], "precision": k[3], "launches": v[0], "total_ms": round(v[1], 3),
+                           "mean_us": round(v[1] / v[0] * 1e3, 1),
+                           "mma_tflops": round((3 if k[3] == "3xtf32" else 1) * 2.0 * k[0] * k[1] * k[2] * v[0] / v[1] / 1e9, 1)} for k, v in rows]
+    out["gemm_total_ms"] = sum(v[1] for v in tab.values())
 if args.train:
     model.train()
     params_ = [p_ for p_ in model.parameters() if p_.requires_grad]
