@@ -180,6 +180,16 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def same_on_all_ranks(n, dev, dist):
+    """A step count derived from a LOCAL timing must be agreed on before it drives a loop that issues collectives: every rank
+    takes the maximum (ranks with different counts would wait for each other's all-reduces forever)."""
+    if dist is None:
+        return int(n)
+    t = torch.tensor([int(n)], dtype=torch.int64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return int(t.item())
+
+
 def workload_config(n_gpus, extra=None):
     cfg = {"workload": "language_modeling: synthetic char-level tokens, seq 256, d=16, V=51, 8 x [ActNorm, InvConv1x1, "
                        "MixtureCDFCoupling K=8], batch 4096 per GPU",
@@ -251,7 +261,7 @@ def run_gpu(args, rank, local_rank, world):
     ms_total = ev0.elapsed_time(ev1)
     launches = ops.launch_count() - launches0
     # the same step sustained for >= 1 s (the timed region above is K steps = tens of milliseconds)
-    sus_n = max(args.steps, int(1100.0 / (ms_total / args.steps)) + 1)
+    sus_n = same_on_all_ranks(max(args.steps, int(1100.0 / (ms_total / args.steps)) + 1), dev, dist if distributed else None)
     ev0.record()
     for i in range(sus_n):
         ldj, ll = step(args.warmup + args.steps + i)
@@ -359,7 +369,7 @@ def run_gpu(args, rank, local_rank, world):
     e2e_ms_total = e0.elapsed_time(e1)
     ops.check_status(dev, "bench e2e leg")
     clk = clocks.stop() if rank == 0 else None
-    e2e_sus_n = max(args.steps, int(1100.0 / (e2e_ms_total / args.steps)) + 1)
+    e2e_sus_n = same_on_all_ranks(max(args.steps, int(1100.0 / (e2e_ms_total / args.steps)) + 1), dev, dist if distributed else None)
     e0.record()
     e2e_run(e2e_sus_n)
     reducer.finish()
