@@ -163,6 +163,17 @@ class MixtureCDFCoupling(CouplingLayer):
         folded = split is not None and not self.needs_masked_input()
         if folded:
             x_in = z                      # mask folded into the weight columns below
+        elif split is None and fuse is None and ldj_acc is None and self._train_fold_possible(z, mask_s):
+            # training step with a per-position linear network: the mask goes into the (tiny) weight instead of two
+            # elementwise passes over z (z * mask forward, grad * mask backward) - see _compact_projection
+            compact = self._compact_projection(z, None, mask_c, mask_s, channel_padding_mask, kwargs)
+            if compact is not None:
+                z_out, ldj, reg = CF.mixcdf(z, compact, self.num_mixtures, self.scaling_factor, self.mixture_scaling_factor,
+                                            mask_c=mask_c, mask_s=mask_s, pad=channel_padding_mask, reverse=reverse,
+                                            reg_max=self.regularizer_max, reg_factor=self.regularizer_factor,
+                                            training=self.training, compact=True)
+                return z_out, ldj, {"ldj": ldj, "regularizer_ldj": reg}
+            x_in = masked_input if masked_input is not None else z * self._prepare_mask(self.mask, z)
         else:
             x_in = masked_input if masked_input is not None else z * self._prepare_mask(self.mask, z)
         if split is not None:
@@ -217,8 +228,15 @@ class MixtureCDFCoupling(CouplingLayer):
     # channels in dL/dnn_out.  Gradients of the skipped weight rows are exactly zero in the reference too.
     compact_projection_in_training = True
 
+    def _train_fold_possible(self, z, mask_s):
+        return (self.compact_projection_in_training and torch.is_grad_enabled() and z.is_cuda and z.dim() == 3 and mask_s is None
+                and getattr(self.nn, "cnf_features_are_input", False) and self.mask.dim() == 2 and self.mask.size(0) == 1)
+
     def _compact_projection(self, z, x_in, mask_c, mask_s, channel_padding_mask, kwargs):
-        """Compact network output [B,S,Ct*(2+3K)] (differentiable), or None when this configuration does not allow it."""
+        """Compact network output [B,S,Ct*(2+3K)] (differentiable), or None when this configuration does not allow it.
+        ``x_in`` None: the network is its final Linear on the masked input (``_train_fold_possible``) - the projection runs
+        on the UNMASKED z with the mask folded into the weight columns, ``(z * m) W^T = z (W * m)^T``: the weight gradient
+        flows back through that [rows, C] multiply, and the gradient wrt z comes out of the GEMM already masked."""
         if not (self.compact_projection_in_training and torch.is_grad_enabled() and z.is_cuda and z.dim() == 3):
             return None
         if mask_c is None or mask_s is not None:
@@ -239,12 +257,20 @@ class MixtureCDFCoupling(CouplingLayer):
         probe = z.new_empty(z.shape[0], z.shape[1], r1 - r0)
         if ops.mixcdf_path(z, probe, self.num_mixtures, mask_c=mask_c, compact=True) == "generic":
             return None
-        feats = features_fn(x_in, **kwargs)
+        weight = lin.weight[r0:r1]
+        if x_in is None:
+            if lin.in_features != z.shape[-1]:
+                return None
+            feats = z
+            weight = weight * self.mask.reshape(1, -1).to(weight.dtype)
+        else:
+            feats = features_fn(x_in, **kwargs)
         if feats.dim() != 3:
             return None
         from ..networks.linear import _TCLinearFn
         bias = None if lin.bias is None else lin.bias[r0:r1]
-        out = _TCLinearFn.apply(feats.reshape(-1, feats.shape[-1]), lin.weight[r0:r1], bias, self.projection_precision)
+        weight._cnf_cache_lo = True       # a weight block: its 3xTF32 split is made once per call, not once per tile (ops.weight_split)
+        out = _TCLinearFn.apply(feats.reshape(-1, feats.shape[-1]), weight, bias, self.projection_precision)
         # (no pad multiply here: channel_padding_mask is bound by forward() and never reaches run_network, App. B #3)
         return out.view(z.shape[0], z.shape[1], r1 - r0)
 
