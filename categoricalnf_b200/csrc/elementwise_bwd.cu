@@ -145,6 +145,74 @@ __global__ void actnorm_bwd_kernel(const ActNormBwdParams p) {
     block_channel_add(s_acc, p.gscales, gs, c, p.C);
 }
 
+// C % 4 == 0: four channels per thread with 16-byte streaming accesses; the thread's channels stay fixed over its
+// grid-stride loop (block size and grid stride are multiples of C / 4), the position index - needed for the padding mask
+// only - comes from a float-reciprocal division instead of a 64-bit one per element (the scalar kernel above: 116 us for
+// the 201 MB of the LM shape, instruction bound).
+__global__ void actnorm_bwd4_kernel(const ActNormBwdParams p) {
+    __shared__ float s_acc[CNF_MAX_CHANNELS];
+    const int C4 = p.C >> 2;
+    const long long n4 = p.n >> 2;
+    const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const int c0 = (int)(gtid % C4) * 4;
+    float e[4], b[4], gb[4], gs[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float s = p.scales[c0 + j];
+        e[j] = __expf(p.reverse ? -s : s);
+        b[j] = p.bias[c0 + j];
+        gb[j] = 0.f;
+        gs[j] = 0.f;
+    }
+    for (long long i = gtid; i < n4; i += stride) {
+        const float pv = p.pad ? p.pad[i / C4] : 1.0f;
+        const float4 g = ldg_stream4(reinterpret_cast<const float4*>(p.gz_out) + i);
+        const float4 x = ldg_stream4(reinterpret_cast<const float4*>(p.z) + i);
+        const float go[4] = {g.x * pv, g.y * pv, g.z * pv, g.w * pv};
+        const float xv[4] = {x.x, x.y, x.z, x.w};
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            o[j] = go[j] * e[j];
+            if (!p.reverse) {
+                gb[j] += o[j];
+                gs[j] += o[j] * (xv[j] + b[j]);
+            } else {
+                gb[j] -= go[j];
+                gs[j] -= o[j] * xv[j];
+            }
+        }
+        stg_stream4(reinterpret_cast<float4*>(p.gz) + i, make_float4(o[0], o[1], o[2], o[3]));
+    }
+    if (p.gldj != nullptr && blockIdx.x == 0) {
+        // ldj[b] += (+/-) sum_c s_c len_b -> dL/ds_c += (+/-) sum_b gldj[b] len_b (same for every channel): the threads of
+        // the first block that share a channel group split the samples
+        float t = 0.f;
+        for (long long bi = threadIdx.x / C4; bi < p.B; bi += blockDim.x / C4) {
+            float len;
+            if (p.length) len = p.length[bi];
+            else if (p.pad) { len = 0.f; for (int q = 0; q < p.S; ++q) len += p.pad[bi * p.S + q]; }
+            else len = (float)p.S;
+            t += p.gldj[bi] * len;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) gs[j] += p.reverse ? -t : t;
+    }
+    for (int i = threadIdx.x; i < 2 * p.C; i += blockDim.x) s_acc[i] = 0.f;      // [gb | gs], 2 C <= CNF_MAX_CHANNELS checked by the launcher
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (gb[j] != 0.f) atomicAdd(s_acc + c0 + j, gb[j]);
+        if (gs[j] != 0.f) atomicAdd(s_acc + p.C + c0 + j, gs[j]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < p.C; i += blockDim.x) {
+        if (p.gbias && s_acc[i] != 0.f) atomicAdd(p.gbias + i, s_acc[i]);
+        if (p.gscales && s_acc[p.C + i] != 0.f) atomicAdd(p.gscales + i, s_acc[p.C + i]);
+    }
+}
+
 // --------------------------------------------------------------------------------------------
 // ExtActNorm: ext = [bias | raw scale] per element, s = tanh(raw)
 // --------------------------------------------------------------------------------------------
@@ -253,6 +321,103 @@ __global__ void __launch_bounds__(256) invconv_bwd_kernel(const ConvBwdParams p)
     }
 }
 
+// C = 16: thread per position.  The tile kernel above issues two shared-memory loads per FMA (l1tex-bound: 164 us for the
+// 201 MB of the LM shape); here a thread keeps its position's z and g rows in registers:
+//   dL/dz  : 16 dot products against W rows read as 16-byte shared-memory broadcasts (4 FMA per load)
+//   dL/dW  : the warp's 32 rows are staged in a per-warp shared-memory tile (16-byte chunk j of row r at chunk
+//            j ^ ((r >> 1) & 3): conflict-free row writes), then lane l accumulates the 8 entries (c = l / 2,
+//            o = 8 (l % 2) ..) of z^T g over the 32 rows - 3 loads per 8 FMA - in registers across all of its tiles;
+//            one shared + one global atomic per entry and CTA at the end.
+// No CTA barrier in the position loop.
+__global__ void __launch_bounds__(256) invconv_bwd16_kernel(const ConvBwdParams p) {
+    constexpr int C = 16;
+    __shared__ __align__(16) float s_w[C * C];            // W[c][o]
+    __shared__ __align__(16) float s_zt[8][32 * C];       // per warp: z rows of the current 32 positions (swizzled)
+    __shared__ __align__(16) float s_gt[8][32 * C];       // per warp: g rows
+    __shared__ float s_gw[C * C];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < C * C; i += 256) { s_w[i] = p.w[i]; s_gw[i] = 0.f; }
+    __syncthreads();
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    const int ac = lane >> 1, ao = (lane & 1) * 8;        // this lane's dL/dW entries: row ac, columns ao .. ao + 7
+    float* zt = s_zt[warp];
+    float* gt = s_gt[warp];
+    const int sw = (lane >> 1) & 3;
+    const long long n_round = (p.P + 31) & ~31ll;
+    const long long stride = (long long)gridDim.x * 256;
+    for (long long pos = (long long)blockIdx.x * 256 + tid; pos < n_round; pos += stride) {
+        const bool in = pos < p.P;
+        float4 z4[4], g4[4];
+        const float pv = (in && p.pad) ? p.pad[pos] : 1.0f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            z4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            g4[j] = z4[j];
+            if (in) {
+                z4[j] = ldg_stream4(reinterpret_cast<const float4*>(p.z + pos * C) + j);
+                const float4 g = ldg_stream4(reinterpret_cast<const float4*>(p.gz_out + pos * C) + j);
+                g4[j] = make_float4(g.x * pv, g.y * pv, g.z * pv, g.w * pv);
+            }
+        }
+        if (p.gw != nullptr) {
+            __syncwarp();      // the previous tile's reads are done
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                reinterpret_cast<float4*>(zt + lane * C)[j ^ sw] = z4[j];
+                reinterpret_cast<float4*>(gt + lane * C)[j ^ sw] = g4[j];
+            }
+            __syncwarp();
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r) {
+                const int rs = (r >> 1) & 3;
+                const float zc = zt[r * C + ((((ac >> 2) ^ rs) << 2) | (ac & 3))];
+                const float4 ga = reinterpret_cast<const float4*>(gt + r * C)[(ao >> 2) ^ rs];
+                const float4 gb = reinterpret_cast<const float4*>(gt + r * C)[((ao >> 2) + 1) ^ rs];
+                acc[0] = fmaf(zc, ga.x, acc[0]); acc[1] = fmaf(zc, ga.y, acc[1]);
+                acc[2] = fmaf(zc, ga.z, acc[2]); acc[3] = fmaf(zc, ga.w, acc[3]);
+                acc[4] = fmaf(zc, gb.x, acc[4]); acc[5] = fmaf(zc, gb.y, acc[5]);
+                acc[6] = fmaf(zc, gb.z, acc[6]); acc[7] = fmaf(zc, gb.w, acc[7]);
+            }
+        }
+        if (in) {
+            // dL/dz[c] = sum_o g[o] W[c][o]
+            const float g[16] = {g4[0].x, g4[0].y, g4[0].z, g4[0].w, g4[1].x, g4[1].y, g4[1].z, g4[1].w,
+                                 g4[2].x, g4[2].y, g4[2].z, g4[2].w, g4[3].x, g4[3].y, g4[3].z, g4[3].w};
+            float out[16];
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                float a = 0.f;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4 wv = reinterpret_cast<const float4*>(s_w + c * C)[j];
+                    a = fmaf(g[4 * j], wv.x, a); a = fmaf(g[4 * j + 1], wv.y, a);
+                    a = fmaf(g[4 * j + 2], wv.z, a); a = fmaf(g[4 * j + 3], wv.w, a);
+                }
+                out[c] = a;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                stg_stream4(reinterpret_cast<float4*>(p.gz + pos * C) + j, make_float4(out[4 * j], out[4 * j + 1], out[4 * j + 2], out[4 * j + 3]));
+        }
+    }
+    if (p.gw != nullptr) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (acc[k] != 0.f) atomicAdd(s_gw + ac * C + ao + k, acc[k]);
+        __syncthreads();
+        for (int i = tid; i < C * C; i += 256)
+            if (s_gw[i] != 0.f) atomicAdd(p.gw + i, s_gw[i]);
+    }
+    if (p.gsldj != nullptr && p.gldj != nullptr && blockIdx.x == 0) {
+        float tsum = 0.f;
+        for (long long b = tid; b < p.B; b += 256) tsum += p.gldj[b] * (p.length ? p.length[b] : (float)p.S);
+        tsum = warp_sum(tsum);
+        if (lane == 0 && tsum != 0.f) atomicAdd(p.gsldj, p.reverse ? -tsum : tsum);
+    }
+}
+
 // --------------------------------------------------------------------------------------------
 // logistic log-density: d/dx -(softplus(v) + softplus(-v) + log sigma) = -tanh(v / 2) / sigma, v = (x - mu) / sigma
 // --------------------------------------------------------------------------------------------
@@ -312,6 +477,12 @@ extern "C" int cnf_actnorm_bwd(const cnf_actnorm_bwd_args* a, cnf_stream_t strea
     p.z = a->z; p.bias = a->bias; p.scales = a->scales; p.pad = a->pad; p.length = a->length;
     p.gz_out = a->grad_z_out; p.gldj = a->grad_ldj; p.gz = a->grad_z; p.gbias = a->grad_bias; p.gscales = a->grad_scales;
     p.B = a->B; p.S = (int)a->S; p.C = a->C; p.reverse = a->reverse;
+    if (a->C % 4 == 0 && 2 * a->C <= CNF_MAX_CHANNELS && p.n > 0 &&
+        ((reinterpret_cast<uintptr_t>(a->z) | reinterpret_cast<uintptr_t>(a->grad_z_out) | reinterpret_cast<uintptr_t>(a->grad_z)) & 15) == 0) {
+        const int threads4 = block_for(a->C / 4);
+        actnorm_bwd4_kernel<<<grid_for_threads(p.n / 4, threads4, 4), threads4, 0, stream>>>(p);
+        return launch_status("actnorm_bwd4_kernel");
+    }
     const int threads = block_for(a->C);
     actnorm_bwd_kernel<<<grid_for_threads(p.n > 0 ? p.n : 1, threads), threads, 0, stream>>>(p);
     return launch_status("actnorm_bwd_kernel");
@@ -342,6 +513,14 @@ extern "C" int cnf_invconv_bwd(const cnf_invconv_bwd_args* a, cnf_stream_t strea
     p.z = a->z; p.w = a->weight; p.pad = a->pad; p.length = a->length; p.gz_out = a->grad_z_out; p.gldj = a->grad_ldj;
     p.gz = a->grad_z; p.gw = a->grad_weight; p.gsldj = a->grad_sldj;
     p.B = a->B; p.S = (int)a->S; p.C = a->C; p.reverse = a->reverse;
+    if (a->C == 16 && p.P > 0 &&
+        ((reinterpret_cast<uintptr_t>(a->z) | reinterpret_cast<uintptr_t>(a->grad_z_out) | reinterpret_cast<uintptr_t>(a->grad_z)) & 15) == 0) {
+        long long grid16 = (p.P + 255) / 256;
+        const long long cap16 = (long long)sm_count() * 4;
+        if (grid16 > cap16) grid16 = cap16;
+        invconv_bwd16_kernel<<<(unsigned)grid16, 256, 0, stream>>>(p);
+        return launch_status("invconv_bwd16_kernel");
+    }
     p.TP = a->C <= 16 ? 256 : (a->C <= 32 ? 128 : 64);
     const size_t smem = ((size_t)a->C * (a->C | 1) + 2 * (size_t)p.TP * a->C) * sizeof(float);
     long long grid = (p.P + p.TP - 1) / p.TP;
