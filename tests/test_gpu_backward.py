@@ -120,11 +120,12 @@ def test_affine_backward(reverse, zero_sf):
     grads_close(sg.grad, so.grad, "dL/dscaling_factor", rtol=5e-4, atol_rel=5e-4)
 
 
+@pytest.mark.parametrize("C", [6, 16, 12])      # 6: scalar kernel; 16 / 12: four channels per thread (actnorm_bwd4_kernel)
 @pytest.mark.parametrize("reverse,padded,with_length", [(False, False, False), (False, True, False), (True, True, True), (False, False, True)])
-def test_actnorm_backward(reverse, padded, with_length):
+def test_actnorm_backward(reverse, padded, with_length, C):
     from categoricalnf_b200 import functional as CF
     g = torch.Generator().manual_seed(5)
-    B, S, C = 7, 23, 6
+    B, S = 7, 23
     z = torch.randn(B, S, C, generator=g)
     bias, scales = torch.randn(1, 1, C, generator=g) * 0.3, torch.randn(1, 1, C, generator=g) * 0.3
     wz, wl = torch.randn(B, S, C, generator=g), torch.randn(B, generator=g)
@@ -162,7 +163,8 @@ def test_ext_actnorm_backward(reverse):
     grads_close(eg.grad, eo.grad, "dL/dext")
 
 
-@pytest.mark.parametrize("C,reverse,padded", [(16, False, False), (6, False, True), (2, True, True), (40, False, False)])
+@pytest.mark.parametrize("C,reverse,padded", [(16, False, False), (16, True, True), (16, False, True), (6, False, True), (2, True, True),
+                                               (40, False, False)])
 def test_invconv_backward(C, reverse, padded):
     from categoricalnf_b200 import functional as CF
     g = torch.Generator().manual_seed(11 + C)
