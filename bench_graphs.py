@@ -237,7 +237,7 @@ def run_molecules(c: Ctx):
     x, adj, length = G.molecules(torch.Generator().manual_seed(200), Bg)
     x, adj, length = x[lo:hi].contiguous(), adj[lo:hi].contiguous(), length[lo:hi].contiguous()
     xc, ac, lc = x.to(dev), adj.to(dev), length.to(dev)
-    graphed = GraphedLogLikelihood(model) if B <= 128 else None
+    graphed = GraphedLogLikelihood(model) if B <= G.MOL.get("graph_replay_max", 512) else None
 
     def fwd(xi=xc, ai=ac, li=lc):
         with torch.no_grad():
@@ -367,7 +367,7 @@ def run_molecule_training(c: Ctx, model, ops):
     model.train()
     params = [p for p in model.parameters() if p.requires_grad]
     n_params = sum(p.numel() for p in params)
-    use_graph = B <= 128
+    use_graph = B <= G.MOL.get("graph_replay_max_train", 256)
     red = GradientReducer(params, bucket_bytes=32 << 20, profile=True, hooks=not use_graph)
     opt = torch.optim.Adam(params, lr=1e-5, fused=True)
     state = {}
