@@ -7,12 +7,14 @@ import torch
 from categoricalnf_b200 import ops
 ap = argparse.ArgumentParser()
 ap.add_argument("--reps", type=int, default=30)
+ap.add_argument("--shape", type=int, nargs=3, default=None, help="only this M N K (e.g. for an ncu capture)")
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 shapes = [(2432, 768, 384), (2432, 192, 384), (2432, 384, 768), (2432, 384, 384), (2432, 1152, 384), (2432, 1536, 384),
           (1944, 192, 192), (1944, 388, 192), (27656, 192, 192), (27656, 388, 192), (27656, 384, 192), (9, 12, 64),
           (2432, 384, 8), (9728, 768, 384), (9728, 192, 384)]
-flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+if a.shape:
+    shapes = [tuple(a.shape)]
 for (M, N, K) in shapes:
     x = torch.randn(M, K, device=dev)
     w = torch.nn.Parameter(torch.randn(N, K, device=dev) / K ** 0.5)
