@@ -16,12 +16,21 @@
 // written with coalesced 8-byte stores.  Scaling-factor gradients are reduced in shared memory and leave
 // with one atomic per (CTA, parameter).  Elements outside the fp32-safe range (same test as the forward
 // kernels) are differentiated in float64.
+#include <stdlib.h>
+
 #include "cnf_common.cuh"
+#include "tc_ptx.cuh"
 
 namespace cnf {
 namespace {
 
 constexpr int kThreads = 256;
+
+// shared -> global bulk copy (TMA engine, no tensor map), tracked by the thread's bulk async-group
+__device__ __forceinline__ void bulk_store_rows(void* gdst, const void* ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(tc::smem_addr(ssrc)), "r"(bytes)
+                 : "memory");
+}
 
 struct BwdParams {
     const float* z;
@@ -40,6 +49,8 @@ struct BwdParams {
     MaskView mask;
     int vec_params, vec_out;
     int compact;      // nn / gnn hold the transformed channels' records only: [P, Ct * PN] (needs vec_params && vec_out)
+    int bulk;         // compact layout + 16-byte aligned rows: the tile moves in and out through cp.async.bulk (three loads,
+                      // two stores per tile, issued by one thread) instead of per-thread cp.async / 16-byte store loops
     float reg_max, reg_factor;
     int use_reg;
     int pre;
@@ -67,7 +78,7 @@ struct Mth<double> {
 // element's contribution to d/d mixture_scaling_factor (written only when the parameters are not pre-bounded).
 // Returns false (nothing written) when T = float and the element is outside the fp32-safe range.
 template <typename T, int KT>
-__device__ __forceinline__ bool mix_backward_elem(float xf, float* rec, const float* mfac, float sfac, int Krt, bool pre,
+__device__ __forceinline__ bool mix_backward_elem(float xf, float* rec, const float* mfac, const float* imf, float sfac, int Krt, bool pre,
                                                   float g_out_f, float gl_f, bool use_reg, float reg_max, float reg_factor,
                                                   float* gx_out, float* gsf_out, float* gmsf_k) {
     using M = Mth<T>;
@@ -84,7 +95,9 @@ __device__ __forceinline__ bool mix_backward_elem(float xf, float* rec, const fl
     for (int k = 0; k < K; ++k) {
         const float mf = pre ? 1.0f : mfac[k];
         // the reference bounds the raw log-scales in float32 before its .double() (:157-178)
-        const T ls = pre ? (T)ms[k] : M::th((T)ms[k] * M::rc((T)fmaxf(mf, 1.0f))) * (T)mf;
+        // imf[k] = 1 / max(e^{msf}, 1): a per-(channel, component) constant, tabulated by the caller for the fp32 path (it
+        // was a MUFU.RCP per component and pass: 16 of ~127 MUFU operations per element)
+        const T ls = pre ? (T)ms[k] : M::th((T)ms[k] * (imf ? (T)imf[k] : M::rc((T)fmaxf(mf, 1.0f)))) * (T)mf;
         const T e = M::ex(-ls);
         const T u = (x - (T)mu[k]) * e;
         const T ea = M::ex(-fabs(u));
@@ -129,7 +142,7 @@ __device__ __forceinline__ bool mix_backward_elem(float xf, float* rec, const fl
         const float mf = pre ? 1.0f : mfac[k];
         const float mf_max = fmaxf(mf, 1.0f);
         const T raw = (T)ms[k];
-        const T imf_max = M::rc((T)mf_max);
+        const T imf_max = imf ? (T)imf[k] : M::rc((T)mf_max);
         const T thk = pre ? (T)0 : M::th(raw * imf_max);
         const T ls = pre ? raw : thk * (T)mf;
         const T e = M::ex(-ls);
@@ -188,12 +201,27 @@ __global__ void __launch_bounds__(kThreads) mixcdf_bwd_kernel(const BwdParams p)
     float* s_mfac = s_fac + Ct;                            // [Ct * K] e^{msf}
     float* s_gsf = s_mfac + Ct * K;                        // [Ct]
     float* s_gmsf = s_gsf + Ct;                            // [Ct * K]
-    int* s_jmap = reinterpret_cast<int*>(s_gmsf + Ct * K); // [C] channel -> transformed index or -1
+    float* s_imf = s_gmsf + Ct * K;                        // [Ct * K] 1 / max(e^{msf}, 1)
+    int* s_jmap = reinterpret_cast<int*>(s_imf + Ct * K);  // [C] channel -> transformed index or -1
 
     const long long pos0 = (long long)blockIdx.x * TP;
     const int rows = (int)min((long long)TP, p.P - pos0);
 
-    if (p.vec_params) {
+    __shared__ __align__(8) uint64_t s_bar;
+    if (p.bulk) {
+        // compact layout: the tile's parameter records, z rows and incoming gradient rows are three contiguous runs of global
+        // memory - one bulk copy each, completion on an mbarrier (the per-thread staging loops were ~11 % of the kernel's
+        // instructions)
+        if (tid == 0) {
+            tc::mbar_init(&s_bar, 1);
+            tc::mbar_fence_init();
+            const uint32_t b_par = (uint32_t)rows * (uint32_t)L * 4u, b_row = (uint32_t)rows * (uint32_t)C * 4u;
+            tc::mbar_arrive_expect_tx(&s_bar, b_par + 2u * b_row);
+            tc::bulk_load(s_par, p.nn + pos0 * (long long)L, b_par, &s_bar);
+            tc::bulk_load(s_z, p.z + pos0 * C, b_row, &s_bar);
+            tc::bulk_load(s_g, p.gz_out + pos0 * C, b_row, &s_bar);
+        }
+    } else if (p.vec_params) {
         const int L4 = L >> 2, total = rows * L4;
         const float inv = 1.0f / (float)L4;
         const float4* src = reinterpret_cast<const float4*>(p.nn);
@@ -213,7 +241,7 @@ __global__ void __launch_bounds__(kThreads) mixcdf_bwd_kernel(const BwdParams p)
             cp_async4(s_par + i, p.nn + ((pos0 + r) * C + p.mask.tch[j]) * (long long)PN + pp);
         }
     }
-    {
+    if (!p.bulk) {
         const int n = rows * C;
         for (int i = tid; i < n; i += kThreads) {
             cp_async4(s_z + i, p.z + pos0 * C + i);
@@ -227,11 +255,13 @@ __global__ void __launch_bounds__(kThreads) mixcdf_bwd_kernel(const BwdParams p)
     for (int i = tid; i < Ct * K; i += kThreads) {
         const int j = i / K, k = i - j * K;
         s_mfac[i] = p.msf ? expf(p.msf[p.mask.tch[j] * K + k]) : 1.0f;
+        s_imf[i] = 1.0f / fmaxf(s_mfac[i], 1.0f);
         s_gmsf[i] = 0.f;
     }
     for (int i = tid; i < C; i += kThreads) s_jmap[i] = -1;
     cp_async_wait_all();
-    __syncthreads();
+    __syncthreads();      // (also: the mbarrier initialised by thread 0 is visible to everybody)
+    if (p.bulk) tc::mbar_wait(&s_bar, 0u);
     for (int i = tid; i < Ct; i += kThreads) s_jmap[p.mask.tch[i]] = i;
 
     // ---- one thread per (position, transformed channel) ----------------------------------------
@@ -269,12 +299,12 @@ __global__ void __launch_bounds__(kThreads) mixcdf_bwd_kernel(const BwdParams p)
                 const float gl = (p.gldj ? p.gldj[pos / p.S] : 0.f) * padv;
                 const float x = s_z[r * C + ch];
                 float gx = 0.f;
-                const bool ok = mix_backward_elem<float, KT>(x, rec, s_mfac + j * K, s_fac[j], K, p.pre != 0, g_out, gl, p.use_reg != 0,
+                const bool ok = mix_backward_elem<float, KT>(x, rec, s_mfac + j * K, s_imf + j * K, s_fac[j], K, p.pre != 0, g_out, gl, p.use_reg != 0,
                                                               p.reg_max, p.reg_factor, &gx, &gsf, KT > 0 ? gm : s_gmsf + j * K);
                 if (!ok) {
 #pragma unroll
                     for (int k = 0; k < (KT > 0 ? KT : 1); ++k) gm[k] = 0.f;
-                    mix_backward_elem<double, 0>(x, rec, s_mfac + j * K, s_fac[j], K, p.pre != 0, g_out, gl, p.use_reg != 0, p.reg_max,
+                    mix_backward_elem<double, 0>(x, rec, s_mfac + j * K, nullptr, s_fac[j], K, p.pre != 0, g_out, gl, p.use_reg != 0, p.reg_max,
                                                  p.reg_factor, &gx, &gsf, s_gmsf + j * K);
                 }
                 s_g[r * C + ch] = gx + gzo * (1.0f - padv) * padv;
@@ -317,7 +347,16 @@ __global__ void __launch_bounds__(kThreads) mixcdf_bwd_kernel(const BwdParams p)
     }
 
     // ---- dL/dnn_out rows: gradient records of the transformed channels, zeros elsewhere ----------
-    if (p.vec_params && p.vec_out) {
+    if (p.bulk) {
+        // the gradient records (in place in s_par) and the dL/dz rows leave as two bulk stores
+        tc::fence_proxy_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+            bulk_store_rows(p.gnn + pos0 * (long long)L, s_par, (uint32_t)rows * (uint32_t)L * 4u);
+            bulk_store_rows(p.gz + pos0 * C, s_g, (uint32_t)rows * (uint32_t)C * 4u);
+            tc::tma_store_commit();
+        }
+    } else if (p.vec_params && p.vec_out) {
         // contiguous, 16-byte aligned run of transformed records per position: copy it with 16-byte stores and zero the
         // conditioner records before / after it the same way (no per-granule record lookup)
         const int L4 = L >> 2, row4 = p.compact ? L4 : (C * PN) >> 2, off4 = p.compact ? 0 : (p.mask.c0 * PN) >> 2;
@@ -362,7 +401,7 @@ __global__ void __launch_bounds__(kThreads) mixcdf_bwd_kernel(const BwdParams p)
         }
     }
     // ---- dL/dz rows ----------------------------------------------------------------------------
-    {
+    if (!p.bulk) {
         const int n = rows * C;
         float* dst = p.gz + pos0 * C;
         for (int i = tid; i < n; i += kThreads) dst[i] = s_g[i];
@@ -374,12 +413,13 @@ __global__ void __launch_bounds__(kThreads) mixcdf_bwd_kernel(const BwdParams p)
     if (p.gmsf)
         for (int i = tid; i < Ct * K; i += kThreads)
             if (s_gmsf[i] != 0.f) atomicAdd(p.gmsf + p.mask.tch[i / K] * K + i % K, s_gmsf[i]);
+    if (p.bulk && tid == 0) tc::tma_store_wait_read<0>();      // shared memory must outlive the engine's reads of it
 }
 
 size_t bwd_smem(int TP, int L, int C, int Ct, int K) {
     size_t f = ((size_t)TP * L + 3) & ~(size_t)3;
     f += 2 * (((size_t)TP * C + 3) & ~(size_t)3);
-    f += 2 * (size_t)Ct + 2 * (size_t)Ct * K + (size_t)C;
+    f += 2 * (size_t)Ct + 3 * (size_t)Ct * K + (size_t)C;
     return f * sizeof(float);
 }
 
@@ -442,6 +482,10 @@ extern "C" int cnf_mixcdf_bwd(const cnf_mixcdf_bwd_args* a, cnf_stream_t stream_
         CNF_SUPPORTED(p.vec_params && p.vec_out, "the compact gradient layout needs a contiguous run of transformed channels with "
                                                    "Ct * (2 + 3K) a multiple of 4 and 16-byte aligned nn_out / grad_nn_out");
     }
+    static const bool no_bulk = getenv("CNF_B200_MIXCDF_BWD_NO_BULK") != nullptr;      // A/B switch
+    p.bulk = (p.compact && !no_bulk && (a->C % 4 == 0) &&
+              ((reinterpret_cast<uintptr_t>(a->z) | reinterpret_cast<uintptr_t>(a->grad_z_out) | reinterpret_cast<uintptr_t>(a->grad_z)) & 15) == 0)
+                 ? 1 : 0;
     CNF_REQUIRE((reinterpret_cast<uintptr_t>(a->grad_nn_out) & 7) == 0, "grad_nn_out must be 8-byte aligned");
     CNF_SUPPORTED((long long)TP * a->C * p.PN < (1 << 21), "tile too large for the index arithmetic");
     const size_t smem = bwd_smem(TP, L, a->C, Ct, a->K);
