@@ -49,8 +49,8 @@ struct BwdParams {
     MaskView mask;
     int vec_params, vec_out;
     int compact;      // nn / gnn hold the transformed channels' records only: [P, Ct * PN] (needs vec_params && vec_out)
-    int bulk;         // compact layout + 16-byte aligned rows: the tile moves in and out through cp.async.bulk (three loads,
-                      // two stores per tile, issued by one thread) instead of per-thread cp.async / 16-byte store loops
+    int bulk;         // compact layout + 16-byte aligned rows: mixcdf_bwd_pipe_kernel (persistent CTAs, cp.async.bulk)
+    int nbuf;         // its shared-memory buffers per CTA
     float reg_max, reg_factor;
     int use_reg;
     int pre;
@@ -207,21 +207,7 @@ __global__ void __launch_bounds__(kThreads) mixcdf_bwd_kernel(const BwdParams p)
     const long long pos0 = (long long)blockIdx.x * TP;
     const int rows = (int)min((long long)TP, p.P - pos0);
 
-    __shared__ __align__(8) uint64_t s_bar;
-    if (p.bulk) {
-        // compact layout: the tile's parameter records, z rows and incoming gradient rows are three contiguous runs of global
-        // memory - one bulk copy each, completion on an mbarrier (the per-thread staging loops were ~11 % of the kernel's
-        // instructions)
-        if (tid == 0) {
-            tc::mbar_init(&s_bar, 1);
-            tc::mbar_fence_init();
-            const uint32_t b_par = (uint32_t)rows * (uint32_t)L * 4u, b_row = (uint32_t)rows * (uint32_t)C * 4u;
-            tc::mbar_arrive_expect_tx(&s_bar, b_par + 2u * b_row);
-            tc::bulk_load(s_par, p.nn + pos0 * (long long)L, b_par, &s_bar);
-            tc::bulk_load(s_z, p.z + pos0 * C, b_row, &s_bar);
-            tc::bulk_load(s_g, p.gz_out + pos0 * C, b_row, &s_bar);
-        }
-    } else if (p.vec_params) {
+    if (p.vec_params) {
         const int L4 = L >> 2, total = rows * L4;
         const float inv = 1.0f / (float)L4;
         const float4* src = reinterpret_cast<const float4*>(p.nn);
@@ -241,7 +227,7 @@ __global__ void __launch_bounds__(kThreads) mixcdf_bwd_kernel(const BwdParams p)
             cp_async4(s_par + i, p.nn + ((pos0 + r) * C + p.mask.tch[j]) * (long long)PN + pp);
         }
     }
-    if (!p.bulk) {
+    {
         const int n = rows * C;
         for (int i = tid; i < n; i += kThreads) {
             cp_async4(s_z + i, p.z + pos0 * C + i);
@@ -260,8 +246,7 @@ __global__ void __launch_bounds__(kThreads) mixcdf_bwd_kernel(const BwdParams p)
     }
     for (int i = tid; i < C; i += kThreads) s_jmap[i] = -1;
     cp_async_wait_all();
-    __syncthreads();      // (also: the mbarrier initialised by thread 0 is visible to everybody)
-    if (p.bulk) tc::mbar_wait(&s_bar, 0u);
+    __syncthreads();
     for (int i = tid; i < Ct; i += kThreads) s_jmap[p.mask.tch[i]] = i;
 
     // ---- one thread per (position, transformed channel) ----------------------------------------
@@ -347,16 +332,7 @@ __global__ void __launch_bounds__(kThreads) mixcdf_bwd_kernel(const BwdParams p)
     }
 
     // ---- dL/dnn_out rows: gradient records of the transformed channels, zeros elsewhere ----------
-    if (p.bulk) {
-        // the gradient records (in place in s_par) and the dL/dz rows leave as two bulk stores
-        tc::fence_proxy_async_smem();
-        __syncthreads();
-        if (tid == 0) {
-            bulk_store_rows(p.gnn + pos0 * (long long)L, s_par, (uint32_t)rows * (uint32_t)L * 4u);
-            bulk_store_rows(p.gz + pos0 * C, s_g, (uint32_t)rows * (uint32_t)C * 4u);
-            tc::tma_store_commit();
-        }
-    } else if (p.vec_params && p.vec_out) {
+    if (p.vec_params && p.vec_out) {
         // contiguous, 16-byte aligned run of transformed records per position: copy it with 16-byte stores and zero the
         // conditioner records before / after it the same way (no per-granule record lookup)
         const int L4 = L >> 2, row4 = p.compact ? L4 : (C * PN) >> 2, off4 = p.compact ? 0 : (p.mask.c0 * PN) >> 2;
@@ -401,7 +377,7 @@ __global__ void __launch_bounds__(kThreads) mixcdf_bwd_kernel(const BwdParams p)
         }
     }
     // ---- dL/dz rows ----------------------------------------------------------------------------
-    if (!p.bulk) {
+    {
         const int n = rows * C;
         float* dst = p.gz + pos0 * C;
         for (int i = tid; i < n; i += kThreads) dst[i] = s_g[i];
@@ -413,7 +389,197 @@ __global__ void __launch_bounds__(kThreads) mixcdf_bwd_kernel(const BwdParams p)
     if (p.gmsf)
         for (int i = tid; i < Ct * K; i += kThreads)
             if (s_gmsf[i] != 0.f) atomicAdd(p.gmsf + p.mask.tch[i / K] * K + i % K, s_gmsf[i]);
-    if (p.bulk && tid == 0) tc::tma_store_wait_read<0>();      // shared memory must outlive the engine's reads of it
+}
+
+// Compact layout (nn / dL/dnn_out hold the transformed channels' records only, rows 16-byte aligned): PERSISTENT CTAs over
+// the tiles, data movement by the TMA engine.  A tile's parameter records, z rows and incoming gradient rows are three
+// contiguous runs of global memory: one cp.async.bulk each into one of `nbuf` shared-memory buffers, completion on the
+// buffer's mbarrier; the gradient records (written in place) and the dL/dz rows leave as two bulk stores.  One thread
+// issues everything: after its own element of tile k it waits until the store of tile k-1 has been read out of shared
+// memory (long done) and loads tile k + nbuf - 1 into that buffer, so up to nbuf - 1 loads are in flight under the math.
+// The per-CTA tables (e^{sf}, e^{msf}, 1 / max(e^{msf}, 1)) are built once and the scaling-factor gradients leave with one
+// atomic per (CTA, parameter) at the very end - the tile kernel above pays both per tile of 32 positions (32768 CTAs x 72
+// global atomics at the LM shape).
+template <int KT>
+__global__ void __launch_bounds__(kThreads) mixcdf_bwd_pipe_kernel(const BwdParams p) {
+    extern __shared__ __align__(16) float smem[];
+    __shared__ __align__(8) uint64_t s_full[4];
+    const int tid = threadIdx.x;
+    const int K = KT > 0 ? KT : p.K;
+    const int PN = 2 + 3 * K;
+    const int C = p.C, Ct = p.mask.n_t, TP = p.TP, nbuf = p.nbuf;
+    const int L = Ct * PN;
+    const int buf_floats = TP * L + 2 * TP * C;            // [TP * L | TP * C | TP * C], all multiples of 4 floats
+    float* s_fac = smem + (size_t)nbuf * buf_floats;       // [Ct] e^{sf}
+    float* s_mfac = s_fac + Ct;                            // [Ct * K] e^{msf}
+    float* s_gsf = s_mfac + Ct * K;                        // [Ct]
+    float* s_gmsf = s_gsf + Ct;                            // [Ct * K]
+    float* s_imf = s_gmsf + Ct * K;                        // [Ct * K] 1 / max(e^{msf}, 1)
+    int* s_jmap = reinterpret_cast<int*>(s_imf + Ct * K);  // [C] channel -> transformed index or -1
+
+    for (int i = tid; i < Ct; i += kThreads) {
+        s_fac[i] = p.sf ? expf(p.sf[p.mask.tch[i]]) : 1.0f;
+        s_gsf[i] = 0.f;
+    }
+    for (int i = tid; i < Ct * K; i += kThreads) {
+        const int j = i / K, k = i - j * K;
+        s_mfac[i] = p.msf ? expf(p.msf[p.mask.tch[j] * K + k]) : 1.0f;
+        s_imf[i] = 1.0f / fmaxf(s_mfac[i], 1.0f);
+        s_gmsf[i] = 0.f;
+    }
+    for (int i = tid; i < C; i += kThreads) s_jmap[i] = -1;
+    if (tid == 0) {
+        for (int b = 0; b < nbuf; ++b) tc::mbar_init(&s_full[b], 1);
+        tc::mbar_fence_init();
+    }
+    __syncthreads();
+    for (int i = tid; i < Ct; i += kThreads) s_jmap[p.mask.tch[i]] = i;
+    __syncthreads();
+
+    const long long ntiles = (p.P + TP - 1) / TP;
+    const int n_my = (int)((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x);      // tiles blockIdx.x, + gridDim.x, ...
+    auto issue_load = [&](int k) {      // thread 0 only
+        const long long pos0 = ((long long)blockIdx.x + (long long)k * gridDim.x) * TP;
+        const int rows = (int)min((long long)TP, p.P - pos0);
+        float* bpar = smem + (size_t)(k % nbuf) * buf_floats;
+        const uint32_t b_par = (uint32_t)rows * (uint32_t)L * 4u, b_row = (uint32_t)rows * (uint32_t)C * 4u;
+        uint64_t* bar = &s_full[k % nbuf];
+        tc::mbar_arrive_expect_tx(bar, b_par + 2u * b_row);
+        tc::bulk_load(bpar, p.nn + pos0 * (long long)L, b_par, bar);
+        tc::bulk_load(bpar + TP * L, p.z + pos0 * C, b_row, bar);
+        tc::bulk_load(bpar + TP * L + TP * C, p.gz_out + pos0 * C, b_row, bar);
+    };
+    const int ahead = nbuf > 1 ? nbuf - 1 : 1;
+    if (tid == 0)
+        for (int k = 0; k < ahead && k < n_my; ++k) issue_load(k);
+
+    const bool warp_reduce = KT > 0 && (32 % Ct) == 0 && (kThreads % Ct) == 0;
+    const float inv_ct = 1.0f / (float)Ct;
+    for (int k = 0; k < n_my; ++k) {
+        const long long pos0 = ((long long)blockIdx.x + (long long)k * gridDim.x) * TP;
+        const int rows = (int)min((long long)TP, p.P - pos0);
+        float* s_par = smem + (size_t)(k % nbuf) * buf_floats;
+        float* s_z = s_par + TP * L;
+        float* s_g = s_z + TP * C;
+        tc::mbar_wait(&s_full[k % nbuf], (uint32_t)((k / nbuf) & 1));
+
+        // ---- one thread per (position, transformed channel): TP * Ct <= kThreads elements per tile ----------------------
+        const int nelem = rows * Ct;
+        const int e = tid;
+        float gm[KT > 0 ? KT : 1];
+#pragma unroll
+        for (int kk = 0; kk < (KT > 0 ? KT : 1); ++kk) gm[kk] = 0.f;
+        float gsf = 0.f;
+        int j = 0;
+        if (e < nelem) {
+            const int r = fast_div(e, inv_ct);
+            j = e - r * Ct;
+            const long long pos = pos0 + r;
+            const int ch = p.mask.tch[j];
+            float* rec = s_par + (size_t)e * PN;
+            const float padv = p.pad ? p.pad[pos] : 1.0f;
+            bool active = padv != 0.0f;
+            if (p.mask.s_period > 0) {
+                const int sp = (int)(pos % p.S);
+                if ((p.mask.cond_s >> (sp % p.mask.s_period)) & 1ull) active = false;
+            }
+            const float gzo = s_g[r * C + ch];
+            if (!active) {   // copied through (times pad): no parameter gradient
+                for (int i = 0; i < PN; ++i) rec[i] = 0.f;
+                s_g[r * C + ch] = gzo * padv;
+            } else {
+                const float g_out = gzo * padv * padv;
+                const float gl = (p.gldj ? p.gldj[pos / p.S] : 0.f) * padv;
+                const float x = s_z[r * C + ch];
+                float gx = 0.f;
+                const bool ok = mix_backward_elem<float, KT>(x, rec, s_mfac + j * K, s_imf + j * K, s_fac[j], K, p.pre != 0, g_out, gl,
+                                                              p.use_reg != 0, p.reg_max, p.reg_factor, &gx, &gsf, KT > 0 ? gm : s_gmsf + j * K);
+                if (!ok) {
+#pragma unroll
+                    for (int kk = 0; kk < (KT > 0 ? KT : 1); ++kk) gm[kk] = 0.f;
+                    mix_backward_elem<double, 0>(x, rec, s_mfac + j * K, nullptr, s_fac[j], K, p.pre != 0, g_out, gl, p.use_reg != 0,
+                                                 p.reg_max, p.reg_factor, &gx, &gsf, s_gmsf + j * K);
+                }
+                s_g[r * C + ch] = gx + gzo * (1.0f - padv) * padv;
+            }
+        }
+        if (p.pre == 0 && (p.gsf != nullptr || p.gmsf != nullptr)) {
+            if (warp_reduce) {
+                for (int d = 16; d >= Ct; d >>= 1) {
+                    gsf += __shfl_xor_sync(0xffffffffu, gsf, d);
+#pragma unroll
+                    for (int kk = 0; kk < (KT > 0 ? KT : 1); ++kk) gm[kk] += __shfl_xor_sync(0xffffffffu, gm[kk], d);
+                }
+                const int jj = (tid & 31) % Ct;
+                if ((tid & 31) < Ct) {
+                    if (gsf != 0.f) atomicAdd(s_gsf + jj, gsf);
+#pragma unroll
+                    for (int kk = 0; kk < (KT > 0 ? KT : 1); ++kk)
+                        if (gm[kk] != 0.f) atomicAdd(s_gmsf + jj * K + kk, gm[kk]);
+                }
+            } else if (e < nelem) {
+                if (gsf != 0.f) atomicAdd(s_gsf + j, gsf);
+                if (KT > 0) {
+#pragma unroll
+                    for (int kk = 0; kk < (KT > 0 ? KT : 1); ++kk)
+                        if (gm[kk] != 0.f) atomicAdd(s_gmsf + j * K + kk, gm[kk]);
+                }
+            }
+        }
+        // conditioner channels: dL/dz = dL/dz_out * pad (entries no element thread touches)
+        if (Ct < C && p.pad) {
+            const int n = rows * C;
+            const float inv_c = 1.0f / (float)C;
+            for (int i = tid; i < n; i += kThreads) {
+                const int r = fast_div(i, inv_c), c = i - r * C;
+                if (s_jmap[c] < 0) s_g[i] *= p.pad[pos0 + r];
+            }
+        }
+        // ---- next load, this tile's stores ---------------------------------------------------------------------------
+        if (tid == 0 && nbuf > 1 && k + ahead < n_my) {
+            tc::tma_store_wait_read<0>();      // the store of tile k - 1 has been read out of the buffer tile k + ahead takes
+            issue_load(k + ahead);
+        }
+        tc::fence_proxy_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+            bulk_store_rows(p.gnn + pos0 * (long long)L, s_par, (uint32_t)rows * (uint32_t)L * 4u);
+            bulk_store_rows(p.gz + pos0 * C, s_g, (uint32_t)rows * (uint32_t)C * 4u);
+            tc::tma_store_commit();
+            if (nbuf == 1 && k + 1 < n_my) {      // single buffer: the next tile lands where this one is being read from
+                tc::tma_store_wait_read<0>();
+                issue_load(k + 1);
+            }
+        }
+    }
+    __syncthreads();
+    if (p.gsf)
+        for (int i = tid; i < Ct; i += kThreads)
+            if (s_gsf[i] != 0.f) atomicAdd(p.gsf + p.mask.tch[i], s_gsf[i]);
+    if (p.gmsf)
+        for (int i = tid; i < Ct * K; i += kThreads)
+            if (s_gmsf[i] != 0.f) atomicAdd(p.gmsf + p.mask.tch[i / K] * K + i % K, s_gmsf[i]);
+    if (tid == 0) tc::tma_store_wait_read<0>();      // shared memory must outlive the engine's reads of it
+}
+
+template <int KT>
+int launch_bwd_pipe(BwdParams p, int L, int C, int Ct, int K, cudaStream_t stream) {
+    static const int want = getenv("CNF_B200_MIXCDF_BWD_NBUF") ? atoi(getenv("CNF_B200_MIXCDF_BWD_NBUF")) : 2;      // tuning knob
+    int nbuf = want < 1 ? 1 : (want > 4 ? 4 : want);
+    const size_t buf = ((size_t)p.TP * L + 2 * (size_t)p.TP * C) * sizeof(float);
+    const size_t tables = (2 * (size_t)Ct + 3 * (size_t)Ct * K + (size_t)C) * sizeof(float);
+    while (nbuf > 1 && nbuf * buf + tables > 200 * 1024) --nbuf;
+    p.nbuf = nbuf;
+    const size_t smem = nbuf * buf + tables;
+    CNF_CUDA(cudaFuncSetAttribute(mixcdf_bwd_pipe_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    CNF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mixcdf_bwd_pipe_kernel<KT>, kThreads, smem));
+    if (per_sm < 1) per_sm = 1;
+    const long long ntiles = (p.P + p.TP - 1) / p.TP;
+    long long grid = (long long)per_sm * sm_count();
+    if (grid > ntiles) grid = ntiles;
+    mixcdf_bwd_pipe_kernel<KT><<<(unsigned)grid, kThreads, smem, stream>>>(p);
+    return launch_status("mixcdf_bwd_pipe_kernel");
 }
 
 size_t bwd_smem(int TP, int L, int C, int Ct, int K) {
@@ -488,6 +654,14 @@ extern "C" int cnf_mixcdf_bwd(const cnf_mixcdf_bwd_args* a, cnf_stream_t stream_
                  ? 1 : 0;
     CNF_REQUIRE((reinterpret_cast<uintptr_t>(a->grad_nn_out) & 7) == 0, "grad_nn_out must be 8-byte aligned");
     CNF_SUPPORTED((long long)TP * a->C * p.PN < (1 << 21), "tile too large for the index arithmetic");
+    if (p.bulk && TP * Ct <= kThreads && (TP * L) % 4 == 0) {
+        switch (a->K) {
+            case 4: return launch_bwd_pipe<4>(p, L, a->C, Ct, a->K, stream);
+            case 8: return launch_bwd_pipe<8>(p, L, a->C, Ct, a->K, stream);
+            case 16: return launch_bwd_pipe<16>(p, L, a->C, Ct, a->K, stream);
+            default: return launch_bwd_pipe<0>(p, L, a->C, Ct, a->K, stream);
+        }
+    }
     const size_t smem = bwd_smem(TP, L, a->C, Ct, a->K);
     CNF_SUPPORTED(smem <= 200 * 1024, "C=%d K=%d needs %zu bytes of shared memory per tile", a->C, a->K, smem);
     switch (a->K) {
