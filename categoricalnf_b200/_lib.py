@@ -202,7 +202,7 @@ class MixcdfBwdArgs(C.Structure):
         ("scaling_factor", vp), ("mixture_scaling_factor", vp),
         ("reg_max", C.c_float), ("reg_factor", C.c_float), ("training", C.c_int32), ("params_prebounded", C.c_int32),
         ("grad_z_out", vp), ("grad_ldj", vp), ("grad_z", vp), ("grad_nn_out", vp),
-        ("grad_scaling_factor", vp), ("grad_mixture_scaling_factor", vp), ("nn_compact", C.c_int32),
+        ("grad_scaling_factor", vp), ("grad_mixture_scaling_factor", vp), ("nn_compact", C.c_int32), ("grad_nn_colsum", vp),
     ]
 
 
@@ -341,7 +341,7 @@ ENTRY_POINTS = {
 PLAIN_SYMBOLS = ("cnf_last_error_string", "cnf_abi_version", "cnf_built_for_sm", "cnf_mixcdf_fusable", "cnf_mixcdf_path",
                  "cnf_categ_encode_fusable", "cnf_linear_mixcdf_fusable")
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 _lib = None
 
 

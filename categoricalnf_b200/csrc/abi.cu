@@ -48,5 +48,5 @@ int sm_count() {
 }  // namespace cnf
 
 extern "C" const char* cnf_last_error_string(void) { return cnf::g_err; }
-extern "C" int cnf_abi_version(void) { return 4; }
+extern "C" int cnf_abi_version(void) { return 5; }
 extern "C" int cnf_built_for_sm(void) { return 100; }

@@ -505,6 +505,17 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ g
     }
 }
 
+int tc_colsum(const float* gy, float* gb, long long M, int N, cudaStream_t stream) {
+    const int col_blocks = (N + 31) / 32;
+    long long row_blocks = (4ll * sm_count() + col_blocks - 1) / col_blocks;
+    if (row_blocks > (M + 255) / 256) row_blocks = (M + 255) / 256;
+    if (row_blocks < 1) row_blocks = 1;
+    if (row_blocks > 65535) row_blocks = 65535;
+    const long long rows_per_cta = (M + row_blocks - 1) / row_blocks;
+    colsum_kernel<<<dim3((unsigned)col_blocks, (unsigned)row_blocks), 256, 0, stream>>>(gy, gb, M, N, rows_per_cta);
+    return launch_status("colsum_kernel");
+}
+
 }  // namespace cnf
 
 extern "C" int cnf_linear_fwd(const cnf_linear_args* a, cnf_stream_t stream_) {
@@ -565,16 +576,6 @@ extern "C" int cnf_linear_bwd(const cnf_linear_bwd_args* a, cnf_stream_t stream_
         const int rc = launch_gemm(g, "cnf_linear_bwd (grad_weight)", stream);
         if (rc != CNF_OK) return rc;
     }
-    if (a->grad_bias != nullptr) {
-        const int col_blocks = (a->N + 31) / 32;
-        long long row_blocks = (4ll * sm_count() + col_blocks - 1) / col_blocks;
-        if (row_blocks > (a->M + 255) / 256) row_blocks = (a->M + 255) / 256;
-        if (row_blocks < 1) row_blocks = 1;
-        if (row_blocks > 65535) row_blocks = 65535;
-        const long long rows_per_cta = (a->M + row_blocks - 1) / row_blocks;
-        colsum_kernel<<<dim3((unsigned)col_blocks, (unsigned)row_blocks), 256, 0, stream>>>(a->grad_y, a->grad_bias, a->M, a->N,
-                                                                                             rows_per_cta);
-        return launch_status("colsum_kernel");
-    }
+    if (a->grad_bias != nullptr) return tc_colsum(a->grad_y, a->grad_bias, a->M, a->N, stream);
     return CNF_OK;
 }

@@ -22,6 +22,9 @@
 #include "tc_ptx.cuh"
 
 namespace cnf {
+
+int tc_colsum(const float* gy, float* gb, long long M, int N, cudaStream_t stream);      // linear_tc.cu: gb[n] += sum_m gy[m,n]
+
 namespace {
 
 constexpr int kThreads = 256;
@@ -44,6 +47,7 @@ struct BwdParams {
     float* gnn;
     float* gsf;
     float* gmsf;
+    float* gcol;      // [Ct * PN] += column sums of dL/dnn_out (= the bias gradient of a final Linear), pipe kernel only
     long long P;
     int S, C, K, PN, TP;
     MaskView mask;
@@ -416,6 +420,7 @@ __global__ void __launch_bounds__(kThreads) mixcdf_bwd_pipe_kernel(const BwdPara
     float* s_gmsf = s_gsf + Ct;                            // [Ct * K]
     float* s_imf = s_gmsf + Ct * K;                        // [Ct * K] 1 / max(e^{msf}, 1)
     int* s_jmap = reinterpret_cast<int*>(s_imf + Ct * K);  // [C] channel -> transformed index or -1
+    float* s_col = reinterpret_cast<float*>(s_jmap + C);   // [L] column sums of the gradient records (p.gcol)
 
     for (int i = tid; i < Ct; i += kThreads) {
         s_fac[i] = p.sf ? expf(p.sf[p.mask.tch[i]]) : 1.0f;
@@ -428,6 +433,8 @@ __global__ void __launch_bounds__(kThreads) mixcdf_bwd_pipe_kernel(const BwdPara
         s_gmsf[i] = 0.f;
     }
     for (int i = tid; i < C; i += kThreads) s_jmap[i] = -1;
+    if (p.gcol)
+        for (int i = tid; i < L; i += kThreads) s_col[i] = 0.f;
     if (tid == 0) {
         for (int b = 0; b < nbuf; ++b) tc::mbar_init(&s_full[b], 1);
         tc::mbar_fence_init();
@@ -535,20 +542,28 @@ __global__ void __launch_bounds__(kThreads) mixcdf_bwd_pipe_kernel(const BwdPara
                 if (s_jmap[c] < 0) s_g[i] *= p.pad[pos0 + r];
             }
         }
-        // ---- next load, this tile's stores ---------------------------------------------------------------------------
-        if (tid == 0 && nbuf > 1 && k + ahead < n_my) {
-            tc::tma_store_wait_read<0>();      // the store of tile k - 1 has been read out of the buffer tile k + ahead takes
-            issue_load(k + ahead);
-        }
+        // ---- this tile's stores, next load, column sums ---------------------------------------------------------------
         tc::fence_proxy_async_smem();
         __syncthreads();
         if (tid == 0) {
             bulk_store_rows(p.gnn + pos0 * (long long)L, s_par, (uint32_t)rows * (uint32_t)L * 4u);
             bulk_store_rows(p.gz + pos0 * C, s_g, (uint32_t)rows * (uint32_t)C * 4u);
             tc::tma_store_commit();
-            if (nbuf == 1 && k + 1 < n_my) {      // single buffer: the next tile lands where this one is being read from
-                tc::tma_store_wait_read<0>();
-                issue_load(k + 1);
+            // the load of tile k + ahead goes into the buffer of tile k - nbuf + ahead: for nbuf > 1 an OLDER tile's, whose
+            // store has been read out (all but the group just committed are complete) and whose column sums every thread
+            // finished before the barrier above; a single buffer is the one being read right now
+            if (k + ahead < n_my) {
+                if (nbuf > 1) tc::tma_store_wait_read<1>(); else tc::tma_store_wait_read<0>();
+                issue_load(k + ahead);
+            }
+        }
+        if (p.gcol) {
+            // d/dbias of the network's final Linear = column sums of dL/dnn_out: column tid of the tile's rows, read while
+            // the TMA engine reads the same rows for the store (needs nbuf > 1: a single buffer is re-filled right away)
+            for (int c = tid; c < L; c += kThreads) {
+                float a = 0.f;
+                for (int r = 0; r < rows; ++r) a += s_par[r * L + c];
+                s_col[c] += a;
             }
         }
     }
@@ -559,6 +574,9 @@ __global__ void __launch_bounds__(kThreads) mixcdf_bwd_pipe_kernel(const BwdPara
     if (p.gmsf)
         for (int i = tid; i < Ct * K; i += kThreads)
             if (s_gmsf[i] != 0.f) atomicAdd(p.gmsf + p.mask.tch[i / K] * K + i % K, s_gmsf[i]);
+    if (p.gcol)
+        for (int i = tid; i < L; i += kThreads)
+            if (s_col[i] != 0.f) atomicAdd(p.gcol + i, s_col[i]);
     if (tid == 0) tc::tma_store_wait_read<0>();      // shared memory must outlive the engine's reads of it
 }
 
@@ -566,9 +584,11 @@ template <int KT>
 int launch_bwd_pipe(BwdParams p, int L, int C, int Ct, int K, cudaStream_t stream) {
     static const int want = getenv("CNF_B200_MIXCDF_BWD_NBUF") ? atoi(getenv("CNF_B200_MIXCDF_BWD_NBUF")) : 2;      // tuning knob
     int nbuf = want < 1 ? 1 : (want > 4 ? 4 : want);
+    if (p.gcol != nullptr && nbuf < 2) nbuf = 2;      // the fused column sums read a tile after its store was issued
     const size_t buf = ((size_t)p.TP * L + 2 * (size_t)p.TP * C) * sizeof(float);
-    const size_t tables = (2 * (size_t)Ct + 3 * (size_t)Ct * K + (size_t)C) * sizeof(float);
-    while (nbuf > 1 && nbuf * buf + tables > 200 * 1024) --nbuf;
+    const size_t tables = (2 * (size_t)Ct + 3 * (size_t)Ct * K + (size_t)C + (size_t)L) * sizeof(float);
+    while (nbuf > 2 && nbuf * buf + tables > 200 * 1024) --nbuf;
+    if (nbuf * buf + tables > 200 * 1024) return -1;      // caller falls back to the tile kernel
     p.nbuf = nbuf;
     const size_t smem = nbuf * buf + tables;
     CNF_CUDA(cudaFuncSetAttribute(mixcdf_bwd_pipe_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -654,20 +674,28 @@ extern "C" int cnf_mixcdf_bwd(const cnf_mixcdf_bwd_args* a, cnf_stream_t stream_
                  ? 1 : 0;
     CNF_REQUIRE((reinterpret_cast<uintptr_t>(a->grad_nn_out) & 7) == 0, "grad_nn_out must be 8-byte aligned");
     CNF_SUPPORTED((long long)TP * a->C * p.PN < (1 << 21), "tile too large for the index arithmetic");
+    CNF_SUPPORTED(a->grad_nn_colsum == nullptr || p.compact, "grad_nn_colsum needs the compact layout (nn_compact = 1)");
     if (p.bulk && TP * Ct <= kThreads && (TP * L) % 4 == 0) {
+        p.gcol = a->grad_nn_colsum;
+        int prc;
         switch (a->K) {
-            case 4: return launch_bwd_pipe<4>(p, L, a->C, Ct, a->K, stream);
-            case 8: return launch_bwd_pipe<8>(p, L, a->C, Ct, a->K, stream);
-            case 16: return launch_bwd_pipe<16>(p, L, a->C, Ct, a->K, stream);
-            default: return launch_bwd_pipe<0>(p, L, a->C, Ct, a->K, stream);
+            case 4: prc = launch_bwd_pipe<4>(p, L, a->C, Ct, a->K, stream); break;
+            case 8: prc = launch_bwd_pipe<8>(p, L, a->C, Ct, a->K, stream); break;
+            case 16: prc = launch_bwd_pipe<16>(p, L, a->C, Ct, a->K, stream); break;
+            default: prc = launch_bwd_pipe<0>(p, L, a->C, Ct, a->K, stream); break;
         }
+        if (prc != -1) return prc;
+        p.gcol = nullptr;
     }
     const size_t smem = bwd_smem(TP, L, a->C, Ct, a->K);
     CNF_SUPPORTED(smem <= 200 * 1024, "C=%d K=%d needs %zu bytes of shared memory per tile", a->C, a->K, smem);
     switch (a->K) {
-        case 4: return launch_bwd<4>(p, smem, stream);
-        case 8: return launch_bwd<8>(p, smem, stream);
-        case 16: return launch_bwd<16>(p, smem, stream);
-        default: return launch_bwd<0>(p, smem, stream);
+        case 4: rc = launch_bwd<4>(p, smem, stream); break;
+        case 8: rc = launch_bwd<8>(p, smem, stream); break;
+        case 16: rc = launch_bwd<16>(p, smem, stream); break;
+        default: rc = launch_bwd<0>(p, smem, stream); break;
     }
+    // the tile kernel does not sum columns: a separate pass over the gradient it just wrote (same result)
+    if (rc == CNF_OK && a->grad_nn_colsum != nullptr) rc = tc_colsum(a->grad_nn_out, a->grad_nn_colsum, P, L, stream);
+    return rc;
 }

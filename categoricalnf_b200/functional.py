@@ -54,6 +54,49 @@ def mixcdf(z, nn_out, num_mixtures, scaling_factor=None, mixture_scaling_factor=
                       reg_factor=reg_factor, training=training, want_reg=True, prebounded=prebounded, compact=compact)
 
 
+class _ProjMixCDF(torch.autograd.Function):
+    """Final projection of the coupling network (compact form: only the transformed channels' weight rows) + mixture
+    transform as ONE autograd node, so that the backward kernel of the transform can hand the projection's bias gradient
+    over: it is the column sum of dL/dnn_out, which ``cnf_mixcdf_bwd`` (ABI v5 ``grad_nn_colsum``) forms while the
+    gradient tile is still in shared memory - the separate column-sum pass re-read the whole gradient (0.87 GB at the LM
+    shape).  Forward and the other gradients are exactly ``_TCLinearFn`` followed by ``_MixCDF``."""
+
+    @staticmethod
+    def forward(ctx, z, feats, weight, bias, sf, msf, pad, cfg, precision):
+        B, S = z.shape[0], z.shape[1]
+        nn_out = ops.linear(feats, weight, bias, precision=precision, cache_weight=False).view(B, S, weight.shape[0])
+        z_out, ldj, reg = ops.mixcdf(z, nn_out, cfg["K"], mask_c=cfg["mask_c"], mask_s=cfg["mask_s"], pad=pad,
+                                     scaling_factor=sf, mixture_scaling_factor=msf, reverse=False,
+                                     reg_max=cfg["reg_max"], reg_factor=cfg["reg_factor"], training=cfg["training"],
+                                     want_reg=True, compact=True)
+        ctx.cfg, ctx.precision, ctx.has_bias = cfg, precision, bias is not None
+        ctx.save_for_backward(z, nn_out, sf, msf, pad, z_out, feats, weight)
+        ctx.mark_non_differentiable(reg)
+        return z_out, ldj, reg
+
+    @staticmethod
+    def backward(ctx, g_z, g_ldj, g_reg):
+        from . import ops_bwd
+        from .layers.networks.linear import BACKWARD_PRECISION
+        z, nn_out, sf, msf, pad, z_out, feats, weight = ctx.saved_tensors
+        need = ctx.needs_input_grad
+        want_col = ctx.has_bias and need[3]
+        out = ops_bwd.mixcdf_backward(ctx.cfg, z, nn_out, sf, msf, pad, z_out, g_z, g_ldj, need, want_colsum=want_col)
+        gz, gnn, gsf, gmsf = out[:4]
+        gx, gw, _ = ops.linear_bwd(feats, weight, gnn.view(-1, gnn.shape[-1]), need_x=need[1], need_weight=need[2], need_bias=False,
+                                   precision=BACKWARD_PRECISION or ctx.precision)
+        return gz, gx, gw, (out[4] if want_col else None), gsf, gmsf, None, None, None
+
+
+def proj_mixcdf(z, feats, weight, bias, num_mixtures, scaling_factor=None, mixture_scaling_factor=None, *, mask_c=None,
+                pad=None, reg_max=-1.0, reg_factor=1.0, training=False, precision="3xtf32"):
+    """``mixcdf(z, feats @ weight.T + bias, ..., compact=True)`` (forward direction) with ``weight`` / ``bias`` holding the
+    transformed channels' rows only; ``feats`` [B*S, H].  -> (z_out, ldj [B], reg_ldj [B])."""
+    cfg = dict(K=int(num_mixtures), mask_c=mask_c, mask_s=None, reverse=False, reg_max=float(reg_max),
+               reg_factor=float(reg_factor), training=bool(training), prebounded=False, compact=True)
+    return _ProjMixCDF.apply(z, feats, weight, bias, scaling_factor, mixture_scaling_factor, pad, cfg, precision)
+
+
 # ----------------------------------------------------------------------------------------------
 # affine coupling
 # ----------------------------------------------------------------------------------------------

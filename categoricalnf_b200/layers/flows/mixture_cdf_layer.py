@@ -166,12 +166,12 @@ class MixtureCDFCoupling(CouplingLayer):
         elif split is None and fuse is None and ldj_acc is None and self._train_fold_possible(z, mask_s):
             # training step with a per-position linear network: the mask goes into the (tiny) weight instead of two
             # elementwise passes over z (z * mask forward, grad * mask backward) - see _compact_projection
-            compact = self._compact_projection(z, None, mask_c, mask_s, channel_padding_mask, kwargs)
+            compact = self._compact_projection(z, None, mask_c, mask_s, channel_padding_mask, kwargs) if not reverse else None
             if compact is not None:
-                z_out, ldj, reg = CF.mixcdf(z, compact, self.num_mixtures, self.scaling_factor, self.mixture_scaling_factor,
-                                            mask_c=mask_c, mask_s=mask_s, pad=channel_padding_mask, reverse=reverse,
-                                            reg_max=self.regularizer_max, reg_factor=self.regularizer_factor,
-                                            training=self.training, compact=True)
+                z_out, ldj, reg = CF.proj_mixcdf(z, compact[0], compact[1], compact[2], self.num_mixtures, self.scaling_factor,
+                                                 self.mixture_scaling_factor, mask_c=mask_c, pad=channel_padding_mask,
+                                                 reg_max=self.regularizer_max, reg_factor=self.regularizer_factor,
+                                                 training=self.training, precision=self.projection_precision)
                 return z_out, ldj, {"ldj": ldj, "regularizer_ldj": reg}
             x_in = masked_input if masked_input is not None else z * self._prepare_mask(self.mask, z)
         else:
@@ -207,12 +207,12 @@ class MixtureCDFCoupling(CouplingLayer):
         else:
             if fuse is not None or ldj_acc is not None:
                 return None
-            compact = self._compact_projection(z, x_in, mask_c, mask_s, channel_padding_mask, kwargs)
+            compact = self._compact_projection(z, x_in, mask_c, mask_s, channel_padding_mask, kwargs) if not reverse else None
             if compact is not None:
-                z_out, ldj, reg = CF.mixcdf(z, compact, self.num_mixtures, self.scaling_factor, self.mixture_scaling_factor,
-                                            mask_c=mask_c, mask_s=mask_s, pad=channel_padding_mask, reverse=reverse,
-                                            reg_max=self.regularizer_max, reg_factor=self.regularizer_factor,
-                                            training=self.training, compact=True)
+                z_out, ldj, reg = CF.proj_mixcdf(z, compact[0], compact[1], compact[2], self.num_mixtures, self.scaling_factor,
+                                                 self.mixture_scaling_factor, mask_c=mask_c, pad=channel_padding_mask,
+                                                 reg_max=self.regularizer_max, reg_factor=self.regularizer_factor,
+                                                 training=self.training, precision=self.projection_precision)
                 return z_out, ldj, {"ldj": ldj, "regularizer_ldj": reg}
             nn_out = self.run_network(x=x_in, **kwargs)
         z_out, ldj, reg = CF.mixcdf(z, nn_out, self.num_mixtures, self.scaling_factor, self.mixture_scaling_factor,
@@ -233,7 +233,8 @@ class MixtureCDFCoupling(CouplingLayer):
                 and getattr(self.nn, "cnf_features_are_input", False) and self.mask.dim() == 2 and self.mask.size(0) == 1)
 
     def _compact_projection(self, z, x_in, mask_c, mask_s, channel_padding_mask, kwargs):
-        """Compact network output [B,S,Ct*(2+3K)] (differentiable), or None when this configuration does not allow it.
+        """Operands of the compact projection - (features [B*S,H], weight rows and bias entries of the transformed channels'
+        records) - or None when this configuration does not allow it.
         ``x_in`` None: the network is its final Linear on the masked input (``_train_fold_possible``) - the projection runs
         on the UNMASKED z with the mask folded into the weight columns, ``(z * m) W^T = z (W * m)^T``: the weight gradient
         flows back through that [rows, C] multiply, and the gradient wrt z comes out of the GEMM already masked."""
@@ -267,12 +268,11 @@ class MixtureCDFCoupling(CouplingLayer):
             feats = features_fn(x_in, **kwargs)
         if feats.dim() != 3:
             return None
-        from ..networks.linear import _TCLinearFn
         bias = None if lin.bias is None else lin.bias[r0:r1]
         weight._cnf_cache_lo = True       # a weight block: its 3xTF32 split is made once per call, not once per tile (ops.weight_split)
-        out = _TCLinearFn.apply(feats.reshape(-1, feats.shape[-1]), weight, bias, self.projection_precision)
-        # (no pad multiply here: channel_padding_mask is bound by forward() and never reaches run_network, App. B #3)
-        return out.view(z.shape[0], z.shape[1], r1 - r0)
+        # (no pad multiply on the network output: channel_padding_mask is bound by forward() and never reaches run_network,
+        # App. B #3).  The projection and the transform run as one autograd node (CF.proj_mixcdf).
+        return feats.reshape(-1, feats.shape[-1]), weight, bias
 
     def try_forward_fused(self, z, actnorm, conv, channel_padding_mask=None, length=None, cnf_masked_input=None,
                           cnf_next_mask=None, **kwargs):

@@ -18,7 +18,9 @@ def _grad(t, like):
     return _f32(t, "grad")
 
 
-def mixcdf_backward(cfg, z, nn_out, sf, msf, pad, z_out, g_z, g_ldj, needs):
+def mixcdf_backward(cfg, z, nn_out, sf, msf, pad, z_out, g_z, g_ldj, needs, want_colsum=False):
+    """-> (grad_z, grad_nn_out, grad_sf | None, grad_msf | None[, column sums of grad_nn_out]).  ``want_colsum`` (compact layout
+    only, ABI v5): the bias gradient of the network's final Linear, summed by the backward kernel itself."""
     if cfg["reverse"]:
         raise NotImplementedError("categoricalnf_b200: differentiating the INVERSE mixture coupling is not supported "
                                   "(training differentiates the density direction only)")
@@ -46,7 +48,15 @@ def mixcdf_backward(cfg, z, nn_out, sf, msf, pad, z_out, g_z, g_ldj, needs):
     a.nn_compact = int(compact)
     a.grad_z_out, a.grad_ldj, a.grad_z, a.grad_nn_out = _ptr(gz_out), _ptr(gl), _ptr(gz), _ptr(gnn)
     a.grad_scaling_factor, a.grad_mixture_scaling_factor = _ptr(gsf), _ptr(gmsf)
+    gcol = None
+    if want_colsum:
+        if not compact:
+            raise ValueError("mixcdf_backward: column sums need the compact layout")
+        gcol = torch.zeros(nn_out.shape[-1], dtype=torch.float32, device=z.device)
+        a.grad_nn_colsum = _ptr(gcol)
     _call("cnf_mixcdf_bwd", a, z, (keep, z, nn_out, pad, sf, msf, gz_out, gl))
+    if want_colsum:
+        return gz, gnn, gsf, gmsf, gcol
     return gz, gnn, gsf, gmsf
 
 

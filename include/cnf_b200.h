@@ -589,6 +589,11 @@ typedef struct {
     /* ABI v4: 1 = nn_out AND grad_nn_out are compact, [B,S,Ct*(2+3K)] (see cnf_mixcdf_args.nn_compact): no zeros are
      * written for conditioner channels.  Needs a contiguous run of transformed channels and 16-byte aligned rows. */
     int32_t nn_compact;
+    /* ABI v5 (needs nn_compact): [Ct*(2+3K)] += column sums of grad_nn_out over all positions = dL/dbias of the network's
+     * final nn.Linear (the reference gets it from autograd through that Linear, general/train.py:148-152).  The persistent
+     * compact-layout kernel sums the columns of every tile while its rows are still in shared memory; otherwise a pass
+     * over grad_nn_out follows the kernel.  NULL: not wanted.                                                          */
+    float* grad_nn_colsum;
 } cnf_mixcdf_bwd_args;
 
 /* forward direction of cnf_mixcdf_fwd (training differentiates the density direction only) */
