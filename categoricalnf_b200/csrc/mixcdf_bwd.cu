@@ -94,25 +94,40 @@ __device__ __forceinline__ bool mix_backward_elem(float xf, float* rec, const fl
     float m = lp[0];
 #pragma unroll(KT > 0 ? KT : 4)
     for (int k = 1; k < K; ++k) m = fmaxf(m, lp[k]);
+    // The record is read (and, in the second pass, overwritten) in 8-byte pieces when K is even: lp / mu / ms start at even
+    // offsets of the 8-byte aligned record, and with records 2 + 3K floats apart the 16 lanes of a half warp then hit 32
+    // different banks - scalar accesses at that pitch are 2-way conflicted (35 M conflicts per launch at the LM shape).
+    constexpr bool kPairs = KT > 0 && (KT % 2) == 0;
     T W = 0, Fs = 0, Gs = 0, fs = 0;
-#pragma unroll(KT > 0 ? KT : 4)
-    for (int k = 0; k < K; ++k) {
+    auto pass1 = [&](int k, float ms_k, float mu_k, float lp_k) {
         const float mf = pre ? 1.0f : mfac[k];
         // the reference bounds the raw log-scales in float32 before its .double() (:157-178)
         // imf[k] = 1 / max(e^{msf}, 1): a per-(channel, component) constant, tabulated by the caller for the fp32 path (it
         // was a MUFU.RCP per component and pass: 16 of ~127 MUFU operations per element)
-        const T ls = pre ? (T)ms[k] : M::th((T)ms[k] * (imf ? (T)imf[k] : M::rc((T)fmaxf(mf, 1.0f)))) * (T)mf;
+        const T ls = pre ? (T)ms_k : M::th((T)ms_k * (imf ? (T)imf[k] : M::rc((T)fmaxf(mf, 1.0f)))) * (T)mf;
         const T e = M::ex(-ls);
-        const T u = (x - (T)mu[k]) * e;
+        const T u = (x - (T)mu_k) * e;
         const T ea = M::ex(-fabs(u));
         const T r = M::rc((T)1 + ea);
         const T q = ea * r;
         const T sg = u >= 0 ? r : q, tg = u >= 0 ? q : r;   // sigma, 1 - sigma
-        const T w = M::ex((T)lp[k] - (T)m);
+        const T w = M::ex((T)lp_k - (T)m);
         W += w;
         Fs += w * sg;
         Gs += w * tg;
         fs += w * (q * r) * e;
+    };
+    if constexpr (kPairs) {
+#pragma unroll
+        for (int k = 0; k < KT; k += 2) {
+            const float2 a = *reinterpret_cast<const float2*>(ms + k), b = *reinterpret_cast<const float2*>(mu + k),
+                         c = *reinterpret_cast<const float2*>(lp + k);
+            pass1(k, a.x, b.x, c.x);
+            pass1(k + 1, a.y, b.y, c.y);
+        }
+    } else {
+#pragma unroll(KT > 0 ? KT : 4)
+        for (int k = 0; k < K; ++k) pass1(k, ms[k], mu[k], lp[k]);
     }
     const T iw = M::rc(W);
     const T F = Fs * iw, G = Gs * iw, f = fs * iw;
@@ -141,40 +156,55 @@ __device__ __forceinline__ bool mix_backward_elem(float xf, float* rec, const fl
     const T LF = LlF * M::rc(F), LG = LlG * M::rc(G), Lf = gl * M::rc(f);
     const T Ssum = LF * F + LG * G + Lf * f;             // sum_j pi_j P_j
     T gx = 0;
-#pragma unroll(KT > 0 ? KT : 4)
-    for (int k = 0; k < K; ++k) {
+    auto pass2 = [&](int k, float ms_k, float mu_k, float lp_k, float& o_ms, float& o_mu, float& o_lp) {
         const float mf = pre ? 1.0f : mfac[k];
         const float mf_max = fmaxf(mf, 1.0f);
-        const T raw = (T)ms[k];
+        const T raw = (T)ms_k;
         const T imf_max = imf ? (T)imf[k] : M::rc((T)mf_max);
         const T thk = pre ? (T)0 : M::th(raw * imf_max);
         const T ls = pre ? raw : thk * (T)mf;
         const T e = M::ex(-ls);
-        const T u = (x - (T)mu[k]) * e;
+        const T u = (x - (T)mu_k) * e;
         const T ea = M::ex(-fabs(u));
         const T r = M::rc((T)1 + ea);
         const T q = ea * r;
         const T sg = u >= 0 ? r : q, tg = u >= 0 ? q : r;
         const T d = q * r;
-        const T pi = M::ex((T)lp[k] - (T)m) * iw;
+        const T pi = M::ex((T)lp_k - (T)m) * iw;
         const T Pk = LF * sg + LG * tg + Lf * d * e;
         const T Lsig = pi * ((LF - LG) + Lf * (tg - sg) * e);
         const T Lu = Lsig * d;
         const T Lue = Lu * e;
         gx += Lue;
         const T Lls = -u * Lu - Lf * pi * d * e;
-        lp[k] = (float)(pi * (Pk - Ssum));
-        mu[k] = (float)(-Lue);
+        o_lp = (float)(pi * (Pk - Ssum));
+        o_mu = (float)(-Lue);
         if (pre) {
-            ms[k] = (float)Lls;
+            o_ms = (float)Lls;
         } else {
             const T sech2 = (T)1 - thk * thk;
-            ms[k] = (float)(Lls * sech2 * (T)mf * imf_max);
+            o_ms = (float)(Lls * sech2 * (T)mf * imf_max);
             // ls = tanh(raw / max(M,1)) M, M = e^{msf}: d ls / d msf  (for M > 1: max(M,1) = M)
             const T dmsf = (T)mf * thk - (mf >= 1.0f ? sech2 * raw : (T)0);
             if (KT > 0) gmsf_k[k] = (float)(Lls * dmsf);            // registers, reduced across the warp by the caller
             else atomicAdd(gmsf_k + k, (float)(Lls * dmsf));       // generic K / float64 path: shared-memory accumulator
         }
+    };
+    if constexpr (kPairs) {
+#pragma unroll
+        for (int k = 0; k < KT; k += 2) {
+            const float2 a = *reinterpret_cast<const float2*>(ms + k), b = *reinterpret_cast<const float2*>(mu + k),
+                         c = *reinterpret_cast<const float2*>(lp + k);
+            float2 oa, ob, oc;
+            pass2(k, a.x, b.x, c.x, oa.x, ob.x, oc.x);
+            pass2(k + 1, a.y, b.y, c.y, oa.y, ob.y, oc.y);
+            *reinterpret_cast<float2*>(ms + k) = oa;
+            *reinterpret_cast<float2*>(mu + k) = ob;
+            *reinterpret_cast<float2*>(lp + k) = oc;
+        }
+    } else {
+#pragma unroll(KT > 0 ? KT : 4)
+        for (int k = 0; k < K; ++k) pass2(k, ms[k], mu[k], lp[k], ms[k], mu[k], lp[k]);
     }
     rec[0] = (float)g_t;
     if (pre) {
