@@ -134,7 +134,7 @@ class LinearBwdArgs(C.Structure):
     _fields_ = [
         ("M", C.c_int64), ("N", C.c_int32), ("K", C.c_int32),
         ("x", vp), ("weight", vp), ("grad_y", vp), ("precision", C.c_int32),
-        ("grad_x", vp), ("grad_weight", vp), ("grad_bias", vp),
+        ("grad_x", vp), ("grad_weight", vp), ("grad_bias", vp), ("weight_lo", vp),
     ]
 
 

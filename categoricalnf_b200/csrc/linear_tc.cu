@@ -127,7 +127,14 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
                     mbar_wait(&empty[stage], phase ^ 1u);
                     unsigned char* sa = smem + stage * stage_bytes;
                     mbar_arrive_expect_tx(&full[stage], (uint32_t)(half_bytes + (STRICT && p.w_lo ? b_bytes : 0)));
-                    if (STRICT && p.w_lo) tma_load_2d(sa + half_bytes + kABytes, &tm_blo, &full[stage], kb * kBK, n0);
+                    if (STRICT && p.w_lo) {      // pre-split B: its low part arrives like the high part, from its own tensor
+                        if (p.b_mn) {
+                            for (int j = 0; j < p.block_n / 32; ++j)
+                                tma_load_2d(sa + half_bytes + kABytes + j * 4096, &tm_blo, &full[stage], n0 + 32 * j, kb * kBK);
+                        } else {
+                            tma_load_2d(sa + half_bytes + kABytes, &tm_blo, &full[stage], kb * kBK, n0);
+                        }
+                    }
                     if (p.a_mn) {   // [32 reduction rows x 32 MN] slabs, one per 128-byte swizzle atom along MN
                         for (int j = 0; j < kBM / 32; ++j) tma_load_2d(sa + j * 4096, &tm_x, &full[stage], m0 + 32 * j, kb * kBK);
                     } else {
@@ -447,13 +454,13 @@ int launch_gemm(const GemmDesc& g, const char* who, cudaStream_t stream) {
     const size_t smem = (size_t)fixed + (size_t)stages * stage_bytes;
 
     CUtensorMap tm_a, tm_b, tm_y, tm_blo;
-    p.w_lo = (strict && g.b_lo != nullptr && !g.b_mn) ? 1 : 0;
+    p.w_lo = (strict && g.b_lo != nullptr) ? 1 : 0;
     int rc = g.a_mn ? tc_encode_2d(&tm_a, g.a, g.Mg, g.R, 32, kBK, 1) : tc_encode_2d(&tm_a, g.a, g.R, g.Mg, kBK, kBM, 0);
     if (rc != CNF_OK) return rc;
     rc = g.b_mn ? tc_encode_2d(&tm_b, g.b, g.Ng, g.R, 32, kBK, 1) : tc_encode_2d(&tm_b, g.b, g.R, g.Ng, kBK, p.block_n, 0);
     if (rc != CNF_OK) return rc;
     if (p.w_lo) {
-        rc = tc_encode_2d(&tm_blo, g.b_lo, g.R, g.Ng, kBK, p.block_n, 0);
+        rc = g.b_mn ? tc_encode_2d(&tm_blo, g.b_lo, g.Ng, g.R, 32, kBK, 1) : tc_encode_2d(&tm_blo, g.b_lo, g.R, g.Ng, kBK, p.block_n, 0);
         if (rc != CNF_OK) return rc;
     } else {
         tm_blo = tm_b;
@@ -564,6 +571,10 @@ extern "C" int cnf_linear_bwd(const cnf_linear_bwd_args* a, cnf_stream_t stream_
         g.a = a->grad_y; g.a_mn = 0; g.b = a->weight; g.b_mn = 1;
         g.Mg = a->M; g.Ng = a->K; g.R = a->N;
         g.precision = a->precision; g.y = a->grad_x;
+        if (a->weight_lo != nullptr) {
+            CNF_REQUIRE((reinterpret_cast<uintptr_t>(a->weight_lo) & 15) == 0, "cnf_linear_bwd: weight_lo must be 16-byte aligned");
+            g.b_lo = a->weight_lo;
+        }
         const int rc = launch_gemm(g, "cnf_linear_bwd (grad_x)", stream);
         if (rc != CNF_OK) return rc;
     }

@@ -64,13 +64,17 @@ class _ProjMixCDF(torch.autograd.Function):
     @staticmethod
     def forward(ctx, z, feats, weight, bias, sf, msf, pad, cfg, precision):
         B, S = z.shape[0], z.shape[1]
-        nn_out = ops.linear(feats, weight, bias, precision=precision, cache_weight=False).view(B, S, weight.shape[0])
+        split = None
+        if precision == "3xtf32" and weight.dtype == torch.float32 and weight.is_contiguous():
+            split = ops.weight_split(weight, use_cache=False)
+        ctx.has_split = split is not None
+        nn_out = ops.linear(feats, weight, bias, precision=precision, cache_weight=False, split=split).view(B, S, weight.shape[0])
         z_out, ldj, reg = ops.mixcdf(z, nn_out, cfg["K"], mask_c=cfg["mask_c"], mask_s=cfg["mask_s"], pad=pad,
                                      scaling_factor=sf, mixture_scaling_factor=msf, reverse=False,
                                      reg_max=cfg["reg_max"], reg_factor=cfg["reg_factor"], training=cfg["training"],
                                      want_reg=True, compact=True)
         ctx.cfg, ctx.precision, ctx.has_bias = cfg, precision, bias is not None
-        ctx.save_for_backward(z, nn_out, sf, msf, pad, z_out, feats, weight)
+        ctx.save_for_backward(z, nn_out, sf, msf, pad, z_out, feats, weight, *(split or ()))
         ctx.mark_non_differentiable(reg)
         return z_out, ldj, reg
 
@@ -78,13 +82,14 @@ class _ProjMixCDF(torch.autograd.Function):
     def backward(ctx, g_z, g_ldj, g_reg):
         from . import ops_bwd
         from .layers.networks.linear import BACKWARD_PRECISION
-        z, nn_out, sf, msf, pad, z_out, feats, weight = ctx.saved_tensors
+        z, nn_out, sf, msf, pad, z_out, feats, weight = ctx.saved_tensors[:8]
+        split = tuple(ctx.saved_tensors[8:10]) if ctx.has_split else None
         need = ctx.needs_input_grad
         want_col = ctx.has_bias and need[3]
         out = ops_bwd.mixcdf_backward(ctx.cfg, z, nn_out, sf, msf, pad, z_out, g_z, g_ldj, need, want_colsum=want_col)
         gz, gnn, gsf, gmsf = out[:4]
         gx, gw, _ = ops.linear_bwd(feats, weight, gnn.view(-1, gnn.shape[-1]), need_x=need[1], need_weight=need[2], need_bias=False,
-                                   precision=BACKWARD_PRECISION or ctx.precision)
+                                   precision=BACKWARD_PRECISION or ctx.precision, weight_split=split)
         return gz, gx, gw, (out[4] if want_col else None), gsf, gmsf, None, None, None
 
 

@@ -84,7 +84,9 @@ class _FusedPair:
             if extra:
                 ws.append(a.weight.new_zeros(extra, K))
                 bs.append(a.bias.new_zeros(extra))
-        return torch.cat(ws, dim=0).contiguous(), torch.cat(bs, dim=0).contiguous()
+        w = torch.cat(ws, dim=0).contiguous()
+        w._cnf_cache_lo = True      # a weight: ops.weight_split splits it once per call (training) or once per version (get)
+        return w, torch.cat(bs, dim=0).contiguous()
 
     def get(self, a, b, attn_weight=None):
         key = (a.weight.data_ptr(), a.weight._version, a.bias._version, b.weight.data_ptr(), b.weight._version,

@@ -34,17 +34,23 @@ class _TCLinearFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, precision):
         ctx.precision = precision
-        ctx.save_for_backward(x, weight)
         ctx.has_bias = bias is not None
-        # grad mode is off inside Function.forward, so say explicitly that this is a training step: no cached split
-        return ops.linear(x, weight, bias, precision=precision, cache_weight=False)
+        # grad mode is off inside Function.forward, so say explicitly that this is a training step: no cached split.  The
+        # split made here (parameters / weight blocks only) is kept for the grad_x product of the backward pass.
+        split = None
+        if precision == "3xtf32" and weight.dtype == torch.float32 and weight.is_contiguous():
+            split = ops.weight_split(weight, use_cache=False)
+        ctx.has_split = split is not None
+        ctx.save_for_backward(x, weight, *(split or ()))
+        return ops.linear(x, weight, bias, precision=precision, cache_weight=False, split=split)
 
     @staticmethod
     def backward(ctx, gy):
-        x, weight = ctx.saved_tensors
+        x, weight = ctx.saved_tensors[:2]
+        split = tuple(ctx.saved_tensors[2:4]) if ctx.has_split else None
         gx, gw, gb = ops.linear_bwd(x, weight, gy, need_x=ctx.needs_input_grad[0], need_weight=ctx.needs_input_grad[1],
                                     need_bias=ctx.has_bias and ctx.needs_input_grad[2],
-                                    precision=BACKWARD_PRECISION or ctx.precision)
+                                    precision=BACKWARD_PRECISION or ctx.precision, weight_split=split)
         return gx, gw, gb, None
 
 

@@ -600,15 +600,17 @@ def weight_split(weight, use_cache=True):
     return hit[2], hit[3]
 
 
-def linear(x, weight, bias=None, *, precision="3xtf32", activation=None, block_n=0, cache_weight=True):
+def linear(x, weight, bias=None, *, precision="3xtf32", activation=None, block_n=0, cache_weight=True, split=None):
     """y = x @ weight.T + bias (nn.Linear) on the tensor cores (``cnf_linear_fwd``).
 
     ``x`` [..., K] fp32 CUDA, ``weight`` [N, K], ``bias`` [N] | None.  ``precision``: "tf32" (one pass)
     or "3xtf32" (hi/lo split, fp32-level accuracy - default, keeps the 1e-4 parity of the flow).
     K that is not a multiple of 4 is zero-padded (a copy); everything else runs in place.  ``cache_weight=False``: the
-    3xTF32 split of the weight is recomputed for this call (training step: the weight is about to change)."""
+    3xTF32 split of the weight is recomputed for this call (training step: the weight is about to change).  ``split`` =
+    (hi, lo): a split the caller made already with :func:`weight_split` (it keeps it for the backward pass)."""
     x = _f32(x, "x")
-    split = weight_split(weight, cache_weight) if precision == "3xtf32" and weight.dtype == torch.float32 and weight.is_contiguous() else None
+    if split is None and precision == "3xtf32" and weight.dtype == torch.float32 and weight.is_contiguous():
+        split = weight_split(weight, cache_weight)
     weight = _f32(weight, "weight")
     w_lo = None
     if split is not None:
@@ -645,12 +647,14 @@ def linear(x, weight, bias=None, *, precision="3xtf32", activation=None, block_n
 
 
 def linear_bwd(x, weight, grad_y, *, need_x=True, need_weight=True, need_bias=False, precision="3xtf32",
-               grad_weight=None, grad_bias=None):
+               grad_weight=None, grad_bias=None, weight_split=None):
     """Backward of :func:`linear` (``cnf_linear_bwd``): ``(grad_x | None, grad_weight | None, grad_bias | None)``.
 
     The three products read ``x`` / ``weight`` / ``grad_y`` in place (MN-major tensor-core operands, no transposed
     copies).  ``grad_weight`` / ``grad_bias`` given -> accumulated into (gradient accumulation); otherwise fresh
-    zero-initialised tensors.  N or K not a multiple of 4 is zero-padded (copies)."""
+    zero-initialised tensors.  N or K not a multiple of 4 is zero-padded (copies).  ``weight_split = (hi, lo)`` (3xTF32): the
+    split of ``weight`` the forward pass made (:func:`weight_split`) - the grad_x product then reads it through TMA instead of
+    splitting the weight tile in every CTA and k-block."""
     x = _f32(x, "x")
     weight = _f32(weight, "weight")
     grad_y = _f32(grad_y, "grad_y")
@@ -687,9 +691,14 @@ def linear_bwd(x, weight, grad_y, *, need_x=True, need_weight=True, need_bias=Fa
     a = L.LinearBwdArgs()
     a.M, a.N, a.K = M, N, K
     a.x, a.weight, a.grad_y = _ptr(x2), _ptr(weight), _ptr(gy2)
+    if weight_split is not None and precision == "3xtf32" and need_x and tuple(weight_split[0].shape) == (N, K):
+        w_hi, w_lo = _f32(weight_split[0], "weight (high part)"), _f32(weight_split[1], "weight (low part)")
+        a.weight, a.weight_lo = _ptr(w_hi), _ptr(w_lo)
+    else:
+        w_hi = w_lo = None
     a.precision = PRECISION[precision]
     a.grad_x, a.grad_weight, a.grad_bias = _ptr(gx), _ptr(gw), _ptr(gb)
-    _call("cnf_linear_bwd", a, x2, (x2, weight, gy2, gx, gw, gb))
+    _call("cnf_linear_bwd", a, x2, (x2, weight, gy2, gx, gw, gb, w_hi, w_lo))
     return (gx.reshape(x.shape) if gx is not None else None), gw, gb
 
 

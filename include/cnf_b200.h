@@ -393,6 +393,10 @@ typedef struct {
     float* grad_x;         /* [M,K] or NULL                    */
     float* grad_weight;    /* [N,K] or NULL, accumulated into  */
     float* grad_bias;      /* [N] or NULL, accumulated into    */
+    /* ABI v5, 3xTF32 only: pre-split weight as in cnf_linear_args.weight_lo - `weight` then holds the high parts
+     * rna_tf32(W) and weight_lo = rna_tf32(W - weight); the grad_x product reads both through TMA instead of splitting
+     * the weight tile again in every CTA and k-block.  NULL: split in the kernel.                                    */
+    const float* weight_lo;
 } cnf_linear_bwd_args;
 
 CNF_API int cnf_linear_bwd(const cnf_linear_bwd_args* a, cnf_stream_t stream);
