@@ -646,6 +646,9 @@ def linear(x, weight, bias=None, *, precision="3xtf32", activation=None, block_n
     return y.reshape(lead + (N,))
 
 
+_BWD_NO_PRESPLIT = bool(os.environ.get("CNF_B200_BWD_NO_PRESPLIT"))      # A/B switch: grad_x splits the weight tile in the kernel
+
+
 def linear_bwd(x, weight, grad_y, *, need_x=True, need_weight=True, need_bias=False, precision="3xtf32",
                grad_weight=None, grad_bias=None, weight_split=None):
     """Backward of :func:`linear` (``cnf_linear_bwd``): ``(grad_x | None, grad_weight | None, grad_bias | None)``.
@@ -691,7 +694,7 @@ def linear_bwd(x, weight, grad_y, *, need_x=True, need_weight=True, need_bias=Fa
     a = L.LinearBwdArgs()
     a.M, a.N, a.K = M, N, K
     a.x, a.weight, a.grad_y = _ptr(x2), _ptr(weight), _ptr(gy2)
-    if weight_split is not None and precision == "3xtf32" and need_x and tuple(weight_split[0].shape) == (N, K):
+    if weight_split is not None and precision == "3xtf32" and need_x and tuple(weight_split[0].shape) == (N, K) and not _BWD_NO_PRESPLIT:
         w_hi, w_lo = _f32(weight_split[0], "weight (high part)"), _f32(weight_split[1], "weight (low part)")
         a.weight, a.weight_lo = _ptr(w_hi), _ptr(w_lo)
     else:
