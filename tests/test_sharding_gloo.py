@@ -184,3 +184,32 @@ def test_reduce_now_without_hooks_single_process():
         assert torch.equal(p.grad, w)
         assert p.grad.data_ptr() == red._owner[id(p)][1].data_ptr()
     red.close()
+
+
+def _step_count_worker(rank, world_size, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world_size)
+    try:
+        import bench
+        # every rank derives a different count from its own timing (here: 500 + 37 rank) ...
+        n = bench.same_on_all_ranks(500 + 37 * rank, torch.device("cpu"), dist)
+        # ... and a loop of that many collectives only terminates when the counts agree
+        t = torch.zeros(1)
+        for _ in range(n % 7 + 1):
+            dist.all_reduce(t)
+        out[rank] = n
+    finally:
+        dist.destroy_process_group()
+
+
+def test_bench_step_counts_are_agreed_across_ranks():
+    """bench.py's sustained legs size their loops from a LOCAL timing; the count must be made identical on all ranks
+    before it drives per-step all-reduces (a rank-local count hung the N = 2 run once): every rank takes the maximum."""
+    world_size, port = 2, _free_port()
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_step_count_worker, args=(world_size, port, out), nprocs=world_size, join=True)
+        res = {k: v for k, v in out.items()}
+    assert res[0] == res[1] == 537
+    import bench
+    assert bench.same_on_all_ranks(12, torch.device("cpu"), None) == 12
