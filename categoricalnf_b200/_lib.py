@@ -203,6 +203,7 @@ class MixcdfBwdArgs(C.Structure):
         ("reg_max", C.c_float), ("reg_factor", C.c_float), ("training", C.c_int32), ("params_prebounded", C.c_int32),
         ("grad_z_out", vp), ("grad_ldj", vp), ("grad_z", vp), ("grad_nn_out", vp),
         ("grad_scaling_factor", vp), ("grad_mixture_scaling_factor", vp), ("nn_compact", C.c_int32), ("grad_nn_colsum", vp),
+        ("proj_weight", vp), ("grad_proj_weight", vp),
     ]
 
 

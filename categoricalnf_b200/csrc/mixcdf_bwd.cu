@@ -48,6 +48,8 @@ struct BwdParams {
     float* gsf;
     float* gmsf;
     float* gcol;      // [Ct * PN] += column sums of dL/dnn_out (= the bias gradient of a final Linear), pipe kernel only
+    const float* proj_w;   // [Ct * PN, C] weight block of a final Linear whose input is z itself (pipe kernel, C 16 / Ct 8)
+    float* gproj_w;        // [Ct * PN, C] += dL/dnn_out^T z (conditioner columns)
     long long P;
     int S, C, K, PN, TP;
     MaskView mask;
@@ -434,8 +436,11 @@ __global__ void __launch_bounds__(kThreads) mixcdf_bwd_kernel(const BwdParams p)
 // The per-CTA tables (e^{sf}, e^{msf}, 1 / max(e^{msf}, 1)) are built once and the scaling-factor gradients leave with one
 // atomic per (CTA, parameter) at the very end - the tile kernel above pays both per tile of 32 positions (32768 CTAs x 72
 // global atomics at the LM shape).
-template <int KT>
-__global__ void __launch_bounds__(kThreads) mixcdf_bwd_pipe_kernel(const BwdParams p) {
+#ifndef CNF_BWD_PROJ_MIN_CTAS
+#define CNF_BWD_PROJ_MIN_CTAS 3      // 80 registers: 3 CTAs per SM (15.5 ms per LM training step; 1 CTA at 150 registers: 21.1 ms)
+#endif
+template <int KT, bool PROJ>
+__global__ void __launch_bounds__(kThreads, PROJ ? CNF_BWD_PROJ_MIN_CTAS : 1) mixcdf_bwd_pipe_kernel(const BwdParams p) {
     extern __shared__ __align__(16) float smem[];
     __shared__ __align__(8) uint64_t s_full[4];
     const int tid = threadIdx.x;
@@ -451,6 +456,8 @@ __global__ void __launch_bounds__(kThreads) mixcdf_bwd_pipe_kernel(const BwdPara
     float* s_imf = s_gmsf + Ct * K;                        // [Ct * K] 1 / max(e^{msf}, 1)
     int* s_jmap = reinterpret_cast<int*>(s_imf + Ct * K);  // [C] channel -> transformed index or -1
     float* s_col = reinterpret_cast<float*>(s_jmap + C);   // [L] column sums of the gradient records (p.gcol)
+    float* s_pw = s_col + ((L + 3) & ~3);                  // [L][8] conditioner columns of the projection weight (p.proj_w)
+    const int cb = p.mask.c0 == 0 ? Ct : 0;                // first conditioner channel (C = 16, Ct = 8 in this mode)
 
     for (int i = tid; i < Ct; i += kThreads) {
         s_fac[i] = p.sf ? expf(p.sf[p.mask.tch[i]]) : 1.0f;
@@ -465,6 +472,15 @@ __global__ void __launch_bounds__(kThreads) mixcdf_bwd_pipe_kernel(const BwdPara
     for (int i = tid; i < C; i += kThreads) s_jmap[i] = -1;
     if (p.gcol)
         for (int i = tid; i < L; i += kThreads) s_col[i] = 0.f;
+    // two planes [L][4] (conditioner columns 0..3 | 4..7): the eight n-slices of a position read eight consecutive rows of a
+    // plane per step = 32 different banks
+    if constexpr (PROJ)
+        for (int i = tid; i < L * 8; i += kThreads) {
+            const int n = i >> 3, j = i & 7;
+            s_pw[(j >> 2) * (L * 4) + n * 4 + (j & 3)] = p.proj_w[n * C + cb + j];
+        }
+    // dL/dW entries of this thread: row n = tid < L, the 8 conditioner columns
+    float accw[PROJ ? 2 : 1][4] = {};
     if (tid == 0) {
         for (int b = 0; b < nbuf; ++b) tc::mbar_init(&s_full[b], 1);
         tc::mbar_fence_init();
@@ -575,8 +591,64 @@ __global__ void __launch_bounds__(kThreads) mixcdf_bwd_pipe_kernel(const BwdPara
         // ---- this tile's stores, next load, column sums ---------------------------------------------------------------
         tc::fence_proxy_async_smem();
         __syncthreads();
+        if constexpr (PROJ) {
+            // The network IS a per-position Linear on z (training path of MixtureCDFCoupling with the mask folded into the
+            // weight): its backward products consume the gradient records right here, from shared memory, in fp32 -
+            //   dL/dz[pos, cond] += sum_n G[pos, n] W[n, cond]        thread (pos = tid / 8, slice s = tid % 8 of the n range),
+            //                                                          8 conditioner columns per thread, reduced over the 8 slices
+            //   dL/dW[n, cond]   += sum_pos G[pos, n] z[pos, cond]     lane-owned entries, accumulated in registers over all tiles
+            // - so dL/dnn_out never has to leave the chip (the two GEMMs re-read 0.87 GB each per block at the LM shape).
+            {
+                const int pp = tid >> 3, sl = tid & 7;
+                float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                if (pp < rows) {
+                    const float* grow = s_par + (size_t)pp * L;
+                    const float* w1p = s_pw + L * 4;
+#pragma unroll 2
+                    for (int n = sl; n < L; n += 8) {      // slice sl: rows sl, sl + 8, ...
+                        const float g = grow[n];
+                        const float4 w0 = *reinterpret_cast<const float4*>(s_pw + n * 4), w1 = *reinterpret_cast<const float4*>(w1p + n * 4);
+                        a[0] = fmaf(g, w0.x, a[0]); a[1] = fmaf(g, w0.y, a[1]); a[2] = fmaf(g, w0.z, a[2]); a[3] = fmaf(g, w0.w, a[3]);
+                        a[4] = fmaf(g, w1.x, a[4]); a[5] = fmaf(g, w1.y, a[5]); a[6] = fmaf(g, w1.z, a[6]); a[7] = fmaf(g, w1.w, a[7]);
+                    }
+                }
+#pragma unroll
+                for (int d = 1; d < 8; d <<= 1) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) a[j] += __shfl_xor_sync(0xffffffffu, a[j], d);
+                }
+                if (sl == 0 && pp < rows) {
+                    float4* dst = reinterpret_cast<float4*>(s_g + pp * C + cb);
+                    float4 v0 = dst[0], v1 = dst[1];
+                    v0.x += a[0]; v0.y += a[1]; v0.z += a[2]; v0.w += a[3];
+                    v1.x += a[4]; v1.y += a[5]; v1.z += a[6]; v1.w += a[7];
+                    dst[0] = v0; dst[1] = v1;
+                }
+            }
+            if (p.gproj_w && tid < L) {      // thread n < L owns row n of dL/dW (8 conditioner columns) over all of its tiles
+                const float* zc = s_z + cb;
+#pragma unroll 4
+                for (int r = 0; r < rows; ++r) {
+                    const float g = s_par[r * L + tid];
+                    const float4 z0 = *reinterpret_cast<const float4*>(zc + r * C), z1 = *reinterpret_cast<const float4*>(zc + r * C + 4);
+                    accw[0][0] = fmaf(g, z0.x, accw[0][0]); accw[0][1] = fmaf(g, z0.y, accw[0][1]);
+                    accw[0][2] = fmaf(g, z0.z, accw[0][2]); accw[0][3] = fmaf(g, z0.w, accw[0][3]);
+                    accw[1][0] = fmaf(g, z1.x, accw[1][0]); accw[1][1] = fmaf(g, z1.y, accw[1][1]);
+                    accw[1][2] = fmaf(g, z1.z, accw[1][2]); accw[1][3] = fmaf(g, z1.w, accw[1][3]);
+                }
+            }
+            if (p.gcol) {
+                for (int c = tid; c < L; c += kThreads) {
+                    float a = 0.f;
+                    for (int r = 0; r < rows; ++r) a += s_par[r * L + c];
+                    s_col[c] += a;
+                }
+            }
+            tc::fence_proxy_async_smem();
+            __syncthreads();
+        }
         if (tid == 0) {
-            bulk_store_rows(p.gnn + pos0 * (long long)L, s_par, (uint32_t)rows * (uint32_t)L * 4u);
+            if (p.gnn) bulk_store_rows(p.gnn + pos0 * (long long)L, s_par, (uint32_t)rows * (uint32_t)L * 4u);
             bulk_store_rows(p.gz + pos0 * C, s_g, (uint32_t)rows * (uint32_t)C * 4u);
             tc::tma_store_commit();
             // the load of tile k + ahead goes into the buffer of tile k - nbuf + ahead: for nbuf > 1 an OLDER tile's, whose
@@ -587,7 +659,7 @@ __global__ void __launch_bounds__(kThreads) mixcdf_bwd_pipe_kernel(const BwdPara
                 issue_load(k + ahead);
             }
         }
-        if (p.gcol) {
+        if (p.gcol && !PROJ) {
             // d/dbias of the network's final Linear = column sums of dL/dnn_out: column tid of the tile's rows, read while
             // the TMA engine reads the same rows for the store (needs nbuf > 1: a single buffer is re-filled right away)
             for (int c = tid; c < L; c += kThreads) {
@@ -607,29 +679,46 @@ __global__ void __launch_bounds__(kThreads) mixcdf_bwd_pipe_kernel(const BwdPara
     if (p.gcol)
         for (int i = tid; i < L; i += kThreads)
             if (s_col[i] != 0.f) atomicAdd(p.gcol + i, s_col[i]);
+    if (PROJ && p.gproj_w && tid < L) {
+        float* dst = p.gproj_w + (size_t)tid * C + cb;
+#pragma unroll
+        for (int it = 0; it < (PROJ ? 2 : 1); ++it)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (accw[it][j] != 0.f) atomicAdd(dst + 4 * it + j, accw[it][j]);
+    }
     if (tid == 0) tc::tma_store_wait_read<0>();      // shared memory must outlive the engine's reads of it
 }
 
-template <int KT>
-int launch_bwd_pipe(BwdParams p, int L, int C, int Ct, int K, cudaStream_t stream) {
+template <int KT, bool PROJ>
+int launch_bwd_pipe_t(BwdParams p, int L, int C, int Ct, int K, cudaStream_t stream) {
     static const int want = getenv("CNF_B200_MIXCDF_BWD_NBUF") ? atoi(getenv("CNF_B200_MIXCDF_BWD_NBUF")) : 2;      // tuning knob
     int nbuf = want < 1 ? 1 : (want > 4 ? 4 : want);
     if (p.gcol != nullptr && nbuf < 2) nbuf = 2;      // the fused column sums read a tile after its store was issued
     const size_t buf = ((size_t)p.TP * L + 2 * (size_t)p.TP * C) * sizeof(float);
-    const size_t tables = (2 * (size_t)Ct + 3 * (size_t)Ct * K + (size_t)C + (size_t)L) * sizeof(float);
+    const size_t tables = (2 * (size_t)Ct + 3 * (size_t)Ct * K + (size_t)C + (size_t)((L + 3) & ~3) + (p.proj_w ? 8 * (size_t)L : 0)) * sizeof(float);
     while (nbuf > 2 && nbuf * buf + tables > 200 * 1024) --nbuf;
     if (nbuf * buf + tables > 200 * 1024) return -1;      // caller falls back to the tile kernel
     p.nbuf = nbuf;
     const size_t smem = nbuf * buf + tables;
-    CNF_CUDA(cudaFuncSetAttribute(mixcdf_bwd_pipe_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CNF_CUDA(cudaFuncSetAttribute(mixcdf_bwd_pipe_kernel<KT, PROJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
-    CNF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mixcdf_bwd_pipe_kernel<KT>, kThreads, smem));
+    CNF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mixcdf_bwd_pipe_kernel<KT, PROJ>, kThreads, smem));
     if (per_sm < 1) per_sm = 1;
     const long long ntiles = (p.P + p.TP - 1) / p.TP;
     long long grid = (long long)per_sm * sm_count();
     if (grid > ntiles) grid = ntiles;
-    mixcdf_bwd_pipe_kernel<KT><<<(unsigned)grid, kThreads, smem, stream>>>(p);
+    mixcdf_bwd_pipe_kernel<KT, PROJ><<<(unsigned)grid, kThreads, smem, stream>>>(p);
     return launch_status("mixcdf_bwd_pipe_kernel");
+}
+
+template <int KT>
+int launch_bwd_pipe(const BwdParams& p, int L, int C, int Ct, int K, cudaStream_t stream) {
+    if constexpr (KT > 0) {
+        if (p.proj_w != nullptr) return launch_bwd_pipe_t<KT, true>(p, L, C, Ct, K, stream);
+    }
+    if (p.proj_w != nullptr) return fail(CNF_ERR_UNSUPPORTED, "proj_weight: K must be 4, 8 or 16");
+    return launch_bwd_pipe_t<KT, false>(p, L, C, Ct, K, stream);
 }
 
 size_t bwd_smem(int TP, int L, int C, int Ct, int K) {
@@ -663,7 +752,7 @@ extern "C" int cnf_mixcdf_bwd(const cnf_mixcdf_bwd_args* a, cnf_stream_t stream_
     if (rc != CNF_OK) return rc;
     const long long P = a->B * a->S;
     if (P == 0) return CNF_OK;
-    CNF_REQUIRE(a->z && a->nn_out && a->grad_z_out && a->grad_z && a->grad_nn_out, "z / nn_out / grad_z_out / grad_z / grad_nn_out is NULL");
+    CNF_REQUIRE(a->z && a->nn_out && a->grad_z_out && a->grad_z, "z / nn_out / grad_z_out / grad_z is NULL");
     const size_t nz = (size_t)P * a->C;
     p.PN = 2 + 3 * a->K;
     if (p.mask.n_t == 0) {   // nothing transformed: identity (times pad), no parameter gradient
@@ -705,6 +794,19 @@ extern "C" int cnf_mixcdf_bwd(const cnf_mixcdf_bwd_args* a, cnf_stream_t stream_
     CNF_REQUIRE((reinterpret_cast<uintptr_t>(a->grad_nn_out) & 7) == 0, "grad_nn_out must be 8-byte aligned");
     CNF_SUPPORTED((long long)TP * a->C * p.PN < (1 << 21), "tile too large for the index arithmetic");
     CNF_SUPPORTED(a->grad_nn_colsum == nullptr || p.compact, "grad_nn_colsum needs the compact layout (nn_compact = 1)");
+    const bool want_proj = a->proj_weight != nullptr;
+    if (want_proj) {
+        CNF_SUPPORTED(p.bulk && TP * Ct <= kThreads && (TP * L) % 4 == 0 && a->C == 16 && Ct == 8 && p.mask.contiguous &&
+                          (p.mask.c0 == 0 || p.mask.c0 == 8) && p.mask.s_period == 0 && L <= kThreads && TP * 8 <= kThreads,
+                      "proj_weight: the fused projection backward is compiled for the compact layout with C = 16 and 8 contiguous "
+                      "transformed channels at either end (channel mask only)");
+        CNF_REQUIRE((reinterpret_cast<uintptr_t>(a->proj_weight) & 15) == 0, "proj_weight must be 16-byte aligned");
+        p.proj_w = a->proj_weight;
+        p.gproj_w = a->grad_proj_weight;
+    } else {
+        CNF_REQUIRE(a->grad_proj_weight == nullptr, "grad_proj_weight needs proj_weight");
+        CNF_REQUIRE(a->grad_nn_out != nullptr, "grad_nn_out is NULL");
+    }
     if (p.bulk && TP * Ct <= kThreads && (TP * L) % 4 == 0) {
         p.gcol = a->grad_nn_colsum;
         int prc;
@@ -715,6 +817,7 @@ extern "C" int cnf_mixcdf_bwd(const cnf_mixcdf_bwd_args* a, cnf_stream_t stream_
             default: prc = launch_bwd_pipe<0>(p, L, a->C, Ct, a->K, stream); break;
         }
         if (prc != -1) return prc;
+        CNF_SUPPORTED(!want_proj, "proj_weight: tile does not fit shared memory");
         p.gcol = nullptr;
     }
     const size_t smem = bwd_smem(TP, L, a->C, Ct, a->K);

@@ -7,6 +7,8 @@ hand-written backward kernels.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import ops
@@ -74,6 +76,14 @@ class _ProjMixCDF(torch.autograd.Function):
                                      reg_max=cfg["reg_max"], reg_factor=cfg["reg_factor"], training=cfg["training"],
                                      want_reg=True, compact=True)
         ctx.cfg, ctx.precision, ctx.has_bias = cfg, precision, bias is not None
+        # the network is one per-position Linear on z itself: its backward products can run inside the transform's backward
+        # kernel (cnf_mixcdf_bwd proj_weight, compiled for the LM layout: 16 channels, 8 contiguous transformed ones)
+        mc = cfg["mask_c"]
+        tch = [c for c, m in enumerate(mc)] if mc is None else [c for c, m in enumerate(mc) if float(m) == 0.0]
+        ctx.fuse_linear_bwd = bool(
+            cfg.get("linear_on_z", False) and FUSE_LINEAR_BACKWARD and feats.data_ptr() == z.data_ptr() and z.shape[-1] == 16
+            and feats.shape[-1] == 16 and len(tch) == 8 and tch in (list(range(0, 8)), list(range(8, 16))) and cfg["K"] in (4, 8, 16)
+            and weight.is_contiguous())
         ctx.save_for_backward(z, nn_out, sf, msf, pad, z_out, feats, weight, *(split or ()))
         ctx.mark_non_differentiable(reg)
         return z_out, ldj, reg
@@ -86,6 +96,12 @@ class _ProjMixCDF(torch.autograd.Function):
         split = tuple(ctx.saved_tensors[8:10]) if ctx.has_split else None
         need = ctx.needs_input_grad
         want_col = ctx.has_bias and need[3]
+        if ctx.fuse_linear_bwd:
+            gz, _, gsf, gmsf, gcol, gw = ops_bwd.mixcdf_backward(ctx.cfg, z, nn_out, sf, msf, pad, z_out, g_z, g_ldj, need,
+                                                                  want_colsum=want_col, proj_weight=weight,
+                                                                  want_proj_weight_grad=need[2])
+            # (the gradient with respect to `feats` - the same tensor as z - is already inside gz)
+            return gz, None, gw, gcol, gsf, gmsf, None, None, None
         out = ops_bwd.mixcdf_backward(ctx.cfg, z, nn_out, sf, msf, pad, z_out, g_z, g_ldj, need, want_colsum=want_col)
         gz, gnn, gsf, gmsf = out[:4]
         gx, gw, _ = ops.linear_bwd(feats, weight, gnn.view(-1, gnn.shape[-1]), need_x=need[1], need_weight=need[2], need_bias=False,
@@ -93,12 +109,17 @@ class _ProjMixCDF(torch.autograd.Function):
         return gz, gx, gw, (out[4] if want_col else None), gsf, gmsf, None, None, None
 
 
+FUSE_LINEAR_BACKWARD = os.environ.get("CNF_B200_NO_FUSED_LINEAR_BWD", "0") in ("", "0")      # A/B switch
+
+
 def proj_mixcdf(z, feats, weight, bias, num_mixtures, scaling_factor=None, mixture_scaling_factor=None, *, mask_c=None,
-                pad=None, reg_max=-1.0, reg_factor=1.0, training=False, precision="3xtf32"):
+                pad=None, reg_max=-1.0, reg_factor=1.0, training=False, precision="3xtf32", linear_on_z=False):
     """``mixcdf(z, feats @ weight.T + bias, ..., compact=True)`` (forward direction) with ``weight`` / ``bias`` holding the
-    transformed channels' rows only; ``feats`` [B*S, H].  -> (z_out, ldj [B], reg_ldj [B])."""
+    transformed channels' rows only; ``feats`` [B*S, H].  -> (z_out, ldj [B], reg_ldj [B]).  ``linear_on_z``: ``feats`` is z
+    itself and ``weight`` already carries the coupling mask (zero columns for the transformed inputs) - the Linear's backward
+    then runs inside the transform's backward kernel where that is compiled."""
     cfg = dict(K=int(num_mixtures), mask_c=mask_c, mask_s=None, reverse=False, reg_max=float(reg_max),
-               reg_factor=float(reg_factor), training=bool(training), prebounded=False, compact=True)
+               reg_factor=float(reg_factor), training=bool(training), prebounded=False, compact=True, linear_on_z=bool(linear_on_z))
     return _ProjMixCDF.apply(z, feats, weight, bias, scaling_factor, mixture_scaling_factor, pad, cfg, precision)
 
 

@@ -171,7 +171,7 @@ class MixtureCDFCoupling(CouplingLayer):
                 z_out, ldj, reg = CF.proj_mixcdf(z, compact[0], compact[1], compact[2], self.num_mixtures, self.scaling_factor,
                                                  self.mixture_scaling_factor, mask_c=mask_c, pad=channel_padding_mask,
                                                  reg_max=self.regularizer_max, reg_factor=self.regularizer_factor,
-                                                 training=self.training, precision=self.projection_precision)
+                                                 training=self.training, precision=self.projection_precision, linear_on_z=True)
                 return z_out, ldj, {"ldj": ldj, "regularizer_ldj": reg}
             x_in = masked_input if masked_input is not None else z * self._prepare_mask(self.mask, z)
         else:

@@ -18,9 +18,13 @@ def _grad(t, like):
     return _f32(t, "grad")
 
 
-def mixcdf_backward(cfg, z, nn_out, sf, msf, pad, z_out, g_z, g_ldj, needs, want_colsum=False):
+def mixcdf_backward(cfg, z, nn_out, sf, msf, pad, z_out, g_z, g_ldj, needs, want_colsum=False, proj_weight=None,
+                    want_proj_weight_grad=False):
     """-> (grad_z, grad_nn_out, grad_sf | None, grad_msf | None[, column sums of grad_nn_out]).  ``want_colsum`` (compact layout
-    only, ABI v5): the bias gradient of the network's final Linear, summed by the backward kernel itself."""
+    only, ABI v5): the bias gradient of the network's final Linear, summed by the backward kernel itself.  ``proj_weight``
+    [Ct*(2+3K), C] (ABI v5, see ``cnf_mixcdf_bwd_args.proj_weight``): the network is one per-position Linear on z - the kernel
+    adds its input gradient into grad_z, returns its weight gradient (``want_proj_weight_grad``) as a sixth value and does
+    NOT write grad_nn_out (returned as None)."""
     if cfg["reverse"]:
         raise NotImplementedError("categoricalnf_b200: differentiating the INVERSE mixture coupling is not supported "
                                   "(training differentiates the density direction only)")
@@ -38,7 +42,7 @@ def mixcdf_backward(cfg, z, nn_out, sf, msf, pad, z_out, g_z, g_ldj, needs, want
     gz_out = _grad(g_z, z)
     gl = _opt_f32(g_ldj, "grad_ldj", (B,))
     gz = torch.empty_like(z)
-    gnn = torch.empty_like(nn_out)
+    gnn = torch.empty_like(nn_out) if proj_weight is None else None
     pre = bool(cfg.get("prebounded", False))
     gsf = torch.zeros(Cc, dtype=torch.float32, device=z.device) if (sf is not None and not pre) else None
     gmsf = torch.zeros(Cc, K, dtype=torch.float32, device=z.device) if (msf is not None and not pre) else None
@@ -54,7 +58,18 @@ def mixcdf_backward(cfg, z, nn_out, sf, msf, pad, z_out, g_z, g_ldj, needs, want
             raise ValueError("mixcdf_backward: column sums need the compact layout")
         gcol = torch.zeros(nn_out.shape[-1], dtype=torch.float32, device=z.device)
         a.grad_nn_colsum = _ptr(gcol)
-    _call("cnf_mixcdf_bwd", a, z, (keep, z, nn_out, pad, sf, msf, gz_out, gl))
+    gpw = None
+    if proj_weight is not None:
+        if not compact:
+            raise ValueError("mixcdf_backward: proj_weight needs the compact layout")
+        proj_weight = _f32(proj_weight, "proj_weight", (nn_out.shape[-1], Cc))
+        a.proj_weight = _ptr(proj_weight)
+        if want_proj_weight_grad:
+            gpw = torch.zeros_like(proj_weight)
+            a.grad_proj_weight = _ptr(gpw)
+    _call("cnf_mixcdf_bwd", a, z, (keep, z, nn_out, pad, sf, msf, gz_out, gl, proj_weight))
+    if proj_weight is not None:
+        return gz, gnn, gsf, gmsf, gcol, gpw
     if want_colsum:
         return gz, gnn, gsf, gmsf, gcol
     return gz, gnn, gsf, gmsf

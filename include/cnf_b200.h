@@ -587,7 +587,7 @@ typedef struct {
     const float* grad_z_out;             /* [B,S,C]                                   */
     const float* grad_ldj;               /* [B] or NULL                               */
     float* grad_z;                       /* [B,S,C] direct path only (not through nn) */
-    float* grad_nn_out;                  /* [B,S,C*(2+3K)], zeros for conditioners    */
+    float* grad_nn_out;                  /* [B,S,C*(2+3K)], zeros for conditioners (NULL allowed with proj_weight) */
     float* grad_scaling_factor;          /* [C] += or NULL                            */
     float* grad_mixture_scaling_factor;  /* [C,K] += or NULL                          */
     /* ABI v4: 1 = nn_out AND grad_nn_out are compact, [B,S,Ct*(2+3K)] (see cnf_mixcdf_args.nn_compact): no zeros are
@@ -598,6 +598,16 @@ typedef struct {
      * compact-layout kernel sums the columns of every tile while its rows are still in shared memory; otherwise a pass
      * over grad_nn_out follows the kernel.  NULL: not wanted.                                                          */
     float* grad_nn_colsum;
+    /* ABI v5 (needs nn_compact, C = 16 with 8 contiguous transformed channels at either end, channel mask only): the
+     * coupling network is ONE per-position nn.Linear applied to the (masked) block input z, nn_out = (z * mask) W^T + b,
+     * and proj_weight [Ct*(2+3K), C] holds the weight rows of the transformed channels' records.  The kernel then also
+     * evaluates that Linear's backward from the gradient tile in shared memory, in fp32:
+     *   grad_z[pos, conditioner channels] += grad_nn_out[pos, :] . proj_weight[:, conditioner channels]
+     *   grad_proj_weight[n, conditioner channels] += sum_pos grad_nn_out[pos, n] z[pos, conditioner channels]   (may be NULL)
+     * (columns of masked-out inputs receive nothing: the reference's `z * mask` gives them a zero gradient).  grad_nn_out
+     * may then be NULL: the [B,S,Ct*(2+3K)] gradient never leaves the chip.                                               */
+    const float* proj_weight;
+    float* grad_proj_weight;
 } cnf_mixcdf_bwd_args;
 
 /* forward direction of cnf_mixcdf_fwd (training differentiates the density direction only) */
