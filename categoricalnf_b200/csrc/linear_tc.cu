@@ -410,9 +410,10 @@ int launch_gemm(const GemmDesc& g, const char* who, cudaStream_t stream) {
     if (g.block_n >= 32 && g.block_n <= 256 && g.block_n % 32 == 0) {
         p.block_n = g.block_n;
         p.n_tiles = (g.Ng + g.block_n - 1) / g.block_n;
-    } else if (!g.split_k && !g.a_mn && !g.b_mn && !auto_block_n_off() && p.m_tiles * p.n_tiles <= 2 * sm_count()) {
-        // Forward products (both operands K-major: the shapes the model below was fitted on; the MN-major backward products
-        // keep the widest tile - 327 vs 331 ms per GraphCNF training step at 512 molecules with / without).
+    } else if (!g.split_k && !auto_block_n_off() && p.m_tiles * p.n_tiles <= ((g.a_mn || g.b_mn) ? 1 : 2) * sm_count()) {
+        // (The model below was fitted on forward products, both operands K-major; the MN-major backward products use it
+        // only below ONE wave, where SMs would otherwise idle: between one and two waves it cost them 1 %, 331 vs 327 ms per
+        // GraphCNF training step at 512 molecules.)
         // Few tiles - less than two waves of the widest N tile; larger problems keep it (measured 0.91 of the TF32 peak
         // there) - e.g. the projections of a 64-molecule shard, M = 2432 is 19 row tiles: the widest N tile leaves most SMs
         // idle and - at 96 KB per 3xTF32 stage - runs on a 2-deep ring.  Choose the N tile that minimises
