@@ -625,19 +625,23 @@ __global__ void __launch_bounds__(kThreads, PROJ ? CNF_BWD_PROJ_MIN_CTAS : 1) mi
                     dst[0] = v0; dst[1] = v1;
                 }
             }
+            const bool col_here = p.gcol != nullptr && p.gproj_w != nullptr;      // column sums ride on the dL/dW loop's reads
             if (p.gproj_w && tid < L) {      // thread n < L owns row n of dL/dW (8 conditioner columns) over all of its tiles
                 const float* zc = s_z + cb;
+                float csum = 0.f;
 #pragma unroll 4
                 for (int r = 0; r < rows; ++r) {
                     const float g = s_par[r * L + tid];
+                    csum += g;
                     const float4 z0 = *reinterpret_cast<const float4*>(zc + r * C), z1 = *reinterpret_cast<const float4*>(zc + r * C + 4);
                     accw[0][0] = fmaf(g, z0.x, accw[0][0]); accw[0][1] = fmaf(g, z0.y, accw[0][1]);
                     accw[0][2] = fmaf(g, z0.z, accw[0][2]); accw[0][3] = fmaf(g, z0.w, accw[0][3]);
                     accw[1][0] = fmaf(g, z1.x, accw[1][0]); accw[1][1] = fmaf(g, z1.y, accw[1][1]);
                     accw[1][2] = fmaf(g, z1.z, accw[1][2]); accw[1][3] = fmaf(g, z1.w, accw[1][3]);
                 }
+                if (col_here) s_col[tid] += csum;
             }
-            if (p.gcol) {
+            if (p.gcol && !col_here) {
                 for (int c = tid; c < L; c += kThreads) {
                     float a = 0.f;
                     for (int r = 0; r < rows; ++r) a += s_par[r * L + c];
