@@ -328,15 +328,25 @@ def test_mixcdf_compact_layout_matches_full(B, S, C, K, flip):
     grads_close(res[True][3], res[False][3], "dL/dmsf", rtol=1e-4, atol_rel=1e-5)
 
 
-def test_compact_projection_in_training_matches_two_step_path():
+@pytest.mark.parametrize("padded,flip,fused", [(False, False, True), (True, False, True), (True, True, True), (True, False, False)])
+def test_compact_projection_in_training_matches_two_step_path(padded, flip, fused):
     """MixtureCDFCoupling in training mode with a network that ends in a Linear: the compact path (only the transformed
     channels' weight rows are multiplied) gives the same outputs and the same gradients - incl. exact zeros for the skipped
     weight rows - as the full network output through the two-step path."""
     import workload as W
+    from categoricalnf_b200 import functional as CFm
     from categoricalnf_b200.layers.flows import MixtureCDFCoupling
     torch.manual_seed(0)
     D, K, B, S = 16, 8, 7, 50
     mask = torch.cat([torch.ones(D // 2), torch.zeros(D - D // 2)]).view(1, D)
+    if flip:
+        mask = 1 - mask
+    pad = None
+    if padded:
+        lens = torch.randint(S // 2, S + 1, (B,))
+        pad = (torch.arange(S)[None, :] < lens[:, None]).float().unsqueeze(-1).cuda()
+    # fused = True: the per-position Linear's backward runs inside the transform's backward kernel (ABI v5 proj_weight)
+    CFm.FUSE_LINEAR_BACKWARD = fused
     layer = MixtureCDFCoupling(c_in=D, mask=mask, model_func=lambda c_out: W.StandInNet(D, c_out), num_mixtures=K).cuda().train()
     with torch.no_grad():
         layer.scaling_factor.normal_(0, 0.3)
@@ -348,12 +358,14 @@ def test_compact_projection_in_training_matches_two_step_path():
         layer.compact_projection_in_training = compact
         layer.zero_grad()
         zin = z.clone().requires_grad_(True)
-        zo, ldj, _ = layer(zin)
+        zo, ldj, _ = layer(zin, channel_padding_mask=pad)
         ((zo * wz).sum() + (ldj * wl).sum()).backward()
         out[compact] = (zo.detach(), ldj.detach(), zin.grad, layer.nn.lin.weight.grad.clone(), layer.nn.lin.bias.grad.clone(),
                         layer.scaling_factor.grad.clone(), layer.mixture_scaling_factor.grad.clone())
+    CFm.FUSE_LINEAR_BACKWARD = True
     names = ["z", "ldj", "dL/dz", "dL/dW", "dL/db", "dL/dsf", "dL/dmsf"]
     for a, b, n in zip(out[True], out[False], names):
         grads_close(a, b, n, rtol=2e-5, atol_rel=2e-6)
     pn = 2 + 3 * K
-    assert float(out[True][3][: (D // 2) * pn].abs().sum()) == 0.0        # conditioner records: no gradient, as in the reference
+    cond_rows = slice((D // 2) * pn, None) if flip else slice(0, (D // 2) * pn)
+    assert float(out[True][3][cond_rows].abs().sum()) == 0.0        # conditioner records: no gradient, as in the reference
