@@ -16,6 +16,15 @@
 // written with coalesced 8-byte stores.  Scaling-factor gradients are reduced in shared memory and leave
 // with one atomic per (CTA, parameter).  Elements outside the fp32-safe range (same test as the forward
 // kernels) are differentiated in float64.
+//
+// Two kernels share the element function mix_backward_elem:
+//   mixcdf_bwd_kernel       the tile kernel described above (any layout / mask)
+//   mixcdf_bwd_pipe_kernel  compact layout (nn_out / dL/dnn_out hold the transformed channels' records only): persistent
+//                           CTAs, tiles moved by cp.async.bulk into two shared-memory buffers and out by bulk stores,
+//                           per-CTA tables and atomics, optional column sums of dL/dnn_out (the final Linear's bias
+//                           gradient) and - PROJ = true, the network is one per-position Linear on z - that Linear's
+//                           grad_x / grad_W products from the gradient tile in shared memory, so that dL/dnn_out never
+//                           reaches HBM (cnf_mixcdf_bwd_args.grad_nn_colsum / proj_weight, ABI v5).
 #include <stdlib.h>
 
 #include "cnf_common.cuh"
