@@ -367,7 +367,7 @@ def run_molecule_training(c: Ctx, model, ops):
     model.train()
     params = [p for p in model.parameters() if p.requires_grad]
     n_params = sum(p.numel() for p in params)
-    use_graph = B <= G.MOL.get("graph_replay_max_train", 256)
+    use_graph = B <= G.MOL.get("graph_replay_max_train", 512)
     red = GradientReducer(params, bucket_bytes=32 << 20, profile=True, hooks=not use_graph)
     opt = torch.optim.Adam(params, lr=1e-5, fused=True)
     state = {}
