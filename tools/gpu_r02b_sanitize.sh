@@ -7,7 +7,7 @@ out=gpurun_out; mkdir -p $out
 for tool in memcheck racecheck; do
     start=$(date +%s)
     timeout ${SAN_TIMEOUT:-500} compute-sanitizer --tool $tool --print-limit 20 --error-exitcode 99 \
-        python -m pytest tests/test_gpu_backward.py -m gpu -q -x -k "categ_encode_backward or invconv_backward or actnorm_backward or training_step" -p no:cacheprovider \
+        python -m pytest tests/test_gpu_backward.py -m gpu -q -x -k "categ_encode_backward or invconv_backward or actnorm_backward or training_step or compact or mixcdf_backward" -p no:cacheprovider \
         > $out/r02b_sanitizer_$tool.log 2>&1
     rc=$?
     echo "== $tool rc=$rc $(( $(date +%s) - start )) s: $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' $out/r02b_sanitizer_$tool.log | tail -1) | $(grep -E 'passed|failed' $out/r02b_sanitizer_$tool.log | tail -1)"
