@@ -290,8 +290,11 @@ __global__ void __launch_bounds__(kThreadsT16) categ_encode_bwd_tpt16_kernel(con
         if (in) {
             pd = p.pad ? p.pad[tk] : 1.0f;
             if (pd != 0.0f) {
-                t = (int)p.tokens[tk];
-                gl = (p.gldj ? p.gldj[tk / p.S] : 0.f) * pd;
+                const long long tok = p.tokens[tk];
+                if (tok >= 0 && tok < V) {      // (the forward kernel flags out-of-range tokens; here they get no gradient)
+                    t = (int)tok;
+                    gl = (p.gldj ? p.gldj[tk / p.S] : 0.f) * pd;
+                }
             }
         }
 #pragma unroll
