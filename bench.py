@@ -513,8 +513,10 @@ def lm_training_record(args, model, prm, dev, rank, world, dist, tokens):
                 "gpu_launches_per_step": launches, "loss_bits_per_dim": float(state["loss"]) * 1.4426950408889634,
                 "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30, "dtype": "f32 (projections 3xTF32)",
                 "mode": "eager; stand-in Linear coupling nets with the compact [B,S,Ct(2+3K)] projection (only the transformed "
-                        "channels' weight rows), mixture / ActNorm / 1x1 conv / encode backward kernels, gradients reduced in "
-                        "%d flat bucket(s) on a communication stream, fused Adam" % len(red.buckets),
+                        "channels' weight rows, coupling mask folded into the weight block); backward: the projection's grad_x / "
+                        "grad_W / grad_b are formed inside the mixture transform's backward kernel from the gradient tile in "
+                        "shared memory (dL/dnn_out is never stored), ActNorm / 1x1 conv / encode backward kernels; gradients "
+                        "reduced in %d flat bucket(s) on a communication stream, fused Adam" % len(red.buckets),
                 "collective": {"kind": "NCCL all-reduce (sum) of the flat gradient buckets, overlapped with backward",
                                "bytes_per_step": nbytes / steps if world > 1 else 0,
                                "comm_stream_ms_per_step": comm_ms / steps if world > 1 else 0.0, "bus_GBps": bus}}
